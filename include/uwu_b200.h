@@ -1,0 +1,141 @@
+/*
+ * uwu_b200.h — C ABI of libuwu_b200.so: the sm_100a kernels behind the duwu diffusion training step.
+ *
+ * Conventions
+ *   - plain C types only; device pointers are `void*` / typed pointers to DEVICE memory,
+ *   - every entry point is asynchronous on the `stream` argument (a cudaStream_t passed as void*),
+ *     never synchronises, never allocates, never keeps a pointer after returning,
+ *   - return value: 0 = OK, <0 = invalid argument / unsupported shape, >0 = cudaError_t;
+ *     the message is available through uwu_last_error() (thread-local),
+ *   - there is NO CPU fallback: an unsupported shape is an error, a missing GPU is an error.
+ *
+ * Each function cites the reference call site it replaces (paths relative to /root/reference).
+ */
+#ifndef UWU_B200_H
+#define UWU_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UWU_OK 0
+#define UWU_ERR_INVALID (-1)
+#define UWU_ERR_UNSUPPORTED (-2)
+
+/* dtype codes */
+#define UWU_F32 0
+#define UWU_BF16 1
+
+/* target / prediction types (src/duwu/loss/diffusion.py:84-98) */
+#define UWU_TARGET_EPSILON 0
+#define UWU_TARGET_V 1
+#define UWU_TARGET_SAMPLE 2
+#define UWU_TARGET_RF 3
+
+/* loss-weight flags (src/duwu/loss/diffusion.py:141-167) */
+#define UWU_WEIGHT_MIN_SNR 1
+#define UWU_WEIGHT_DEBIASED 2
+
+const char* uwu_last_error(void);
+int uwu_version(void);
+/* number of kernels launched by this library in this process (bench.py's gpu_launches) */
+int64_t uwu_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * GEMM / implicit-GEMM convolution (tcgen05 + TMEM + TMA)
+ *   replaces torch.nn.functional.linear / conv2d under diffusers' UNet2DConditionModel, i.e. the
+ *   `unet(noisy_latent, timesteps, **unet_kwargs)` call at src/duwu/loss/diffusion.py:172-176, and the
+ *   LyCORIS `F.linear(x, W + dW)` forward patched in at src/duwu/trainer/trainer.py:152-154.
+ * ------------------------------------------------------------------------------------------------ */
+#define UWU_A_ROW 0  /* A[M,K], K contiguous                                  */
+#define UWU_A_COL 1  /* A stored [K,M], M contiguous (reduction over rows)    */
+#define UWU_A_CONV 2 /* A = NHWC activation [n_img_buf,H,W,Cin] + tap table   */
+#define UWU_B_NK 0   /* B[N,K], K contiguous  (y = x W^T)                     */
+#define UWU_B_KN 1   /* B stored [K,N], N contiguous                          */
+
+typedef struct uwu_gemm_desc {
+    const void* a;  /* bf16 */
+    const void* a2; /* bf16, second channel-concatenated conv source or NULL */
+    const void* b;  /* bf16 */
+    int64_t M, N, K;
+    int32_t a_layout, b_layout;
+    int64_t lda, ldb; /* leading dimensions in elements (ignored for UWU_A_CONV) */
+    /* conv geometry (UWU_A_CONV): output pixel m = ((n*H + h)*W + w) reads input pixel
+       (n + tap_dn[t], h + tap_dh[t], w + tap_dw[t]) for tap t; out-of-range h/w read zeros.
+       K index = t*(Cin1+Cin2) + c. */
+    int32_t n_img_buf, H, W, Cin1, Cin2, ntaps;
+    int32_t tap_dn[9], tap_dh[9], tap_dw[9];
+    /* epilogue: out[m,n] = alpha*acc + bias[n] + bias_rows[m/rows_per_bias, n] + residual[m,n] */
+    void* out;
+    void* out2; /* columns >= n_split are written to out2[m, n - n_split] (or NULL) */
+    int64_t ldo, ldo2;
+    int32_t n_split;
+    int32_t out_dtype; /* UWU_BF16 or UWU_F32 */
+    const float* bias;
+    const float* bias_rows;
+    int32_t rows_per_bias;
+    const void* residual; /* bf16 [M, ldr] or NULL */
+    int64_t ldr;
+    float alpha;
+    int32_t accumulate; /* fp32 output only: out += result */
+    int32_t block_n;    /* 0 = choose */
+    /* diagnostics: override shared-memory descriptor fields (0 = default) */
+    int32_t dbg_a_lbo, dbg_a_sbo, dbg_a_kadv, dbg_b_lbo, dbg_b_sbo, dbg_b_kadv;
+} uwu_gemm_desc;
+
+int uwu_gemm(const uwu_gemm_desc* desc, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Fused noising: timestep sampling (or injected), sigma gather, x_t, target, loss weights, t-embedding.
+ *   replaces DiffusionLoss.get_noise_noisy_latents_and_timesteps (src/duwu/loss/diffusion.py:74-82),
+ *   sample_timesteps_and_sigmas (:64-72), get_target (:84-98), the weight factors of apply_snr_weight
+ *   (:141-153) and apply_debiased_estimation (:155-167), and diffusers' Timesteps(dim, flip=True, shift=0).
+ *   Arithmetic follows the reference op by op (one rounding per op, no FMA contraction) so that with
+ *   injected eps/t the fp32 outputs are bit-identical to the PyTorch reference.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct uwu_noise_desc {
+    const void* x0;       /* [B, n_per] latents, dtype below */
+    const void* eps_in;   /* optional injected noise, same dtype/shape (NULL => in-kernel Philox4x32-10) */
+    const int64_t* t_in;  /* optional injected timesteps [B] (NULL => Philox) */
+    uint64_t seed, offset;
+    const float* acp;     /* scheduler.alphas_cumprod [T] */
+    const float* sigma_t; /* sigma of TIMESTEP t, [T] (= scheduler.sigmas[T-1-t]) */
+    const float* snr;     /* scheduler.all_snr [T] (src/duwu/loss/diffusion.py:42-51) */
+    int32_t T, B;
+    int64_t n_per;
+    int32_t dtype;        /* UWU_F32 | UWU_BF16: dtype of x0/eps/x_t/target */
+    int32_t target_type;  /* UWU_TARGET_* */
+    int32_t pred_type;    /* UWU_TARGET_* (selects the min-SNR formula) */
+    int32_t weight_flags; /* UWU_WEIGHT_* */
+    float gamma;          /* min_snr_gamma */
+    void* x_t;            /* out */
+    void* target;         /* out */
+    void* eps_out;        /* out, optional */
+    int64_t* t_out;       /* out [B] */
+    float* sigma_out;     /* out [B] */
+    float* w_out;         /* out [2,B]: min-SNR factor, debiased factor (1.0 when disabled) */
+    void* temb_out;       /* out, optional bf16 [B, temb_dim] = [cos | sin] */
+    int32_t temb_dim;
+} uwu_noise_desc;
+
+int uwu_noise_fwd(const uwu_noise_desc* desc, void* stream);
+
+/* Timesteps(dim)(vals) -> bf16 [n, dim]; SDXL add_time_proj on time_ids (diffusers, restated). */
+int uwu_sincos_embed(const float* vals, int32_t n, int32_t dim, int32_t flip_sin_to_cos, void* out_bf16, void* stream);
+
+/* Weighted MSE (src/duwu/loss/diffusion.py:179-193): losses[b] = w[1,b] * (mean_i (pred-target)^2 * w[0,b]),
+ * loss = mean_b losses[b].  `workspace` holds uwu_wmse_workspace_floats(B, n_per) floats. Deterministic. */
+int64_t uwu_wmse_workspace_floats(int32_t B, int64_t n_per);
+int uwu_wmse_fwd(const void* pred, int32_t pred_dtype, const void* target, int32_t target_dtype, int32_t B,
+                 int64_t n_per, const float* w, float* workspace, float* losses, float* loss, void* stream);
+/* dpred = grad_scale * (*grad_scale_dev or 1) * w0*w1 * 2 (pred - target) / (n_per * B) */
+int uwu_wmse_bwd(const void* pred, int32_t pred_dtype, const void* target, int32_t target_dtype, int32_t B,
+                 int64_t n_per, const float* w, const float* grad_scale_dev, float grad_scale, void* dpred,
+                 int32_t dpred_dtype, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UWU_B200_H */

@@ -1,0 +1,499 @@
+// Persistent warp-specialised tcgen05 GEMM / implicit-GEMM convolution for sm_100a.
+//
+//   D[M,N] = alpha * sum_k A[m,k] * B[n,k]  (+ bias[n]) (+ bias_rows[m / rows_per_bias, n]) (+ residual[m,n])
+//
+// * operands bf16, accumulation fp32 in TMEM (two accumulator buffers of <=256 columns),
+// * tiles 128 x block_n x 64, operands staged by TMA into 128-byte-swizzled shared memory,
+// * warp 0 = TMA producer, warp 1 = MMA issuer (one elected thread), warps 2..5 = epilogue
+//   (tcgen05.ld -> registers -> fused epilogue -> global),
+// * A may be: row-major [M,K] (K contiguous), "column-major" [K,M] (M contiguous, used for the
+//   token-reduction weight-gradient GEMMs), or an NHWC activation read through a 4-D tensor map with a
+//   table of (dn,dh,dw) taps (3x3 conv, stride-2 conv through phase planes, transposed-conv phases);
+//   out-of-image taps are zero-filled by TMA.  A second A source covers channel-concatenated inputs.
+// * B may be [N,K] (K contiguous: y = x W^T) or [K,N] (N contiguous).
+//
+// Replaces the cuBLASLt / cuDNN calls under diffusers' Linear / Conv2d.
+#include "api_internal.h"
+#include "common.cuh"
+
+namespace uwu {
+
+static constexpr int BLOCK_M = 128;
+static constexpr int BLOCK_K = 64;
+static constexpr int UMMA_K = 16;
+static constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KiB
+static constexpr int NUM_THREADS = 192;                      // 6 warps
+static constexpr int MAX_STAGES = 8;
+static constexpr int TMEM_COLS = 512;
+static constexpr int ACC_STRIDE = 256;
+
+struct GemmKernelArgs {
+    CUtensorMap tmA;
+    CUtensorMap tmA2;
+    CUtensorMap tmB;
+    int M, N;
+    int num_kb;  // number of 64-wide K blocks (conv: ntaps * kb_per_tap)
+    int block_n;
+    int num_m_tiles, num_n_tiles;
+    int a_mode;  // 0 K-major 2D, 1 MN-major 2D, 2 conv 4D
+    int b_mode;  // 0 K-major [N,K], 1 MN-major [K,N]
+    int stages;
+    int b_stage_bytes;
+    int tx_bytes;
+    uint32_t a_lbo, a_sbo, a_kadv, b_lbo, b_sbo, b_kadv;
+    // conv
+    int H, W, kb_per_tap, kb_src1;  // kb_src1: 64-blocks per tap that come from source 1
+    int tap_dn[9], tap_dh[9], tap_dw[9];
+    // epilogue
+    void* out;
+    void* out2;
+    long long ldo, ldo2;
+    int n_split;
+    int out_fp32;
+    const float* bias;
+    const float* bias_rows;
+    int rows_per_bias;
+    const __nv_bfloat16* residual;
+    long long ldr;
+    float alpha;
+    int accumulate;
+};
+
+__global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __grid_constant__ GemmKernelArgs p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // 1024-byte alignment is required by the 128B swizzle atoms
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int stage_bytes = A_STAGE_BYTES + p.b_stage_bytes;
+    uint8_t* bar_base = smem + (size_t)p.stages * stage_bytes;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(bar_base);
+    uint64_t* empty_bar = full_bar + MAX_STAGES;
+    uint64_t* tmem_full = empty_bar + MAX_STAGES;  // [2]
+    uint64_t* tmem_empty = tmem_full + 2;          // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&p.tmA);
+        tma_prefetch_desc(&p.tmA2);
+        tma_prefetch_desc(&p.tmB);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < p.stages; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&tmem_full[s], 1);
+            mbar_init(&tmem_empty[s], 4);  // one arrive per epilogue warp
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) {
+        tmem_alloc(tmem_slot, TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+
+    if (warp == 0) {
+        // ===================================== TMA producer =====================================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            const uint32_t tx_bytes = (uint32_t)p.tx_bytes;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int n_blk = tile % p.num_n_tiles;
+                const int m_blk = tile / p.num_n_tiles;
+                const int m0 = m_blk * BLOCK_M;
+                const int n0 = n_blk * p.block_n;
+                int cw = 0, ch = 0, cn = 0;
+                if (p.a_mode == 2) {
+                    cw = m0 % p.W;
+                    ch = (m0 / p.W) % p.H;
+                    cn = m0 / (p.W * p.H);
+                }
+                for (int kb = 0; kb < p.num_kb; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t* sa = smem + (size_t)stage * stage_bytes;
+                    uint8_t* sb = sa + A_STAGE_BYTES;
+                    mbar_expect_tx(&full_bar[stage], tx_bytes);
+                    // ---- A ----
+                    if (p.a_mode == 0) {
+                        tma_load_2d(sa, &p.tmA, &full_bar[stage], kb * BLOCK_K, m0);
+                    } else if (p.a_mode == 1) {
+                        tma_load_2d(sa, &p.tmA, &full_bar[stage], m0, kb * BLOCK_K);
+                        tma_load_2d(sa + 8192, &p.tmA, &full_bar[stage], m0 + 64, kb * BLOCK_K);
+                    } else {
+                        const int tap = kb / p.kb_per_tap;
+                        const int cb = kb - tap * p.kb_per_tap;
+                        if (cb < p.kb_src1)
+                            tma_load_4d(sa, &p.tmA, &full_bar[stage], cb * BLOCK_K, cw + p.tap_dw[tap],
+                                        ch + p.tap_dh[tap], cn + p.tap_dn[tap]);
+                        else
+                            tma_load_4d(sa, &p.tmA2, &full_bar[stage], (cb - p.kb_src1) * BLOCK_K, cw + p.tap_dw[tap],
+                                        ch + p.tap_dh[tap], cn + p.tap_dn[tap]);
+                    }
+                    // ---- B ----
+                    if (p.b_mode == 0) {
+                        tma_load_2d(sb, &p.tmB, &full_bar[stage], kb * BLOCK_K, n0);
+                    } else {
+                        for (int j = 0; j * 64 < p.block_n; ++j)
+                            tma_load_2d(sb + j * 8192, &p.tmB, &full_bar[stage], n0 + j * 64, kb * BLOCK_K);
+                    }
+                    if (++stage == p.stages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================== MMA issuer =====================================
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_bf16(BLOCK_M, (uint32_t)p.block_n, p.a_mode == 1, p.b_mode == 1);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * ACC_STRIDE);
+                for (int kb = 0; kb < p.num_kb; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+                    const uint32_t sb = sa + A_STAGE_BYTES;
+                    const uint64_t adesc = make_smem_desc(sa, p.a_lbo, p.a_sbo);
+                    const uint64_t bdesc = make_smem_desc(sb, p.b_lbo, p.b_sbo);
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                        umma_bf16(d_tmem, adesc + (uint64_t)((k * p.a_kadv) >> 4), bdesc + (uint64_t)((k * p.b_kadv) >> 4),
+                                  idesc, (uint32_t)((kb | k) != 0));
+                    }
+                    umma_commit(&empty_bar[stage]);  // frees this smem stage once the MMAs retire
+                    if (++stage == p.stages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+                umma_commit(&tmem_full[acc]);  // accumulator ready for the epilogue
+                if (++acc == 2) {
+                    acc = 0;
+                    acc_phase ^= 1;
+                }
+            }
+        }
+    } else {
+        // ===================================== epilogue =====================================
+        // warp w may only touch TMEM lanes [32*(w%4), 32*(w%4)+32)
+        const int sub = warp & 3;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int n_blk = tile % p.num_n_tiles;
+            const int m_blk = tile / p.num_n_tiles;
+            const int row = m_blk * BLOCK_M + sub * 32 + lane;
+            const int n0 = n_blk * p.block_n;
+            const int n_end = min(p.N, n0 + p.block_n);
+            mbar_wait(&tmem_full[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t t_row = tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(acc * ACC_STRIDE);
+            const bool row_ok = row < p.M;
+            const float* brow = (p.bias_rows != nullptr && row_ok)
+                                    ? p.bias_rows + (size_t)(row / p.rows_per_bias) * p.N
+                                    : nullptr;
+            for (int c = 0; c < p.block_n; c += 32) {
+                uint32_t r[32];
+                tmem_ld32(t_row + (uint32_t)c, r);
+                tmem_ld_wait();
+                const int col0 = n0 + c;
+                if (!row_ok || col0 >= n_end) continue;
+                // destination (out or out2 after the split column)
+                uint8_t* obase;
+                long long ld;
+                int ocol;
+                if (col0 >= p.n_split) {
+                    obase = reinterpret_cast<uint8_t*>(p.out2);
+                    ld = p.ldo2;
+                    ocol = col0 - p.n_split;
+                } else {
+                    obase = reinterpret_cast<uint8_t*>(p.out);
+                    ld = p.ldo;
+                    ocol = col0;
+                }
+                const int ncols = min(32, n_end - col0);
+                float v[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
+                if (p.bias != nullptr) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (j < ncols) v[j] += __ldg(p.bias + col0 + j);
+                }
+                if (brow != nullptr) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (j < ncols) v[j] += __ldg(brow + col0 + j);
+                }
+                const bool vec_ok = (ncols == 32);
+                if (p.residual != nullptr) {
+                    const __nv_bfloat16* rp = p.residual + (size_t)row * p.ldr + col0;
+                    if (vec_ok && ((reinterpret_cast<uintptr_t>(rp) & 15) == 0)) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            uint4 u = *reinterpret_cast<const uint4*>(rp + q * 8);
+                            float2 f0 = unpack_bf16(u.x), f1 = unpack_bf16(u.y), f2 = unpack_bf16(u.z),
+                                   f3 = unpack_bf16(u.w);
+                            v[q * 8 + 0] += f0.x; v[q * 8 + 1] += f0.y; v[q * 8 + 2] += f1.x; v[q * 8 + 3] += f1.y;
+                            v[q * 8 + 4] += f2.x; v[q * 8 + 5] += f2.y; v[q * 8 + 6] += f3.x; v[q * 8 + 7] += f3.y;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (j < ncols) v[j] += __bfloat162float(rp[j]);
+                    }
+                }
+                if (p.out_fp32) {
+                    float* op = reinterpret_cast<float*>(obase) + (size_t)row * ld + ocol;
+                    if (vec_ok && ((reinterpret_cast<uintptr_t>(op) & 15) == 0)) {
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            float4 o = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+                            if (p.accumulate) {
+                                float4 old = *reinterpret_cast<float4*>(op + q * 4);
+                                o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+                            }
+                            *reinterpret_cast<float4*>(op + q * 4) = o;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (j < ncols) op[j] = p.accumulate ? op[j] + v[j] : v[j];
+                    }
+                } else {
+                    __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(obase) + (size_t)row * ld + ocol;
+                    if (vec_ok && ((reinterpret_cast<uintptr_t>(op) & 15) == 0)) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            uint4 o;
+                            o.x = pack_bf16(v[q * 8 + 0], v[q * 8 + 1]);
+                            o.y = pack_bf16(v[q * 8 + 2], v[q * 8 + 3]);
+                            o.z = pack_bf16(v[q * 8 + 4], v[q * 8 + 5]);
+                            o.w = pack_bf16(v[q * 8 + 6], v[q * 8 + 7]);
+                            *reinterpret_cast<uint4*>(op + q * 8) = o;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (j < ncols) op[j] = __float2bfloat16(v[j]);
+                    }
+                }
+            }
+            // release the accumulator buffer back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            if (++acc == 2) {
+                acc = 0;
+                acc_phase ^= 1;
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
+// host side
+// ----------------------------------------------------------------------------------------------
+static int pick_block_n(long long N) {
+    if (N <= 16) return 16;
+    if (N <= 32) return 32;
+    if (N <= 64) return 64;
+    if (N <= 128) return 128;
+    if (N % 256 == 0) return 256;
+    if (N % 160 == 0) return 160;
+    if (N % 128 == 0) return 128;
+    if (N % 192 == 0) return 192;
+    return 256;
+}
+
+}  // namespace uwu
+
+using namespace uwu;
+
+extern "C" int uwu_gemm(const uwu_gemm_desc* d, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    UWU_CHECK_ARG(d != nullptr, "uwu_gemm: null descriptor");
+    UWU_CHECK_ARG(d->a && d->b && d->out, "uwu_gemm: null operand pointer");
+    UWU_CHECK_ARG(d->M > 0 && d->N > 0 && d->K > 0, "uwu_gemm: non-positive shape M=%lld N=%lld K=%lld",
+                  (long long)d->M, (long long)d->N, (long long)d->K);
+    UWU_CHECK_ARG(d->M < (1ll << 31) && d->N < (1ll << 31) && d->K < (1ll << 31), "uwu_gemm: shape exceeds int32");
+    UWU_CHECK_ARG(d->a_layout >= 0 && d->a_layout <= 2, "uwu_gemm: bad a_layout %d", d->a_layout);
+    UWU_CHECK_ARG(d->b_layout >= 0 && d->b_layout <= 1, "uwu_gemm: bad b_layout %d", d->b_layout);
+    UWU_CHECK_ARG(d->out_dtype == UWU_BF16 || d->out_dtype == UWU_F32, "uwu_gemm: bad out dtype %d", d->out_dtype);
+    UWU_CHECK_ARG(!(d->accumulate && d->out_dtype != UWU_F32), "uwu_gemm: accumulate requires fp32 output");
+
+    static thread_local GemmKernelArgs args;  // large (3 tensor maps); avoid re-zeroing cost on the stack
+    GemmKernelArgs& p = args;
+    p.M = (int)d->M;
+    p.N = (int)d->N;
+    int bn = d->block_n > 0 ? d->block_n : pick_block_n(d->N);
+    UWU_CHECK_ARG(bn % 16 == 0 && bn >= 16 && bn <= 256, "uwu_gemm: block_n %d must be a multiple of 16 in [16,256]", bn);
+    p.block_n = bn;
+    p.num_m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
+    p.num_n_tiles = (p.N + bn - 1) / bn;
+    p.a_mode = d->a_layout;
+    p.b_mode = d->b_layout;
+
+    // ---------------- A tensor map(s) ----------------
+    if (d->a_layout == UWU_A_ROW) {
+        UWU_CHECK_ARG(d->lda % 8 == 0 && d->lda >= d->K, "uwu_gemm: lda %lld must be >= K and a multiple of 8", (long long)d->lda);
+        uint64_t dims[2] = {(uint64_t)d->K, (uint64_t)d->M};
+        uint64_t str[1] = {(uint64_t)d->lda * 2};
+        uint32_t box[2] = {BLOCK_K, BLOCK_M};
+        if (encode_tmap_bf16(&p.tmA, d->a, 2, dims, str, box, 1)) return UWU_ERR_INVALID;
+        p.tmA2 = p.tmA;
+        p.num_kb = (int)((d->K + BLOCK_K - 1) / BLOCK_K);
+        p.a_lbo = 0; p.a_sbo = 1024; p.a_kadv = 32;
+    } else if (d->a_layout == UWU_A_COL) {
+        UWU_CHECK_ARG(d->lda % 8 == 0 && d->lda >= d->M, "uwu_gemm: lda %lld must be >= M and a multiple of 8", (long long)d->lda);
+        uint64_t dims[2] = {(uint64_t)d->M, (uint64_t)d->K};
+        uint64_t str[1] = {(uint64_t)d->lda * 2};
+        uint32_t box[2] = {64, BLOCK_K};
+        if (encode_tmap_bf16(&p.tmA, d->a, 2, dims, str, box, 1)) return UWU_ERR_INVALID;
+        p.tmA2 = p.tmA;
+        p.num_kb = (int)((d->K + BLOCK_K - 1) / BLOCK_K);
+        p.a_lbo = 8192; p.a_sbo = 1024; p.a_kadv = 2048;
+    } else {
+        // NHWC activation(s): [n_img_buf, H, W, C]
+        const int H = d->H, W = d->W, C1 = d->Cin1, C2 = d->Cin2;
+        UWU_CHECK_ARG(H > 0 && W > 0 && C1 > 0 && C2 >= 0, "uwu_gemm(conv): bad geometry H=%d W=%d C1=%d C2=%d", H, W, C1, C2);
+        UWU_CHECK_ARG(C1 % 64 == 0 && C2 % 64 == 0, "uwu_gemm(conv): channel counts must be multiples of 64 (got %d,%d)", C1, C2);
+        UWU_CHECK_ARG(d->ntaps >= 1 && d->ntaps <= 9, "uwu_gemm(conv): ntaps %d out of range", d->ntaps);
+        UWU_CHECK_ARG(d->K == (long long)d->ntaps * (C1 + C2), "uwu_gemm(conv): K %lld != ntaps*(C1+C2)", (long long)d->K);
+        UWU_CHECK_ARG(C2 == 0 || d->a2 != nullptr, "uwu_gemm(conv): Cin2 > 0 but a2 is null");
+        int bw, bh, bnimg;
+        if (W >= 128) {
+            UWU_CHECK_ARG(W % 128 == 0, "uwu_gemm(conv): W=%d must be a multiple of 128 when >= 128", W);
+            bw = 128; bh = 1; bnimg = 1;
+        } else {
+            UWU_CHECK_ARG(128 % W == 0, "uwu_gemm(conv): W=%d must divide 128", W);
+            bw = W;
+            int rows = 128 / W;
+            if (H >= rows) {
+                UWU_CHECK_ARG(H % rows == 0, "uwu_gemm(conv): H=%d incompatible with 128-pixel tiles", H);
+                bh = rows; bnimg = 1;
+            } else {
+                UWU_CHECK_ARG(rows % H == 0, "uwu_gemm(conv): H=%d incompatible with 128-pixel tiles", H);
+                bh = H; bnimg = rows / H;
+            }
+        }
+        const int nbuf = d->n_img_buf;
+        UWU_CHECK_ARG(nbuf > 0, "uwu_gemm(conv): n_img_buf must be > 0");
+        {
+            uint64_t dims[4] = {(uint64_t)C1, (uint64_t)W, (uint64_t)H, (uint64_t)nbuf};
+            uint64_t str[3] = {(uint64_t)C1 * 2, (uint64_t)C1 * W * 2, (uint64_t)C1 * W * H * 2};
+            uint32_t box[4] = {64, (uint32_t)bw, (uint32_t)bh, (uint32_t)bnimg};
+            if (encode_tmap_bf16(&p.tmA, d->a, 4, dims, str, box, 1)) return UWU_ERR_INVALID;
+        }
+        if (C2 > 0) {
+            uint64_t dims[4] = {(uint64_t)C2, (uint64_t)W, (uint64_t)H, (uint64_t)nbuf};
+            uint64_t str[3] = {(uint64_t)C2 * 2, (uint64_t)C2 * W * 2, (uint64_t)C2 * W * H * 2};
+            uint32_t box[4] = {64, (uint32_t)bw, (uint32_t)bh, (uint32_t)bnimg};
+            if (encode_tmap_bf16(&p.tmA2, d->a2, 4, dims, str, box, 1)) return UWU_ERR_INVALID;
+        } else {
+            p.tmA2 = p.tmA;
+        }
+        p.H = H; p.W = W;
+        p.kb_per_tap = (C1 + C2) / 64;
+        p.kb_src1 = C1 / 64;
+        p.num_kb = d->ntaps * p.kb_per_tap;
+        for (int t = 0; t < 9; ++t) {
+            p.tap_dn[t] = t < d->ntaps ? d->tap_dn[t] : 0;
+            p.tap_dh[t] = t < d->ntaps ? d->tap_dh[t] : 0;
+            p.tap_dw[t] = t < d->ntaps ? d->tap_dw[t] : 0;
+        }
+        p.a_mode = 2;
+        p.a_lbo = 0; p.a_sbo = 1024; p.a_kadv = 32;
+    }
+
+    // ---------------- B tensor map ----------------
+    if (d->b_layout == UWU_B_NK) {
+        UWU_CHECK_ARG(d->ldb % 8 == 0 && d->ldb >= d->K, "uwu_gemm: ldb %lld must be >= K and a multiple of 8", (long long)d->ldb);
+        uint64_t dims[2] = {(uint64_t)d->K, (uint64_t)d->N};
+        uint64_t str[1] = {(uint64_t)d->ldb * 2};
+        uint32_t box[2] = {BLOCK_K, (uint32_t)bn};
+        if (encode_tmap_bf16(&p.tmB, d->b, 2, dims, str, box, 1)) return UWU_ERR_INVALID;
+        p.b_stage_bytes = bn * BLOCK_K * 2;
+        p.b_lbo = 0; p.b_sbo = 1024; p.b_kadv = 32;
+    } else {
+        UWU_CHECK_ARG(d->ldb % 8 == 0 && d->ldb >= d->N, "uwu_gemm: ldb %lld must be >= N and a multiple of 8", (long long)d->ldb);
+        uint64_t dims[2] = {(uint64_t)d->N, (uint64_t)d->K};
+        uint64_t str[1] = {(uint64_t)d->ldb * 2};
+        uint32_t box[2] = {64, BLOCK_K};
+        if (encode_tmap_bf16(&p.tmB, d->b, 2, dims, str, box, 1)) return UWU_ERR_INVALID;
+        p.b_stage_bytes = ((bn + 63) / 64) * 8192;
+        p.b_lbo = 8192; p.b_sbo = 1024; p.b_kadv = 2048;
+    }
+    p.tx_bytes = A_STAGE_BYTES + p.b_stage_bytes;
+    // B stage must keep the next A stage 1024-byte aligned
+    p.b_stage_bytes = (p.b_stage_bytes + 1023) & ~1023;
+
+    if (d->dbg_a_lbo) p.a_lbo = (uint32_t)d->dbg_a_lbo;
+    if (d->dbg_a_sbo) p.a_sbo = (uint32_t)d->dbg_a_sbo;
+    if (d->dbg_a_kadv) p.a_kadv = (uint32_t)d->dbg_a_kadv;
+    if (d->dbg_b_lbo) p.b_lbo = (uint32_t)d->dbg_b_lbo;
+    if (d->dbg_b_sbo) p.b_sbo = (uint32_t)d->dbg_b_sbo;
+    if (d->dbg_b_kadv) p.b_kadv = (uint32_t)d->dbg_b_kadv;
+
+    // ---------------- epilogue ----------------
+    p.out = d->out;
+    p.ldo = d->ldo > 0 ? d->ldo : d->N;
+    p.out2 = d->out2;
+    p.ldo2 = d->ldo2;
+    p.n_split = d->out2 ? d->n_split : 0x7fffffff;
+    UWU_CHECK_ARG(d->out2 == nullptr || (d->n_split > 0 && d->n_split % 32 == 0 && d->n_split % bn == 0),
+                  "uwu_gemm: n_split %d must be a positive multiple of block_n %d", d->n_split, bn);
+    p.out_fp32 = d->out_dtype == UWU_F32;
+    p.bias = d->bias;
+    p.bias_rows = d->bias_rows;
+    p.rows_per_bias = d->rows_per_bias > 0 ? d->rows_per_bias : 1;
+    p.residual = reinterpret_cast<const __nv_bfloat16*>(d->residual);
+    p.ldr = d->ldr > 0 ? d->ldr : d->N;
+    p.alpha = d->alpha;
+    p.accumulate = d->accumulate;
+
+    // ---------------- launch ----------------
+    const int stage_bytes = A_STAGE_BYTES + p.b_stage_bytes;
+    const int smem_budget = 227 * 1024 - 1024 /*align slack*/ - 256 /*barriers*/;
+    int stages = smem_budget / stage_bytes;
+    if (stages > MAX_STAGES) stages = MAX_STAGES;
+    UWU_CHECK_ARG(stages >= 2, "uwu_gemm: tile too large for shared memory");
+    p.stages = stages;
+    const size_t smem_bytes = (size_t)stages * stage_bytes + 1024 + 256;
+
+    static bool attr_set = false;
+    if (!attr_set) {
+        UWU_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_set = true;
+    }
+    const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+    int grid = sm_count();
+    if (grid > num_tiles) grid = num_tiles;
+    gemm_tcgen05_kernel<<<grid, NUM_THREADS, smem_bytes, stream>>>(p);
+    UWU_CHECK_LAUNCH();
+    return UWU_OK;
+}

@@ -1,0 +1,469 @@
+// Fused diffusion noising + target + loss weights + sinusoidal timestep embedding, and the fused
+// weighted-MSE reduction (forward and backward).  All HBM-bound: one read of x0, one write each of
+// x_t / target (/ eps), vectorised 16-byte accesses, no host synchronisation.
+//
+// Replaces (paths relative to /root/reference):
+//   src/duwu/loss/diffusion.py:53-82   sample_timesteps_and_sigmas / get_noise_noisy_latents_and_timesteps
+//   src/duwu/loss/diffusion.py:84-98   get_target (epsilon | v_prediction | sample | rectified_flow)
+//   src/duwu/loss/diffusion.py:141-167 apply_snr_weight / apply_debiased_estimation (weights only)
+//   src/duwu/loss/diffusion.py:179-193 MSELoss(reduction="none") -> flatten(1).mean(1) -> weights -> mean()
+//   diffusers Timesteps(flip_sin_to_cos=True, freq_shift=0)  [third-party, restated in oracle/]
+#include "api_internal.h"
+#include "common.cuh"
+
+namespace uwu {
+
+// ------------------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al. 2011).  counter = {group_lo, group_hi, offset_lo, offset_hi}, key = seed.
+// oracle/philox.py restates this bit-for-bit.
+// ------------------------------------------------------------------------------------------------
+struct Philox4 {
+    uint32_t v[4];
+};
+UWU_DEVINL Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(M0, c0), lo0 = M0 * c0;
+        const uint32_t hi1 = __umulhi(M1, c2), lo1 = M1 * c2;
+        const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += W0; k1 += W1;
+    }
+    Philox4 o;
+    o.v[0] = c0; o.v[1] = c1; o.v[2] = c2; o.v[3] = c3;
+    return o;
+}
+static constexpr uint32_t TSTEP_KEY_XOR0 = 0x5851F42Du;
+static constexpr uint32_t TSTEP_KEY_XOR1 = 0x4C957F2Du;
+
+UWU_DEVINL int sample_timestep(int b, int T, uint64_t seed, uint64_t offset) {
+    Philox4 r = philox4x32_10((uint32_t)b, 0u, (uint32_t)offset, (uint32_t)(offset >> 32),
+                              (uint32_t)seed ^ TSTEP_KEY_XOR0, (uint32_t)(seed >> 32) ^ TSTEP_KEY_XOR1);
+    return (int)(((uint64_t)r.v[0] * (uint64_t)T) >> 32);
+}
+
+// four N(0,1) samples for element group g (elements 4g .. 4g+3 of the flattened batch)
+UWU_DEVINL void normal4(uint64_t g, uint64_t seed, uint64_t offset, float (&z)[4]) {
+    Philox4 r = philox4x32_10((uint32_t)g, (uint32_t)(g >> 32), (uint32_t)offset, (uint32_t)(offset >> 32),
+                              (uint32_t)seed, (uint32_t)(seed >> 32));
+    const float inv32 = 2.3283064365386963e-10f;  // 2^-32
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const float u1 = ((float)(r.v[2 * h] >> 8) + 1.0f) * 5.9604644775390625e-08f;  // (0,1], 24-bit
+        const float u2 = (float)r.v[2 * h + 1] * inv32;
+        const float rad = sqrtf(-2.0f * __logf(u1));
+        float s, c;
+        __sincosf(6.283185307179586f * u2, &s, &c);
+        z[2 * h] = rad * c;
+        z[2 * h + 1] = rad * s;
+    }
+}
+
+template <typename T>
+struct IO;
+template <>
+struct IO<float> {
+    static UWU_DEVINL float ld(const float* p) { return *p; }
+    static UWU_DEVINL void st(float* p, float v) { *p = v; }
+    static UWU_DEVINL float rnd(float v) { return v; }
+    static UWU_DEVINL void ld4(const float* p, float (&v)[4]) {
+        float4 f = *reinterpret_cast<const float4*>(p);
+        v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
+    }
+    static UWU_DEVINL void st4(float* p, const float (&v)[4]) {
+        *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+};
+template <>
+struct IO<__nv_bfloat16> {
+    static UWU_DEVINL float ld(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+    static UWU_DEVINL void st(__nv_bfloat16* p, float v) { *p = __float2bfloat16(v); }
+    static UWU_DEVINL float rnd(float v) { return __bfloat162float(__float2bfloat16(v)); }
+    static UWU_DEVINL void ld4(const __nv_bfloat16* p, float (&v)[4]) {
+        uint2 u = *reinterpret_cast<const uint2*>(p);
+        float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y);
+        v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+    }
+    static UWU_DEVINL void st4(__nv_bfloat16* p, const float (&v)[4]) {
+        uint2 u;
+        u.x = pack_bf16(v[0], v[1]);
+        u.y = pack_bf16(v[2], v[3]);
+        *reinterpret_cast<uint2*>(p) = u;
+    }
+};
+
+struct NoiseArgs {
+    const void* x0;
+    const void* eps_in;      // optional injected noise
+    const int64_t* t_in;     // optional injected timesteps
+    uint64_t seed, offset;
+    const float* acp;        // alphas_cumprod[T]
+    const float* sigma_t;    // sigma for timestep t, [T]
+    const float* snr;        // all_snr[T]
+    int T;
+    int B;
+    long long n_per;
+    int target_type;
+    int pred_type;
+    int weight_flags;
+    float gamma;
+    void* x_t;
+    void* target;
+    void* eps_out;           // optional
+    int64_t* t_out;
+    float* sigma_out;        // [B]
+    float* w_out;            // [2,B]: min-SNR weight, debiased weight (1.0 when disabled)
+    __nv_bfloat16* temb_out; // optional [B, temb_dim]
+    int temb_dim;
+    int vec_ok;
+};
+
+// Rounding discipline: the reference runs one ATen kernel per arithmetic op, so every intermediate is
+// rounded to the tensor dtype and no FMA contraction happens.  __fmul_rn/__fadd_rn forbid contraction
+// and IO<T>::rnd() re-rounds to bf16 when the latents are bf16.
+template <typename T>
+__global__ void __launch_bounds__(256) noise_fwd_kernel(const NoiseArgs a) {
+    const int b = blockIdx.y;
+    const int t = a.t_in ? (int)a.t_in[b] : sample_timestep(b, a.T, a.seed, a.offset);
+    const float sigma = IO<T>::rnd(a.sigma_t[t]);                                   // sigmas.to(ref_params)
+    const float sig2p1 = IO<T>::rnd(__fadd_rn(IO<T>::rnd(__fmul_rn(sigma, sigma)), 1.0f));
+    const float scale = IO<T>::rnd(__fdiv_rn(1.0f, IO<T>::rnd(__fsqrt_rn(sig2p1))));  // 1 / (sigma**2 + 1) ** 0.5
+    // get_velocity coefficients (diffusers): acp.to(dtype)[t] ** 0.5, (1 - acp[t]) ** 0.5
+    const float acp_t = IO<T>::rnd(a.acp[t]);
+    const float sa = IO<T>::rnd(__fsqrt_rn(acp_t));
+    const float s1a = IO<T>::rnd(__fsqrt_rn(IO<T>::rnd(__fsub_rn(1.0f, acp_t))));
+
+    if (blockIdx.x == 0) {
+        if (threadIdx.x == 0) {
+            a.t_out[b] = t;
+            a.sigma_out[b] = sigma;
+            const float snr = a.snr[t];
+            float w1 = 1.0f, w2 = 1.0f;
+            if (a.weight_flags & UWU_WEIGHT_MIN_SNR) {
+                const float m = fminf(snr, a.gamma);
+                w1 = (a.pred_type == UWU_TARGET_V) ? __fdiv_rn(m, __fadd_rn(snr, 1.0f)) : __fdiv_rn(m, snr);
+            }
+            if (a.weight_flags & UWU_WEIGHT_DEBIASED) w2 = __fdiv_rn(1.0f, __fsqrt_rn(fminf(snr, 1000.0f)));
+            a.w_out[b] = w1;
+            a.w_out[a.B + b] = w2;
+        }
+        if (a.temb_out) {
+            // Timesteps(dim, flip_sin_to_cos=True, downscale_freq_shift=0): [cos(t f_i), sin(t f_i)]
+            const int half = a.temb_dim / 2;
+            for (int i = threadIdx.x; i < half; i += blockDim.x) {
+                const float f = expf(-9.210340371976184f * (float)i / (float)half);
+                const float ang = (float)t * f;
+                a.temb_out[(size_t)b * a.temb_dim + i] = __float2bfloat16(cosf(ang));
+                a.temb_out[(size_t)b * a.temb_dim + half + i] = __float2bfloat16(sinf(ang));
+            }
+        }
+    }
+
+    const T* x0 = reinterpret_cast<const T*>(a.x0) + (size_t)b * a.n_per;
+    const T* ein = a.eps_in ? reinterpret_cast<const T*>(a.eps_in) + (size_t)b * a.n_per : nullptr;
+    T* xt = reinterpret_cast<T*>(a.x_t) + (size_t)b * a.n_per;
+    T* tg = reinterpret_cast<T*>(a.target) + (size_t)b * a.n_per;
+    T* eo = a.eps_out ? reinterpret_cast<T*>(a.eps_out) + (size_t)b * a.n_per : nullptr;
+
+    const long long ngroups = (a.n_per + 3) / 4;
+    for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < ngroups;
+         g += (long long)gridDim.x * blockDim.x) {
+        const long long i0 = g * 4;
+        const int cnt = (int)min(4ll, a.n_per - i0);
+        float x[4] = {0.f, 0.f, 0.f, 0.f}, e[4];
+        if (a.vec_ok) {
+            IO<T>::ld4(x0 + i0, x);
+        } else {
+            for (int j = 0; j < cnt; ++j) x[j] = IO<T>::ld(x0 + i0 + j);
+        }
+        if (ein) {
+            if (a.vec_ok) {
+                IO<T>::ld4(ein + i0, e);
+            } else {
+                for (int j = 0; j < 4; ++j) e[j] = j < cnt ? IO<T>::ld(ein + i0 + j) : 0.f;
+            }
+        } else {
+            // group index over the flattened batch so that every element has its own counter
+            normal4((uint64_t)b * (uint64_t)ngroups + (uint64_t)g, a.seed, a.offset, e);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) e[j] = IO<T>::rnd(e[j]);
+        }
+        float o[4], tv[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float noisy = IO<T>::rnd(__fadd_rn(x[j], IO<T>::rnd(__fmul_rn(e[j], sigma))));
+            o[j] = __fmul_rn(noisy, scale);
+            switch (a.target_type) {
+                case UWU_TARGET_EPSILON: tv[j] = e[j]; break;
+                case UWU_TARGET_V:
+                    tv[j] = __fsub_rn(IO<T>::rnd(__fmul_rn(sa, e[j])), IO<T>::rnd(__fmul_rn(s1a, x[j])));
+                    break;
+                case UWU_TARGET_SAMPLE: tv[j] = x[j]; break;
+                default: tv[j] = __fsub_rn(e[j], x[j]); break;  // rectified flow: noise - x0
+            }
+        }
+        if (a.vec_ok) {
+            IO<T>::st4(xt + i0, o);
+            IO<T>::st4(tg + i0, tv);
+            if (eo) IO<T>::st4(eo + i0, e);
+        } else {
+            for (int j = 0; j < cnt; ++j) {
+                IO<T>::st(xt + i0 + j, o[j]);
+                IO<T>::st(tg + i0 + j, tv[j]);
+                if (eo) IO<T>::st(eo + i0 + j, e[j]);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// sinusoidal embedding of arbitrary scalars (SDXL add_time_ids: Timesteps(256) on 6 ids per sample)
+// ------------------------------------------------------------------------------------------------
+__global__ void sincos_embed_kernel(const float* vals, int n, int dim, int flip, __nv_bfloat16* out) {
+    const int half = dim / 2;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n * half) return;
+    const int r = idx / half, i = idx - r * half;
+    const float f = expf(-9.210340371976184f * (float)i / (float)half);
+    const float ang = vals[r] * f;
+    const float s = sinf(ang), c = cosf(ang);
+    out[(size_t)r * dim + i] = __float2bfloat16(flip ? c : s);
+    out[(size_t)r * dim + half + i] = __float2bfloat16(flip ? s : c);
+}
+
+// ------------------------------------------------------------------------------------------------
+// weighted MSE: two-stage deterministic reduction
+// ------------------------------------------------------------------------------------------------
+static constexpr int WMSE_THREADS = 256;
+static constexpr int WMSE_ELEMS_PER_BLOCK = WMSE_THREADS * 4 * 8;
+
+template <typename TP, typename TT>
+__global__ void __launch_bounds__(WMSE_THREADS) wmse_partial_kernel(const TP* pred, const TT* target, long long n_per,
+                                                                    int chunks, int vec_ok, float* partial) {
+    const int b = blockIdx.y;
+    const TP* p = pred + (size_t)b * n_per;
+    const TT* q = target + (size_t)b * n_per;
+    const long long base = (long long)blockIdx.x * WMSE_ELEMS_PER_BLOCK;
+    float acc = 0.f;
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+        const long long i0 = base + ((long long)it * WMSE_THREADS + threadIdx.x) * 4;
+        if (i0 >= n_per) break;
+        float x[4], y[4];
+        if (vec_ok) {
+            IO<TP>::ld4(p + i0, x);
+            IO<TT>::ld4(q + i0, y);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float d = x[j] - y[j];
+                acc = fmaf(d, d, acc);
+            }
+        } else {
+            const int cnt = (int)min(4ll, n_per - i0);
+            for (int j = 0; j < cnt; ++j) {
+                const float d = IO<TP>::ld(p + i0 + j) - IO<TT>::ld(q + i0 + j);
+                acc = fmaf(d, d, acc);
+            }
+        }
+    }
+    __shared__ float red[WMSE_THREADS / 32];
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float v = threadIdx.x < WMSE_THREADS / 32 ? red[threadIdx.x] : 0.f;
+        v = warp_sum(v);
+        if (threadIdx.x == 0) partial[(size_t)b * chunks + blockIdx.x] = v;
+    }
+}
+
+__global__ void __launch_bounds__(256) wmse_final_kernel(const float* partial, int B, int chunks, long long n_per,
+                                                         const float* w, float* losses, float* loss) {
+    __shared__ float sh[256];
+    float tot = 0.f;
+    for (int b = threadIdx.x; b < B; b += blockDim.x) {
+        float s = 0.f;
+        for (int c = 0; c < chunks; ++c) s += partial[(size_t)b * chunks + c];
+        float l = s / (float)n_per;
+        if (w) {
+            l = __fmul_rn(l, w[b]);      // losses * snr_weight
+            l = __fmul_rn(w[B + b], l);  // weight * losses
+        }
+        losses[b] = l;
+        tot += l;
+    }
+    sh[threadIdx.x] = tot;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if (threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *loss = sh[0] / (float)B;
+}
+
+// d loss / d pred = gscale * w1[b]*w2[b] * 2 (pred - target) / (n_per * B)
+template <typename TP, typename TT, typename TO>
+__global__ void __launch_bounds__(256) wmse_bwd_kernel(const TP* pred, const TT* target, long long n_per, int B,
+                                                       const float* w, const float* gscale_ptr, float gscale, int vec_ok,
+                                                       TO* dpred) {
+    const int b = blockIdx.y;
+    float coef = gscale * (gscale_ptr ? *gscale_ptr : 1.0f) * 2.0f / ((float)n_per * (float)B);
+    if (w) coef *= w[b] * w[B + b];
+    const TP* p = pred + (size_t)b * n_per;
+    const TT* q = target + (size_t)b * n_per;
+    TO* o = dpred + (size_t)b * n_per;
+    const long long ngroups = (n_per + 3) / 4;
+    for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < ngroups;
+         g += (long long)gridDim.x * blockDim.x) {
+        const long long i0 = g * 4;
+        if (vec_ok) {
+            float x[4], y[4], d[4];
+            IO<TP>::ld4(p + i0, x);
+            IO<TT>::ld4(q + i0, y);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) d[j] = coef * (x[j] - y[j]);
+            IO<TO>::st4(o + i0, d);
+        } else {
+            const int cnt = (int)min(4ll, n_per - i0);
+            for (int j = 0; j < cnt; ++j)
+                IO<TO>::st(o + i0 + j, coef * (IO<TP>::ld(p + i0 + j) - IO<TT>::ld(q + i0 + j)));
+        }
+    }
+}
+
+}  // namespace uwu
+
+using namespace uwu;
+
+extern "C" int uwu_noise_fwd(const uwu_noise_desc* d, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    UWU_CHECK_ARG(d != nullptr, "uwu_noise_fwd: null descriptor");
+    UWU_CHECK_ARG(d->B >= 0 && d->n_per >= 0, "uwu_noise_fwd: negative size");
+    if (d->B == 0 || d->n_per == 0) return UWU_OK;  // empty batch: nothing to do (reference returns empty tensors)
+    UWU_CHECK_ARG(d->x0 && d->x_t && d->target && d->t_out && d->sigma_out && d->w_out, "uwu_noise_fwd: null pointer");
+    UWU_CHECK_ARG(d->acp && d->sigma_t && d->snr && d->T > 0, "uwu_noise_fwd: scheduler tables missing");
+    UWU_CHECK_ARG(d->dtype == UWU_F32 || d->dtype == UWU_BF16, "uwu_noise_fwd: bad dtype %d", d->dtype);
+    if (d->target_type < UWU_TARGET_EPSILON || d->target_type > UWU_TARGET_RF) {
+        // mirrors `raise ValueError(f"Unsupported target type ...")`, src/duwu/loss/diffusion.py:98
+        set_error("Unsupported target type %d", d->target_type);
+        return UWU_ERR_UNSUPPORTED;
+    }
+    UWU_CHECK_ARG(d->B <= 65535, "uwu_noise_fwd: batch %d exceeds 65535", d->B);
+    UWU_CHECK_ARG(d->temb_out == nullptr || (d->temb_dim > 0 && d->temb_dim % 2 == 0), "uwu_noise_fwd: bad temb_dim");
+    NoiseArgs a;
+    a.x0 = d->x0; a.eps_in = d->eps_in; a.t_in = d->t_in; a.seed = d->seed; a.offset = d->offset;
+    a.acp = d->acp; a.sigma_t = d->sigma_t; a.snr = d->snr; a.T = d->T; a.B = d->B; a.n_per = d->n_per;
+    a.target_type = d->target_type; a.pred_type = d->pred_type; a.weight_flags = d->weight_flags; a.gamma = d->gamma;
+    a.x_t = d->x_t; a.target = d->target; a.eps_out = d->eps_out; a.t_out = d->t_out; a.sigma_out = d->sigma_out;
+    a.w_out = d->w_out; a.temb_out = reinterpret_cast<__nv_bfloat16*>(d->temb_out); a.temb_dim = d->temb_dim;
+    const size_t esz = d->dtype == UWU_F32 ? 4 : 2;
+    auto al = [&](const void* p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) % (4 * esz)) == 0; };
+    a.vec_ok = (d->n_per % 4 == 0) && al(d->x0) && al(d->eps_in) && al(d->x_t) && al(d->target) && al(d->eps_out);
+    const long long ngroups = (d->n_per + 3) / 4;
+    long long bx = (ngroups + 255) / 256;
+    // ~8 blocks per SM in total, several groups per thread for large samples
+    const long long cap = (long long)sm_count() * 16 / d->B + 1;
+    if (bx > cap) bx = cap;
+    if (bx < 1) bx = 1;
+    dim3 grid((unsigned)bx, (unsigned)d->B);
+    if (d->dtype == UWU_F32)
+        noise_fwd_kernel<float><<<grid, 256, 0, stream>>>(a);
+    else
+        noise_fwd_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(a);
+    UWU_CHECK_LAUNCH();
+    return UWU_OK;
+}
+
+extern "C" int uwu_sincos_embed(const float* vals, int32_t n, int32_t dim, int32_t flip_sin_to_cos, void* out_bf16,
+                                void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    UWU_CHECK_ARG(n >= 0 && dim > 0 && dim % 2 == 0, "uwu_sincos_embed: bad shape n=%d dim=%d", n, dim);
+    if (n == 0) return UWU_OK;
+    UWU_CHECK_ARG(vals && out_bf16, "uwu_sincos_embed: null pointer");
+    const int total = n * (dim / 2);
+    sincos_embed_kernel<<<(total + 255) / 256, 256, 0, stream>>>(vals, n, dim, flip_sin_to_cos,
+                                                                  reinterpret_cast<__nv_bfloat16*>(out_bf16));
+    UWU_CHECK_LAUNCH();
+    return UWU_OK;
+}
+
+extern "C" int64_t uwu_wmse_workspace_floats(int32_t B, int64_t n_per) {
+    if (B <= 0 || n_per <= 0) return 0;
+    const int64_t chunks = (n_per + WMSE_ELEMS_PER_BLOCK - 1) / WMSE_ELEMS_PER_BLOCK;
+    return (int64_t)B * chunks;
+}
+
+template <typename TP>
+static int wmse_fwd_dispatch(const void* pred, const void* target, int tgt_dtype, long long n_per, int chunks, int vec_ok,
+                             float* ws, dim3 grid, cudaStream_t stream) {
+    if (tgt_dtype == UWU_F32)
+        wmse_partial_kernel<TP, float><<<grid, WMSE_THREADS, 0, stream>>>(reinterpret_cast<const TP*>(pred),
+                                                                          reinterpret_cast<const float*>(target), n_per,
+                                                                          chunks, vec_ok, ws);
+    else
+        wmse_partial_kernel<TP, __nv_bfloat16><<<grid, WMSE_THREADS, 0, stream>>>(
+            reinterpret_cast<const TP*>(pred), reinterpret_cast<const __nv_bfloat16*>(target), n_per, chunks, vec_ok, ws);
+    UWU_CHECK_LAUNCH();
+    return UWU_OK;
+}
+
+extern "C" int uwu_wmse_fwd(const void* pred, int32_t pred_dtype, const void* target, int32_t target_dtype, int32_t B,
+                            int64_t n_per, const float* w, float* workspace, float* losses, float* loss, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    UWU_CHECK_ARG(B > 0 && n_per > 0, "uwu_wmse_fwd: empty input (B=%d, n_per=%lld): mean of empty batch is undefined", B,
+                  (long long)n_per);
+    UWU_CHECK_ARG(B <= 65535, "uwu_wmse_fwd: batch too large");
+    UWU_CHECK_ARG(pred && target && workspace && losses && loss, "uwu_wmse_fwd: null pointer");
+    const int chunks = (int)((n_per + WMSE_ELEMS_PER_BLOCK - 1) / WMSE_ELEMS_PER_BLOCK);
+    const int vec_ok = (n_per % 4 == 0) && (reinterpret_cast<uintptr_t>(pred) % 16 == 0) &&
+                       (reinterpret_cast<uintptr_t>(target) % 16 == 0);
+    dim3 grid(chunks, B);
+    int rc;
+    if (pred_dtype == UWU_F32)
+        rc = wmse_fwd_dispatch<float>(pred, target, target_dtype, n_per, chunks, vec_ok, workspace, grid, stream);
+    else
+        rc = wmse_fwd_dispatch<__nv_bfloat16>(pred, target, target_dtype, n_per, chunks, vec_ok, workspace, grid, stream);
+    if (rc) return rc;
+    wmse_final_kernel<<<1, 256, 0, stream>>>(workspace, B, chunks, n_per, w, losses, loss);
+    UWU_CHECK_LAUNCH();
+    return UWU_OK;
+}
+
+template <typename TP, typename TT>
+static int wmse_bwd_dispatch(const void* pred, const void* target, long long n_per, int B, const float* w,
+                             const float* gptr, float g, int vec_ok, void* dpred, int out_dtype, dim3 grid,
+                             cudaStream_t stream) {
+    if (out_dtype == UWU_F32)
+        wmse_bwd_kernel<TP, TT, float><<<grid, 256, 0, stream>>>(reinterpret_cast<const TP*>(pred),
+                                                                 reinterpret_cast<const TT*>(target), n_per, B, w, gptr, g,
+                                                                 vec_ok, reinterpret_cast<float*>(dpred));
+    else
+        wmse_bwd_kernel<TP, TT, __nv_bfloat16><<<grid, 256, 0, stream>>>(
+            reinterpret_cast<const TP*>(pred), reinterpret_cast<const TT*>(target), n_per, B, w, gptr, g, vec_ok,
+            reinterpret_cast<__nv_bfloat16*>(dpred));
+    UWU_CHECK_LAUNCH();
+    return UWU_OK;
+}
+
+extern "C" int uwu_wmse_bwd(const void* pred, int32_t pred_dtype, const void* target, int32_t target_dtype, int32_t B,
+                            int64_t n_per, const float* w, const float* grad_scale_dev, float grad_scale, void* dpred,
+                            int32_t dpred_dtype, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    UWU_CHECK_ARG(B > 0 && n_per > 0 && B <= 65535, "uwu_wmse_bwd: bad shape");
+    UWU_CHECK_ARG(pred && target && dpred, "uwu_wmse_bwd: null pointer");
+    const int vec_ok = (n_per % 4 == 0) && (reinterpret_cast<uintptr_t>(pred) % 16 == 0) &&
+                       (reinterpret_cast<uintptr_t>(target) % 16 == 0) && (reinterpret_cast<uintptr_t>(dpred) % 16 == 0);
+    const long long ngroups = (n_per + 3) / 4;
+    long long bx = (ngroups + 255) / 256;
+    const long long cap = (long long)sm_count() * 16 / B + 1;
+    if (bx > cap) bx = cap;
+    dim3 grid((unsigned)bx, (unsigned)B);
+    if (pred_dtype == UWU_F32 && target_dtype == UWU_F32)
+        return wmse_bwd_dispatch<float, float>(pred, target, n_per, B, w, grad_scale_dev, grad_scale, vec_ok, dpred, dpred_dtype, grid, stream);
+    if (pred_dtype == UWU_F32 && target_dtype == UWU_BF16)
+        return wmse_bwd_dispatch<float, __nv_bfloat16>(pred, target, n_per, B, w, grad_scale_dev, grad_scale, vec_ok, dpred, dpred_dtype, grid, stream);
+    if (pred_dtype == UWU_BF16 && target_dtype == UWU_F32)
+        return wmse_bwd_dispatch<__nv_bfloat16, float>(pred, target, n_per, B, w, grad_scale_dev, grad_scale, vec_ok, dpred, dpred_dtype, grid, stream);
+    return wmse_bwd_dispatch<__nv_bfloat16, __nv_bfloat16>(pred, target, n_per, B, w, grad_scale_dev, grad_scale, vec_ok, dpred, dpred_dtype, grid, stream);
+}
