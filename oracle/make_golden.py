@@ -1,0 +1,80 @@
+"""Generate tests/golden/loss_golden.npz by running the REFERENCE's loss code verbatim (container only).
+
+    python -m oracle.make_golden
+
+For each case: seed torch, run `DiffusionLoss.forward(x, unet)` from /root/reference/src/duwu/loss/diffusion.py with
+a fixed stand-in denoiser (unet(x_t, t) = 0.5 * x_t), and record inputs (x0, the eps/t the reference drew —
+recovered by replaying randn_like -> randint in the reference's order, src/duwu/loss/diffusion.py:75-76,68-70) and
+outputs (noisy_latent, target, losses, loss).  Also records the scheduler tables and the in-tree known answers
+(sigma_max = 14.6146, configs/sampling/demo_sampling.yaml:49).  TEST INFRASTRUCTURE.
+"""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+import torch
+
+from . import diffusers_shim, ref_loss
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "loss_golden.npz")
+
+CASES = [
+    # name, target/pred type, use_snr, use_debiased, dtype, shape
+    ("eps_plain", "epsilon", False, False, torch.float32, (4, 4, 8, 8)),
+    ("eps_minsnr", "epsilon", True, False, torch.float32, (4, 4, 8, 8)),
+    ("eps_minsnr_debiased", "epsilon", True, True, torch.float32, (4, 4, 32, 32)),
+    ("v_plain", "v_prediction", False, False, torch.float32, (4, 4, 8, 8)),
+    ("v_minsnr", "v_prediction", True, False, torch.float32, (5, 4, 8, 8)),
+    ("sample_plain", "sample", False, False, torch.float32, (3, 4, 8, 8)),
+    ("rf_plain", "rectified_flow", False, False, torch.float32, (3, 4, 8, 8)),
+    ("eps_bf16", "epsilon", True, True, torch.bfloat16, (4, 4, 8, 8)),
+    ("v_bf16", "v_prediction", True, False, torch.bfloat16, (4, 4, 8, 8)),
+    ("ragged_fp32", "epsilon", True, True, torch.float32, (3, 3, 5, 7)),  # n_per = 105, not a multiple of 4
+    ("pixel_c1", "epsilon", False, False, torch.float32, (4, 3, 32, 32)),  # BASELINE configs[0] shape
+]
+
+
+def unet_stub(x, t, **kw):
+    return (0.5 * x,)
+
+
+def main():
+    assert ref_loss.available(), "needs /root/reference"
+    mod = ref_loss.load_reference_loss_module()
+    out = {}
+    sch = diffusers_shim.EulerDiscreteScheduler.from_pretrained("stabilityai/stable-diffusion-xl-base-1.0", subfolder="scheduler")
+    loss0 = mod.DiffusionLoss(sch)
+    out["tab_acp"] = sch.alphas_cumprod.numpy()
+    out["tab_sigmas"] = sch.sigmas.numpy()
+    out["tab_timesteps"] = sch.timesteps.numpy()
+    out["tab_snr"] = sch.all_snr.numpy()
+    out["tab_sigma_by_t"] = loss0.get_sigmas_for_timesteps(torch.arange(1000)).numpy()
+    for i, (name, ttype, snr, deb, dtype, shape) in enumerate(CASES):
+        sch = diffusers_shim.EulerDiscreteScheduler.from_pretrained("x", prediction_type=ttype)
+        L = mod.DiffusionLoss(sch, use_snr_weight=snr, use_debiased_estimation=deb, prediction_type=ttype, target_type=ttype)
+        g = torch.Generator().manual_seed(1215 + i)
+        x0 = torch.randn(shape, generator=g).to(dtype)
+        torch.manual_seed(777 + i)
+        loss, aux = L(x0, unet_stub)
+        # replay the reference's RNG order to recover eps (randn_like, then randint)
+        torch.manual_seed(777 + i)
+        eps = torch.randn_like(x0)
+        t = torch.randint(0, 1000, (shape[0],))
+        assert torch.equal(t, aux.timesteps)
+        out[f"{name}/x0"] = x0.float().numpy()
+        out[f"{name}/eps"] = eps.float().numpy()
+        out[f"{name}/t"] = t.numpy()
+        out[f"{name}/x_t"] = aux.noisy_latent.float().numpy()
+        out[f"{name}/target"] = aux.target.float().numpy()
+        out[f"{name}/pred"] = aux.pred.float().numpy()
+        out[f"{name}/losses"] = aux.losses.float().numpy()
+        out[f"{name}/loss"] = np.float32(loss.float().item())
+        out[f"{name}/meta"] = np.array([ttype, str(int(snr)), str(int(deb)), str(dtype).replace("torch.", "")])
+    # unsupported target type -> ValueError in the reference (:98)
+    np.savez_compressed(OUT, **out)
+    print("wrote", OUT, os.path.getsize(OUT), "bytes;", len(CASES), "cases")
+
+
+if __name__ == "__main__":
+    main()

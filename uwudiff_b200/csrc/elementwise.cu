@@ -1,0 +1,301 @@
+// Elementwise / layout glue over channels-last bf16 activations: GEGLU fwd/bwd, SiLU, residual add,
+// NCHW<->NHWC boundary conversion (the reference API is NCHW, src/duwu/data/base.py:13), nearest-2x upsample
+// fwd/bwd, stride-2 phase split (space-to-depth) and its inverse.  All vectorised 16-byte accesses.
+//
+// Replaces ATen elementwise kernels under diffusers GEGLU / Upsample2D / Downsample2D / residual adds
+// [third-party, restated in oracle/unet_oracle.py; GEGLU chunk order hidden, gate per SURVEY.md Appendix A.3].
+#include "api_internal.h"
+#include "common.cuh"
+
+namespace uwu {
+
+UWU_DEVINL void ld8e(const __nv_bfloat16* p, float (&v)[8]) {
+    uint4 u = *reinterpret_cast<const uint4*>(p);
+    float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), c = unpack_bf16(u.z), d = unpack_bf16(u.w);
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
+}
+UWU_DEVINL void st8e(__nv_bfloat16* p, const float (&v)[8]) {
+    uint4 u;
+    u.x = pack_bf16(v[0], v[1]); u.y = pack_bf16(v[2], v[3]); u.z = pack_bf16(v[4], v[5]); u.w = pack_bf16(v[6], v[7]);
+    *reinterpret_cast<uint4*>(p) = u;
+}
+
+// out[m, f] = in[m, f] * gelu(in[m, F + f])
+__global__ void geglu_fwd_kernel(const __nv_bfloat16* __restrict__ in, long long M, int F, __nv_bfloat16* __restrict__ out) {
+    const int fv = F / 8;
+    const long long total = M * fv;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long m = i / fv;
+        const int f = (int)(i - m * fv) * 8;
+        float h[8], g[8];
+        ld8e(in + m * 2 * F + f, h);
+        ld8e(in + m * 2 * F + F + f, g);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) h[j] *= gelu_erf_f(g[j]);
+        st8e(out + m * F + f, h);
+    }
+}
+// din[m, f] = dout * gelu(g);  din[m, F+f] = dout * h * gelu'(g)
+__global__ void geglu_bwd_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16* __restrict__ dout, long long M,
+                                 int F, __nv_bfloat16* __restrict__ din) {
+    const int fv = F / 8;
+    const long long total = M * fv;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long m = i / fv;
+        const int f = (int)(i - m * fv) * 8;
+        float h[8], g[8], d[8], dh[8], dg[8];
+        ld8e(in + m * 2 * F + f, h);
+        ld8e(in + m * 2 * F + F + f, g);
+        ld8e(dout + m * F + f, d);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            dh[j] = d[j] * gelu_erf_f(g[j]);
+            dg[j] = d[j] * h[j] * gelu_erf_grad_f(g[j]);
+        }
+        st8e(din + m * 2 * F + f, dh);
+        st8e(din + m * 2 * F + F + f, dg);
+    }
+}
+
+// mode 0: y = silu(x); mode 1: y = x * silu'(a) (x = dy, a = pre-activation); mode 2: y = x + a; mode 3: y = x
+__global__ void ew_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ a, long long nvec,
+                          int mode, __nv_bfloat16* __restrict__ y) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+        float f[8], b[8];
+        ld8e(x + i * 8, f);
+        if (mode == 1 || mode == 2) ld8e(a + i * 8, b);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (mode == 0) f[j] = silu_f(f[j]);
+            else if (mode == 1) f[j] *= silu_grad_f(b[j]);
+            else if (mode == 2) f[j] += b[j];
+        }
+        st8e(y + i * 8, f);
+    }
+}
+
+// NCHW (fp32 or bf16) -> NHWC bf16 with zero channel padding to Cpad
+template <typename T>
+__global__ void nchw_to_nhwc_kernel(const T* __restrict__ src, int N, int C, int HW, int Cpad, __nv_bfloat16* __restrict__ dst) {
+    const long long total = (long long)N * HW;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long n = i / HW;
+        const int p = (int)(i - n * HW);
+        __nv_bfloat16* d = dst + i * Cpad;
+        for (int c = 0; c < Cpad; ++c) {
+            float v = 0.f;
+            if (c < C) v = (float)src[(n * C + c) * HW + p];
+            d[c] = __float2bfloat16(v);
+        }
+    }
+}
+// rows [N*HW, ld] (bf16 or fp32), first C columns -> NCHW fp32
+template <typename T>
+__global__ void nhwc_to_nchw_kernel(const T* __restrict__ src, int N, int C, int HW, long long ld, float* __restrict__ dst) {
+    const long long total = (long long)N * HW;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long n = i / HW;
+        const int p = (int)(i - n * HW);
+        for (int c = 0; c < C; ++c) dst[(n * C + c) * HW + p] = (float)src[i * ld + c];
+    }
+}
+
+// nearest 2x upsample: y[n, 2h+a, 2w+b, c] = x[n, h, w, c]
+__global__ void upsample2x_kernel(const __nv_bfloat16* __restrict__ x, int N, int H, int W, int C,
+                                  __nv_bfloat16* __restrict__ y) {
+    const int cv = C / 8;
+    const long long total = (long long)N * 4 * H * W * cv;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int v = (int)(i % cv);
+        long long r = i / cv;
+        const int ow = (int)(r % (2 * W)); r /= (2 * W);
+        const int oh = (int)(r % (2 * H));
+        const long long n = r / (2 * H);
+        const uint4 u = *reinterpret_cast<const uint4*>(x + (((n * H + oh / 2) * W + ow / 2) * C + v * 8));
+        *reinterpret_cast<uint4*>(y + (((n * 2 * H + oh) * 2 * W + ow) * (long long)C + v * 8)) = u;
+    }
+}
+// backward: dx[n,h,w,c] = sum_{a,b} dy[n, 2h+a, 2w+b, c]
+__global__ void upsample2x_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int N, int H, int W, int C,
+                                      __nv_bfloat16* __restrict__ dx) {
+    const int cv = C / 8;
+    const long long total = (long long)N * H * W * cv;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int v = (int)(i % cv);
+        long long r = i / cv;
+        const int w = (int)(r % W); r /= W;
+        const int h = (int)(r % H);
+        const long long n = r / H;
+        float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+            for (int b = 0; b < 2; ++b) {
+                float f[8];
+                ld8e(dy + (((n * 2 * H + 2 * h + a) * 2 * W + 2 * w + b) * (long long)C + v * 8), f);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[j] += f[j];
+            }
+        st8e(dx + (((n * H + h) * W + w) * (long long)C + v * 8), acc);
+    }
+}
+
+// space-to-depth by 2: planes[(py*2+px)*N + n, i, j, c] = x[n, 2i+py, 2j+px, c]   (inverse = true: scatter back)
+__global__ void phase_split_kernel(const __nv_bfloat16* __restrict__ src, int N, int H, int W, int C, int inverse,
+                                   __nv_bfloat16* __restrict__ dst) {
+    const int cv = C / 8;
+    const int H2 = H / 2, W2 = W / 2;
+    const long long total = (long long)N * H * W * cv;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int v = (int)(i % cv);
+        long long r = i / cv;
+        const int w = (int)(r % W); r /= W;
+        const int h = (int)(r % H);
+        const long long n = r / H;
+        const long long full = (((n * H + h) * W + w) * (long long)C + v * 8);
+        const int p = (h & 1) * 2 + (w & 1);
+        const long long pl = ((((long long)p * N + n) * H2 + h / 2) * W2 + w / 2) * (long long)C + v * 8;
+        if (inverse)
+            *reinterpret_cast<uint4*>(dst + full) = *reinterpret_cast<const uint4*>(src + pl);
+        else
+            *reinterpret_cast<uint4*>(dst + pl) = *reinterpret_cast<const uint4*>(src + full);
+    }
+}
+
+// column sums of a bf16 matrix (bias gradients): partial[blockIdx.y][c] over a row chunk
+__global__ void colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, long long M, int C, long long ld, int rows_per_block,
+                                   float* __restrict__ partial) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const long long r0 = (long long)blockIdx.y * rows_per_block;
+    const long long r1 = min(M, r0 + rows_per_block);
+    float a = 0.f;
+    for (long long r = r0; r < r1; ++r) a += __bfloat162float(x[r * ld + c]);
+    partial[(size_t)blockIdx.y * C + c] = a;
+}
+__global__ void colsum_final_kernel(const float* __restrict__ partial, int P, int C, int accumulate, float* __restrict__ out) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    float a = 0.f;
+    for (int p = 0; p < P; ++p) a += partial[(size_t)p * C + c];
+    out[c] = accumulate ? out[c] + a : a;
+}
+
+static int ew_grid(long long work, int threads) {
+    long long b = (work + threads - 1) / threads;
+    const long long cap = (long long)sm_count() * 16;
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return (int)b;
+}
+
+}  // namespace uwu
+
+using namespace uwu;
+typedef __nv_bfloat16 bf16;
+
+extern "C" int uwu_geglu_fwd(const void* in, int64_t M, int32_t F, void* out, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    UWU_CHECK_ARG(M >= 0 && F > 0 && F % 8 == 0, "uwu_geglu_fwd: bad shape M=%lld F=%d", (long long)M, F);
+    if (M == 0) return UWU_OK;
+    UWU_CHECK_ARG(in && out, "uwu_geglu_fwd: null pointer");
+    geglu_fwd_kernel<<<ew_grid(M * (F / 8), 256), 256, 0, stream>>>(reinterpret_cast<const bf16*>(in), M, F,
+                                                                    reinterpret_cast<bf16*>(out));
+    UWU_CHECK_LAUNCH();
+    return UWU_OK;
+}
+extern "C" int uwu_geglu_bwd(const void* in, const void* dout, int64_t M, int32_t F, void* din, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    UWU_CHECK_ARG(M >= 0 && F > 0 && F % 8 == 0, "uwu_geglu_bwd: bad shape");
+    if (M == 0) return UWU_OK;
+    UWU_CHECK_ARG(in && dout && din, "uwu_geglu_bwd: null pointer");
+    geglu_bwd_kernel<<<ew_grid(M * (F / 8), 256), 256, 0, stream>>>(
+        reinterpret_cast<const bf16*>(in), reinterpret_cast<const bf16*>(dout), M, F, reinterpret_cast<bf16*>(din));
+    UWU_CHECK_LAUNCH();
+    return UWU_OK;
+}
+extern "C" int uwu_elementwise(const void* x, const void* a, int64_t n, int32_t mode, void* y, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    UWU_CHECK_ARG(n >= 0 && n % 8 == 0, "uwu_elementwise: n=%lld must be a multiple of 8", (long long)n);
+    UWU_CHECK_ARG(mode >= 0 && mode <= 3, "uwu_elementwise: bad mode %d", mode);
+    if (n == 0) return UWU_OK;
+    UWU_CHECK_ARG(x && y && (mode == 0 || mode == 3 || a), "uwu_elementwise: null pointer");
+    ew_kernel<<<ew_grid(n / 8, 256), 256, 0, stream>>>(reinterpret_cast<const bf16*>(x), reinterpret_cast<const bf16*>(a),
+                                                       n / 8, mode, reinterpret_cast<bf16*>(y));
+    UWU_CHECK_LAUNCH();
+    return UWU_OK;
+}
+extern "C" int uwu_nchw_to_nhwc(const void* src, int32_t src_dtype, int32_t N, int32_t C, int32_t HW, int32_t Cpad,
+                                void* dst_bf16, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    UWU_CHECK_ARG(N >= 0 && C > 0 && HW > 0 && Cpad >= C, "uwu_nchw_to_nhwc: bad shape");
+    if (N == 0) return UWU_OK;
+    UWU_CHECK_ARG(src && dst_bf16, "uwu_nchw_to_nhwc: null pointer");
+    const int grid = ew_grid((long long)N * HW, 256);
+    if (src_dtype == UWU_F32)
+        nchw_to_nhwc_kernel<float><<<grid, 256, 0, stream>>>(reinterpret_cast<const float*>(src), N, C, HW, Cpad,
+                                                             reinterpret_cast<bf16*>(dst_bf16));
+    else
+        nchw_to_nhwc_kernel<bf16><<<grid, 256, 0, stream>>>(reinterpret_cast<const bf16*>(src), N, C, HW, Cpad,
+                                                            reinterpret_cast<bf16*>(dst_bf16));
+    UWU_CHECK_LAUNCH();
+    return UWU_OK;
+}
+extern "C" int uwu_nhwc_to_nchw(const void* src, int32_t src_dtype, int32_t N, int32_t C, int32_t HW, int64_t ld,
+                                float* dst, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    UWU_CHECK_ARG(N >= 0 && C > 0 && HW > 0 && ld >= C, "uwu_nhwc_to_nchw: bad shape");
+    if (N == 0) return UWU_OK;
+    UWU_CHECK_ARG(src && dst, "uwu_nhwc_to_nchw: null pointer");
+    const int grid = ew_grid((long long)N * HW, 256);
+    if (src_dtype == UWU_F32)
+        nhwc_to_nchw_kernel<float><<<grid, 256, 0, stream>>>(reinterpret_cast<const float*>(src), N, C, HW, ld, dst);
+    else
+        nhwc_to_nchw_kernel<bf16><<<grid, 256, 0, stream>>>(reinterpret_cast<const bf16*>(src), N, C, HW, ld, dst);
+    UWU_CHECK_LAUNCH();
+    return UWU_OK;
+}
+extern "C" int uwu_upsample2x(const void* x, int32_t N, int32_t H, int32_t W, int32_t C, int32_t backward, void* y,
+                              void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    UWU_CHECK_ARG(N >= 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0, "uwu_upsample2x: bad shape");
+    if (N == 0) return UWU_OK;
+    UWU_CHECK_ARG(x && y, "uwu_upsample2x: null pointer");
+    if (!backward)
+        upsample2x_kernel<<<ew_grid((long long)N * 4 * H * W * (C / 8), 256), 256, 0, stream>>>(
+            reinterpret_cast<const bf16*>(x), N, H, W, C, reinterpret_cast<bf16*>(y));
+    else
+        upsample2x_bwd_kernel<<<ew_grid((long long)N * H * W * (C / 8), 256), 256, 0, stream>>>(
+            reinterpret_cast<const bf16*>(x), N, H, W, C, reinterpret_cast<bf16*>(y));
+    UWU_CHECK_LAUNCH();
+    return UWU_OK;
+}
+extern "C" int uwu_phase_split2(const void* src, int32_t N, int32_t H, int32_t W, int32_t C, int32_t inverse, void* dst,
+                                void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    UWU_CHECK_ARG(N >= 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0 && C > 0 && C % 8 == 0, "uwu_phase_split2: bad shape");
+    if (N == 0) return UWU_OK;
+    UWU_CHECK_ARG(src && dst, "uwu_phase_split2: null pointer");
+    phase_split_kernel<<<ew_grid((long long)N * H * W * (C / 8), 256), 256, 0, stream>>>(
+        reinterpret_cast<const bf16*>(src), N, H, W, C, inverse, reinterpret_cast<bf16*>(dst));
+    UWU_CHECK_LAUNCH();
+    return UWU_OK;
+}
+extern "C" int64_t uwu_colsum_workspace_floats(int64_t M, int32_t C) {
+    if (M <= 0 || C <= 0) return 0;
+    const int64_t P = (M + 511) / 512;
+    return P * C;
+}
+extern "C" int uwu_colsum_bf16(const void* x, int64_t M, int32_t C, int64_t ld, int32_t accumulate, float* out,
+                               float* workspace, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    UWU_CHECK_ARG(M > 0 && C > 0 && ld >= C, "uwu_colsum_bf16: bad shape");
+    UWU_CHECK_ARG(x && out && workspace, "uwu_colsum_bf16: null pointer");
+    const int P = (int)((M + 511) / 512);
+    dim3 grid((C + 127) / 128, P);
+    colsum_bf16_kernel<<<grid, 128, 0, stream>>>(reinterpret_cast<const bf16*>(x), M, C, ld, 512, workspace);
+    UWU_CHECK_LAUNCH();
+    colsum_final_kernel<<<(C + 127) / 128, 128, 0, stream>>>(workspace, P, C, accumulate, out);
+    UWU_CHECK_LAUNCH();
+    return UWU_OK;
+}

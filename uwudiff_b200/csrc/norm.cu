@@ -1,0 +1,545 @@
+// Bandwidth-bound normalisation kernels over channels-last bf16 activations (fp32 statistics):
+//   GroupNorm(+SiLU) forward/backward on NHWC [N, HW, C], LayerNorm(+adaLN modulate) forward/backward on [M, C].
+// 16-byte vector accesses, per-thread fixed channel ownership (no atomics in the streaming loops),
+// deterministic two-stage reductions through caller-provided workspaces.
+//
+// Replaces ATen group_norm / layer_norm (+ SiLU) under diffusers ResnetBlock2D / Transformer2DModel /
+// BasicTransformerBlock [third-party, restated in oracle/unet_oracle.py]; the in-tree evidence for the block
+// algebra is src/duwu/modules/rope_unet.py:288-415.
+#include "api_internal.h"
+#include "common.cuh"
+
+namespace uwu {
+
+UWU_DEVINL void ld8(const __nv_bfloat16* p, float (&v)[8]) {
+    uint4 u = *reinterpret_cast<const uint4*>(p);
+    float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), c = unpack_bf16(u.z), d = unpack_bf16(u.w);
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
+}
+UWU_DEVINL void st8(__nv_bfloat16* p, const float (&v)[8]) {
+    uint4 u;
+    u.x = pack_bf16(v[0], v[1]); u.y = pack_bf16(v[2], v[3]); u.z = pack_bf16(v[4], v[5]); u.w = pack_bf16(v[6], v[7]);
+    *reinterpret_cast<uint4*>(p) = u;
+}
+
+// ================================================================================================
+// GroupNorm
+// ================================================================================================
+// thread layout: blockDim = cv * rpi  (cv = C/8 channel vectors, rpi rows per iteration);
+// thread owns channel vector (tid % cv) for rows r0 + tid / cv + k * rpi.
+struct GNGeom {
+    int N, HW, C, G, cv, rpi, chunks, rows_per_chunk;
+};
+
+// partial sums: ws[((n * chunks + chunk) * G + g) * 2 + {0,1}] = {sum, sumsq}
+__global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x, GNGeom g, float* __restrict__ ws) {
+    extern __shared__ float sh[];  // [2][C]
+    const int n = blockIdx.y, chunk = blockIdx.x;
+    const int v = threadIdx.x % g.cv, rr = threadIdx.x / g.cv;
+    const int r0 = chunk * g.rows_per_chunk;
+    const int r1 = min(g.HW, r0 + g.rows_per_chunk);
+    float s[8], q[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
+    const __nv_bfloat16* base = x + ((size_t)n * g.HW) * g.C + v * 8;
+    for (int r = r0 + rr; r < r1; r += g.rpi) {
+        float f[8];
+        ld8(base + (size_t)r * g.C, f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            s[j] += f[j];
+            q[j] = fmaf(f[j], f[j], q[j]);
+        }
+    }
+    for (int i = threadIdx.x; i < 2 * g.C; i += blockDim.x) sh[i] = 0.f;
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        atomicAdd(&sh[v * 8 + j], s[j]);
+        atomicAdd(&sh[g.C + v * 8 + j], q[j]);
+    }
+    __syncthreads();
+    const int cpg = g.C / g.G;
+    for (int gi = threadIdx.x; gi < g.G; gi += blockDim.x) {
+        float a = 0.f, b = 0.f;
+        for (int c = gi * cpg; c < (gi + 1) * cpg; ++c) {
+            a += sh[c];
+            b += sh[g.C + c];
+        }
+        float* o = ws + (((size_t)n * g.chunks + chunk) * g.G + gi) * 2;
+        o[0] = a;
+        o[1] = b;
+    }
+}
+
+// finalise mean / rstd per (n, g) from the chunk partials; stats[n, g, {mean, rstd}]
+__global__ void gn_finalize_kernel(const float* __restrict__ ws, GNGeom g, float eps, float* __restrict__ stats) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= g.N * g.G) return;
+    const int n = idx / g.G, gi = idx - n * g.G;
+    float a = 0.f, b = 0.f;
+    for (int c = 0; c < g.chunks; ++c) {
+        const float* p = ws + (((size_t)n * g.chunks + c) * g.G + gi) * 2;
+        a += p[0];
+        b += p[1];
+    }
+    const float cnt = (float)g.HW * (float)(g.C / g.G);
+    const float mean = a / cnt;
+    const float var = fmaxf(b / cnt - mean * mean, 0.f);
+    stats[idx * 2] = mean;
+    stats[idx * 2 + 1] = rsqrtf(var + eps);
+}
+
+template <bool kSilu>
+__global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ stats,
+                                const float* __restrict__ gamma, const float* __restrict__ beta, GNGeom g,
+                                __nv_bfloat16* __restrict__ y) {
+    const int n = blockIdx.y, chunk = blockIdx.x;
+    const int v = threadIdx.x % g.cv, rr = threadIdx.x / g.cv;
+    const int cpg = g.C / g.G;
+    float sc[8], sf[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int c = v * 8 + j;
+        const int gi = c / cpg;
+        const float mean = stats[((size_t)n * g.G + gi) * 2], rstd = stats[((size_t)n * g.G + gi) * 2 + 1];
+        sc[j] = rstd * gamma[c];
+        sf[j] = beta[c] - mean * sc[j];
+    }
+    const int r0 = chunk * g.rows_per_chunk;
+    const int r1 = min(g.HW, r0 + g.rows_per_chunk);
+    const size_t off = ((size_t)n * g.HW) * g.C + v * 8;
+    for (int r = r0 + rr; r < r1; r += g.rpi) {
+        float f[8];
+        ld8(x + off + (size_t)r * g.C, f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float z = fmaf(f[j], sc[j], sf[j]);
+            f[j] = kSilu ? silu_f(z) : z;
+        }
+        st8(y + off + (size_t)r * g.C, f);
+    }
+}
+
+// backward pass 1: per (n, chunk, channel) sums of dz and dz*xhat  (dz = dy * silu'(z))
+//   wsb[((n * chunks + chunk) * 2 + {0,1}) * C + c]
+template <bool kSilu>
+__global__ void gn_bwd_stats_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
+                                    const float* __restrict__ stats, const float* __restrict__ gamma,
+                                    const float* __restrict__ beta, GNGeom g, float* __restrict__ wsb) {
+    extern __shared__ float sh[];  // [2][C]
+    const int n = blockIdx.y, chunk = blockIdx.x;
+    const int v = threadIdx.x % g.cv, rr = threadIdx.x / g.cv;
+    const int cpg = g.C / g.G;
+    float mean[8], rstd[8], ga[8], be[8], s1[8], s2[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int c = v * 8 + j, gi = c / cpg;
+        mean[j] = stats[((size_t)n * g.G + gi) * 2];
+        rstd[j] = stats[((size_t)n * g.G + gi) * 2 + 1];
+        ga[j] = gamma[c];
+        be[j] = beta[c];
+        s1[j] = s2[j] = 0.f;
+    }
+    const int r0 = chunk * g.rows_per_chunk;
+    const int r1 = min(g.HW, r0 + g.rows_per_chunk);
+    const size_t off = ((size_t)n * g.HW) * g.C + v * 8;
+    for (int r = r0 + rr; r < r1; r += g.rpi) {
+        float f[8], d[8];
+        ld8(x + off + (size_t)r * g.C, f);
+        ld8(dy + off + (size_t)r * g.C, d);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float xh = (f[j] - mean[j]) * rstd[j];
+            float dz = d[j];
+            if (kSilu) dz *= silu_grad_f(fmaf(xh, ga[j], be[j]));
+            s1[j] += dz;
+            s2[j] = fmaf(dz, xh, s2[j]);
+        }
+    }
+    for (int i = threadIdx.x; i < 2 * g.C; i += blockDim.x) sh[i] = 0.f;
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        atomicAdd(&sh[v * 8 + j], s1[j]);
+        atomicAdd(&sh[g.C + v * 8 + j], s2[j]);
+    }
+    __syncthreads();
+    float* o = wsb + ((size_t)n * g.chunks + chunk) * 2 * g.C;
+    for (int i = threadIdx.x; i < 2 * g.C; i += blockDim.x) o[i] = sh[i];
+}
+
+// backward pass 1b: reduce chunk partials -> per (n, c) sums; then per (n, g): A = sum_c gamma*S1, B = sum_c gamma*S2;
+// also accumulates dgamma/dbeta (sum over n) when requested.
+//   red[n, {0,1}, g] = {A/cnt, B/cnt}
+__global__ void gn_bwd_reduce_kernel(const float* __restrict__ wsb, const float* __restrict__ gamma, GNGeom g,
+                                     float* __restrict__ red, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+    // one block per n; threads over channels
+    extern __shared__ float sh[];  // [2][C] per-channel sums for this n
+    const int n = blockIdx.x;
+    for (int c = threadIdx.x; c < g.C; c += blockDim.x) {
+        float a = 0.f, b = 0.f;
+        for (int k = 0; k < g.chunks; ++k) {
+            const float* p = wsb + ((size_t)n * g.chunks + k) * 2 * g.C;
+            a += p[c];
+            b += p[g.C + c];
+        }
+        sh[c] = a;
+        sh[g.C + c] = b;
+        if (dgamma) atomicAdd(&dgamma[c], b);
+        if (dbeta) atomicAdd(&dbeta[c], a);
+    }
+    __syncthreads();
+    const int cpg = g.C / g.G;
+    const float cnt = (float)g.HW * (float)cpg;
+    for (int gi = threadIdx.x; gi < g.G; gi += blockDim.x) {
+        float A = 0.f, B = 0.f;
+        for (int c = gi * cpg; c < (gi + 1) * cpg; ++c) {
+            A = fmaf(gamma[c], sh[c], A);
+            B = fmaf(gamma[c], sh[g.C + c], B);
+        }
+        red[((size_t)n * 2) * g.G + gi] = A / cnt;
+        red[((size_t)n * 2 + 1) * g.G + gi] = B / cnt;
+    }
+}
+
+// backward pass 2: dx = rstd * (gamma*dz - A - xhat*B) (+ dres)
+template <bool kSilu>
+__global__ void gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
+                                    const float* __restrict__ stats, const float* __restrict__ gamma,
+                                    const float* __restrict__ beta, const float* __restrict__ red,
+                                    const __nv_bfloat16* __restrict__ dres, GNGeom g, __nv_bfloat16* __restrict__ dx) {
+    const int n = blockIdx.y, chunk = blockIdx.x;
+    const int v = threadIdx.x % g.cv, rr = threadIdx.x / g.cv;
+    const int cpg = g.C / g.G;
+    float mean[8], rstd[8], ga[8], be[8], A[8], Bc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int c = v * 8 + j, gi = c / cpg;
+        mean[j] = stats[((size_t)n * g.G + gi) * 2];
+        rstd[j] = stats[((size_t)n * g.G + gi) * 2 + 1];
+        ga[j] = gamma[c];
+        be[j] = beta[c];
+        A[j] = red[((size_t)n * 2) * g.G + gi];
+        Bc[j] = red[((size_t)n * 2 + 1) * g.G + gi];
+    }
+    const int r0 = chunk * g.rows_per_chunk;
+    const int r1 = min(g.HW, r0 + g.rows_per_chunk);
+    const size_t off = ((size_t)n * g.HW) * g.C + v * 8;
+    for (int r = r0 + rr; r < r1; r += g.rpi) {
+        float f[8], d[8], o[8];
+        ld8(x + off + (size_t)r * g.C, f);
+        ld8(dy + off + (size_t)r * g.C, d);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float xh = (f[j] - mean[j]) * rstd[j];
+            float dz = d[j];
+            if (kSilu) dz *= silu_grad_f(fmaf(xh, ga[j], be[j]));
+            o[j] = rstd[j] * (ga[j] * dz - A[j] - xh * Bc[j]);
+        }
+        if (dres) {
+            float e[8];
+            ld8(dres + off + (size_t)r * g.C, e);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] += e[j];
+        }
+        st8(dx + off + (size_t)r * g.C, o);
+    }
+}
+
+static int gn_geom(int N, int HW, int C, int G, GNGeom* g) {
+    UWU_CHECK_ARG(N > 0 && HW > 0 && C > 0 && G > 0, "groupnorm: bad shape N=%d HW=%d C=%d G=%d", N, HW, C, G);
+    UWU_CHECK_ARG(C % 8 == 0 && C % G == 0, "groupnorm: C=%d must be a multiple of 8 and of G=%d", C, G);
+    UWU_CHECK_ARG(C <= 8192, "groupnorm: C=%d too large", C);
+    g->N = N; g->HW = HW; g->C = C; g->G = G;
+    g->cv = C / 8;
+    int rpi = 256 / g->cv;
+    if (rpi < 1) rpi = 1;
+    if (g->cv * rpi > 1024) rpi = 1;
+    UWU_CHECK_ARG(g->cv <= 1024, "groupnorm: C too large");
+    g->rpi = rpi;
+    int chunks = (2 * sm_count() + N - 1) / N;
+    int max_chunks = (HW + rpi * 4 - 1) / (rpi * 4);
+    if (chunks > max_chunks) chunks = max_chunks;
+    if (chunks > 64) chunks = 64;
+    if (chunks < 1) chunks = 1;
+    g->rows_per_chunk = (HW + chunks - 1) / chunks;
+    g->chunks = (HW + g->rows_per_chunk - 1) / g->rows_per_chunk;
+    return 0;
+}
+
+// ================================================================================================
+// LayerNorm: one warp per row, two passes over the row (second pass hits L1)
+// ================================================================================================
+// y = ((x - mean) * rstd * gamma + beta) [* (1 + mscale[b]) + mshift[b]]   ;  stats[row] = {mean, rstd}
+__global__ void __launch_bounds__(256) ln_fwd_kernel(const __nv_bfloat16* __restrict__ x, int M, int C, float eps,
+                                                     const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                     const float* __restrict__ mscale, const float* __restrict__ mshift,
+                                                     int rows_per_mod, __nv_bfloat16* __restrict__ y,
+                                                     float* __restrict__ stats) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int cv = C / 8;
+    for (int row = blockIdx.x * 8 + warp; row < M; row += gridDim.x * 8) {
+        const __nv_bfloat16* xr = x + (size_t)row * C;
+        float s = 0.f;
+        for (int v = lane; v < cv; v += 32) {
+            float f[8];
+            ld8(xr + v * 8, f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) s += f[j];
+        }
+        const float mean = warp_sum(s) / (float)C;
+        float q = 0.f;
+        for (int v = lane; v < cv; v += 32) {
+            float f[8];
+            ld8(xr + v * 8, f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float d = f[j] - mean;
+                q = fmaf(d, d, q);
+            }
+        }
+        const float rstd = rsqrtf(warp_sum(q) / (float)C + eps);
+        if (lane == 0 && stats) {
+            stats[(size_t)row * 2] = mean;
+            stats[(size_t)row * 2 + 1] = rstd;
+        }
+        const float* ms = mscale ? mscale + (size_t)(row / rows_per_mod) * C : nullptr;
+        const float* mh = mshift ? mshift + (size_t)(row / rows_per_mod) * C : nullptr;
+        __nv_bfloat16* yr = y + (size_t)row * C;
+        for (int v = lane; v < cv; v += 32) {
+            float f[8];
+            ld8(xr + v * 8, f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int c = v * 8 + j;
+                float o = (f[j] - mean) * rstd;
+                if (gamma) o = fmaf(o, gamma[c], beta ? beta[c] : 0.f);
+                if (ms) o = fmaf(o, 1.0f + ms[c], mh ? mh[c] : 0.f);
+                f[j] = o;
+            }
+            st8(yr + v * 8, f);
+        }
+    }
+}
+
+// dx = rstd * (g - mean(g) - xhat * mean(g * xhat)) (+ dres), g = gamma * dy
+// partial param grads: pg[blockIdx.x][0][c] += dy*xhat, pg[blockIdx.x][1][c] += dy   (kMaxV vectors per lane)
+template <int kMaxV>
+__global__ void __launch_bounds__(256) ln_bwd_kernel(const __nv_bfloat16* __restrict__ x,
+                                                     const __nv_bfloat16* __restrict__ dy, int M, int C,
+                                                     const float* __restrict__ gamma, const float* __restrict__ stats,
+                                                     const __nv_bfloat16* __restrict__ dres,
+                                                     __nv_bfloat16* __restrict__ dx, float* __restrict__ pg) {
+    extern __shared__ float sh[];  // [2][C]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int cv = C / 8;
+    float ag[kMaxV][8], ab[kMaxV][8];
+#pragma unroll
+    for (int k = 0; k < kMaxV; ++k)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) ag[k][j] = ab[k][j] = 0.f;
+    for (int row = blockIdx.x * 8 + warp; row < M; row += gridDim.x * 8) {
+        const float mean = stats[(size_t)row * 2], rstd = stats[(size_t)row * 2 + 1];
+        const __nv_bfloat16* xr = x + (size_t)row * C;
+        const __nv_bfloat16* dr = dy + (size_t)row * C;
+        float xh[kMaxV][8], gg[kMaxV][8];
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int k = 0; k < kMaxV; ++k) {
+            const int v = lane + k * 32;
+            if (v < cv) {
+                float f[8], d[8];
+                ld8(xr + v * 8, f);
+                ld8(dr + v * 8, d);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float h = (f[j] - mean) * rstd;
+                    const float gmul = gamma ? gamma[v * 8 + j] : 1.0f;
+                    const float gv = d[j] * gmul;
+                    xh[k][j] = h;
+                    gg[k][j] = gv;
+                    s1 += gv;
+                    s2 = fmaf(gv, h, s2);
+                    ag[k][j] = fmaf(d[j], h, ag[k][j]);
+                    ab[k][j] += d[j];
+                }
+            }
+        }
+        s1 = warp_sum(s1) / (float)C;
+        s2 = warp_sum(s2) / (float)C;
+#pragma unroll
+        for (int k = 0; k < kMaxV; ++k) {
+            const int v = lane + k * 32;
+            if (v < cv) {
+                float o[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) o[j] = rstd * (gg[k][j] - s1 - xh[k][j] * s2);
+                if (dres) {
+                    float e[8];
+                    ld8(dres + (size_t)row * C + v * 8, e);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) o[j] += e[j];
+                }
+                st8(dx + (size_t)row * C + v * 8, o);
+            }
+        }
+    }
+    if (pg) {
+        for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sh[i] = 0.f;
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < kMaxV; ++k) {
+            const int v = lane + k * 32;
+            if (v < cv) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    atomicAdd(&sh[v * 8 + j], ag[k][j]);
+                    atomicAdd(&sh[C + v * 8 + j], ab[k][j]);
+                }
+            }
+        }
+        __syncthreads();
+        float* o = pg + (size_t)blockIdx.x * 2 * C;
+        for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) o[i] = sh[i];
+    }
+}
+
+// out[c] (+)= sum_p partial[p, c]
+__global__ void colsum_partials_kernel(const float* __restrict__ partial, int P, int stride, int n, int accumulate,
+                                       float* __restrict__ out) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    float a = 0.f;
+    for (int p = 0; p < P; ++p) a += partial[(size_t)p * stride + c];
+    out[c] = accumulate ? out[c] + a : a;
+}
+
+static int ln_grid(int M) {
+    int blocks = (M + 7) / 8;
+    const int cap = sm_count() * 8;
+    return blocks < cap ? blocks : cap;
+}
+
+}  // namespace uwu
+
+using namespace uwu;
+
+extern "C" int64_t uwu_groupnorm_workspace_floats(int32_t N, int32_t HW, int32_t C, int32_t G) {
+    GNGeom g;
+    if (gn_geom(N, HW, C, G, &g)) return -1;
+    // forward partials (N*chunks*G*2) or backward partials (N*chunks*2*C) + reduced (N*2*G)
+    return (int64_t)N * g.chunks * 2 * C + (int64_t)N * 2 * G + 64;
+}
+
+extern "C" int uwu_groupnorm_fwd(const void* x, int32_t N, int32_t HW, int32_t C, int32_t G, float eps,
+                                 const float* gamma, const float* beta, int32_t fuse_silu, void* y, float* stats,
+                                 float* workspace, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    GNGeom g;
+    if (gn_geom(N, HW, C, G, &g)) return UWU_ERR_INVALID;
+    UWU_CHECK_ARG(x && y && stats && workspace && gamma && beta, "uwu_groupnorm_fwd: null pointer");
+    const auto* xp = reinterpret_cast<const __nv_bfloat16*>(x);
+    auto* yp = reinterpret_cast<__nv_bfloat16*>(y);
+    dim3 grid(g.chunks, N);
+    const int threads = g.cv * g.rpi;
+    gn_stats_kernel<<<grid, threads, 2 * C * sizeof(float), stream>>>(xp, g, workspace);
+    UWU_CHECK_LAUNCH();
+    gn_finalize_kernel<<<(N * G + 127) / 128, 128, 0, stream>>>(workspace, g, eps, stats);
+    UWU_CHECK_LAUNCH();
+    if (fuse_silu)
+        gn_apply_kernel<true><<<grid, threads, 0, stream>>>(xp, stats, gamma, beta, g, yp);
+    else
+        gn_apply_kernel<false><<<grid, threads, 0, stream>>>(xp, stats, gamma, beta, g, yp);
+    UWU_CHECK_LAUNCH();
+    return UWU_OK;
+}
+
+extern "C" int uwu_groupnorm_bwd(const void* x, const void* dy, int32_t N, int32_t HW, int32_t C, int32_t G,
+                                 const float* gamma, const float* beta, const float* stats, int32_t fuse_silu,
+                                 const void* dres, void* dx, float* dgamma, float* dbeta, float* workspace,
+                                 void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    GNGeom g;
+    if (gn_geom(N, HW, C, G, &g)) return UWU_ERR_INVALID;
+    UWU_CHECK_ARG(x && dy && dx && stats && workspace && gamma && beta, "uwu_groupnorm_bwd: null pointer");
+    const auto* xp = reinterpret_cast<const __nv_bfloat16*>(x);
+    const auto* dyp = reinterpret_cast<const __nv_bfloat16*>(dy);
+    dim3 grid(g.chunks, N);
+    const int threads = g.cv * g.rpi;
+    float* wsb = workspace;
+    float* red = workspace + (size_t)N * g.chunks * 2 * C;
+    if (fuse_silu)
+        gn_bwd_stats_kernel<true><<<grid, threads, 2 * C * sizeof(float), stream>>>(xp, dyp, stats, gamma, beta, g, wsb);
+    else
+        gn_bwd_stats_kernel<false><<<grid, threads, 2 * C * sizeof(float), stream>>>(xp, dyp, stats, gamma, beta, g, wsb);
+    UWU_CHECK_LAUNCH();
+    gn_bwd_reduce_kernel<<<N, 256, 2 * C * sizeof(float), stream>>>(wsb, gamma, g, red, dgamma, dbeta);
+    UWU_CHECK_LAUNCH();
+    if (fuse_silu)
+        gn_bwd_apply_kernel<true><<<grid, threads, 0, stream>>>(xp, dyp, stats, gamma, beta, red,
+                                                                reinterpret_cast<const __nv_bfloat16*>(dres), g,
+                                                                reinterpret_cast<__nv_bfloat16*>(dx));
+    else
+        gn_bwd_apply_kernel<false><<<grid, threads, 0, stream>>>(xp, dyp, stats, gamma, beta, red,
+                                                                 reinterpret_cast<const __nv_bfloat16*>(dres), g,
+                                                                 reinterpret_cast<__nv_bfloat16*>(dx));
+    UWU_CHECK_LAUNCH();
+    return UWU_OK;
+}
+
+extern "C" int uwu_layernorm_fwd(const void* x, int32_t M, int32_t C, float eps, const float* gamma, const float* beta,
+                                 const float* mod_scale, const float* mod_shift, int32_t rows_per_mod, void* y,
+                                 float* stats, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    UWU_CHECK_ARG(M >= 0 && C > 0 && C % 8 == 0, "uwu_layernorm_fwd: bad shape M=%d C=%d (C must be a multiple of 8)", M, C);
+    if (M == 0) return UWU_OK;
+    UWU_CHECK_ARG(x && y, "uwu_layernorm_fwd: null pointer");
+    ln_fwd_kernel<<<ln_grid(M), 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), M, C, eps, gamma, beta,
+                                                   mod_scale, mod_shift, rows_per_mod > 0 ? rows_per_mod : 1,
+                                                   reinterpret_cast<__nv_bfloat16*>(y), stats);
+    UWU_CHECK_LAUNCH();
+    return UWU_OK;
+}
+
+extern "C" int64_t uwu_layernorm_bwd_workspace_floats(int32_t M, int32_t C) {
+    if (M <= 0 || C <= 0) return 0;
+    return (int64_t)ln_grid(M) * 2 * C;
+}
+
+extern "C" int uwu_layernorm_bwd(const void* x, const void* dy, int32_t M, int32_t C, const float* gamma,
+                                 const float* stats, const void* dres, void* dx, float* dgamma, float* dbeta,
+                                 int32_t accumulate, float* workspace, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    UWU_CHECK_ARG(M > 0 && C > 0 && C % 8 == 0, "uwu_layernorm_bwd: bad shape M=%d C=%d", M, C);
+    UWU_CHECK_ARG(C <= 8 * 32 * 5, "uwu_layernorm_bwd: C=%d > 1280 unsupported", C);
+    UWU_CHECK_ARG(x && dy && dx && stats, "uwu_layernorm_bwd: null pointer");
+    const bool want_pg = dgamma != nullptr || dbeta != nullptr;
+    UWU_CHECK_ARG(!want_pg || workspace, "uwu_layernorm_bwd: workspace required for parameter gradients");
+    const int grid = ln_grid(M);
+    const int cv = C / 8;
+    const auto* xp = reinterpret_cast<const __nv_bfloat16*>(x);
+    const auto* dyp = reinterpret_cast<const __nv_bfloat16*>(dy);
+    const auto* rp = reinterpret_cast<const __nv_bfloat16*>(dres);
+    auto* dxp = reinterpret_cast<__nv_bfloat16*>(dx);
+    float* pg = want_pg ? workspace : nullptr;
+    const size_t sm = 2 * C * sizeof(float);
+    if (cv <= 64)
+        ln_bwd_kernel<2><<<grid, 256, sm, stream>>>(xp, dyp, M, C, gamma, stats, rp, dxp, pg);
+    else if (cv <= 96)
+        ln_bwd_kernel<3><<<grid, 256, sm, stream>>>(xp, dyp, M, C, gamma, stats, rp, dxp, pg);
+    else
+        ln_bwd_kernel<5><<<grid, 256, sm, stream>>>(xp, dyp, M, C, gamma, stats, rp, dxp, pg);
+    UWU_CHECK_LAUNCH();
+    if (want_pg) {
+        if (dgamma) {
+            colsum_partials_kernel<<<(C + 127) / 128, 128, 0, stream>>>(pg, grid, 2 * C, C, accumulate, dgamma);
+            UWU_CHECK_LAUNCH();
+        }
+        if (dbeta) {
+            colsum_partials_kernel<<<(C + 127) / 128, 128, 0, stream>>>(pg + C, grid, 2 * C, C, accumulate, dbeta);
+            UWU_CHECK_LAUNCH();
+        }
+    }
+    return UWU_OK;
+}
