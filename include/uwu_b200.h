@@ -135,6 +135,66 @@ int uwu_wmse_bwd(const void* pred, int32_t pred_dtype, const void* target, int32
                  int64_t n_per, const float* w, const float* grad_scale_dev, float grad_scale, void* dpred,
                  int32_t dpred_dtype, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Flash attention forward / backward (tcgen05 + TMEM + TMA), head_dim 64.
+ *   replaces F.scaled_dot_product_attention in diffusers' AttnProcessor2_0 (in-tree copy of the flow:
+ *   src/duwu/modules/rope_unet.py:76-175, SDPA call :151) for attn1 (self) and attn2 (cross, Lk = 77).
+ *   q/o: bf16 [B*Lq, ld], k/v: bf16 [B*Lk, ld]; head h occupies columns [64h, 64h+64).
+ *   lse: fp32 [B, heads, roundup(Lq,128)] (uwu_attn_lse_floats), natural-log-sum-exp of scale*QK^T.
+ *   backward workspace: uwu_attn_bwd_workspace_floats floats, 16-byte aligned.
+ * ------------------------------------------------------------------------------------------------ */
+int64_t uwu_attn_lse_floats(int32_t B, int32_t heads, int32_t Lq);
+int uwu_attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int32_t B, int32_t heads, int32_t Lq,
+                 int32_t Lk, int32_t head_dim, int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo, float scale,
+                 void* stream);
+int64_t uwu_attn_bwd_workspace_floats(int32_t B, int32_t heads, int32_t Lq);
+int uwu_attn_bwd(const void* q, const void* k, const void* v, const void* o, const void* dout, const float* lse, void* dq,
+                 void* dk, void* dv, int32_t B, int32_t heads, int32_t Lq, int32_t Lk, int32_t head_dim, int64_t ldq,
+                 int64_t ldk, int64_t ldv, int64_t ldo, int64_t lddo, int64_t lddq, int64_t lddk, int64_t lddv, float scale,
+                 float* workspace, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Bandwidth-bound glue over channels-last bf16 activations (fp32 statistics and parameters).
+ *   replaces ATen group_norm / layer_norm / silu / gelu / add / upsample kernels under diffusers'
+ *   ResnetBlock2D, Transformer2DModel, BasicTransformerBlock (in-tree copy of the block algebra:
+ *   src/duwu/modules/rope_unet.py:288-415), GEGLU, Upsample2D, Downsample2D [third-party, restated in oracle/].
+ * ------------------------------------------------------------------------------------------------ */
+/* GroupNorm(+SiLU) on x[N, HW, C]; stats[N, G, 2] = {mean, rstd}; workspace: uwu_groupnorm_workspace_floats */
+int64_t uwu_groupnorm_workspace_floats(int32_t N, int32_t HW, int32_t C, int32_t G);
+int uwu_groupnorm_fwd(const void* x, int32_t N, int32_t HW, int32_t C, int32_t G, float eps, const float* gamma,
+                      const float* beta, int32_t fuse_silu, void* y, float* stats, float* workspace, void* stream);
+/* dx = GN'(dy) (+ dres); dgamma/dbeta (optional) are ACCUMULATED into */
+int uwu_groupnorm_bwd(const void* x, const void* dy, int32_t N, int32_t HW, int32_t C, int32_t G, const float* gamma,
+                      const float* beta, const float* stats, int32_t fuse_silu, const void* dres, void* dx,
+                      float* dgamma, float* dbeta, float* workspace, void* stream);
+/* LayerNorm on x[M, C] with optional adaLN modulation y = LN(x) * (1 + mod_scale[m / rows_per_mod]) + mod_shift[..];
+ * stats[M, 2] = {mean, rstd} (optional) */
+int uwu_layernorm_fwd(const void* x, int32_t M, int32_t C, float eps, const float* gamma, const float* beta,
+                      const float* mod_scale, const float* mod_shift, int32_t rows_per_mod, void* y, float* stats,
+                      void* stream);
+int64_t uwu_layernorm_bwd_workspace_floats(int32_t M, int32_t C);
+int uwu_layernorm_bwd(const void* x, const void* dy, int32_t M, int32_t C, const float* gamma, const float* stats,
+                      const void* dres, void* dx, float* dgamma, float* dbeta, int32_t accumulate, float* workspace,
+                      void* stream);
+/* GEGLU: out[m, f] = in[m, f] * gelu_erf(in[m, F + f])  (hidden, gate = proj.chunk(2)) */
+int uwu_geglu_fwd(const void* in, int64_t M, int32_t F, void* out, void* stream);
+int uwu_geglu_bwd(const void* in, const void* dout, int64_t M, int32_t F, void* din, void* stream);
+/* mode 0: y = silu(x); 1: y = x * silu'(a); 2: y = x + a; 3: y = x   (bf16, n multiple of 8) */
+int uwu_elementwise(const void* x, const void* a, int64_t n, int32_t mode, void* y, void* stream);
+/* API boundary layout conversion: the reference tensors are NCHW (src/duwu/data/base.py:13) */
+int uwu_nchw_to_nhwc(const void* src, int32_t src_dtype, int32_t N, int32_t C, int32_t HW, int32_t Cpad, void* dst_bf16,
+                     void* stream);
+int uwu_nhwc_to_nchw(const void* src, int32_t src_dtype, int32_t N, int32_t C, int32_t HW, int64_t ld, float* dst,
+                     void* stream);
+/* nearest 2x upsample (backward = 1: sum of the 2x2 children) */
+int uwu_upsample2x(const void* x, int32_t N, int32_t H, int32_t W, int32_t C, int32_t backward, void* y, void* stream);
+/* space-to-depth by 2 into 4 phase planes [(py*2+px)*N + n, H/2, W/2, C] (stride-2 conv input); inverse = 1 scatters back */
+int uwu_phase_split2(const void* src, int32_t N, int32_t H, int32_t W, int32_t C, int32_t inverse, void* dst, void* stream);
+/* column sums of a bf16 matrix (bias gradients) */
+int64_t uwu_colsum_workspace_floats(int64_t M, int32_t C);
+int uwu_colsum_bf16(const void* x, int64_t M, int32_t C, int64_t ld, int32_t accumulate, float* out, float* workspace,
+                    void* stream);
+
 #ifdef __cplusplus
 }
 #endif

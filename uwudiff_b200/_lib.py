@@ -69,6 +69,25 @@ SIGNATURES = {
     "uwu_wmse_workspace_floats": (C.c_int64, [_I32, _I64]),
     "uwu_wmse_fwd": (C.c_int, [_P, _I32, _P, _I32, _I32, _I64, _P, _P, _P, _P, _P]),
     "uwu_wmse_bwd": (C.c_int, [_P, _I32, _P, _I32, _I32, _I64, _P, _P, _F, _P, _I32, _P]),
+    "uwu_attn_lse_floats": (C.c_int64, [_I32, _I32, _I32]),
+    "uwu_attn_fwd": (C.c_int, [_P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I64, _I64, _I64, _I64, _F, _P]),
+    "uwu_attn_bwd_workspace_floats": (C.c_int64, [_I32, _I32, _I32]),
+    "uwu_attn_bwd": (C.c_int, [_P] * 9 + [_I32] * 5 + [_I64] * 8 + [_F, _P, _P]),
+    "uwu_groupnorm_workspace_floats": (C.c_int64, [_I32, _I32, _I32, _I32]),
+    "uwu_groupnorm_fwd": (C.c_int, [_P, _I32, _I32, _I32, _I32, _F, _P, _P, _I32, _P, _P, _P, _P]),
+    "uwu_groupnorm_bwd": (C.c_int, [_P, _P, _I32, _I32, _I32, _I32, _P, _P, _P, _I32, _P, _P, _P, _P, _P, _P]),
+    "uwu_layernorm_fwd": (C.c_int, [_P, _I32, _I32, _F, _P, _P, _P, _P, _I32, _P, _P, _P]),
+    "uwu_layernorm_bwd_workspace_floats": (C.c_int64, [_I32, _I32]),
+    "uwu_layernorm_bwd": (C.c_int, [_P, _P, _I32, _I32, _P, _P, _P, _P, _P, _P, _I32, _P, _P]),
+    "uwu_geglu_fwd": (C.c_int, [_P, _I64, _I32, _P, _P]),
+    "uwu_geglu_bwd": (C.c_int, [_P, _P, _I64, _I32, _P, _P]),
+    "uwu_elementwise": (C.c_int, [_P, _P, _I64, _I32, _P, _P]),
+    "uwu_nchw_to_nhwc": (C.c_int, [_P, _I32, _I32, _I32, _I32, _I32, _P, _P]),
+    "uwu_nhwc_to_nchw": (C.c_int, [_P, _I32, _I32, _I32, _I32, _I64, _P, _P]),
+    "uwu_upsample2x": (C.c_int, [_P, _I32, _I32, _I32, _I32, _I32, _P, _P]),
+    "uwu_phase_split2": (C.c_int, [_P, _I32, _I32, _I32, _I32, _I32, _P, _P]),
+    "uwu_colsum_workspace_floats": (C.c_int64, [_I64, _I32]),
+    "uwu_colsum_bf16": (C.c_int, [_P, _I64, _I32, _I64, _I32, _P, _P, _P]),
 }
 
 

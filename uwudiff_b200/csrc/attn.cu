@@ -1,0 +1,722 @@
+// Flash-style attention forward and backward on tcgen05 / TMEM / TMA for sm_100a (head_dim 64, bf16, fp32 softmax).
+//
+//   forward : O = softmax(scale * Q K^T) V, LSE      one CTA = 2 x 128 query rows of one (batch, head), ping-ponged
+//   backward: dQ, dK, dV                              one CTA = 128 keys of one (batch, head), loops over query tiles
+//
+// Q/K/V/O live in token-major activations [B*L, ld] with head h in columns [64h, 64h+64) (exactly how the fused
+// QKV projection GEMM writes them), so no permutes are needed: 3-D tensor maps {64h.., l, b} pick the head slice.
+//
+// forward roles : warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 softmax of query tile 0, warps 6-9 of tile 1.
+//   S = Q K^T lands in TMEM (128 lanes x 128 fp32 columns per tile); each softmax thread owns one query row
+//   (tcgen05.ld 32x32b), writes P as bf16 into 128B-swizzled shared memory, the P V product goes to a second TMEM
+//   region and is folded into fp32 register accumulators with the running-max rescale.
+// backward roles: warp 0 TMA, warp 1 MMA, warps 2-9 compute.  Per query tile: S^T = K Q^T and dP^T = V dO^T in TMEM
+//   (thread = key row), P^T = exp2(S^T*c - lse), dS^T = P^T o (dP^T - delta) written to swizzled smem as bf16,
+//   then dV += P^T dO, dK += dS^T Q (TMEM accumulators over the whole loop) and dQ_tile = dS K, which is reduced
+//   into an fp32 scratch with one 32 KiB cp.reduce.async.bulk per tile (no per-element atomics).
+//
+// Replaces F.scaled_dot_product_attention under diffusers' AttnProcessor2_0 (the in-tree copy of that flow is
+// src/duwu/modules/rope_unet.py:76-175; SDPA call at :151) for attn1 (self) and attn2 (cross, Lk = 77).
+#include "api_internal.h"
+#include "common.cuh"
+
+namespace uwu {
+
+static constexpr int AT_TILE = 128 * 64 * 2;  // one [128 x 64] bf16 operand tile, 16 KiB
+static constexpr float LOG2E = 1.4426950408889634f;
+
+UWU_DEVINL uint8_t* align1024(uint8_t* p) {
+    return reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(p) + 1023) & ~uintptr_t(1023));
+}
+
+// K-major SW128 descriptors (row = M/N index, 64 bf16 = 128 B per row): LBO unused, SBO = 8 rows * 128 B
+UWU_DEVINL uint64_t desc_kmajor(uint32_t saddr) { return make_smem_desc(saddr, 0, 1024); }
+// MN-major SW128 descriptors (row = K index, 64 contiguous M/N elements per row)
+UWU_DEVINL uint64_t desc_mnmajor(uint32_t saddr, uint32_t lbo) { return make_smem_desc(saddr, lbo, 1024); }
+
+// ================================================================================================
+// forward
+// ================================================================================================
+struct AttnFwdArgs {
+    CUtensorMap tmQ, tmK, tmV;
+    int Lq, Lk, heads, Lq_pad;
+    float scale, scale_log2;
+    __nv_bfloat16* o;
+    long long ldo;
+    float* lse;  // [B, heads, Lq_pad]
+};
+
+static constexpr int FWD_SQ = 0;                  // 2 query tiles
+static constexpr int FWD_SK = 2 * AT_TILE;        // 2 stages
+static constexpr int FWD_SV = 4 * AT_TILE;        // 2 stages
+static constexpr int FWD_SP = 6 * AT_TILE;        // 2 tiles x [128 x 128] bf16
+static constexpr int FWD_BAR = 10 * AT_TILE;      // 163840
+static constexpr int FWD_SMEM = FWD_BAR + 256 + 1024;
+static constexpr int FWD_THREADS = 320;
+
+__global__ void __launch_bounds__(FWD_THREADS, 1) attn_fwd_kernel(const __grid_constant__ AttnFwdArgs p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = align1024(smem_raw);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + FWD_BAR);
+    uint64_t* q_full = bars;        // [1]
+    uint64_t* k_full = bars + 1;    // [2]
+    uint64_t* k_empty = bars + 3;   // [2]
+    uint64_t* v_full = bars + 5;    // [2]
+    uint64_t* v_empty = bars + 7;   // [2]
+    uint64_t* s_full = bars + 9;    // [2] per tile
+    uint64_t* p_full = bars + 11;   // [2]
+    uint64_t* pv_full = bars + 13;  // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q0 = blockIdx.x * 256, h = blockIdx.y, b = blockIdx.z;
+    const int ntiles = (q0 + 128 < p.Lq) ? 2 : 1;
+    const int nkv = (p.Lk + 127) / 128;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&p.tmQ);
+        tma_prefetch_desc(&p.tmK);
+        tma_prefetch_desc(&p.tmV);
+    }
+    if (warp == 1 && lane == 0) {
+        mbar_init(q_full, 1);
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&k_full[s], 1);
+            mbar_init(&k_empty[s], 1);
+            mbar_init(&v_full[s], 1);
+            mbar_init(&v_empty[s], 1);
+            mbar_init(&s_full[s], 1);
+            mbar_init(&p_full[s], 4);
+            mbar_init(&pv_full[s], 1);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) {
+        tmem_alloc(tmem_slot, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    // TMEM columns: S tile t at [128 t, 128 t + 128), PV tile t at [256 + 64 t, +64)
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_expect_tx(q_full, (uint32_t)(ntiles * AT_TILE));
+            tma_load_3d(smem + FWD_SQ, &p.tmQ, q_full, h * 64, q0, b);
+            if (ntiles == 2) tma_load_3d(smem + FWD_SQ + AT_TILE, &p.tmQ, q_full, h * 64, q0 + 128, b);
+            for (int j = 0; j < nkv; ++j) {
+                const int s = j & 1;
+                const uint32_t ph = (uint32_t)((j >> 1) & 1);
+                mbar_wait(&k_empty[s], ph ^ 1);
+                mbar_expect_tx(&k_full[s], AT_TILE);
+                tma_load_3d(smem + FWD_SK + s * AT_TILE, &p.tmK, &k_full[s], h * 64, j * 128, b);
+                mbar_wait(&v_empty[s], ph ^ 1);
+                mbar_expect_tx(&v_full[s], AT_TILE);
+                tma_load_3d(smem + FWD_SV + s * AT_TILE, &p.tmV, &v_full[s], h * 64, j * 128, b);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc_qk = make_idesc_bf16(128, 128, 0, 0);
+            const uint32_t idesc_pv = make_idesc_bf16(128, 64, 0, 1);
+            const uint32_t sq = smem_u32(smem + FWD_SQ), sk = smem_u32(smem + FWD_SK), sv = smem_u32(smem + FWD_SV),
+                           sp = smem_u32(smem + FWD_SP);
+            auto issue_qk = [&](int t, int s) {
+                const uint64_t ad = desc_kmajor(sq + t * AT_TILE), bd = desc_kmajor(sk + s * AT_TILE);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    umma_bf16(tmem_base + (uint32_t)(t * 128), ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc_qk,
+                              (uint32_t)(k != 0));
+            };
+            mbar_wait(q_full, 0);
+            mbar_wait(&k_full[0], 0);
+            tc_fence_after();
+            for (int t = 0; t < ntiles; ++t) {
+                issue_qk(t, 0);
+                umma_commit(&s_full[t]);
+            }
+            umma_commit(&k_empty[0]);
+            for (int j = 0; j < nkv; ++j) {
+                const int s = j & 1;
+                const uint32_t ph = (uint32_t)((j >> 1) & 1);
+                const bool has_next = j + 1 < nkv;
+                const int s1 = (j + 1) & 1;
+                mbar_wait(&v_full[s], ph);
+                if (has_next) mbar_wait(&k_full[s1], (uint32_t)(((j + 1) >> 1) & 1));
+                for (int t = 0; t < ntiles; ++t) {
+                    mbar_wait(&p_full[t], (uint32_t)(j & 1));
+                    tc_fence_after();
+                    const uint64_t vd = desc_mnmajor(sv + s * AT_TILE, 8192);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const uint64_t ad = desc_kmajor(sp + t * 2 * AT_TILE + (k >> 2) * AT_TILE) + (uint64_t)((k & 3) * 2);
+                        umma_bf16(tmem_base + 256u + (uint32_t)(t * 64), ad, vd + (uint64_t)(k * 128), idesc_pv,
+                                  (uint32_t)(k != 0));
+                    }
+                    umma_commit(&pv_full[t]);
+                    if (has_next) {
+                        issue_qk(t, s1);
+                        umma_commit(&s_full[t]);
+                    }
+                }
+                umma_commit(&v_empty[s]);
+                if (has_next) umma_commit(&k_empty[s1]);
+            }
+        }
+    } else {
+        const int t = (warp - 2) >> 2;
+        if (t < ntiles) {
+            const int sub = warp & 3;
+            const int row = sub * 32 + lane;  // row within the 128-query tile == TMEM lane
+            const uint32_t lane_addr = (uint32_t)(sub * 32) << 16;
+            const uint32_t t_s = tmem_base + lane_addr + (uint32_t)(t * 128);
+            const uint32_t t_pv = tmem_base + lane_addr + 256u + (uint32_t)(t * 64);
+            uint8_t* prow = smem + FWD_SP + t * 2 * AT_TILE + row * 128;
+            const int sw = row & 7;
+            const float sl2 = p.scale_log2;
+            float O[64];
+#pragma unroll
+            for (int i = 0; i < 64; ++i) O[i] = 0.f;
+            float m = -INFINITY, l = 0.f;
+            for (int j = 0; j < nkv; ++j) {
+                mbar_wait(&s_full[t], (uint32_t)(j & 1));
+                tc_fence_after();
+                const int kv_valid = min(128, p.Lk - j * 128);
+                // pass 1: row maximum
+                float mx = -INFINITY;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    uint32_t r[32];
+                    tmem_ld32(t_s + (uint32_t)(c * 32), r);
+                    tmem_ld_wait();
+                    if (kv_valid == 128) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            if (c * 32 + i < kv_valid) mx = fmaxf(mx, __uint_as_float(r[i]));
+                    }
+                }
+                const float m_new = fmaxf(m, mx);
+                const float alpha = ex2_approx((m - m_new) * sl2);
+                const float msl = m_new * sl2;
+                // pass 2: probabilities -> bf16 -> swizzled smem, row sum
+                float rs = 0.f;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    uint32_t r[32];
+                    tmem_ld32(t_s + (uint32_t)(c * 32), r);
+                    tmem_ld_wait();
+                    float pe[32];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        float e = ex2_approx(fmaf(__uint_as_float(r[i]), sl2, -msl));
+                        if (kv_valid != 128 && c * 32 + i >= kv_valid) e = 0.f;
+                        pe[i] = e;
+                        rs += e;
+                    }
+#pragma unroll
+                    for (int q4 = 0; q4 < 4; ++q4) {
+                        uint4 u;
+                        u.x = pack_bf16(pe[q4 * 8 + 0], pe[q4 * 8 + 1]);
+                        u.y = pack_bf16(pe[q4 * 8 + 2], pe[q4 * 8 + 3]);
+                        u.z = pack_bf16(pe[q4 * 8 + 4], pe[q4 * 8 + 5]);
+                        u.w = pack_bf16(pe[q4 * 8 + 6], pe[q4 * 8 + 7]);
+                        const int cc = (c & 1) * 4 + q4;
+                        *reinterpret_cast<uint4*>(prow + (c >> 1) * AT_TILE + ((cc ^ sw) << 4)) = u;
+                    }
+                }
+                l = fmaf(l, alpha, rs);
+                m = m_new;
+                tc_fence_before();
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&p_full[t]);
+                // fold P V into the register accumulators
+                mbar_wait(&pv_full[t], (uint32_t)(j & 1));
+                tc_fence_after();
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    uint32_t r[32];
+                    tmem_ld32(t_pv + (uint32_t)(c * 32), r);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) O[c * 32 + i] = fmaf(O[c * 32 + i], alpha, __uint_as_float(r[i]));
+                }
+            }
+            const int q = q0 + t * 128 + row;
+            if (q < p.Lq) {
+                const float inv = 1.0f / l;
+                __nv_bfloat16* op = p.o + ((size_t)b * p.Lq + q) * p.ldo + h * 64;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    uint4 u;
+                    u.x = pack_bf16(O[c * 8 + 0] * inv, O[c * 8 + 1] * inv);
+                    u.y = pack_bf16(O[c * 8 + 2] * inv, O[c * 8 + 3] * inv);
+                    u.z = pack_bf16(O[c * 8 + 4] * inv, O[c * 8 + 5] * inv);
+                    u.w = pack_bf16(O[c * 8 + 6] * inv, O[c * 8 + 7] * inv);
+                    *reinterpret_cast<uint4*>(op + c * 8) = u;
+                }
+                p.lse[((size_t)b * p.heads + h) * p.Lq_pad + q] = fmaf(m, p.scale, __logf(l));
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// ================================================================================================
+// backward
+// ================================================================================================
+// delta[b,h,q] = sum_d O[q,d] dO[q,d];  lse2 = lse * log2(e)
+__global__ void attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ o, long long ldo, const __nv_bfloat16* __restrict__ dout,
+                                     long long lddo, const float* __restrict__ lse, int B, int heads, int Lq, int Lq_pad,
+                                     float* __restrict__ lse2, float* __restrict__ delta) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long)B * Lq * heads;
+    if (idx >= total) return;
+    const int h = (int)(idx % heads);
+    const long long bq = idx / heads;
+    const int q = (int)(bq % Lq);
+    const int b = (int)(bq / Lq);
+    const __nv_bfloat16* op = o + bq * ldo + h * 64;
+    const __nv_bfloat16* dp = dout + bq * lddo + h * 64;
+    float acc = 0.f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const uint4 a = *reinterpret_cast<const uint4*>(op + c * 8);
+        const uint4 d = *reinterpret_cast<const uint4*>(dp + c * 8);
+        const float2 a0 = unpack_bf16(a.x), a1 = unpack_bf16(a.y), a2 = unpack_bf16(a.z), a3 = unpack_bf16(a.w);
+        const float2 d0 = unpack_bf16(d.x), d1 = unpack_bf16(d.y), d2 = unpack_bf16(d.z), d3 = unpack_bf16(d.w);
+        acc += a0.x * d0.x + a0.y * d0.y + a1.x * d1.x + a1.y * d1.y + a2.x * d2.x + a2.y * d2.y + a3.x * d3.x + a3.y * d3.y;
+    }
+    const size_t oi = ((size_t)b * heads + h) * Lq_pad + q;
+    delta[oi] = acc;
+    lse2[oi] = lse[oi] * LOG2E;
+}
+
+// dq[b*Lq+q, 64h+d] = scale * acc[b,h,q/128, d/4, q%128, d%4]
+__global__ void attn_bwd_dq_convert_kernel(const float* __restrict__ acc, int B, int heads, int Lq, int nqt, float scale,
+                                           __nv_bfloat16* __restrict__ dq, long long lddq) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // one 8-wide d chunk per thread
+    const long long total = (long long)B * Lq * heads * 8;
+    if (idx >= total) return;
+    const int c8 = (int)(idx & 7);
+    long long r = idx >> 3;
+    const int h = (int)(r % heads);
+    r /= heads;
+    const int q = (int)(r % Lq);
+    const int b = (int)(r / Lq);
+    const size_t tile = (((size_t)b * heads + h) * nqt + (q >> 7)) * (16 * 128 * 4);
+    const float4 f0 = *reinterpret_cast<const float4*>(acc + tile + ((size_t)(2 * c8) * 128 + (q & 127)) * 4);
+    const float4 f1 = *reinterpret_cast<const float4*>(acc + tile + ((size_t)(2 * c8 + 1) * 128 + (q & 127)) * 4);
+    uint4 u;
+    u.x = pack_bf16(f0.x * scale, f0.y * scale);
+    u.y = pack_bf16(f0.z * scale, f0.w * scale);
+    u.z = pack_bf16(f1.x * scale, f1.y * scale);
+    u.w = pack_bf16(f1.z * scale, f1.w * scale);
+    *reinterpret_cast<uint4*>(dq + ((size_t)b * Lq + q) * lddq + h * 64 + c8 * 8) = u;
+}
+
+struct AttnBwdArgs {
+    CUtensorMap tmQ, tmK, tmV, tmdO;
+    int Lq, Lk, heads, Lq_pad;
+    float scale, scale_log2;
+    const float* lse2;   // [B, heads, Lq_pad]
+    const float* delta;  // [B, heads, Lq_pad]
+    float* dq_acc;       // [B, heads, Lq_pad/128, 16, 128, 4]
+    __nv_bfloat16* dk;
+    long long lddk;
+    __nv_bfloat16* dv;
+    long long lddv;
+};
+
+static constexpr int BWD_SK = 0;
+static constexpr int BWD_SV = AT_TILE;
+static constexpr int BWD_SQ = 2 * AT_TILE;    // 2 stages
+static constexpr int BWD_SDO = 4 * AT_TILE;   // 2 stages
+static constexpr int BWD_SPT = 6 * AT_TILE;   // [128 keys x 128 q] bf16
+static constexpr int BWD_SDS = 8 * AT_TILE;   // [128 keys x 128 q] bf16
+static constexpr int BWD_SDQ = 10 * AT_TILE;  // fp32 staging [16][128][4]
+static constexpr int BWD_SLSE = 12 * AT_TILE; // 2 stages x 128 floats
+static constexpr int BWD_SDEL = BWD_SLSE + 1024;
+static constexpr int BWD_BAR = BWD_SDEL + 1024;
+static constexpr int BWD_SMEM = BWD_BAR + 256 + 1024;
+static constexpr int BWD_THREADS = 320;
+// TMEM columns: S^T [0,128) dP^T [128,256) dV [256,320) dK [320,384) dQ [384,448)
+
+__global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_kernel(const __grid_constant__ AttnBwdArgs p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = align1024(smem_raw);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BWD_BAR);
+    uint64_t* kv_full = bars;        // [1]
+    uint64_t* qdo_full = bars + 1;   // [2]
+    uint64_t* qdo_empty = bars + 3;  // [2]
+    uint64_t* sdp_full = bars + 5;
+    uint64_t* sdp_empty = bars + 6;
+    uint64_t* pds_full = bars + 7;
+    uint64_t* pds_empty = bars + 8;
+    uint64_t* dq_full = bars + 9;
+    uint64_t* dq_empty = bars + 10;
+    uint64_t* acc_full = bars + 11;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int k0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
+    const int nq = (p.Lq + 127) / 128;
+    const int nqt = p.Lq_pad / 128;
+    const size_t bh = (size_t)b * p.heads + h;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&p.tmQ);
+        tma_prefetch_desc(&p.tmK);
+        tma_prefetch_desc(&p.tmV);
+        tma_prefetch_desc(&p.tmdO);
+    }
+    if (warp == 1 && lane == 0) {
+        mbar_init(kv_full, 1);
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&qdo_full[s], 1);
+            mbar_init(&qdo_empty[s], 1);
+        }
+        mbar_init(sdp_full, 1);
+        mbar_init(sdp_empty, 8);
+        mbar_init(pds_full, 8);
+        mbar_init(pds_empty, 1);
+        mbar_init(dq_full, 1);
+        mbar_init(dq_empty, 8);
+        mbar_init(acc_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 2) {
+        tmem_alloc(tmem_slot, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_expect_tx(kv_full, 2 * AT_TILE);
+            tma_load_3d(smem + BWD_SK, &p.tmK, kv_full, h * 64, k0, b);
+            tma_load_3d(smem + BWD_SV, &p.tmV, kv_full, h * 64, k0, b);
+            for (int i = 0; i < nq; ++i) {
+                const int s = i & 1;
+                const uint32_t ph = (uint32_t)((i >> 1) & 1);
+                mbar_wait(&qdo_empty[s], ph ^ 1);
+                mbar_expect_tx(&qdo_full[s], 2 * AT_TILE + 1024);
+                tma_load_3d(smem + BWD_SQ + s * AT_TILE, &p.tmQ, &qdo_full[s], h * 64, i * 128, b);
+                tma_load_3d(smem + BWD_SDO + s * AT_TILE, &p.tmdO, &qdo_full[s], h * 64, i * 128, b);
+                bulk_load_1d(smem + BWD_SLSE + s * 512, p.lse2 + bh * p.Lq_pad + (size_t)i * 128, 512, &qdo_full[s]);
+                bulk_load_1d(smem + BWD_SDEL + s * 512, p.delta + bh * p.Lq_pad + (size_t)i * 128, 512, &qdo_full[s]);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);   // S^T, dP^T: both operands K-major
+            const uint32_t idesc_kv = make_idesc_bf16(128, 64, 0, 1);   // dV, dK: A K-major (smem P^T/dS^T), B MN-major
+            const uint32_t idesc_dq = make_idesc_bf16(128, 64, 1, 1);   // dQ: A = dS^T read MN-major, B = K MN-major
+            const uint32_t sk = smem_u32(smem + BWD_SK), sv = smem_u32(smem + BWD_SV), sq = smem_u32(smem + BWD_SQ),
+                           sdo = smem_u32(smem + BWD_SDO), spt = smem_u32(smem + BWD_SPT), sds = smem_u32(smem + BWD_SDS);
+            mbar_wait(kv_full, 0);
+            for (int i = 0; i < nq; ++i) {
+                const int s = i & 1;
+                const uint32_t ph = (uint32_t)((i >> 1) & 1);
+                mbar_wait(&qdo_full[s], ph);
+                mbar_wait(sdp_empty, (uint32_t)((i & 1) ^ 1));
+                tc_fence_after();
+                {
+                    const uint64_t kd = desc_kmajor(sk), vd = desc_kmajor(sv);
+                    const uint64_t qd = desc_kmajor(sq + s * AT_TILE), dod = desc_kmajor(sdo + s * AT_TILE);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        umma_bf16(tmem_base + 0u, kd + (uint64_t)(k * 2), qd + (uint64_t)(k * 2), idesc_s, (uint32_t)(k != 0));
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        umma_bf16(tmem_base + 128u, vd + (uint64_t)(k * 2), dod + (uint64_t)(k * 2), idesc_s, (uint32_t)(k != 0));
+                }
+                umma_commit(sdp_full);
+                mbar_wait(pds_full, (uint32_t)(i & 1));
+                mbar_wait(dq_empty, (uint32_t)((i & 1) ^ 1));
+                tc_fence_after();
+                {
+                    const uint64_t dob = desc_mnmajor(sdo + s * AT_TILE, 8192);
+                    const uint64_t qb = desc_mnmajor(sq + s * AT_TILE, 8192);
+                    const uint64_t kb = desc_mnmajor(sk, 8192);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const uint64_t ad = desc_kmajor(spt + (k >> 2) * AT_TILE) + (uint64_t)((k & 3) * 2);
+                        umma_bf16(tmem_base + 256u, ad, dob + (uint64_t)(k * 128), idesc_kv, (uint32_t)((i | k) != 0));
+                    }
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const uint64_t ad = desc_kmajor(sds + (k >> 2) * AT_TILE) + (uint64_t)((k & 3) * 2);
+                        umma_bf16(tmem_base + 320u, ad, qb + (uint64_t)(k * 128), idesc_kv, (uint32_t)((i | k) != 0));
+                    }
+                    // dQ[q, d] = sum_key dS^T[key, q] K[key, d]: A is dS^T read as MN-major (M = q), two 64-query
+                    // blocks 16 KiB apart (LBO), 16 key rows = 2048 B per UMMA_K step
+                    const uint64_t ad = desc_mnmajor(sds, 16384);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                        umma_bf16(tmem_base + 384u, ad + (uint64_t)(k * 128), kb + (uint64_t)(k * 128), idesc_dq,
+                                  (uint32_t)(k != 0));
+                }
+                umma_commit(&qdo_empty[s]);
+                umma_commit(pds_empty);
+                umma_commit(dq_full);
+            }
+            umma_commit(acc_full);
+        }
+    } else {
+        const int cw = warp - 2;
+        const int sub = warp & 3;
+        const int half = cw >> 2;
+        const int row = sub * 32 + lane;
+        const int sw = row & 7;
+        const uint32_t lane_addr = (uint32_t)(sub * 32) << 16;
+        const float sl2 = p.scale_log2;
+        uint8_t* ptrow = smem + BWD_SPT + half * AT_TILE + row * 128;
+        uint8_t* dsrow = smem + BWD_SDS + half * AT_TILE + row * 128;
+        float* stage = reinterpret_cast<float*>(smem + BWD_SDQ);
+        for (int i = 0; i < nq; ++i) {
+            const int s = i & 1;
+            const uint32_t ph = (uint32_t)((i >> 1) & 1);
+            mbar_wait(&qdo_full[s], ph);  // lse2 / delta of this query tile are in smem
+            mbar_wait(sdp_full, (uint32_t)(i & 1));
+            tc_fence_after();
+            mbar_wait(pds_empty, (uint32_t)((i & 1) ^ 1));
+            const float* l2 = reinterpret_cast<const float*>(smem + BWD_SLSE + s * 512) + half * 64;
+            const float* dl = reinterpret_cast<const float*>(smem + BWD_SDEL + s * 512) + half * 64;
+            const int q_valid = p.Lq - i * 128 - half * 64;  // columns [0, q_valid) of this half are real queries
+#pragma unroll
+            for (int cc = 0; cc < 2; ++cc) {
+                uint32_t rs[32], rp[32];
+                tmem_ld32(tmem_base + lane_addr + (uint32_t)(half * 64 + cc * 32), rs);
+                tmem_ld32(tmem_base + lane_addr + 128u + (uint32_t)(half * 64 + cc * 32), rp);
+                tmem_ld_wait();
+                float pe[32], ds[32];
+#pragma unroll
+                for (int g = 0; g < 8; ++g) {
+                    const float4 lv = *reinterpret_cast<const float4*>(l2 + cc * 32 + g * 4);
+                    const float4 dv4 = *reinterpret_cast<const float4*>(dl + cc * 32 + g * 4);
+                    const float lvv[4] = {lv.x, lv.y, lv.z, lv.w};
+                    const float dvv[4] = {dv4.x, dv4.y, dv4.z, dv4.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int i2 = g * 4 + e;
+                        float pv = ex2_approx(fmaf(__uint_as_float(rs[i2]), sl2, -lvv[e]));
+                        float dsv = pv * (__uint_as_float(rp[i2]) - dvv[e]);
+                        if (cc * 32 + i2 >= q_valid) {
+                            pv = 0.f;
+                            dsv = 0.f;
+                        }
+                        pe[i2] = pv;
+                        ds[i2] = dsv;
+                    }
+                }
+#pragma unroll
+                for (int q4 = 0; q4 < 4; ++q4) {
+                    uint4 u, w;
+                    u.x = pack_bf16(pe[q4 * 8 + 0], pe[q4 * 8 + 1]);
+                    u.y = pack_bf16(pe[q4 * 8 + 2], pe[q4 * 8 + 3]);
+                    u.z = pack_bf16(pe[q4 * 8 + 4], pe[q4 * 8 + 5]);
+                    u.w = pack_bf16(pe[q4 * 8 + 6], pe[q4 * 8 + 7]);
+                    w.x = pack_bf16(ds[q4 * 8 + 0], ds[q4 * 8 + 1]);
+                    w.y = pack_bf16(ds[q4 * 8 + 2], ds[q4 * 8 + 3]);
+                    w.z = pack_bf16(ds[q4 * 8 + 4], ds[q4 * 8 + 5]);
+                    w.w = pack_bf16(ds[q4 * 8 + 6], ds[q4 * 8 + 7]);
+                    const int chunk = ((cc * 4 + q4) ^ sw) << 4;
+                    *reinterpret_cast<uint4*>(ptrow + chunk) = u;
+                    *reinterpret_cast<uint4*>(dsrow + chunk) = w;
+                }
+            }
+            tc_fence_before();
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(sdp_empty);
+                mbar_arrive(pds_full);
+            }
+            // ---- dQ tile: TMEM -> fp32 staging -> one bulk reduce-add into the scratch ----
+            mbar_wait(dq_full, (uint32_t)(i & 1));
+            tc_fence_after();
+            {
+                uint32_t r[32];
+                tmem_ld32(tmem_base + lane_addr + 384u + (uint32_t)(half * 32), r);
+                tmem_ld_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(dq_empty);
+                named_bar_sync(1, 256);  // previous tile's bulk reduce has finished reading the staging buffer
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    float4 f = make_float4(__uint_as_float(r[c * 4]), __uint_as_float(r[c * 4 + 1]),
+                                           __uint_as_float(r[c * 4 + 2]), __uint_as_float(r[c * 4 + 3]));
+                    *reinterpret_cast<float4*>(stage + ((half * 8 + c) * 128 + row) * 4) = f;
+                }
+                fence_proxy_async();
+                named_bar_sync(1, 256);
+                if (cw == 0 && lane == 0) {
+                    bulk_reduce_add_f32(p.dq_acc + (bh * nqt + i) * (size_t)(16 * 128 * 4), stage, 16 * 128 * 4 * 4);
+                    bulk_commit_group();
+                    bulk_wait_group_read0();
+                }
+            }
+        }
+        // ---- final dV / dK ----
+        mbar_wait(acc_full, 0);
+        tc_fence_after();
+        const int key = k0 + row;
+#pragma unroll
+        for (int which = 0; which < 2; ++which) {
+            uint32_t r[32];
+            tmem_ld32(tmem_base + lane_addr + 256u + (uint32_t)(which * 64 + half * 32), r);
+            tmem_ld_wait();
+            if (key < p.Lk) {
+                const float sc = which ? p.scale : 1.0f;
+                __nv_bfloat16* base = which ? p.dk + ((size_t)b * p.Lk + key) * p.lddk
+                                            : p.dv + ((size_t)b * p.Lk + key) * p.lddv;
+                __nv_bfloat16* op = base + h * 64 + half * 32;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    uint4 u;
+                    u.x = pack_bf16(__uint_as_float(r[c * 8 + 0]) * sc, __uint_as_float(r[c * 8 + 1]) * sc);
+                    u.y = pack_bf16(__uint_as_float(r[c * 8 + 2]) * sc, __uint_as_float(r[c * 8 + 3]) * sc);
+                    u.z = pack_bf16(__uint_as_float(r[c * 8 + 4]) * sc, __uint_as_float(r[c * 8 + 5]) * sc);
+                    u.w = pack_bf16(__uint_as_float(r[c * 8 + 6]) * sc, __uint_as_float(r[c * 8 + 7]) * sc);
+                    *reinterpret_cast<uint4*>(op + c * 8) = u;
+                }
+            }
+        }
+        if (cw == 0 && lane == 0) bulk_wait_group0();  // all dQ reductions have landed before the kernel ends
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+static int make_head_map(CUtensorMap* tm, const void* base, int heads, int L, int B, long long ld, const char* what) {
+    if (ld % 8 != 0 || ld < (long long)heads * 64) {
+        set_error("uwu_attn: leading dimension %lld of %s must be a multiple of 8 and >= heads*64", ld, what);
+        return UWU_ERR_INVALID;
+    }
+    uint64_t dims[3] = {(uint64_t)heads * 64, (uint64_t)L, (uint64_t)B};
+    uint64_t str[2] = {(uint64_t)ld * 2, (uint64_t)ld * 2 * (uint64_t)L};
+    uint32_t box[3] = {64, 128, 1};
+    return encode_tmap_bf16(tm, base, 3, dims, str, box, 1);
+}
+
+}  // namespace uwu
+
+using namespace uwu;
+
+static int attn_check(int32_t B, int32_t heads, int32_t Lq, int32_t Lk, int32_t head_dim) {
+    if (head_dim != 64) {
+        set_error("uwu_attn: head_dim %d unsupported (this build has the d=64 kernels only)", head_dim);
+        return UWU_ERR_UNSUPPORTED;
+    }
+    UWU_CHECK_ARG(B > 0 && heads > 0 && Lq > 0 && Lk > 0, "uwu_attn: bad shape B=%d heads=%d Lq=%d Lk=%d", B, heads, Lq, Lk);
+    UWU_CHECK_ARG(B <= 65535 && heads <= 65535, "uwu_attn: batch/heads exceed grid limits");
+    return UWU_OK;
+}
+
+extern "C" int64_t uwu_attn_lse_floats(int32_t B, int32_t heads, int32_t Lq) {
+    if (B <= 0 || heads <= 0 || Lq <= 0) return 0;
+    return (int64_t)B * heads * ((Lq + 127) / 128 * 128);
+}
+
+extern "C" int uwu_attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int32_t B, int32_t heads,
+                            int32_t Lq, int32_t Lk, int32_t head_dim, int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo,
+                            float scale, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    if (int rc = attn_check(B, heads, Lq, Lk, head_dim)) return rc;
+    UWU_CHECK_ARG(q && k && v && o && lse, "uwu_attn_fwd: null pointer");
+    UWU_CHECK_ARG(ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(o) & 15) == 0, "uwu_attn_fwd: output must be 16-byte aligned");
+    static thread_local AttnFwdArgs a;
+    if (int rc = make_head_map(&a.tmQ, q, heads, Lq, B, ldq, "q")) return rc;
+    if (int rc = make_head_map(&a.tmK, k, heads, Lk, B, ldk, "k")) return rc;
+    if (int rc = make_head_map(&a.tmV, v, heads, Lk, B, ldv, "v")) return rc;
+    a.Lq = Lq; a.Lk = Lk; a.heads = heads; a.Lq_pad = (Lq + 127) / 128 * 128;
+    a.scale = scale; a.scale_log2 = scale * LOG2E;
+    a.o = reinterpret_cast<__nv_bfloat16*>(o); a.ldo = ldo; a.lse = lse;
+    static bool attr_set = false;
+    if (!attr_set) {
+        UWU_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM));
+        attr_set = true;
+    }
+    dim3 grid((Lq + 255) / 256, heads, B);
+    attn_fwd_kernel<<<grid, FWD_THREADS, FWD_SMEM, stream>>>(a);
+    UWU_CHECK_LAUNCH();
+    return UWU_OK;
+}
+
+extern "C" int64_t uwu_attn_bwd_workspace_floats(int32_t B, int32_t heads, int32_t Lq) {
+    if (B <= 0 || heads <= 0 || Lq <= 0) return 0;
+    const int64_t rows = (int64_t)B * heads * ((Lq + 127) / 128 * 128);
+    return rows * 2 + rows * 64;  // lse2, delta, dq scratch
+}
+
+extern "C" int uwu_attn_bwd(const void* q, const void* k, const void* v, const void* o, const void* dout, const float* lse,
+                            void* dq, void* dk, void* dv, int32_t B, int32_t heads, int32_t Lq, int32_t Lk,
+                            int32_t head_dim, int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo, int64_t lddo,
+                            int64_t lddq, int64_t lddk, int64_t lddv, float scale, float* workspace, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    if (int rc = attn_check(B, heads, Lq, Lk, head_dim)) return rc;
+    UWU_CHECK_ARG(q && k && v && o && dout && lse && dq && dk && dv && workspace, "uwu_attn_bwd: null pointer");
+    UWU_CHECK_ARG(ldo % 8 == 0 && lddo % 8 == 0 && lddq % 8 == 0 && lddk % 8 == 0 && lddv % 8 == 0,
+                  "uwu_attn_bwd: leading dimensions must be multiples of 8");
+    UWU_CHECK_ARG(((reinterpret_cast<uintptr_t>(o) | reinterpret_cast<uintptr_t>(dout) | reinterpret_cast<uintptr_t>(dq) |
+                    reinterpret_cast<uintptr_t>(dk) | reinterpret_cast<uintptr_t>(dv) |
+                    reinterpret_cast<uintptr_t>(workspace)) & 15) == 0,
+                  "uwu_attn_bwd: pointers must be 16-byte aligned");
+    const int Lq_pad = (Lq + 127) / 128 * 128;
+    const int64_t rows = (int64_t)B * heads * Lq_pad;
+    float* lse2 = workspace;
+    float* delta = workspace + rows;
+    float* dq_acc = workspace + 2 * rows;
+    static thread_local AttnBwdArgs a;
+    if (int rc = make_head_map(&a.tmQ, q, heads, Lq, B, ldq, "q")) return rc;
+    if (int rc = make_head_map(&a.tmK, k, heads, Lk, B, ldk, "k")) return rc;
+    if (int rc = make_head_map(&a.tmV, v, heads, Lk, B, ldv, "v")) return rc;
+    if (int rc = make_head_map(&a.tmdO, dout, heads, Lq, B, lddo, "dout")) return rc;
+    a.Lq = Lq; a.Lk = Lk; a.heads = heads; a.Lq_pad = Lq_pad;
+    a.scale = scale; a.scale_log2 = scale * LOG2E;
+    a.lse2 = lse2; a.delta = delta; a.dq_acc = dq_acc;
+    a.dk = reinterpret_cast<__nv_bfloat16*>(dk); a.lddk = lddk;
+    a.dv = reinterpret_cast<__nv_bfloat16*>(dv); a.lddv = lddv;
+    UWU_CHECK_CUDA(cudaMemsetAsync(workspace, 0, (size_t)(rows * 66) * sizeof(float), stream));
+    {
+        const long long total = (long long)B * Lq * heads;
+        attn_bwd_prep_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(
+            reinterpret_cast<const __nv_bfloat16*>(o), ldo, reinterpret_cast<const __nv_bfloat16*>(dout), lddo, lse, B, heads,
+            Lq, Lq_pad, lse2, delta);
+        UWU_CHECK_LAUNCH();
+    }
+    static bool attr_set = false;
+    if (!attr_set) {
+        UWU_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM));
+        attr_set = true;
+    }
+    dim3 grid((Lk + 127) / 128, heads, B);
+    attn_bwd_kernel<<<grid, BWD_THREADS, BWD_SMEM, stream>>>(a);
+    UWU_CHECK_LAUNCH();
+    {
+        const long long total = (long long)B * Lq * heads * 8;
+        attn_bwd_dq_convert_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(
+            dq_acc, B, heads, Lq, Lq_pad / 128, scale, reinterpret_cast<__nv_bfloat16*>(dq), lddq);
+        UWU_CHECK_LAUNCH();
+    }
+    return UWU_OK;
+}

@@ -106,6 +106,32 @@ UWU_DEVINL void tma_load_4d(void* smem_dst, const CUtensorMap* m, uint64_t* bar,
         : "memory");
 }
 
+// 1-D bulk copy global -> shared, completion on an mbarrier (bytes multiple of 16, 16-byte aligned)
+UWU_DEVINL void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+// 1-D bulk reduction shared -> global: gdst[i] += smem[i] (fp32), tracked by the bulk async-group
+UWU_DEVINL void bulk_reduce_add_f32(void* gdst, const void* smem_src, uint32_t bytes) {
+    asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(
+                     reinterpret_cast<uint64_t>(gdst)),
+                 "r"(smem_u32(smem_src)), "r"(bytes)
+                 : "memory");
+}
+UWU_DEVINL void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+UWU_DEVINL void bulk_wait_group_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+UWU_DEVINL void bulk_wait_group0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+UWU_DEVINL void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+UWU_DEVINL float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 // ----------------------------------------------------------------------------------------------
 // tcgen05 / TMEM
 // ----------------------------------------------------------------------------------------------

@@ -188,3 +188,181 @@ def wmse_bwd(pred: torch.Tensor, target: torch.Tensor, w: Optional[torch.Tensor]
     check(lib().uwu_wmse_bwd(_ptr(pred), _DT[pred.dtype], _ptr(target), _DT[target.dtype], B, n_per, _ptr(w), _ptr(grad),
                              grad_scale, _ptr(dpred), _DT[out_dtype], _stream()), "uwu_wmse_bwd")
     return dpred
+
+
+# --------------------------------------------------------------------------------------------------
+# attention
+# --------------------------------------------------------------------------------------------------
+_ws_cache: dict = {}
+
+
+def _workspace(nfloats: int, device, tag: str = "ws") -> torch.Tensor:
+    """Grow-only fp32 scratch per (device, tag); kernels on one stream serialise their use of it."""
+    key = (str(device), tag)
+    buf = _ws_cache.get(key)
+    if buf is None or buf.numel() < nfloats:
+        buf = torch.empty((max(nfloats, 1),), device=device, dtype=torch.float32)
+        _ws_cache[key] = buf
+    return buf
+
+
+def attn_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, B: int, heads: int, Lq: int, Lk: int,
+             scale: Optional[float] = None, head_dim: int = 64, out: Optional[torch.Tensor] = None):
+    """q: [B*Lq, >=heads*64] bf16 (may be a column-slice view of a fused QKV buffer), k/v: [B*Lk, ...].
+    Returns (o [B*Lq, heads*64], lse [B, heads, Lq_pad])."""
+    _req_cuda(q, k, v)
+    assert q.dtype == k.dtype == v.dtype == torch.bfloat16
+    assert q.stride(1) == 1 and k.stride(1) == 1 and v.stride(1) == 1
+    scale = head_dim ** -0.5 if scale is None else scale
+    if out is None:
+        out = torch.empty((B * Lq, heads * head_dim), device=q.device, dtype=torch.bfloat16)
+    lse = torch.empty((int(lib().uwu_attn_lse_floats(B, heads, Lq)),), device=q.device, dtype=torch.float32)
+    check(lib().uwu_attn_fwd(_ptr(q), _ptr(k), _ptr(v), _ptr(out), _ptr(lse), B, heads, Lq, Lk, head_dim, q.stride(0),
+                             k.stride(0), v.stride(0), out.stride(0), scale, _stream()), "uwu_attn_fwd")
+    return out, lse
+
+
+def attn_bwd(q, k, v, o, dout, lse, B: int, heads: int, Lq: int, Lk: int, scale: Optional[float] = None,
+             head_dim: int = 64, dq=None, dk=None, dv=None):
+    _req_cuda(q, k, v, o, dout, lse)
+    scale = head_dim ** -0.5 if scale is None else scale
+    C = heads * head_dim
+    if dq is None:
+        dq = torch.empty((B * Lq, C), device=q.device, dtype=torch.bfloat16)
+    if dk is None:
+        dk = torch.empty((B * Lk, C), device=q.device, dtype=torch.bfloat16)
+    if dv is None:
+        dv = torch.empty((B * Lk, C), device=q.device, dtype=torch.bfloat16)
+    ws = _workspace(int(lib().uwu_attn_bwd_workspace_floats(B, heads, Lq)), q.device, "attn")
+    check(lib().uwu_attn_bwd(_ptr(q), _ptr(k), _ptr(v), _ptr(o), _ptr(dout), _ptr(lse), _ptr(dq), _ptr(dk), _ptr(dv), B,
+                             heads, Lq, Lk, head_dim, q.stride(0), k.stride(0), v.stride(0), o.stride(0), dout.stride(0),
+                             dq.stride(0), dk.stride(0), dv.stride(0), scale, _ptr(ws), _stream()), "uwu_attn_bwd")
+    return dq, dk, dv
+
+
+# --------------------------------------------------------------------------------------------------
+# normalisation / elementwise glue (channels-last bf16)
+# --------------------------------------------------------------------------------------------------
+def groupnorm_fwd(x: torch.Tensor, N: int, HW: int, C: int, G: int, eps: float, gamma: torch.Tensor, beta: torch.Tensor,
+                  silu: bool):
+    """x: [N*HW, C] bf16 -> (y, stats[N,G,2])."""
+    _req_cuda(x, gamma, beta)
+    assert x.dtype == torch.bfloat16 and x.is_contiguous() and gamma.dtype == torch.float32
+    y = torch.empty_like(x)
+    stats = torch.empty((N, G, 2), device=x.device, dtype=torch.float32)
+    ws = _workspace(int(lib().uwu_groupnorm_workspace_floats(N, HW, C, G)), x.device)
+    check(lib().uwu_groupnorm_fwd(_ptr(x), N, HW, C, G, eps, _ptr(gamma), _ptr(beta), int(silu), _ptr(y), _ptr(stats),
+                                  _ptr(ws), _stream()), "uwu_groupnorm_fwd")
+    return y, stats
+
+
+def groupnorm_bwd(x, dy, N, HW, C, G, gamma, beta, stats, silu: bool, dres=None, dgamma=None, dbeta=None):
+    _req_cuda(x, dy, dres, dgamma, dbeta)
+    assert dy.is_contiguous() and (dres is None or dres.is_contiguous())
+    dx = torch.empty_like(x)
+    ws = _workspace(int(lib().uwu_groupnorm_workspace_floats(N, HW, C, G)), x.device)
+    check(lib().uwu_groupnorm_bwd(_ptr(x), _ptr(dy), N, HW, C, G, _ptr(gamma), _ptr(beta), _ptr(stats), int(silu),
+                                  _ptr(dres), _ptr(dx), _ptr(dgamma), _ptr(dbeta), _ptr(ws), _stream()),
+          "uwu_groupnorm_bwd")
+    return dx
+
+
+def layernorm_fwd(x: torch.Tensor, gamma, beta, eps: float = 1e-5, mod_scale=None, mod_shift=None, rows_per_mod: int = 1,
+                  want_stats: bool = True):
+    _req_cuda(x, gamma, beta, mod_scale, mod_shift)
+    assert x.dtype == torch.bfloat16 and x.is_contiguous()
+    M, C = x.shape
+    y = torch.empty_like(x)
+    stats = torch.empty((M, 2), device=x.device, dtype=torch.float32) if want_stats else None
+    check(lib().uwu_layernorm_fwd(_ptr(x), M, C, eps, _ptr(gamma), _ptr(beta), _ptr(mod_scale), _ptr(mod_shift),
+                                  rows_per_mod, _ptr(y), _ptr(stats), _stream()), "uwu_layernorm_fwd")
+    return y, stats
+
+
+def layernorm_bwd(x, dy, gamma, stats, dres=None, dgamma=None, dbeta=None, accumulate: bool = True):
+    _req_cuda(x, dy, dres, dgamma, dbeta)
+    assert dy.is_contiguous() and (dres is None or dres.is_contiguous())
+    M, C = x.shape
+    dx = torch.empty_like(x)
+    ws = None
+    if dgamma is not None or dbeta is not None:
+        ws = _workspace(int(lib().uwu_layernorm_bwd_workspace_floats(M, C)), x.device)
+    check(lib().uwu_layernorm_bwd(_ptr(x), _ptr(dy), M, C, _ptr(gamma), _ptr(stats), _ptr(dres), _ptr(dx), _ptr(dgamma),
+                                  _ptr(dbeta), int(accumulate), _ptr(ws), _stream()), "uwu_layernorm_bwd")
+    return dx
+
+
+def geglu_fwd(x: torch.Tensor) -> torch.Tensor:
+    _req_cuda(x)
+    assert x.dtype == torch.bfloat16 and x.is_contiguous()
+    M, F2 = x.shape
+    out = torch.empty((M, F2 // 2), device=x.device, dtype=torch.bfloat16)
+    check(lib().uwu_geglu_fwd(_ptr(x), M, F2 // 2, _ptr(out), _stream()), "uwu_geglu_fwd")
+    return out
+
+
+def geglu_bwd(x: torch.Tensor, dout: torch.Tensor) -> torch.Tensor:
+    _req_cuda(x, dout)
+    assert dout.is_contiguous()
+    M, F2 = x.shape
+    din = torch.empty_like(x)
+    check(lib().uwu_geglu_bwd(_ptr(x), _ptr(dout), M, F2 // 2, _ptr(din), _stream()), "uwu_geglu_bwd")
+    return din
+
+
+EW_SILU, EW_SILU_BWD, EW_ADD, EW_COPY = 0, 1, 2, 3
+
+
+def elementwise(x: torch.Tensor, a: Optional[torch.Tensor], mode: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _req_cuda(x, a, out)
+    assert x.dtype == torch.bfloat16 and x.is_contiguous() and (a is None or (a.is_contiguous() and a.dtype == x.dtype))
+    y = torch.empty_like(x) if out is None else out
+    check(lib().uwu_elementwise(_ptr(x), _ptr(a), x.numel(), mode, _ptr(y), _stream()), "uwu_elementwise")
+    return y
+
+
+def nchw_to_nhwc(x: torch.Tensor, cpad: int) -> torch.Tensor:
+    """[N,C,H,W] fp32/bf16 -> [N*H*W, cpad] bf16 (zero-padded channels)."""
+    _req_cuda(x)
+    x = x.contiguous()
+    N, Cc, H, W = x.shape
+    out = torch.empty((N * H * W, cpad), device=x.device, dtype=torch.bfloat16)
+    check(lib().uwu_nchw_to_nhwc(_ptr(x), _DT[x.dtype], N, Cc, H * W, cpad, _ptr(out), _stream()), "uwu_nchw_to_nhwc")
+    return out
+
+
+def nhwc_to_nchw(x: torch.Tensor, N: int, Cc: int, H: int, W: int) -> torch.Tensor:
+    """[N*H*W, ld] bf16/fp32 (first Cc columns) -> [N,Cc,H,W] fp32."""
+    _req_cuda(x)
+    out = torch.empty((N, Cc, H, W), device=x.device, dtype=torch.float32)
+    check(lib().uwu_nhwc_to_nchw(_ptr(x), _DT[x.dtype], N, Cc, H * W, x.stride(0), _ptr(out), _stream()), "uwu_nhwc_to_nchw")
+    return out
+
+
+def upsample2x(x: torch.Tensor, N: int, H: int, W: int, C: int, backward: bool = False) -> torch.Tensor:
+    """forward: [N*H*W, C] -> [N*2H*2W, C]; backward: dy [N*2H*2W, C] -> dx [N*H*W, C] (H, W = low-res size)."""
+    _req_cuda(x)
+    assert x.is_contiguous()
+    rows = N * H * W * (1 if backward else 4)
+    y = torch.empty((rows, C), device=x.device, dtype=torch.bfloat16)
+    check(lib().uwu_upsample2x(_ptr(x), N, H, W, C, int(backward), _ptr(y), _stream()), "uwu_upsample2x")
+    return y
+
+
+def phase_split2(x: torch.Tensor, N: int, H: int, W: int, C: int, inverse: bool = False) -> torch.Tensor:
+    _req_cuda(x)
+    assert x.is_contiguous()
+    y = torch.empty_like(x)
+    check(lib().uwu_phase_split2(_ptr(x), N, H, W, C, int(inverse), _ptr(y), _stream()), "uwu_phase_split2")
+    return y
+
+
+def colsum(x: torch.Tensor, out: Optional[torch.Tensor] = None, accumulate: bool = False) -> torch.Tensor:
+    _req_cuda(x, out)
+    M, C = x.shape
+    if out is None:
+        out = torch.empty((C,), device=x.device, dtype=torch.float32)
+        accumulate = False
+    ws = _workspace(int(lib().uwu_colsum_workspace_floats(M, C)), x.device)
+    check(lib().uwu_colsum_bf16(_ptr(x), M, C, x.stride(0), int(accumulate), _ptr(out), _ptr(ws), _stream()), "uwu_colsum_bf16")
+    return out
