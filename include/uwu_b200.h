@@ -195,6 +195,40 @@ int64_t uwu_colsum_workspace_floats(int64_t M, int32_t C);
 int uwu_colsum_bf16(const void* x, int64_t M, int32_t C, int64_t ld, int32_t accumulate, float* out, float* workspace,
                     void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * LyCORIS adapters (LoRA / LoKr full_matrix / norm deltas) and the optimizer.
+ *   replaces lycoris-lora's patched forward `F.linear(x, W + dW * multiplier)` and its autograd backward through
+ *   kron / up@down (wrapper applied at src/duwu/trainer/trainer.py:148-169; preset configs/lycoris/sdxl-diffusers.toml),
+ *   torch.optim.AdamW (src/duwu/trainer/trainer.py:52-74; configs/demo_training_lycoris.yaml:48-55) and Lightning's
+ *   gradient_clip_val (configs/demo_training_lycoris.yaml:13).
+ *   Shape bookkeeping is checked exactly: (out_l*out_k, in_m*in_n) must equal (N, K).
+ * ------------------------------------------------------------------------------------------------ */
+/* dst[N,K] bf16 = W + kron(w1[out_l,in_m], w2[out_k,in_n]) * multiplier   (w1 == NULL: plain fp32 -> bf16 cast) */
+int uwu_fold_lokr(const float* W, const float* w1, const float* w2, int32_t N, int32_t K, int32_t out_l, int32_t out_k,
+                  int32_t in_m, int32_t in_n, float multiplier, void* dst_bf16, void* stream);
+/* dst[N,K] bf16 = W + (up[N,r] @ down[r,K]) * scale */
+int uwu_fold_lora(const float* W, const float* up, const float* down, int32_t N, int32_t K, int32_t r, float scale,
+                  void* dst_bf16, void* stream);
+/* out = a + alpha * b (fp32; effective norm affine = gamma + w_norm * multiplier) */
+int uwu_axpy_f32(const float* a, const float* b, float alpha, int32_t n, float* out, void* stream);
+/* adapter gradients from G = dY^T X (fp32 [N, ldg]); dw1/dw2 (dup/ddown) are ACCUMULATED into */
+int uwu_lokr_grad(const float* G, int64_t ldg, const float* w1, const float* w2, int32_t out_l, int32_t out_k, int32_t in_m,
+                  int32_t in_n, float multiplier, float* dw1, float* dw2, void* stream);
+int uwu_lora_grad(const float* G, int64_t ldg, const float* up, const float* down, int32_t N, int32_t K, int32_t r, float scale,
+                  float* dup, float* ddown, void* stream);
+/* multi-tensor global grad norm: out2 = {||g||_2, min(1, max_norm/(norm+1e-6))}; tables are DEVICE arrays
+ * (pointers as uint64, numels, and a chunk table (tensor index, chunk index) of n_chunks entries) */
+int uwu_mt_gradnorm(const uint64_t* g_ptrs, const int64_t* numels, const int32_t* chunk_tensor, const int32_t* chunk_index,
+                    int32_t n_chunks, int32_t chunk_elems, float max_norm, float* partial_ws, float* out2, void* stream);
+/* torch.optim.AdamW step (decoupled weight decay, bias correction by `step`), gradients scaled by norm_clip[1] if given */
+int uwu_mt_adamw(const uint64_t* p_ptrs, const uint64_t* g_ptrs, const uint64_t* m_ptrs, const uint64_t* v_ptrs,
+                 const int64_t* numels, const int32_t* chunk_tensor, const int32_t* chunk_index, int32_t n_chunks,
+                 int32_t chunk_elems, float lr, float beta1, float beta2, float eps, float weight_decay, int64_t step,
+                 const float* norm_clip, void* stream);
+/* strided 2-D copy with cast to bf16 (skip-connection concat, conditioning staging) */
+int uwu_copy2d_bf16(const void* src, int32_t src_dtype, int64_t lds, void* dst_bf16, int64_t ldd, int64_t rows, int32_t cols,
+                    void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -366,3 +366,69 @@ def colsum(x: torch.Tensor, out: Optional[torch.Tensor] = None, accumulate: bool
     ws = _workspace(int(lib().uwu_colsum_workspace_floats(M, C)), x.device)
     check(lib().uwu_colsum_bf16(_ptr(x), M, C, x.stride(0), int(accumulate), _ptr(out), _ptr(ws), _stream()), "uwu_colsum_bf16")
     return out
+
+
+# --------------------------------------------------------------------------------------------------
+# adapters / optimizer / copies
+# --------------------------------------------------------------------------------------------------
+def fold_lokr(W: torch.Tensor, w1: Optional[torch.Tensor], w2: Optional[torch.Tensor], dst: torch.Tensor,
+              multiplier: float = 1.0) -> torch.Tensor:
+    """dst (bf16 [N,K], may be a row-slice of a fused weight buffer) = W + kron(w1, w2) * multiplier; w1 None = cast."""
+    _req_cuda(W, w1, w2, dst)
+    assert W.dtype == torch.float32 and W.is_contiguous() and dst.dtype == torch.bfloat16 and dst.is_contiguous()
+    N, K = W.shape
+    if w1 is not None:
+        assert w1.is_contiguous() and w2.is_contiguous() and w1.dtype == w2.dtype == torch.float32
+        (ol, im), (ok, inn) = w1.shape, w2.shape
+    else:
+        ol = im = ok = inn = 0
+    check(lib().uwu_fold_lokr(_ptr(W), _ptr(w1), _ptr(w2), N, K, ol, ok, im, inn, multiplier, _ptr(dst), _stream()),
+          "uwu_fold_lokr")
+    return dst
+
+
+def fold_lora(W: torch.Tensor, up: torch.Tensor, down: torch.Tensor, scale: float, dst: torch.Tensor) -> torch.Tensor:
+    _req_cuda(W, up, down, dst)
+    assert W.is_contiguous() and up.is_contiguous() and down.is_contiguous() and dst.is_contiguous()
+    N, K = W.shape
+    r = down.shape[0]
+    assert up.shape == (N, r) and down.shape == (r, K)
+    check(lib().uwu_fold_lora(_ptr(W), _ptr(up), _ptr(down), N, K, r, scale, _ptr(dst), _stream()), "uwu_fold_lora")
+    return dst
+
+
+def axpy_f32(a: torch.Tensor, b: torch.Tensor, alpha: float, out: torch.Tensor) -> torch.Tensor:
+    _req_cuda(a, b, out)
+    check(lib().uwu_axpy_f32(_ptr(a), _ptr(b), alpha, a.numel(), _ptr(out), _stream()), "uwu_axpy_f32")
+    return out
+
+
+def lokr_grad(G: torch.Tensor, w1: torch.Tensor, w2: torch.Tensor, dw1: torch.Tensor, dw2: torch.Tensor,
+              multiplier: float = 1.0) -> None:
+    _req_cuda(G, w1, w2, dw1, dw2)
+    (ol, im), (ok, inn) = w1.shape, w2.shape
+    assert G.shape == (ol * ok, im * inn) and G.dtype == torch.float32 and G.stride(1) == 1
+    check(lib().uwu_lokr_grad(_ptr(G), G.stride(0), _ptr(w1), _ptr(w2), ol, ok, im, inn, multiplier, _ptr(dw1), _ptr(dw2),
+                              _stream()), "uwu_lokr_grad")
+
+
+def lora_grad(G: torch.Tensor, up: torch.Tensor, down: torch.Tensor, scale: float, dup: torch.Tensor, ddown: torch.Tensor) -> None:
+    _req_cuda(G, up, down, dup, ddown)
+    N, K = G.shape
+    r = down.shape[0]
+    check(lib().uwu_lora_grad(_ptr(G), G.stride(0), _ptr(up), _ptr(down), N, K, r, scale, _ptr(dup), _ptr(ddown), _stream()),
+          "uwu_lora_grad")
+
+
+def copy2d(src: torch.Tensor, dst: torch.Tensor) -> torch.Tensor:
+    """dst[r, c] = bf16(src[r, c]) for 2-D (possibly column-sliced) views."""
+    _req_cuda(src, dst)
+    if src.dtype not in _DT:
+        src = src.float()
+    if src.stride(1) != 1:
+        src = src.contiguous()
+    assert src.dim() == 2 and dst.dim() == 2 and src.shape == dst.shape and dst.stride(1) == 1
+    assert dst.dtype == torch.bfloat16
+    check(lib().uwu_copy2d_bf16(_ptr(src), _DT[src.dtype], src.stride(0), _ptr(dst), dst.stride(0), src.shape[0], src.shape[1],
+                                _stream()), "uwu_copy2d_bf16")
+    return dst
