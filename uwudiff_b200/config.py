@@ -1,0 +1,186 @@
+"""Config -> object instantiation with the reference's conventions, without hydra / omegaconf (not installable here).
+
+Mirrors `duwu.utils.instantiate_any` / `instantiate_class` (src/duwu/utils/__init__.py:17-50), `duwu.loader.load_any`,
+`prepare_model`, `load_all` (src/duwu/loader.py:13-79) and the runner's config merge (test_scripts/test_train.py:19-33):
+  * Hydra form `{_target_: dotted.path, _partial_: bool, _recursive_: bool, **kwargs}` (nested dicts with `_target_`
+    are instantiated first unless `_recursive_: false`),
+  * custom form `{class: dotted.path, factory: name, args: [...], kwargs: {...}}`, or a bare dotted string,
+  * `_load_config_` -> ModelLoadingConfig(ckpt_path, state_dict_key, state_dict_prefix, precision, device, to_compile, to_freeze).
+Dotted targets that name the reference package or its un-vendored dependencies are routed to this package
+(`duwu.*` -> `uwudiff_b200.*`, `diffusers.EulerDiscreteScheduler` -> the embedded scheduler duck type, ...).
+"""
+from __future__ import annotations
+
+import copy
+import functools
+import importlib
+from dataclasses import dataclass
+from typing import Any, Optional
+
+import torch
+import torch.nn as nn
+
+# reference dotted path -> drop-in provided here
+TARGET_ALIASES = {
+    "duwu.trainer.DMTrainer": "uwudiff_b200.trainer.DMTrainer",
+    "duwu.loss.DiffusionLoss": "uwudiff_b200.loss.DiffusionLoss",
+    "duwu.data.TrainDataModule": "uwudiff_b200.data.TrainDataModule",
+    "duwu.data.DummyDataset": "uwudiff_b200.data.DummyDataset",
+    "duwu.modules.unet_patch.UNet2DFromScratch": "uwudiff_b200.unet.UNet2DFromScratch",
+    "duwu.modules.text_encoders.ConcatTextEncoders": "uwudiff_b200.data.SyntheticTextEncoders",
+    "diffusers.EulerDiscreteScheduler": "uwudiff_b200.scheduler.EulerDiscreteScheduler",
+    "diffusers.AutoencoderKL": "uwudiff_b200.data.SyntheticVAE",
+    "torch.optim.AdamW": "uwudiff_b200.optim.FusedAdamW",
+    "lycoris.LycorisNetwork": "uwudiff_b200.lycoris.LycorisNetwork",
+    "lycoris.create_lycoris": "uwudiff_b200.lycoris.create_lycoris",
+}
+
+
+def get_obj_from_str(string: str):
+    """Resolve `pkg.mod.Class[.method]`, longest importable module prefix first (Hydra's `_locate` behaviour)."""
+    for ref, ours in TARGET_ALIASES.items():
+        if string == ref or string.startswith(ref + "."):
+            string = ours + string[len(ref):]
+            break
+    parts = string.split(".")
+    for i in range(len(parts) - 1, 0, -1):
+        try:
+            obj = importlib.import_module(".".join(parts[:i]))
+        except ImportError:
+            continue
+        try:
+            for p in parts[i:]:
+                obj = getattr(obj, p)
+        except AttributeError:
+            continue
+        return obj
+    raise ImportError(f"cannot locate '{string}'")
+
+
+def _hydra_instantiate(cfg: dict):
+    cfg = dict(cfg)
+    target = cfg.pop("_target_")
+    partial = cfg.pop("_partial_", False)
+    recursive = cfg.pop("_recursive_", True)
+    cfg.pop("_convert_", None)
+    args = cfg.pop("_args_", [])
+    fn = get_obj_from_str(target) if isinstance(target, str) else target
+    if recursive:
+        def rec(v):
+            if isinstance(v, dict):
+                return _hydra_instantiate(v) if "_target_" in v else {k: rec(x) for k, x in v.items()}
+            if isinstance(v, (list, tuple)):
+                return [rec(x) for x in v]
+            return v
+
+        cfg = {k: rec(v) for k, v in cfg.items()}
+        args = [rec(a) for a in args]
+    if partial:
+        return functools.partial(fn, *args, **cfg)
+    return fn(*args, **cfg)
+
+
+def instantiate_class(obj):
+    if isinstance(obj, dict) and "class" in obj:
+        obj = dict(obj)
+        factory = instantiate_class(obj.pop("class"))
+        if "factory" in obj:
+            factory = getattr(factory, obj.pop("factory"))
+        if "args" in obj or "kwargs" in obj:
+            return factory(*obj.get("args", []), **obj.get("kwargs", {}))
+        return factory(**obj)
+    if isinstance(obj, str):
+        return get_obj_from_str(obj)
+    return obj
+
+
+def instantiate_any(obj):
+    if isinstance(obj, dict) and "_target_" in obj:
+        return _hydra_instantiate(obj)
+    return instantiate_class(obj)
+
+
+@dataclass
+class ModelLoadingConfig:
+    ckpt_path: Optional[str] = None
+    state_dict_key: Optional[str] = None
+    state_dict_prefix: Optional[str] = None
+    precision: Optional[str] = None
+    device: Optional[str] = None
+    to_compile: bool = False
+    to_freeze: bool = False
+
+
+def extract_state_dict(state_dict: dict, key: Optional[str], prefix: Optional[str]):
+    if key is not None:
+        state_dict = state_dict[key]
+    if prefix is None:
+        return state_dict
+    return {k[len(prefix):]: v for k, v in state_dict.items() if k.startswith(prefix)}
+
+
+_DTYPES = {"torch.float32": torch.float32, "torch.float": torch.float32, "torch.float16": torch.float16,
+           "torch.half": torch.float16, "torch.bfloat16": torch.bfloat16, "torch.float64": torch.float64}
+
+
+def prepare_model(model: nn.Module, cfg: ModelLoadingConfig):
+    if cfg.ckpt_path is not None:
+        sd = torch.load(cfg.ckpt_path, map_location=lambda storage, loc: storage)
+        model.load_state_dict(extract_state_dict(sd, cfg.state_dict_key, cfg.state_dict_prefix))
+    if cfg.precision is not None:
+        if cfg.precision not in _DTYPES:  # the reference eval()s this string (src/duwu/loader.py:48); keep it to dtypes
+            raise ValueError(f"unsupported precision '{cfg.precision}'")
+        model = model.to(_DTYPES[cfg.precision])
+    if cfg.device is not None:
+        model = model.to(cfg.device)
+    if cfg.to_compile:
+        raise NotImplementedError("to_compile: torch.compile is not part of the sm_100a kernel path")
+    if cfg.to_freeze:
+        model.requires_grad_(False).eval()
+    return model
+
+
+def load_any(obj):
+    load_config = None
+    if isinstance(obj, dict) and "_load_config_" in obj:
+        obj = dict(obj)
+        load_config = ModelLoadingConfig(**obj.pop("_load_config_"))
+    obj = instantiate_any(obj)
+    if load_config is not None and isinstance(obj, nn.Module):
+        obj = prepare_model(obj, load_config)
+    return obj
+
+
+def load_all(conf: dict, trainer=None, data_module=None):
+    conf = copy.deepcopy(conf)
+    trainer = trainer or instantiate_any(conf.pop("trainer"))
+    data_module = data_module or instantiate_any(conf.pop("data"))
+    data_module.set_tokenizers(getattr(trainer.te, "tokenizers", []))
+    return data_module, trainer
+
+
+def merge(*configs: dict) -> dict:
+    """OmegaConf.merge for plain dicts: later configs override, nested dicts merge key-wise."""
+    out: dict = {}
+    for c in configs:
+        for k, v in c.items():
+            if isinstance(v, dict) and isinstance(out.get(k), dict):
+                out[k] = merge(out[k], v)
+            else:
+                out[k] = copy.deepcopy(v)
+    return out
+
+
+def load_config_files(paths) -> dict:
+    """test_scripts/test_train.py:19-33: YAMLs merged left to right, then non-YAML (TOML) configs on top."""
+    import toml
+    import yaml
+
+    yamls, tomls = [], []
+    for p in paths:
+        if p.endswith(".yaml"):
+            with open(p) as f:
+                yamls.append(yaml.safe_load(f) or {})
+        else:
+            tomls.append(toml.load(p))
+    return merge(*yamls, *tomls)

@@ -1,0 +1,232 @@
+"""`DMTrainer` — drop-in for `duwu.trainer.DMTrainer` (src/duwu/trainer/trainer.py:95-318) without Lightning.
+
+Same constructor keywords, same attributes (`unet, te, vae, lycoris_model, loss, ema_loss, n_diffusion_time_steps,
+train_params`), same `training_step(batch, idx) -> {"loss", "aux_output"}`, `validation_step`, `configure_optimizers`,
+`merge_lycoris`, LyCORIS weight dump.  What Lightning did implicitly around the step (autocast `bf16-mixed`, backward,
+`gradient_clip_val`, optimizer / LR-scheduler step, DDP gradient all-reduce) is the explicit
+`fit_step()` here: loss.backward() runs the hand-scheduled kernel backward, gradient buckets are all-reduced over NCCL on
+a side stream while earlier blocks are still in backward, and clip + AdamW are two kernels with no host sync.
+The reference logs `loss.item()` every step (2 host syncs, trainer.py:280-293); here the EMA stays on the device and the
+host reads it only every `log_every_n_steps`.
+"""
+from __future__ import annotations
+
+import os
+from typing import Any, Dict, Iterator, Optional
+
+import torch
+import torch.nn as nn
+
+from .config import instantiate_any, load_any
+from .data import BaseTextEncoder
+
+
+class BaseTrainer(nn.Module):
+    def __init__(self, *args, name: str = "", lr: float = 1e-5, optimizer="torch.optim.AdamW",
+                 opt_config: Dict[str, Any] = {"weight_decay": 0.01, "betas": (0.9, 0.999)},
+                 lr_scheduler="torch.optim.lr_scheduler.CosineAnnealingLR",
+                 lr_scheduler_config: Dict[str, Any] = {"T_max": 100_000, "eta_min": 1e-7}, use_warm_up: bool = True,
+                 warm_up_period: int = 1000, **kwargs):
+        super().__init__()
+        self.name = name
+        self.train_params: Optional[Iterator[nn.Parameter]] = None
+        self.optimizer = instantiate_any(optimizer)
+        if self.optimizer is torch.optim.AdamW:  # the class itself (reference default argument) -> fused kernel
+            from .optim import FusedAdamW
+
+            self.optimizer = FusedAdamW
+        self.opt_config = dict(opt_config)
+        self.lr = lr
+        self.lr_sch = instantiate_any(lr_scheduler)
+        self.lr_sch_config = dict(lr_scheduler_config)
+        self.use_warm_up = use_warm_up
+        self.warm_up_period = warm_up_period
+        self.global_step = 0
+
+    def configure_optimizers(self, max_grad_norm: Optional[float] = None):
+        """src/duwu/trainer/trainer.py:52-74.  `torch.optim.AdamW` resolves to the fused multi-tensor kernel."""
+        assert self.train_params is not None
+        kw = dict(self.opt_config)
+        from .optim import FusedAdamW
+
+        if self.optimizer is FusedAdamW and max_grad_norm is not None:
+            kw["max_grad_norm"] = max_grad_norm
+        optimizer = self.optimizer(list(self.train_params), lr=self.lr, **kw)
+        lr_sch = self.lr_sch(optimizer, **self.lr_sch_config) if self.lr_sch is not None else None
+        if self.use_warm_up:
+            lr_scheduler = GradualWarmup(optimizer, self.warm_up_period, lr_sch)
+        else:
+            lr_scheduler = lr_sch
+        if lr_scheduler is None:
+            return optimizer
+        return {"optimizer": optimizer, "lr_scheduler": {"scheduler": lr_scheduler, "interval": "step"}}
+
+
+class GradualWarmup:
+    """`warmup_scheduler.GradualWarmupScheduler(optimizer, multiplier=1, total_epoch, after_scheduler)` as the reference
+    uses it (trainer.py:62-65): lr ramps linearly 0 -> base over `total_epoch` steps, then hands over."""
+
+    def __init__(self, optimizer, total_epoch: int, after_scheduler=None):
+        self.optimizer, self.total_epoch, self.after_scheduler = optimizer, total_epoch, after_scheduler
+        self.base_lrs = [g["lr"] for g in optimizer.param_groups]
+        self.last_epoch = 0
+        self.step()
+
+    def step(self):
+        self.last_epoch += 1
+        if self.last_epoch <= self.total_epoch:
+            for g, b in zip(self.optimizer.param_groups, self.base_lrs):
+                g["lr"] = b * self.last_epoch / self.total_epoch
+        elif self.after_scheduler is not None:
+            self.after_scheduler.step()
+
+
+class DMTrainer(BaseTrainer):
+    def __init__(self, model_config: dict, te_use_normed_ctx: bool = False, vae_std: Optional[float] = None,
+                 vae_mean: Optional[float] = None, lycoris_config=None, *args, name: str = "", lr: float = 1e-5,
+                 optimizer="torch.optim.AdamW", opt_config: Dict[str, Any] = {"weight_decay": 0.01, "betas": (0.9, 0.999)},
+                 lr_scheduler="torch.optim.lr_scheduler.CosineAnnealingLR",
+                 lr_scheduler_config: Dict[str, Any] = {"T_max": 100_000, "eta_min": 1e-7}, use_warm_up: bool = True,
+                 warm_up_period: int = 1000, loss_config: Optional[dict] = None, device: Optional[str] = None):
+        super().__init__(*args, name=name, lr=lr, optimizer=optimizer, opt_config=opt_config, lr_scheduler=lr_scheduler,
+                         lr_scheduler_config=lr_scheduler_config, use_warm_up=use_warm_up, warm_up_period=warm_up_period)
+        dev = torch.device(device or ("cuda" if torch.cuda.is_available() else "cpu"))
+        with torch.device(dev):
+            unet = load_any(model_config["unet"])
+        self.unet = unet.to(dev)
+        te = load_any(model_config.get("te"))
+        vae = load_any(model_config.get("vae"))
+        self.te = te.to(dev) if isinstance(te, nn.Module) else te
+        self.vae = vae.to(dev) if isinstance(vae, nn.Module) else vae
+        self.te_use_normed_ctx = te_use_normed_ctx
+        self.vae_std = vae_std
+        self.vae_mean = vae_mean or 0
+        if self.vae_std is None and self.vae is not None:
+            self.vae_std = 1 / self.vae.config.scaling_factor
+
+        if isinstance(lycoris_config, str):
+            import toml
+
+            lycoris_config = toml.load(lycoris_config)
+        if lycoris_config is not None:
+            from .lycoris import LycorisNetwork, create_lycoris
+
+            LycorisNetwork.apply_preset(lycoris_config["preset"])
+            lycoris_model = create_lycoris(self.unet, **lycoris_config["config"])
+            lycoris_model.apply_to()
+        else:
+            lycoris_model = None
+        self.lycoris_model = lycoris_model
+
+        self.register_buffer("ema_loss", torch.tensor(0.0, device=dev))
+        self.ema_decay = 0.99
+        if lycoris_model is not None:
+            self.lycoris_model.train()
+            self.unet.requires_grad_(False)
+            self.train_params = self.lycoris_model.parameters()
+        else:
+            self.unet.requires_grad_(True).train()
+            self.train_params = self.unet.parameters()
+
+        if loss_config is None:
+            from .loss import DiffusionLoss
+            from .scheduler import EulerDiscreteScheduler
+
+            scheduler = EulerDiscreteScheduler.from_pretrained("stabilityai/stable-diffusion-xl-base-1.0", subfolder="scheduler")
+            self.loss = DiffusionLoss(scheduler)
+        else:
+            self.loss = instantiate_any(loss_config)
+        self.n_diffusion_time_steps = self.loss.n_diffusion_time_steps
+        # fused sinusoidal timestep embedding from the noising kernel (diffusers Timesteps(block_out_channels[0]))
+        self.loss.temb_dim = int(self.unet.config.block_out_channels[0])
+        self._fit = None
+
+    # ---- reference API ---------------------------------------------------------------------------------------
+    def merge_lycoris(self):
+        self.lycoris_model.restore()
+        self.lycoris_model.merge_to()
+
+    def save_lycoris_weight(self, dirpath: str = "./lycoris_weight", epoch: int = 0):
+        """on_train_epoch_end (trainer.py:189-215): lycoris state dict ∪ trainable unet params -> epoch=N.pt."""
+        os.makedirs(dirpath, exist_ok=True)
+        model_weight = {k: v for k, v in self.unet.named_parameters() if v.requires_grad}
+        lycoris_weight = {k: v.detach().clone() for k, v in self.lycoris_model.state_dict().items()} | model_weight
+        path = os.path.join(dirpath, f"epoch={epoch}.pt")
+        torch.save(lycoris_weight, path)
+        return path
+
+    def get_latent_and_conditioning(self, batch):
+        x, captions, tokenizer_outputs, added_cond, cross_attn_kwargs = batch
+        dev = self.ema_loss.device
+        x = x.to(dev, non_blocking=True)
+        added_cond = {k: v.to(dev, non_blocking=True) for k, v in added_cond.items()}
+        attn_mask = None
+        with torch.no_grad():
+            if self.vae is not None:
+                latent_dist = self.vae.encode(x).latent_dist
+                x = latent_dist.sample()
+                x = (x - self.vae_mean) / self.vae_std
+            if isinstance(self.te, BaseTextEncoder):
+                try:
+                    embedding, normed_embedding, pooled_embedding, attn_mask = self.te(tokenizer_outputs, batch_size=x.shape[0])
+                except TypeError:
+                    embedding, normed_embedding, pooled_embedding, attn_mask = self.te(tokenizer_outputs)
+            else:
+                normed_embedding, pooled_embedding, *embeddings = self.te(**tokenizer_outputs[0], return_dict=False,
+                                                                           output_hidden_states=True)
+                embedding = embeddings[-1][-1]
+            ctx = normed_embedding if self.te_use_normed_ctx else embedding
+        added_cond["text_embeds"] = pooled_embedding
+        return x, ctx, attn_mask, added_cond, cross_attn_kwargs
+
+    def training_step(self, batch, idx):
+        x, ctx, attn_mask, added_cond, cross_attn_kwargs = self.get_latent_and_conditioning(batch)
+        loss, aux_output = self.loss(x, self.unet, encoder_hidden_states=ctx, encoder_attention_mask=attn_mask,
+                                     added_cond_kwargs=added_cond, cross_attention_kwargs=cross_attn_kwargs)
+        ema_decay = min(self.global_step / (10 + self.global_step), self.ema_decay)
+        self.ema_loss = ema_decay * self.ema_loss + (1 - ema_decay) * loss.detach()  # stays on the device, no .item()
+        return {"loss": loss, "aux_output": aux_output}
+
+    @torch.no_grad()
+    def validation_step(self, batch, idx):
+        x, ctx, attn_mask, added_cond, cross_attn_kwargs = self.get_latent_and_conditioning(batch)
+        return self.loss(x, self.unet, encoder_hidden_states=ctx, encoder_attention_mask=attn_mask,
+                         added_cond_kwargs=added_cond, cross_attention_kwargs=cross_attn_kwargs)
+
+    # ---- what Lightning's fit loop did around training_step -----------------------------------------------------
+    def setup_fit(self, gradient_clip_val: Optional[float] = None, process_group=None, seed: Optional[int] = None,
+                  n_buckets: int = 4):
+        from .parallel import GradientBuckets
+
+        opt = self.configure_optimizers(max_grad_norm=gradient_clip_val)
+        sched = None
+        if isinstance(opt, dict):
+            sched = opt["lr_scheduler"]["scheduler"]
+            opt = opt["optimizer"]
+        buckets = None
+        if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()
+                                         and torch.distributed.get_world_size() > 1):
+            buckets = GradientBuckets(self, process_group=process_group, n_buckets=n_buckets)
+        if seed is not None:
+            rank = torch.distributed.get_rank() if (torch.distributed.is_available() and torch.distributed.is_initialized()) else 0
+            self.loss.seed = int(seed) + rank  # pl.seed_everything(seed + global_rank), test_scripts/test_train.py:68-69
+        self._fit = dict(opt=opt, sched=sched, buckets=buckets)
+        return self._fit
+
+    def fit_step(self, batch, idx: int = 0):
+        """forward + backward + (DDP all-reduce) + clip + optimizer + lr schedule for one batch; returns the step dict."""
+        if self._fit is None:
+            self.setup_fit()
+        f = self._fit
+        if f["buckets"] is not None:
+            f["buckets"].begin_step()
+        out = self.training_step(batch, idx)
+        out["loss"].backward()
+        if f["buckets"] is not None:
+            f["buckets"].finish()
+        f["opt"].step()
+        if f["sched"] is not None:
+            f["sched"].step()
+        f["opt"].zero_grad(set_to_none=False)  # gradients keep their (flat) storage
+        self.global_step += 1
+        return out
