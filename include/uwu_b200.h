@@ -81,6 +81,8 @@ typedef struct uwu_gemm_desc {
     float alpha;
     int32_t accumulate; /* fp32 output only: out += result */
     int32_t block_n;    /* 0 = choose */
+    int32_t stream_k;   /* fp32 output, plain epilogue: 1 = split the (tile, k-block) space evenly over the SMs and
+                           reduce partial tiles with atomics, 0 = whole tiles per CTA, -1 = choose */
     /* diagnostics: override shared-memory descriptor fields (0 = default) */
     int32_t dbg_a_lbo, dbg_a_sbo, dbg_a_kadv, dbg_b_lbo, dbg_b_sbo, dbg_b_kadv;
 } uwu_gemm_desc;

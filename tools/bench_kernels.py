@@ -1,0 +1,132 @@
+"""Micro-benchmarks of the kernels at the shapes the SDXL step uses (distinct buffers, CUDA-event timed).
+
+    python tools/bench_kernels.py [ln] [geglu] [gn] [lokr] [wgrad] [lin] [attn]
+"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+from uwudiff_b200 import ops
+from uwudiff_b200._lib import A_COL, B_KN
+
+dev = "cuda"
+HBM = 6546.9
+
+
+def mk(*shape, s=1.0):
+    return (torch.randn(*shape, device=dev) * s).to(torch.bfloat16)
+
+
+def timeit(fn, iters=20, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters * 1e3  # us
+
+
+def bw(name, us, nbytes):
+    print(f"{name}: {us:8.1f} us  {nbytes/us/1e3:7.0f} GB/s  ({100*nbytes/us/1e3/HBM:4.1f}% of {HBM:.0f})", flush=True)
+
+
+def tf(name, us, flops):
+    print(f"{name}: {us:8.1f} us  {flops/us/1e6:7.1f} TFLOP/s", flush=True)
+
+
+def case_ln():
+    for (M, C) in [(16384, 1280), (65536, 640)]:
+        x, dy, dres = mk(M, C), mk(M, C), mk(M, C)
+        gamma, beta = torch.ones(C, device=dev), torch.zeros(C, device=dev)
+        dg, db = torch.zeros(C, device=dev), torch.zeros(C, device=dev)
+        y, stats = ops.layernorm_fwd(x, gamma, beta)
+        bw(f"ln fwd M{M} C{C}", timeit(lambda: ops.layernorm_fwd(x, gamma, beta)), x.numel() * 4)
+        bw(f"ln bwd(+dres,+param grads) M{M} C{C}",
+           timeit(lambda: ops.layernorm_bwd(x, dy, gamma, stats, dres=dres, dgamma=dg, dbeta=db)), x.numel() * 8)
+        bw(f"ln bwd(+dres) M{M} C{C}", timeit(lambda: ops.layernorm_bwd(x, dy, gamma, stats, dres=dres)), x.numel() * 8)
+
+
+def case_geglu():
+    for (M, F) in [(16384, 5120), (65536, 2560)]:
+        x, dout = mk(M, 2 * F), mk(M, F)
+        bw(f"geglu fwd M{M} F{F}", timeit(lambda: ops.geglu_fwd(x)), M * F * 2 * 3)
+        bw(f"geglu bwd M{M} F{F}", timeit(lambda: ops.geglu_bwd(x, dout)), M * F * 2 * 5)
+
+
+def case_gn():
+    for (N, HW, C) in [(16, 128 * 128, 320), (16, 64 * 64, 640), (16, 32 * 32, 1280), (16, 64 * 64, 1920)]:
+        x, dy, dres = mk(N * HW, C), mk(N * HW, C), mk(N * HW, C)
+        gamma, beta = torch.ones(C, device=dev), torch.zeros(C, device=dev)
+        y, stats = ops.groupnorm_fwd(x, N, HW, C, 32, 1e-5, gamma, beta, True)
+        bw(f"gn+silu fwd N{N} HW{HW} C{C}", timeit(lambda: ops.groupnorm_fwd(x, N, HW, C, 32, 1e-5, gamma, beta, True)),
+           x.numel() * 4)
+        bw(f"gn+silu bwd(+dres)", timeit(lambda: ops.groupnorm_bwd(x, dy, N, HW, C, 32, gamma, beta, stats, True, dres=dres)),
+           x.numel() * 8)
+
+
+def case_lokr():
+    for (ol, ok, im, inn) in [(20, 64, 20, 64), (5, 2048, 5, 256), (5, 256, 5, 1024), (20, 64, 32, 64), (10, 64, 10, 64),
+                              (5, 1024, 5, 128)]:
+        N, K = ol * ok, im * inn
+        G = torch.randn(N, K, device=dev)
+        w1, w2 = torch.randn(ol, im, device=dev), torch.randn(ok, inn, device=dev)
+        dw1, dw2 = torch.zeros_like(w1), torch.zeros_like(w2)
+        bw(f"lokr_grad N{N} K{K} w1 {ol}x{im} w2 {ok}x{inn}", timeit(lambda: ops.lokr_grad(G, w1, w2, dw1, dw2)), N * K * 4 * 2)
+        W = torch.randn(N, K, device=dev)
+        dst = torch.empty(N, K, device=dev, dtype=torch.bfloat16)
+        bw(f"fold_lokr N{N} K{K}", timeit(lambda: ops.fold_lokr(W, w1, w2, dst)), N * K * 6)
+
+
+def case_wgrad():
+    for (Mtok, Co, Ci) in [(16384, 1280, 1280), (65536, 640, 640), (16384, 10240, 1280), (16384, 1280, 5120),
+                           (65536, 5120, 640), (65536, 640, 2560), (1232, 1280, 2048)]:
+        dy, x = mk(Mtok, Co), mk(Mtok, Ci)
+        G = torch.empty(Co, Ci, device=dev)
+        for sk in (0, 1, -1):
+            tf(f"wgrad dY^T X tokens{Mtok} {Co}x{Ci} stream_k={sk}",
+               timeit(lambda: ops.gemm(dy, x, Co, Ci, Mtok, a_layout=A_COL, lda=Co, b_layout=B_KN, ldb=Ci, out=G, stream_k=sk)),
+               2.0 * Mtok * Co * Ci)
+
+
+def case_lin():
+    for (M, N, K) in [(16384, 1280, 1280), (16384, 3840, 1280), (16384, 10240, 1280), (16384, 1280, 5120), (65536, 640, 640),
+                      (65536, 1920, 640), (65536, 5120, 640), (65536, 640, 2560)]:
+        a, b = mk(M, K), mk(N, K)
+        out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+        res = mk(M, N)
+        tf(f"lin M{M} N{N} K{K}", timeit(lambda: ops.gemm(a, b, M, N, K, out=out)), 2.0 * M * N * K)
+        tf(f"lin+residual M{M} N{N} K{K}", timeit(lambda: ops.gemm(a, b, M, N, K, out=out, residual=res)), 2.0 * M * N * K)
+        tf(f"torch.matmul M{M} N{N} K{K}", timeit(lambda: torch.matmul(a, b.t())), 2.0 * M * N * K)
+
+
+def case_attn():
+    for (B, heads, L, Lk) in [(16, 10, 4096, 4096), (16, 20, 1024, 1024), (16, 10, 4096, 77), (16, 20, 1024, 77)]:
+        C = heads * 64
+        if Lk == L:
+            qkv = mk(B * L, 3 * C)
+            q, k, v = qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:]
+        else:
+            q, k, v = mk(B * L, C), mk(B * Lk, C), mk(B * Lk, C)
+        do = mk(B * L, C)
+        o, lse = ops.attn_fwd(q, k, v, B, heads, L, Lk)
+        fl = 4.0 * B * heads * L * Lk * 64
+        tf(f"attn_fwd B{B} h{heads} L{L} Lk{Lk}", timeit(lambda: ops.attn_fwd(q, k, v, B, heads, L, Lk)), fl)
+        tf(f"attn_bwd B{B} h{heads} L{L} Lk{Lk} (2.5x)", timeit(lambda: ops.attn_bwd(q, k, v, o, do, lse, B, heads, L, Lk)), 2.5 * fl)
+
+
+if __name__ == "__main__":
+    cases = sys.argv[1:] or ["ln", "geglu", "gn", "lokr", "wgrad", "lin", "attn"]
+    for c in cases:
+        try:
+            globals()["case_" + c]()
+        except Exception as e:
+            import traceback
+
+            traceback.print_exc()
+            print(f"CASE {c} FAILED: {e}", flush=True)

@@ -35,7 +35,7 @@ class GemmDesc(C.Structure):
         ("n_split", C.c_int32), ("out_dtype", C.c_int32),
         ("bias", C.c_void_p), ("bias_rows", C.c_void_p), ("rows_per_bias", C.c_int32),
         ("residual", C.c_void_p), ("ldr", C.c_int64),
-        ("alpha", C.c_float), ("accumulate", C.c_int32), ("block_n", C.c_int32),
+        ("alpha", C.c_float), ("accumulate", C.c_int32), ("block_n", C.c_int32), ("stream_k", C.c_int32),
         ("dbg_a_lbo", C.c_int32), ("dbg_a_sbo", C.c_int32), ("dbg_a_kadv", C.c_int32),
         ("dbg_b_lbo", C.c_int32), ("dbg_b_sbo", C.c_int32), ("dbg_b_kadv", C.c_int32),
     ]

@@ -72,16 +72,33 @@ __global__ void axpy_f32_kernel(const float* __restrict__ a, const float* __rest
 // ------------------------------------------------------------------------------------------------
 // adapter gradients from G [N, K] fp32 (ldg)
 // ------------------------------------------------------------------------------------------------
-// one block per (l, i): reduce over the [ok x in] tile of G times w2
+// dw1[l,i] += mult * sum_{k,n} G[l*ok+k, i*in+n] w2[k,n]
+// grid (ol*im, row_splits): block (b, s) reduces rows [s*rows_per, ...) of the [ok x in] tile of G against w2.
+// VEC: in_n % 4 == 0 and 16-byte aligned rows -> float4 loads.
+template <bool VEC>
 __global__ void __launch_bounds__(256) lokr_dw1_kernel(const float* __restrict__ G, long long ldg, const float* __restrict__ w2,
-                                                       int ok, int in_n, int im, float mult, float* __restrict__ dw1) {
+                                                       int ok, int in_n, int im, int rows_per, float mult,
+                                                       float* __restrict__ dw1) {
     const int l = blockIdx.x / im, i = blockIdx.x - l * im;
+    const int k0 = blockIdx.y * rows_per;
+    const int k1 = min(ok, k0 + rows_per);
     const float* g = G + (size_t)l * ok * ldg + (size_t)i * in_n;
     float acc = 0.f;
-    const int total = ok * in_n;
-    for (int e = threadIdx.x; e < total; e += blockDim.x) {
-        const int k = e / in_n, n = e - k * in_n;
-        acc = fmaf(g[(size_t)k * ldg + n], w2[e], acc);
+    if (VEC) {
+        const int nv = in_n >> 2;
+        const int total = (k1 - k0) * nv;
+        for (int e = threadIdx.x; e < total; e += blockDim.x) {
+            const int k = k0 + e / nv, n = (e - (e / nv) * nv) << 2;
+            const float4 a = *reinterpret_cast<const float4*>(g + (size_t)k * ldg + n);
+            const float4 b = *reinterpret_cast<const float4*>(w2 + (size_t)k * in_n + n);
+            acc = fmaf(a.x, b.x, acc); acc = fmaf(a.y, b.y, acc); acc = fmaf(a.z, b.z, acc); acc = fmaf(a.w, b.w, acc);
+        }
+    } else {
+        const int total = (k1 - k0) * in_n;
+        for (int e = threadIdx.x; e < total; e += blockDim.x) {
+            const int k = k0 + e / in_n, n = e - (e / in_n) * in_n;
+            acc = fmaf(g[(size_t)k * ldg + n], w2[(size_t)k * in_n + n], acc);
+        }
     }
     __shared__ float red[8];
     acc = warp_sum(acc);
@@ -90,21 +107,48 @@ __global__ void __launch_bounds__(256) lokr_dw1_kernel(const float* __restrict__
     if (threadIdx.x == 0) {
         float s = 0.f;
         for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[w];
-        dw1[blockIdx.x] += s * mult;
+        if (gridDim.y > 1)
+            atomicAdd(&dw1[blockIdx.x], s * mult);
+        else
+            dw1[blockIdx.x] += s * mult;
     }
 }
-// one thread per (k, n): loop over (l, i)
-__global__ void lokr_dw2_kernel(const float* __restrict__ G, long long ldg, const float* __restrict__ w1, int ol, int ok, int im,
-                                int in_n, float mult, float* __restrict__ dw2) {
+// dw2[k,n] += mult * sum_{l,i} G[l*ok+k, i*in+n] w1[l,i]
+// grid (ceil(ok*in/VW/128), l_splits): one thread per (k, VW consecutive n), looping over its slice of l and all i.
+template <int VW>
+__global__ void __launch_bounds__(128) lokr_dw2_kernel(const float* __restrict__ G, long long ldg, const float* __restrict__ w1,
+                                                       int ol, int ok, int im, int in_n, int l_per, float mult,
+                                                       float* __restrict__ dw2) {
+    const int nv = in_n / VW;
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= ok * in_n) return;
-    const int k = e / in_n, n = e - k * in_n;
-    float acc = 0.f;
-    for (int l = 0; l < ol; ++l) {
+    if (e >= ok * nv) return;
+    const int k = e / nv, n = (e - k * nv) * VW;
+    const int l0 = blockIdx.y * l_per, l1 = min(ol, l0 + l_per);
+    float acc[VW];
+#pragma unroll
+    for (int j = 0; j < VW; ++j) acc[j] = 0.f;
+    for (int l = l0; l < l1; ++l) {
         const float* g = G + ((size_t)l * ok + k) * ldg + n;
-        for (int i = 0; i < im; ++i) acc = fmaf(g[(size_t)i * in_n], w1[l * im + i], acc);
+#pragma unroll 4
+        for (int i = 0; i < im; ++i) {
+            const float w = __ldg(w1 + l * im + i);
+            if (VW == 4) {
+                const float4 a = *reinterpret_cast<const float4*>(g + (size_t)i * in_n);
+                acc[0] = fmaf(a.x, w, acc[0]); acc[1 % VW] = fmaf(a.y, w, acc[1 % VW]);
+                acc[2 % VW] = fmaf(a.z, w, acc[2 % VW]); acc[3 % VW] = fmaf(a.w, w, acc[3 % VW]);
+            } else {
+                acc[0] = fmaf(g[(size_t)i * in_n], w, acc[0]);
+            }
+        }
     }
-    dw2[e] += acc * mult;
+    float* o = dw2 + (size_t)k * in_n + n;
+    if (gridDim.y > 1) {
+#pragma unroll
+        for (int j = 0; j < VW; ++j) atomicAdd(o + j, acc[j] * mult);
+    } else {
+#pragma unroll
+        for (int j = 0; j < VW; ++j) o[j] += acc[j] * mult;
+    }
 }
 // dup[o, q] += s * sum_k G[o,k] down[q,k] : one warp per (o, q)
 __global__ void __launch_bounds__(256) lora_dup_kernel(const float* __restrict__ G, long long ldg, const float* __restrict__ down,
@@ -281,10 +325,39 @@ extern "C" int uwu_lokr_grad(const float* G, int64_t ldg, const float* w1, const
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     UWU_CHECK_ARG(G && w1 && w2 && dw1 && dw2, "uwu_lokr_grad: null pointer");
     UWU_CHECK_ARG(out_l > 0 && out_k > 0 && in_m > 0 && in_n > 0 && ldg >= (int64_t)in_m * in_n, "uwu_lokr_grad: bad shape");
-    lokr_dw1_kernel<<<out_l * in_m, 256, 0, stream>>>(G, ldg, w2, out_k, in_n, in_m, multiplier, dw1);
-    UWU_CHECK_LAUNCH();
-    lokr_dw2_kernel<<<(out_k * in_n + 127) / 128, 128, 0, stream>>>(G, ldg, w1, out_l, out_k, in_m, in_n, multiplier, dw2);
-    UWU_CHECK_LAUNCH();
+    const bool vec = in_n % 4 == 0 && ldg % 4 == 0 && (reinterpret_cast<uintptr_t>(G) & 15) == 0 &&
+                     (reinterpret_cast<uintptr_t>(w2) & 15) == 0;
+    const int target = 4 * sm_count();
+    {
+        // enough blocks to fill the machine: split each (l, i) tile over row ranges (>= 8 rows each)
+        const int tiles = out_l * in_m;
+        int splits = (target + tiles - 1) / tiles;
+        if (splits > (out_k + 7) / 8) splits = (out_k + 7) / 8;
+        if (splits < 1) splits = 1;
+        const int rows_per = (out_k + splits - 1) / splits;
+        splits = (out_k + rows_per - 1) / rows_per;
+        dim3 grid(tiles, splits);
+        if (vec)
+            lokr_dw1_kernel<true><<<grid, 256, 0, stream>>>(G, ldg, w2, out_k, in_n, in_m, rows_per, multiplier, dw1);
+        else
+            lokr_dw1_kernel<false><<<grid, 256, 0, stream>>>(G, ldg, w2, out_k, in_n, in_m, rows_per, multiplier, dw1);
+        UWU_CHECK_LAUNCH();
+    }
+    {
+        const int vw = vec ? 4 : 1;
+        const int blocks = (out_k * (in_n / vw) + 127) / 128;
+        int lsplits = (target + blocks - 1) / blocks;
+        if (lsplits > out_l) lsplits = out_l;
+        if (lsplits < 1) lsplits = 1;
+        const int l_per = (out_l + lsplits - 1) / lsplits;
+        lsplits = (out_l + l_per - 1) / l_per;
+        dim3 grid(blocks, lsplits);
+        if (vec)
+            lokr_dw2_kernel<4><<<grid, 128, 0, stream>>>(G, ldg, w1, out_l, out_k, in_m, in_n, l_per, multiplier, dw2);
+        else
+            lokr_dw2_kernel<1><<<grid, 128, 0, stream>>>(G, ldg, w1, out_l, out_k, in_m, in_n, l_per, multiplier, dw2);
+        UWU_CHECK_LAUNCH();
+    }
     return UWU_OK;
 }
 

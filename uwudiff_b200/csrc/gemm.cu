@@ -57,7 +57,50 @@ struct GemmKernelArgs {
     long long ldr;
     float alpha;
     int accumulate;
+    int stream_k;  // 1: the (tile, k-block) space is cut into equal contiguous ranges, one per CTA; partial tiles are
+                   //    reduced with vector atomics into the fp32 output (which the host zeroed unless accumulating)
 };
+
+// One unit of work for the three warp roles: k-blocks [kb0, kb1) of output tile `tile`.
+struct WorkIter {
+    long long cur, end;
+    int step, num_kb, stream_k;
+    int tile, kb0, kb1;
+    __device__ __forceinline__ void init(const GemmKernelArgs& p, int num_tiles) {
+        num_kb = p.num_kb;
+        stream_k = p.stream_k;
+        if (stream_k) {
+            const long long units = (long long)num_tiles * num_kb;
+            cur = units * blockIdx.x / gridDim.x;
+            end = units * (blockIdx.x + 1) / gridDim.x;
+            step = 0;
+        } else {
+            cur = blockIdx.x;
+            end = num_tiles;
+            step = gridDim.x;
+        }
+    }
+    __device__ __forceinline__ bool next() {
+        if (cur >= end) return false;
+        if (stream_k) {
+            tile = (int)(cur / num_kb);
+            kb0 = (int)(cur - (long long)tile * num_kb);
+            const long long left = end - cur;
+            kb1 = (left < (long long)(num_kb - kb0)) ? kb0 + (int)left : num_kb;
+            cur += kb1 - kb0;
+        } else {
+            tile = (int)cur;
+            kb0 = 0;
+            kb1 = num_kb;
+            cur += step;
+        }
+        return true;
+    }
+};
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
 
 __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __grid_constant__ GemmKernelArgs p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -107,7 +150,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
             int stage = 0;
             uint32_t phase = 0;
             const uint32_t tx_bytes = (uint32_t)p.tx_bytes;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            WorkIter wi;
+            wi.init(p, num_tiles);
+            while (wi.next()) {
+                const int tile = wi.tile;
                 const int n_blk = tile % p.num_n_tiles;
                 const int m_blk = tile / p.num_n_tiles;
                 const int m0 = m_blk * BLOCK_M;
@@ -118,7 +164,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
                     ch = (m0 / p.W) % p.H;
                     cn = m0 / (p.W * p.H);
                 }
-                for (int kb = 0; kb < p.num_kb; ++kb) {
+                for (int kb = wi.kb0; kb < wi.kb1; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* sa = smem + (size_t)stage * stage_bytes;
                     uint8_t* sb = sa + A_STAGE_BYTES;
@@ -161,11 +207,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            WorkIter wi;
+            wi.init(p, num_tiles);
+            while (wi.next()) {
                 mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * ACC_STRIDE);
-                for (int kb = 0; kb < p.num_kb; ++kb) {
+                for (int kb = wi.kb0; kb < wi.kb1; ++kb) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
@@ -175,7 +223,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
 #pragma unroll
                     for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
                         umma_bf16(d_tmem, adesc + (uint64_t)((k * p.a_kadv) >> 4), bdesc + (uint64_t)((k * p.b_kadv) >> 4),
-                                  idesc, (uint32_t)((kb | k) != 0));
+                                  idesc, (uint32_t)(kb != wi.kb0 || k != 0));
                     }
                     umma_commit(&empty_bar[stage]);  // frees this smem stage once the MMAs retire
                     if (++stage == p.stages) {
@@ -196,7 +244,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
         const int sub = warp & 3;
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        WorkIter wi;
+        wi.init(p, num_tiles);
+        while (wi.next()) {
+            const int tile = wi.tile;
             const int n_blk = tile % p.num_n_tiles;
             const int m_blk = tile / p.num_n_tiles;
             const int row = m_blk * BLOCK_M + sub * 32 + lane;
@@ -260,7 +311,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
                             if (j < ncols) v[j] += __bfloat162float(rp[j]);
                     }
                 }
-                if (p.out_fp32) {
+                if (p.stream_k) {
+                    float* op = reinterpret_cast<float*>(obase) + (size_t)row * ld + ocol;
+                    if (vec_ok && ((reinterpret_cast<uintptr_t>(op) & 15) == 0)) {
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) red_add_v4(op + q * 4, v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (j < ncols) atomicAdd(op + j, v[j]);
+                    }
+                } else if (p.out_fp32) {
                     float* op = reinterpret_cast<float*>(obase) + (size_t)row * ld + ocol;
                     if (vec_ok && ((reinterpret_cast<uintptr_t>(op) & 15) == 0)) {
 #pragma unroll
@@ -475,6 +536,27 @@ extern "C" int uwu_gemm(const uwu_gemm_desc* d, void* stream_) {
     p.ldr = d->ldr > 0 ? d->ldr : d->N;
     p.alpha = d->alpha;
     p.accumulate = d->accumulate;
+    // stream-K: few output tiles but a long reduction (token-reduction weight gradients) would leave most SMs idle
+    const int n_tiles_all = p.num_m_tiles * p.num_n_tiles;
+    int sk = d->stream_k;
+    if (sk < 0) {
+        const int sms = sm_count();
+        const int waves = (n_tiles_all + sms - 1) / sms;
+        sk = (p.out_fp32 && !d->bias && !d->bias_rows && !d->residual && p.num_kb >= 32 &&
+              (double)n_tiles_all < 0.85 * (double)waves * sms) ? 1 : 0;
+    }
+    if (sk) {
+        UWU_CHECK_ARG(p.out_fp32 && !d->bias && !d->bias_rows && !d->residual,
+                      "uwu_gemm: stream_k needs an fp32 output and a plain (alpha-only) epilogue");
+        if (!d->accumulate) {
+            // atomics add onto the destination: give "out = A.B" semantics by clearing it first
+            UWU_CHECK_CUDA(cudaMemset2DAsync(p.out, (size_t)p.ldo * 4, 0, (size_t)min((long long)p.N, (long long)p.n_split) * 4,
+                                             (size_t)p.M, stream));
+            if (d->out2)
+                UWU_CHECK_CUDA(cudaMemset2DAsync(p.out2, (size_t)p.ldo2 * 4, 0, (size_t)(p.N - p.n_split) * 4, (size_t)p.M, stream));
+        }
+    }
+    p.stream_k = sk;
 
     // ---------------- launch ----------------
     const int stage_bytes = A_STAGE_BYTES + p.b_stage_bytes;
@@ -492,7 +574,8 @@ extern "C" int uwu_gemm(const uwu_gemm_desc* d, void* stream_) {
     }
     const int num_tiles = p.num_m_tiles * p.num_n_tiles;
     int grid = sm_count();
-    if (grid > num_tiles) grid = num_tiles;
+    if (!p.stream_k && grid > num_tiles) grid = num_tiles;
+    if (p.stream_k && (long long)grid > (long long)num_tiles * p.num_kb) grid = (int)((long long)num_tiles * p.num_kb);
     gemm_tcgen05_kernel<<<grid, NUM_THREADS, smem_bytes, stream>>>(p);
     UWU_CHECK_LAUNCH();
     return UWU_OK;

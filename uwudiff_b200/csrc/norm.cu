@@ -269,9 +269,19 @@ static int gn_geom(int N, int HW, int C, int G, GNGeom* g) {
 }
 
 // ================================================================================================
-// LayerNorm: one warp per row, two passes over the row (second pass hits L1)
+// LayerNorm: one warp per row, the row lives in registers (one HBM read, one write); kMaxV = ceil(C / 256)
 // ================================================================================================
+UWU_DEVINL void unpack8(const uint4& u, float (&v)[8]) {
+    float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), c = unpack_bf16(u.z), d = unpack_bf16(u.w);
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
+}
+UWU_DEVINL void ldf8(const float* p, float (&v)[8]) {
+    const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+
 // y = ((x - mean) * rstd * gamma + beta) [* (1 + mscale[b]) + mshift[b]]   ;  stats[row] = {mean, rstd}
+template <int kMaxV>
 __global__ void __launch_bounds__(256) ln_fwd_kernel(const __nv_bfloat16* __restrict__ x, int M, int C, float eps,
                                                      const float* __restrict__ gamma, const float* __restrict__ beta,
                                                      const float* __restrict__ mscale, const float* __restrict__ mshift,
@@ -279,27 +289,38 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const __nv_bfloat16* __rest
                                                      float* __restrict__ stats) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int cv = C / 8;
+    const float inv_c = 1.0f / (float)C;
     for (int row = blockIdx.x * 8 + warp; row < M; row += gridDim.x * 8) {
         const __nv_bfloat16* xr = x + (size_t)row * C;
+        uint4 raw[kMaxV];
+#pragma unroll
+        for (int k = 0; k < kMaxV; ++k) {
+            const int v = lane + k * 32;
+            raw[k] = v < cv ? *reinterpret_cast<const uint4*>(xr + v * 8) : make_uint4(0, 0, 0, 0);
+        }
         float s = 0.f;
-        for (int v = lane; v < cv; v += 32) {
+#pragma unroll
+        for (int k = 0; k < kMaxV; ++k) {
             float f[8];
-            ld8(xr + v * 8, f);
+            unpack8(raw[k], f);
 #pragma unroll
             for (int j = 0; j < 8; ++j) s += f[j];
         }
-        const float mean = warp_sum(s) / (float)C;
+        const float mean = warp_sum(s) * inv_c;
         float q = 0.f;
-        for (int v = lane; v < cv; v += 32) {
-            float f[8];
-            ld8(xr + v * 8, f);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const float d = f[j] - mean;
-                q = fmaf(d, d, q);
+        for (int k = 0; k < kMaxV; ++k) {
+            if (lane + k * 32 < cv) {
+                float f[8];
+                unpack8(raw[k], f);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float d = f[j] - mean;
+                    q = fmaf(d, d, q);
+                }
             }
         }
-        const float rstd = rsqrtf(warp_sum(q) / (float)C + eps);
+        const float rstd = rsqrtf(warp_sum(q) * inv_c + eps);
         if (lane == 0 && stats) {
             stats[(size_t)row * 2] = mean;
             stats[(size_t)row * 2 + 1] = rstd;
@@ -307,85 +328,122 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const __nv_bfloat16* __rest
         const float* ms = mscale ? mscale + (size_t)(row / rows_per_mod) * C : nullptr;
         const float* mh = mshift ? mshift + (size_t)(row / rows_per_mod) * C : nullptr;
         __nv_bfloat16* yr = y + (size_t)row * C;
-        for (int v = lane; v < cv; v += 32) {
-            float f[8];
-            ld8(xr + v * 8, f);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int c = v * 8 + j;
-                float o = (f[j] - mean) * rstd;
-                if (gamma) o = fmaf(o, gamma[c], beta ? beta[c] : 0.f);
-                if (ms) o = fmaf(o, 1.0f + ms[c], mh ? mh[c] : 0.f);
-                f[j] = o;
+        for (int k = 0; k < kMaxV; ++k) {
+            const int v = lane + k * 32;
+            if (v < cv) {
+                float f[8];
+                unpack8(raw[k], f);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[j] = (f[j] - mean) * rstd;
+                if (gamma) {
+                    float ga[8];
+                    ldf8(gamma + v * 8, ga);
+                    if (beta) {
+                        float be[8];
+                        ldf8(beta + v * 8, be);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) f[j] = fmaf(f[j], ga[j], be[j]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) f[j] *= ga[j];
+                    }
+                }
+                if (ms) {
+                    float a[8];
+                    ldf8(ms + v * 8, a);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) f[j] = f[j] * (1.0f + a[j]);
+                    if (mh) {
+                        ldf8(mh + v * 8, a);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) f[j] += a[j];
+                    }
+                }
+                st8(yr + v * 8, f);
             }
-            st8(yr + v * 8, f);
         }
     }
 }
 
 // dx = rstd * (g - mean(g) - xhat * mean(g * xhat)) (+ dres), g = gamma * dy
-// partial param grads: pg[blockIdx.x][0][c] += dy*xhat, pg[blockIdx.x][1][c] += dy   (kMaxV vectors per lane)
-template <int kMaxV>
-__global__ void __launch_bounds__(256) ln_bwd_kernel(const __nv_bfloat16* __restrict__ x,
-                                                     const __nv_bfloat16* __restrict__ dy, int M, int C,
-                                                     const float* __restrict__ gamma, const float* __restrict__ stats,
-                                                     const __nv_bfloat16* __restrict__ dres,
-                                                     __nv_bfloat16* __restrict__ dx, float* __restrict__ pg) {
-    extern __shared__ float sh[];  // [2][C]
+// partial param grads: pg[blockIdx.x][0][c] = sum_rows dy*xhat, pg[blockIdx.x][1][c] = sum_rows dy
+// 4 warps per block, each streaming rows with x / dy / dres held packed in registers (all loads of a row in flight
+// before the first use); per-lane fp32 accumulators for the parameter gradients.
+template <int kMaxV, bool kParamGrads>
+__global__ void __launch_bounds__(128, (kMaxV >= 5 && kParamGrads) ? 2 : 3) ln_bwd_kernel(const __nv_bfloat16* __restrict__ x,
+                                                        const __nv_bfloat16* __restrict__ dy, int M, int C,
+                                                        const float* __restrict__ gamma, const float* __restrict__ stats,
+                                                        const __nv_bfloat16* __restrict__ dres,
+                                                        __nv_bfloat16* __restrict__ dx, float* __restrict__ pg) {
+    extern __shared__ float sh[];  // gamma [C] ; later [2][C] partial sums
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int cv = C / 8;
-    float ag[kMaxV][8], ab[kMaxV][8];
+    const float inv_c = 1.0f / (float)C;
+    for (int i = threadIdx.x; i < C; i += blockDim.x) sh[i] = gamma ? gamma[i] : 1.0f;
+    __syncthreads();
+    float ag[kParamGrads ? kMaxV : 1][8], ab[kParamGrads ? kMaxV : 1][8];
 #pragma unroll
-    for (int k = 0; k < kMaxV; ++k)
+    for (int k = 0; k < (kParamGrads ? kMaxV : 1); ++k)
 #pragma unroll
         for (int j = 0; j < 8; ++j) ag[k][j] = ab[k][j] = 0.f;
-    for (int row = blockIdx.x * 8 + warp; row < M; row += gridDim.x * 8) {
-        const float mean = stats[(size_t)row * 2], rstd = stats[(size_t)row * 2 + 1];
+    for (int row = blockIdx.x * 4 + warp; row < M; row += gridDim.x * 4) {
         const __nv_bfloat16* xr = x + (size_t)row * C;
         const __nv_bfloat16* dr = dy + (size_t)row * C;
-        float xh[kMaxV][8], gg[kMaxV][8];
+        uint4 rx[kMaxV], rd[kMaxV], rr[kMaxV];
+#pragma unroll
+        for (int k = 0; k < kMaxV; ++k) {
+            const int v = lane + k * 32;
+            const bool ok = v < cv;
+            rx[k] = ok ? *reinterpret_cast<const uint4*>(xr + v * 8) : make_uint4(0, 0, 0, 0);
+            rd[k] = ok ? *reinterpret_cast<const uint4*>(dr + v * 8) : make_uint4(0, 0, 0, 0);
+            rr[k] = (ok && dres) ? *reinterpret_cast<const uint4*>(dres + (size_t)row * C + v * 8) : make_uint4(0, 0, 0, 0);
+        }
+        const float mean = stats[(size_t)row * 2], rstd = stats[(size_t)row * 2 + 1];
         float s1 = 0.f, s2 = 0.f;
 #pragma unroll
         for (int k = 0; k < kMaxV; ++k) {
             const int v = lane + k * 32;
             if (v < cv) {
-                float f[8], d[8];
-                ld8(xr + v * 8, f);
-                ld8(dr + v * 8, d);
+                float f[8], d[8], ga[8];
+                unpack8(rx[k], f);
+                unpack8(rd[k], d);
+                ldf8(sh + v * 8, ga);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     const float h = (f[j] - mean) * rstd;
-                    const float gmul = gamma ? gamma[v * 8 + j] : 1.0f;
-                    const float gv = d[j] * gmul;
-                    xh[k][j] = h;
-                    gg[k][j] = gv;
+                    const float gv = d[j] * ga[j];
                     s1 += gv;
                     s2 = fmaf(gv, h, s2);
-                    ag[k][j] = fmaf(d[j], h, ag[k][j]);
-                    ab[k][j] += d[j];
+                    if (kParamGrads) {
+                        ag[k][j] = fmaf(d[j], h, ag[k][j]);
+                        ab[k][j] += d[j];
+                    }
                 }
             }
         }
-        s1 = warp_sum(s1) / (float)C;
-        s2 = warp_sum(s2) / (float)C;
+        s1 = warp_sum(s1) * inv_c;
+        s2 = warp_sum(s2) * inv_c;
 #pragma unroll
         for (int k = 0; k < kMaxV; ++k) {
             const int v = lane + k * 32;
             if (v < cv) {
-                float o[8];
+                float f[8], d[8], ga[8], e[8], o[8];
+                unpack8(rx[k], f);
+                unpack8(rd[k], d);
+                unpack8(rr[k], e);
+                ldf8(sh + v * 8, ga);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) o[j] = rstd * (gg[k][j] - s1 - xh[k][j] * s2);
-                if (dres) {
-                    float e[8];
-                    ld8(dres + (size_t)row * C + v * 8, e);
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) o[j] += e[j];
+                for (int j = 0; j < 8; ++j) {
+                    const float h = (f[j] - mean) * rstd;
+                    o[j] = rstd * (d[j] * ga[j] - s1 - h * s2) + e[j];
                 }
                 st8(dx + (size_t)row * C + v * 8, o);
             }
         }
     }
-    if (pg) {
+    if (kParamGrads) {
+        __syncthreads();  // everyone is done reading gamma from sh
         for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sh[i] = 0.f;
         __syncthreads();
 #pragma unroll
@@ -413,6 +471,30 @@ __global__ void colsum_partials_kernel(const float* __restrict__ partial, int P,
     float a = 0.f;
     for (int p = 0; p < P; ++p) a += partial[(size_t)p * stride + c];
     out[c] = accumulate ? out[c] + a : a;
+}
+
+// LayerNorm parameter gradients: partial [P][2][C] -> dgamma[c] += sum_p partial[p][0][c], dbeta[c] += sum_p partial[p][1][c].
+// grid (ceil(2C/128), slices): each block sums its slice of p and adds atomically (outputs pre-zeroed unless accumulating).
+__global__ void __launch_bounds__(128) ln_param_reduce_kernel(const float* __restrict__ partial, int P, int C, int p_per,
+                                                              float* __restrict__ dgamma, float* __restrict__ dbeta) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= 2 * C) return;
+    const int p0 = blockIdx.y * p_per, p1 = min(P, p0 + p_per);
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int p = p0;
+    for (; p + 3 < p1; p += 4) {
+        a0 += partial[(size_t)p * 2 * C + c];
+        a1 += partial[(size_t)(p + 1) * 2 * C + c];
+        a2 += partial[(size_t)(p + 2) * 2 * C + c];
+        a3 += partial[(size_t)(p + 3) * 2 * C + c];
+    }
+    for (; p < p1; ++p) a0 += partial[(size_t)p * 2 * C + c];
+    const float a = (a0 + a1) + (a2 + a3);
+    if (c < C) {
+        if (dgamma) atomicAdd(&dgamma[c], a);
+    } else {
+        if (dbeta) atomicAdd(&dbeta[c - C], a);
+    }
 }
 
 static int ln_grid(int M) {
@@ -495,16 +577,31 @@ extern "C" int uwu_layernorm_fwd(const void* x, int32_t M, int32_t C, float eps,
     UWU_CHECK_ARG(M >= 0 && C > 0 && C % 8 == 0, "uwu_layernorm_fwd: bad shape M=%d C=%d (C must be a multiple of 8)", M, C);
     if (M == 0) return UWU_OK;
     UWU_CHECK_ARG(x && y, "uwu_layernorm_fwd: null pointer");
-    ln_fwd_kernel<<<ln_grid(M), 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), M, C, eps, gamma, beta,
-                                                   mod_scale, mod_shift, rows_per_mod > 0 ? rows_per_mod : 1,
-                                                   reinterpret_cast<__nv_bfloat16*>(y), stats);
+    UWU_CHECK_ARG(C <= 8 * 32 * 8, "uwu_layernorm_fwd: C=%d > 2048 unsupported", C);
+    const auto* xp = reinterpret_cast<const __nv_bfloat16*>(x);
+    auto* yp = reinterpret_cast<__nv_bfloat16*>(y);
+    const int rpm = rows_per_mod > 0 ? rows_per_mod : 1;
+    const int cv = C / 8;
+#define UWU_LN_FWD(V) ln_fwd_kernel<V><<<ln_grid(M), 256, 0, stream>>>(xp, M, C, eps, gamma, beta, mod_scale, mod_shift, rpm, yp, stats)
+    if (cv <= 32) UWU_LN_FWD(1);
+    else if (cv <= 64) UWU_LN_FWD(2);
+    else if (cv <= 96) UWU_LN_FWD(3);
+    else if (cv <= 160) UWU_LN_FWD(5);
+    else UWU_LN_FWD(8);
+#undef UWU_LN_FWD
     UWU_CHECK_LAUNCH();
     return UWU_OK;
 }
 
+static int ln_bwd_grid(int M) {
+    int blocks = (M + 3) / 4;
+    const int cap = sm_count() * 3;
+    return blocks < cap ? blocks : cap;
+}
+
 extern "C" int64_t uwu_layernorm_bwd_workspace_floats(int32_t M, int32_t C) {
     if (M <= 0 || C <= 0) return 0;
-    return (int64_t)ln_grid(M) * 2 * C;
+    return (int64_t)ln_bwd_grid(M) * 2 * C;
 }
 
 extern "C" int uwu_layernorm_bwd(const void* x, const void* dy, int32_t M, int32_t C, const float* gamma,
@@ -516,7 +613,7 @@ extern "C" int uwu_layernorm_bwd(const void* x, const void* dy, int32_t M, int32
     UWU_CHECK_ARG(x && dy && dx && stats, "uwu_layernorm_bwd: null pointer");
     const bool want_pg = dgamma != nullptr || dbeta != nullptr;
     UWU_CHECK_ARG(!want_pg || workspace, "uwu_layernorm_bwd: workspace required for parameter gradients");
-    const int grid = ln_grid(M);
+    const int grid = ln_bwd_grid(M);
     const int cv = C / 8;
     const auto* xp = reinterpret_cast<const __nv_bfloat16*>(x);
     const auto* dyp = reinterpret_cast<const __nv_bfloat16*>(dy);
@@ -524,22 +621,30 @@ extern "C" int uwu_layernorm_bwd(const void* x, const void* dy, int32_t M, int32
     auto* dxp = reinterpret_cast<__nv_bfloat16*>(dx);
     float* pg = want_pg ? workspace : nullptr;
     const size_t sm = 2 * C * sizeof(float);
-    if (cv <= 64)
-        ln_bwd_kernel<2><<<grid, 256, sm, stream>>>(xp, dyp, M, C, gamma, stats, rp, dxp, pg);
-    else if (cv <= 96)
-        ln_bwd_kernel<3><<<grid, 256, sm, stream>>>(xp, dyp, M, C, gamma, stats, rp, dxp, pg);
-    else
-        ln_bwd_kernel<5><<<grid, 256, sm, stream>>>(xp, dyp, M, C, gamma, stats, rp, dxp, pg);
+#define UWU_LN_BWD(V)                                                                                          \
+    do {                                                                                                       \
+        if (want_pg)                                                                                           \
+            ln_bwd_kernel<V, true><<<grid, 128, sm, stream>>>(xp, dyp, M, C, gamma, stats, rp, dxp, pg);      \
+        else                                                                                                   \
+            ln_bwd_kernel<V, false><<<grid, 128, sm, stream>>>(xp, dyp, M, C, gamma, stats, rp, dxp, pg);     \
+    } while (0)
+    if (cv <= 32) UWU_LN_BWD(1);
+    else if (cv <= 64) UWU_LN_BWD(2);
+    else if (cv <= 96) UWU_LN_BWD(3);
+    else UWU_LN_BWD(5);
+#undef UWU_LN_BWD
     UWU_CHECK_LAUNCH();
     if (want_pg) {
-        if (dgamma) {
-            colsum_partials_kernel<<<(C + 127) / 128, 128, 0, stream>>>(pg, grid, 2 * C, C, accumulate, dgamma);
-            UWU_CHECK_LAUNCH();
+        if (!accumulate) {
+            if (dgamma) UWU_CHECK_CUDA(cudaMemsetAsync(dgamma, 0, (size_t)C * 4, stream));
+            if (dbeta) UWU_CHECK_CUDA(cudaMemsetAsync(dbeta, 0, (size_t)C * 4, stream));
         }
-        if (dbeta) {
-            colsum_partials_kernel<<<(C + 127) / 128, 128, 0, stream>>>(pg + C, grid, 2 * C, C, accumulate, dbeta);
-            UWU_CHECK_LAUNCH();
-        }
+        int slices = 16;
+        if (slices > grid) slices = grid;
+        const int p_per = (grid + slices - 1) / slices;
+        slices = (grid + p_per - 1) / p_per;
+        ln_param_reduce_kernel<<<dim3((2 * C + 127) / 128, slices), 128, 0, stream>>>(pg, grid, C, p_per, dgamma, dbeta);
+        UWU_CHECK_LAUNCH();
     }
     return UWU_OK;
 }

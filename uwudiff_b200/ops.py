@@ -44,7 +44,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, M: int, N: int, K: int, *, a_layout: 
          bias_rows: Optional[torch.Tensor] = None, rows_per_bias: int = 1, residual: Optional[torch.Tensor] = None,
          alpha: float = 1.0, accumulate: bool = False, block_n: int = 0, out2: Optional[torch.Tensor] = None,
          n_split: int = 0, conv: Optional[dict] = None, a2: Optional[torch.Tensor] = None,
-         dbg: Optional[dict] = None) -> torch.Tensor:
+         dbg: Optional[dict] = None, stream_k: int = -1) -> torch.Tensor:
     """out[M,N] = alpha * A·Bᵀ + bias + bias_rows + residual (see uwu_gemm in include/uwu_b200.h)."""
     _req_cuda(a, b, out, bias, bias_rows, residual, out2, a2)
     assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16, "GEMM operands must be bf16"
@@ -79,7 +79,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, M: int, N: int, K: int, *, a_layout: 
     if residual is not None:
         assert residual.dtype == torch.bfloat16
         d.residual, d.ldr = _ptr(residual), residual.stride(0) if residual.dim() == 2 else N
-    d.alpha, d.accumulate, d.block_n = alpha, int(accumulate), block_n
+    d.alpha, d.accumulate, d.block_n, d.stream_k = alpha, int(accumulate), block_n, stream_k
     if dbg:
         for k, v in dbg.items():
             setattr(d, "dbg_" + k, v)

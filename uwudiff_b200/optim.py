@@ -26,6 +26,7 @@ class FusedAdamW(torch.optim.Optimizer):
         super().__init__(params, defaults)
         self.max_grad_norm = max_grad_norm
         self._tables = None
+        self._step = 0
         self.last_norm = None  # device tensor {norm, clip coefficient} of the latest step
 
     # ---- device tables (built once; parameters, gradients and moments must keep their storage) ----------------
@@ -64,7 +65,8 @@ class FusedAdamW(torch.optim.Optimizer):
             ))
         self._tables = groups
         self._norm_out = torch.ones((2,), dtype=torch.float32, device=groups[0]["device"]) if groups else None
-        self._step = max((int(self.state[p]["step"]) for g in groups for p in g["params"]), default=0)
+        # a rebuild (gradient storage replaced) must not restart the bias-correction counter
+        self._step = max([getattr(self, "_step", 0)] + [int(self.state[p]["step"]) for g in groups for p in g["params"]])
 
     def _check_storage(self):
         for t in self._tables:
@@ -121,6 +123,7 @@ class FusedAdamW(torch.optim.Optimizer):
     def load_state_dict(self, sd):
         super().load_state_dict(sd)
         self._tables = None
+        self._step = 0  # re-read from the loaded per-parameter `step` entries
 
     def launches_per_step(self) -> int:
         n = len(self._tables or [])
