@@ -105,6 +105,28 @@ def case_lin():
         tf(f"torch.matmul M{M} N{N} K{K}", timeit(lambda: torch.matmul(a, b.t())), 2.0 * M * N * K)
 
 
+def case_lin_cold():
+    """Same GEMMs with L2 flushed (a 512 MB copy) before every timed launch: the in-step condition for weights."""
+    big = torch.empty(256 << 20, device=dev, dtype=torch.uint8)
+    big2 = torch.empty_like(big)
+    for (M, N, K) in [(16384, 1280, 1280), (16384, 10240, 1280), (16384, 1280, 5120), (65536, 640, 640)]:
+        a, b = mk(M, K), mk(N, K)
+        out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+        res = mk(M, N)
+        for name, kw in (("plain", {}), ("residual", {"residual": res})):
+            ts = []
+            for it in range(8):
+                big2.copy_(big)
+                s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s.record()
+                ops.gemm(a, b, M, N, K, out=out, **kw)
+                e.record()
+                torch.cuda.synchronize()
+                ts.append(s.elapsed_time(e) * 1e3)
+            ts = sorted(ts[2:])
+            tf(f"lin cold-L2 {name} M{M} N{N} K{K} (median of 6)", ts[len(ts) // 2], 2.0 * M * N * K)
+
+
 def case_attn():
     for (B, heads, L, Lk) in [(16, 10, 4096, 4096), (16, 20, 1024, 1024), (16, 10, 4096, 77), (16, 20, 1024, 77)]:
         C = heads * 64

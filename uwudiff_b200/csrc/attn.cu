@@ -1,7 +1,8 @@
 // Flash-style attention forward and backward on tcgen05 / TMEM / TMA for sm_100a (head_dim 64, bf16, fp32 softmax).
 //
 //   forward : O = softmax(scale * Q K^T) V, LSE      one CTA = 2 x 128 query rows of one (batch, head), ping-ponged
-//   backward: dQ, dK, dV                              one CTA = 128 keys of one (batch, head), loops over query tiles
+//   backward: dK, dV                                  pass 1: one CTA = 128 keys of one (batch, head), loops over query tiles
+//             dQ                                      pass 2: one CTA = 128 queries, loops over key tiles (S / dP recomputed)
 //
 // Q/K/V/O live in token-major activations [B*L, ld] with head h in columns [64h, 64h+64) (exactly how the fused
 // QKV projection GEMM writes them), so no permutes are needed: 3-D tensor maps {64h.., l, b} pick the head slice.
@@ -10,10 +11,10 @@
 //   S = Q K^T lands in TMEM (128 lanes x 128 fp32 columns per tile); each softmax thread owns one query row
 //   (tcgen05.ld 32x32b), writes P as bf16 into 128B-swizzled shared memory, the P V product goes to a second TMEM
 //   region and is folded into fp32 register accumulators with the running-max rescale.
-// backward roles: warp 0 TMA, warp 1 MMA, warps 2-9 compute.  Per query tile: S^T = K Q^T and dP^T = V dO^T in TMEM
-//   (thread = key row), P^T = exp2(S^T*c - lse), dS^T = P^T o (dP^T - delta) written to swizzled smem as bf16,
-//   then dV += P^T dO, dK += dS^T Q (TMEM accumulators over the whole loop) and dQ_tile = dS K, which is reduced
-//   into an fp32 scratch with one 32 KiB cp.reduce.async.bulk per tile (no per-element atomics).
+// backward roles: warp 0 TMA, warp 1 MMA, warps 2-9 compute.  Pass 1, per query tile: S^T = K Q^T and dP^T = V dO^T in
+//   TMEM (thread = key row), P^T = exp2(S^T*c - lse), dS^T = P^T o (dP^T - delta) written to swizzled smem as bf16, then
+//   dV += P^T dO and dK += dS^T Q (TMEM accumulators over the whole loop).  Pass 2 mirrors it with the roles of queries
+//   and keys swapped (thread = query row) and accumulates dQ += dS K.  No cross-CTA reduction, no fp32 scratch.
 //
 // Replaces F.scaled_dot_product_attention under diffusers' AttnProcessor2_0 (the in-tree copy of that flow is
 // src/duwu/modules/rope_unet.py:76-175; SDPA call at :151) for attn1 (self) and attn2 (cross, Lk = 77).
@@ -46,11 +47,12 @@ struct AttnFwdArgs {
     float* lse;  // [B, heads, Lq_pad]
 };
 
-static constexpr int FWD_SQ = 0;                  // 2 query tiles
-static constexpr int FWD_SK = 2 * AT_TILE;        // 2 stages
-static constexpr int FWD_SV = 4 * AT_TILE;        // 2 stages
-static constexpr int FWD_SP = 6 * AT_TILE;        // 2 tiles x [128 x 128] bf16
-static constexpr int FWD_BAR = 10 * AT_TILE;      // 163840
+static constexpr int FWD_ST = 4;                            // K / V stages (TMA runs up to 4 key tiles ahead)
+static constexpr int FWD_SQ = 0;                            // 2 query tiles
+static constexpr int FWD_SK = 2 * AT_TILE;                  // FWD_ST stages
+static constexpr int FWD_SV = (2 + FWD_ST) * AT_TILE;       // FWD_ST stages
+static constexpr int FWD_SP = (2 + 2 * FWD_ST) * AT_TILE;   // 2 tiles x [128 x 128] bf16
+static constexpr int FWD_BAR = (6 + 2 * FWD_ST) * AT_TILE;
 static constexpr int FWD_SMEM = FWD_BAR + 256 + 1024;
 static constexpr int FWD_THREADS = 320;
 
@@ -58,15 +60,15 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) attn_fwd_kernel(const __grid_c
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = align1024(smem_raw);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + FWD_BAR);
-    uint64_t* q_full = bars;        // [1]
-    uint64_t* k_full = bars + 1;    // [2]
-    uint64_t* k_empty = bars + 3;   // [2]
-    uint64_t* v_full = bars + 5;    // [2]
-    uint64_t* v_empty = bars + 7;   // [2]
-    uint64_t* s_full = bars + 9;    // [2] per tile
-    uint64_t* p_full = bars + 11;   // [2]
-    uint64_t* pv_full = bars + 13;  // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
+    uint64_t* q_full = bars;                      // [1]
+    uint64_t* k_full = bars + 1;                  // [FWD_ST]
+    uint64_t* k_empty = k_full + FWD_ST;          // [FWD_ST]
+    uint64_t* v_full = k_empty + FWD_ST;          // [FWD_ST]
+    uint64_t* v_empty = v_full + FWD_ST;          // [FWD_ST]
+    uint64_t* s_full = v_empty + FWD_ST;          // [2] per tile
+    uint64_t* p_full = s_full + 2;                // [2]
+    uint64_t* pv_full = p_full + 2;               // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_full + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q0 = blockIdx.x * 256, h = blockIdx.y, b = blockIdx.z;
@@ -80,11 +82,13 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) attn_fwd_kernel(const __grid_c
     }
     if (warp == 1 && lane == 0) {
         mbar_init(q_full, 1);
-        for (int s = 0; s < 2; ++s) {
+        for (int s = 0; s < FWD_ST; ++s) {
             mbar_init(&k_full[s], 1);
             mbar_init(&k_empty[s], 1);
             mbar_init(&v_full[s], 1);
             mbar_init(&v_empty[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
             mbar_init(&s_full[s], 1);
             mbar_init(&p_full[s], 4);
             mbar_init(&pv_full[s], 1);
@@ -107,8 +111,8 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) attn_fwd_kernel(const __grid_c
             tma_load_3d(smem + FWD_SQ, &p.tmQ, q_full, h * 64, q0, b);
             if (ntiles == 2) tma_load_3d(smem + FWD_SQ + AT_TILE, &p.tmQ, q_full, h * 64, q0 + 128, b);
             for (int j = 0; j < nkv; ++j) {
-                const int s = j & 1;
-                const uint32_t ph = (uint32_t)((j >> 1) & 1);
+                const int s = j % FWD_ST;
+                const uint32_t ph = (uint32_t)((j / FWD_ST) & 1);
                 mbar_wait(&k_empty[s], ph ^ 1);
                 mbar_expect_tx(&k_full[s], AT_TILE);
                 tma_load_3d(smem + FWD_SK + s * AT_TILE, &p.tmK, &k_full[s], h * 64, j * 128, b);
@@ -139,12 +143,12 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) attn_fwd_kernel(const __grid_c
             }
             umma_commit(&k_empty[0]);
             for (int j = 0; j < nkv; ++j) {
-                const int s = j & 1;
-                const uint32_t ph = (uint32_t)((j >> 1) & 1);
+                const int s = j % FWD_ST;
+                const uint32_t ph = (uint32_t)((j / FWD_ST) & 1);
                 const bool has_next = j + 1 < nkv;
-                const int s1 = (j + 1) & 1;
+                const int s1 = (j + 1) % FWD_ST;
                 mbar_wait(&v_full[s], ph);
-                if (has_next) mbar_wait(&k_full[s1], (uint32_t)(((j + 1) >> 1) & 1));
+                if (has_next) mbar_wait(&k_full[s1], (uint32_t)(((j + 1) / FWD_ST) & 1));
                 for (int t = 0; t < ntiles; ++t) {
                     mbar_wait(&p_full[t], (uint32_t)(j & 1));
                     tc_fence_after();
@@ -302,76 +306,65 @@ __global__ void attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ o, long l
     lse2[oi] = lse[oi] * LOG2E;
 }
 
-// dq[b*Lq+q, 64h+d] = scale * acc[b,h,q/128, d/4, q%128, d%4]
-__global__ void attn_bwd_dq_convert_kernel(const float* __restrict__ acc, int B, int heads, int Lq, int nqt, float scale,
-                                           __nv_bfloat16* __restrict__ dq, long long lddq) {
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // one 8-wide d chunk per thread
-    const long long total = (long long)B * Lq * heads * 8;
-    if (idx >= total) return;
-    const int c8 = (int)(idx & 7);
-    long long r = idx >> 3;
-    const int h = (int)(r % heads);
-    r /= heads;
-    const int q = (int)(r % Lq);
-    const int b = (int)(r / Lq);
-    const size_t tile = (((size_t)b * heads + h) * nqt + (q >> 7)) * (16 * 128 * 4);
-    const float4 f0 = *reinterpret_cast<const float4*>(acc + tile + ((size_t)(2 * c8) * 128 + (q & 127)) * 4);
-    const float4 f1 = *reinterpret_cast<const float4*>(acc + tile + ((size_t)(2 * c8 + 1) * 128 + (q & 127)) * 4);
-    uint4 u;
-    u.x = pack_bf16(f0.x * scale, f0.y * scale);
-    u.y = pack_bf16(f0.z * scale, f0.w * scale);
-    u.z = pack_bf16(f1.x * scale, f1.y * scale);
-    u.w = pack_bf16(f1.z * scale, f1.w * scale);
-    *reinterpret_cast<uint4*>(dq + ((size_t)b * Lq + q) * lddq + h * 64 + c8 * 8) = u;
-}
-
 struct AttnBwdArgs {
     CUtensorMap tmQ, tmK, tmV, tmdO;
     int Lq, Lk, heads, Lq_pad;
     float scale, scale_log2;
     const float* lse2;   // [B, heads, Lq_pad]
     const float* delta;  // [B, heads, Lq_pad]
-    float* dq_acc;       // [B, heads, Lq_pad/128, 16, 128, 4]
+    __nv_bfloat16* dq;
+    long long lddq;
     __nv_bfloat16* dk;
     long long lddk;
     __nv_bfloat16* dv;
     long long lddv;
 };
 
-static constexpr int BWD_SK = 0;
-static constexpr int BWD_SV = AT_TILE;
-static constexpr int BWD_SQ = 2 * AT_TILE;    // 2 stages
-static constexpr int BWD_SDO = 4 * AT_TILE;   // 2 stages
-static constexpr int BWD_SPT = 6 * AT_TILE;   // [128 keys x 128 q] bf16
-static constexpr int BWD_SDS = 8 * AT_TILE;   // [128 keys x 128 q] bf16
-static constexpr int BWD_SDQ = 10 * AT_TILE;  // fp32 staging [16][128][4]
-static constexpr int BWD_SLSE = 12 * AT_TILE; // 2 stages x 128 floats
-static constexpr int BWD_SDEL = BWD_SLSE + 1024;
-static constexpr int BWD_BAR = BWD_SDEL + 1024;
-static constexpr int BWD_SMEM = BWD_BAR + 256 + 1024;
+// Shared-memory plan: two resident operand tiles, kStages x two streamed operand tiles, P / dS tiles.
+static constexpr int BWD_SR0 = 0;            // resident 0: K (dK/dV pass) or Q  (dQ pass)
+static constexpr int BWD_SR1 = AT_TILE;      // resident 1: V              or dO
+static constexpr int BWD_SDS = 2 * AT_TILE;  // dS [128 queries x 128 keys] bf16, two [128 x 64] K-major tiles
+static constexpr int BWD_SP = 4 * AT_TILE;   // P, same layout (dK/dV pass only)
+template <bool kDQ>
+struct BwdCfg {
+    static constexpr int kStages = kDQ ? 4 : 3;
+    static constexpr int SS0 = (kDQ ? 4 : 6) * AT_TILE;  // streamed 0: Q (dK/dV pass) or K (dQ pass)
+    static constexpr int SS1 = SS0 + kStages * AT_TILE;   // streamed 1: dO             or V
+    static constexpr int BAR = SS1 + kStages * AT_TILE;
+    static constexpr int SMEM = BAR + 256 + 1024;
+};
 static constexpr int BWD_THREADS = 320;
-// TMEM columns: S^T [0,128) dP^T [128,256) dV [256,320) dK [320,384) dQ [384,448)
+// TMEM columns: S [0,128) dP [128,256) acc0 [256,320) acc1 [320,384)
 
+// Two passes over the (query tile, key tile) pairs, neither needs a cross-CTA reduction or an fp32 scratch:
+//   kDQ = false: CTA = 128 keys of one (batch, head), streams the query tiles (3 stages): dV += P^T dO, dK += dS^T Q
+//   kDQ = true : CTA = 128 queries, streams the key tiles (4 stages):                     dQ += dS K
+// In both, S = Q K^T and dP = dO V^T land in TMEM with one thread per QUERY row, so lse / delta are per-thread scalars;
+// P = exp2(S c - lse) and dS = P o (dP - delta) go to 128B-swizzled smem as [query][key] bf16, which the accumulating
+// products read K-major (dQ) or MN-major (dV, dK: the transposes, for free).  S / dP are recomputed in the second pass
+// (7 instead of 5 tile products per pair): the single-pass version was bound by the streamed-operand latency and the
+// per-iteration handshakes, not by the tensor pipe (profiles/r01_attn_bwd_ncu.md).  The MMA warp issues S / dP of
+// iteration i+1 before the accumulating products of iteration i, so the exp / dS math overlaps the tensor pipe.
+template <bool kDQ>
 __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_kernel(const __grid_constant__ AttnBwdArgs p) {
+    using Cfg = BwdCfg<kDQ>;
+    constexpr int kStages = Cfg::kStages;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = align1024(smem_raw);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BWD_BAR);
-    uint64_t* kv_full = bars;        // [1]
-    uint64_t* qdo_full = bars + 1;   // [2]
-    uint64_t* qdo_empty = bars + 3;  // [2]
-    uint64_t* sdp_full = bars + 5;
-    uint64_t* sdp_empty = bars + 6;
-    uint64_t* pds_full = bars + 7;
-    uint64_t* pds_empty = bars + 8;
-    uint64_t* dq_full = bars + 9;
-    uint64_t* dq_empty = bars + 10;
-    uint64_t* acc_full = bars + 11;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::BAR);
+    uint64_t* res_full = bars;       // [1]
+    uint64_t* st_full = bars + 1;    // [4]
+    uint64_t* st_empty = bars + 5;   // [4]
+    uint64_t* sdp_full = bars + 9;
+    uint64_t* sdp_empty = bars + 10;
+    uint64_t* pds_full = bars + 11;
+    uint64_t* pds_empty = bars + 12;
+    uint64_t* acc_full = bars + 13;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int k0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
-    const int nq = (p.Lq + 127) / 128;
-    const int nqt = p.Lq_pad / 128;
+    const int r0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;  // first resident row (key or query)
+    const int n_iter = kDQ ? (p.Lk + 127) / 128 : (p.Lq + 127) / 128;
     const size_t bh = (size_t)b * p.heads + h;
 
     if (warp == 0 && lane == 0) {
@@ -381,17 +374,15 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_kernel(const __grid_c
         tma_prefetch_desc(&p.tmdO);
     }
     if (warp == 1 && lane == 0) {
-        mbar_init(kv_full, 1);
-        for (int s = 0; s < 2; ++s) {
-            mbar_init(&qdo_full[s], 1);
-            mbar_init(&qdo_empty[s], 1);
+        mbar_init(res_full, 1);
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(&st_full[s], 1);
+            mbar_init(&st_empty[s], 1);
         }
         mbar_init(sdp_full, 1);
         mbar_init(sdp_empty, 8);
         mbar_init(pds_full, 8);
         mbar_init(pds_empty, 1);
-        mbar_init(dq_full, 1);
-        mbar_init(dq_empty, 8);
         mbar_init(acc_full, 1);
         fence_barrier_init();
     }
@@ -406,73 +397,91 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_kernel(const __grid_c
 
     if (warp == 0) {
         if (lane == 0) {
-            mbar_expect_tx(kv_full, 2 * AT_TILE);
-            tma_load_3d(smem + BWD_SK, &p.tmK, kv_full, h * 64, k0, b);
-            tma_load_3d(smem + BWD_SV, &p.tmV, kv_full, h * 64, k0, b);
-            for (int i = 0; i < nq; ++i) {
-                const int s = i & 1;
-                const uint32_t ph = (uint32_t)((i >> 1) & 1);
-                mbar_wait(&qdo_empty[s], ph ^ 1);
-                mbar_expect_tx(&qdo_full[s], 2 * AT_TILE + 1024);
-                tma_load_3d(smem + BWD_SQ + s * AT_TILE, &p.tmQ, &qdo_full[s], h * 64, i * 128, b);
-                tma_load_3d(smem + BWD_SDO + s * AT_TILE, &p.tmdO, &qdo_full[s], h * 64, i * 128, b);
-                bulk_load_1d(smem + BWD_SLSE + s * 512, p.lse2 + bh * p.Lq_pad + (size_t)i * 128, 512, &qdo_full[s]);
-                bulk_load_1d(smem + BWD_SDEL + s * 512, p.delta + bh * p.Lq_pad + (size_t)i * 128, 512, &qdo_full[s]);
+            const CUtensorMap* tmR0 = kDQ ? &p.tmQ : &p.tmK;
+            const CUtensorMap* tmR1 = kDQ ? &p.tmdO : &p.tmV;
+            const CUtensorMap* tmS0 = kDQ ? &p.tmK : &p.tmQ;
+            const CUtensorMap* tmS1 = kDQ ? &p.tmV : &p.tmdO;
+            mbar_expect_tx(res_full, 2 * AT_TILE);
+            tma_load_3d(smem + BWD_SR0, tmR0, res_full, h * 64, r0, b);
+            tma_load_3d(smem + BWD_SR1, tmR1, res_full, h * 64, r0, b);
+            int s = 0;
+            uint32_t ph = 0;
+            for (int i = 0; i < n_iter; ++i) {
+                mbar_wait(&st_empty[s], ph ^ 1);
+                mbar_expect_tx(&st_full[s], 2 * AT_TILE);
+                tma_load_3d(smem + Cfg::SS0 + s * AT_TILE, tmS0, &st_full[s], h * 64, i * 128, b);
+                tma_load_3d(smem + Cfg::SS1 + s * AT_TILE, tmS1, &st_full[s], h * 64, i * 128, b);
+                if (++s == kStages) {
+                    s = 0;
+                    ph ^= 1;
+                }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            const uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);   // S^T, dP^T: both operands K-major
-            const uint32_t idesc_kv = make_idesc_bf16(128, 64, 0, 1);   // dV, dK: A K-major (smem P^T/dS^T), B MN-major
-            const uint32_t idesc_dq = make_idesc_bf16(128, 64, 1, 1);   // dQ: A = dS^T read MN-major, B = K MN-major
-            const uint32_t sk = smem_u32(smem + BWD_SK), sv = smem_u32(smem + BWD_SV), sq = smem_u32(smem + BWD_SQ),
-                           sdo = smem_u32(smem + BWD_SDO), spt = smem_u32(smem + BWD_SPT), sds = smem_u32(smem + BWD_SDS);
-            mbar_wait(kv_full, 0);
-            for (int i = 0; i < nq; ++i) {
-                const int s = i & 1;
-                const uint32_t ph = (uint32_t)((i >> 1) & 1);
-                mbar_wait(&qdo_full[s], ph);
-                mbar_wait(sdp_empty, (uint32_t)((i & 1) ^ 1));
-                tc_fence_after();
-                {
-                    const uint64_t kd = desc_kmajor(sk), vd = desc_kmajor(sv);
-                    const uint64_t qd = desc_kmajor(sq + s * AT_TILE), dod = desc_kmajor(sdo + s * AT_TILE);
+            const uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);              // S, dP: both operands K-major
+            const uint32_t idesc_acc = make_idesc_bf16(128, 64, kDQ ? 0 : 1, 1);  // dQ: A K-major; dV/dK: A MN-major; B MN-major
+            const uint32_t sr0 = smem_u32(smem + BWD_SR0), sr1 = smem_u32(smem + BWD_SR1), ss0 = smem_u32(smem + Cfg::SS0),
+                           ss1 = smem_u32(smem + Cfg::SS1), sp = smem_u32(smem + BWD_SP), sds = smem_u32(smem + BWD_SDS);
+            // S = Q K^T, dP = dO V^T with the query tile as the M operand in both passes
+            auto issue_sdp = [&](int s) {
+                const uint64_t q_d = desc_kmajor(kDQ ? sr0 : ss0 + s * AT_TILE), k_d = desc_kmajor(kDQ ? ss0 + s * AT_TILE : sr0);
+                const uint64_t do_d = desc_kmajor(kDQ ? sr1 : ss1 + s * AT_TILE), v_d = desc_kmajor(kDQ ? ss1 + s * AT_TILE : sr1);
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        umma_bf16(tmem_base + 0u, kd + (uint64_t)(k * 2), qd + (uint64_t)(k * 2), idesc_s, (uint32_t)(k != 0));
+                for (int k = 0; k < 4; ++k)
+                    umma_bf16(tmem_base + 0u, q_d + (uint64_t)(k * 2), k_d + (uint64_t)(k * 2), idesc_s, (uint32_t)(k != 0));
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        umma_bf16(tmem_base + 128u, vd + (uint64_t)(k * 2), dod + (uint64_t)(k * 2), idesc_s, (uint32_t)(k != 0));
+                for (int k = 0; k < 4; ++k)
+                    umma_bf16(tmem_base + 128u, do_d + (uint64_t)(k * 2), v_d + (uint64_t)(k * 2), idesc_s, (uint32_t)(k != 0));
+            };
+            mbar_wait(res_full, 0);
+            mbar_wait(&st_full[0], 0);
+            tc_fence_after();
+            issue_sdp(0);
+            umma_commit(sdp_full);
+            int s = 0, s1 = (kStages > 1) ? 1 : 0;
+            uint32_t ph1 = 0;  // phase of stage s1
+            for (int i = 0; i < n_iter; ++i) {
+                if (i + 1 < n_iter) {
+                    mbar_wait(&st_full[s1], ph1);
+                    mbar_wait(sdp_empty, (uint32_t)(i & 1));  // compute warps have pulled S / dP of iteration i out of TMEM
+                    tc_fence_after();
+                    issue_sdp(s1);
+                    umma_commit(sdp_full);
                 }
-                umma_commit(sdp_full);
                 mbar_wait(pds_full, (uint32_t)(i & 1));
-                mbar_wait(dq_empty, (uint32_t)((i & 1) ^ 1));
                 tc_fence_after();
                 {
-                    const uint64_t dob = desc_mnmajor(sdo + s * AT_TILE, 8192);
-                    const uint64_t qb = desc_mnmajor(sq + s * AT_TILE, 8192);
-                    const uint64_t kb = desc_mnmajor(sk, 8192);
+                    const uint64_t b0 = desc_mnmajor(ss0 + s * AT_TILE, 8192);  // Q (dK) or K (dQ), [rows = reduction, 64 d]
+                    const uint64_t b1 = desc_mnmajor(ss1 + s * AT_TILE, 8192);  // dO (dV)
+                    if (kDQ) {
+                        // dQ[q, d] += sum_key dS[q, key] K[key, d]: A = dS K-major
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        const uint64_t ad = desc_kmajor(spt + (k >> 2) * AT_TILE) + (uint64_t)((k & 3) * 2);
-                        umma_bf16(tmem_base + 256u, ad, dob + (uint64_t)(k * 128), idesc_kv, (uint32_t)((i | k) != 0));
+                        for (int k = 0; k < 8; ++k) {
+                            const uint64_t ad = desc_kmajor(sds + (k >> 2) * AT_TILE) + (uint64_t)((k & 3) * 2);
+                            umma_bf16(tmem_base + 320u, ad, b0 + (uint64_t)(k * 128), idesc_acc, (uint32_t)((i | k) != 0));
+                        }
+                    } else {
+                        // dV[key, d] += sum_q P[q, key] dO[q, d], dK[key, d] += sum_q dS[q, key] Q[q, d]:
+                        // A = P / dS read MN-major (M = key: two 64-key blocks 16 KiB apart, 16 query rows = 2048 B per K step)
+                        const uint64_t ap = desc_mnmajor(sp, 16384), ads = desc_mnmajor(sds, 16384);
+#pragma unroll
+                        for (int k = 0; k < 8; ++k)
+                            umma_bf16(tmem_base + 256u, ap + (uint64_t)(k * 128), b1 + (uint64_t)(k * 128), idesc_acc,
+                                      (uint32_t)((i | k) != 0));
+#pragma unroll
+                        for (int k = 0; k < 8; ++k)
+                            umma_bf16(tmem_base + 320u, ads + (uint64_t)(k * 128), b0 + (uint64_t)(k * 128), idesc_acc,
+                                      (uint32_t)((i | k) != 0));
                     }
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        const uint64_t ad = desc_kmajor(sds + (k >> 2) * AT_TILE) + (uint64_t)((k & 3) * 2);
-                        umma_bf16(tmem_base + 320u, ad, qb + (uint64_t)(k * 128), idesc_kv, (uint32_t)((i | k) != 0));
-                    }
-                    // dQ[q, d] = sum_key dS^T[key, q] K[key, d]: A is dS^T read as MN-major (M = q), two 64-query
-                    // blocks 16 KiB apart (LBO), 16 key rows = 2048 B per UMMA_K step
-                    const uint64_t ad = desc_mnmajor(sds, 16384);
-#pragma unroll
-                    for (int k = 0; k < 8; ++k)
-                        umma_bf16(tmem_base + 384u, ad + (uint64_t)(k * 128), kb + (uint64_t)(k * 128), idesc_dq,
-                                  (uint32_t)(k != 0));
                 }
-                umma_commit(&qdo_empty[s]);
+                umma_commit(&st_empty[s]);
                 umma_commit(pds_empty);
-                umma_commit(dq_full);
+                s = s1;
+                if (++s1 == kStages) {
+                    s1 = 0;
+                    ph1 ^= 1;
+                }
             }
             umma_commit(acc_full);
         }
@@ -480,124 +489,118 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_kernel(const __grid_c
         const int cw = warp - 2;
         const int sub = warp & 3;
         const int half = cw >> 2;
-        const int row = sub * 32 + lane;
+        const int row = sub * 32 + lane;  // query row within the tile == TMEM lane
         const int sw = row & 7;
         const uint32_t lane_addr = (uint32_t)(sub * 32) << 16;
         const float sl2 = p.scale_log2;
-        uint8_t* ptrow = smem + BWD_SPT + half * AT_TILE + row * 128;
+        uint8_t* prow = smem + BWD_SP + half * AT_TILE + row * 128;
         uint8_t* dsrow = smem + BWD_SDS + half * AT_TILE + row * 128;
-        float* stage = reinterpret_cast<float*>(smem + BWD_SDQ);
-        for (int i = 0; i < nq; ++i) {
-            const int s = i & 1;
-            const uint32_t ph = (uint32_t)((i >> 1) & 1);
-            mbar_wait(&qdo_full[s], ph);  // lse2 / delta of this query tile are in smem
+        // lse * log2(e) and delta of this thread's query row (padded rows of the scratch are zero and never written out)
+        const float* lse_p = p.lse2 + bh * p.Lq_pad + row;
+        const float* del_p = p.delta + bh * p.Lq_pad + row;
+        float my_lse = lse_p[kDQ ? r0 : 0], my_delta = del_p[kDQ ? r0 : 0];
+        for (int i = 0; i < n_iter; ++i) {
+            float nx_lse = my_lse, nx_delta = my_delta;
+            if (!kDQ && i + 1 < n_iter) {  // next query tile's scalars, in flight during this tile's math
+                nx_lse = lse_p[(size_t)(i + 1) * 128];
+                nx_delta = del_p[(size_t)(i + 1) * 128];
+            }
             mbar_wait(sdp_full, (uint32_t)(i & 1));
             tc_fence_after();
-            mbar_wait(pds_empty, (uint32_t)((i & 1) ^ 1));
-            const float* l2 = reinterpret_cast<const float*>(smem + BWD_SLSE + s * 512) + half * 64;
-            const float* dl = reinterpret_cast<const float*>(smem + BWD_SDEL + s * 512) + half * 64;
-            const int q_valid = p.Lq - i * 128 - half * 64;  // columns [0, q_valid) of this half are real queries
+            uint4 pu[kDQ ? 1 : 8], du[8];
 #pragma unroll
             for (int cc = 0; cc < 2; ++cc) {
-                uint32_t rs[32], rp[32];
-                tmem_ld32(tmem_base + lane_addr + (uint32_t)(half * 64 + cc * 32), rs);
-                tmem_ld32(tmem_base + lane_addr + 128u + (uint32_t)(half * 64 + cc * 32), rp);
+                // pull 32 S and 32 dP values out of TMEM; after the second half the accumulators go back to the MMA warp
+                uint32_t rs1[32], rp1[32];
+                tmem_ld32(tmem_base + lane_addr + (uint32_t)(half * 64 + cc * 32), rs1);
+                tmem_ld32(tmem_base + lane_addr + 128u + (uint32_t)(half * 64 + cc * 32), rp1);
                 tmem_ld_wait();
-                float pe[32], ds[32];
-#pragma unroll
-                for (int g = 0; g < 8; ++g) {
-                    const float4 lv = *reinterpret_cast<const float4*>(l2 + cc * 32 + g * 4);
-                    const float4 dv4 = *reinterpret_cast<const float4*>(dl + cc * 32 + g * 4);
-                    const float lvv[4] = {lv.x, lv.y, lv.z, lv.w};
-                    const float dvv[4] = {dv4.x, dv4.y, dv4.z, dv4.w};
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const int i2 = g * 4 + e;
-                        float pv = ex2_approx(fmaf(__uint_as_float(rs[i2]), sl2, -lvv[e]));
-                        float dsv = pv * (__uint_as_float(rp[i2]) - dvv[e]);
-                        if (cc * 32 + i2 >= q_valid) {
-                            pv = 0.f;
-                            dsv = 0.f;
-                        }
-                        pe[i2] = pv;
-                        ds[i2] = dsv;
-                    }
+                if (cc == 1) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(sdp_empty);
                 }
 #pragma unroll
                 for (int q4 = 0; q4 < 4; ++q4) {
-                    uint4 u, w;
-                    u.x = pack_bf16(pe[q4 * 8 + 0], pe[q4 * 8 + 1]);
-                    u.y = pack_bf16(pe[q4 * 8 + 2], pe[q4 * 8 + 3]);
-                    u.z = pack_bf16(pe[q4 * 8 + 4], pe[q4 * 8 + 5]);
-                    u.w = pack_bf16(pe[q4 * 8 + 6], pe[q4 * 8 + 7]);
-                    w.x = pack_bf16(ds[q4 * 8 + 0], ds[q4 * 8 + 1]);
-                    w.y = pack_bf16(ds[q4 * 8 + 2], ds[q4 * 8 + 3]);
-                    w.z = pack_bf16(ds[q4 * 8 + 4], ds[q4 * 8 + 5]);
-                    w.w = pack_bf16(ds[q4 * 8 + 6], ds[q4 * 8 + 7]);
-                    const int chunk = ((cc * 4 + q4) ^ sw) << 4;
-                    *reinterpret_cast<uint4*>(ptrow + chunk) = u;
-                    *reinterpret_cast<uint4*>(dsrow + chunk) = w;
+                    float pe[8], ds[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const int i2 = q4 * 8 + e;
+                        pe[e] = ex2_approx(fmaf(__uint_as_float(rs1[i2]), sl2, -my_lse));
+                        ds[e] = pe[e] * (__uint_as_float(rp1[i2]) - my_delta);
+                    }
+                    uint4 w;
+                    w.x = pack_bf16(ds[0], ds[1]);
+                    w.y = pack_bf16(ds[2], ds[3]);
+                    w.z = pack_bf16(ds[4], ds[5]);
+                    w.w = pack_bf16(ds[6], ds[7]);
+                    du[cc * 4 + q4] = w;
+                    if (!kDQ) {
+                        uint4 u;
+                        u.x = pack_bf16(pe[0], pe[1]);
+                        u.y = pack_bf16(pe[2], pe[3]);
+                        u.z = pack_bf16(pe[4], pe[5]);
+                        u.w = pack_bf16(pe[6], pe[7]);
+                        pu[kDQ ? 0 : cc * 4 + q4] = u;
+                    }
                 }
             }
-            tc_fence_before();
+            // the accumulating products of the previous iteration have retired: their smem operands may be overwritten
+            mbar_wait(pds_empty, (uint32_t)((i & 1) ^ 1));
+#pragma unroll
+            for (int c8 = 0; c8 < 8; ++c8) {
+                const int chunk = (c8 ^ sw) << 4;
+                if (!kDQ) *reinterpret_cast<uint4*>(prow + chunk) = pu[kDQ ? 0 : c8];
+                *reinterpret_cast<uint4*>(dsrow + chunk) = du[c8];
+            }
             fence_proxy_async();
             __syncwarp();
-            if (lane == 0) {
-                mbar_arrive(sdp_empty);
-                mbar_arrive(pds_full);
-            }
-            // ---- dQ tile: TMEM -> fp32 staging -> one bulk reduce-add into the scratch ----
-            mbar_wait(dq_full, (uint32_t)(i & 1));
-            tc_fence_after();
-            {
-                uint32_t r[32];
-                tmem_ld32(tmem_base + lane_addr + 384u + (uint32_t)(half * 32), r);
-                tmem_ld_wait();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(dq_empty);
-                named_bar_sync(1, 256);  // previous tile's bulk reduce has finished reading the staging buffer
-#pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    float4 f = make_float4(__uint_as_float(r[c * 4]), __uint_as_float(r[c * 4 + 1]),
-                                           __uint_as_float(r[c * 4 + 2]), __uint_as_float(r[c * 4 + 3]));
-                    *reinterpret_cast<float4*>(stage + ((half * 8 + c) * 128 + row) * 4) = f;
-                }
-                fence_proxy_async();
-                named_bar_sync(1, 256);
-                if (cw == 0 && lane == 0) {
-                    bulk_reduce_add_f32(p.dq_acc + (bh * nqt + i) * (size_t)(16 * 128 * 4), stage, 16 * 128 * 4 * 4);
-                    bulk_commit_group();
-                    bulk_wait_group_read0();
-                }
-            }
+            if (lane == 0) mbar_arrive(pds_full);
+            my_lse = nx_lse;
+            my_delta = nx_delta;
         }
-        // ---- final dV / dK ----
+        // ---- write the accumulators (TMEM lane = key row in the dK/dV pass, query row in the dQ pass) ----
         mbar_wait(acc_full, 0);
         tc_fence_after();
-        const int key = k0 + row;
-#pragma unroll
-        for (int which = 0; which < 2; ++which) {
-            uint32_t r[32];
-            tmem_ld32(tmem_base + lane_addr + 256u + (uint32_t)(which * 64 + half * 32), r);
+        const int r = r0 + row;
+        if (kDQ) {
+            uint32_t v[32];
+            tmem_ld32(tmem_base + lane_addr + 320u + (uint32_t)(half * 32), v);
             tmem_ld_wait();
-            if (key < p.Lk) {
-                const float sc = which ? p.scale : 1.0f;
-                __nv_bfloat16* base = which ? p.dk + ((size_t)b * p.Lk + key) * p.lddk
-                                            : p.dv + ((size_t)b * p.Lk + key) * p.lddv;
-                __nv_bfloat16* op = base + h * 64 + half * 32;
+            if (r < p.Lq) {
+                __nv_bfloat16* op = p.dq + ((size_t)b * p.Lq + r) * p.lddq + h * 64 + half * 32;
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                     uint4 u;
-                    u.x = pack_bf16(__uint_as_float(r[c * 8 + 0]) * sc, __uint_as_float(r[c * 8 + 1]) * sc);
-                    u.y = pack_bf16(__uint_as_float(r[c * 8 + 2]) * sc, __uint_as_float(r[c * 8 + 3]) * sc);
-                    u.z = pack_bf16(__uint_as_float(r[c * 8 + 4]) * sc, __uint_as_float(r[c * 8 + 5]) * sc);
-                    u.w = pack_bf16(__uint_as_float(r[c * 8 + 6]) * sc, __uint_as_float(r[c * 8 + 7]) * sc);
+                    u.x = pack_bf16(__uint_as_float(v[c * 8 + 0]) * p.scale, __uint_as_float(v[c * 8 + 1]) * p.scale);
+                    u.y = pack_bf16(__uint_as_float(v[c * 8 + 2]) * p.scale, __uint_as_float(v[c * 8 + 3]) * p.scale);
+                    u.z = pack_bf16(__uint_as_float(v[c * 8 + 4]) * p.scale, __uint_as_float(v[c * 8 + 5]) * p.scale);
+                    u.w = pack_bf16(__uint_as_float(v[c * 8 + 6]) * p.scale, __uint_as_float(v[c * 8 + 7]) * p.scale);
                     *reinterpret_cast<uint4*>(op + c * 8) = u;
                 }
             }
+        } else {
+#pragma unroll
+            for (int which = 0; which < 2; ++which) {
+                uint32_t v[32];
+                tmem_ld32(tmem_base + lane_addr + 256u + (uint32_t)(which * 64 + half * 32), v);
+                tmem_ld_wait();
+                if (r < p.Lk) {
+                    const float sc = which ? p.scale : 1.0f;
+                    __nv_bfloat16* base = which ? p.dk + ((size_t)b * p.Lk + r) * p.lddk : p.dv + ((size_t)b * p.Lk + r) * p.lddv;
+                    __nv_bfloat16* op = base + h * 64 + half * 32;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        uint4 u;
+                        u.x = pack_bf16(__uint_as_float(v[c * 8 + 0]) * sc, __uint_as_float(v[c * 8 + 1]) * sc);
+                        u.y = pack_bf16(__uint_as_float(v[c * 8 + 2]) * sc, __uint_as_float(v[c * 8 + 3]) * sc);
+                        u.z = pack_bf16(__uint_as_float(v[c * 8 + 4]) * sc, __uint_as_float(v[c * 8 + 5]) * sc);
+                        u.w = pack_bf16(__uint_as_float(v[c * 8 + 6]) * sc, __uint_as_float(v[c * 8 + 7]) * sc);
+                        *reinterpret_cast<uint4*>(op + c * 8) = u;
+                    }
+                }
+            }
         }
-        if (cw == 0 && lane == 0) bulk_wait_group0();  // all dQ reductions have landed before the kernel ends
     }
     tc_fence_before();
     __syncthreads();
@@ -665,7 +668,7 @@ extern "C" int uwu_attn_fwd(const void* q, const void* k, const void* v, void* o
 extern "C" int64_t uwu_attn_bwd_workspace_floats(int32_t B, int32_t heads, int32_t Lq) {
     if (B <= 0 || heads <= 0 || Lq <= 0) return 0;
     const int64_t rows = (int64_t)B * heads * ((Lq + 127) / 128 * 128);
-    return rows * 2 + rows * 64;  // lse2, delta, dq scratch
+    return rows * 2;  // lse * log2(e), delta
 }
 
 extern "C" int uwu_attn_bwd(const void* q, const void* k, const void* v, const void* o, const void* dout, const float* lse,
@@ -685,7 +688,6 @@ extern "C" int uwu_attn_bwd(const void* q, const void* k, const void* v, const v
     const int64_t rows = (int64_t)B * heads * Lq_pad;
     float* lse2 = workspace;
     float* delta = workspace + rows;
-    float* dq_acc = workspace + 2 * rows;
     static thread_local AttnBwdArgs a;
     if (int rc = make_head_map(&a.tmQ, q, heads, Lq, B, ldq, "q")) return rc;
     if (int rc = make_head_map(&a.tmK, k, heads, Lk, B, ldk, "k")) return rc;
@@ -693,10 +695,12 @@ extern "C" int uwu_attn_bwd(const void* q, const void* k, const void* v, const v
     if (int rc = make_head_map(&a.tmdO, dout, heads, Lq, B, lddo, "dout")) return rc;
     a.Lq = Lq; a.Lk = Lk; a.heads = heads; a.Lq_pad = Lq_pad;
     a.scale = scale; a.scale_log2 = scale * LOG2E;
-    a.lse2 = lse2; a.delta = delta; a.dq_acc = dq_acc;
+    a.lse2 = lse2; a.delta = delta;
+    a.dq = reinterpret_cast<__nv_bfloat16*>(dq); a.lddq = lddq;
     a.dk = reinterpret_cast<__nv_bfloat16*>(dk); a.lddk = lddk;
     a.dv = reinterpret_cast<__nv_bfloat16*>(dv); a.lddv = lddv;
-    UWU_CHECK_CUDA(cudaMemsetAsync(workspace, 0, (size_t)(rows * 66) * sizeof(float), stream));
+    if (Lq_pad != Lq)  // padded query rows of the scratch are read (and masked) by the kernels: keep them finite
+        UWU_CHECK_CUDA(cudaMemsetAsync(workspace, 0, (size_t)(rows * 2) * sizeof(float), stream));
     {
         const long long total = (long long)B * Lq * heads;
         attn_bwd_prep_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(
@@ -706,17 +710,13 @@ extern "C" int uwu_attn_bwd(const void* q, const void* k, const void* v, const v
     }
     static bool attr_set = false;
     if (!attr_set) {
-        UWU_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM));
+        UWU_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdCfg<false>::SMEM));
+        UWU_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdCfg<true>::SMEM));
         attr_set = true;
     }
-    dim3 grid((Lk + 127) / 128, heads, B);
-    attn_bwd_kernel<<<grid, BWD_THREADS, BWD_SMEM, stream>>>(a);
+    attn_bwd_kernel<false><<<dim3((Lk + 127) / 128, heads, B), BWD_THREADS, BwdCfg<false>::SMEM, stream>>>(a);  // dK, dV
     UWU_CHECK_LAUNCH();
-    {
-        const long long total = (long long)B * Lq * heads * 8;
-        attn_bwd_dq_convert_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(
-            dq_acc, B, heads, Lq, Lq_pad / 128, scale, reinterpret_cast<__nv_bfloat16*>(dq), lddq);
-        UWU_CHECK_LAUNCH();
-    }
+    attn_bwd_kernel<true><<<dim3((Lq + 127) / 128, heads, B), BWD_THREADS, BwdCfg<true>::SMEM, stream>>>(a);   // dQ
+    UWU_CHECK_LAUNCH();
     return UWU_OK;
 }

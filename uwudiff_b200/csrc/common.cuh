@@ -219,9 +219,9 @@ UWU_DEVINL uint32_t make_idesc_bf16(uint32_t M, uint32_t N, uint32_t a_mn_major,
 // ----------------------------------------------------------------------------------------------
 // math
 // ----------------------------------------------------------------------------------------------
-UWU_DEVINL float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+UWU_DEVINL float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 UWU_DEVINL float silu_grad_f(float x) {
-    float s = 1.0f / (1.0f + __expf(-x));
+    float s = __fdividef(1.0f, 1.0f + __expf(-x));
     return s * (1.0f + x * (1.0f - s));
 }
 UWU_DEVINL float gelu_erf_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }

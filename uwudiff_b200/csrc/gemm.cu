@@ -253,14 +253,31 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
             const int row = m_blk * BLOCK_M + sub * 32 + lane;
             const int n0 = n_blk * p.block_n;
             const int n_end = min(p.N, n0 + p.block_n);
+            const bool row_ok = row < p.M;
+            // The residual does not depend on the accumulator: pull this thread's whole row segment (<= 256 bf16) into
+            // registers BEFORE waiting for the MMAs, so its global-memory latency hides behind the main loop.
+            uint4 rres[8][4];
+            const __nv_bfloat16* rrow = p.residual != nullptr ? p.residual + (size_t)row * p.ldr + n0 : nullptr;
+            const bool res_vec = rrow != nullptr && row_ok && ((reinterpret_cast<uintptr_t>(rrow) & 15) == 0);
+            if (res_vec) {
+#pragma unroll
+                for (int ci = 0; ci < 8; ++ci) {
+                    if (ci * 32 < p.block_n && n0 + ci * 32 + 32 <= n_end) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) rres[ci][q] = *reinterpret_cast<const uint4*>(rrow + ci * 32 + q * 8);
+                    }
+                }
+            }
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
             const uint32_t t_row = tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(acc * ACC_STRIDE);
-            const bool row_ok = row < p.M;
             const float* brow = (p.bias_rows != nullptr && row_ok)
                                     ? p.bias_rows + (size_t)(row / p.rows_per_bias) * p.N
                                     : nullptr;
-            for (int c = 0; c < p.block_n; c += 32) {
+#pragma unroll
+            for (int ci = 0; ci < 8; ++ci) {
+                const int c = ci * 32;
+                if (c >= p.block_n) break;
                 uint32_t r[32];
                 tmem_ld32(t_row + (uint32_t)c, r);
                 tmem_ld_wait();
@@ -283,23 +300,41 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
                 float v[32];
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
+                const bool vec_ok = (ncols == 32);
                 if (p.bias != nullptr) {
+                    const float* bp = p.bias + col0;
+                    if (vec_ok && ((reinterpret_cast<uintptr_t>(bp) & 15) == 0)) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (j < ncols) v[j] += __ldg(p.bias + col0 + j);
+                        for (int q = 0; q < 8; ++q) {
+                            const float4 t = __ldg(reinterpret_cast<const float4*>(bp) + q);
+                            v[q * 4] += t.x; v[q * 4 + 1] += t.y; v[q * 4 + 2] += t.z; v[q * 4 + 3] += t.w;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (j < ncols) v[j] += __ldg(bp + j);
+                    }
                 }
                 if (brow != nullptr) {
+                    const float* bp = brow + col0;
+                    if (vec_ok && ((reinterpret_cast<uintptr_t>(bp) & 15) == 0)) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (j < ncols) v[j] += __ldg(brow + col0 + j);
+                        for (int q = 0; q < 8; ++q) {
+                            const float4 t = __ldg(reinterpret_cast<const float4*>(bp) + q);
+                            v[q * 4] += t.x; v[q * 4 + 1] += t.y; v[q * 4 + 2] += t.z; v[q * 4 + 3] += t.w;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (j < ncols) v[j] += __ldg(bp + j);
+                    }
                 }
-                const bool vec_ok = (ncols == 32);
                 if (p.residual != nullptr) {
                     const __nv_bfloat16* rp = p.residual + (size_t)row * p.ldr + col0;
-                    if (vec_ok && ((reinterpret_cast<uintptr_t>(rp) & 15) == 0)) {
+                    if (vec_ok && res_vec) {
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
-                            uint4 u = *reinterpret_cast<const uint4*>(rp + q * 8);
+                            const uint4 u = rres[ci][q];
                             float2 f0 = unpack_bf16(u.x), f1 = unpack_bf16(u.y), f2 = unpack_bf16(u.z),
                                    f3 = unpack_bf16(u.w);
                             v[q * 8 + 0] += f0.x; v[q * 8 + 1] += f0.y; v[q * 8 + 2] += f1.x; v[q * 8 + 3] += f1.y;

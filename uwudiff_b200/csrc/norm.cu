@@ -51,12 +51,20 @@ __global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x, GNGeom g, f
             q[j] = fmaf(f[j], f[j], q[j]);
         }
     }
-    for (int i = threadIdx.x; i < 2 * g.C; i += blockDim.x) sh[i] = 0.f;
-    __syncthreads();
+    // fixed-order block reduction over the rpi row groups (deterministic: no atomics)
+    {
+        float* mine = sh + (size_t)rr * 2 * g.C;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        atomicAdd(&sh[v * 8 + j], s[j]);
-        atomicAdd(&sh[g.C + v * 8 + j], q[j]);
+        for (int j = 0; j < 8; ++j) {
+            mine[v * 8 + j] = s[j];
+            mine[g.C + v * 8 + j] = q[j];
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * g.C; i += blockDim.x) {
+        float a = sh[i];
+        for (int k = 1; k < g.rpi; ++k) a += sh[(size_t)k * 2 * g.C + i];
+        sh[i] = a;
     }
     __syncthreads();
     const int cpg = g.C / g.G;
@@ -157,12 +165,19 @@ __global__ void gn_bwd_stats_kernel(const __nv_bfloat16* __restrict__ x, const _
             s2[j] = fmaf(dz, xh, s2[j]);
         }
     }
-    for (int i = threadIdx.x; i < 2 * g.C; i += blockDim.x) sh[i] = 0.f;
-    __syncthreads();
+    {
+        float* mine = sh + (size_t)rr * 2 * g.C;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        atomicAdd(&sh[v * 8 + j], s1[j]);
-        atomicAdd(&sh[g.C + v * 8 + j], s2[j]);
+        for (int j = 0; j < 8; ++j) {
+            mine[v * 8 + j] = s1[j];
+            mine[g.C + v * 8 + j] = s2[j];
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * g.C; i += blockDim.x) {
+        float a = sh[i];
+        for (int k = 1; k < g.rpi; ++k) a += sh[(size_t)k * 2 * g.C + i];
+        sh[i] = a;
     }
     __syncthreads();
     float* o = wsb + ((size_t)n * g.chunks + chunk) * 2 * g.C;
@@ -258,10 +273,10 @@ static int gn_geom(int N, int HW, int C, int G, GNGeom* g) {
     if (g->cv * rpi > 1024) rpi = 1;
     UWU_CHECK_ARG(g->cv <= 1024, "groupnorm: C too large");
     g->rpi = rpi;
-    int chunks = (2 * sm_count() + N - 1) / N;
+    int chunks = (8 * sm_count() + N - 1) / N;  // ~8 resident blocks per SM keep enough 16-byte loads in flight
     int max_chunks = (HW + rpi * 4 - 1) / (rpi * 4);
     if (chunks > max_chunks) chunks = max_chunks;
-    if (chunks > 64) chunks = 64;
+    if (chunks > 256) chunks = 256;
     if (chunks < 1) chunks = 1;
     g->rows_per_chunk = (HW + chunks - 1) / chunks;
     g->chunks = (HW + g->rows_per_chunk - 1) / g->rows_per_chunk;
@@ -525,7 +540,7 @@ extern "C" int uwu_groupnorm_fwd(const void* x, int32_t N, int32_t HW, int32_t C
     auto* yp = reinterpret_cast<__nv_bfloat16*>(y);
     dim3 grid(g.chunks, N);
     const int threads = g.cv * g.rpi;
-    gn_stats_kernel<<<grid, threads, 2 * C * sizeof(float), stream>>>(xp, g, workspace);
+    gn_stats_kernel<<<grid, threads, (size_t)g.rpi * 2 * C * sizeof(float), stream>>>(xp, g, workspace);
     UWU_CHECK_LAUNCH();
     gn_finalize_kernel<<<(N * G + 127) / 128, 128, 0, stream>>>(workspace, g, eps, stats);
     UWU_CHECK_LAUNCH();
@@ -552,9 +567,9 @@ extern "C" int uwu_groupnorm_bwd(const void* x, const void* dy, int32_t N, int32
     float* wsb = workspace;
     float* red = workspace + (size_t)N * g.chunks * 2 * C;
     if (fuse_silu)
-        gn_bwd_stats_kernel<true><<<grid, threads, 2 * C * sizeof(float), stream>>>(xp, dyp, stats, gamma, beta, g, wsb);
+        gn_bwd_stats_kernel<true><<<grid, threads, (size_t)g.rpi * 2 * C * sizeof(float), stream>>>(xp, dyp, stats, gamma, beta, g, wsb);
     else
-        gn_bwd_stats_kernel<false><<<grid, threads, 2 * C * sizeof(float), stream>>>(xp, dyp, stats, gamma, beta, g, wsb);
+        gn_bwd_stats_kernel<false><<<grid, threads, (size_t)g.rpi * 2 * C * sizeof(float), stream>>>(xp, dyp, stats, gamma, beta, g, wsb);
     UWU_CHECK_LAUNCH();
     gn_bwd_reduce_kernel<<<N, 256, 2 * C * sizeof(float), stream>>>(wsb, gamma, g, red, dgamma, dbeta);
     UWU_CHECK_LAUNCH();

@@ -108,6 +108,25 @@ class Linear(nn.Linear, _Cached):
             ad.grads_from(G)
 
 
+def _fused_param_grads(mods, dy, x, M):
+    """Adapter gradients of several Linears that share the input x and whose output gradients sit side by side in `dy`
+    (the fused QKV / KV projections): ONE token-reduction GEMM G = dy^T x for all of them, then per-layer contractions."""
+    if any(m.weight.requires_grad or (m.bias is not None and m.bias.requires_grad) for m in mods) or \
+            not all(m._uwu_adapter is not None and m._uwu_adapter.trainable() for m in mods):
+        off = 0
+        for m in mods:
+            m.param_grads(dy[:, off:off + m.out_features], x, M)
+            off += m.out_features
+        return
+    N, K = sum(m.out_features for m in mods), mods[0].in_features
+    G = ops._workspace(N * K, dy.device, "wgrad")[: N * K].view(N, K)
+    ops.gemm(dy, x, N, K, M, a_layout=A_COL, lda=dy.stride(0), b_layout=B_KN, ldb=x.stride(0), out=G)
+    off = 0
+    for m in mods:
+        m._uwu_adapter.grads_from(G[off:off + m.out_features])
+        off += m.out_features
+
+
 class Conv2d(nn.Conv2d, _Cached):
     """3x3 (stride 1 / 2) or 1x1 convolution as an implicit GEMM over NHWC bf16 activations."""
 
@@ -353,16 +372,14 @@ class Attention(nn.Module):
             dkv = torch.empty((Mc, 2 * C), device=dx.device, dtype=BF16)
             ops.attn_bwd(q, kv[:, :C], kv[:, C:], o, do, lse, B, self.heads, L, st.ctx_len, head_dim=self.dim_head,
                          dq=dq, dk=dkv[:, :C], dv=dkv[:, C:])
-            self.to_k.param_grads(dkv[:, :C], st.ctx, Mc)
-            self.to_v.param_grads(dkv[:, C:], st.ctx, Mc)
+            _fused_param_grads((self.to_k, self.to_v), dkv, st.ctx, Mc)
             dn = self.to_q.bwd(dq, n, M)
         else:
             (qkv,) = self._sv_proj
             dqkv = torch.empty((M, 3 * C), device=dx.device, dtype=BF16)
             ops.attn_bwd(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], o, do, lse, B, self.heads, L, L, head_dim=self.dim_head,
                          dq=dqkv[:, :C], dk=dqkv[:, C:2 * C], dv=dqkv[:, 2 * C:])
-            for i, m in enumerate((self.to_q, self.to_k, self.to_v)):
-                m.param_grads(dqkv[:, i * C:(i + 1) * C], n, M)
+            _fused_param_grads((self.to_q, self.to_k, self.to_v), dqkv, n, M)
             dn = ops.gemm(dqkv, Wf, M, Wf.shape[1], 3 * C, b_layout=B_KN, ldb=Wf.shape[1])
         self._sv_proj = None
         return dn
