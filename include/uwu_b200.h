@@ -83,6 +83,12 @@ typedef struct uwu_gemm_desc {
     int32_t block_n;    /* 0 = choose */
     int32_t stream_k;   /* fp32 output, plain epilogue: 1 = split the (tile, k-block) space evenly over the SMs and
                            reduce partial tiles with atomics, 0 = whole tiles per CTA, -1 = choose */
+    /* segmented reduction (UWU_A_COL x UWU_B_KN): out = sum_{s < k_segs} A[:, s*a_seg_off + m]^T B[:, s*b_seg_off + n];
+       K is the length of ONE segment. Used for the factored LoKr gradient dw2 = sum_l dY_l^T Z_l. 0/1 = off. */
+    int32_t k_segs, a_seg_off, b_seg_off;
+    /* grouped N (UWU_A_ROW x UWU_B_KN): out[:, g*grp_n + n] = A[:, g*a_grp_koff : +K] B[:, n] with one B [K, grp_n]
+       shared by all N/grp_n groups (block-diagonal right operand). Used for V_l = dY_l w2. 0 = off. */
+    int32_t grp_n, a_grp_koff;
     /* diagnostics: override shared-memory descriptor fields (0 = default) */
     int32_t dbg_a_lbo, dbg_a_sbo, dbg_a_kadv, dbg_b_lbo, dbg_b_sbo, dbg_b_kadv;
 } uwu_gemm_desc;
@@ -213,11 +219,39 @@ int uwu_fold_lora(const float* W, const float* up, const float* down, int32_t N,
                   void* dst_bf16, void* stream);
 /* out = a + alpha * b (fp32; effective norm affine = gamma + w_norm * multiplier) */
 int uwu_axpy_f32(const float* a, const float* b, float alpha, int32_t n, float* out, void* stream);
+
+/* Every adapter fold of a step in one launch.  `entries` (device memory) describe the folds; chunk c of the grid works on
+ * entry chunk_entry[c], elements [(c - chunk0) * chunk_elems, +chunk_elems) of its N*K weight (K % 4 == 0).
+ *   kind 0: dst_bf16 = W                         kind 1: dst_bf16 = W + kron(a [N/p0, p2], b [p0, p1]) * scale   (LoKr)
+ *   kind 2: dst_bf16 = W + (a [N, p0] @ b [p0, K]) * scale (LoRA)   kind 3: dst_f32 = W + a * scale  (norm deltas, N = 1)
+ * Same arithmetic as uwu_fold_lokr / uwu_fold_lora / uwu_axpy_f32 (bit-identical results). */
+typedef struct uwu_fold_entry {
+    const float* W;
+    const float* a;
+    const float* b;
+    void* dst;
+    int32_t kind, N, K, p0, p1, p2;
+    float scale;
+    int32_t chunk0;
+} uwu_fold_entry;
+int uwu_fold_batch(const uwu_fold_entry* entries_dev, const int32_t* chunk_entry_dev, int32_t n_chunks, int32_t chunk_elems,
+                   void* stream);
 /* adapter gradients from G = dY^T X (fp32 [N, ldg]); dw1/dw2 (dup/ddown) are ACCUMULATED into */
 int uwu_lokr_grad(const float* G, int64_t ldg, const float* w1, const float* w2, int32_t out_l, int32_t out_k, int32_t in_m,
                   int32_t in_n, float multiplier, float* dw1, float* dw2, void* stream);
 int uwu_lora_grad(const float* G, int64_t ldg, const float* up, const float* down, int32_t N, int32_t K, int32_t r, float scale,
                   float* dup, float* ddown, void* stream);
+
+/* Factored LoKr gradients: the adapter gradients of  y = x (W + kron(w1, w2))^T  without forming
+ * G = dY^T X.  x: bf16 [M, in_m*in_n] (row stride ldx), w1: fp32 [out_l, in_m].
+ *   uwu_lokr_z  : z[m, l*in_n + n] = sum_i w1[l, i] x[m, i*in_n + n]            (bf16 [M, out_l*in_n], contiguous)
+ *   uwu_lokr_dw1: dw1[l, i] += multiplier * sum_{m, n} v[m, l*in_n + n] x[m, i*in_n + n]   (v: bf16 [M, out_l*in_n])
+ * The two tensor-core steps in between (dw2 += sum_l dY_l^T Z_l and V_l = dY_l w2) are uwu_gemm calls with k_segs / grp_n.
+ * Replaces autograd through lycoris' `make_kron` weight rebuild (forward patch installed at src/duwu/trainer/trainer.py:152-154). */
+int uwu_lokr_z(const void* x, int64_t ldx, const float* w1, int64_t M, int32_t out_l, int32_t in_m, int32_t in_n, void* z,
+               void* stream);
+int uwu_lokr_dw1(const void* v, const void* x, int64_t ldx, int64_t M, int32_t out_l, int32_t in_m, int32_t in_n,
+                 float multiplier, float* dw1, void* stream);
 /* multi-tensor global grad norm: out2 = {||g||_2, min(1, max_norm/(norm+1e-6))}; tables are DEVICE arrays
  * (pointers as uint64, numels, and a chunk table (tensor index, chunk index) of n_chunks entries) */
 int uwu_mt_gradnorm(const uint64_t* g_ptrs, const int64_t* numels, const int32_t* chunk_tensor, const int32_t* chunk_index,

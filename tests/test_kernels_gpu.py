@@ -339,6 +339,32 @@ def test_lokr_fold_and_grads(ops, ol, ok, im, inn):
     assert relerr(dw1, 2 * torch.einsum("lkin,kn->li", G4, w2)) < 1e-4
 
 
+@pytest.mark.parametrize("M,ol,ok,im,inn", [(4096, 20, 64, 20, 64), (2048, 5, 2048, 5, 256), (8192, 10, 64, 10, 64),
+                                             (1024, 5, 1024, 5, 128), (1000, 4, 128, 4, 16), (1232, 20, 64, 32, 64),
+                                             (640, 3, 192, 7, 48)])
+def test_lokr_factored_gradients(ops, M, ol, ok, im, inn):
+    """Factored adapter gradients (Z / segmented-K GEMM / grouped-N GEMM / mma.sync contraction) == the einsum over the
+    full weight gradient; dY is a column slice of a wider buffer (as in the fused QKV gradient)."""
+    from uwudiff_b200.lycoris import lokr_factored_grads
+
+    N, K = ol * ok, im * inn
+    wide = mk(M, N + 64, s=1.0)
+    dy = wide[:, 64:]  # 128-byte offset, row stride N + 64
+    x = mk(M, K, s=1.0)
+    w1 = torch.randn(ol, im, device=DEV)
+    w2 = torch.randn(ok, inn, device=DEV) * 0.5
+    w2b = w2.to(torch.bfloat16)
+    dw1, dw2 = torch.zeros_like(w1), torch.zeros_like(w2)
+    lokr_factored_grads(dy, x, M, w1, w2b, dw1, dw2, 1.0)
+    G4 = (dy.float().t() @ x.float()).view(ol, ok, im, inn)
+    r1 = torch.einsum("lkin,kn->li", G4, w2b.float())
+    r2 = torch.einsum("lkin,li->kn", G4, w1)
+    # Z and V are rounded to bf16 before the second contraction -> bf16-level tolerance on the result
+    assert relerr(dw1, r1) < TOL_BF16 and relerr(dw2, r2) < TOL_BF16
+    lokr_factored_grads(dy, x, M, w1, w2b, dw1, dw2, 0.5)  # accumulates, scaled
+    assert relerr(dw1, 1.5 * r1) < TOL_BF16 and relerr(dw2, 1.5 * r2) < TOL_BF16
+
+
 def test_lora_fold_and_grads(ops):
     N, K, r, scale = 640, 320, 4, 0.25
     W = torch.randn(N, K, device=DEV) * 0.1

@@ -83,6 +83,36 @@ def case_lokr():
         bw(f"fold_lokr N{N} K{K}", timeit(lambda: ops.fold_lokr(W, w1, w2, dst)), N * K * 6)
 
 
+def case_lokr_fact():
+    """The four stages of the factored LoKr gradient at the SDXL shapes, against the G = dY^T X route."""
+    from uwudiff_b200._lib import A_ROW
+    from uwudiff_b200.lycoris import lokr_factored_grads
+
+    for (M, ol, ok, im, inn) in [(16384, 20, 64, 20, 64), (16384, 5, 2048, 5, 256), (65536, 10, 64, 10, 64), (65536, 5, 1024, 5, 128)]:
+        N, K = ol * ok, im * inn
+        dy, x = mk(M, N), mk(M, K)
+        w1, w2 = torch.randn(ol, im, device=dev), torch.randn(ok, inn, device=dev)
+        w2b = w2.to(torch.bfloat16)
+        dw1, dw2 = torch.zeros_like(w1), torch.zeros_like(w2)
+        z = torch.empty(M, ol * inn, device=dev, dtype=torch.bfloat16)
+        v = torch.empty(M, ol * inn, device=dev, dtype=torch.bfloat16)
+        tag = f"M{M} w1 {ol}x{im} w2 {ok}x{inn}"
+        bw(f"lokr_z {tag}", timeit(lambda: ops.lokr_z(x, w1, M, inn, z)), M * (K + ol * inn) * 2)
+        tf(f"dw2 gemm (segmented, stream-K) {tag}",
+           timeit(lambda: ops.gemm(dy, z, ok, inn, M, a_layout=A_COL, lda=N, b_layout=B_KN, ldb=ol * inn, out=dw2, accumulate=True,
+                                   stream_k=1, k_segs=ol, a_seg_off=ok, b_seg_off=inn)), 2.0 * M * ol * ok * inn)
+        bn = next(b for b in (256, 128, 64, 32, 16) if inn % b == 0)
+        tf(f"V gemm (grouped N) {tag}",
+           timeit(lambda: ops.gemm(dy, w2b, M, ol * inn, ok, a_layout=A_ROW, lda=N, b_layout=B_KN, ldb=inn, out=v, grp_n=inn,
+                                   a_grp_koff=ok, block_n=bn)), 2.0 * M * ol * ok * inn)
+        bw(f"lokr_dw1 {tag}", timeit(lambda: ops.lokr_dw1(v, x, M, ol, im, inn, dw1)), M * (K + ol * inn) * 2)
+        us = timeit(lambda: lokr_factored_grads(dy, x, M, w1, w2b, dw1, dw2))
+        print(f"factored total {tag}: {us:.1f} us", flush=True)
+        G = torch.empty(N, K, device=dev)
+        us = timeit(lambda: (ops.gemm(dy, x, N, K, M, a_layout=A_COL, lda=N, b_layout=B_KN, ldb=K, out=G), ops.lokr_grad(G, w1, w2, dw1, dw2)))
+        print(f"G route total {tag}: {us:.1f} us", flush=True)
+
+
 def case_wgrad():
     for (Mtok, Co, Ci) in [(16384, 1280, 1280), (65536, 640, 640), (16384, 10240, 1280), (16384, 1280, 5120),
                            (65536, 5120, 640), (65536, 640, 2560), (1232, 1280, 2048)]:

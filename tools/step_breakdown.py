@@ -19,7 +19,7 @@ from uwudiff_b200 import ops
 
 WRAP = ["gemm", "noise_fwd", "sincos_embed", "wmse_fwd", "wmse_bwd", "attn_fwd", "attn_bwd", "groupnorm_fwd", "groupnorm_bwd",
         "layernorm_fwd", "layernorm_bwd", "geglu_fwd", "geglu_bwd", "elementwise", "nchw_to_nhwc", "nhwc_to_nchw", "upsample2x",
-        "phase_split2", "colsum", "fold_lokr", "fold_lora", "axpy_f32", "lokr_grad", "lora_grad", "copy2d"]
+        "phase_split2", "colsum", "fold_lokr", "fold_lora", "axpy_f32", "lokr_grad", "lora_grad", "copy2d", "lokr_z", "lokr_dw1"]
 
 
 def main():

@@ -36,6 +36,7 @@ class GemmDesc(C.Structure):
         ("bias", C.c_void_p), ("bias_rows", C.c_void_p), ("rows_per_bias", C.c_int32),
         ("residual", C.c_void_p), ("ldr", C.c_int64),
         ("alpha", C.c_float), ("accumulate", C.c_int32), ("block_n", C.c_int32), ("stream_k", C.c_int32),
+        ("k_segs", C.c_int32), ("a_seg_off", C.c_int32), ("b_seg_off", C.c_int32), ("grp_n", C.c_int32), ("a_grp_koff", C.c_int32),
         ("dbg_a_lbo", C.c_int32), ("dbg_a_sbo", C.c_int32), ("dbg_a_kadv", C.c_int32),
         ("dbg_b_lbo", C.c_int32), ("dbg_b_sbo", C.c_int32), ("dbg_b_kadv", C.c_int32),
     ]
@@ -53,6 +54,12 @@ class NoiseDesc(C.Structure):
         ("t_out", C.c_void_p), ("sigma_out", C.c_void_p), ("w_out", C.c_void_p),
         ("temb_out", C.c_void_p), ("temb_dim", C.c_int32),
     ]
+
+
+class FoldEntry(C.Structure):
+    _fields_ = [("W", C.c_void_p), ("a", C.c_void_p), ("b", C.c_void_p), ("dst", C.c_void_p), ("kind", C.c_int32),
+                ("N", C.c_int32), ("K", C.c_int32), ("p0", C.c_int32), ("p1", C.c_int32), ("p2", C.c_int32),
+                ("scale", C.c_float), ("chunk0", C.c_int32)]
 
 
 _lib = None
@@ -93,6 +100,9 @@ SIGNATURES = {
     "uwu_axpy_f32": (C.c_int, [_P, _P, _F, _I32, _P, _P]),
     "uwu_lokr_grad": (C.c_int, [_P, _I64, _P, _P, _I32, _I32, _I32, _I32, _F, _P, _P, _P]),
     "uwu_lora_grad": (C.c_int, [_P, _I64, _P, _P, _I32, _I32, _I32, _F, _P, _P, _P]),
+    "uwu_fold_batch": (C.c_int, [_P, _P, _I32, _I32, _P]),
+    "uwu_lokr_z": (C.c_int, [_P, _I64, _P, _I64, _I32, _I32, _I32, _P, _P]),
+    "uwu_lokr_dw1": (C.c_int, [_P, _P, _I64, _I64, _I32, _I32, _I32, _F, _P, _P]),
     "uwu_mt_gradnorm": (C.c_int, [_P, _P, _P, _P, _I32, _I32, _F, _P, _P, _P]),
     "uwu_mt_adamw": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _I32, _I32, _F, _F, _F, _F, _F, _I64, _P, _P]),
     "uwu_copy2d_bf16": (C.c_int, [_P, _I32, _I64, _P, _I64, _I64, _I32, _P]),

@@ -63,6 +63,51 @@ __global__ void fold_lora_kernel(const float* __restrict__ W, const float* __res
     }
 }
 
+// All adapter folds of one step in ONE launch: block -> (entry, chunk) through a table built once on the host.
+__global__ void __launch_bounds__(256) fold_batch_kernel(const uwu_fold_entry* __restrict__ entries,
+                                                         const int32_t* __restrict__ chunk_entry, int chunk_elems) {
+    const uwu_fold_entry e = entries[chunk_entry[blockIdx.x]];
+    const long long total = (long long)e.N * e.K;
+    const long long beg = (long long)(blockIdx.x - e.chunk0) * chunk_elems;
+    const long long end = min(total, beg + chunk_elems);
+    const int K = e.K;
+    if (e.kind == 3) {  // fp32 dst = W + scale * a   (norm deltas)
+        float* dst = reinterpret_cast<float*>(e.dst);
+        for (long long i = beg + threadIdx.x; i < end; i += blockDim.x) dst[i] = __fadd_rn(e.W[i], __fmul_rn(e.a[i], e.scale));
+        return;
+    }
+    __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(e.dst);
+    for (long long i4 = beg + threadIdx.x * 4; i4 < end; i4 += blockDim.x * 4) {
+        const int n = (int)(i4 / K), k = (int)(i4 - (long long)n * K);
+        const float4 w = *reinterpret_cast<const float4*>(e.W + i4);
+        float v[4] = {w.x, w.y, w.z, w.w};
+        if (e.kind == 1) {  // LoKr: + kron(w1, w2)[n, k] * scale, same rounding sequence as fold_lokr_kernel
+            const int ok = e.p0, in_n = e.p1, im = e.p2;
+            const int l = n / ok, kk = n - l * ok;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int c = k + j;
+                const int ii = c / in_n, nn = c - ii * in_n;
+                v[j] = __fadd_rn(v[j], __fmul_rn(__fmul_rn(e.a[l * im + ii], e.b[kk * in_n + nn]), e.scale));
+            }
+        } else if (e.kind == 2) {  // LoRA: + (up @ down)[n, k] * scale
+            const int r = e.p0;
+            float d[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int q = 0; q < r; ++q) {
+                const float u = e.a[n * r + q];
+                const float4 dn = *reinterpret_cast<const float4*>(e.b + (size_t)q * K + k);
+                d[0] = fmaf(u, dn.x, d[0]); d[1] = fmaf(u, dn.y, d[1]); d[2] = fmaf(u, dn.z, d[2]); d[3] = fmaf(u, dn.w, d[3]);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v[j] = v[j] + d[j] * e.scale;
+        }
+        uint2 u;
+        u.x = pack_bf16(v[0], v[1]);
+        u.y = pack_bf16(v[2], v[3]);
+        *reinterpret_cast<uint2*>(dst + i4) = u;
+    }
+}
+
 // out = a + alpha * b (fp32 vectors; norm deltas gamma + w_norm * multiplier)
 __global__ void axpy_f32_kernel(const float* __restrict__ a, const float* __restrict__ b, float alpha, int n, float* __restrict__ out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -150,6 +195,134 @@ __global__ void __launch_bounds__(128) lokr_dw2_kernel(const float* __restrict__
         for (int j = 0; j < VW; ++j) o[j] += acc[j] * mult;
     }
 }
+// ------------------------------------------------------------------------------------------------
+// factored LoKr gradients (no G = dY^T X): with X [M, im, in], dY [M, ol, ok], w1 [ol, im], w2 [ok, in]
+//   Z[m, l, n] = sum_i w1[l, i] X[m, i, n]            (lokr_z_kernel, bandwidth / FMA bound)
+//   dw2[k, n] += sum_{m, l} dY[m, l, k] Z[m, l, n]      (tcgen05 GEMM, segmented reduction over l, stream-K)
+//   V[m, l, n] = sum_k dY[m, l, k] w2[k, n]            (tcgen05 GEMM, grouped N)
+//   dw1[l, i] += sum_{m, n} V[m, l, n] X[m, i, n]       (lokr_dw1_mma_kernel, warp-level mma.sync, bandwidth bound)
+// FLOPs: 2 * (2 M ol ok in) instead of 2 M (ol ok)(im in) for the full weight gradient, i.e. 2/im of it.
+// ------------------------------------------------------------------------------------------------
+// thread = (row m, 8 consecutive n); l processed in blocks of LB so the accumulators stay in registers
+template <int LB>
+__global__ void __launch_bounds__(256) lokr_z_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, const float* __restrict__ w1,
+                                                     long long M, int ol, int im, int in_n, __nv_bfloat16* __restrict__ z) {
+    extern __shared__ float sw1[];  // [ol][im]
+    for (int i = threadIdx.x; i < ol * im; i += blockDim.x) sw1[i] = w1[i];
+    __syncthreads();
+    const int nv = in_n >> 3;
+    const long long total = M * nv;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const long long m = t / nv;
+        const int n = (int)(t - m * nv) << 3;
+        const __nv_bfloat16* xr = x + m * ldx + n;
+        __nv_bfloat16* zr = z + m * ((long long)ol * in_n) + n;
+        for (int l0 = 0; l0 < ol; l0 += LB) {
+            float acc[LB][8];
+#pragma unroll
+            for (int l = 0; l < LB; ++l)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[l][j] = 0.f;
+            for (int i = 0; i < im; ++i) {
+                const uint4 u = *reinterpret_cast<const uint4*>(xr + (long long)i * in_n);
+                const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), c = unpack_bf16(u.z), d = unpack_bf16(u.w);
+                const float f[8] = {a.x, a.y, b.x, b.y, c.x, c.y, d.x, d.y};
+#pragma unroll
+                for (int l = 0; l < LB; ++l) {
+                    const float w = (l0 + l < ol) ? sw1[(l0 + l) * im + i] : 0.f;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc[l][j] = fmaf(w, f[j], acc[l][j]);
+                }
+            }
+#pragma unroll
+            for (int l = 0; l < LB; ++l) {
+                if (l0 + l < ol) {
+                    uint4 o;
+                    o.x = pack_bf16(acc[l][0], acc[l][1]);
+                    o.y = pack_bf16(acc[l][2], acc[l][3]);
+                    o.z = pack_bf16(acc[l][4], acc[l][5]);
+                    o.w = pack_bf16(acc[l][6], acc[l][7]);
+                    *reinterpret_cast<uint4*>(zr + (long long)(l0 + l) * in_n) = o;
+                }
+            }
+        }
+    }
+}
+
+UWU_DEVINL void mma_bf16_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+// dw1[l, i] += mult * sum_{m, n} V[m, l, n] X[m, i, n].  Each warp owns rows m = w, w + W, ... and accumulates the
+// [LT*16 x IT*8] output in mma fragments across all of them (the (m, n) pairs ARE the reduction dimension).  Operand
+// fragments come straight from global memory as 16-byte loads: lane (g = lane/4, t = lane%4) reads elements 8t..8t+7 of
+// a 32-wide n chunk of row g; the same permutation of the reduction index is used for both operands, so the two
+// m16n8k16 products per chunk sum exactly the 32 products.
+template <int LT, int IT>
+__global__ void __launch_bounds__(256) lokr_dw1_mma_kernel(const __nv_bfloat16* __restrict__ v, const __nv_bfloat16* __restrict__ x,
+                                                           long long ldx, long long M, int ol, int im, int in_n, float mult,
+                                                           float* __restrict__ dw1) {
+    __shared__ float red[LT * 16 * IT * 8];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, t = lane & 3;
+    float c[LT][IT][4];
+#pragma unroll
+    for (int a = 0; a < LT; ++a)
+#pragma unroll
+        for (int b = 0; b < IT; ++b)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) c[a][b][j] = 0.f;
+    const long long ldv = (long long)ol * in_n;
+    const uint4 zero = make_uint4(0, 0, 0, 0);
+    for (long long m = (long long)blockIdx.x * 8 + warp; m < M; m += (long long)gridDim.x * 8) {
+        const __nv_bfloat16* vr = v + m * ldv;
+        const __nv_bfloat16* xr = x + m * ldx;
+        for (int n0 = 0; n0 < in_n; n0 += 32) {
+            const int n = n0 + t * 8;
+            const bool nok = n < in_n;
+            uint4 av[LT][2], bv[IT];
+#pragma unroll
+            for (int a = 0; a < LT; ++a) {
+                const int l0 = a * 16 + g, l1 = l0 + 8;
+                av[a][0] = (nok && l0 < ol) ? *reinterpret_cast<const uint4*>(vr + (long long)l0 * in_n + n) : zero;
+                av[a][1] = (nok && l1 < ol) ? *reinterpret_cast<const uint4*>(vr + (long long)l1 * in_n + n) : zero;
+            }
+#pragma unroll
+            for (int b = 0; b < IT; ++b) {
+                const int i = b * 8 + g;
+                bv[b] = (nok && i < im) ? *reinterpret_cast<const uint4*>(xr + (long long)i * in_n + n) : zero;
+            }
+#pragma unroll
+            for (int a = 0; a < LT; ++a)
+#pragma unroll
+                for (int b = 0; b < IT; ++b) {
+                    mma_bf16_16816(c[a][b], av[a][0].x, av[a][1].x, av[a][0].y, av[a][1].y, bv[b].x, bv[b].y);
+                    mma_bf16_16816(c[a][b], av[a][0].z, av[a][1].z, av[a][0].w, av[a][1].w, bv[b].z, bv[b].w);
+                }
+        }
+    }
+    // block reduction of the 8 warps' fragments, then one atomic per output element
+    for (int i = threadIdx.x; i < LT * 16 * IT * 8; i += blockDim.x) red[i] = 0.f;
+    __syncthreads();
+#pragma unroll
+    for (int a = 0; a < LT; ++a)
+#pragma unroll
+        for (int b = 0; b < IT; ++b) {
+            const int r0 = a * 16 + g, c0 = b * 8 + t * 2;
+            atomicAdd(&red[r0 * (IT * 8) + c0], c[a][b][0]);
+            atomicAdd(&red[r0 * (IT * 8) + c0 + 1], c[a][b][1]);
+            atomicAdd(&red[(r0 + 8) * (IT * 8) + c0], c[a][b][2]);
+            atomicAdd(&red[(r0 + 8) * (IT * 8) + c0 + 1], c[a][b][3]);
+        }
+    __syncthreads();
+    for (int i = threadIdx.x; i < LT * 16 * IT * 8; i += blockDim.x) {
+        const int l = i / (IT * 8), ii = i - l * (IT * 8);
+        if (l < ol && ii < im) atomicAdd(&dw1[l * im + ii], red[i] * mult);
+    }
+}
+
 // dup[o, q] += s * sum_k G[o,k] down[q,k] : one warp per (o, q)
 __global__ void __launch_bounds__(256) lora_dup_kernel(const float* __restrict__ G, long long ldg, const float* __restrict__ down,
                                                        int N, int K, int r, float s, float* __restrict__ dup) {
@@ -421,6 +594,61 @@ extern "C" int uwu_copy2d_bf16(const void* src, int32_t src_dtype, int64_t lds, 
         copy2d_kernel<float><<<grid_for(rows * cols, 256), 256, 0, stream>>>(reinterpret_cast<const float*>(src), lds, d, ldd, rows,
                                                                              cols);
     }
+    UWU_CHECK_LAUNCH();
+    return UWU_OK;
+}
+
+extern "C" int uwu_lokr_z(const void* x, int64_t ldx, const float* w1, int64_t M, int32_t out_l, int32_t in_m, int32_t in_n,
+                          void* z, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    UWU_CHECK_ARG(x && w1 && z && M > 0, "uwu_lokr_z: bad arguments");
+    UWU_CHECK_ARG(out_l > 0 && out_l <= 64 && in_m > 0 && in_m <= 64 && in_n > 0 && in_n % 8 == 0 && ldx % 8 == 0 &&
+                      ldx >= (int64_t)in_m * in_n,
+                  "uwu_lokr_z: unsupported factor shape ol=%d im=%d in=%d ldx=%lld", out_l, in_m, in_n, (long long)ldx);
+    UWU_CHECK_ARG(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(z)) & 15) == 0, "uwu_lokr_z: 16-byte alignment");
+    const long long total = M * (in_n / 8);
+    const int grid = grid_for(total, 256);
+    const size_t sm = (size_t)out_l * in_m * sizeof(float);
+    const auto* xp = reinterpret_cast<const __nv_bfloat16*>(x);
+    auto* zp = reinterpret_cast<__nv_bfloat16*>(z);
+    if (out_l % 5 == 0)
+        lokr_z_kernel<5><<<grid, 256, sm, stream>>>(xp, ldx, w1, M, out_l, in_m, in_n, zp);
+    else
+        lokr_z_kernel<4><<<grid, 256, sm, stream>>>(xp, ldx, w1, M, out_l, in_m, in_n, zp);
+    UWU_CHECK_LAUNCH();
+    return UWU_OK;
+}
+
+extern "C" int uwu_lokr_dw1(const void* v, const void* x, int64_t ldx, int64_t M, int32_t out_l, int32_t in_m, int32_t in_n,
+                            float multiplier, float* dw1, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    UWU_CHECK_ARG(v && x && dw1 && M > 0, "uwu_lokr_dw1: bad arguments");
+    UWU_CHECK_ARG(out_l > 0 && out_l <= 32 && in_m > 0 && in_m <= 32 && in_n > 0 && in_n % 8 == 0 && ldx % 8 == 0,
+                  "uwu_lokr_dw1: unsupported factor shape ol=%d im=%d in=%d (ol, im <= 32; in %% 8 == 0)", out_l, in_m, in_n);
+    UWU_CHECK_ARG(((reinterpret_cast<uintptr_t>(v) | reinterpret_cast<uintptr_t>(x)) & 15) == 0, "uwu_lokr_dw1: 16-byte alignment");
+    long long blocks = (M + 7) / 8;
+    const long long cap = 2ll * sm_count();
+    if (blocks > cap) blocks = cap;
+    const auto* vp = reinterpret_cast<const __nv_bfloat16*>(v);
+    const auto* xp = reinterpret_cast<const __nv_bfloat16*>(x);
+    const int LT = (out_l + 15) / 16, IT = (in_m + 7) / 8;
+#define UWU_DW1(A, B) lokr_dw1_mma_kernel<A, B><<<(int)blocks, 256, 0, stream>>>(vp, xp, ldx, M, out_l, in_m, in_n, multiplier, dw1)
+    if (LT == 1) {
+        if (IT == 1) UWU_DW1(1, 1); else if (IT == 2) UWU_DW1(1, 2); else if (IT == 3) UWU_DW1(1, 3); else UWU_DW1(1, 4);
+    } else {
+        if (IT == 1) UWU_DW1(2, 1); else if (IT == 2) UWU_DW1(2, 2); else if (IT == 3) UWU_DW1(2, 3); else UWU_DW1(2, 4);
+    }
+#undef UWU_DW1
+    UWU_CHECK_LAUNCH();
+    return UWU_OK;
+}
+
+extern "C" int uwu_fold_batch(const uwu_fold_entry* entries_dev, const int32_t* chunk_entry_dev, int32_t n_chunks,
+                              int32_t chunk_elems, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    UWU_CHECK_ARG(entries_dev && chunk_entry_dev && n_chunks > 0 && chunk_elems > 0 && chunk_elems % 1024 == 0,
+                  "uwu_fold_batch: bad arguments (chunk_elems must be a multiple of 1024)");
+    fold_batch_kernel<<<n_chunks, 256, 0, stream>>>(entries_dev, chunk_entry_dev, chunk_elems);
     UWU_CHECK_LAUNCH();
     return UWU_OK;
 }

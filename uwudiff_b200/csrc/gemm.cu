@@ -57,6 +57,12 @@ struct GemmKernelArgs {
     long long ldr;
     float alpha;
     int accumulate;
+    // segmented reduction (a_mode 1 / b_mode 1): k-block kb belongs to segment kb / kb_per_seg, whose operands start
+    // seg * a_seg_off / seg * b_seg_off elements further along the contiguous (M / N) axis of A / B
+    int kb_per_seg, a_seg_off, b_seg_off;
+    // grouped N (a_mode 0): output columns [g * grp_n, (g+1) * grp_n) use A columns starting at g * a_grp_koff and the
+    // SAME B ([K, grp_n]) for every group
+    int grp_n, a_grp_koff;
     int stream_k;  // 1: the (tile, k-block) space is cut into equal contiguous ranges, one per CTA; partial tiles are
                    //    reduced with vector atomics into the fp32 output (which the host zeroed unless accumulating)
 };
@@ -170,11 +176,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
                     uint8_t* sb = sa + A_STAGE_BYTES;
                     mbar_expect_tx(&full_bar[stage], tx_bytes);
                     // ---- A ----
+                    int kseg = 0, kbs = kb;  // segment and k-block within it
+                    if (p.kb_per_seg > 0) {
+                        kseg = kb / p.kb_per_seg;
+                        kbs = kb - kseg * p.kb_per_seg;
+                    }
+                    const int grp = p.grp_n > 0 ? n0 / p.grp_n : 0;
                     if (p.a_mode == 0) {
-                        tma_load_2d(sa, &p.tmA, &full_bar[stage], kb * BLOCK_K, m0);
+                        tma_load_2d(sa, &p.tmA, &full_bar[stage], kb * BLOCK_K + grp * p.a_grp_koff, m0);
                     } else if (p.a_mode == 1) {
-                        tma_load_2d(sa, &p.tmA, &full_bar[stage], m0, kb * BLOCK_K);
-                        tma_load_2d(sa + 8192, &p.tmA, &full_bar[stage], m0 + 64, kb * BLOCK_K);
+                        const int am = m0 + kseg * p.a_seg_off;
+                        tma_load_2d(sa, &p.tmA, &full_bar[stage], am, kbs * BLOCK_K);
+                        tma_load_2d(sa + 8192, &p.tmA, &full_bar[stage], am + 64, kbs * BLOCK_K);
                     } else {
                         const int tap = kb / p.kb_per_tap;
                         const int cb = kb - tap * p.kb_per_tap;
@@ -189,8 +202,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
                     if (p.b_mode == 0) {
                         tma_load_2d(sb, &p.tmB, &full_bar[stage], kb * BLOCK_K, n0);
                     } else {
+                        const int bn0 = n0 - grp * p.grp_n + kseg * p.b_seg_off;
                         for (int j = 0; j * 64 < p.block_n; ++j)
-                            tma_load_2d(sb + j * 8192, &p.tmB, &full_bar[stage], n0 + j * 64, kb * BLOCK_K);
+                            tma_load_2d(sb + j * 8192, &p.tmB, &full_bar[stage], bn0 + j * 64, kbs * BLOCK_K);
                     }
                     if (++stage == p.stages) {
                         stage = 0;
@@ -453,11 +467,21 @@ extern "C" int uwu_gemm(const uwu_gemm_desc* d, void* stream_) {
     p.num_n_tiles = (p.N + bn - 1) / bn;
     p.a_mode = d->a_layout;
     p.b_mode = d->b_layout;
+    p.kb_per_seg = 0; p.a_seg_off = 0; p.b_seg_off = 0;
+    p.grp_n = 0; p.a_grp_koff = 0;
+    if (d->grp_n > 0) {
+        UWU_CHECK_ARG(d->a_layout == UWU_A_ROW && d->b_layout == UWU_B_KN, "uwu_gemm: grp_n needs the A_ROW x B_KN form");
+        UWU_CHECK_ARG(d->grp_n % bn == 0, "uwu_gemm: block_n %d must divide grp_n %d", bn, d->grp_n);
+        p.grp_n = d->grp_n;
+        p.a_grp_koff = d->a_grp_koff;
+    }
 
     // ---------------- A tensor map(s) ----------------
     if (d->a_layout == UWU_A_ROW) {
         UWU_CHECK_ARG(d->lda % 8 == 0 && d->lda >= d->K, "uwu_gemm: lda %lld must be >= K and a multiple of 8", (long long)d->lda);
-        uint64_t dims[2] = {(uint64_t)d->K, (uint64_t)d->M};
+        const int n_grp = d->grp_n > 0 ? (int)((d->N + d->grp_n - 1) / d->grp_n) : 1;
+        uint64_t dims[2] = {(uint64_t)d->K + (uint64_t)(n_grp - 1) * (uint64_t)d->a_grp_koff, (uint64_t)d->M};
+        UWU_CHECK_ARG((int64_t)dims[0] <= d->lda, "uwu_gemm: grouped A columns exceed lda");
         uint64_t str[1] = {(uint64_t)d->lda * 2};
         uint32_t box[2] = {BLOCK_K, BLOCK_M};
         if (encode_tmap_bf16(&p.tmA, d->a, 2, dims, str, box, 1)) return UWU_ERR_INVALID;
@@ -466,13 +490,22 @@ extern "C" int uwu_gemm(const uwu_gemm_desc* d, void* stream_) {
         p.a_lbo = 0; p.a_sbo = 1024; p.a_kadv = 32;
     } else if (d->a_layout == UWU_A_COL) {
         UWU_CHECK_ARG(d->lda % 8 == 0 && d->lda >= d->M, "uwu_gemm: lda %lld must be >= M and a multiple of 8", (long long)d->lda);
-        uint64_t dims[2] = {(uint64_t)d->M, (uint64_t)d->K};
+        const int segs = d->k_segs > 1 ? d->k_segs : 1;
+        UWU_CHECK_ARG(segs == 1 || d->b_layout == UWU_B_KN, "uwu_gemm: k_segs needs the A_COL x B_KN (token-reduction) form");
+        uint64_t dims[2] = {(uint64_t)d->M + (uint64_t)(segs - 1) * (uint64_t)d->a_seg_off, (uint64_t)d->K};
+        UWU_CHECK_ARG((int64_t)dims[0] <= d->lda, "uwu_gemm: segmented A columns exceed lda");
         uint64_t str[1] = {(uint64_t)d->lda * 2};
         uint32_t box[2] = {64, BLOCK_K};
         if (encode_tmap_bf16(&p.tmA, d->a, 2, dims, str, box, 1)) return UWU_ERR_INVALID;
         p.tmA2 = p.tmA;
         p.num_kb = (int)((d->K + BLOCK_K - 1) / BLOCK_K);
         p.a_lbo = 8192; p.a_sbo = 1024; p.a_kadv = 2048;
+        if (segs > 1) {
+            p.kb_per_seg = p.num_kb;
+            p.num_kb *= segs;
+            p.a_seg_off = d->a_seg_off;
+            p.b_seg_off = d->b_seg_off;
+        }
     } else {
         // NHWC activation(s): [n_img_buf, H, W, C]
         const int H = d->H, W = d->W, C1 = d->Cin1, C2 = d->Cin2;
@@ -536,8 +569,12 @@ extern "C" int uwu_gemm(const uwu_gemm_desc* d, void* stream_) {
         p.b_stage_bytes = bn * BLOCK_K * 2;
         p.b_lbo = 0; p.b_sbo = 1024; p.b_kadv = 32;
     } else {
-        UWU_CHECK_ARG(d->ldb % 8 == 0 && d->ldb >= d->N, "uwu_gemm: ldb %lld must be >= N and a multiple of 8", (long long)d->ldb);
-        uint64_t dims[2] = {(uint64_t)d->N, (uint64_t)d->K};
+        UWU_CHECK_ARG(d->ldb % 8 == 0 && (d->grp_n > 0 || d->ldb >= d->N), "uwu_gemm: ldb %lld must be >= N and a multiple of 8",
+                      (long long)d->ldb);
+        const int segs = (d->a_layout == UWU_A_COL && d->k_segs > 1) ? d->k_segs : 1;
+        uint64_t bw = d->grp_n > 0 ? (uint64_t)d->grp_n : (uint64_t)d->N + (uint64_t)(segs - 1) * (uint64_t)d->b_seg_off;
+        UWU_CHECK_ARG((int64_t)bw <= d->ldb, "uwu_gemm: segmented / grouped B columns exceed ldb");
+        uint64_t dims[2] = {bw, (uint64_t)d->K};
         uint64_t str[1] = {(uint64_t)d->ldb * 2};
         uint32_t box[2] = {64, BLOCK_K};
         if (encode_tmap_bf16(&p.tmB, d->b, 2, dims, str, box, 1)) return UWU_ERR_INVALID;
@@ -545,6 +582,7 @@ extern "C" int uwu_gemm(const uwu_gemm_desc* d, void* stream_) {
         p.b_lbo = 8192; p.b_sbo = 1024; p.b_kadv = 2048;
     }
     p.tx_bytes = A_STAGE_BYTES + p.b_stage_bytes;
+    // ldb check for plain B_KN uses N, for grouped B the group width (done above)
     // B stage must keep the next A stage 1024-byte aligned
     p.b_stage_bytes = (p.b_stage_bytes + 1023) & ~1023;
 

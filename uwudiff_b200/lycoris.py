@@ -95,6 +95,7 @@ class LokrLinear(_Adapter):
         self.lokr_w2 = nn.Parameter(torch.empty(out_k, in_n))
         self.register_buffer("alpha", torch.tensor(float(dim)))  # full_matrix: alpha := lora_dim -> scale 1
         self.scale = 1.0
+        self._w2_bf16 = None  # view into LycorisNetwork.flat_params_bf16 (refreshed once per backward)
         nn.init.constant_(self.lokr_w2, 0)
         nn.init.kaiming_uniform_(self.lokr_w1, a=math.sqrt(5))
 
@@ -109,6 +110,43 @@ class LokrLinear(_Adapter):
 
     def delta(self):
         return torch.kron(self.lokr_w1, self.lokr_w2.contiguous()) * self.scale
+
+    def factored_ok(self, M: int) -> bool:
+        """Use the factored gradient (no G = dY^T X) when the factor shapes fit its kernels and it is cheaper than the
+        full token-reduction GEMM: 2/in_m of the FLOPs, but four passes over [M, *]-sized data."""
+        (ol, ok), (im, inn) = self.shape
+        # measured on B200 (profiles/r01_lokr_factored_stages.log): the factored route wins for the FeedForward adapters
+        # (w2 2048x256: 263 vs 454 us, w2 1024x128: 404 vs 673 us) and loses for the 64x64 attention factors (135 vs 82 us),
+        # whose four stages are latency / issue bound rather than FLOP bound
+        return (self._w2_bf16 is not None and M >= 4096 and ol <= 32 and im <= 32 and im >= 4 and inn % 16 == 0 and ok % 8 == 0
+                and inn <= 256 and ok * inn >= 32768)
+
+    def grads_factored(self, dy, x, M):
+        """dy: bf16 [M, ol*ok] (row stride dy.stride(0)), x: bf16 [M, im*inn]; accumulates into lokr_w1.grad / lokr_w2.grad."""
+        from .unet import _grad_of
+
+        lokr_factored_grads(dy, x, M, self.lokr_w1, self._w2_bf16, _grad_of(self.lokr_w1), _grad_of(self.lokr_w2),
+                            self.scale * self.multiplier)
+
+
+def lokr_factored_grads(dy, x, M, w1, w2_bf16, dw1, dw2, mult: float = 1.0):
+    """Adapter gradients of y = x (W + kron(w1, w2))^T without G = dY^T X:
+         Z[m,l,n] = sum_i w1[l,i] X[m,i,n];  dw2 += sum_{m,l} dY[m,l,:]^T Z[m,l,:];
+         V[m,l,n] = sum_k dY[m,l,k] w2[k,n]; dw1[l,i] += sum_{m,n} V[m,l,n] X[m,i,n]."""
+    from ._lib import A_COL, A_ROW, B_KN
+
+    (ol, im), (ok, inn) = w1.shape, w2_bf16.shape
+    zw = ops._workspace((M * ol * inn + 1) // 2, dy.device, "lokr_z").view(torch.bfloat16)[: M * ol * inn].view(M, ol * inn)
+    ops.lokr_z(x, w1, M, inn, zw)
+    # token-reduction GEMM whose reduction runs over (l, m): segment l reads dY[:, l*ok:(l+1)*ok] and Z[:, l*inn:(l+1)*inn]
+    ops.gemm(dy, zw, ok, inn, M, a_layout=A_COL, lda=dy.stride(0), b_layout=B_KN, ldb=ol * inn, out=dw2, accumulate=True,
+             alpha=mult, stream_k=1, k_segs=ol, a_seg_off=ok, b_seg_off=inn)
+    # V_l = dY_l w2: one shared right operand for all l (grouped N)
+    vw = ops._workspace((M * ol * inn + 1) // 2, dy.device, "lokr_v").view(torch.bfloat16)[: M * ol * inn].view(M, ol * inn)
+    bn = next(b for b in (256, 128, 64, 32, 16) if inn % b == 0)
+    ops.gemm(dy, w2_bf16, M, ol * inn, ok, a_layout=A_ROW, lda=dy.stride(0), b_layout=B_KN, ldb=inn, out=vw, grp_n=inn,
+             a_grp_koff=ok, block_n=bn)
+    ops.lokr_dw1(vw, x, M, ol, im, inn, dw1, mult)
 
 
 class NormDelta(_Adapter):
@@ -142,6 +180,7 @@ class LycorisNetwork(nn.Module):
                  algo: str = "lora", train_norm: bool = False, **kwargs):
         super().__init__()
         self.multiplier = multiplier
+        object.__setattr__(self, "_root", module)
         self.loras: List[_Adapter] = []
         self._orgs: List[nn.Module] = []
         names = set()
@@ -188,19 +227,87 @@ class LycorisNetwork(nn.Module):
     # all adapter parameters (and gradients) are views into two flat fp32 buffers
     def _flatten(self, device):
         params = list(self.parameters())
-        total = sum(_pad4(p.numel()) for p in params)
+        total = sum(_pad8(p.numel()) for p in params)
+        total = (total + 1023) // 1024 * 1024
         flat = torch.zeros((total,), device=device, dtype=torch.float32)
         gflat = torch.zeros((total,), device=device, dtype=torch.float32)
+        flat16 = torch.zeros((total,), device=device, dtype=torch.bfloat16) if flat.is_cuda else None
         off = 0
+        offs = {}
         for p in params:
             n = p.numel()
             v = flat[off:off + n].view(p.shape)
             v.copy_(p.data)
             p.data = v
             p.grad = gflat[off:off + n].view(p.shape)
-            off += _pad4(n)
+            offs[id(p)] = off
+            off += _pad8(n)
         object.__setattr__(self, "flat_params", flat)
         object.__setattr__(self, "flat_grads", gflat)
+        object.__setattr__(self, "flat_params_bf16", flat16)
+        object.__setattr__(self, "_fold", None)
+        for lora in self.loras:
+            if isinstance(lora, LokrLinear):
+                o2 = offs[id(lora.lokr_w2)]
+                lora._w2_bf16 = None if flat16 is None else flat16[o2:o2 + lora.lokr_w2.numel()].view(lora.lokr_w2.shape)
+
+    def fold_all(self):
+        """One launch folding every adapter into the operand its module's GEMM / norm kernel reads (uwu_fold_batch)."""
+        import ctypes as C
+
+        from . import _lib
+        from .unet import FOLD, Attention
+
+        if not self.flat_params.is_cuda:
+            return
+        t = getattr(self, "_fold", None)
+        if t is None or t["gen"] != FOLD.gen:
+            for m in self._root.modules():
+                if isinstance(m, Attention):
+                    m.ensure_fused()
+            ents, keep = [], []
+            chunk = 1 << 14
+
+            def add(kind, W, a, b, dst, N, K, p0=0, p1=0, p2=0, scale=1.0):
+                assert W.is_contiguous() and dst.is_contiguous() and (kind == 3 or K % 4 == 0)
+                e = _lib.FoldEntry()
+                e.W, e.a, e.b, e.dst = W.data_ptr(), a.data_ptr(), (b.data_ptr() if b is not None else None), dst.data_ptr()
+                e.kind, e.N, e.K, e.p0, e.p1, e.p2, e.scale = kind, N, K, p0, p1, p2, scale
+                ents.append(e)
+                keep.extend([W, a, b, dst])
+
+            for lora, org in zip(self.loras, self._orgs):
+                if isinstance(lora, NormDelta):
+                    g, b = org.fold_dst()
+                    Cn = org.weight.numel()
+                    add(3, org.weight, lora.w_norm, None, g, 1, Cn, scale=lora.multiplier)
+                    add(3, org.bias, lora.b_norm, None, b, 1, Cn, scale=lora.multiplier)
+                elif isinstance(lora, LokrLinear):
+                    (ol, ok), (im, inn) = lora.shape
+                    add(1, org.weight, lora.lokr_w1, lora.lokr_w2, org.fold_dst(), org.out_features, org.in_features, ok, inn, im,
+                        lora.scale * lora.multiplier)
+                else:
+                    add(2, org.weight, lora.lora_up.weight, lora.lora_down.weight, org.fold_dst(), org.out_features,
+                        org.in_features, lora.dim, scale=lora.scale * lora.multiplier)
+            chunk_entry = []
+            for i, e in enumerate(ents):
+                e.chunk0 = len(chunk_entry)
+                chunk_entry += [i] * ((e.N * e.K + chunk - 1) // chunk)
+            arr = (_lib.FoldEntry * len(ents))(*ents)
+            dev = self.flat_params.device
+            table = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(dev)
+            ce = torch.tensor(chunk_entry, dtype=torch.int32, device=dev)
+            t = dict(gen=FOLD.gen, table=table, ce=ce, n=len(chunk_entry), chunk=chunk, keep=keep)
+            object.__setattr__(self, "_fold", t)
+        _lib.check(_lib.lib().uwu_fold_batch(t["table"].data_ptr(), t["ce"].data_ptr(), t["n"], t["chunk"],
+                                             torch.cuda.current_stream().cuda_stream), "uwu_fold_batch")
+        for org in self._orgs:
+            org._fold_epoch = FOLD.epoch
+
+    def refresh_bf16(self):
+        """bf16 copy of all adapter parameters (operands of the factored-gradient GEMMs): one kernel per backward."""
+        if self.flat_params_bf16 is not None:
+            ops.copy2d(self.flat_params.view(-1, 1024), self.flat_params_bf16.view(-1, 1024))
 
     def _apply(self, fn, *a, **k):
         r = super()._apply(fn, *a, **k)
@@ -213,12 +320,14 @@ class LycorisNetwork(nn.Module):
         self.flat_grads.zero_()
 
     def apply_to(self):
+        object.__setattr__(self._root, "_uwu_lycoris", self)
         for lora, org in zip(self.loras, self._orgs):
             object.__setattr__(org, "_uwu_adapter", lora)
             if hasattr(org, "drop_cache"):
                 org.drop_cache()
 
     def restore(self):
+        object.__setattr__(self._root, "_uwu_lycoris", None)
         for org in self._orgs:
             object.__setattr__(org, "_uwu_adapter", None)
             if hasattr(org, "drop_cache"):
@@ -236,8 +345,8 @@ class LycorisNetwork(nn.Module):
                 org.drop_cache()
 
 
-def _pad4(n: int) -> int:
-    return (n + 3) // 4 * 4
+def _pad8(n: int) -> int:
+    return (n + 7) // 8 * 8
 
 
 def create_lycoris(module: nn.Module, multiplier: float = 1.0, linear_dim: int = 4, linear_alpha: float = 1.0,

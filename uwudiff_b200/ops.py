@@ -44,7 +44,8 @@ def gemm(a: torch.Tensor, b: torch.Tensor, M: int, N: int, K: int, *, a_layout: 
          bias_rows: Optional[torch.Tensor] = None, rows_per_bias: int = 1, residual: Optional[torch.Tensor] = None,
          alpha: float = 1.0, accumulate: bool = False, block_n: int = 0, out2: Optional[torch.Tensor] = None,
          n_split: int = 0, conv: Optional[dict] = None, a2: Optional[torch.Tensor] = None,
-         dbg: Optional[dict] = None, stream_k: int = -1) -> torch.Tensor:
+         dbg: Optional[dict] = None, stream_k: int = -1, k_segs: int = 0, a_seg_off: int = 0, b_seg_off: int = 0,
+         grp_n: int = 0, a_grp_koff: int = 0) -> torch.Tensor:
     """out[M,N] = alpha * A·Bᵀ + bias + bias_rows + residual (see uwu_gemm in include/uwu_b200.h)."""
     _req_cuda(a, b, out, bias, bias_rows, residual, out2, a2)
     assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16, "GEMM operands must be bf16"
@@ -80,6 +81,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, M: int, N: int, K: int, *, a_layout: 
         assert residual.dtype == torch.bfloat16
         d.residual, d.ldr = _ptr(residual), residual.stride(0) if residual.dim() == 2 else N
     d.alpha, d.accumulate, d.block_n, d.stream_k = alpha, int(accumulate), block_n, stream_k
+    d.k_segs, d.a_seg_off, d.b_seg_off, d.grp_n, d.a_grp_koff = k_segs, a_seg_off, b_seg_off, grp_n, a_grp_koff
     if dbg:
         for k, v in dbg.items():
             setattr(d, "dbg_" + k, v)
@@ -410,6 +412,22 @@ def lokr_grad(G: torch.Tensor, w1: torch.Tensor, w2: torch.Tensor, dw1: torch.Te
     assert G.shape == (ol * ok, im * inn) and G.dtype == torch.float32 and G.stride(1) == 1
     check(lib().uwu_lokr_grad(_ptr(G), G.stride(0), _ptr(w1), _ptr(w2), ol, ok, im, inn, multiplier, _ptr(dw1), _ptr(dw2),
                               _stream()), "uwu_lokr_grad")
+
+
+def lokr_z(x: torch.Tensor, w1: torch.Tensor, M: int, in_n: int, out: torch.Tensor) -> torch.Tensor:
+    """out[m, l*in_n + n] = sum_i w1[l, i] x[m, i*in_n + n]  (bf16 [M, ol*in_n]); x may be a column-sliced view."""
+    _req_cuda(x, w1, out)
+    ol, im = w1.shape
+    assert x.dtype == torch.bfloat16 and x.stride(1) == 1 and out.dtype == torch.bfloat16 and out.is_contiguous()
+    check(lib().uwu_lokr_z(_ptr(x), x.stride(0), _ptr(w1), M, ol, im, in_n, _ptr(out), _stream()), "uwu_lokr_z")
+    return out
+
+
+def lokr_dw1(v: torch.Tensor, x: torch.Tensor, M: int, ol: int, im: int, in_n: int, dw1: torch.Tensor, multiplier: float = 1.0):
+    """dw1[l, i] += multiplier * sum_{m, n} v[m, l*in_n + n] x[m, i*in_n + n]."""
+    _req_cuda(v, x, dw1)
+    assert v.dtype == x.dtype == torch.bfloat16 and v.is_contiguous() and x.stride(1) == 1 and dw1.dtype == torch.float32
+    check(lib().uwu_lokr_dw1(_ptr(v), _ptr(x), x.stride(0), M, ol, im, in_n, multiplier, _ptr(dw1), _stream()), "uwu_lokr_dw1")
 
 
 def lora_grad(G: torch.Tensor, up: torch.Tensor, down: torch.Tensor, scale: float, dup: torch.Tensor, ddown: torch.Tensor) -> None:

@@ -44,6 +44,11 @@ SDXL_UNET_CONFIG = dict(
 KNOWN_UNET_CONFIGS = {"stabilityai/stable-diffusion-xl-base-1.0": SDXL_UNET_CONFIG}
 
 
+# Adapter folds are batched into one launch per forward (LycorisNetwork.fold_all): `epoch` marks operands folded for the
+# current forward, `gen` changes whenever an operand cache is dropped (the fold table holds raw destination pointers).
+FOLD = types.SimpleNamespace(epoch=0, gen=0)
+
+
 def _pad_to(n: int, m: int) -> int:
     return (n + m - 1) // m * m
 
@@ -56,17 +61,34 @@ class _Cached:
 
     _uwu_adapter = None  # set by uwudiff_b200.lycoris.LycorisNetwork.apply_to()
 
+    _fold_epoch = -1     # FOLD.epoch of the forward whose batched fold refreshed this module's operand
+    _dst_override = None  # Linear only: row slice of a fused QKV / KV operand buffer owned by the Attention module
+
+    def _folded(self) -> bool:
+        return self._uwu_adapter is not None and self._fold_epoch == FOLD.epoch
+
     def _needs_refresh(self) -> bool:
         if getattr(self, "_cache", None) is None:
             return True
+        if self._folded():
+            return False
         return self._uwu_adapter is not None or self.weight.requires_grad
 
     def drop_cache(self):
         self._cache = None
+        FOLD.gen += 1
 
 
 class Linear(nn.Linear, _Cached):
     """y = x W^T + b on the tcgen05 GEMM; optional LoRA / LoKr adapter folded into the bf16 operand."""
+
+    def fold_dst(self) -> torch.Tensor:
+        """bf16 operand buffer the adapter fold writes (the fused-projection slice when there is one)."""
+        if self._dst_override is not None:
+            return self._dst_override
+        if getattr(self, "_cache", None) is None:
+            self._cache = torch.empty(self.weight.shape, device=self.weight.device, dtype=BF16)
+        return self._cache
 
     def w16(self, dst: Optional[torch.Tensor] = None) -> torch.Tensor:
         if dst is None:
@@ -103,6 +125,9 @@ class Linear(nn.Linear, _Cached):
         if self.bias is not None and self.bias.requires_grad:
             ops.colsum(dy, out=_grad_of(self.bias), accumulate=True)
         if ad is not None and ad.trainable():
+            if hasattr(ad, "factored_ok") and ad.factored_ok(M):
+                ad.grads_factored(dy, x, M)
+                return
             G = ops._workspace(N * K, dy.device, "wgrad")[: N * K].view(N, K)
             ops.gemm(dy, x, N, K, M, a_layout=A_COL, lda=dy.stride(0), b_layout=B_KN, ldb=x.stride(0), out=G)
             ad.grads_from(G)
@@ -112,7 +137,8 @@ def _fused_param_grads(mods, dy, x, M):
     """Adapter gradients of several Linears that share the input x and whose output gradients sit side by side in `dy`
     (the fused QKV / KV projections): ONE token-reduction GEMM G = dy^T x for all of them, then per-layer contractions."""
     if any(m.weight.requires_grad or (m.bias is not None and m.bias.requires_grad) for m in mods) or \
-            not all(m._uwu_adapter is not None and m._uwu_adapter.trainable() for m in mods):
+            not all(m._uwu_adapter is not None and m._uwu_adapter.trainable() for m in mods) or \
+            all(hasattr(m._uwu_adapter, "factored_ok") and m._uwu_adapter.factored_ok(M) for m in mods):
         off = 0
         for m in mods:
             m.param_grads(dy[:, off:off + m.out_features], x, M)
@@ -200,12 +226,17 @@ class _NormMixin(_Cached):
         ad = self._uwu_adapter
         if ad is None:
             return self.weight, self.bias
-        if getattr(self, "_cache", None) is None:
-            self._cache = (torch.empty_like(self.weight), torch.empty_like(self.bias))
-        g, b = self._cache
+        g, b = self.fold_dst()
+        if self._folded():
+            return g, b
         ops.axpy_f32(self.weight, ad.w_norm, ad.multiplier, g)
         ops.axpy_f32(self.bias, ad.b_norm, ad.multiplier, b)
         return g, b
+
+    def fold_dst(self):
+        if getattr(self, "_cache", None) is None:
+            self._cache = (torch.empty_like(self.weight), torch.empty_like(self.bias))
+        return self._cache
 
     def grad_targets(self):
         ad = self._uwu_adapter
@@ -328,16 +359,30 @@ class Attention(nn.Module):
     def _fused_w(self):
         """to_q|to_k|to_v (self) or to_k|to_v (cross) stacked into one bf16 operand -> one projection GEMM."""
         mods = [self.to_k, self.to_v] if self.is_cross else [self.to_q, self.to_k, self.to_v]
-        fresh = self._fused is None
-        if fresh:
-            self._fused = torch.empty((len(mods) * self.inner, mods[0].in_features), device=self.to_q.weight.device, dtype=BF16)
+        fresh = self._fused is None or getattr(self, "_fresh_fused", False)
+        self.ensure_fused()
+        self._fresh_fused = False
         for i, m in enumerate(mods):
+            if not fresh and m._folded():
+                continue
             if fresh or m._uwu_adapter is not None or m.weight.requires_grad:
                 m.w16(dst=self._fused[i * self.inner:(i + 1) * self.inner])
         return self._fused
 
+    def ensure_fused(self):
+        if self._fused is None:
+            mods = [self.to_k, self.to_v] if self.is_cross else [self.to_q, self.to_k, self.to_v]
+            self._fused = torch.empty((len(mods) * self.inner, mods[0].in_features), device=self.to_q.weight.device, dtype=BF16)
+            for i, m in enumerate(mods):
+                m._dst_override = self._fused[i * self.inner:(i + 1) * self.inner]
+            self._fresh_fused = True
+        return self._fused
+
     def drop_cache(self):
         self._fused = None
+        for m in (self.to_q, self.to_k, self.to_v):
+            m._dst_override = None
+        FOLD.gen += 1
 
     def fwd(self, n, x_res, st):
         """n: normed tokens [M, C]; x_res: residual stream; returns x_res + to_out(attn(n))."""
@@ -722,6 +767,10 @@ class UNet2DConditionModel(nn.Module):
         c = self.config
         B, Cin, H, W = sample.shape
         dev = sample.device
+        FOLD.epoch += 1
+        ly = getattr(self, "_uwu_lycoris", None)
+        if ly is not None:
+            ly.fold_all()  # every adapter delta folded into its bf16 operand (or norm affine) in one launch
         st = _State()
         st.N, st.H, st.W = B, H, W
         st.need_temb_grad = any(p.requires_grad for p in self.time_embedding.parameters())
@@ -791,6 +840,9 @@ class UNet2DConditionModel(nn.Module):
     def _backward_impl(self, gout):
         st, x_last, s_out, cat_shapes, (B, H, W) = self._fsv
         self._fsv = None
+        ly = getattr(self, "_uwu_lycoris", None)
+        if ly is not None:
+            ly.refresh_bf16()
         done = self.after_backward or (lambda mods: None)
         st.H, st.W = H, W
         dy = ops.nchw_to_nhwc(gout, self.conv_out._cache.cod_p)
