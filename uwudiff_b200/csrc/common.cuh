@@ -120,6 +120,14 @@ UWU_DEVINL void bulk_reduce_add_f32(void* gdst, const void* smem_src, uint32_t b
                  "r"(smem_u32(smem_src)), "r"(bytes)
                  : "memory");
 }
+// 2-D tile store shared -> global through a tensor map (bulk async-group completion); out-of-range parts are clipped
+UWU_DEVINL void tma_store_2d(const CUtensorMap* m, const void* smem_src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                     reinterpret_cast<uint64_t>(m)),
+                 "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+UWU_DEVINL void bulk_wait_group_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 UWU_DEVINL void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 UWU_DEVINL void bulk_wait_group_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 UWU_DEVINL void bulk_wait_group0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
@@ -223,6 +231,25 @@ UWU_DEVINL float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 UWU_DEVINL float silu_grad_f(float x) {
     float s = __fdividef(1.0f, 1.0f + __expf(-x));
     return s * (1.0f + x * (1.0f - s));
+}
+// erf-GELU pieces with Abramowitz-Stegun 7.1.26 (|erf error| <= 1.5e-7, far below a bf16 ulp): one ex2 + one rcp.
+// cdf = Phi(x) = 0.5 (1 + erf(x / sqrt 2)), pdf = phi(x); the exponential exp(-x^2/2) is shared by both.
+UWU_DEVINL void gelu_cdf_pdf(float x, float& cdf, float& pdf) {
+    const float u = fabsf(x) * 0.70710678118654752440f;
+    const float t = __fdividef(1.0f, fmaf(0.3275911f, u, 1.0f));
+    const float e = ex2_approx(-u * u * 1.4426950408889634f);
+    float p = fmaf(1.061405429f, t, -1.453152027f);
+    p = fmaf(p, t, 1.421413741f);
+    p = fmaf(p, t, -0.284496736f);
+    p = fmaf(p, t, 0.254829592f);
+    const float half_tail = 0.5f * p * t * e;  // 0.5 (1 - erf|u|)
+    cdf = x >= 0.f ? 1.0f - half_tail : half_tail;
+    pdf = 0.39894228040143267794f * e;
+}
+UWU_DEVINL float gelu_fast_f(float x) {
+    float c, p;
+    gelu_cdf_pdf(x, c, p);
+    return x * c;
 }
 UWU_DEVINL float gelu_erf_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 UWU_DEVINL float gelu_erf_grad_f(float x) {

@@ -20,40 +20,65 @@ UWU_DEVINL void st8e(__nv_bfloat16* p, const float (&v)[8]) {
     *reinterpret_cast<uint4*>(p) = u;
 }
 
-// out[m, f] = in[m, f] * gelu(in[m, F + f])
-__global__ void geglu_fwd_kernel(const __nv_bfloat16* __restrict__ in, long long M, int F, __nv_bfloat16* __restrict__ out) {
-    const int fv = F / 8;
-    const long long total = M * fv;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const long long m = i / fv;
-        const int f = (int)(i - m * fv) * 8;
+// out[m, f] = in[m, f] * gelu(in[m, F + f]).  Each block owns a contiguous range of rows and its threads walk the
+// (row, 8-wide column vector) pairs of that range with incremental 32-bit index updates (no 64-bit division).
+__global__ void __launch_bounds__(256) geglu_fwd_kernel(const __nv_bfloat16* __restrict__ in, long long M, int F,
+                                                        __nv_bfloat16* __restrict__ out) {
+    const int fv = F >> 3;
+    const long long rows_per = (M + gridDim.x - 1) / gridDim.x;
+    const long long m0 = blockIdx.x * rows_per;
+    const int nrows = (int)min(rows_per, M - m0);
+    if (nrows <= 0) return;
+    int r = threadIdx.x / fv, v = threadIdx.x - r * fv;
+    const int dr = blockDim.x / fv, dv = blockDim.x - dr * fv;
+    while (r < nrows) {
+        const __nv_bfloat16* ip = in + (m0 + r) * 2 * F;
         float h[8], g[8];
-        ld8e(in + m * 2 * F + f, h);
-        ld8e(in + m * 2 * F + F + f, g);
+        ld8e(ip + v * 8, h);
+        ld8e(ip + F + v * 8, g);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) h[j] *= gelu_erf_f(g[j]);
-        st8e(out + m * F + f, h);
+        for (int j = 0; j < 8; ++j) h[j] *= gelu_fast_f(g[j]);
+        st8e(out + (m0 + r) * F + v * 8, h);
+        r += dr;
+        v += dv;
+        if (v >= fv) {
+            v -= fv;
+            ++r;
+        }
     }
 }
-// din[m, f] = dout * gelu(g);  din[m, F+f] = dout * h * gelu'(g)
-__global__ void geglu_bwd_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16* __restrict__ dout, long long M,
-                                 int F, __nv_bfloat16* __restrict__ din) {
-    const int fv = F / 8;
-    const long long total = M * fv;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const long long m = i / fv;
-        const int f = (int)(i - m * fv) * 8;
+// din[m, f] = dout * gelu(g);  din[m, F+f] = dout * h * gelu'(g),  gelu'(g) = Phi(g) + g phi(g)
+__global__ void __launch_bounds__(256) geglu_bwd_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16* __restrict__ dout,
+                                                        long long M, int F, __nv_bfloat16* __restrict__ din) {
+    const int fv = F >> 3;
+    const long long rows_per = (M + gridDim.x - 1) / gridDim.x;
+    const long long m0 = blockIdx.x * rows_per;
+    const int nrows = (int)min(rows_per, M - m0);
+    if (nrows <= 0) return;
+    int r = threadIdx.x / fv, v = threadIdx.x - r * fv;
+    const int dr = blockDim.x / fv, dv = blockDim.x - dr * fv;
+    while (r < nrows) {
+        const __nv_bfloat16* ip = in + (m0 + r) * 2 * F;
+        __nv_bfloat16* op = din + (m0 + r) * 2 * F;
         float h[8], g[8], d[8], dh[8], dg[8];
-        ld8e(in + m * 2 * F + f, h);
-        ld8e(in + m * 2 * F + F + f, g);
-        ld8e(dout + m * F + f, d);
+        ld8e(ip + v * 8, h);
+        ld8e(ip + F + v * 8, g);
+        ld8e(dout + (m0 + r) * F + v * 8, d);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            dh[j] = d[j] * gelu_erf_f(g[j]);
-            dg[j] = d[j] * h[j] * gelu_erf_grad_f(g[j]);
+            float cdf, pdf;
+            gelu_cdf_pdf(g[j], cdf, pdf);
+            dh[j] = d[j] * g[j] * cdf;
+            dg[j] = d[j] * h[j] * fmaf(g[j], pdf, cdf);
         }
-        st8e(din + m * 2 * F + f, dh);
-        st8e(din + m * 2 * F + F + f, dg);
+        st8e(op + v * 8, dh);
+        st8e(op + F + v * 8, dg);
+        r += dr;
+        v += dv;
+        if (v >= fv) {
+            v -= fv;
+            ++r;
+        }
     }
 }
 
@@ -199,7 +224,7 @@ extern "C" int uwu_geglu_fwd(const void* in, int64_t M, int32_t F, void* out, vo
     UWU_CHECK_ARG(M >= 0 && F > 0 && F % 8 == 0, "uwu_geglu_fwd: bad shape M=%lld F=%d", (long long)M, F);
     if (M == 0) return UWU_OK;
     UWU_CHECK_ARG(in && out, "uwu_geglu_fwd: null pointer");
-    geglu_fwd_kernel<<<ew_grid(M * (F / 8), 256), 256, 0, stream>>>(reinterpret_cast<const bf16*>(in), M, F,
+    geglu_fwd_kernel<<<(unsigned)(M < 16ll * sm_count() ? M : 16ll * sm_count()), 256, 0, stream>>>(reinterpret_cast<const bf16*>(in), M, F,
                                                                     reinterpret_cast<bf16*>(out));
     UWU_CHECK_LAUNCH();
     return UWU_OK;
@@ -209,7 +234,7 @@ extern "C" int uwu_geglu_bwd(const void* in, const void* dout, int64_t M, int32_
     UWU_CHECK_ARG(M >= 0 && F > 0 && F % 8 == 0, "uwu_geglu_bwd: bad shape");
     if (M == 0) return UWU_OK;
     UWU_CHECK_ARG(in && dout && din, "uwu_geglu_bwd: null pointer");
-    geglu_bwd_kernel<<<ew_grid(M * (F / 8), 256), 256, 0, stream>>>(
+    geglu_bwd_kernel<<<(unsigned)(M < 16ll * sm_count() ? M : 16ll * sm_count()), 256, 0, stream>>>(
         reinterpret_cast<const bf16*>(in), reinterpret_cast<const bf16*>(dout), M, F, reinterpret_cast<bf16*>(din));
     UWU_CHECK_LAUNCH();
     return UWU_OK;

@@ -26,11 +26,15 @@ static constexpr int NUM_THREADS = 192;                      // 6 warps
 static constexpr int MAX_STAGES = 8;
 static constexpr int TMEM_COLS = 512;
 static constexpr int ACC_STRIDE = 256;
+static constexpr int EPI_STAGE_BYTES = 4 * 2 * 4096;  // 4 epilogue warps x 2 buffers x [32 rows x 128 B]
 
 struct GemmKernelArgs {
     CUtensorMap tmA;
     CUtensorMap tmA2;
     CUtensorMap tmB;
+    CUtensorMap tmO;   // bf16 output, box {64 columns, 32 rows}, 128B swizzle (epilogue TMA stores)
+    CUtensorMap tmO2;  // same for out2 (columns >= n_split)
+    int epi_tma;       // 1: bf16 output through shared-memory staging + TMA stores (coalesced), else direct stores
     int M, N;
     int num_kb;  // number of 64-wide K blocks (conv: ntaps * kb_per_tap)
     int block_n;
@@ -113,7 +117,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
     // 1024-byte alignment is required by the 128B swizzle atoms
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int stage_bytes = A_STAGE_BYTES + p.b_stage_bytes;
-    uint8_t* bar_base = smem + (size_t)p.stages * stage_bytes;
+    uint8_t* epi_stage = smem + (size_t)p.stages * stage_bytes;  // 1024-byte aligned (stage sizes are multiples of 1024)
+    uint8_t* bar_base = epi_stage + EPI_STAGE_BYTES;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(bar_base);
     uint64_t* empty_bar = full_bar + MAX_STAGES;
     uint64_t* tmem_full = empty_bar + MAX_STAGES;  // [2]
@@ -127,6 +132,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
         tma_prefetch_desc(&p.tmA);
         tma_prefetch_desc(&p.tmA2);
         tma_prefetch_desc(&p.tmB);
+        if (p.epi_tma) {
+            tma_prefetch_desc(&p.tmO);
+            tma_prefetch_desc(&p.tmO2);
+        }
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < p.stages; ++s) {
@@ -260,6 +269,155 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
         uint32_t acc_phase = 0;
         WorkIter wi;
         wi.init(p, num_tiles);
+        if (p.epi_tma) {
+            // ---- bf16 output: TMEM -> registers -> fused epilogue -> 128B-swizzled smem -> TMA store ----
+            // Each warp owns 32 rows and works in 64-column chunks through two private 4 KiB staging buffers; the store of
+            // chunk c overlaps the math of chunk c+1.  Residual rows are read with fully coalesced 16-byte loads (4 rows
+            // per warp instruction, one chunk ahead), transposed through the same staging buffer.
+            uint8_t* stg = epi_stage + sub * 8192;
+            const int lrow = lane >> 3, lchk = lane & 7;  // coalesced residual layout: 4 rows x 8 16-byte chunks per instruction
+            int buf = 0;
+            while (wi.next()) {
+                const int tile = wi.tile;
+                const int n_blk = tile % p.num_n_tiles;
+                const int m_blk = tile / p.num_n_tiles;
+                const int row0 = m_blk * BLOCK_M + sub * 32;
+                const int row = row0 + lane;
+                const int n0 = n_blk * p.block_n;
+                const int n_end = min(p.N, n0 + p.block_n);
+                const int nchunks = (n_end - n0 + 63) >> 6;
+                const bool row_ok = row < p.M;
+                const float* brow = (p.bias_rows != nullptr && row_ok) ? p.bias_rows + (size_t)(row / p.rows_per_bias) * p.N : nullptr;
+                uint4 rnext[8];
+                auto load_res = [&](int col0) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int r = row0 + lrow + 4 * i, cc = col0 + lchk * 8;
+                        rnext[i] = (r < p.M && cc < n_end) ? *reinterpret_cast<const uint4*>(p.residual + (size_t)r * p.ldr + cc)
+                                                           : make_uint4(0, 0, 0, 0);
+                    }
+                };
+                if (p.residual != nullptr) load_res(n0);
+                mbar_wait(&tmem_full[acc], acc_phase);
+                tc_fence_after();
+                const uint32_t t_row = tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(acc * ACC_STRIDE);
+                for (int ch = 0; ch < nchunks; ++ch) {
+                    const int col0 = n0 + ch * 64;
+                    uint32_t r[2][32];
+                    tmem_ld32(t_row + (uint32_t)(ch * 64), r[0]);
+                    tmem_ld32(t_row + (uint32_t)(ch * 64 + 32), r[1]);
+                    tmem_ld_wait();
+                    if (ch == nchunks - 1) {  // accumulator fully read: hand it back to the MMA warp before the stores
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+                    }
+                    uint8_t* sbuf = stg + buf * 4096;
+                    // the TMA store that last used this buffer (two chunks ago) must have finished reading it
+                    if (lane == 0) bulk_wait_group_read1();
+                    __syncwarp();
+                    uint4 rc[8];
+                    if (p.residual != nullptr) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int rr = lrow + 4 * i;
+                            *reinterpret_cast<uint4*>(sbuf + rr * 128 + ((lchk ^ (rr & 7)) << 4)) = rnext[i];
+                        }
+                        if (ch + 1 < nchunks) load_res(col0 + 64);  // next chunk's residual in flight during this chunk's math
+                        __syncwarp();
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) rc[j] = *reinterpret_cast<const uint4*>(sbuf + lane * 128 + ((j ^ (lane & 7)) << 4));
+                    }
+#pragma unroll
+                    for (int hh = 0; hh < 2; ++hh) {
+                        const int c32 = col0 + hh * 32;
+                        float v[32];
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[hh][j]) * p.alpha;
+                        if (c32 < n_end) {
+                            const bool full = c32 + 32 <= n_end;
+                            if (p.bias != nullptr) {
+                                const float* bp = p.bias + c32;
+                                if (full && ((reinterpret_cast<uintptr_t>(bp) & 15) == 0)) {
+#pragma unroll
+                                    for (int q = 0; q < 8; ++q) {
+                                        const float4 t = __ldg(reinterpret_cast<const float4*>(bp) + q);
+                                        v[q * 4] += t.x; v[q * 4 + 1] += t.y; v[q * 4 + 2] += t.z; v[q * 4 + 3] += t.w;
+                                    }
+                                } else {
+#pragma unroll
+                                    for (int j = 0; j < 32; ++j)
+                                        if (c32 + j < n_end) v[j] += __ldg(bp + j);
+                                }
+                            }
+                            if (brow != nullptr) {
+                                const float* bp = brow + c32;
+                                if (full && ((reinterpret_cast<uintptr_t>(bp) & 15) == 0)) {
+#pragma unroll
+                                    for (int q = 0; q < 8; ++q) {
+                                        const float4 t = __ldg(reinterpret_cast<const float4*>(bp) + q);
+                                        v[q * 4] += t.x; v[q * 4 + 1] += t.y; v[q * 4 + 2] += t.z; v[q * 4 + 3] += t.w;
+                                    }
+                                } else {
+#pragma unroll
+                                    for (int j = 0; j < 32; ++j)
+                                        if (c32 + j < n_end) v[j] += __ldg(bp + j);
+                                }
+                            }
+                        }
+                        if (p.residual != nullptr) {
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                const uint4 u = rc[hh * 4 + q];
+                                const float2 f0 = unpack_bf16(u.x), f1 = unpack_bf16(u.y), f2 = unpack_bf16(u.z), f3 = unpack_bf16(u.w);
+                                v[q * 8 + 0] += f0.x; v[q * 8 + 1] += f0.y; v[q * 8 + 2] += f1.x; v[q * 8 + 3] += f1.y;
+                                v[q * 8 + 4] += f2.x; v[q * 8 + 5] += f2.y; v[q * 8 + 6] += f3.x; v[q * 8 + 7] += f3.y;
+                            }
+                        }
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            uint4 o;
+                            o.x = pack_bf16(v[q * 8 + 0], v[q * 8 + 1]);
+                            o.y = pack_bf16(v[q * 8 + 2], v[q * 8 + 3]);
+                            o.z = pack_bf16(v[q * 8 + 4], v[q * 8 + 5]);
+                            o.w = pack_bf16(v[q * 8 + 6], v[q * 8 + 7]);
+                            const int j = hh * 4 + q;
+                            *reinterpret_cast<uint4*>(sbuf + lane * 128 + ((j ^ (lane & 7)) << 4)) = o;
+                        }
+                    }
+                    // a 64-wide box may only be stored when it stays inside this tile's columns (or runs off the end of
+                    // the tensor, where TMA clips); the narrow tail chunk of tiles with block_n % 64 != 0 is stored directly
+                    const bool box_ok = (col0 + 64 <= n0 + p.block_n) || (n0 + p.block_n >= p.N);
+                    if (box_ok) {
+                        fence_proxy_async();
+                        __syncwarp();
+                        if (lane == 0) {
+                            if (col0 >= p.n_split)
+                                tma_store_2d(&p.tmO2, sbuf, col0 - p.n_split, row0);
+                            else
+                                tma_store_2d(&p.tmO, sbuf, col0, row0);
+                            bulk_commit_group();
+                        }
+                        buf ^= 1;
+                    } else if (row_ok) {
+                        __nv_bfloat16* op = (col0 >= p.n_split)
+                                                ? reinterpret_cast<__nv_bfloat16*>(p.out2) + (size_t)row * p.ldo2 + (col0 - p.n_split)
+                                                : reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)row * p.ldo + col0;
+                        const int w8 = (n_end - col0) >> 3;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            if (j < w8)
+                                *reinterpret_cast<uint4*>(op + j * 8) =
+                                    *reinterpret_cast<const uint4*>(sbuf + lane * 128 + ((j ^ (lane & 7)) << 4));
+                    }
+                }
+                if (++acc == 2) {
+                    acc = 0;
+                    acc_phase ^= 1;
+                }
+            }
+            if (lane == 0) bulk_wait_group0();  // all stores have landed before the CTA releases its shared memory
+        } else
         while (wi.next()) {
             const int tile = wi.tile;
             const int n_blk = tile % p.num_n_tiles;
@@ -268,30 +426,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
             const int n0 = n_blk * p.block_n;
             const int n_end = min(p.N, n0 + p.block_n);
             const bool row_ok = row < p.M;
-            // The residual does not depend on the accumulator: pull this thread's whole row segment (<= 256 bf16) into
-            // registers BEFORE waiting for the MMAs, so its global-memory latency hides behind the main loop.
-            uint4 rres[8][4];
-            const __nv_bfloat16* rrow = p.residual != nullptr ? p.residual + (size_t)row * p.ldr + n0 : nullptr;
-            const bool res_vec = rrow != nullptr && row_ok && ((reinterpret_cast<uintptr_t>(rrow) & 15) == 0);
-            if (res_vec) {
-#pragma unroll
-                for (int ci = 0; ci < 8; ++ci) {
-                    if (ci * 32 < p.block_n && n0 + ci * 32 + 32 <= n_end) {
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) rres[ci][q] = *reinterpret_cast<const uint4*>(rrow + ci * 32 + q * 8);
-                    }
-                }
-            }
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
             const uint32_t t_row = tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(acc * ACC_STRIDE);
             const float* brow = (p.bias_rows != nullptr && row_ok)
                                     ? p.bias_rows + (size_t)(row / p.rows_per_bias) * p.N
                                     : nullptr;
-#pragma unroll
-            for (int ci = 0; ci < 8; ++ci) {
-                const int c = ci * 32;
-                if (c >= p.block_n) break;
+            for (int c = 0; c < p.block_n; c += 32) {
                 uint32_t r[32];
                 tmem_ld32(t_row + (uint32_t)c, r);
                 tmem_ld_wait();
@@ -345,10 +486,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
                 }
                 if (p.residual != nullptr) {
                     const __nv_bfloat16* rp = p.residual + (size_t)row * p.ldr + col0;
-                    if (vec_ok && res_vec) {
+                    if (vec_ok && ((reinterpret_cast<uintptr_t>(rp) & 15) == 0)) {
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
-                            const uint4 u = rres[ci][q];
+                            const uint4 u = *reinterpret_cast<const uint4*>(rp + q * 8);
                             float2 f0 = unpack_bf16(u.x), f1 = unpack_bf16(u.y), f2 = unpack_bf16(u.z),
                                    f3 = unpack_bf16(u.w);
                             v[q * 8 + 0] += f0.x; v[q * 8 + 1] += f0.y; v[q * 8 + 2] += f1.x; v[q * 8 + 3] += f1.y;
@@ -609,6 +750,26 @@ extern "C" int uwu_gemm(const uwu_gemm_desc* d, void* stream_) {
     p.ldr = d->ldr > 0 ? d->ldr : d->N;
     p.alpha = d->alpha;
     p.accumulate = d->accumulate;
+    // bf16 outputs whose rows are 16-byte aligned go through the staged TMA-store epilogue
+    p.epi_tma = 0;
+    {
+        const bool res_ok = d->residual == nullptr || (p.ldr % 8 == 0 && (reinterpret_cast<uintptr_t>(d->residual) & 15) == 0);
+        const bool o2_ok = d->out2 == nullptr || (p.ldo2 % 8 == 0 && (reinterpret_cast<uintptr_t>(d->out2) & 15) == 0 && d->n_split % 64 == 0);
+        if (!p.out_fp32 && p.ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(d->out) & 15) == 0 && p.N % 8 == 0 && res_ok && o2_ok) {
+            const long long n1 = d->out2 ? (long long)d->n_split : (long long)p.N;
+            uint64_t dims[2] = {(uint64_t)n1, (uint64_t)p.M};
+            uint64_t str[1] = {(uint64_t)p.ldo * 2};
+            uint32_t box[2] = {64, 32};
+            if (encode_tmap_bf16(&p.tmO, d->out, 2, dims, str, box, 1)) return UWU_ERR_INVALID;
+            p.tmO2 = p.tmO;
+            if (d->out2) {
+                uint64_t dims2[2] = {(uint64_t)(p.N - d->n_split), (uint64_t)p.M};
+                uint64_t str2[1] = {(uint64_t)p.ldo2 * 2};
+                if (encode_tmap_bf16(&p.tmO2, d->out2, 2, dims2, str2, box, 1)) return UWU_ERR_INVALID;
+            }
+            p.epi_tma = 1;
+        }
+    }
     // stream-K: few output tiles but a long reduction (token-reduction weight gradients) would leave most SMs idle
     const int n_tiles_all = p.num_m_tiles * p.num_n_tiles;
     int sk = d->stream_k;
@@ -633,12 +794,12 @@ extern "C" int uwu_gemm(const uwu_gemm_desc* d, void* stream_) {
 
     // ---------------- launch ----------------
     const int stage_bytes = A_STAGE_BYTES + p.b_stage_bytes;
-    const int smem_budget = 227 * 1024 - 1024 /*align slack*/ - 256 /*barriers*/;
+    const int smem_budget = 227 * 1024 - 1024 /*align slack*/ - 256 /*barriers*/ - EPI_STAGE_BYTES;
     int stages = smem_budget / stage_bytes;
     if (stages > MAX_STAGES) stages = MAX_STAGES;
     UWU_CHECK_ARG(stages >= 2, "uwu_gemm: tile too large for shared memory");
     p.stages = stages;
-    const size_t smem_bytes = (size_t)stages * stage_bytes + 1024 + 256;
+    const size_t smem_bytes = (size_t)stages * stage_bytes + EPI_STAGE_BYTES + 1024 + 256;
 
     static bool attr_set = false;
     if (!attr_set) {

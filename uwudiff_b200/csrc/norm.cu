@@ -478,6 +478,109 @@ __global__ void __launch_bounds__(128, (kMaxV >= 5 && kParamGrads) ? 2 : 3) ln_b
     }
 }
 
+// LayerNorm backward WITH parameter gradients: thread = one 8-wide column vector of the row (block = ceil(C/256) warps
+// covers a whole row), R rows per step.  Column ownership makes the dgamma / dbeta accumulators 16 registers per thread
+// and their reduction deterministic (no atomics); the two per-row sums are combined across the block's warps through
+// shared memory, one barrier per step (double-buffered partials).
+//   pg[blockIdx.x][0][c] = sum_rows dy * xhat,  pg[blockIdx.x][1][c] = sum_rows dy
+template <int R>
+__global__ void __launch_bounds__(192, 4) ln_bwd_cols_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
+                                                          int M, int C, const float* __restrict__ gamma,
+                                                          const float* __restrict__ stats, const __nv_bfloat16* __restrict__ dres,
+                                                          __nv_bfloat16* __restrict__ dx, float* __restrict__ pg) {
+    __shared__ float part[2][R][8][2];  // [parity][row][warp][s1, s2]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    const int cv = C >> 3;
+    const int v = threadIdx.x;
+    const bool active = v < cv;
+    const float inv_c = 1.0f / (float)C;
+    float ga[8], ag[8], ab[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) ag[j] = ab[j] = 0.f;
+    if (active) {
+        if (gamma) ldf8(gamma + v * 8, ga);
+        else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) ga[j] = 1.0f;
+        }
+    }
+    int par = 0;
+    for (int r0 = blockIdx.x * R; r0 < M; r0 += gridDim.x * R, par ^= 1) {
+        uint4 rx[R], rd[R], rr[R];
+        float mean[R], rstd[R];
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+            const int row = r0 + k;
+            const bool ok = active && row < M;
+            const size_t off = (size_t)row * C + v * 8;
+            rx[k] = ok ? *reinterpret_cast<const uint4*>(x + off) : make_uint4(0, 0, 0, 0);
+            rd[k] = ok ? *reinterpret_cast<const uint4*>(dy + off) : make_uint4(0, 0, 0, 0);
+            rr[k] = (ok && dres) ? *reinterpret_cast<const uint4*>(dres + off) : make_uint4(0, 0, 0, 0);
+            mean[k] = row < M ? stats[(size_t)row * 2] : 0.f;
+            rstd[k] = row < M ? stats[(size_t)row * 2 + 1] : 0.f;
+        }
+        float s1[R], s2[R];
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+            float f[8], d[8];
+            unpack8(rx[k], f);
+            unpack8(rd[k], d);
+            float a = 0.f, b = 0.f;
+            if (active && r0 + k < M) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float h = (f[j] - mean[k]) * rstd[k];
+                    const float gv = d[j] * ga[j];
+                    a += gv;
+                    b = fmaf(gv, h, b);
+                    ag[j] = fmaf(d[j], h, ag[j]);
+                    ab[j] += d[j];
+                }
+            }
+            s1[k] = warp_sum(a);
+            s2[k] = warp_sum(b);
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int k = 0; k < R; ++k) {
+                part[par][k][warp][0] = s1[k];
+                part[par][k][warp][1] = s2[k];
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+            float a = 0.f, b = 0.f;
+            for (int w = 0; w < nw; ++w) {
+                a += part[par][k][w][0];
+                b += part[par][k][w][1];
+            }
+            a *= inv_c;
+            b *= inv_c;
+            if (active && r0 + k < M) {
+                float f[8], d[8], e[8], o[8];
+                unpack8(rx[k], f);
+                unpack8(rd[k], d);
+                unpack8(rr[k], e);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float h = (f[j] - mean[k]) * rstd[k];
+                    o[j] = rstd[k] * (d[j] * ga[j] - a - h * b) + e[j];
+                }
+                st8(dx + (size_t)(r0 + k) * C + v * 8, o);
+            }
+        }
+    }
+    if (active) {
+        float* o = pg + (size_t)blockIdx.x * 2 * C + v * 8;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            o[j] = ag[j];
+            o[C + j] = ab[j];
+        }
+    }
+}
+
 // out[c] (+)= sum_p partial[p, c]
 __global__ void colsum_partials_kernel(const float* __restrict__ partial, int P, int stride, int n, int accumulate,
                                        float* __restrict__ out) {
@@ -610,7 +713,7 @@ extern "C" int uwu_layernorm_fwd(const void* x, int32_t M, int32_t C, float eps,
 
 static int ln_bwd_grid(int M) {
     int blocks = (M + 3) / 4;
-    const int cap = sm_count() * 3;
+    const int cap = sm_count() * 6;
     return blocks < cap ? blocks : cap;
 }
 
@@ -628,6 +731,26 @@ extern "C" int uwu_layernorm_bwd(const void* x, const void* dy, int32_t M, int32
     UWU_CHECK_ARG(x && dy && dx && stats, "uwu_layernorm_bwd: null pointer");
     const bool want_pg = dgamma != nullptr || dbeta != nullptr;
     UWU_CHECK_ARG(!want_pg || workspace, "uwu_layernorm_bwd: workspace required for parameter gradients");
+    if (want_pg && C <= 192 * 8) {
+        const int threads = ((C / 8 + 31) / 32) * 32;
+        const int grid2 = ln_bwd_grid(M);
+        ln_bwd_cols_kernel<2><<<grid2, threads, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x),
+                                                             reinterpret_cast<const __nv_bfloat16*>(dy), M, C, gamma, stats,
+                                                             reinterpret_cast<const __nv_bfloat16*>(dres),
+                                                             reinterpret_cast<__nv_bfloat16*>(dx), workspace);
+        UWU_CHECK_LAUNCH();
+        if (!accumulate) {
+            if (dgamma) UWU_CHECK_CUDA(cudaMemsetAsync(dgamma, 0, (size_t)C * 4, stream));
+            if (dbeta) UWU_CHECK_CUDA(cudaMemsetAsync(dbeta, 0, (size_t)C * 4, stream));
+        }
+        int slices = 16;
+        if (slices > grid2) slices = grid2;
+        const int p_per = (grid2 + slices - 1) / slices;
+        slices = (grid2 + p_per - 1) / p_per;
+        ln_param_reduce_kernel<<<dim3((2 * C + 127) / 128, slices), 128, 0, stream>>>(workspace, grid2, C, p_per, dgamma, dbeta);
+        UWU_CHECK_LAUNCH();
+        return UWU_OK;
+    }
     const int grid = ln_bwd_grid(M);
     const int cv = C / 8;
     const auto* xp = reinterpret_cast<const __nv_bfloat16*>(x);
