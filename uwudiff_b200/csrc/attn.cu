@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) attn_fwd_kernel(const __grid_c
             const uint32_t lane_addr = (uint32_t)(sub * 32) << 16;
             const uint32_t t_s = tmem_base + lane_addr + (uint32_t)(t * 128);
             const uint32_t t_pv = tmem_base + lane_addr + 256u + (uint32_t)(t * 64);
-            uint8_t* prow = smem + FWD_SP + t * 2 * AT_TILE + row * 128;
+            const uint32_t prow_s = smem_u32(smem + FWD_SP + t * 2 * AT_TILE + row * 128);
             const int sw = row & 7;
             const float sl2 = p.scale_log2;
             float O[64];
@@ -230,7 +230,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) attn_fwd_kernel(const __grid_c
                         u.z = pack_bf16(pe[q4 * 8 + 4], pe[q4 * 8 + 5]);
                         u.w = pack_bf16(pe[q4 * 8 + 6], pe[q4 * 8 + 7]);
                         const int cc = (c & 1) * 4 + q4;
-                        *reinterpret_cast<uint4*>(prow + (c >> 1) * AT_TILE + ((cc ^ sw) << 4)) = u;
+                        st_shared_v4(prow_s + (uint32_t)((c >> 1) * AT_TILE + ((cc ^ sw) << 4)), u);
                     }
                 }
                 l = fmaf(l, alpha, rs);
@@ -333,7 +333,7 @@ struct BwdCfg {
     static constexpr int BAR = SS1 + kStages * AT_TILE;
     static constexpr int SMEM = BAR + 256 + 1024;
 };
-static constexpr int BWD_THREADS = 320;
+static constexpr int BWD_THREADS = 64 + 512;  // TMA warp, MMA warp, 16 compute warps (4 per SM sub-partition)
 // TMEM columns: S [0,128) dP [128,256) acc0 [256,320) acc1 [320,384)
 
 // Two passes over the (query tile, key tile) pairs, neither needs a cross-CTA reduction or an fp32 scratch:
@@ -380,8 +380,8 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_kernel(const __grid_c
             mbar_init(&st_empty[s], 1);
         }
         mbar_init(sdp_full, 1);
-        mbar_init(sdp_empty, 8);
-        mbar_init(pds_full, 8);
+        mbar_init(sdp_empty, 16);
+        mbar_init(pds_full, 16);
         mbar_init(pds_empty, 1);
         mbar_init(acc_full, 1);
         fence_barrier_init();
@@ -486,15 +486,17 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_kernel(const __grid_c
             umma_commit(acc_full);
         }
     } else {
+        // 16 compute warps: warp (sub, quarter) owns TMEM lanes [32 sub, +32) (the query rows) and key columns [32 quarter, +32)
         const int cw = warp - 2;
         const int sub = warp & 3;
-        const int half = cw >> 2;
+        const int quarter = cw >> 2;
+        const int half = quarter >> 1;    // which [128 x 64] smem tile / which 32-column half of the 64-wide accumulators
         const int row = sub * 32 + lane;  // query row within the tile == TMEM lane
         const int sw = row & 7;
         const uint32_t lane_addr = (uint32_t)(sub * 32) << 16;
         const float sl2 = p.scale_log2;
-        uint8_t* prow = smem + BWD_SP + half * AT_TILE + row * 128;
-        uint8_t* dsrow = smem + BWD_SDS + half * AT_TILE + row * 128;
+        const uint32_t prow_s = smem_u32(smem + BWD_SP + half * AT_TILE + row * 128);
+        const uint32_t dsrow_s = smem_u32(smem + BWD_SDS + half * AT_TILE + row * 128);
         // lse * log2(e) and delta of this thread's query row (padded rows of the scratch are zero and never written out)
         const float* lse_p = p.lse2 + bh * p.Lq_pad + row;
         const float* del_p = p.delta + bh * p.Lq_pad + row;
@@ -507,51 +509,46 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_kernel(const __grid_c
             }
             mbar_wait(sdp_full, (uint32_t)(i & 1));
             tc_fence_after();
-            uint4 pu[kDQ ? 1 : 8], du[8];
+            // pull this thread's 32 S and 32 dP values out of TMEM and hand the accumulators back to the MMA warp
+            uint32_t rs1[32], rp1[32];
+            tmem_ld32(tmem_base + lane_addr + (uint32_t)(quarter * 32), rs1);
+            tmem_ld32(tmem_base + lane_addr + 128u + (uint32_t)(quarter * 32), rp1);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(sdp_empty);
+            uint4 pu[kDQ ? 1 : 4], du[4];
 #pragma unroll
-            for (int cc = 0; cc < 2; ++cc) {
-                // pull 32 S and 32 dP values out of TMEM; after the second half the accumulators go back to the MMA warp
-                uint32_t rs1[32], rp1[32];
-                tmem_ld32(tmem_base + lane_addr + (uint32_t)(half * 64 + cc * 32), rs1);
-                tmem_ld32(tmem_base + lane_addr + 128u + (uint32_t)(half * 64 + cc * 32), rp1);
-                tmem_ld_wait();
-                if (cc == 1) {
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(sdp_empty);
+            for (int q4 = 0; q4 < 4; ++q4) {
+                float pe[8], ds[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const int i2 = q4 * 8 + e;
+                    pe[e] = ex2_approx(fmaf(__uint_as_float(rs1[i2]), sl2, -my_lse));
+                    ds[e] = pe[e] * (__uint_as_float(rp1[i2]) - my_delta);
                 }
-#pragma unroll
-                for (int q4 = 0; q4 < 4; ++q4) {
-                    float pe[8], ds[8];
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        const int i2 = q4 * 8 + e;
-                        pe[e] = ex2_approx(fmaf(__uint_as_float(rs1[i2]), sl2, -my_lse));
-                        ds[e] = pe[e] * (__uint_as_float(rp1[i2]) - my_delta);
-                    }
-                    uint4 w;
-                    w.x = pack_bf16(ds[0], ds[1]);
-                    w.y = pack_bf16(ds[2], ds[3]);
-                    w.z = pack_bf16(ds[4], ds[5]);
-                    w.w = pack_bf16(ds[6], ds[7]);
-                    du[cc * 4 + q4] = w;
-                    if (!kDQ) {
-                        uint4 u;
-                        u.x = pack_bf16(pe[0], pe[1]);
-                        u.y = pack_bf16(pe[2], pe[3]);
-                        u.z = pack_bf16(pe[4], pe[5]);
-                        u.w = pack_bf16(pe[6], pe[7]);
-                        pu[kDQ ? 0 : cc * 4 + q4] = u;
-                    }
+                uint4 w;
+                w.x = pack_bf16(ds[0], ds[1]);
+                w.y = pack_bf16(ds[2], ds[3]);
+                w.z = pack_bf16(ds[4], ds[5]);
+                w.w = pack_bf16(ds[6], ds[7]);
+                du[q4] = w;
+                if (!kDQ) {
+                    uint4 u;
+                    u.x = pack_bf16(pe[0], pe[1]);
+                    u.y = pack_bf16(pe[2], pe[3]);
+                    u.z = pack_bf16(pe[4], pe[5]);
+                    u.w = pack_bf16(pe[6], pe[7]);
+                    pu[kDQ ? 0 : q4] = u;
                 }
             }
             // the accumulating products of the previous iteration have retired: their smem operands may be overwritten
             mbar_wait(pds_empty, (uint32_t)((i & 1) ^ 1));
 #pragma unroll
-            for (int c8 = 0; c8 < 8; ++c8) {
-                const int chunk = (c8 ^ sw) << 4;
-                if (!kDQ) *reinterpret_cast<uint4*>(prow + chunk) = pu[kDQ ? 0 : c8];
-                *reinterpret_cast<uint4*>(dsrow + chunk) = du[c8];
+            for (int q4 = 0; q4 < 4; ++q4) {
+                const uint32_t chunk = (uint32_t)(((((quarter & 1) << 2) + q4) ^ sw) << 4);
+                if (!kDQ) st_shared_v4(prow_s + chunk, pu[kDQ ? 0 : q4]);
+                st_shared_v4(dsrow_s + chunk, du[q4]);
             }
             fence_proxy_async();
             __syncwarp();
@@ -560,17 +557,18 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_kernel(const __grid_c
             my_delta = nx_delta;
         }
         // ---- write the accumulators (TMEM lane = key row in the dK/dV pass, query row in the dQ pass) ----
+        // warp (sub, quarter) writes columns [16 quarter, +16) of its 32 rows
         mbar_wait(acc_full, 0);
         tc_fence_after();
         const int r = r0 + row;
         if (kDQ) {
-            uint32_t v[32];
-            tmem_ld32(tmem_base + lane_addr + 320u + (uint32_t)(half * 32), v);
+            uint32_t v[16];
+            tmem_ld16(tmem_base + lane_addr + 320u + (uint32_t)(quarter * 16), v);
             tmem_ld_wait();
             if (r < p.Lq) {
-                __nv_bfloat16* op = p.dq + ((size_t)b * p.Lq + r) * p.lddq + h * 64 + half * 32;
+                __nv_bfloat16* op = p.dq + ((size_t)b * p.Lq + r) * p.lddq + h * 64 + quarter * 16;
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
+                for (int c = 0; c < 2; ++c) {
                     uint4 u;
                     u.x = pack_bf16(__uint_as_float(v[c * 8 + 0]) * p.scale, __uint_as_float(v[c * 8 + 1]) * p.scale);
                     u.y = pack_bf16(__uint_as_float(v[c * 8 + 2]) * p.scale, __uint_as_float(v[c * 8 + 3]) * p.scale);
@@ -582,15 +580,15 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_kernel(const __grid_c
         } else {
 #pragma unroll
             for (int which = 0; which < 2; ++which) {
-                uint32_t v[32];
-                tmem_ld32(tmem_base + lane_addr + 256u + (uint32_t)(which * 64 + half * 32), v);
+                uint32_t v[16];
+                tmem_ld16(tmem_base + lane_addr + 256u + (uint32_t)(which * 64 + quarter * 16), v);
                 tmem_ld_wait();
                 if (r < p.Lk) {
                     const float sc = which ? p.scale : 1.0f;
                     __nv_bfloat16* base = which ? p.dk + ((size_t)b * p.Lk + r) * p.lddk : p.dv + ((size_t)b * p.Lk + r) * p.lddv;
-                    __nv_bfloat16* op = base + h * 64 + half * 32;
+                    __nv_bfloat16* op = base + h * 64 + quarter * 16;
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) {
+                    for (int c = 0; c < 2; ++c) {
                         uint4 u;
                         u.x = pack_bf16(__uint_as_float(v[c * 8 + 0]) * sc, __uint_as_float(v[c * 8 + 1]) * sc);
                         u.y = pack_bf16(__uint_as_float(v[c * 8 + 2]) * sc, __uint_as_float(v[c * 8 + 3]) * sc);

@@ -16,6 +16,10 @@ namespace uwu {
 // ----------------------------------------------------------------------------------------------
 UWU_DEVINL uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// explicit shared-window 16-byte store (a generic ST forces the fence before an async-proxy read to drain global traffic too)
+UWU_DEVINL void st_shared_v4(uint32_t saddr, const uint4& v) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
 UWU_DEVINL uint32_t lane_id() { return threadIdx.x & 31; }
 
 UWU_DEVINL bool elect_one() {
