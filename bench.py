@@ -282,16 +282,25 @@ def run_gpu(args):
             ms = t.item()
         return ms / n, ops.launch_count() - l0, (w0, w1), last
 
+    def note(msg):
+        if rank == 0:
+            print(f"[bench] {msg}", file=sys.stderr, flush=True)
+
+    note(f"trainer ready (world {world})")
     for i in range(max(args.warmup, 3)):
         trainer.fit_step(dev_batch, i)
+    barrier()
+    note("warm-up done")
     clocks = ClockSampler(local) if rank == 0 else None
     ms_dev, launches, (w0, _), loss_dev = timed(args.steps, lambda: dev_batch, False)
     ms_e2e, _, (_, w1), loss_host = timed(args.steps, host_batch, True)
     clk = clocks.stop(w0, w1) if clocks is not None else None
+    note(f"timed: {ms_dev:.1f} ms/step resident, {ms_e2e:.1f} ms/step end-to-end")
 
     # ---- dominant kernel: every tcgen05 GEMM / conv launch of one more step, CUDA events on the launching stream ----
+    # (every rank runs this extra step: it contains the gradient all-reduce; only rank 0 keeps the timings)
     roof = None
-    if rank == 0:
+    if True:
         real_gemm = ops.gemm
         recs = []
 
@@ -300,7 +309,7 @@ def run_gpu(args):
             s.record()
             r = real_gemm(a, b, M, N, K, **kw)
             e.record()
-            recs.append((s, e, 2.0 * M * N * K))
+            recs.append((s, e, 2.0 * M * N * K * max(1, kw.get("k_segs", 0))))
             return r
 
         ops.gemm = timed_gemm
@@ -309,6 +318,7 @@ def run_gpu(args):
             torch.cuda.synchronize()
         finally:
             ops.gemm = real_gemm
+    if rank == 0:
         t_ms = sum(s.elapsed_time(e) for s, e, _ in recs)
         fl = sum(f for _, _, f in recs)
         pk, pk_src = peaks()
