@@ -188,16 +188,17 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) attn_fwd_kernel(const __grid_c
                 mbar_wait(&s_full[t], (uint32_t)(j & 1));
                 tc_fence_after();
                 const int kv_valid = min(128, p.Lk - j * 128);
-                // pass 1: row maximum
+                const bool full = kv_valid == 128;
+                // pass 1: row maximum (3-input max: two scores per instruction)
                 float mx = -INFINITY;
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                     uint32_t r[32];
                     tmem_ld32(t_s + (uint32_t)(c * 32), r);
                     tmem_ld_wait();
-                    if (kv_valid == 128) {
+                    if (full) {
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
+                        for (int i = 0; i < 32; i += 2) mx = fmax3(mx, __uint_as_float(r[i]), __uint_as_float(r[i + 1]));
                     } else {
 #pragma unroll
                         for (int i = 0; i < 32; ++i)
@@ -215,12 +216,19 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) attn_fwd_kernel(const __grid_c
                     tmem_ld32(t_s + (uint32_t)(c * 32), r);
                     tmem_ld_wait();
                     float pe[32];
+                    if (full) {
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        float e = ex2_approx(fmaf(__uint_as_float(r[i]), sl2, -msl));
-                        if (kv_valid != 128 && c * 32 + i >= kv_valid) e = 0.f;
-                        pe[i] = e;
-                        rs += e;
+                        for (int i = 0; i < 32; ++i) {
+                            pe[i] = ex2_approx(fmaf(__uint_as_float(r[i]), sl2, -msl));
+                            rs += pe[i];
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            const float e = ex2_approx(fmaf(__uint_as_float(r[i]), sl2, -msl));
+                            pe[i] = (c * 32 + i < kv_valid) ? e : 0.f;
+                            rs += pe[i];
+                        }
                     }
 #pragma unroll
                     for (int q4 = 0; q4 < 4; ++q4) {
@@ -495,6 +503,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_kernel(const __grid_c
         const int sw = row & 7;
         const uint32_t lane_addr = (uint32_t)(sub * 32) << 16;
         const float sl2 = p.scale_log2;
+        const uint64_t sl2_2 = pk2(sl2, sl2);
         const uint32_t prow_s = smem_u32(smem + BWD_SP + half * AT_TILE + row * 128);
         const uint32_t dsrow_s = smem_u32(smem + BWD_SDS + half * AT_TILE + row * 128);
         // lse * log2(e) and delta of this thread's query row (padded rows of the scratch are zero and never written out)
@@ -518,29 +527,22 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_kernel(const __grid_c
             __syncwarp();
             if (lane == 0) mbar_arrive(sdp_empty);
             uint4 pu[kDQ ? 1 : 4], du[4];
+            const uint64_t nl2 = pk2(-my_lse, -my_lse), nd2 = pk2(-my_delta, -my_delta);
 #pragma unroll
             for (int q4 = 0; q4 < 4; ++q4) {
-                float pe[8], ds[8];
+                uint32_t pw[4], dw[4];
 #pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    const int i2 = q4 * 8 + e;
-                    pe[e] = ex2_approx(fmaf(__uint_as_float(rs1[i2]), sl2, -my_lse));
-                    ds[e] = pe[e] * (__uint_as_float(rp1[i2]) - my_delta);
+                for (int e = 0; e < 4; ++e) {  // two elements per step: FFMA2 / FADD2 / FMUL2
+                    const int i2 = q4 * 8 + 2 * e;
+                    float a0, a1, d0, d1;
+                    unpk2(ffma2(pk2u(rs1[i2], rs1[i2 + 1]), sl2_2, nl2), a0, a1);
+                    const float p0 = ex2_approx(a0), p1 = ex2_approx(a1);
+                    unpk2(fmul2(pk2(p0, p1), fadd2(pk2u(rp1[i2], rp1[i2 + 1]), nd2)), d0, d1);
+                    pw[e] = pack_bf16(p0, p1);
+                    dw[e] = pack_bf16(d0, d1);
                 }
-                uint4 w;
-                w.x = pack_bf16(ds[0], ds[1]);
-                w.y = pack_bf16(ds[2], ds[3]);
-                w.z = pack_bf16(ds[4], ds[5]);
-                w.w = pack_bf16(ds[6], ds[7]);
-                du[q4] = w;
-                if (!kDQ) {
-                    uint4 u;
-                    u.x = pack_bf16(pe[0], pe[1]);
-                    u.y = pack_bf16(pe[2], pe[3]);
-                    u.z = pack_bf16(pe[4], pe[5]);
-                    u.w = pack_bf16(pe[6], pe[7]);
-                    pu[kDQ ? 0 : q4] = u;
-                }
+                du[q4] = make_uint4(dw[0], dw[1], dw[2], dw[3]);
+                if (!kDQ) pu[kDQ ? 0 : q4] = make_uint4(pw[0], pw[1], pw[2], pw[3]);
             }
             // the accumulating products of the previous iteration have retired: their smem operands may be overwritten
             mbar_wait(pds_empty, (uint32_t)((i & 1) ^ 1));
