@@ -236,6 +236,18 @@ typedef struct uwu_fold_entry {
 } uwu_fold_entry;
 int uwu_fold_batch(const uwu_fold_entry* entries_dev, const int32_t* chunk_entry_dev, int32_t n_chunks, int32_t chunk_elems,
                    void* stream);
+
+/* Full fine-tuning (trainable base weights, trainer.py:160-169 `self.unet.requires_grad_(True)` when lycoris_config is None):
+ * the 3x3 convolution weight gradient is the token-reduction GEMM dW = dY^T im2col(X) (uwu_gemm, A_COL x B_KN, stream-K);
+ *   uwu_im2col3x3        : cols[(n,ho,wo), t*C + c] = x[n, ho*stride + t/3 - 1, wo*stride + t%3 - 1, c] (zero padded), bf16 NHWC
+ *   uwu_conv_wgrad_unpack: wgrad[co, ci, t] (+)= G[co, t*Ci_pad + ci]   (torch Conv2d layout <- packed GEMM layout)
+ *   uwu_colsum_groups_bf16: out[g, c] (+)= sum_r x[g*rows + r, c]        (per-image sums: gradient of the time-embedding bias rows)
+ * Replaces autograd's conv2d weight gradient / sum reductions under loss.backward() in the reference's full fine-tuning mode. */
+int uwu_im2col3x3(const void* x, int32_t N, int32_t H, int32_t W, int32_t C, int32_t stride, void* cols, void* stream);
+int uwu_conv_wgrad_unpack(const float* G, int64_t ldg, int32_t Co, int32_t Ci, int32_t Ci_pad, int32_t taps, int32_t accumulate,
+                          float* wgrad, void* stream);
+int uwu_colsum_groups_bf16(const void* x, int64_t ldx, int32_t groups, int32_t rows, int32_t C, int32_t accumulate, float* out,
+                           void* stream);
 /* adapter gradients from G = dY^T X (fp32 [N, ldg]); dw1/dw2 (dup/ddown) are ACCUMULATED into */
 int uwu_lokr_grad(const float* G, int64_t ldg, const float* w1, const float* w2, int32_t out_l, int32_t out_k, int32_t in_m,
                   int32_t in_n, float multiplier, float* dw1, float* dw2, void* stream);

@@ -172,6 +172,99 @@ def test_training_step_loss_and_update_match_oracle(ttype, snr, deb):
     assert (num / den) ** 0.5 < 0.3
 
 
+def test_full_finetune_all_parameter_gradients_match_oracle():
+    """Full fine-tuning (lycoris_config = None, trainer.py:160-169): every UNet parameter gets a gradient — conv weights
+    through dW = dY^T im2col(X), biases, norms, the time / add embeddings through the per-resnet time projections."""
+    cfg, o, p, x, t, ctx, ac = build(seed=7)
+    o.requires_grad_(True)
+    p.requires_grad_(True)
+    gout = torch.randn(x.shape, generator=torch.Generator().manual_seed(2))
+    yo = o(x, t, encoder_hidden_states=ctx, added_cond_kwargs=ac)[0]
+    yo.backward(gout)
+    yp = p(x.cuda(), t.cuda(), **cuda_kwargs(ctx, ac))[0]
+    yp.backward(gout.cuda())
+    torch.cuda.synchronize()
+    assert rel(yp, yo) < 3e-2
+    po = dict(o.named_parameters())
+    missing = [n for n, q in p.named_parameters() if q.grad is None]
+    assert not missing, f"parameters without gradient: {missing[:5]}"
+    worst, worst_name = 0.0, ""
+    num = den = dot = 0.0
+    for n, q in p.named_parameters():
+        go, gp = po[n].grad.float(), q.grad.float().cpu()
+        assert gp.shape == go.shape, n
+        r = rel(gp, go)
+        if r > worst:
+            worst, worst_name = r, n
+        num += (gp * gp).sum().item()
+        den += (go * go).sum().item()
+        dot += (gp * go).sum().item()
+    assert worst < 1.5e-1, (worst, worst_name)
+    assert abs(num ** 0.5 - den ** 0.5) / den ** 0.5 < 2e-2
+    assert dot / (num ** 0.5 * den ** 0.5) > 0.995
+
+
+def test_c1_pixel_unet_full_training_step_matches_oracle():
+    """BASELINE.json configs[0]: tiny pixel-space UNet, batch 4 at 3x32x32, eps-prediction plain MSE, every weight trained.
+    Loss within 1e-2 of the fp32 oracle (bf16 compute), x_t / target bit-exact, gradient direction cos > 0.995."""
+    from uwudiff_b200 import unet as P
+    from uwudiff_b200.loss import DiffusionLoss
+    from uwudiff_b200.scheduler import EulerDiscreteScheduler
+
+    torch.manual_seed(11)
+    cfg = U.tiny_config(in_channels=3, out_channels=3, sample_size=32)
+    o = U.UNet2DConditionModel(**cfg)
+    p = P.UNet2DFromScratch.from_config(cfg)
+    p.load_state_dict(o.state_dict())
+    p = p.cuda()
+    o.requires_grad_(True)
+    p.requires_grad_(True)
+    B = 4
+    x0, eps = torch.randn(B, 3, 32, 32), torch.randn(B, 3, 32, 32)
+    t = torch.tensor([3, 250, 600, 999])
+    ctx = torch.randn(B, 77, cfg["cross_attention_dim"])
+    ac = dict(text_embeds=torch.randn(B, 64), time_ids=torch.tensor([[1024., 1024, 0, 0, 1024, 1024]] * B))
+    tab = loss_oracle.scheduler_tables(diffusers_shim.EulerDiscreteScheduler.from_pretrained("x"))
+    loss_o, aux_o = loss_oracle.diffusion_loss(x0, eps, t, o, tab, encoder_hidden_states=ctx, added_cond_kwargs=ac)
+    loss_o.backward()
+    sch = EulerDiscreteScheduler.from_pretrained("stabilityai/stable-diffusion-xl-base-1.0", subfolder="scheduler")
+    L = DiffusionLoss(sch)
+    L.temb_dim = cfg["block_out_channels"][0]
+    loss_p, aux_p = L(x0.cuda(), p, noise=eps.cuda(), timesteps=t.cuda(), **cuda_kwargs(ctx, ac))
+    loss_p.backward()
+    assert torch.equal(aux_p.noisy_latent.cpu(), aux_o["noisy_latent"]) and torch.equal(aux_p.target.cpu(), aux_o["target"])
+    assert abs(loss_p.item() - loss_o.item()) / abs(loss_o.item()) < 1e-2
+    po = dict(o.named_parameters())
+    gp = torch.cat([q.grad.flatten().cpu() for _, q in p.named_parameters()])
+    go = torch.cat([po[n].grad.flatten() for n, _ in p.named_parameters()])
+    assert torch.nn.functional.cosine_similarity(gp, go, dim=0).item() > 0.995
+    assert abs(gp.norm() - go.norm()).item() / go.norm().item() < 2e-2
+
+
+def test_full_finetune_fit_step():
+    from uwudiff_b200 import config as ucfg
+
+    cfg = U.tiny_config()
+    conf = {
+        "_target_": "duwu.trainer.DMTrainer", "_recursive_": False, "lr": 1e-4, "optimizer": "torch.optim.AdamW",
+        "opt_config": {"weight_decay": 0.01, "betas": [0.9, 0.999]}, "use_warm_up": False,
+        "model_config": {"unet": {"_target_": "duwu.modules.unet_patch.UNet2DFromScratch.from_config", "config": cfg},
+                         "te": {"_target_": "duwu.modules.text_encoders.ConcatTextEncoders", "hidden_dim": 128,
+                                "pooled_dim": 64, "_load_config_": {"to_freeze": True}},
+                         "vae": None},
+    }
+    tr = ucfg.instantiate_any(conf)
+    assert tr.lycoris_model is None
+    tr.setup_fit(gradient_clip_val=1.0, seed=1215)
+    B = 2
+    batch = (torch.randn(B, 4, 16, 16).cuda(), ["DUMMY TEST"] * B, [], {"time_ids": torch.tensor([[1024., 1024, 0, 0, 1024, 1024]] * B).cuda()}, {})
+    w0 = tr.unet.conv_in.weight.detach().clone()
+    losses = [tr.fit_step(batch, i)["loss"].item() for i in range(3)]
+    assert all(l == l and l > 0 for l in losses)
+    assert (tr.unet.conv_in.weight.detach() - w0).abs().max().item() > 0
+    assert (tr.unet.time_embedding.linear_1.weight.grad is not None)
+
+
 def test_dmtrainer_fit_step_runs_and_learns():
     """Public API: config -> DMTrainer -> fit_step; adapters move, loss is finite, no host-side fallbacks."""
     from uwudiff_b200 import config as ucfg

@@ -100,6 +100,9 @@ SIGNATURES = {
     "uwu_axpy_f32": (C.c_int, [_P, _P, _F, _I32, _P, _P]),
     "uwu_lokr_grad": (C.c_int, [_P, _I64, _P, _P, _I32, _I32, _I32, _I32, _F, _P, _P, _P]),
     "uwu_lora_grad": (C.c_int, [_P, _I64, _P, _P, _I32, _I32, _I32, _F, _P, _P, _P]),
+    "uwu_im2col3x3": (C.c_int, [_P, _I32, _I32, _I32, _I32, _I32, _P, _P]),
+    "uwu_conv_wgrad_unpack": (C.c_int, [_P, _I64, _I32, _I32, _I32, _I32, _I32, _P, _P]),
+    "uwu_colsum_groups_bf16": (C.c_int, [_P, _I64, _I32, _I32, _I32, _I32, _P, _P]),
     "uwu_fold_batch": (C.c_int, [_P, _P, _I32, _I32, _P]),
     "uwu_lokr_z": (C.c_int, [_P, _I64, _P, _I64, _I32, _I32, _I32, _P, _P]),
     "uwu_lokr_dw1": (C.c_int, [_P, _P, _I64, _I64, _I32, _I32, _I32, _F, _P, _P]),

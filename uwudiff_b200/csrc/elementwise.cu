@@ -206,6 +206,60 @@ __global__ void colsum_final_kernel(const float* __restrict__ partial, int P, in
     out[c] = accumulate ? out[c] + a : a;
 }
 
+// ------------------------------------------------------------------------------------------------
+// full fine-tuning support: convolution weight gradients as  dW = dY^T im2col(X)  (token-reduction GEMM)
+// ------------------------------------------------------------------------------------------------
+// cols[m, t*C + c] = x[n, ho*stride + dy_t - 1, wo*stride + dx_t - 1, c]  (0 outside the image), m = (n, ho, wo), t = 3*ky + kx
+__global__ void __launch_bounds__(256) im2col3x3_kernel(const __nv_bfloat16* __restrict__ x, int N, int H, int W, int C, int stride,
+                                                        int Ho, int Wo, __nv_bfloat16* __restrict__ cols) {
+    const int cv = C >> 3;
+    const long long total = (long long)N * Ho * Wo * 9 * cv;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int v = (int)(i % cv);
+        long long r = i / cv;
+        const int t = (int)(r % 9);
+        r /= 9;
+        const int wo = (int)(r % Wo);
+        r /= Wo;
+        const int ho = (int)(r % Ho);
+        const int n = (int)(r / Ho);
+        const int hi = ho * stride + t / 3 - 1, wi = wo * stride + t % 3 - 1;
+        uint4 u = make_uint4(0, 0, 0, 0);
+        if (hi >= 0 && hi < H && wi >= 0 && wi < W)
+            u = *reinterpret_cast<const uint4*>(x + (((size_t)n * H + hi) * W + wi) * C + v * 8);
+        *reinterpret_cast<uint4*>(cols + (((size_t)n * Ho + ho) * Wo + wo) * (size_t)(9 * C) + (size_t)t * C + v * 8) = u;
+    }
+}
+// wgrad[co, ci, ky, kx] (+)= G[co, (3*ky + kx) * Cp + ci]   (torch Conv2d weight layout <- packed GEMM layout), kk = kh*kw
+__global__ void conv_wgrad_unpack_kernel(const float* __restrict__ G, long long ldg, int Co, int Ci, int Cp, int kk, int accumulate,
+                                         float* __restrict__ wgrad) {
+    const long long total = (long long)Co * Ci * kk;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int t = (int)(i % kk);
+        long long r = i / kk;
+        const int ci = (int)(r % Ci);
+        const int co = (int)(r / Ci);
+        const float g = G[(size_t)co * ldg + (size_t)t * Cp + ci];
+        wgrad[i] = accumulate ? wgrad[i] + g : g;
+    }
+}
+// out[n, c] (+)= sum_{r < rows} x[n * rows + r, c]   (per-image column sums: time-embedding gradients), one block per (n, 64 columns)
+__global__ void __launch_bounds__(256) colsum_groups_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, int rows, int C,
+                                                            int accumulate, float* __restrict__ out) {
+    __shared__ float sh[4][64];
+    const int n = blockIdx.y, c = blockIdx.x * 64 + (threadIdx.x & 63), rr = threadIdx.x >> 6;
+    float a = 0.f;
+    if (c < C)
+        for (int r = rr; r < rows; r += 4) a += __bfloat162float(x[((size_t)n * rows + r) * ldx + c]);
+    sh[rr][threadIdx.x & 63] = a;
+    __syncthreads();
+    if (rr == 0 && c < C) {
+        const float s = (sh[0][threadIdx.x] + sh[1][threadIdx.x]) + (sh[2][threadIdx.x] + sh[3][threadIdx.x]);
+        float* o = out + (size_t)n * C + c;
+        *o = accumulate ? *o + s : s;
+    }
+}
+
 static int ew_grid(long long work, int threads) {
     long long b = (work + threads - 1) / threads;
     const long long cap = (long long)sm_count() * 16;
@@ -321,6 +375,34 @@ extern "C" int uwu_colsum_bf16(const void* x, int64_t M, int32_t C, int64_t ld, 
     colsum_bf16_kernel<<<grid, 128, 0, stream>>>(reinterpret_cast<const bf16*>(x), M, C, ld, 512, workspace);
     UWU_CHECK_LAUNCH();
     colsum_final_kernel<<<(C + 127) / 128, 128, 0, stream>>>(workspace, P, C, accumulate, out);
+    UWU_CHECK_LAUNCH();
+    return UWU_OK;
+}
+
+extern "C" int uwu_im2col3x3(const void* x, int32_t N, int32_t H, int32_t W, int32_t C, int32_t stride, void* cols, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    UWU_CHECK_ARG(x && cols && N > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0 && (stride == 1 || stride == 2),
+                  "uwu_im2col3x3: bad arguments (C %% 8 == 0, stride 1 or 2)");
+    const int Ho = (H + 2 - 3) / stride + 1, Wo = (W + 2 - 3) / stride + 1;
+    im2col3x3_kernel<<<ew_grid((long long)N * Ho * Wo * 9 * (C / 8), 256), 256, 0, stream>>>(
+        reinterpret_cast<const bf16*>(x), N, H, W, C, stride, Ho, Wo, reinterpret_cast<bf16*>(cols));
+    UWU_CHECK_LAUNCH();
+    return UWU_OK;
+}
+extern "C" int uwu_conv_wgrad_unpack(const float* G, int64_t ldg, int32_t Co, int32_t Ci, int32_t Ci_pad, int32_t taps,
+                                     int32_t accumulate, float* wgrad, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    UWU_CHECK_ARG(G && wgrad && Co > 0 && Ci > 0 && Ci_pad >= Ci && taps > 0 && ldg >= (int64_t)taps * Ci_pad,
+                  "uwu_conv_wgrad_unpack: bad arguments");
+    conv_wgrad_unpack_kernel<<<ew_grid((long long)Co * Ci * taps, 256), 256, 0, stream>>>(G, ldg, Co, Ci, Ci_pad, taps, accumulate, wgrad);
+    UWU_CHECK_LAUNCH();
+    return UWU_OK;
+}
+extern "C" int uwu_colsum_groups_bf16(const void* x, int64_t ldx, int32_t groups, int32_t rows, int32_t C, int32_t accumulate,
+                                      float* out, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    UWU_CHECK_ARG(x && out && groups > 0 && rows > 0 && C > 0 && ldx >= C, "uwu_colsum_groups_bf16: bad arguments");
+    colsum_groups_kernel<<<dim3((C + 63) / 64, groups), 256, 0, stream>>>(reinterpret_cast<const bf16*>(x), ldx, rows, C, accumulate, out);
     UWU_CHECK_LAUNCH();
     return UWU_OK;
 }

@@ -370,6 +370,36 @@ def colsum(x: torch.Tensor, out: Optional[torch.Tensor] = None, accumulate: bool
     return out
 
 
+def im2col3x3(x: torch.Tensor, N: int, H: int, W: int, C: int, stride: int = 1) -> torch.Tensor:
+    """x: [N*H*W, C] bf16 (NHWC) -> cols [N*Ho*Wo, 9*C] bf16, zero padded borders (pad 1)."""
+    _req_cuda(x)
+    assert x.dtype == torch.bfloat16 and x.is_contiguous()
+    Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
+    n = N * Ho * Wo * 9 * C
+    cols = _workspace((n + 1) // 2, x.device, "im2col").view(torch.bfloat16)[:n].view(N * Ho * Wo, 9 * C)
+    check(lib().uwu_im2col3x3(_ptr(x), N, H, W, C, stride, _ptr(cols), _stream()), "uwu_im2col3x3")
+    return cols
+
+
+def conv_wgrad_unpack(G: torch.Tensor, Co: int, Ci: int, Ci_pad: int, taps: int, wgrad: torch.Tensor, accumulate: bool = True):
+    _req_cuda(G, wgrad)
+    assert G.dtype == torch.float32 and wgrad.dtype == torch.float32 and wgrad.is_contiguous() and G.stride(1) == 1
+    check(lib().uwu_conv_wgrad_unpack(_ptr(G), G.stride(0), Co, Ci, Ci_pad, taps, int(accumulate), _ptr(wgrad), _stream()),
+          "uwu_conv_wgrad_unpack")
+
+
+def colsum_groups(x: torch.Tensor, groups: int, rows: int, out: Optional[torch.Tensor] = None, accumulate: bool = False):
+    """out[g, c] (+)= sum over the `rows` consecutive rows of group g of x[:, c]."""
+    _req_cuda(x, out)
+    C = x.shape[1]
+    if out is None:
+        out = torch.empty((groups, C), device=x.device, dtype=torch.float32)
+        accumulate = False
+    check(lib().uwu_colsum_groups_bf16(_ptr(x), x.stride(0), groups, rows, C, int(accumulate), _ptr(out), _stream()),
+          "uwu_colsum_groups_bf16")
+    return out
+
+
 # --------------------------------------------------------------------------------------------------
 # adapters / optimizer / copies
 # --------------------------------------------------------------------------------------------------

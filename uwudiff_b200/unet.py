@@ -202,11 +202,36 @@ class Conv2d(nn.Conv2d, _Cached):
                                 residual=residual)
 
     def dgrad3x3(self, dy, N, H, W, *, residual=None):
-        if self.weight.requires_grad:
-            raise NotImplementedError("uwudiff_b200: 3x3 convolution weight gradients are not built yet "
-                                      "(LyCORIS training keeps the convolutions frozen: enable_conv = false)")
         c = self._cache
         return ops.conv3x3_nhwc(dy.view(N, H, W, c.cod_p), c.dgrad, residual=residual)
+
+    def param_grads3x3(self, x_in, dy, N, H, W, stride: int = 1):
+        """Full fine-tuning: dW = dY^T im2col(X) as a token-reduction GEMM (+ bias = column sums of dY).
+        x_in: conv input [N*H*W, ci_p] bf16, dy: [N*Ho*Wo, >= Co] bf16."""
+        c = self._cache
+        Co, Ci = self.out_channels, self.in_channels
+        if self.weight.requires_grad:
+            cols = ops.im2col3x3(x_in, N, H, W, c.ci_p, stride)
+            M, K = cols.shape
+            G = ops._workspace(Co * K, dy.device, "wgrad")[: Co * K].view(Co, K)
+            ops.gemm(dy, cols, Co, K, M, a_layout=A_COL, lda=dy.stride(0), b_layout=B_KN, ldb=K, out=G)
+            ops.conv_wgrad_unpack(G, Co, Ci, c.ci_p, 9, _grad_of(self.weight))
+        if self.bias is not None and self.bias.requires_grad:
+            ops.colsum(dy[:, :Co], out=_grad_of(self.bias), accumulate=True)
+
+    def param_grads1x1(self, x_in, dy, M):
+        c = self._cache
+        Co, Ci = self.out_channels, self.in_channels
+        if self.weight.requires_grad:
+            G = ops._workspace(Co * c.ci_p, dy.device, "wgrad")[: Co * c.ci_p].view(Co, c.ci_p)
+            ops.gemm(dy, x_in, Co, c.ci_p, M, a_layout=A_COL, lda=dy.stride(0), b_layout=B_KN, ldb=x_in.stride(0), out=G)
+            ops.conv_wgrad_unpack(G, Co, Ci, c.ci_p, 1, _grad_of(self.weight))
+        if self.bias is not None and self.bias.requires_grad:
+            ops.colsum(dy[:, :Co], out=_grad_of(self.bias), accumulate=True)
+
+    @property
+    def trainable(self) -> bool:
+        return self.weight.requires_grad or (self.bias is not None and self.bias.requires_grad)
 
     # 1x1 convolution == Linear over channels
     def fwd1x1(self, x, M):
@@ -214,8 +239,6 @@ class Conv2d(nn.Conv2d, _Cached):
         return ops.gemm(x, c.fwd, M, c.co_p, c.ci_p, lda=x.stride(0), bias=c.bias)
 
     def dgrad1x1(self, dy, M, *, residual=None):
-        if self.weight.requires_grad:
-            raise NotImplementedError("uwudiff_b200: convolution weight gradients are not built yet")
         c = self._cache
         return ops.gemm(dy, c.fwd, M, c.ci_p, c.co_p, lda=dy.stride(0), b_layout=B_KN, ldb=c.ci_p, residual=residual)
 
@@ -327,19 +350,30 @@ class ResnetBlock2D(nn.Module):
         b, s2 = self.norm2.fwd(h1, N, H * W, True)
         res = x if self.conv_shortcut is None else self.conv_shortcut.fwd1x1(x, N * H * W)
         out = self.conv2.fwd3x3(b, N, H, W, residual=res)
-        self._sv = (x, s1, h1, s2, (N, H, W))
+        # full fine-tuning keeps the normalised activations: they are the inputs of the conv weight gradients
+        keep = (a if self.conv1.trainable else None, b if self.conv2.trainable else None)
+        self._sv = (x, s1, h1, s2, (N, H, W), keep)
         return out
 
     def bwd(self, dout, st):
-        x, s1, h1, s2, (N, H, W) = self._sv
+        x, s1, h1, s2, (N, H, W), (a, b) = self._sv
         self._sv = None
         dout = _contig(dout)
+        if b is not None:
+            self.conv2.param_grads3x3(b, dout, N, H, W)
         db = self.conv2.dgrad3x3(dout, N, H, W)
         dh1 = self.norm2.bwd(h1, db, s2, N, H * W, True)
         if st.need_temb_grad:
             st.add_temb_grad(self.time_emb_proj, dh1, N, H * W)
+        if a is not None:
+            self.conv1.param_grads3x3(a, dh1, N, H, W)
         da = self.conv1.dgrad3x3(dh1, N, H, W)
-        dres = dout if self.conv_shortcut is None else self.conv_shortcut.dgrad1x1(dout, N * H * W)
+        if self.conv_shortcut is None:
+            dres = dout
+        else:
+            if self.conv_shortcut.trainable:
+                self.conv_shortcut.param_grads1x1(x, dout, N * H * W)
+            dres = self.conv_shortcut.dgrad1x1(dout, N * H * W)
         return self.norm1.bwd(x, da, s1, N, H * W, True, dres=dres)
 
 
@@ -536,18 +570,19 @@ class Downsample2D(nn.Module):
         c = self.conv._pack()
         planes = ops.phase_split2(x, N, H, W, C).view(4 * N, H // 2, W // 2, C)
         taps = [(p * N, dh, dw) for (p, dh, dw) in self._TAPS]
-        self._sv = (N, H, W)
+        self._sv = (N, H, W, x if self.conv.trainable else None)
         return ops.conv3x3_nhwc(planes, c.fwd, taps=taps, n_out_img=N, bias=c.bias)
 
     def bwd(self, dy, st):
-        N, H, W = self._sv
+        N, H, W, x_in = self._sv
         self._sv = None
-        if self.conv.weight.requires_grad:
-            raise NotImplementedError("uwudiff_b200: convolution weight gradients are not built yet")
         C = self.conv.in_channels
         c = self.conv._cache
         H2, W2 = H // 2, W // 2
-        dyv = _contig(dy).view(N, H2, W2, c.cod_p)
+        dy = _contig(dy)
+        if x_in is not None:
+            self.conv.param_grads3x3(x_in, dy, N, H, W, stride=2)
+        dyv = dy.view(N, H2, W2, c.cod_p)
         dplanes = torch.empty((4 * N * H2 * W2, C), device=dy.device, dtype=BF16)
         for p, (taps, wp) in enumerate(c.dgrad_phase):
             ops.conv3x3_nhwc(dyv, wp, taps=taps, out=dplanes[p * N * H2 * W2:(p + 1) * N * H2 * W2])
@@ -562,13 +597,16 @@ class Upsample2D(nn.Module):
     def fwd(self, x, st):
         N, H, W, C = st.N, st.H, st.W, self.conv.in_channels
         up = ops.upsample2x(x, N, H, W, C)
-        self._sv = (N, H, W)
+        self._sv = (N, H, W, up if self.conv.trainable else None)
         return self.conv.fwd3x3(up, N, 2 * H, 2 * W)
 
     def bwd(self, dy, st):
-        N, H, W = self._sv
+        N, H, W, up = self._sv
         self._sv = None
-        dup = self.conv.dgrad3x3(_contig(dy), N, 2 * H, 2 * W)
+        dy = _contig(dy)
+        if up is not None:
+            self.conv.param_grads3x3(up, dy, N, 2 * H, 2 * W)
+        dup = self.conv.dgrad3x3(dy, N, 2 * H, 2 * W)
         return ops.upsample2x(dup, N, H, W, self.conv.in_channels, backward=True)
 
 
@@ -617,14 +655,23 @@ class _State:
         self.ctx = None
         self.ctx_len = 0
         self.need_temb_grad = False
-        self.temb_grads = []
+        self.dsemb = None  # fp32 [N, temb]: gradient w.r.t. silu(emb), accumulated over every resnet
 
     @property
     def M(self):
         return self.N * self.H * self.W
 
     def add_temb_grad(self, lin, dh1, N, HW):
-        raise NotImplementedError("uwudiff_b200: time-embedding gradients (full fine-tuning) are not built yet")
+        """Gradient of a resnet's time-embedding projection: d(tproj)[n, c] = sum over the image of dh1, then through
+        `time_emb_proj` (parameter gradients + d(silu(emb)) accumulated in fp32 over all resnets)."""
+        dt32 = ops.colsum_groups(dh1, N, HW)                      # [N, Cout] fp32
+        dt = torch.empty((N, dt32.shape[1]), device=dh1.device, dtype=BF16)
+        ops.copy2d(dt32, dt)
+        lin.param_grads(dt, self.semb, N)
+        if self.dsemb is None:
+            self.dsemb = torch.zeros((N, lin.in_features), device=dh1.device, dtype=torch.float32)
+        ops.gemm(dt, lin._cache, N, lin.in_features, lin.out_features, b_layout=B_KN, ldb=lin.in_features, out=self.dsemb,
+                 accumulate=True, stream_k=0)
 
 
 class _UNetFunction(torch.autograd.Function):
@@ -773,7 +820,8 @@ class UNet2DConditionModel(nn.Module):
             ly.fold_all()  # every adapter delta folded into its bf16 operand (or norm affine) in one launch
         st = _State()
         st.N, st.H, st.W = B, H, W
-        st.need_temb_grad = any(p.requires_grad for p in self.time_embedding.parameters())
+        st.need_temb_grad = any(p.requires_grad for p in self.time_embedding.parameters()) or any(
+            p.requires_grad for blk in self.down_blocks for p in blk.resnets[0].time_emb_proj.parameters())
         # --- conditioning ---
         if fused_temb is not None:
             temb = fused_temb
@@ -791,12 +839,14 @@ class UNet2DConditionModel(nn.Module):
             ops.copy2d(te, add_in[:, text_embeds.shape[1]:])
             emb = self.add_embedding.fwd(add_in, B, residual=emb)
         st.semb = ops.elementwise(emb, None, ops.EW_SILU)
+        st.emb = emb
         if ehs is not None:
             st.ctx_len = ehs.shape[1]
             ctx2d = ehs.reshape(B * ehs.shape[1], ehs.shape[2])
             st.ctx = ops.copy2d(ctx2d, torch.empty(ctx2d.shape, device=dev, dtype=BF16))
         # --- trunk ---
         x = ops.nchw_to_nhwc(sample, _pad_to(Cin, 64))
+        x_in0 = x if self.conv_in.trainable else None
         x = self.conv_in.fwd3x3(x, B, H, W)
         skips: List[torch.Tensor] = [x]
         geo = []
@@ -831,14 +881,14 @@ class UNet2DConditionModel(nn.Module):
         y, s_out = self.conv_norm_out.fwd(x, B, H * W, True)
         o = self.conv_out.fwd3x3(y, B, H, W)
         out = ops.nhwc_to_nchw(o, B, c.out_channels, H, W)
-        self._fsv = (st, x, s_out, cat_shapes, (B, H, W))
+        self._fsv = (st, x, s_out, cat_shapes, (B, H, W), x_in0, y if self.conv_out.trainable else None)
         return out
 
     # ---------------------------------------------------------------------------------------------
     # backward
     # ---------------------------------------------------------------------------------------------
     def _backward_impl(self, gout):
-        st, x_last, s_out, cat_shapes, (B, H, W) = self._fsv
+        st, x_last, s_out, cat_shapes, (B, H, W), x_in0, y_last = self._fsv
         self._fsv = None
         ly = getattr(self, "_uwu_lycoris", None)
         if ly is not None:
@@ -846,6 +896,8 @@ class UNet2DConditionModel(nn.Module):
         done = self.after_backward or (lambda mods: None)
         st.H, st.W = H, W
         dy = ops.nchw_to_nhwc(gout, self.conv_out._cache.cod_p)
+        if y_last is not None:
+            self.conv_out.param_grads3x3(y_last, dy, B, H, W)
         dyn = self.conv_out.dgrad3x3(dy, B, H, W)
         dx = self.conv_norm_out.bwd(x_last, dyn, s_out, B, H * W, True)
         done([self.conv_norm_out, self.conv_out])
@@ -882,9 +934,17 @@ class UNet2DConditionModel(nn.Module):
                     dx = blk.attentions[i].bwd(dx, st)
                 dx = blk.resnets[i].bwd(dx, st)
             done([blk])
-        # conv_in / embeddings: frozen under LyCORIS (no gradient flows to x_t); full fine-tune needs conv wgrad
-        if self.conv_in.weight.requires_grad:
-            raise NotImplementedError("uwudiff_b200: convolution weight gradients are not built yet")
+        # conv_in / embeddings: frozen under LyCORIS (no gradient flows to x_t); trained in full fine-tuning
+        if x_in0 is not None:
+            dx = ops.elementwise(_contig(dx), take(), ops.EW_ADD)  # + gradient of the first skip connection
+            self.conv_in.param_grads3x3(x_in0, dx, B, H, W)
+        if st.need_temb_grad and st.dsemb is not None:
+            ds = torch.empty(st.dsemb.shape, device=st.dsemb.device, dtype=BF16)
+            ops.copy2d(st.dsemb, ds)
+            demb = ops.elementwise(ds, st.emb, ops.EW_SILU_BWD)
+            if self.add_embedding is not None:
+                self.add_embedding.bwd(demb, B)
+            self.time_embedding.bwd(demb, B)
         done([self.conv_in, self.time_embedding] + ([self.add_embedding] if self.add_embedding is not None else []))
         self._drop_saved()
 
