@@ -117,58 +117,61 @@ __global__ void axpy_f32_kernel(const float* __restrict__ a, const float* __rest
 // ------------------------------------------------------------------------------------------------
 // adapter gradients from G [N, K] fp32 (ldg)
 // ------------------------------------------------------------------------------------------------
-// dw1[l,i] += mult * sum_{k,n} G[l*ok+k, i*in+n] w2[k,n]
-// grid (ol*im, row_splits): block (b, s) reduces rows [s*rows_per, ...) of the [ok x in] tile of G against w2.
+// dw1[l,i] += mult * sum_{k,n} G[l*ok+k, i*in+n] w2[k,n]  and  dw2[k,n] += mult * sum_{l,i} G[l*ok+k, i*in+n] w1[l,i]
+// in ONE launch (the per-layer contractions are latency bound, so two launches cost twice):
+//   blocks [0, n1): (tile = (l, i), split s) reduce rows [s*rows_per, ...) of the [ok x in] tile of G against w2 -> dw1
+//   blocks [n1, ..): one thread per (k, VW consecutive n), looping over its slice of l and all i            -> dw2
 // VEC: in_n % 4 == 0 and 16-byte aligned rows -> float4 loads.
 template <bool VEC>
-__global__ void __launch_bounds__(256) lokr_dw1_kernel(const float* __restrict__ G, long long ldg, const float* __restrict__ w2,
-                                                       int ok, int in_n, int im, int rows_per, float mult,
-                                                       float* __restrict__ dw1) {
-    const int l = blockIdx.x / im, i = blockIdx.x - l * im;
-    const int k0 = blockIdx.y * rows_per;
-    const int k1 = min(ok, k0 + rows_per);
-    const float* g = G + (size_t)l * ok * ldg + (size_t)i * in_n;
-    float acc = 0.f;
-    if (VEC) {
-        const int nv = in_n >> 2;
-        const int total = (k1 - k0) * nv;
-        for (int e = threadIdx.x; e < total; e += blockDim.x) {
-            const int k = k0 + e / nv, n = (e - (e / nv) * nv) << 2;
-            const float4 a = *reinterpret_cast<const float4*>(g + (size_t)k * ldg + n);
-            const float4 b = *reinterpret_cast<const float4*>(w2 + (size_t)k * in_n + n);
-            acc = fmaf(a.x, b.x, acc); acc = fmaf(a.y, b.y, acc); acc = fmaf(a.z, b.z, acc); acc = fmaf(a.w, b.w, acc);
+__global__ void __launch_bounds__(256) lokr_grad_kernel(const float* __restrict__ G, long long ldg, const float* __restrict__ w1,
+                                                        const float* __restrict__ w2, int ol, int ok, int im, int in_n, int rows_per,
+                                                        int splits, int l_per, int lsplits, int blocks2, int n1, float mult,
+                                                        float* __restrict__ dw1, float* __restrict__ dw2) {
+    if ((int)blockIdx.x < n1) {
+        const int tile = blockIdx.x / splits, sp = blockIdx.x - tile * splits;
+        const int l = tile / im, i = tile - l * im;
+        const int k0 = sp * rows_per;
+        const int k1 = min(ok, k0 + rows_per);
+        const float* g = G + (size_t)l * ok * ldg + (size_t)i * in_n;
+        float acc = 0.f;
+        if (VEC) {
+            const int nv = in_n >> 2;
+            const int total = (k1 - k0) * nv;
+            for (int e = threadIdx.x; e < total; e += blockDim.x) {
+                const int k = k0 + e / nv, n = (e - (e / nv) * nv) << 2;
+                const float4 a = *reinterpret_cast<const float4*>(g + (size_t)k * ldg + n);
+                const float4 b = *reinterpret_cast<const float4*>(w2 + (size_t)k * in_n + n);
+                acc = fmaf(a.x, b.x, acc); acc = fmaf(a.y, b.y, acc); acc = fmaf(a.z, b.z, acc); acc = fmaf(a.w, b.w, acc);
+            }
+        } else {
+            const int total = (k1 - k0) * in_n;
+            for (int e = threadIdx.x; e < total; e += blockDim.x) {
+                const int k = k0 + e / in_n, n = e - (e / in_n) * in_n;
+                acc = fmaf(g[(size_t)k * ldg + n], w2[(size_t)k * in_n + n], acc);
+            }
         }
-    } else {
-        const int total = (k1 - k0) * in_n;
-        for (int e = threadIdx.x; e < total; e += blockDim.x) {
-            const int k = k0 + e / in_n, n = e - (e / in_n) * in_n;
-            acc = fmaf(g[(size_t)k * ldg + n], w2[(size_t)k * in_n + n], acc);
+        __shared__ float red[8];
+        acc = warp_sum(acc);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float s = 0.f;
+            for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[w];
+            if (splits > 1)
+                atomicAdd(&dw1[tile], s * mult);
+            else
+                dw1[tile] += s * mult;
         }
+        return;
     }
-    __shared__ float red[8];
-    acc = warp_sum(acc);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        float s = 0.f;
-        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[w];
-        if (gridDim.y > 1)
-            atomicAdd(&dw1[blockIdx.x], s * mult);
-        else
-            dw1[blockIdx.x] += s * mult;
-    }
-}
-// dw2[k,n] += mult * sum_{l,i} G[l*ok+k, i*in+n] w1[l,i]
-// grid (ceil(ok*in/VW/128), l_splits): one thread per (k, VW consecutive n), looping over its slice of l and all i.
-template <int VW>
-__global__ void __launch_bounds__(128) lokr_dw2_kernel(const float* __restrict__ G, long long ldg, const float* __restrict__ w1,
-                                                       int ol, int ok, int im, int in_n, int l_per, float mult,
-                                                       float* __restrict__ dw2) {
+    constexpr int VW = VEC ? 4 : 1;
+    const int b2 = blockIdx.x - n1;
+    const int bx = b2 % blocks2, by = b2 / blocks2;
     const int nv = in_n / VW;
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    const int e = bx * blockDim.x + threadIdx.x;
     if (e >= ok * nv) return;
     const int k = e / nv, n = (e - k * nv) * VW;
-    const int l0 = blockIdx.y * l_per, l1 = min(ol, l0 + l_per);
+    const int l0 = by * l_per, l1 = min(ol, l0 + l_per);
     float acc[VW];
 #pragma unroll
     for (int j = 0; j < VW; ++j) acc[j] = 0.f;
@@ -187,7 +190,7 @@ __global__ void __launch_bounds__(128) lokr_dw2_kernel(const float* __restrict__
         }
     }
     float* o = dw2 + (size_t)k * in_n + n;
-    if (gridDim.y > 1) {
+    if (lsplits > 1) {
 #pragma unroll
         for (int j = 0; j < VW; ++j) atomicAdd(o + j, acc[j] * mult);
     } else {
@@ -195,6 +198,7 @@ __global__ void __launch_bounds__(128) lokr_dw2_kernel(const float* __restrict__
         for (int j = 0; j < VW; ++j) o[j] += acc[j] * mult;
     }
 }
+
 // ------------------------------------------------------------------------------------------------
 // factored LoKr gradients (no G = dY^T X): with X [M, im, in], dY [M, ol, ok], w1 [ol, im], w2 [ok, in]
 //   Z[m, l, n] = sum_i w1[l, i] X[m, i, n]            (lokr_z_kernel, bandwidth / FMA bound)
@@ -501,36 +505,30 @@ extern "C" int uwu_lokr_grad(const float* G, int64_t ldg, const float* w1, const
     const bool vec = in_n % 4 == 0 && ldg % 4 == 0 && (reinterpret_cast<uintptr_t>(G) & 15) == 0 &&
                      (reinterpret_cast<uintptr_t>(w2) & 15) == 0;
     const int target = 4 * sm_count();
-    {
-        // enough blocks to fill the machine: split each (l, i) tile over row ranges (>= 8 rows each)
-        const int tiles = out_l * in_m;
-        int splits = (target + tiles - 1) / tiles;
-        if (splits > (out_k + 7) / 8) splits = (out_k + 7) / 8;
-        if (splits < 1) splits = 1;
-        const int rows_per = (out_k + splits - 1) / splits;
-        splits = (out_k + rows_per - 1) / rows_per;
-        dim3 grid(tiles, splits);
-        if (vec)
-            lokr_dw1_kernel<true><<<grid, 256, 0, stream>>>(G, ldg, w2, out_k, in_n, in_m, rows_per, multiplier, dw1);
-        else
-            lokr_dw1_kernel<false><<<grid, 256, 0, stream>>>(G, ldg, w2, out_k, in_n, in_m, rows_per, multiplier, dw1);
-        UWU_CHECK_LAUNCH();
-    }
-    {
-        const int vw = vec ? 4 : 1;
-        const int blocks = (out_k * (in_n / vw) + 127) / 128;
-        int lsplits = (target + blocks - 1) / blocks;
-        if (lsplits > out_l) lsplits = out_l;
-        if (lsplits < 1) lsplits = 1;
-        const int l_per = (out_l + lsplits - 1) / lsplits;
-        lsplits = (out_l + l_per - 1) / l_per;
-        dim3 grid(blocks, lsplits);
-        if (vec)
-            lokr_dw2_kernel<4><<<grid, 128, 0, stream>>>(G, ldg, w1, out_l, out_k, in_m, in_n, l_per, multiplier, dw2);
-        else
-            lokr_dw2_kernel<1><<<grid, 128, 0, stream>>>(G, ldg, w1, out_l, out_k, in_m, in_n, l_per, multiplier, dw2);
-        UWU_CHECK_LAUNCH();
-    }
+    // dw1: split each (l, i) tile over row ranges (>= 8 rows each) so the grid fills the machine
+    const int tiles = out_l * in_m;
+    int splits = (target + tiles - 1) / tiles;
+    if (splits > (out_k + 7) / 8) splits = (out_k + 7) / 8;
+    if (splits < 1) splits = 1;
+    const int rows_per = (out_k + splits - 1) / splits;
+    splits = (out_k + rows_per - 1) / rows_per;
+    // dw2: one thread per (k, 4 n), l range split over blocks
+    const int vw = vec ? 4 : 1;
+    const int blocks2 = (out_k * (in_n / vw) + 255) / 256;
+    int lsplits = (target + blocks2 - 1) / blocks2;
+    if (lsplits > out_l) lsplits = out_l;
+    if (lsplits < 1) lsplits = 1;
+    const int l_per = (out_l + lsplits - 1) / lsplits;
+    lsplits = (out_l + l_per - 1) / l_per;
+    // ONE launch: blocks [0, tiles*splits) do dw1, the rest dw2
+    const int n1 = tiles * splits, n2 = blocks2 * lsplits;
+    if (vec)
+        lokr_grad_kernel<true><<<n1 + n2, 256, 0, stream>>>(G, ldg, w1, w2, out_l, out_k, in_m, in_n, rows_per, splits, l_per, lsplits,
+                                                           blocks2, n1, multiplier, dw1, dw2);
+    else
+        lokr_grad_kernel<false><<<n1 + n2, 256, 0, stream>>>(G, ldg, w1, w2, out_l, out_k, in_m, in_n, rows_per, splits, l_per, lsplits,
+                                                            blocks2, n1, multiplier, dw1, dw2);
+    UWU_CHECK_LAUNCH();
     return UWU_OK;
 }
 
