@@ -135,6 +135,29 @@ def case_lin():
         tf(f"torch.matmul M{M} N{N} K{K}", timeit(lambda: torch.matmul(a, b.t())), 2.0 * M * N * K)
 
 
+def case_dgrad():
+    """dx = dy W with W [out, in] read MN-major (B_KN): the data-gradient GEMMs of the Linear layers."""
+    for (M, N, K) in [(16384, 1280, 10240), (16384, 5120, 1280), (16384, 1280, 1280), (16384, 1280, 3840), (65536, 640, 640)]:
+        dy, w = mk(M, K), mk(K, N)
+        out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+        tf(f"dgrad M{M} N{N} K{K} (B_KN)", timeit(lambda: ops.gemm(dy, w, M, N, K, b_layout=B_KN, ldb=N, out=out)), 2.0 * M * N * K)
+        wt = mk(N, K)
+        tf(f"same shape, K-major B", timeit(lambda: ops.gemm(dy, wt, M, N, K, out=out)), 2.0 * M * N * K)
+
+
+def case_bn640():
+    for (M, N, K) in [(65536, 640, 640), (65536, 640, 2560), (65536, 1920, 640), (262144, 320, 2880)]:
+        a, b, bt = mk(M, K), mk(N, K), mk(K, N)
+        out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+        res = mk(M, N)
+        for bn in (128, 160, 192, 256, 320 if False else 64):
+            if bn > N and bn != 256:
+                continue
+            tf(f"M{M} N{N} K{K} bn{bn} K-major B", timeit(lambda: ops.gemm(a, b, M, N, K, out=out, block_n=bn)), 2.0 * M * N * K)
+            tf(f"M{M} N{N} K{K} bn{bn} K-major B +res", timeit(lambda: ops.gemm(a, b, M, N, K, out=out, block_n=bn, residual=res)), 2.0 * M * N * K)
+            tf(f"M{M} N{N} K{K} bn{bn} B_KN", timeit(lambda: ops.gemm(a, bt, M, N, K, b_layout=B_KN, ldb=N, out=out, block_n=bn)), 2.0 * M * N * K)
+
+
 def case_lin_cold():
     """Same GEMMs with L2 flushed (a 512 MB copy) before every timed launch: the in-step condition for weights."""
     big = torch.empty(256 << 20, device=dev, dtype=torch.uint8)

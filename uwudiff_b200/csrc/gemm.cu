@@ -67,6 +67,7 @@ struct GemmKernelArgs {
     // grouped N (a_mode 0): output columns [g * grp_n, (g+1) * grp_n) use A columns starting at g * a_grp_koff and the
     // SAME B ([K, grp_n]) for every group
     int grp_n, a_grp_koff;
+    int b_3d;  // MN-major B through a 3-D tensor map {64 n, K, N/64}: ONE TMA instruction per stage instead of block_n/64
     int stream_k;  // 1: the (tile, k-block) space is cut into equal contiguous ranges, one per CTA; partial tiles are
                    //    reduced with vector atomics into the fp32 output (which the host zeroed unless accumulating)
 };
@@ -212,8 +213,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
                         tma_load_2d(sb, &p.tmB, &full_bar[stage], kb * BLOCK_K, n0);
                     } else {
                         const int bn0 = n0 - grp * p.grp_n + kseg * p.b_seg_off;
-                        for (int j = 0; j * 64 < p.block_n; ++j)
-                            tma_load_2d(sb + j * 8192, &p.tmB, &full_bar[stage], bn0 + j * 64, kbs * BLOCK_K);
+                        if (p.b_3d) {
+                            tma_load_3d(sb, &p.tmB, &full_bar[stage], 0, kbs * BLOCK_K, bn0 >> 6);
+                        } else {
+                            for (int j = 0; j * 64 < p.block_n; ++j)
+                                tma_load_2d(sb + j * 8192, &p.tmB, &full_bar[stage], bn0 + j * 64, kbs * BLOCK_K);
+                        }
                     }
                     if (++stage == p.stages) {
                         stage = 0;
@@ -575,6 +580,10 @@ static int pick_block_n(long long N) {
     if (N <= 64) return 64;
     if (N <= 128) return 128;
     if (N % 256 == 0) return 256;
+    // measured (profiles/r01_gemm_block_n_sweep.log): from N = 512 up, 256-wide tiles with a partial last tile beat the
+    // exact divisors 160 / 192 (N = 640: 915 vs 586 TFLOP/s, N = 1920: 1110 vs 832), which also need per-chunk loads for
+    // MN-major B and a direct-store tail in the epilogue
+    if (N >= 512) return 256;
     if (N % 160 == 0) return 160;
     if (N % 128 == 0) return 128;
     if (N % 192 == 0) return 192;
@@ -608,7 +617,7 @@ extern "C" int uwu_gemm(const uwu_gemm_desc* d, void* stream_) {
     p.num_n_tiles = (p.N + bn - 1) / bn;
     p.a_mode = d->a_layout;
     p.b_mode = d->b_layout;
-    p.kb_per_seg = 0; p.a_seg_off = 0; p.b_seg_off = 0;
+    p.kb_per_seg = 0; p.a_seg_off = 0; p.b_seg_off = 0; p.b_3d = 0;
     p.grp_n = 0; p.a_grp_koff = 0;
     if (d->grp_n > 0) {
         UWU_CHECK_ARG(d->a_layout == UWU_A_ROW && d->b_layout == UWU_B_KN, "uwu_gemm: grp_n needs the A_ROW x B_KN form");
@@ -715,10 +724,19 @@ extern "C" int uwu_gemm(const uwu_gemm_desc* d, void* stream_) {
         const int segs = (d->a_layout == UWU_A_COL && d->k_segs > 1) ? d->k_segs : 1;
         uint64_t bw = d->grp_n > 0 ? (uint64_t)d->grp_n : (uint64_t)d->N + (uint64_t)(segs - 1) * (uint64_t)d->b_seg_off;
         UWU_CHECK_ARG((int64_t)bw <= d->ldb, "uwu_gemm: segmented / grouped B columns exceed ldb");
-        uint64_t dims[2] = {bw, (uint64_t)d->K};
-        uint64_t str[1] = {(uint64_t)d->ldb * 2};
-        uint32_t box[2] = {64, BLOCK_K};
-        if (encode_tmap_bf16(&p.tmB, d->b, 2, dims, str, box, 1)) return UWU_ERR_INVALID;
+        p.b_3d = 0;
+        if (segs == 1 && d->grp_n == 0 && d->N % 64 == 0 && bn % 64 == 0) {
+            uint64_t dims[3] = {64, (uint64_t)d->K, (uint64_t)(d->N / 64)};
+            uint64_t str[2] = {(uint64_t)d->ldb * 2, 128};
+            uint32_t box[3] = {64, BLOCK_K, (uint32_t)(bn / 64)};
+            if (encode_tmap_bf16(&p.tmB, d->b, 3, dims, str, box, 1)) return UWU_ERR_INVALID;
+            p.b_3d = 1;
+        } else {
+            uint64_t dims[2] = {bw, (uint64_t)d->K};
+            uint64_t str[1] = {(uint64_t)d->ldb * 2};
+            uint32_t box[2] = {64, BLOCK_K};
+            if (encode_tmap_bf16(&p.tmB, d->b, 2, dims, str, box, 1)) return UWU_ERR_INVALID;
+        }
         p.b_stage_bytes = ((bn + 63) / 64) * 8192;
         p.b_lbo = 8192; p.b_sbo = 1024; p.b_kadv = 2048;
     }
