@@ -18,6 +18,7 @@
 //
 // Replaces F.scaled_dot_product_attention under diffusers' AttnProcessor2_0 (the in-tree copy of that flow is
 // src/duwu/modules/rope_unet.py:76-175; SDPA call at :151) for attn1 (self) and attn2 (cross, Lk = 77).
+#include <cstdlib>
 #include "api_internal.h"
 #include "common.cuh"
 
@@ -314,8 +315,32 @@ __global__ void attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ o, long l
     lse2[oi] = lse[oi] * LOG2E;
 }
 
+// dq[b*Lq+q, 64h+d] = scale * acc[b,h,q/128, d/4, q%128, d%4]   (single-pass backward: fp32 dQ scratch -> bf16)
+__global__ void attn_bwd_dq_convert_kernel(const float* __restrict__ acc, int B, int heads, int Lq, int nqt, float scale,
+                                           __nv_bfloat16* __restrict__ dq, long long lddq) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // one 8-wide d chunk per thread
+    const long long total = (long long)B * Lq * heads * 8;
+    if (idx >= total) return;
+    const int c8 = (int)(idx & 7);
+    long long r = idx >> 3;
+    const int h = (int)(r % heads);
+    r /= heads;
+    const int q = (int)(r % Lq);
+    const int b = (int)(r / Lq);
+    const size_t tile = (((size_t)b * heads + h) * nqt + (q >> 7)) * (16 * 128 * 4);
+    const float4 f0 = *reinterpret_cast<const float4*>(acc + tile + ((size_t)(2 * c8) * 128 + (q & 127)) * 4);
+    const float4 f1 = *reinterpret_cast<const float4*>(acc + tile + ((size_t)(2 * c8 + 1) * 128 + (q & 127)) * 4);
+    uint4 u;
+    u.x = pack_bf16(f0.x * scale, f0.y * scale);
+    u.y = pack_bf16(f0.z * scale, f0.w * scale);
+    u.z = pack_bf16(f1.x * scale, f1.y * scale);
+    u.w = pack_bf16(f1.z * scale, f1.w * scale);
+    *reinterpret_cast<uint4*>(dq + ((size_t)b * Lq + q) * lddq + h * 64 + c8 * 8) = u;
+}
+
 struct AttnBwdArgs {
     CUtensorMap tmQ, tmK, tmV, tmdO;
+    float* dq_acc;  // single-pass mode: fp32 [B, heads, Lq_pad/128, 16, 128, 4]
     int Lq, Lk, heads, Lq_pad;
     float scale, scale_log2;
     const float* lse2;   // [B, heads, Lq_pad]
@@ -333,8 +358,10 @@ static constexpr int BWD_SR0 = 0;            // resident 0: K (dK/dV pass) or Q 
 static constexpr int BWD_SR1 = AT_TILE;      // resident 1: V              or dO
 static constexpr int BWD_SDS = 2 * AT_TILE;  // dS [128 queries x 128 keys] bf16, two [128 x 64] K-major tiles
 static constexpr int BWD_SP = 4 * AT_TILE;   // P, same layout (dK/dV pass only)
-template <bool kDQ>
+// kMode 0: dK/dV pass, 1: dQ pass, 2: single pass (dK, dV and dQ partials reduced into an fp32 scratch with vector atomics)
+template <int kMode>
 struct BwdCfg {
+    static constexpr bool kDQ = kMode == 1;
     static constexpr int kStages = kDQ ? 4 : 3;
     static constexpr int SS0 = (kDQ ? 4 : 6) * AT_TILE;  // streamed 0: Q (dK/dV pass) or K (dQ pass)
     static constexpr int SS1 = SS0 + kStages * AT_TILE;   // streamed 1: dO             or V
@@ -353,9 +380,11 @@ static constexpr int BWD_THREADS = 64 + 512;  // TMA warp, MMA warp, 16 compute 
 // (7 instead of 5 tile products per pair): the single-pass version was bound by the streamed-operand latency and the
 // per-iteration handshakes, not by the tensor pipe (profiles/r01_attn_bwd_ncu.md).  The MMA warp issues S / dP of
 // iteration i+1 before the accumulating products of iteration i, so the exp / dS math overlaps the tensor pipe.
-template <bool kDQ>
+template <int kMode>
 __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_kernel(const __grid_constant__ AttnBwdArgs p) {
-    using Cfg = BwdCfg<kDQ>;
+    using Cfg = BwdCfg<kMode>;
+    constexpr bool kDQ = kMode == 1;
+    constexpr bool kFused = kMode == 2;
     constexpr int kStages = Cfg::kStages;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = align1024(smem_raw);
@@ -368,7 +397,9 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_kernel(const __grid_c
     uint64_t* pds_full = bars + 11;
     uint64_t* pds_empty = bars + 12;
     uint64_t* acc_full = bars + 13;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+    uint64_t* dq_full = bars + 14;
+    uint64_t* dq_empty = bars + 15;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int r0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;  // first resident row (key or query)
@@ -392,6 +423,8 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_kernel(const __grid_c
         mbar_init(pds_full, 16);
         mbar_init(pds_empty, 1);
         mbar_init(acc_full, 1);
+        mbar_init(dq_full, 1);
+        mbar_init(dq_empty, 16);
         fence_barrier_init();
     }
     if (warp == 2) {
@@ -481,10 +514,24 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_kernel(const __grid_c
                         for (int k = 0; k < 8; ++k)
                             umma_bf16(tmem_base + 320u, ads + (uint64_t)(k * 128), b0 + (uint64_t)(k * 128), idesc_acc,
                                       (uint32_t)((i | k) != 0));
+                        if (kFused) {
+                            // dQ_i[q, d] = sum_key dS[q, key] K[key, d]: A = dS K-major, B = the resident K tile MN-major;
+                            // a fresh 64-column accumulator per query tile, drained by the compute warps one iteration later
+                            mbar_wait(dq_empty, (uint32_t)((i & 1) ^ 1));
+                            tc_fence_after();
+                            const uint32_t idesc_dq = make_idesc_bf16(128, 64, 0, 1);
+                            const uint64_t kb = desc_mnmajor(sr0, 8192);
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) {
+                                const uint64_t ad = desc_kmajor(sds + (k >> 2) * AT_TILE) + (uint64_t)((k & 3) * 2);
+                                umma_bf16(tmem_base + 384u, ad, kb + (uint64_t)(k * 128), idesc_dq, (uint32_t)(k != 0));
+                            }
+                        }
                     }
                 }
                 umma_commit(&st_empty[s]);
                 umma_commit(pds_empty);
+                if (kFused) umma_commit(dq_full);
                 s = s1;
                 if (++s1 == kStages) {
                     s1 = 0;
@@ -510,6 +557,25 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_kernel(const __grid_c
         const float* lse_p = p.lse2 + bh * p.Lq_pad + row;
         const float* del_p = p.delta + bh * p.Lq_pad + row;
         float my_lse = lse_p[kDQ ? r0 : 0], my_delta = del_p[kDQ ? r0 : 0];
+        // single-pass mode: drain the dQ partial of query tile `tile` (16 columns per warp) into the fp32 scratch with vector
+        // atomics straight from registers: lane-contiguous 16-byte chunks, 512 B per warp instruction
+        auto flush_dq = [&](int tile) __attribute__((always_inline)) {
+            uint32_t rq[16];
+            mbar_wait(dq_full, (uint32_t)(tile & 1));
+            tc_fence_after();
+            tmem_ld16(tmem_base + lane_addr + 384u + (uint32_t)(quarter * 16), rq);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(dq_empty);
+            float* dst = p.dq_acc + (bh * (size_t)(p.Lq_pad / 128) + tile) * (size_t)(16 * 128 * 4) + ((size_t)(quarter * 4) * 128 + row) * 4;
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + (size_t)c * 512),
+                             "f"(__uint_as_float(rq[c * 4])), "f"(__uint_as_float(rq[c * 4 + 1])),
+                             "f"(__uint_as_float(rq[c * 4 + 2])), "f"(__uint_as_float(rq[c * 4 + 3]))
+                             : "memory");
+        };
         for (int i = 0; i < n_iter; ++i) {
             float nx_lse = my_lse, nx_delta = my_delta;
             if (!kDQ && i + 1 < n_iter) {  // next query tile's scalars, in flight during this tile's math
@@ -555,9 +621,11 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_kernel(const __grid_c
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) mbar_arrive(pds_full);
+            if (kFused && i > 0) flush_dq(i - 1);  // previous tile's dQ, off the critical path
             my_lse = nx_lse;
             my_delta = nx_delta;
         }
+        if (kFused) flush_dq(n_iter - 1);
         // ---- write the accumulators (TMEM lane = key row in the dK/dV pass, query row in the dQ pass) ----
         // warp (sub, quarter) writes columns [16 quarter, +16) of its 32 rows
         mbar_wait(acc_full, 0);
@@ -668,7 +736,17 @@ extern "C" int uwu_attn_fwd(const void* q, const void* k, const void* v, void* o
 extern "C" int64_t uwu_attn_bwd_workspace_floats(int32_t B, int32_t heads, int32_t Lq) {
     if (B <= 0 || heads <= 0 || Lq <= 0) return 0;
     const int64_t rows = (int64_t)B * heads * ((Lq + 127) / 128 * 128);
-    return rows * 2;  // lse * log2(e), delta
+    return rows * 2 + rows * 64;  // lse * log2(e), delta, fp32 dQ scratch (single-pass mode)
+}
+
+// 0 = two passes (dK/dV, then dQ; no atomics), 1 = single pass with an fp32 dQ scratch.  Default from UWU_ATTN_BWD_MODE.
+static int attn_bwd_mode() {
+    static int mode = -1;
+    if (mode < 0) {
+        const char* e = getenv("UWU_ATTN_BWD_MODE");
+        mode = e ? atoi(e) : 1;
+    }
+    return mode;
 }
 
 extern "C" int uwu_attn_bwd(const void* q, const void* k, const void* v, const void* o, const void* dout, const float* lse,
@@ -710,13 +788,25 @@ extern "C" int uwu_attn_bwd(const void* q, const void* k, const void* v, const v
     }
     static bool attr_set = false;
     if (!attr_set) {
-        UWU_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdCfg<false>::SMEM));
-        UWU_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdCfg<true>::SMEM));
+        UWU_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdCfg<0>::SMEM));
+        UWU_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdCfg<1>::SMEM));
+        UWU_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdCfg<2>::SMEM));
         attr_set = true;
     }
-    attn_bwd_kernel<false><<<dim3((Lk + 127) / 128, heads, B), BWD_THREADS, BwdCfg<false>::SMEM, stream>>>(a);  // dK, dV
-    UWU_CHECK_LAUNCH();
-    attn_bwd_kernel<true><<<dim3((Lq + 127) / 128, heads, B), BWD_THREADS, BwdCfg<true>::SMEM, stream>>>(a);   // dQ
-    UWU_CHECK_LAUNCH();
+    if (attn_bwd_mode() == 1) {
+        a.dq_acc = workspace + 2 * rows;
+        UWU_CHECK_CUDA(cudaMemsetAsync(a.dq_acc, 0, (size_t)(rows * 64) * sizeof(float), stream));
+        attn_bwd_kernel<2><<<dim3((Lk + 127) / 128, heads, B), BWD_THREADS, BwdCfg<2>::SMEM, stream>>>(a);  // dK, dV, dQ partials
+        UWU_CHECK_LAUNCH();
+        const long long total = (long long)B * Lq * heads * 8;
+        attn_bwd_dq_convert_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(
+            a.dq_acc, B, heads, Lq, Lq_pad / 128, scale, reinterpret_cast<__nv_bfloat16*>(dq), lddq);
+        UWU_CHECK_LAUNCH();
+    } else {
+        attn_bwd_kernel<0><<<dim3((Lk + 127) / 128, heads, B), BWD_THREADS, BwdCfg<0>::SMEM, stream>>>(a);  // dK, dV
+        UWU_CHECK_LAUNCH();
+        attn_bwd_kernel<1><<<dim3((Lq + 127) / 128, heads, B), BWD_THREADS, BwdCfg<1>::SMEM, stream>>>(a);  // dQ
+        UWU_CHECK_LAUNCH();
+    }
     return UWU_OK;
 }
