@@ -190,32 +190,41 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) attn_fwd_kernel(const __grid_c
                 tc_fence_after();
                 const int kv_valid = min(128, p.Lk - j * 128);
                 const bool full = kv_valid == 128;
-                // pass 1: row maximum (3-input max: two scores per instruction)
+                // pass 1: row maximum (3-input max: two scores per instruction); TMEM loads issued in pairs
                 float mx = -INFINITY;
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    uint32_t r[32];
-                    tmem_ld32(t_s + (uint32_t)(c * 32), r);
+                for (int cp = 0; cp < 2; ++cp) {
+                    uint32_t ra[32], rb[32];
+                    tmem_ld32(t_s + (uint32_t)(cp * 64), ra);
+                    tmem_ld32(t_s + (uint32_t)(cp * 64 + 32), rb);
                     tmem_ld_wait();
                     if (full) {
 #pragma unroll
-                        for (int i = 0; i < 32; i += 2) mx = fmax3(mx, __uint_as_float(r[i]), __uint_as_float(r[i + 1]));
+                        for (int i = 0; i < 32; i += 2) {
+                            mx = fmax3(mx, __uint_as_float(ra[i]), __uint_as_float(ra[i + 1]));
+                            mx = fmax3(mx, __uint_as_float(rb[i]), __uint_as_float(rb[i + 1]));
+                        }
                     } else {
 #pragma unroll
-                        for (int i = 0; i < 32; ++i)
-                            if (c * 32 + i < kv_valid) mx = fmaxf(mx, __uint_as_float(r[i]));
+                        for (int i = 0; i < 32; ++i) {
+                            if (cp * 64 + i < kv_valid) mx = fmaxf(mx, __uint_as_float(ra[i]));
+                            if (cp * 64 + 32 + i < kv_valid) mx = fmaxf(mx, __uint_as_float(rb[i]));
+                        }
                     }
                 }
                 const float m_new = fmaxf(m, mx);
                 const float alpha = ex2_approx((m - m_new) * sl2);
                 const float msl = m_new * sl2;
-                // pass 2: probabilities -> bf16 -> swizzled smem, row sum
+                // pass 2: probabilities -> bf16 -> swizzled smem, row sum; the TMEM load of chunk c+1 is in flight while
+                // chunk c is exponentiated
                 float rs = 0.f;
+                uint32_t rbuf[2][32];
+                tmem_ld32(t_s, rbuf[0]);
+                tmem_ld_wait();
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
-                    uint32_t r[32];
-                    tmem_ld32(t_s + (uint32_t)(c * 32), r);
-                    tmem_ld_wait();
+                    if (c < 3) tmem_ld32(t_s + (uint32_t)((c + 1) * 32), rbuf[(c + 1) & 1]);
+                    const uint32_t(&r)[32] = rbuf[c & 1];
                     float pe[32];
                     if (full) {
 #pragma unroll
@@ -241,6 +250,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) attn_fwd_kernel(const __grid_c
                         const int cc = (c & 1) * 4 + q4;
                         st_shared_v4(prow_s + (uint32_t)((c >> 1) * AT_TILE + ((cc ^ sw) << 4)), u);
                     }
+                    if (c < 3) tmem_ld_wait();
                 }
                 l = fmaf(l, alpha, rs);
                 m = m_new;
@@ -251,13 +261,16 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) attn_fwd_kernel(const __grid_c
                 // fold P V into the register accumulators
                 mbar_wait(&pv_full[t], (uint32_t)(j & 1));
                 tc_fence_after();
-#pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                    uint32_t r[32];
-                    tmem_ld32(t_pv + (uint32_t)(c * 32), r);
+                {
+                    uint32_t r0[32], r1[32];
+                    tmem_ld32(t_pv, r0);
+                    tmem_ld32(t_pv + 32u, r1);
                     tmem_ld_wait();
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) O[c * 32 + i] = fmaf(O[c * 32 + i], alpha, __uint_as_float(r[i]));
+                    for (int i = 0; i < 32; ++i) {
+                        O[i] = fmaf(O[i], alpha, __uint_as_float(r0[i]));
+                        O[32 + i] = fmaf(O[32 + i], alpha, __uint_as_float(r1[i]));
+                    }
                 }
             }
             const int q = q0 + t * 128 + row;

@@ -227,6 +227,9 @@ class DMTrainer(BaseTrainer):
         f["opt"].step()
         if f["sched"] is not None:
             f["sched"].step()
-        f["opt"].zero_grad(set_to_none=False)  # gradients keep their (flat) storage
+        if self.lycoris_model is not None:
+            self.lycoris_model.zero_grad()  # one fill over the flat gradient buffer instead of one per adapter tensor
+        else:
+            f["opt"].zero_grad(set_to_none=False)  # gradients keep their (flat) storage
         self.global_step += 1
         return out
