@@ -48,6 +48,26 @@ def test_gemm_row_nk(ops, M, N, K, bn, odt):
     assert relerr(out, a.float() @ b.float().t()) < (TOL_F32 if odt == torch.float32 else TOL_BF16)
 
 
+@pytest.mark.parametrize("M,N,K,layout", [(38528, 512, 256, "nk"), (38500, 640, 192, "nk"), (40960, 1280, 320, "kn"),
+                                            (38528 + 64, 256, 128, "kn"), (65536, 320, 128, "nk")])
+def test_gemm_large_tile_counts(ops, M, N, K, layout):
+    """Shapes with >= 2 tiles per SM (with UWU_GEMM_CLUSTER=1 these run as 2-CTA clusters sharing every B tile through TMA
+    multicast: odd row-tile counts, ragged M, both B layouts)."""
+    from uwudiff_b200._lib import B_KN
+
+    a = mk(M, K)
+    bias, res = torch.randn(N, device=DEV), mk(M, N)
+    if layout == "nk":
+        b = mk(N, K)
+        out = ops.gemm(a, b, M, N, K, bias=bias, residual=res)
+        ref = a.float() @ b.float().t()
+    else:
+        b = mk(K, N)
+        out = ops.gemm(a, b, M, N, K, b_layout=B_KN, ldb=N, bias=bias, residual=res)
+        ref = a.float() @ b.float()
+    assert relerr(out, ref + bias + res.float()) < TOL_BF16
+
+
 def test_gemm_epilogues(ops):
     M, N, K = 512, 320, 256
     a, b = mk(M, K), mk(N, K)

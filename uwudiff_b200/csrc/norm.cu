@@ -42,6 +42,7 @@ __global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x, GNGeom g, f
 #pragma unroll
     for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
     const __nv_bfloat16* base = x + ((size_t)n * g.HW) * g.C + v * 8;
+#pragma unroll 4
     for (int r = r0 + rr; r < r1; r += g.rpi) {
         float f[8];
         ld8(base + (size_t)r * g.C, f);
@@ -117,6 +118,7 @@ __global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x, const float
     const int r0 = chunk * g.rows_per_chunk;
     const int r1 = min(g.HW, r0 + g.rows_per_chunk);
     const size_t off = ((size_t)n * g.HW) * g.C + v * 8;
+#pragma unroll 4
     for (int r = r0 + rr; r < r1; r += g.rpi) {
         float f[8];
         ld8(x + off + (size_t)r * g.C, f);
@@ -152,6 +154,7 @@ __global__ void gn_bwd_stats_kernel(const __nv_bfloat16* __restrict__ x, const _
     const int r0 = chunk * g.rows_per_chunk;
     const int r1 = min(g.HW, r0 + g.rows_per_chunk);
     const size_t off = ((size_t)n * g.HW) * g.C + v * 8;
+#pragma unroll 4
     for (int r = r0 + rr; r < r1; r += g.rpi) {
         float f[8], d[8];
         ld8(x + off + (size_t)r * g.C, f);
@@ -241,6 +244,7 @@ __global__ void gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x, const _
     const int r0 = chunk * g.rows_per_chunk;
     const int r1 = min(g.HW, r0 + g.rows_per_chunk);
     const size_t off = ((size_t)n * g.HW) * g.C + v * 8;
+#pragma unroll 4
     for (int r = r0 + rr; r < r1; r += g.rpi) {
         float f[8], d[8], o[8];
         ld8(x + off + (size_t)r * g.C, f);
