@@ -325,8 +325,19 @@ def run_gpu(args):
         achieved = fl / (t_ms * 1e-3) / 1e12
         peak = pk["bf16_tflops_sustained"]
         fwd = unet_forward_flops(SDXL_UNET_CONFIG, S, S)["total"] * B
+        traffic, traffic_note = None, None
+        try:  # DRAM bytes of the representative launch (GEGLU projection, M16384 N10240 K1280) from the committed ncu capture
+            with open(os.path.join(ROOT, "profiles", "r01_ncu_full_summary.json")) as f:
+                g0 = json.load(f)["gemm"][0]
+            traffic = (g0["dram_read_mb"] + g0["dram_write_mb"]) * 1e6
+            traffic_note = ("ncu --set full, one launch of M16384 N10240 K1280 (the largest Linear class): "
+                            f"{g0['dram_read_mb']:.0f} MB read + {g0['dram_write_mb']:.0f} MB written vs 403 MB algorithmic "
+                            f"(A 42 + B 26 + out 335), tensor pipe {g0['tensor_pct']:.1f}% active, {g0['time_us']:.0f} us")
+        except Exception:
+            pass
         roof = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (Linear + implicit-GEMM conv, fwd/dgrad/adapter-wgrad)",
-                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
+                "traffic_note": traffic_note,
                 "peak_source": pk_src + " bf16_tflops_sustained", "launches_per_step": len(recs),
                 "kernel_ms_per_step": t_ms, "kernel_share_of_step": t_ms / ms_dev,
                 "step_algorithmic_tflop": 2 * fwd / 1e12, "step_algorithmic_tflops": 2 * fwd / 1e12 / (ms_dev * 1e-3),

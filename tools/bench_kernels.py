@@ -40,6 +40,28 @@ def tf(name, us, flops):
     print(f"{name}: {us:8.1f} us  {flops/us/1e6:7.1f} TFLOP/s", flush=True)
 
 
+def case_noise():
+    """Fused noising (Philox eps + t, sigma gather, x_t, target, weights, t-embedding) and the weighted-MSE reduction at the
+    C5 one-GPU size (B128 x 4x128x128 fp32 = 8.4 M elements; 12 B/elem algorithmic for noising, 8 / 12 for the loss)."""
+    from uwudiff_b200.loss import DiffusionLoss
+    from uwudiff_b200.scheduler import EulerDiscreteScheduler
+
+    sch = EulerDiscreteScheduler.from_pretrained("stabilityai/stable-diffusion-xl-base-1.0", subfolder="scheduler",
+                                                 prediction_type="v_prediction")
+    L = DiffusionLoss(sch, use_snr_weight=True)
+    for B in (16, 128, 512):
+        x0 = torch.randn(B, 4, 128, 128, device=dev)
+        tab = L._device_tables(x0.device)
+        n = x0.numel()
+        f = lambda: ops.noise_fwd(x0, tab, target_type="v_prediction", pred_type="v_prediction", use_snr_weight=True,
+                                  use_debiased=False, gamma=5.0, seed=1, offset=0, temb_dim=320, want_eps=False)
+        bw(f"noise_fwd B{B} 4x128x128 fp32 (Philox, no eps out)", timeit(f), n * 12)
+        x_t, target, _, t, sig, w, temb = f()
+        pred = torch.randn_like(x0)
+        bw(f"wmse_fwd B{B}", timeit(lambda: ops.wmse_fwd(pred, target, w)), n * 8)
+        bw(f"wmse_bwd B{B}", timeit(lambda: ops.wmse_bwd(pred, target, w)), n * 12)
+
+
 def case_ln():
     for (M, C) in [(16384, 1280), (65536, 640)]:
         x, dy, dres = mk(M, C), mk(M, C), mk(M, C)

@@ -40,6 +40,39 @@ def main(what):
         bias = torch.zeros(N, device=dev)
         for _ in range(3):
             ops.gemm(a, b, M, N, K, out=out, bias=bias)
+    elif what == "bw":
+        # one launch each of the bandwidth-bound kernels at step shapes
+        from uwudiff_b200.loss import DiffusionLoss
+        from uwudiff_b200.scheduler import EulerDiscreteScheduler
+
+        M, C = 16384, 1280
+        x, dy, dres = mk(M, C), mk(M, C), mk(M, C)
+        gamma, beta = torch.ones(C, device=dev), torch.zeros(C, device=dev)
+        dg, db = torch.zeros(C, device=dev), torch.zeros(C, device=dev)
+        for _ in range(2):
+            y, stats = ops.layernorm_fwd(x, gamma, beta)
+            ops.layernorm_bwd(x, dy, gamma, stats, dres=dres, dgamma=dg, dbeta=db)
+        N, HW, Cg = 16, 128 * 128, 320
+        xg, dyg, drg = mk(N * HW, Cg), mk(N * HW, Cg), mk(N * HW, Cg)
+        gg, bg = torch.ones(Cg, device=dev), torch.zeros(Cg, device=dev)
+        for _ in range(2):
+            yg, sg = ops.groupnorm_fwd(xg, N, HW, Cg, 32, 1e-5, gg, bg, True)
+            ops.groupnorm_bwd(xg, dyg, N, HW, Cg, 32, gg, bg, sg, True, dres=drg)
+        xp, dout = mk(M, 10240), mk(M, 5120)
+        for _ in range(2):
+            ops.geglu_fwd(xp)
+            ops.geglu_bwd(xp, dout)
+        sch = EulerDiscreteScheduler.from_pretrained("stabilityai/stable-diffusion-xl-base-1.0", subfolder="scheduler",
+                                                     prediction_type="v_prediction")
+        L = DiffusionLoss(sch, use_snr_weight=True)
+        x0 = torch.randn(128, 4, 128, 128, device=dev)
+        tab = L._device_tables(x0.device)
+        for _ in range(2):
+            x_t, target, _, t, sig, w, temb = ops.noise_fwd(x0, tab, target_type="v_prediction", pred_type="v_prediction",
+                                                            use_snr_weight=True, use_debiased=False, gamma=5.0, seed=1, offset=0,
+                                                            temb_dim=320, want_eps=False)
+            ops.wmse_fwd(x_t, target, w)
+            ops.wmse_bwd(x_t, target, w)
     torch.cuda.synchronize()
 
 

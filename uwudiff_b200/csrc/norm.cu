@@ -83,20 +83,25 @@ __global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x, GNGeom g, f
 
 // finalise mean / rstd per (n, g) from the chunk partials; stats[n, g, {mean, rstd}]
 __global__ void gn_finalize_kernel(const float* __restrict__ ws, GNGeom g, float eps, float* __restrict__ stats) {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    // one warp per (n, g): lanes stride over the chunk partials
+    const int idx = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (idx >= g.N * g.G) return;
     const int n = idx / g.G, gi = idx - n * g.G;
     float a = 0.f, b = 0.f;
-    for (int c = 0; c < g.chunks; ++c) {
-        const float* p = ws + (((size_t)n * g.chunks + c) * g.G + gi) * 2;
-        a += p[0];
-        b += p[1];
+    for (int c = lane; c < g.chunks; c += 32) {
+        const float2 p = *reinterpret_cast<const float2*>(ws + (((size_t)n * g.chunks + c) * g.G + gi) * 2);
+        a += p.x;
+        b += p.y;
     }
-    const float cnt = (float)g.HW * (float)(g.C / g.G);
-    const float mean = a / cnt;
-    const float var = fmaxf(b / cnt - mean * mean, 0.f);
-    stats[idx * 2] = mean;
-    stats[idx * 2 + 1] = rsqrtf(var + eps);
+    a = warp_sum(a);
+    b = warp_sum(b);
+    if (lane == 0) {
+        const float cnt = (float)g.HW * (float)(g.C / g.G);
+        const float mean = a / cnt;
+        const float var = fmaxf(b / cnt - mean * mean, 0.f);
+        stats[idx * 2] = mean;
+        stats[idx * 2 + 1] = rsqrtf(var + eps);
+    }
 }
 
 template <bool kSilu>
@@ -197,6 +202,7 @@ __global__ void gn_bwd_reduce_kernel(const float* __restrict__ wsb, const float*
     const int n = blockIdx.x;
     for (int c = threadIdx.x; c < g.C; c += blockDim.x) {
         float a = 0.f, b = 0.f;
+#pragma unroll 8
         for (int k = 0; k < g.chunks; ++k) {
             const float* p = wsb + ((size_t)n * g.chunks + k) * 2 * g.C;
             a += p[c];
@@ -649,7 +655,7 @@ extern "C" int uwu_groupnorm_fwd(const void* x, int32_t N, int32_t HW, int32_t C
     const int threads = g.cv * g.rpi;
     gn_stats_kernel<<<grid, threads, (size_t)g.rpi * 2 * C * sizeof(float), stream>>>(xp, g, workspace);
     UWU_CHECK_LAUNCH();
-    gn_finalize_kernel<<<(N * G + 127) / 128, 128, 0, stream>>>(workspace, g, eps, stats);
+    gn_finalize_kernel<<<(N * G * 32 + 255) / 256, 256, 0, stream>>>(workspace, g, eps, stats);
     UWU_CHECK_LAUNCH();
     if (fuse_silu)
         gn_apply_kernel<true><<<grid, threads, 0, stream>>>(xp, stats, gamma, beta, g, yp);
