@@ -143,6 +143,14 @@ int uwu_wmse_bwd(const void* pred, int32_t pred_dtype, const void* target, int32
                  int64_t n_per, const float* w, const float* grad_scale_dev, float grad_scale, void* dpred,
                  int32_t dpred_dtype, void* stream);
 
+/* Prediction -> target space when prediction_type != target_type: get_x0_eps_from_pred_with_sigmas + get_target
+ * (src/duwu/loss/diffusion.py:100-139, called at :177 with the CLEAN latents x — kept bug-compatible).  Per sample the map is
+ * linear: result = A_b * out + C_b * x (forward), result = A_b * out (backward = gradient w.r.t. the model output).
+ * sigma: fp32 [B] (the noising kernel's sigma_out), t: int64 [B], acp: alphas_cumprod table. */
+int uwu_pred_convert(const float* out, const void* x, int32_t x_dtype, const float* sigma, const int64_t* t, const float* acp,
+                     int32_t B, int64_t n_per, int32_t pred_type, int32_t target_type, int32_t backward, float* result,
+                     void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Flash attention forward / backward (tcgen05 + TMEM + TMA), head_dim 64.
  *   replaces F.scaled_dot_product_attention in diffusers' AttnProcessor2_0 (in-tree copy of the flow:

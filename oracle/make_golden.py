@@ -35,6 +35,10 @@ CASES = [
 ]
 
 
+MIXED = [("v_prediction", "epsilon"), ("epsilon", "sample"), ("sample", "v_prediction"), ("rectified_flow", "epsilon"),
+         ("epsilon", "rectified_flow"), ("v_prediction", "sample")]
+
+
 def unet_stub(x, t, **kw):
     return (0.5 * x,)
 
@@ -71,6 +75,28 @@ def main():
         out[f"{name}/losses"] = aux.losses.float().numpy()
         out[f"{name}/loss"] = np.float32(loss.float().item())
         out[f"{name}/meta"] = np.array([ttype, str(int(snr)), str(int(deb)), str(dtype).replace("torch.", "")])
+    # prediction type != target type: get_prediction_for_training -> get_x0_eps_from_pred -> get_target (:100-139)
+    for j, (ptype, ttype) in enumerate(MIXED):
+        name = f"mixed_{ptype}_to_{ttype}"
+        sch = diffusers_shim.EulerDiscreteScheduler.from_pretrained("x", prediction_type=ptype)
+        L = mod.DiffusionLoss(sch, prediction_type=ptype, target_type=ttype)
+        g = torch.Generator().manual_seed(3000 + j)
+        x0 = torch.randn((4, 4, 8, 8), generator=g)
+        torch.manual_seed(4000 + j)
+        loss, aux = L(x0, unet_stub)
+        torch.manual_seed(4000 + j)
+        eps = torch.randn_like(x0)
+        t = torch.randint(0, 1000, (4,))
+        assert torch.equal(t, aux.timesteps)
+        out[f"{name}/x0"] = x0.numpy()
+        out[f"{name}/eps"] = eps.numpy()
+        out[f"{name}/t"] = t.numpy()
+        out[f"{name}/x_t"] = aux.noisy_latent.numpy()
+        out[f"{name}/target"] = aux.target.numpy()
+        out[f"{name}/pred"] = aux.pred.numpy()
+        out[f"{name}/losses"] = aux.losses.numpy()
+        out[f"{name}/loss"] = np.float32(loss.item())
+        out[f"{name}/meta"] = np.array([ptype, ttype])
     # unsupported target type -> ValueError in the reference (:98)
     np.savez_compressed(OUT, **out)
     print("wrote", OUT, os.path.getsize(OUT), "bytes;", len(CASES), "cases")

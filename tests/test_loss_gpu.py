@@ -55,6 +55,42 @@ def test_noising_and_loss_match_golden(golden, dl, name):
     assert abs(loss.item() - float(golden[f"{name}/loss"])) <= rtol * abs(float(golden[f"{name}/loss"]))
 
 
+MIXED = [("v_prediction", "epsilon"), ("epsilon", "sample"), ("sample", "v_prediction"), ("rectified_flow", "epsilon"),
+         ("epsilon", "rectified_flow"), ("v_prediction", "sample")]
+
+
+@pytest.mark.parametrize("ptype,ttype", MIXED)
+def test_mixed_prediction_and_target_types_match_golden(golden, ptype, ttype):
+    """a5: model output converted into the target space by uwu_pred_convert (per-sample linear map), forward value against
+    the reference's golden vectors and the gradient w.r.t. the model output against autograd through the oracle."""
+    from uwudiff_b200.loss import DiffusionLoss
+    from uwudiff_b200.scheduler import EulerDiscreteScheduler
+
+    name = f"mixed_{ptype}_to_{ttype}"
+    sch = EulerDiscreteScheduler.from_pretrained("stabilityai/stable-diffusion-xl-base-1.0", subfolder="scheduler",
+                                                 prediction_type=ptype)
+    L = DiffusionLoss(sch, prediction_type=ptype, target_type=ttype)
+    x0 = torch.from_numpy(golden[f"{name}/x0"]).cuda()
+    eps = torch.from_numpy(golden[f"{name}/eps"]).cuda()
+    t = torch.from_numpy(golden[f"{name}/t"]).cuda()
+    scale = torch.full((), 0.5, device="cuda", requires_grad=True)
+    loss, aux = L(x0, lambda x, tt, **kw: (scale * x,), noise=eps, timesteps=t)
+    np.testing.assert_array_equal(aux.noisy_latent.cpu().numpy(), golden[f"{name}/x_t"])
+    np.testing.assert_array_equal(aux.target.cpu().numpy(), golden[f"{name}/target"])
+    # the kernel evaluates the composed linear map A*out + C*x in fp32 (the reference chains ~6 roundings): 2e-5 of the range
+    ref = golden[f"{name}/pred"]
+    assert np.abs(aux.pred.detach().cpu().numpy() - ref).max() <= 2e-5 * max(1.0, np.abs(ref).max())
+    np.testing.assert_allclose(aux.losses.detach().cpu().numpy(), golden[f"{name}/losses"], rtol=2e-4)
+    loss.backward()
+    # gradient through the conversion: same computation in fp64 autograd on the CPU oracle
+    tab = loss_oracle.scheduler_tables(diffusers_shim.EulerDiscreteScheduler.from_pretrained("x"))
+    s = torch.full((), 0.5, dtype=torch.float64, requires_grad=True)
+    lo, _ = loss_oracle.diffusion_loss(x0.cpu().double(), eps.cpu().double(), t.cpu(), lambda x, tt, **kw: (s * x,), tab,
+                                       target_type=ttype, prediction_type=ptype)
+    lo.backward()
+    assert abs(scale.grad.item() - s.grad.item()) <= 2e-4 * abs(s.grad.item()) + 1e-6
+
+
 def test_weights_bit_exact_all_timesteps(dl):
     from uwudiff_b200 import ops
 

@@ -58,6 +58,25 @@ def test_restatement_matches_golden(golden, name):
         assert abs(loss.item() - float(golden[f"{name}/loss"])) < 2e-2 * abs(float(golden[f"{name}/loss"]))
 
 
+MIXED = [("v_prediction", "epsilon"), ("epsilon", "sample"), ("sample", "v_prediction"), ("rectified_flow", "epsilon"),
+         ("epsilon", "rectified_flow"), ("v_prediction", "sample")]
+
+
+@pytest.mark.parametrize("ptype,ttype", MIXED)
+def test_restatement_matches_golden_mixed_types(golden, ptype, ttype):
+    """prediction_type != target_type: get_prediction_for_training -> get_x0_eps_from_pred -> get_target
+    (src/duwu/loss/diffusion.py:100-139), golden vectors from the reference run verbatim."""
+    name = f"mixed_{ptype}_to_{ttype}"
+    _, tab = _tables()
+    x0, eps, t = (torch.from_numpy(golden[f"{name}/{k}"]) for k in ("x0", "eps", "t"))
+    loss, aux = loss_oracle.diffusion_loss(x0, eps, t, lambda x, tt, **kw: (0.5 * x,), tab, target_type=ttype,
+                                           prediction_type=ptype)
+    np.testing.assert_array_equal(aux["noisy_latent"].numpy(), golden[f"{name}/x_t"])
+    np.testing.assert_array_equal(aux["target"].numpy(), golden[f"{name}/target"])
+    np.testing.assert_array_equal(aux["pred"].numpy(), golden[f"{name}/pred"])
+    np.testing.assert_allclose(aux["losses"].numpy(), golden[f"{name}/losses"], rtol=1e-6)
+
+
 def test_survey_probe_case():
     """seed 1215, x=randn(4,4,32,32), unet = 0.5*x, min-SNR + debiased."""
     _, tab = _tables()

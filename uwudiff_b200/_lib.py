@@ -76,6 +76,7 @@ SIGNATURES = {
     "uwu_wmse_workspace_floats": (C.c_int64, [_I32, _I64]),
     "uwu_wmse_fwd": (C.c_int, [_P, _I32, _P, _I32, _I32, _I64, _P, _P, _P, _P, _P]),
     "uwu_wmse_bwd": (C.c_int, [_P, _I32, _P, _I32, _I32, _I64, _P, _P, _F, _P, _I32, _P]),
+    "uwu_pred_convert": (C.c_int, [_P, _P, _I32, _P, _P, _P, _I32, _I64, _I32, _I32, _I32, _P, _P]),
     "uwu_attn_lse_floats": (C.c_int64, [_I32, _I32, _I32]),
     "uwu_attn_fwd": (C.c_int, [_P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I64, _I64, _I64, _I64, _F, _P]),
     "uwu_attn_bwd_workspace_floats": (C.c_int64, [_I32, _I32, _I32]),

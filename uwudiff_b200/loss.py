@@ -38,6 +38,21 @@ class _WeightedMSE(torch.autograd.Function):
         return dpred, None, None
 
 
+class _PredConvert(torch.autograd.Function):
+    """pred = A_b * model_output + C_b * x per sample (uwu_pred_convert); gradient flows to the model output only."""
+
+    @staticmethod
+    def forward(ctx, out, x, sigma, t, acp, pred_type, target_type):
+        ctx.save_for_backward(sigma, t, acp)
+        ctx.types = (pred_type, target_type)
+        return ops.pred_convert(out, x, sigma, t, acp, pred_type, target_type)
+
+    @staticmethod
+    def backward(ctx, g):
+        sigma, t, acp = ctx.saved_tensors
+        return ops.pred_convert(g, None, sigma, t, acp, *ctx.types, backward=True), None, None, None, None, None, None
+
+
 class DiffusionLoss(nn.Module):
     def __init__(self, scheduler, use_snr_weight: bool = False, min_snr_gamma: float = 5.0,
                  use_debiased_estimation: bool = False, prediction_type: Optional[str] = None,
@@ -92,9 +107,6 @@ class DiffusionLoss(nn.Module):
                 timesteps: Optional[torch.Tensor] = None, **unet_kwargs):
         """`noise=` / `timesteps=` inject the reference's draws ("noise injected identically"); otherwise the
         kernel draws them with Philox4x32-10 keyed by (seed, step)."""
-        if self.prediction_type != self.target_type:
-            raise NotImplementedError("prediction_type != target_type (src/duwu/loss/diffusion.py:133-139) is not on "
-                                      "the kernel path yet; all shipped configs use equal types")
         if self.use_snr_weight:
             assert self.prediction_type == self.target_type
             assert self.prediction_type in ["epsilon", "v_prediction"]
@@ -110,7 +122,11 @@ class DiffusionLoss(nn.Module):
         if temb is not None:
             unet_kwargs = dict(unet_kwargs, _fused_temb=temb)
         model_output = unet(x_t, t, **unet_kwargs)[0]
-        pred = model_output
+        if self.prediction_type == self.target_type:
+            pred = model_output  # src/duwu/loss/diffusion.py:136-137
+        else:
+            # :138-139 (with the reference's argument quirk: the CLEAN latents are passed as `xt`, :177)
+            pred = _PredConvert.apply(model_output, x, _sigma, t, tab["acp"], self.prediction_type, self.target_type)
         weighted = self.use_snr_weight or self.use_debiased_estimation
         loss, losses = _WeightedMSE.apply(pred, target, w if weighted else None)
         aux = DiffusionLossAuxOutput(losses=losses, timesteps=t, pred=pred, target=target, noisy_latent=x_t)
