@@ -126,6 +126,8 @@ typedef struct uwu_noise_desc {
     float* w_out;         /* out [2,B]: min-SNR factor, debiased factor (1.0 when disabled) */
     void* temb_out;       /* out, optional bf16 [B, temb_dim] = [cos | sin] */
     int32_t temb_dim;
+    const float* sigma_in; /* optional fp32 [B]: per-sample sigma used instead of sigma_t[t] (RectifiedFlowLoss "uniform_time"
+                              sampling, src/duwu/loss/rectified_flow.py:27-45,63-71) */
 } uwu_noise_desc;
 
 int uwu_noise_fwd(const uwu_noise_desc* desc, void* stream);

@@ -39,6 +39,16 @@ MIXED = [("v_prediction", "epsilon"), ("epsilon", "sample"), ("sample", "v_predi
          ("epsilon", "rectified_flow"), ("v_prediction", "sample")]
 
 
+RF_CASES = [
+    # name, time_sampling_type, prediction_type, paired-noise input, rescale image+noise
+    ("rf_time_rf", "uniform_time", "rectified_flow", False, False),
+    ("rf_time_eps", "uniform_time", "epsilon", False, False),
+    ("rf_time_v_paired", "uniform_time", "v_prediction", True, False),
+    ("rf_timestep_rf", "uniform_timestep", "rectified_flow", False, False),
+    ("rf_time_sample_rescaled", "uniform_time", "sample", False, True),
+]
+
+
 def unet_stub(x, t, **kw):
     return (0.5 * x,)
 
@@ -97,6 +107,34 @@ def main():
         out[f"{name}/losses"] = aux.losses.numpy()
         out[f"{name}/loss"] = np.float32(loss.item())
         out[f"{name}/meta"] = np.array([ptype, ttype])
+    # RectifiedFlowLoss (src/duwu/loss/rectified_flow.py) run verbatim
+    rf = ref_loss.load_reference_rf_module()
+    for j, (name, sampling, ptype, paired, rescale) in enumerate(RF_CASES):
+        sch = diffusers_shim.EulerDiscreteScheduler.from_pretrained("x", prediction_type=ptype)
+        L = rf.RectifiedFlowLoss(time_sampling_type=sampling, rescale_image=rescale, rescale_noise=rescale, scheduler=sch,
+                                 prediction_type=ptype)
+        g = torch.Generator().manual_seed(5000 + j)
+        x_in = torch.randn((4, 2, 4, 8, 8) if paired else (4, 4, 8, 8), generator=g)
+        torch.manual_seed(6000 + j)
+        loss, aux = L(x_in, unet_stub)
+        torch.manual_seed(6000 + j)  # replay: randn_like (unless paired) -> rand / randint
+        noises = x_in[:, 1] if paired else torch.randn_like(x_in)
+        if sampling == "uniform_time":
+            smax = sch.sigmas[0]
+            time = torch.rand(4) * (smax / (1 + smax))
+            out[f"{name}/time"] = time.numpy()
+        else:
+            t_int = torch.randint(0, 1000, (4,))
+            assert torch.equal(t_int, aux.timesteps)
+        out[f"{name}/x_in"] = x_in.numpy()
+        out[f"{name}/noise"] = noises.numpy()
+        out[f"{name}/timesteps"] = aux.timesteps.numpy()
+        out[f"{name}/x_t"] = aux.noisy_latent.numpy()
+        out[f"{name}/target"] = aux.target.numpy()
+        out[f"{name}/pred"] = aux.pred.numpy()
+        out[f"{name}/losses"] = aux.losses.numpy()
+        out[f"{name}/loss"] = np.float32(loss.item())
+        out[f"{name}/meta"] = np.array([sampling, ptype, str(int(paired)), str(int(rescale))])
     # unsupported target type -> ValueError in the reference (:98)
     np.savez_compressed(OUT, **out)
     print("wrote", OUT, os.path.getsize(OUT), "bytes;", len(CASES), "cases")

@@ -34,3 +34,27 @@ def load_reference_loss_module():
         else:
             sys.modules["diffusers"] = prev
     return mod
+
+
+RF_FILE = "/root/reference/src/duwu/loss/rectified_flow.py"
+
+
+def load_reference_rf_module():
+    """Load the reference's `src/duwu/loss/rectified_flow.py` verbatim; its `from duwu.loss.diffusion import ...` is satisfied
+    by registering the verbatim-loaded diffusion module under that name (stub parent packages, removed afterwards)."""
+    diff = load_reference_loss_module()
+    saved = {k: sys.modules.get(k) for k in ("duwu", "duwu.loss", "duwu.loss.diffusion")}
+    pkg, sub = types.ModuleType("duwu"), types.ModuleType("duwu.loss")
+    pkg.__path__, sub.__path__ = [], []
+    sys.modules.update({"duwu": pkg, "duwu.loss": sub, "duwu.loss.diffusion": diff})
+    try:
+        spec = importlib.util.spec_from_file_location("_duwu_ref_loss_rf", RF_FILE)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    return mod

@@ -77,6 +77,21 @@ def test_restatement_matches_golden_mixed_types(golden, ptype, ttype):
     np.testing.assert_allclose(aux["losses"].numpy(), golden[f"{name}/losses"], rtol=1e-6)
 
 
+@pytest.mark.parametrize("name", ["rf_time_rf", "rf_time_eps", "rf_time_v_paired", "rf_time_sample_rescaled"])
+def test_rf_time_sampling_host_logic_matches_golden(golden, name):
+    """RectifiedFlowLoss.sample_timesteps_and_sigmas / sigma_to_timestep (host logic, no kernels): the fractional timesteps
+    the reference produced for the recorded uniform draws."""
+    from uwudiff_b200.loss import RectifiedFlowLoss
+    from uwudiff_b200.scheduler import EulerDiscreteScheduler
+
+    sch = EulerDiscreteScheduler.from_pretrained("stabilityai/stable-diffusion-xl-base-1.0", subfolder="scheduler")
+    L = RectifiedFlowLoss(scheduler=sch)
+    time = torch.from_numpy(golden[f"{name}/time"])
+    ts, sig = L.sample_timesteps_and_sigmas(torch.zeros(time.numel(), 1), time)
+    np.testing.assert_allclose(ts.numpy(), golden[f"{name}/timesteps"], rtol=1e-6, atol=1e-4)
+    np.testing.assert_allclose(sig.numpy(), (time / (1 - time)).numpy(), rtol=1e-6)
+
+
 def test_survey_probe_case():
     """seed 1215, x=randn(4,4,32,32), unet = 0.5*x, min-SNR + debiased."""
     _, tab = _tables()

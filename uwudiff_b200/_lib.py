@@ -52,7 +52,7 @@ class NoiseDesc(C.Structure):
         ("weight_flags", C.c_int32), ("gamma", C.c_float),
         ("x_t", C.c_void_p), ("target", C.c_void_p), ("eps_out", C.c_void_p),
         ("t_out", C.c_void_p), ("sigma_out", C.c_void_p), ("w_out", C.c_void_p),
-        ("temb_out", C.c_void_p), ("temb_dim", C.c_int32),
+        ("temb_out", C.c_void_p), ("temb_dim", C.c_int32), ("sigma_in", C.c_void_p),
     ]
 
 

@@ -24,6 +24,7 @@ import torch.nn as nn
 TARGET_ALIASES = {
     "duwu.trainer.DMTrainer": "uwudiff_b200.trainer.DMTrainer",
     "duwu.loss.DiffusionLoss": "uwudiff_b200.loss.DiffusionLoss",
+    "duwu.loss.RectifiedFlowLoss": "uwudiff_b200.loss.RectifiedFlowLoss",
     "duwu.data.TrainDataModule": "uwudiff_b200.data.TrainDataModule",
     "duwu.data.DummyDataset": "uwudiff_b200.data.DummyDataset",
     "duwu.modules.unet_patch.UNet2DFromScratch": "uwudiff_b200.unet.UNet2DFromScratch",

@@ -97,6 +97,7 @@ struct NoiseArgs {
     const void* x0;
     const void* eps_in;      // optional injected noise
     const int64_t* t_in;     // optional injected timesteps
+    const float* sigma_in;   // optional per-sample sigma (rectified-flow time sampling); replaces the table gather
     uint64_t seed, offset;
     const float* acp;        // alphas_cumprod[T]
     const float* sigma_t;    // sigma for timestep t, [T]
@@ -126,7 +127,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) noise_fwd_kernel(const NoiseArgs a) {
     const int b = blockIdx.y;
     const int t = a.t_in ? (int)a.t_in[b] : sample_timestep(b, a.T, a.seed, a.offset);
-    const float sigma = IO<T>::rnd(a.sigma_t[t]);                                   // sigmas.to(ref_params)
+    const float sigma = IO<T>::rnd(a.sigma_in ? a.sigma_in[b] : a.sigma_t[t]);        // sigmas.to(ref_params)
     const float sig2p1 = IO<T>::rnd(__fadd_rn(IO<T>::rnd(__fmul_rn(sigma, sigma)), 1.0f));
     const float scale = IO<T>::rnd(__fdiv_rn(1.0f, IO<T>::rnd(__fsqrt_rn(sig2p1))));  // 1 / (sigma**2 + 1) ** 0.5
     // get_velocity coefficients (diffusers): acp.to(dtype)[t] ** 0.5, (1 - acp[t]) ** 0.5
@@ -395,7 +396,7 @@ extern "C" int uwu_noise_fwd(const uwu_noise_desc* d, void* stream_) {
     UWU_CHECK_ARG(d->B <= 65535, "uwu_noise_fwd: batch %d exceeds 65535", d->B);
     UWU_CHECK_ARG(d->temb_out == nullptr || (d->temb_dim > 0 && d->temb_dim % 2 == 0), "uwu_noise_fwd: bad temb_dim");
     NoiseArgs a;
-    a.x0 = d->x0; a.eps_in = d->eps_in; a.t_in = d->t_in; a.seed = d->seed; a.offset = d->offset;
+    a.x0 = d->x0; a.eps_in = d->eps_in; a.t_in = d->t_in; a.sigma_in = d->sigma_in; a.seed = d->seed; a.offset = d->offset;
     a.acp = d->acp; a.sigma_t = d->sigma_t; a.snr = d->snr; a.T = d->T; a.B = d->B; a.n_per = d->n_per;
     a.target_type = d->target_type; a.pred_type = d->pred_type; a.weight_flags = d->weight_flags; a.gamma = d->gamma;
     a.x_t = d->x_t; a.target = d->target; a.eps_out = d->eps_out; a.t_out = d->t_out; a.sigma_out = d->sigma_out;

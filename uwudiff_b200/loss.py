@@ -131,3 +131,90 @@ class DiffusionLoss(nn.Module):
         loss, losses = _WeightedMSE.apply(pred, target, w if weighted else None)
         aux = DiffusionLossAuxOutput(losses=losses, timesteps=t, pred=pred, target=target, noisy_latent=x_t)
         return loss, aux
+
+
+class RectifiedFlowLoss(DiffusionLoss):
+    """Drop-in for `duwu.loss.RectifiedFlowLoss` (src/duwu/loss/rectified_flow.py:9-129): target = eps - x0, time sampling
+    `uniform_time` (sigma = time / (1 - time), fractional timesteps through `sigma_to_timestep`) or `uniform_timestep`,
+    optional paired-noise input [B, 2, C, H, W] and per-sample std rescaling.  Noising / target / conversion / MSE run in
+    the same kernels as DiffusionLoss (the noising kernel takes the sampled sigmas instead of gathering them)."""
+
+    def __init__(self, time_sampling_type: str = "uniform_time", time_sampling_kwargs: dict = {}, rescale_image: bool = False,
+                 rescale_noise: bool = False, **kwargs):
+        super().__init__(**kwargs)
+        self.target_type = "rectified_flow"
+        self.time_sampling_type = time_sampling_type
+        self.time_sampling_kwargs = time_sampling_kwargs
+        self.rescale_image = rescale_image
+        self.rescale_noise = rescale_noise
+
+    def sample_timesteps_and_sigmas(self, ref_params: torch.Tensor, time: Optional[torch.Tensor] = None):
+        """rectified_flow.py:27-45.  `time=` injects the uniform draws (parity runs)."""
+        batch_size = ref_params.size(0)
+        scheduler_sigma_max = self.scheduler.sigmas[0]
+        max_time = scheduler_sigma_max / (1 + scheduler_sigma_max)
+        if self.time_sampling_type == "uniform_timestep":
+            timesteps = torch.randint(0, self.n_diffusion_time_steps, (batch_size,), device=ref_params.device)
+            return timesteps, None
+        if self.time_sampling_type == "uniform_time":
+            if time is None:
+                time = torch.rand(batch_size, device=ref_params.device) * max_time.to(ref_params.device)
+            time = time.to(ref_params.device)
+            sigmas = time / (1 - time).to(ref_params)
+            return self.sigma_to_timestep(sigmas), sigmas
+        raise ValueError(f"Unsupported time sampling type: {self.time_sampling_type}")
+
+    def get_x0_and_noises(self, x: torch.Tensor, noise: Optional[torch.Tensor] = None):
+        """rectified_flow.py:47-61 (noise None -> drawn inside the noising kernel unless it has to be rescaled)."""
+        if x.dim() == 5:
+            noise = x[:, 1, ...]
+            x = x[:, 0, ...]
+        if self.rescale_image:
+            x = x / x.std([1, 2, 3], keepdim=True)
+            x = x * 0.937
+        if self.rescale_noise:
+            if noise is None:
+                noise = torch.randn_like(x)
+            noise = noise / noise.std([1, 2, 3], keepdim=True)
+        return x.contiguous(), (None if noise is None else noise.contiguous())
+
+    def sigma_to_timestep(self, sigmas: torch.Tensor) -> torch.Tensor:
+        """rectified_flow.py:98-129: piecewise-linear interpolation of log sigma over the scheduler's table."""
+        log_sigmas = torch.log(sigmas.clamp(min=1e-10))
+        log_scheduler_sigmas = torch.log(self.scheduler.sigmas[:-1]).flip(0).to(log_sigmas)
+        dists = log_sigmas - log_scheduler_sigmas[:, None]
+        low_idx = dists.ge(0).cumsum(dim=0).argmax(dim=0).clamp(max=log_scheduler_sigmas.shape[0] - 2)
+        high_idx = low_idx + 1
+        low = log_scheduler_sigmas[low_idx]
+        high = log_scheduler_sigmas[high_idx]
+        w = torch.clamp((low - log_sigmas) / (low - high), 0, 1)
+        t = (1 - w) * low_idx + w * high_idx
+        return t.view(sigmas.shape)
+
+    def forward(self, x: torch.Tensor, unet: nn.Module, *, noise: Optional[torch.Tensor] = None,
+                time: Optional[torch.Tensor] = None, timesteps: Optional[torch.Tensor] = None, **unet_kwargs):
+        x, noise = self.get_x0_and_noises(x, noise)
+        tab = self._device_tables(x.device)
+        if timesteps is None:
+            timesteps, sigmas = self.sample_timesteps_and_sigmas(x, time)
+        else:
+            sigmas = None
+        if sigmas is None:  # uniform_timestep: integer timesteps, sigma gathered from the table inside the kernel
+            x_t, target, _e, t, sigma, _w, _temb = ops.noise_fwd(
+                x, tab, target_type="rectified_flow", pred_type=self.prediction_type, use_snr_weight=False, use_debiased=False,
+                gamma=self.min_snr_gamma, eps=noise, timesteps=timesteps, seed=self.seed, offset=self._step, want_eps=False)
+            t_idx, t_unet = t, t
+        else:
+            t_idx = torch.zeros((x.shape[0],), device=x.device, dtype=torch.int64)
+            x_t, target, _e, _t, sigma, _w, _temb = ops.noise_fwd(
+                x, tab, target_type="rectified_flow", pred_type=self.prediction_type, use_snr_weight=False, use_debiased=False,
+                gamma=self.min_snr_gamma, eps=noise, timesteps=t_idx, seed=self.seed, offset=self._step, want_eps=False,
+                sigmas=sigmas)
+            t_unet = timesteps
+        self._step += 1
+        model_output = unet(x_t, t_unet, **unet_kwargs)[0]
+        # pred = pred_eps - pred_x0 with (x0, eps) recovered from the NOISY latents (rectified_flow.py:79-83)
+        pred = _PredConvert.apply(model_output, x_t, sigma, t_idx, tab["acp"], self.prediction_type, "rectified_flow")
+        loss, losses = _WeightedMSE.apply(pred, target, None)
+        aux = DiffusionLossAuxOutput(losses=losses, timesteps=t_unet, pred=pred, target=target, noisy_latent=x_t)
+        return loss, aux

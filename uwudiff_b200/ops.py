@@ -115,7 +115,7 @@ def conv3x3_nhwc(x: torch.Tensor, w_packed: torch.Tensor, *, x2: Optional[torch.
 def noise_fwd(x0: torch.Tensor, tables: dict, *, target_type: str, pred_type: str, use_snr_weight: bool,
               use_debiased: bool, gamma: float, eps: Optional[torch.Tensor] = None,
               timesteps: Optional[torch.Tensor] = None, seed: int = 0, offset: int = 0, temb_dim: int = 0,
-              want_eps: bool = True):
+              want_eps: bool = True, sigmas: Optional[torch.Tensor] = None):
     """One launch: (x_t, target, eps, t, sigma, w[2,B], temb). See uwu_noise_fwd."""
     _req_cuda(x0, eps, timesteps)
     if target_type not in _lib.TARGET_CODES:
@@ -140,6 +140,10 @@ def noise_fwd(x0: torch.Tensor, tables: dict, *, target_type: str, pred_type: st
     if timesteps is not None:
         timesteps = timesteps.to(device=dev, dtype=torch.int64).contiguous()
         d.t_in = _ptr(timesteps)
+    if sigmas is not None:
+        sigmas = sigmas.to(device=dev, dtype=torch.float32).contiguous()
+        assert sigmas.numel() == B
+        d.sigma_in = _ptr(sigmas)
     d.seed, d.offset = seed & (2**64 - 1), offset & (2**64 - 1)
     d.acp, d.sigma_t, d.snr = _ptr(tables["acp"]), _ptr(tables["sigma_t"]), _ptr(tables["snr"])
     d.T, d.B, d.n_per = tables["acp"].numel(), B, n_per
