@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) attn_fwd_kernel(const __grid_c
                     for (int k = 0; k < 8; ++k) {
                         const uint64_t ad = desc_kmajor(sp + t * 2 * AT_TILE + (k >> 2) * AT_TILE) + (uint64_t)((k & 3) * 2);
                         umma_bf16(tmem_base + 256u + (uint32_t)(t * 64), ad, vd + (uint64_t)(k * 128), idesc_pv,
-                                  (uint32_t)(k != 0));
+                                  (uint32_t)((j | k) != 0));  // O accumulates in TMEM over the whole key loop
                     }
                     umma_commit(&pv_full[t]);
                     if (has_next) {
@@ -181,9 +181,9 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) attn_fwd_kernel(const __grid_c
             const uint32_t prow_s = smem_u32(smem + FWD_SP + t * 2 * AT_TILE + row * 128);
             const int sw = row & 7;
             const float sl2 = p.scale_log2;
-            float O[64];
-#pragma unroll
-            for (int i = 0; i < 64; ++i) O[i] = 0.f;
+            // O lives in TMEM (the P V products accumulate there); m is the running maximum the probabilities are expressed
+            // against.  It is only advanced -- and O / l rescaled -- when the true row maximum has grown by more than 2^8
+            // (lazy rescaling): p <= 256 is harmless in bf16 / fp32 and the final O / l is exact for any reference maximum.
             float m = -INFINITY, l = 0.f;
             for (int j = 0; j < nkv; ++j) {
                 mbar_wait(&s_full[t], (uint32_t)(j & 1));
@@ -213,8 +213,27 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) attn_fwd_kernel(const __grid_c
                     }
                 }
                 const float m_new = fmaxf(m, mx);
-                const float alpha = ex2_approx((m - m_new) * sl2);
-                const float msl = m_new * sl2;
+                if (j == 0) {
+                    m = m_new;
+                } else if (__any_sync(0xffffffffu, (m_new - m) * sl2 > 8.0f)) {
+                    // rare: bring O (complete up to the previous key tile) and l to the new reference maximum
+                    mbar_wait(&pv_full[t], (uint32_t)((j - 1) & 1));
+                    tc_fence_after();
+                    const float alpha = ex2_approx((m - m_new) * sl2);
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        uint32_t r[32];
+                        tmem_ld32(t_pv + (uint32_t)(c * 32), r);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
+                        tmem_st32(t_pv + (uint32_t)(c * 32), r);
+                    }
+                    tmem_st_wait();
+                    l *= alpha;
+                    m = m_new;
+                }
+                const float msl = m * sl2;
                 // pass 2: probabilities -> bf16 -> swizzled smem, row sum; the TMEM load of chunk c+1 is in flight while
                 // chunk c is exponentiated
                 float rs = 0.f;
@@ -252,25 +271,25 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) attn_fwd_kernel(const __grid_c
                     }
                     if (c < 3) tmem_ld_wait();
                 }
-                l = fmaf(l, alpha, rs);
-                m = m_new;
+                l += rs;
                 tc_fence_before();
                 fence_proxy_async();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&p_full[t]);
-                // fold P V into the register accumulators
-                mbar_wait(&pv_full[t], (uint32_t)(j & 1));
-                tc_fence_after();
-                {
-                    uint32_t r0[32], r1[32];
-                    tmem_ld32(t_pv, r0);
-                    tmem_ld32(t_pv + 32u, r1);
-                    tmem_ld_wait();
+            }
+            // all products have landed: read O once
+            mbar_wait(&pv_full[t], (uint32_t)((nkv - 1) & 1));
+            tc_fence_after();
+            float O[64];
+            {
+                uint32_t r0[32], r1[32];
+                tmem_ld32(t_pv, r0);
+                tmem_ld32(t_pv + 32u, r1);
+                tmem_ld_wait();
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        O[i] = fmaf(O[i], alpha, __uint_as_float(r0[i]));
-                        O[32 + i] = fmaf(O[32 + i], alpha, __uint_as_float(r1[i]));
-                    }
+                for (int i = 0; i < 32; ++i) {
+                    O[i] = __uint_as_float(r0[i]);
+                    O[32 + i] = __uint_as_float(r1[i]);
                 }
             }
             const int q = q0 + t * 128 + row;
