@@ -199,11 +199,16 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) attn_fwd_kernel(const __grid_c
                     tmem_ld32(t_s + (uint32_t)(cp * 64 + 32), rb);
                     tmem_ld_wait();
                     if (full) {
+                        // four independent max chains (a single chain is a 4-cycle-latency dependency per element pair)
+                        float m0 = mx, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
 #pragma unroll
-                        for (int i = 0; i < 32; i += 2) {
-                            mx = fmax3(mx, __uint_as_float(ra[i]), __uint_as_float(ra[i + 1]));
-                            mx = fmax3(mx, __uint_as_float(rb[i]), __uint_as_float(rb[i + 1]));
+                        for (int i = 0; i < 32; i += 4) {
+                            m0 = fmax3(m0, __uint_as_float(ra[i]), __uint_as_float(ra[i + 1]));
+                            m1 = fmax3(m1, __uint_as_float(ra[i + 2]), __uint_as_float(ra[i + 3]));
+                            m2 = fmax3(m2, __uint_as_float(rb[i]), __uint_as_float(rb[i + 1]));
+                            m3 = fmax3(m3, __uint_as_float(rb[i + 2]), __uint_as_float(rb[i + 3]));
                         }
+                        mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
                     } else {
 #pragma unroll
                         for (int i = 0; i < 32; ++i) {
@@ -246,11 +251,19 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) attn_fwd_kernel(const __grid_c
                     const uint32_t(&r)[32] = rbuf[c & 1];
                     float pe[32];
                     if (full) {
+                        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;  // independent partial row sums (no serial FADD chain)
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) {
+                        for (int i = 0; i < 32; i += 4) {
                             pe[i] = ex2_approx(fmaf(__uint_as_float(r[i]), sl2, -msl));
-                            rs += pe[i];
+                            pe[i + 1] = ex2_approx(fmaf(__uint_as_float(r[i + 1]), sl2, -msl));
+                            pe[i + 2] = ex2_approx(fmaf(__uint_as_float(r[i + 2]), sl2, -msl));
+                            pe[i + 3] = ex2_approx(fmaf(__uint_as_float(r[i + 3]), sl2, -msl));
+                            s0 += pe[i];
+                            s1 += pe[i + 1];
+                            s2 += pe[i + 2];
+                            s3 += pe[i + 3];
                         }
+                        rs += (s0 + s1) + (s2 + s3);
                     } else {
 #pragma unroll
                         for (int i = 0; i < 32; ++i) {
