@@ -123,6 +123,39 @@ def test_rectified_flow_loss_matches_golden(golden, name):
     assert abs(loss.item() - float(golden[f"{name}/loss"])) <= 3e-4 * abs(float(golden[f"{name}/loss"]))
 
 
+def test_nn_weighted_rf_loss_matches_reference_formula(golden):
+    """NNWeightedRFLoss (rectified_flow.py:144-203): rf losses from the kernels, learned weighting as in the reference."""
+    from uwudiff_b200.loss import NNWeightedRFLoss
+    from uwudiff_b200.scheduler import EulerDiscreteScheduler
+
+    name = "rf_time_rf"
+    sch = EulerDiscreteScheduler.from_pretrained("stabilityai/stable-diffusion-xl-base-1.0", subfolder="scheduler",
+                                                 prediction_type="rectified_flow")
+
+    class Head(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.w = torch.nn.Parameter(torch.tensor(0.3))
+
+        def forward(self, x_t, sigmas, **kw):
+            return self.w * torch.log1p(sigmas) - 0.5
+
+    head = Head().cuda()
+    L = NNWeightedRFLoss(loss_pred_module=head, scheduler=sch, prediction_type="rectified_flow")
+    x_in = torch.from_numpy(golden[f"{name}/x_in"]).cuda()
+    noise = torch.from_numpy(golden[f"{name}/noise"]).cuda()
+    time = torch.from_numpy(golden[f"{name}/time"]).cuda()
+    loss, aux = L(x_in, lambda x, tt, **k: (0.5 * x,), noise=noise, time=time)
+    rf = torch.from_numpy(golden[f"{name}/losses"]).cuda()
+    sig = time / (1 - time)
+    lp = (0.3 * torch.log1p(sig) - 0.5)
+    ref = (rf / lp.exp().clamp(min=1e-4) + (rf.log() - lp).square()).mean()
+    np.testing.assert_allclose(aux.losses.detach().cpu().numpy(), golden[f"{name}/losses"], rtol=3e-4)
+    assert abs(loss.item() - ref.item()) <= 1e-3 * abs(ref.item())
+    loss.backward()
+    assert head.w.grad is not None and torch.isfinite(head.w.grad)
+
+
 def test_rectified_flow_loss_through_the_unet():
     """Fractional timesteps reach the denoiser's sinusoidal embedding; loss is finite and gradients flow to the adapters."""
     from conftest import LYCORIS_CFG, LYCORIS_PRESET

@@ -212,9 +212,48 @@ class RectifiedFlowLoss(DiffusionLoss):
                 sigmas=sigmas)
             t_unet = timesteps
         self._step += 1
+        self._last_sigmas = sigma
         model_output = unet(x_t, t_unet, **unet_kwargs)[0]
         # pred = pred_eps - pred_x0 with (x0, eps) recovered from the NOISY latents (rectified_flow.py:79-83)
         pred = _PredConvert.apply(model_output, x_t, sigma, t_idx, tab["acp"], self.prediction_type, "rectified_flow")
         loss, losses = _WeightedMSE.apply(pred, target, None)
         aux = DiffusionLossAuxOutput(losses=losses, timesteps=t_unet, pred=pred, target=target, noisy_latent=x_t)
         return loss, aux
+
+
+class NNWeightedRFLossAuxOutput(NamedTuple):
+    losses: torch.Tensor
+    rescaled_losses: torch.Tensor
+    pred_losses: torch.Tensor
+    loss_pred_losses: torch.Tensor
+    timesteps: torch.Tensor
+    pred: torch.Tensor
+    target: torch.Tensor
+    noisy_latent: torch.Tensor
+
+
+class NNWeightedRFLoss(RectifiedFlowLoss):
+    """Drop-in for `duwu.loss.NNWeightedRFLoss` (src/duwu/loss/rectified_flow.py:144-203): the rectified-flow loss of each
+    sample is divided by a learned prediction of itself (`loss_pred_module(noisy_latent, sigmas, **unet_kwargs)` returns the
+    log-loss), plus the squared log-error of that prediction.  The heavy part (noising, denoiser, conversion, per-sample MSE)
+    runs in the same kernels as RectifiedFlowLoss; the per-sample weighting is B-element host-side torch arithmetic."""
+
+    def __init__(self, loss_pred_module: nn.Module, **kwargs):
+        super().__init__(**kwargs)
+        self.loss_pred_module = loss_pred_module
+
+    def forward(self, x: torch.Tensor, unet: nn.Module, *, noise: Optional[torch.Tensor] = None,
+                time: Optional[torch.Tensor] = None, timesteps: Optional[torch.Tensor] = None, **unet_kwargs):
+        _, aux = super().forward(x, unet, noise=noise, time=time, timesteps=timesteps, **unet_kwargs)
+        rf_losses = aux.losses
+        sigmas = self._last_sigmas
+        log_ls_pred = self.loss_pred_module(aux.noisy_latent, sigmas.flatten(), **unet_kwargs).flatten()
+        log_ls = rf_losses.detach().log()
+        ls_pred_loss = (log_ls - log_ls_pred).square()
+        pred_loss = log_ls_pred.detach().exp().clamp(min=1e-4)
+        rescaled_losses = rf_losses / pred_loss
+        losses = rescaled_losses + ls_pred_loss
+        out = NNWeightedRFLossAuxOutput(losses=rf_losses, rescaled_losses=rescaled_losses, pred_losses=pred_loss,
+                                        loss_pred_losses=ls_pred_loss, timesteps=aux.timesteps, pred=aux.pred, target=aux.target,
+                                        noisy_latent=aux.noisy_latent)
+        return losses.mean(), out
