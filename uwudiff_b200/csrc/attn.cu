@@ -153,6 +153,12 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) attn_fwd_kernel(const __grid_c
                 for (int t = 0; t < ntiles; ++t) {
                     mbar_wait(&p_full[t], (uint32_t)(j & 1));
                     tc_fence_after();
+                    // S(t, j) has been consumed: the next scores go first, they are what the softmax warps wait for;
+                    // nobody waits for P V (O lives in TMEM) except the P-buffer reuse guard below
+                    if (has_next) {
+                        issue_qk(t, s1);
+                        umma_commit(&s_full[t]);
+                    }
                     const uint64_t vd = desc_mnmajor(sv + s * AT_TILE, 8192);
 #pragma unroll
                     for (int k = 0; k < 8; ++k) {
@@ -161,10 +167,6 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) attn_fwd_kernel(const __grid_c
                                   (uint32_t)((j | k) != 0));  // O accumulates in TMEM over the whole key loop
                     }
                     umma_commit(&pv_full[t]);
-                    if (has_next) {
-                        issue_qk(t, s1);
-                        umma_commit(&s_full[t]);
-                    }
                 }
                 umma_commit(&v_empty[s]);
                 if (has_next) umma_commit(&k_empty[s1]);
@@ -239,6 +241,8 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) attn_fwd_kernel(const __grid_c
                     m = m_new;
                 }
                 const float msl = m * sl2;
+                // the P V product of the previous key tile must have finished reading the P buffer before it is overwritten
+                if (j > 0) mbar_wait(&pv_full[t], (uint32_t)((j - 1) & 1));
                 // pass 2: probabilities -> bf16 -> swizzled smem, row sum; the TMEM load of chunk c+1 is in flight while
                 // chunk c is exponentiated
                 float rs = 0.f;
