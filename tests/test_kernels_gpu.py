@@ -182,19 +182,19 @@ ATTN_SHAPES = [(1, 1, 128, 128), (1, 1, 256, 128), (1, 1, 128, 256), (2, 3, 256,
                (2, 5, 256, 77), (1, 2, 320, 200)]
 
 
-def attn_ref(q, k, v, B, heads, Lq, Lk, dout=None):
+def attn_ref(q, k, v, B, heads, Lq, Lk, dout=None, d=64):
     def split(t, L):
-        return t.float().reshape(B, L, heads, 64).transpose(1, 2).detach().requires_grad_(True)
+        return t.float().reshape(B, L, heads, d).transpose(1, 2).detach().requires_grad_(True)
 
     qf, kf, vf = split(q, Lq), split(k, Lk), split(v, Lk)
-    s = (qf @ kf.transpose(-1, -2)) * 0.125
+    s = (qf @ kf.transpose(-1, -2)) * d ** -0.5
     o = torch.softmax(s, dim=-1) @ vf
     lse = torch.logsumexp(s, dim=-1)
-    o2 = o.transpose(1, 2).reshape(B * Lq, heads * 64)
+    o2 = o.transpose(1, 2).reshape(B * Lq, heads * d)
     if dout is None:
         return o2.detach(), lse.detach()
     o2.backward(dout.float())
-    back = lambda t, L: t.grad.transpose(1, 2).reshape(B * L, heads * 64)  # noqa: E731
+    back = lambda t, L: t.grad.transpose(1, 2).reshape(B * L, heads * d)  # noqa: E731
     return o2.detach(), lse.detach(), back(qf, Lq), back(kf, Lk), back(vf, Lk)
 
 
@@ -226,6 +226,44 @@ def test_attention_backward(ops, B, heads, Lq, Lk):
     dq, dk, dv = ops.attn_bwd(q, k, v, o, do, lse, B, heads, Lq, Lk)
     _, _, rdq, rdk, rdv = attn_ref(q, k, v, B, heads, Lq, Lk, do)
     assert relerr(dq, rdq) < TOL_ATTN and relerr(dk, rdk) < TOL_ATTN and relerr(dv, rdv) < TOL_ATTN
+
+
+# head dims other than 64 (SD-1.5: 40 / 80 / 160, DiT-XL/2: 72) run on the mma.sync kernels of attn_any.cu
+ATTN_ANY_SHAPES = [(2, 8, 256, 256, 40), (1, 8, 1024, 1024, 40), (2, 8, 256, 77, 80), (2, 4, 64, 64, 160), (1, 2, 200, 77, 160),
+                   (3, 16, 256, 256, 72), (1, 3, 130, 70, 72), (1, 2, 320, 200, 128), (2, 2, 96, 96, 32), (1, 1, 64, 64, 8)]
+
+
+@pytest.mark.parametrize("B,heads,Lq,Lk,d", ATTN_ANY_SHAPES)
+def test_attention_any_head_dim(ops, B, heads, Lq, Lk, d):
+    C = heads * d
+    q, k, v, do = mk(B * Lq, C, s=1.0), mk(B * Lk, C, s=1.0), mk(B * Lk, C, s=1.0), mk(B * Lq, C, s=1.0)
+    o, lse = ops.attn_fwd(q, k, v, B, heads, Lq, Lk, head_dim=d)
+    dq, dk, dv = ops.attn_bwd(q, k, v, o, do, lse, B, heads, Lq, Lk, head_dim=d)
+    ro, rlse, rdq, rdk, rdv = attn_ref(q, k, v, B, heads, Lq, Lk, do, d=d)
+    assert relerr(o, ro) < TOL_ATTN
+    Lp = (Lq + 127) // 128 * 128
+    assert relerr(lse.view(B, heads, Lp)[:, :, :Lq], rlse) < 1e-4
+    assert relerr(dq, rdq) < TOL_ATTN and relerr(dk, rdk) < TOL_ATTN and relerr(dv, rdv) < TOL_ATTN
+
+
+def test_attention_any_strided_qkv(ops):
+    B, heads, L, d = 2, 8, 192, 40
+    C = heads * d
+    qkv = mk(B * L, 3 * C, s=1.0)
+    do = mk(B * L, C, s=1.0)
+    q, k, v = qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:]
+    o, lse = ops.attn_fwd(q, k, v, B, heads, L, L, head_dim=d)
+    dqkv = torch.empty_like(qkv)
+    ops.attn_bwd(q, k, v, o, do, lse, B, heads, L, L, head_dim=d, dq=dqkv[:, :C], dk=dqkv[:, C:2 * C], dv=dqkv[:, 2 * C:])
+    ro, _, rdq, rdk, rdv = attn_ref(q.contiguous(), k.contiguous(), v.contiguous(), B, heads, L, L, do, d=d)
+    assert relerr(o, ro) < TOL_ATTN
+    assert relerr(dqkv, torch.cat([rdq, rdk, rdv], dim=1)) < TOL_ATTN
+
+
+def test_attention_rejects_bad_head_dim(ops):
+    q = mk(128, 36, s=1.0)
+    with pytest.raises((ValueError, RuntimeError, NotImplementedError)):
+        ops.attn_fwd(q, q, q, 1, 1, 128, 128, head_dim=36)
 
 
 # ------------------------------------------------------------------------------------------------------------------

@@ -738,13 +738,21 @@ static int make_head_map(CUtensorMap* tm, const void* base, int heads, int L, in
     return encode_tmap_bf16(tm, base, 3, dims, str, box, 1);
 }
 
+// mma.sync kernels for head dims other than 64 (attn_any.cu)
+int attn_any_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int B, int heads, int Lq, int Lk, int d,
+                 long long ldq, long long ldk, long long ldv, long long ldo, float scale, cudaStream_t stream);
+int attn_any_bwd(const void* q, const void* k, const void* v, const void* o, const void* dout, const float* lse, void* dq,
+                 void* dk, void* dv, int B, int heads, int Lq, int Lk, int d, long long ldq, long long ldk, long long ldv,
+                 long long ldo, long long lddo, long long lddq, long long lddk, long long lddv, float scale, float* workspace,
+                 cudaStream_t stream);
+
 }  // namespace uwu
 
 using namespace uwu;
 
 static int attn_check(int32_t B, int32_t heads, int32_t Lq, int32_t Lk, int32_t head_dim) {
-    if (head_dim != 64) {
-        set_error("uwu_attn: head_dim %d unsupported (this build has the d=64 kernels only)", head_dim);
+    if (head_dim <= 0 || head_dim % 8 != 0 || head_dim > 160) {
+        set_error("uwu_attn: head_dim %d unsupported (64 on tcgen05; other multiples of 8 up to 160 on mma.sync)", head_dim);
         return UWU_ERR_UNSUPPORTED;
     }
     UWU_CHECK_ARG(B > 0 && heads > 0 && Lq > 0 && Lk > 0, "uwu_attn: bad shape B=%d heads=%d Lq=%d Lk=%d", B, heads, Lq, Lk);
@@ -764,6 +772,7 @@ extern "C" int uwu_attn_fwd(const void* q, const void* k, const void* v, void* o
     if (int rc = attn_check(B, heads, Lq, Lk, head_dim)) return rc;
     UWU_CHECK_ARG(q && k && v && o && lse, "uwu_attn_fwd: null pointer");
     UWU_CHECK_ARG(ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(o) & 15) == 0, "uwu_attn_fwd: output must be 16-byte aligned");
+    if (head_dim != 64) return attn_any_fwd(q, k, v, o, lse, B, heads, Lq, Lk, head_dim, ldq, ldk, ldv, ldo, scale, stream);
     static thread_local AttnFwdArgs a;
     if (int rc = make_head_map(&a.tmQ, q, heads, Lq, B, ldq, "q")) return rc;
     if (int rc = make_head_map(&a.tmK, k, heads, Lk, B, ldk, "k")) return rc;
@@ -811,6 +820,9 @@ extern "C" int uwu_attn_bwd(const void* q, const void* k, const void* v, const v
                     reinterpret_cast<uintptr_t>(dk) | reinterpret_cast<uintptr_t>(dv) |
                     reinterpret_cast<uintptr_t>(workspace)) & 15) == 0,
                   "uwu_attn_bwd: pointers must be 16-byte aligned");
+    if (head_dim != 64)
+        return attn_any_bwd(q, k, v, o, dout, lse, dq, dk, dv, B, heads, Lq, Lk, head_dim, ldq, ldk, ldv, ldo, lddo, lddq, lddk,
+                            lddv, scale, workspace, stream);
     const int Lq_pad = (Lq + 127) / 128 * 128;
     const int64_t rows = (int64_t)B * heads * Lq_pad;
     float* lse2 = workspace;
