@@ -284,3 +284,13 @@ def test_trainer_fit_step_loss_matches_oracle(fake_ops, monkeypatch):
     assert not torch.equal(before, tr.lycoris_model.flat_params)  # the optimizer moved the adapters
     assert float(tr.lycoris_model.flat_grads.abs().sum()) == 0.0  # zero_grad keeps the flat buffer
     assert tr.global_step == 1 and float(tr.ema_loss) > 0
+
+
+def test_sd15_known_config_builds_on_meta():
+    from uwudiff_b200 import unet as P
+
+    with torch.device("meta"):
+        m = P.UNet2DConditionModel(**P.UNet2DConditionModel.load_config("runwayml/stable-diffusion-v1-5", subfolder="unet"))
+    n = sum(q.numel() for q in m.parameters())
+    assert abs(n - 859_520_964) < 1000, n   # public parameter count of the SD-1.5 UNet
+    assert m.mid_block.attentions[0].transformer_blocks[0].attn1.dim_head == 160

@@ -204,6 +204,54 @@ def test_full_finetune_all_parameter_gradients_match_oracle():
     assert dot / (num ** 0.5 * den ** 0.5) > 0.995
 
 
+SD15_TINY = dict(sample_size=16, block_out_channels=(64, 128, 320, 320),
+                 down_block_types=("CrossAttnDownBlock2D", "CrossAttnDownBlock2D", "CrossAttnDownBlock2D", "DownBlock2D"),
+                 up_block_types=("UpBlock2D", "CrossAttnUpBlock2D", "CrossAttnUpBlock2D", "CrossAttnUpBlock2D"),
+                 layers_per_block=1, transformer_layers_per_block=1, attention_head_dim=(8, 8, 4, 2), cross_attention_dim=96,
+                 use_linear_projection=False, addition_embed_type=None, addition_time_embed_dim=None,
+                 projection_class_embeddings_input_dim=None)
+
+
+def test_sd15_style_unet_full_finetune_matches_oracle():
+    """C2 family (SD-1.5 layout): four levels, 1x1-conv proj_in / proj_out, no added conditioning, head dims 8 / 16 / 80 /
+    160 (the non-64 widths run on the mma.sync attention kernels); forward + every parameter gradient vs the oracle."""
+    from uwudiff_b200 import unet as P
+
+    torch.manual_seed(11)
+    o = U.UNet2DConditionModel(**SD15_TINY)
+    p = P.UNet2DFromScratch.from_config(SD15_TINY)
+    p.load_state_dict(o.state_dict())
+    p = p.cuda()
+    assert p.down_blocks[0].attentions[0].proj_in.weight.shape == (64, 64, 1, 1)
+    B, HW = 2, 16
+    x, t, ctx = torch.randn(B, 4, HW, HW), torch.randint(0, 1000, (B,)), torch.randn(B, 77, 96)
+    o.requires_grad_(True)
+    p.requires_grad_(True)
+    gout = torch.randn(x.shape, generator=torch.Generator().manual_seed(2))
+    yo = o(x, t, encoder_hidden_states=ctx)[0]
+    yo.backward(gout)
+    yp = p(x.cuda(), t.cuda(), encoder_hidden_states=ctx.cuda())[0]
+    yp.backward(gout.cuda())
+    torch.cuda.synchronize()
+    assert rel(yp, yo) < 3e-2
+    po = dict(o.named_parameters())
+    assert not [n for n, q in p.named_parameters() if q.grad is None]
+    worst, worst_name = 0.0, ""
+    num = den = dot = 0.0
+    for n, q in p.named_parameters():
+        go, gp = po[n].grad.float(), q.grad.float().cpu()
+        assert gp.shape == go.shape, n
+        r = rel(gp, go)
+        if r > worst:
+            worst, worst_name = r, n
+        num += (gp * gp).sum().item()
+        den += (go * go).sum().item()
+        dot += (gp * go).sum().item()
+    assert worst < 1.5e-1, (worst, worst_name)
+    assert abs(num ** 0.5 - den ** 0.5) / den ** 0.5 < 2e-2
+    assert dot / (num ** 0.5 * den ** 0.5) > 0.995
+
+
 def test_c1_pixel_unet_full_training_step_matches_oracle():
     """BASELINE.json configs[0]: tiny pixel-space UNet, batch 4 at 3x32x32, eps-prediction plain MSE, every weight trained.
     Loss within 1e-2 of the fp32 oracle (bf16 compute), x_t / target bit-exact, gradient direction cos > 0.995."""

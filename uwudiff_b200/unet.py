@@ -41,7 +41,19 @@ SDXL_UNET_CONFIG = dict(
     act_fn="silu", flip_sin_to_cos=True, freq_shift=0,
 )
 # public config.json constants of the checkpoints the reference configs name (the HF hub is unreachable here)
-KNOWN_UNET_CONFIGS = {"stabilityai/stable-diffusion-xl-base-1.0": SDXL_UNET_CONFIG}
+# SD-1.5: 8 heads per attention (head dims 40 / 80 / 160 / 160), 1x1-conv proj_in / proj_out, no added conditioning
+SD15_UNET_CONFIG = dict(
+    in_channels=4, out_channels=4, sample_size=64, block_out_channels=(320, 640, 1280, 1280),
+    down_block_types=("CrossAttnDownBlock2D", "CrossAttnDownBlock2D", "CrossAttnDownBlock2D", "DownBlock2D"),
+    up_block_types=("UpBlock2D", "CrossAttnUpBlock2D", "CrossAttnUpBlock2D", "CrossAttnUpBlock2D"),
+    layers_per_block=2, transformer_layers_per_block=1, attention_head_dim=8,
+    cross_attention_dim=768, use_linear_projection=False, addition_embed_type=None,
+    addition_time_embed_dim=None, projection_class_embeddings_input_dim=None,
+    norm_num_groups=32, norm_eps=1e-5, act_fn="silu", flip_sin_to_cos=True, freq_shift=0,
+)
+KNOWN_UNET_CONFIGS = {"stabilityai/stable-diffusion-xl-base-1.0": SDXL_UNET_CONFIG,
+                      "runwayml/stable-diffusion-v1-5": SD15_UNET_CONFIG,
+                      "stable-diffusion-v1-5/stable-diffusion-v1-5": SD15_UNET_CONFIG}
 
 
 # Adapter folds are batched into one launch per forward (LycorisNetwork.fold_all): `epoch` marks operands folded for the
@@ -87,21 +99,25 @@ class Linear(nn.Linear, _Cached):
         if self._dst_override is not None:
             return self._dst_override
         if getattr(self, "_cache", None) is None:
-            self._cache = torch.empty(self.weight.shape, device=self.weight.device, dtype=BF16)
+            self._cache = torch.empty((self.out_features, self.in_features), device=self.weight.device, dtype=BF16)
         return self._cache
+
+    def _w2d(self) -> torch.Tensor:
+        w = self.weight
+        return w if w.dim() == 2 else w.view(w.shape[0], -1)  # Conv1x1Proj keeps the conv parameter shape
 
     def w16(self, dst: Optional[torch.Tensor] = None) -> torch.Tensor:
         if dst is None:
             if not self._needs_refresh():
                 return self._cache
             if getattr(self, "_cache", None) is None:
-                self._cache = torch.empty(self.weight.shape, device=self.weight.device, dtype=BF16)
+                self._cache = torch.empty((self.out_features, self.in_features), device=self.weight.device, dtype=BF16)
             dst = self._cache
         ad = self._uwu_adapter
         if ad is None:
-            ops.fold_lokr(self.weight, None, None, dst)
+            ops.fold_lokr(self._w2d(), None, None, dst)
         else:
-            ad.fold_into(self.weight, dst)
+            ad.fold_into(self._w2d(), dst)
         return dst
 
     def fwd(self, x, M, *, residual=None, out=None, out_dtype=BF16):
@@ -120,7 +136,7 @@ class Linear(nn.Linear, _Cached):
         ad = self._uwu_adapter
         N, K = self.out_features, self.in_features
         if self.weight.requires_grad:
-            g = _grad_of(self.weight)
+            g = _grad_of(self.weight).view(N, K)
             ops.gemm(dy, x, N, K, M, a_layout=A_COL, lda=dy.stride(0), b_layout=B_KN, ldb=x.stride(0), out=g, accumulate=True)
         if self.bias is not None and self.bias.requires_grad:
             ops.colsum(dy, out=_grad_of(self.bias), accumulate=True)
@@ -131,6 +147,15 @@ class Linear(nn.Linear, _Cached):
             G = ops._workspace(N * K, dy.device, "wgrad")[: N * K].view(N, K)
             ops.gemm(dy, x, N, K, M, a_layout=A_COL, lda=dy.stride(0), b_layout=B_KN, ldb=x.stride(0), out=G)
             ad.grads_from(G)
+
+
+class Conv1x1Proj(Linear):
+    """`Transformer2DModel.proj_in / proj_out` when `use_linear_projection=False` (SD-1.5): a 1x1 convolution, i.e. the
+    same GEMM over channels-last tokens.  The parameter keeps the conv shape [out, in, 1, 1] so diffusers state_dicts load."""
+
+    def __init__(self, in_features: int, out_features: int):
+        super().__init__(in_features, out_features)
+        self.weight = nn.Parameter(self.weight.data.view(out_features, in_features, 1, 1))
 
 
 def _fused_param_grads(mods, dy, x, M):
@@ -524,16 +549,15 @@ class Transformer2DModel(nn.Module):
     def __init__(self, heads: int, dim_head: int, in_channels: int, num_layers: int, cross_attention_dim: int,
                  norm_num_groups: int = 32, use_linear_projection: bool = True):
         super().__init__()
-        if not use_linear_projection:
-            raise NotImplementedError("uwudiff_b200: use_linear_projection=False (SD-1.5 conv projections) is not built yet")
-        if dim_head != 64:
-            raise NotImplementedError(f"uwudiff_b200: attention head_dim {dim_head} unsupported (d=64 kernels only)")
+        if dim_head % 8 != 0 or dim_head > 160:
+            raise NotImplementedError(f"uwudiff_b200: attention head_dim {dim_head} unsupported (multiples of 8 up to 160)")
         inner = heads * dim_head
+        proj = Linear if use_linear_projection else Conv1x1Proj
         self.norm = GroupNorm(norm_num_groups, in_channels, eps=1e-6)
-        self.proj_in = Linear(in_channels, inner)
+        self.proj_in = proj(in_channels, inner)
         self.transformer_blocks = nn.ModuleList(
             [BasicTransformerBlock(inner, heads, dim_head, cross_attention_dim) for _ in range(num_layers)])
-        self.proj_out = Linear(inner, in_channels)
+        self.proj_out = proj(inner, in_channels)
 
     def fwd(self, x, st):
         N, HW = st.N, st.H * st.W
