@@ -11,6 +11,7 @@ import os
 import sys
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import torch
 
 import bench
@@ -19,7 +20,8 @@ from uwudiff_b200 import ops
 
 WRAP = ["gemm", "noise_fwd", "sincos_embed", "wmse_fwd", "wmse_bwd", "attn_fwd", "attn_bwd", "groupnorm_fwd", "groupnorm_bwd",
         "layernorm_fwd", "layernorm_bwd", "geglu_fwd", "geglu_bwd", "elementwise", "nchw_to_nhwc", "nhwc_to_nchw", "upsample2x",
-        "phase_split2", "colsum", "fold_lokr", "fold_lora", "axpy_f32", "lokr_grad", "lora_grad", "copy2d", "lokr_z", "lokr_dw1"]
+        "phase_split2", "colsum", "fold_lokr", "fold_lora", "axpy_f32", "lokr_grad", "lora_grad", "copy2d", "lokr_z", "lokr_dw1",
+        "im2col3x3", "conv_wgrad_unpack", "colsum_groups", "pred_convert"]
 
 
 def main():
@@ -27,13 +29,21 @@ def main():
     ap.add_argument("--batch", type=int, default=16)
     ap.add_argument("--latent", type=int, default=128)
     ap.add_argument("--top", type=int, default=45)
+    ap.add_argument("--config", default="c3", choices=["c3", "c1", "c2", "latent"], help="c3 = bench.py headline workload")
     args = ap.parse_args()
     dev = torch.device("cuda")
-    conf = bench.trainer_config(args.latent, args.batch)
+    shape = (4, args.latent, args.latent)
+    if args.config == "c3":
+        conf = bench.trainer_config(args.latent, args.batch)
+    else:
+        import bench_configs
+
+        args.batch = {"c1": 4, "c2": 32, "latent": 16}[args.config]
+        conf, _, shape, _ = bench_configs.make_conf(args.config, args.batch)
     trainer = ucfg.instantiate_any(conf["trainer"])
     trainer.setup_fit(gradient_clip_val=1.0, seed=1215)
     B, S = args.batch, args.latent
-    batch = (torch.randn((B, 4, S, S), device=dev), ["DUMMY TEST"] * B, [],
+    batch = (torch.randn((B, *shape), device=dev), ["DUMMY TEST"] * B, [],
              {"time_ids": torch.tensor([[1024., 1024, 0, 0, 1024, 1024]] * B, device=dev)}, {})
     for i in range(3):
         trainer.fit_step(batch, i)
@@ -55,8 +65,9 @@ def main():
                 fl = 2.0 * M * N * K
             elif name in ("attn_fwd", "attn_bwd"):
                 Bq, h, Lq, Lk = a[3:7] if name == "attn_fwd" else a[6:10]
-                key = f"{name} B{Bq} h{h} Lq{Lq} Lk{Lk}"
-                fl = 4.0 * Bq * h * Lq * Lk * 64 * (1.0 if name == "attn_fwd" else 2.5)
+                hd = k.get("head_dim", 64)
+                key = f"{name} B{Bq} h{h} Lq{Lq} Lk{Lk} d{hd}"
+                fl = 4.0 * Bq * h * Lq * Lk * hd * (1.0 if name == "attn_fwd" else 2.5)
             else:
                 t0 = next((t for t in a if torch.is_tensor(t)), None)
                 if t0 is not None:

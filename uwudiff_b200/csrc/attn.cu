@@ -40,8 +40,9 @@ UWU_DEVINL uint64_t desc_mnmajor(uint32_t saddr, uint32_t lbo) { return make_sme
 // forward
 // ================================================================================================
 struct AttnFwdArgs {
-    CUtensorMap tmQ, tmK, tmV;
+    CUtensorMap tmQ, tmK, tmV;  // 4-D (head_dim, heads, L, B); boxes are 64 wide, columns >= head_dim read as zero
     int Lq, Lk, heads, Lq_pad;
+    int hd;  // head dim (multiple of 8, <= 64): narrower heads run zero-padded to the 64-wide tiles
     float scale, scale_log2;
     __nv_bfloat16* o;
     long long ldo;
@@ -109,17 +110,17 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) attn_fwd_kernel(const __grid_c
     if (warp == 0) {
         if (lane == 0) {
             mbar_expect_tx(q_full, (uint32_t)(ntiles * AT_TILE));
-            tma_load_3d(smem + FWD_SQ, &p.tmQ, q_full, h * 64, q0, b);
-            if (ntiles == 2) tma_load_3d(smem + FWD_SQ + AT_TILE, &p.tmQ, q_full, h * 64, q0 + 128, b);
+            tma_load_4d(smem + FWD_SQ, &p.tmQ, q_full, 0, h, q0, b);
+            if (ntiles == 2) tma_load_4d(smem + FWD_SQ + AT_TILE, &p.tmQ, q_full, 0, h, q0 + 128, b);
             for (int j = 0; j < nkv; ++j) {
                 const int s = j % FWD_ST;
                 const uint32_t ph = (uint32_t)((j / FWD_ST) & 1);
                 mbar_wait(&k_empty[s], ph ^ 1);
                 mbar_expect_tx(&k_full[s], AT_TILE);
-                tma_load_3d(smem + FWD_SK + s * AT_TILE, &p.tmK, &k_full[s], h * 64, j * 128, b);
+                tma_load_4d(smem + FWD_SK + s * AT_TILE, &p.tmK, &k_full[s], 0, h, j * 128, b);
                 mbar_wait(&v_empty[s], ph ^ 1);
                 mbar_expect_tx(&v_full[s], AT_TILE);
-                tma_load_3d(smem + FWD_SV + s * AT_TILE, &p.tmV, &v_full[s], h * 64, j * 128, b);
+                tma_load_4d(smem + FWD_SV + s * AT_TILE, &p.tmV, &v_full[s], 0, h, j * 128, b);
             }
         }
     } else if (warp == 1) {
@@ -312,9 +313,10 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) attn_fwd_kernel(const __grid_c
             const int q = q0 + t * 128 + row;
             if (q < p.Lq) {
                 const float inv = 1.0f / l;
-                __nv_bfloat16* op = p.o + ((size_t)b * p.Lq + q) * p.ldo + h * 64;
+                __nv_bfloat16* op = p.o + ((size_t)b * p.Lq + q) * p.ldo + h * p.hd;
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
+                    if (c * 8 >= p.hd) break;
                     uint4 u;
                     u.x = pack_bf16(O[c * 8 + 0] * inv, O[c * 8 + 1] * inv);
                     u.y = pack_bf16(O[c * 8 + 2] * inv, O[c * 8 + 3] * inv);
@@ -339,7 +341,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) attn_fwd_kernel(const __grid_c
 // ================================================================================================
 // delta[b,h,q] = sum_d O[q,d] dO[q,d];  lse2 = lse * log2(e)
 __global__ void attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ o, long long ldo, const __nv_bfloat16* __restrict__ dout,
-                                     long long lddo, const float* __restrict__ lse, int B, int heads, int Lq, int Lq_pad,
+                                     long long lddo, const float* __restrict__ lse, int B, int heads, int Lq, int Lq_pad, int hd,
                                      float* __restrict__ lse2, float* __restrict__ delta) {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long total = (long long)B * Lq * heads;
@@ -348,11 +350,12 @@ __global__ void attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ o, long l
     const long long bq = idx / heads;
     const int q = (int)(bq % Lq);
     const int b = (int)(bq / Lq);
-    const __nv_bfloat16* op = o + bq * ldo + h * 64;
-    const __nv_bfloat16* dp = dout + bq * lddo + h * 64;
+    const __nv_bfloat16* op = o + bq * ldo + h * hd;
+    const __nv_bfloat16* dp = dout + bq * lddo + h * hd;
     float acc = 0.f;
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
+        if (c * 8 >= hd) break;
         const uint4 a = *reinterpret_cast<const uint4*>(op + c * 8);
         const uint4 d = *reinterpret_cast<const uint4*>(dp + c * 8);
         const float2 a0 = unpack_bf16(a.x), a1 = unpack_bf16(a.y), a2 = unpack_bf16(a.z), a3 = unpack_bf16(a.w);
@@ -365,12 +368,13 @@ __global__ void attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ o, long l
 }
 
 // dq[b*Lq+q, 64h+d] = scale * acc[b,h,q/128, d/4, q%128, d%4]   (single-pass backward: fp32 dQ scratch -> bf16)
-__global__ void attn_bwd_dq_convert_kernel(const float* __restrict__ acc, int B, int heads, int Lq, int nqt, float scale,
+__global__ void attn_bwd_dq_convert_kernel(const float* __restrict__ acc, int B, int heads, int Lq, int nqt, float scale, int hd,
                                            __nv_bfloat16* __restrict__ dq, long long lddq) {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // one 8-wide d chunk per thread
     const long long total = (long long)B * Lq * heads * 8;
     if (idx >= total) return;
     const int c8 = (int)(idx & 7);
+    if (c8 * 8 >= hd) return;
     long long r = idx >> 3;
     const int h = (int)(r % heads);
     r /= heads;
@@ -384,7 +388,7 @@ __global__ void attn_bwd_dq_convert_kernel(const float* __restrict__ acc, int B,
     u.y = pack_bf16(f0.z * scale, f0.w * scale);
     u.z = pack_bf16(f1.x * scale, f1.y * scale);
     u.w = pack_bf16(f1.z * scale, f1.w * scale);
-    *reinterpret_cast<uint4*>(dq + ((size_t)b * Lq + q) * lddq + h * 64 + c8 * 8) = u;
+    *reinterpret_cast<uint4*>(dq + ((size_t)b * Lq + q) * lddq + h * hd + c8 * 8) = u;
 }
 
 struct AttnBwdArgs {
@@ -400,6 +404,7 @@ struct AttnBwdArgs {
     long long lddk;
     __nv_bfloat16* dv;
     long long lddv;
+    int hd;  // head dim (multiple of 8, <= 64)
 };
 
 // Shared-memory plan: two resident operand tiles, kStages x two streamed operand tiles, P / dS tiles.
@@ -492,15 +497,15 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_kernel(const __grid_c
             const CUtensorMap* tmS0 = kDQ ? &p.tmK : &p.tmQ;
             const CUtensorMap* tmS1 = kDQ ? &p.tmV : &p.tmdO;
             mbar_expect_tx(res_full, 2 * AT_TILE);
-            tma_load_3d(smem + BWD_SR0, tmR0, res_full, h * 64, r0, b);
-            tma_load_3d(smem + BWD_SR1, tmR1, res_full, h * 64, r0, b);
+            tma_load_4d(smem + BWD_SR0, tmR0, res_full, 0, h, r0, b);
+            tma_load_4d(smem + BWD_SR1, tmR1, res_full, 0, h, r0, b);
             int s = 0;
             uint32_t ph = 0;
             for (int i = 0; i < n_iter; ++i) {
                 mbar_wait(&st_empty[s], ph ^ 1);
                 mbar_expect_tx(&st_full[s], 2 * AT_TILE);
-                tma_load_3d(smem + Cfg::SS0 + s * AT_TILE, tmS0, &st_full[s], h * 64, i * 128, b);
-                tma_load_3d(smem + Cfg::SS1 + s * AT_TILE, tmS1, &st_full[s], h * 64, i * 128, b);
+                tma_load_4d(smem + Cfg::SS0 + s * AT_TILE, tmS0, &st_full[s], 0, h, i * 128, b);
+                tma_load_4d(smem + Cfg::SS1 + s * AT_TILE, tmS1, &st_full[s], 0, h, i * 128, b);
                 if (++s == kStages) {
                     s = 0;
                     ph ^= 1;
@@ -685,9 +690,10 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_kernel(const __grid_c
             tmem_ld16(tmem_base + lane_addr + 320u + (uint32_t)(quarter * 16), v);
             tmem_ld_wait();
             if (r < p.Lq) {
-                __nv_bfloat16* op = p.dq + ((size_t)b * p.Lq + r) * p.lddq + h * 64 + quarter * 16;
+                __nv_bfloat16* op = p.dq + ((size_t)b * p.Lq + r) * p.lddq + h * p.hd + quarter * 16;
 #pragma unroll
                 for (int c = 0; c < 2; ++c) {
+                    if (quarter * 16 + c * 8 >= p.hd) break;
                     uint4 u;
                     u.x = pack_bf16(__uint_as_float(v[c * 8 + 0]) * p.scale, __uint_as_float(v[c * 8 + 1]) * p.scale);
                     u.y = pack_bf16(__uint_as_float(v[c * 8 + 2]) * p.scale, __uint_as_float(v[c * 8 + 3]) * p.scale);
@@ -705,9 +711,10 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_kernel(const __grid_c
                 if (r < p.Lk) {
                     const float sc = which ? p.scale : 1.0f;
                     __nv_bfloat16* base = which ? p.dk + ((size_t)b * p.Lk + r) * p.lddk : p.dv + ((size_t)b * p.Lk + r) * p.lddv;
-                    __nv_bfloat16* op = base + h * 64 + quarter * 16;
+                    __nv_bfloat16* op = base + h * p.hd + quarter * 16;
 #pragma unroll
                     for (int c = 0; c < 2; ++c) {
+                        if (quarter * 16 + c * 8 >= p.hd) break;
                         uint4 u;
                         u.x = pack_bf16(__uint_as_float(v[c * 8 + 0]) * sc, __uint_as_float(v[c * 8 + 1]) * sc);
                         u.y = pack_bf16(__uint_as_float(v[c * 8 + 2]) * sc, __uint_as_float(v[c * 8 + 3]) * sc);
@@ -727,15 +734,17 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_kernel(const __grid_c
     }
 }
 
-static int make_head_map(CUtensorMap* tm, const void* base, int heads, int L, int B, long long ld, const char* what) {
-    if (ld % 8 != 0 || ld < (long long)heads * 64) {
-        set_error("uwu_attn: leading dimension %lld of %s must be a multiple of 8 and >= heads*64", ld, what);
+// (head_dim, heads, L, B) view of a [B*L, ld] activation; the box is always 64 columns wide, so heads narrower than 64 are
+// zero-filled by TMA up to the tile width (out-of-bounds fill) and the 128-byte swizzled tile layout does not change.
+static int make_head_map(CUtensorMap* tm, const void* base, int heads, int hd, int L, int B, long long ld, const char* what) {
+    if (ld % 8 != 0 || ld < (long long)heads * hd) {
+        set_error("uwu_attn: leading dimension %lld of %s must be a multiple of 8 and >= heads*head_dim", ld, what);
         return UWU_ERR_INVALID;
     }
-    uint64_t dims[3] = {(uint64_t)heads * 64, (uint64_t)L, (uint64_t)B};
-    uint64_t str[2] = {(uint64_t)ld * 2, (uint64_t)ld * 2 * (uint64_t)L};
-    uint32_t box[3] = {64, 128, 1};
-    return encode_tmap_bf16(tm, base, 3, dims, str, box, 1);
+    uint64_t dims[4] = {(uint64_t)hd, (uint64_t)heads, (uint64_t)L, (uint64_t)B};
+    uint64_t str[3] = {(uint64_t)hd * 2, (uint64_t)ld * 2, (uint64_t)ld * 2 * (uint64_t)L};
+    uint32_t box[4] = {64, 1, 128, 1};
+    return encode_tmap_bf16(tm, base, 4, dims, str, box, 1);
 }
 
 // mma.sync kernels for head dims other than 64 (attn_any.cu)
@@ -772,12 +781,12 @@ extern "C" int uwu_attn_fwd(const void* q, const void* k, const void* v, void* o
     if (int rc = attn_check(B, heads, Lq, Lk, head_dim)) return rc;
     UWU_CHECK_ARG(q && k && v && o && lse, "uwu_attn_fwd: null pointer");
     UWU_CHECK_ARG(ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(o) & 15) == 0, "uwu_attn_fwd: output must be 16-byte aligned");
-    if (head_dim != 64) return attn_any_fwd(q, k, v, o, lse, B, heads, Lq, Lk, head_dim, ldq, ldk, ldv, ldo, scale, stream);
+    if (head_dim > 64) return attn_any_fwd(q, k, v, o, lse, B, heads, Lq, Lk, head_dim, ldq, ldk, ldv, ldo, scale, stream);
     static thread_local AttnFwdArgs a;
-    if (int rc = make_head_map(&a.tmQ, q, heads, Lq, B, ldq, "q")) return rc;
-    if (int rc = make_head_map(&a.tmK, k, heads, Lk, B, ldk, "k")) return rc;
-    if (int rc = make_head_map(&a.tmV, v, heads, Lk, B, ldv, "v")) return rc;
-    a.Lq = Lq; a.Lk = Lk; a.heads = heads; a.Lq_pad = (Lq + 127) / 128 * 128;
+    if (int rc = make_head_map(&a.tmQ, q, heads, head_dim, Lq, B, ldq, "q")) return rc;
+    if (int rc = make_head_map(&a.tmK, k, heads, head_dim, Lk, B, ldk, "k")) return rc;
+    if (int rc = make_head_map(&a.tmV, v, heads, head_dim, Lk, B, ldv, "v")) return rc;
+    a.Lq = Lq; a.Lk = Lk; a.heads = heads; a.Lq_pad = (Lq + 127) / 128 * 128; a.hd = head_dim;
     a.scale = scale; a.scale_log2 = scale * LOG2E;
     a.o = reinterpret_cast<__nv_bfloat16*>(o); a.ldo = ldo; a.lse = lse;
     static bool attr_set = false;
@@ -820,7 +829,7 @@ extern "C" int uwu_attn_bwd(const void* q, const void* k, const void* v, const v
                     reinterpret_cast<uintptr_t>(dk) | reinterpret_cast<uintptr_t>(dv) |
                     reinterpret_cast<uintptr_t>(workspace)) & 15) == 0,
                   "uwu_attn_bwd: pointers must be 16-byte aligned");
-    if (head_dim != 64)
+    if (head_dim > 64)
         return attn_any_bwd(q, k, v, o, dout, lse, dq, dk, dv, B, heads, Lq, Lk, head_dim, ldq, ldk, ldv, ldo, lddo, lddq, lddk,
                             lddv, scale, workspace, stream);
     const int Lq_pad = (Lq + 127) / 128 * 128;
@@ -828,11 +837,11 @@ extern "C" int uwu_attn_bwd(const void* q, const void* k, const void* v, const v
     float* lse2 = workspace;
     float* delta = workspace + rows;
     static thread_local AttnBwdArgs a;
-    if (int rc = make_head_map(&a.tmQ, q, heads, Lq, B, ldq, "q")) return rc;
-    if (int rc = make_head_map(&a.tmK, k, heads, Lk, B, ldk, "k")) return rc;
-    if (int rc = make_head_map(&a.tmV, v, heads, Lk, B, ldv, "v")) return rc;
-    if (int rc = make_head_map(&a.tmdO, dout, heads, Lq, B, lddo, "dout")) return rc;
-    a.Lq = Lq; a.Lk = Lk; a.heads = heads; a.Lq_pad = Lq_pad;
+    if (int rc = make_head_map(&a.tmQ, q, heads, head_dim, Lq, B, ldq, "q")) return rc;
+    if (int rc = make_head_map(&a.tmK, k, heads, head_dim, Lk, B, ldk, "k")) return rc;
+    if (int rc = make_head_map(&a.tmV, v, heads, head_dim, Lk, B, ldv, "v")) return rc;
+    if (int rc = make_head_map(&a.tmdO, dout, heads, head_dim, Lq, B, lddo, "dout")) return rc;
+    a.Lq = Lq; a.Lk = Lk; a.heads = heads; a.Lq_pad = Lq_pad; a.hd = head_dim;
     a.scale = scale; a.scale_log2 = scale * LOG2E;
     a.lse2 = lse2; a.delta = delta;
     a.dq = reinterpret_cast<__nv_bfloat16*>(dq); a.lddq = lddq;
@@ -844,7 +853,7 @@ extern "C" int uwu_attn_bwd(const void* q, const void* k, const void* v, const v
         const long long total = (long long)B * Lq * heads;
         attn_bwd_prep_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(
             reinterpret_cast<const __nv_bfloat16*>(o), ldo, reinterpret_cast<const __nv_bfloat16*>(dout), lddo, lse, B, heads,
-            Lq, Lq_pad, lse2, delta);
+            Lq, Lq_pad, head_dim, lse2, delta);
         UWU_CHECK_LAUNCH();
     }
     static bool attr_set = false;
@@ -861,7 +870,7 @@ extern "C" int uwu_attn_bwd(const void* q, const void* k, const void* v, const v
         UWU_CHECK_LAUNCH();
         const long long total = (long long)B * Lq * heads * 8;
         attn_bwd_dq_convert_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(
-            a.dq_acc, B, heads, Lq, Lq_pad / 128, scale, reinterpret_cast<__nv_bfloat16*>(dq), lddq);
+            a.dq_acc, B, heads, Lq, Lq_pad / 128, scale, head_dim, reinterpret_cast<__nv_bfloat16*>(dq), lddq);
         UWU_CHECK_LAUNCH();
     } else {
         attn_bwd_kernel<0><<<dim3((Lk + 127) / 128, heads, B), BWD_THREADS, BwdCfg<0>::SMEM, stream>>>(a);  // dK, dV

@@ -1,4 +1,4 @@
-// Flash attention forward / backward for head dims other than 64 (SD-1.5: 40 / 80 / 160, DiT-XL/2: 72).
+// Flash attention forward / backward for head dims above 64 (SD-1.5: 80 / 160, DiT-XL/2: 72).
 //
 // replaces: F.scaled_dot_product_attention in diffusers AttnProcessor2_0 (in-tree copy of the flow:
 //           /root/reference/src/duwu/modules/rope_unet.py:76-175, SDPA call :151) for the UNets whose heads are not 64 wide.
@@ -6,7 +6,8 @@
 // The d = 64 heads of the SDXL path run on the tcgen05 / TMEM kernels of attn.cu.  The shapes here carry a few percent of
 // their models' FLOPs (SD-1.5: 8 heads of 40..160; DiT: 16 heads of 72, L = 256) and their widths do not tile the 128-byte
 // swizzle atoms those kernels are built on, so they run on warp-level mma.sync.m16n8k16 tiles instead:
-//   * head dim d (multiple of 8, <= 160) is zero-padded in shared memory to DP in {48, 80, 128, 160};
+//   * head dim d (multiple of 8, 64 < d <= 160; narrower heads run zero-padded on the tcgen05 kernels) is zero-padded in
+//     shared memory to DP in {80, 128, 160};
 //   * forward:   block = 64 query rows (16 per warp), streams 64-key tiles, online softmax in registers, P stays in
 //                registers as the A operand of P.V;
 //   * backward:  two deterministic passes (no atomics).  dK/dV pass: block = 64 keys, computes S^T = K Q^T and dP^T = V dO^T
@@ -432,7 +433,6 @@ int attn_any_fwd(const void* q, const void* k, const void* v, void* o, float* ls
     a.B = B; a.heads = heads; a.Lq = Lq; a.Lk = Lk; a.Lq_pad = (Lq + 127) / 128 * 128; a.d = d;
     a.scale = scale; a.scale_log2 = scale * LOG2E;
     if (int rc = check_any(a, "uwu_attn_fwd")) return rc;
-    if (d <= 48) return launch_fwd<48>(a, stream);
     if (d <= 80) return launch_fwd<80>(a, stream);
     if (d <= 128) return launch_fwd<128>(a, stream);
     return launch_fwd<160>(a, stream);
@@ -464,7 +464,6 @@ int attn_any_bwd(const void* q, const void* k, const void* v, const void* o, con
     const long long total = (long long)B * Lq * heads;
     attn_any_prep_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(a, lse2, delta);
     UWU_CHECK_LAUNCH();
-    if (d <= 48) return launch_bwd<48, 64>(a, stream);
     if (d <= 80) return launch_bwd<80, 64>(a, stream);
     if (d <= 128) return launch_bwd<128, 32>(a, stream);
     return launch_bwd<160, 32>(a, stream);
