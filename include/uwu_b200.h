@@ -197,8 +197,41 @@ int uwu_layernorm_bwd(const void* x, const void* dy, int32_t M, int32_t C, const
 /* GEGLU: out[m, f] = in[m, f] * gelu_erf(in[m, F + f])  (hidden, gate = proj.chunk(2)) */
 int uwu_geglu_fwd(const void* in, int64_t M, int32_t F, void* out, void* stream);
 int uwu_geglu_bwd(const void* in, const void* dout, int64_t M, int32_t F, void* din, void* stream);
-/* mode 0: y = silu(x); 1: y = x * silu'(a); 2: y = x + a; 3: y = x   (bf16, n multiple of 8) */
+/* mode 0: y = silu(x); 1: y = x * silu'(a); 2: y = x + a; 3: y = x; 4: y = gelu_tanh(x); 5: y = x * gelu_tanh'(a)
+ * (bf16, n multiple of 8) */
 int uwu_elementwise(const void* x, const void* a, int64_t n, int32_t mode, void* y, void* stream);
+/* ------------------------------------------------------------------------------------------------
+ * adaLN-Zero glue of DiT blocks (BASELINE.json configs[3]).  The reference tree has no DiT model; the algebra is the
+ * `ada_norm_zero` branch of its patched transformer block: src/duwu/modules/rope_unet.py:306-309 (modulate), :344-345
+ * (gate_msa), :395-398, :406-407 (MLP side).  x/y/dx: bf16 [M, C], M = B * rows_per_mod; mod: fp32 [B, ld_mod] rows holding
+ * shift / scale / gate windows at the given column offsets; dmod: bf16 [B, ld_dmod] (per-sample sums over the rows).
+ * ------------------------------------------------------------------------------------------------ */
+/* y = LN(x) * (1 + scale[b]) + shift[b]  (no affine); stats[M, 2] = {mean, rstd} */
+int uwu_adaln_fwd(const void* x, int64_t M, int32_t C, float eps, const float* mod, int64_t ld_mod, int32_t shift_off,
+                  int32_t scale_off, int32_t rows_per_mod, void* y, float* stats, void* stream);
+/* dx = LN'(dy * (1 + scale[b])) (+ dres); dmod[b, dshift_off + c] = sum_t dy, dmod[b, dscale_off + c] = sum_t dy * xhat */
+int uwu_adaln_bwd(const void* x, const void* dy, int64_t M, int32_t C, const float* mod, int64_t ld_mod, int32_t scale_off,
+                  const float* stats, int32_t rows_per_mod, const void* dres, void* dx, void* dmod_bf16, int64_t ld_dmod,
+                  int32_t dshift_off, int32_t dscale_off, void* stream);
+/* out = x + gate[b] * y */
+int uwu_gate_residual_fwd(const void* x, const void* y, int64_t M, int32_t C, const float* mod, int64_t ld_mod,
+                          int32_t gate_off, int32_t rows_per_mod, void* out, void* stream);
+/* dy = gate[b] * dout; dmod[b, dgate_off + c] = sum_t dout * y */
+int uwu_gate_residual_bwd(const void* dout, const void* y, int64_t M, int32_t C, const float* mod, int64_t ld_mod,
+                          int32_t gate_off, int32_t rows_per_mod, void* dy, void* dmod_bf16, int64_t ld_dmod,
+                          int32_t dgate_off, void* stream);
+/* NCHW fp32 image <-> token rows [B * (H/p) * (W/p), ld].  order 0: column = c*p*p + ph*p + pw (patch-embedding conv
+ * weight flattening); order 1: column = (ph*p + pw)*Ctok + c (DiT unpatchify).  patchify zero-fills channels >= Cimg and
+ * columns >= Ctok*p*p; unpatchify takes the first Cimg of Ctok channels. */
+int uwu_patchify(const float* img, int32_t B, int32_t Cimg, int32_t H, int32_t W, int32_t p, int32_t order, int32_t Ctok,
+                 void* tok_bf16, int64_t ld, void* stream);
+int uwu_unpatchify(const void* tok, int32_t tok_dtype, int64_t ld, int32_t B, int32_t Cimg, int32_t H, int32_t W, int32_t p,
+                   int32_t order, int32_t Ctok, float* img, void* stream);
+/* class-label embedding table: out[b] = table[idx[b]] (bf16 rows); dtable[idx[b]] += dout[b] */
+int uwu_embed_gather(const float* table, const int64_t* idx, int32_t B, int32_t D, int32_t V, void* out_bf16, void* stream);
+int uwu_embed_scatter_add(const void* dout_bf16, const int64_t* idx, int32_t B, int32_t D, int32_t V, float* dtable,
+                          void* stream);
+
 /* API boundary layout conversion: the reference tensors are NCHW (src/duwu/data/base.py:13) */
 int uwu_nchw_to_nhwc(const void* src, int32_t src_dtype, int32_t N, int32_t C, int32_t HW, int32_t Cpad, void* dst_bf16,
                      void* stream);

@@ -4,6 +4,7 @@
 
   c1      configs/demo_training.yaml-style pixel UNet, batch 4 at 3x32x32, eps-pred MSE, full fine-tune
   c2      SD-1.5-size latent UNet (860 M params), 4x64x64 latents, batch 32, bf16 compute, full fine-tune
+  c4      DiT-XL/2 class-conditional (675 M params), 4x32x32 latents, batch 256 on one GPU (32 per GPU at 8), full fine-tune
   latent  the reference's configs/demo_training_latent.yaml as shipped: SDXL UNet, 4x32x32 latents, batch 16, full fine-tune
 
 Same timing rules as bench.py: >= 3 warm-up steps, CUDA events around K whole `DMTrainer.fit_step` calls (forward, backward,
@@ -49,6 +50,13 @@ def make_conf(kind: str, batch: int):
         tr["loss_config"]["use_snr_weight"] = False
         from uwudiff_b200.unet import SD15_UNET_CONFIG
         return conf, SD15_UNET_CONFIG, (4, 64, 64), "SD-1.5-size latent UNet (860 M params) full fine-tune [configs[1]]"
+    if kind == "c4":
+        from uwudiff_b200.dit import DIT_XL_2_CONFIG
+        tr["model_config"]["unet"] = {"_target_": "uwudiff_b200.dit.DiT.from_config", "config": "DiT-XL/2"}
+        tr["model_config"]["te"] = None
+        sched["prediction_type"] = "epsilon"
+        tr["loss_config"]["use_snr_weight"] = False
+        return conf, DIT_XL_2_CONFIG, (4, 32, 32), "DiT-XL/2 class-conditional, adaLN-Zero, full fine-tune [configs[3]]"
     from uwudiff_b200.unet import SDXL_UNET_CONFIG
     sched["prediction_type"] = "epsilon"
     tr["loss_config"]["use_snr_weight"] = False
@@ -57,19 +65,22 @@ def make_conf(kind: str, batch: int):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("kind", choices=["c1", "c2", "latent"])
+    ap.add_argument("kind", choices=["c1", "c2", "c4", "latent"])
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=0)
     args = ap.parse_args()
-    B = args.batch or {"c1": 4, "c2": 32, "latent": 16}[args.kind]
+    B = args.batch or {"c1": 4, "c2": 32, "c4": 256, "latent": 16}[args.kind]
     dev = torch.device("cuda")
     conf, ucfg_dict, shape, label = make_conf(args.kind, B)
     trainer = ucfg.instantiate_any(conf["trainer"])
     trainer.setup_fit(gradient_clip_val=1.0, seed=1215)
     host_x = torch.randn((B, *shape)).pin_memory()
     host_ids = torch.tensor([[1024., 1024, 0, 0, 1024, 1024]] * B).pin_memory()
-    dev_batch = (host_x.to(dev), ["DUMMY TEST"] * B, [], {"time_ids": host_ids.to(dev)}, {})
+    host_cond = {"time_ids": host_ids}
+    if args.kind == "c4":
+        host_cond = {"class_labels": torch.randint(0, 1000, (B,)).pin_memory()}
+    dev_batch = (host_x.to(dev), ["DUMMY TEST"] * B, [], {k: v.to(dev) for k, v in host_cond.items()}, {})
 
     def timed(batch_fn, read):
         torch.cuda.synchronize()
@@ -87,8 +98,12 @@ def main():
     for i in range(max(3, args.warmup)):
         trainer.fit_step(dev_batch, i)
     ms, launches, loss = timed(lambda: dev_batch, False)
-    ms_e2e, _, _ = timed(lambda: (host_x, ["DUMMY TEST"] * B, [], {"time_ids": host_ids}, {}), True)
-    fwd = unet_forward_flops(ucfg_dict, shape[1], shape[2])["total"]
+    ms_e2e, _, _ = timed(lambda: (host_x, ["DUMMY TEST"] * B, [], dict(host_cond), {}), True)
+    if args.kind == "c4":
+        from uwudiff_b200.dit import dit_forward_flops
+        fwd = dit_forward_flops(ucfg_dict)["total"]
+    else:
+        fwd = unet_forward_flops(ucfg_dict, shape[1], shape[2])["total"]
     peak, _ = bench.peaks()
     sus = peak.get("bf16_tflops_sustained") or peak.get("bf16_sustained_tflops")
     tf = 3.0 * fwd * B / (ms * 1e-3) / 1e12
@@ -97,7 +112,7 @@ def main():
         "metric": "train_samples_per_s", "value": B / (ms * 1e-3), "unit": "samples/s", "n_gpus": 1, "steps": args.steps,
         "warmup": max(3, args.warmup), "ms_per_step": ms, "dtype": "bf16", "data": "synthetic", "loss": loss,
         "config": {"workload": label, "batch": B, "input": list(shape), "params": n_params, "trainable": "all (full fine-tune)"},
-        "e2e": {"value": B / (ms_e2e * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": host_x.numel() * 4 + host_ids.numel() * 4,
+        "e2e": {"value": B / (ms_e2e * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": host_x.numel() * 4 + sum(v.numel() * v.element_size() for v in host_cond.values()),
                 "d2h_bytes_per_step": 4},
         "gpu_launches": launches,
         "tensor_tflops": {"achieved": tf, "algorithmic_tflop_per_step": 3.0 * fwd * B / 1e12,

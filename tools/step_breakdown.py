@@ -21,7 +21,8 @@ from uwudiff_b200 import ops
 WRAP = ["gemm", "noise_fwd", "sincos_embed", "wmse_fwd", "wmse_bwd", "attn_fwd", "attn_bwd", "groupnorm_fwd", "groupnorm_bwd",
         "layernorm_fwd", "layernorm_bwd", "geglu_fwd", "geglu_bwd", "elementwise", "nchw_to_nhwc", "nhwc_to_nchw", "upsample2x",
         "phase_split2", "colsum", "fold_lokr", "fold_lora", "axpy_f32", "lokr_grad", "lora_grad", "copy2d", "lokr_z", "lokr_dw1",
-        "im2col3x3", "conv_wgrad_unpack", "colsum_groups", "pred_convert"]
+        "im2col3x3", "conv_wgrad_unpack", "colsum_groups", "pred_convert", "adaln_fwd", "adaln_bwd", "gate_residual_fwd", "gate_residual_bwd", "patchify",
+        "unpatchify", "embed_gather", "embed_scatter_add"]
 
 
 def main():
@@ -29,7 +30,7 @@ def main():
     ap.add_argument("--batch", type=int, default=16)
     ap.add_argument("--latent", type=int, default=128)
     ap.add_argument("--top", type=int, default=45)
-    ap.add_argument("--config", default="c3", choices=["c3", "c1", "c2", "latent"], help="c3 = bench.py headline workload")
+    ap.add_argument("--config", default="c3", choices=["c3", "c1", "c2", "c4", "latent"], help="c3 = bench.py headline workload")
     args = ap.parse_args()
     dev = torch.device("cuda")
     shape = (4, args.latent, args.latent)
@@ -38,13 +39,14 @@ def main():
     else:
         import bench_configs
 
-        args.batch = {"c1": 4, "c2": 32, "latent": 16}[args.config]
+        args.batch = {"c1": 4, "c2": 32, "c4": 256, "latent": 16}[args.config]
         conf, _, shape, _ = bench_configs.make_conf(args.config, args.batch)
     trainer = ucfg.instantiate_any(conf["trainer"])
     trainer.setup_fit(gradient_clip_val=1.0, seed=1215)
     B, S = args.batch, args.latent
     batch = (torch.randn((B, *shape), device=dev), ["DUMMY TEST"] * B, [],
-             {"time_ids": torch.tensor([[1024., 1024, 0, 0, 1024, 1024]] * B, device=dev)}, {})
+             ({"class_labels": torch.randint(0, 1000, (B,), device=dev)} if args.config == "c4" else
+              {"time_ids": torch.tensor([[1024., 1024, 0, 0, 1024, 1024]] * B, device=dev)}), {})
     for i in range(3):
         trainer.fit_step(batch, i)
     torch.cuda.synchronize()

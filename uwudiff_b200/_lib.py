@@ -90,6 +90,14 @@ SIGNATURES = {
     "uwu_geglu_fwd": (C.c_int, [_P, _I64, _I32, _P, _P]),
     "uwu_geglu_bwd": (C.c_int, [_P, _P, _I64, _I32, _P, _P]),
     "uwu_elementwise": (C.c_int, [_P, _P, _I64, _I32, _P, _P]),
+    "uwu_adaln_fwd": (C.c_int, [_P, _I64, _I32, _F, _P, _I64, _I32, _I32, _I32, _P, _P, _P]),
+    "uwu_adaln_bwd": (C.c_int, [_P, _P, _I64, _I32, _P, _I64, _I32, _P, _I32, _P, _P, _P, _I64, _I32, _I32, _P]),
+    "uwu_gate_residual_fwd": (C.c_int, [_P, _P, _I64, _I32, _P, _I64, _I32, _I32, _P, _P]),
+    "uwu_gate_residual_bwd": (C.c_int, [_P, _P, _I64, _I32, _P, _I64, _I32, _I32, _P, _P, _I64, _I32, _P]),
+    "uwu_patchify": (C.c_int, [_P, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _P, _I64, _P]),
+    "uwu_unpatchify": (C.c_int, [_P, _I32, _I64, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _P, _P]),
+    "uwu_embed_gather": (C.c_int, [_P, _P, _I32, _I32, _I32, _P, _P]),
+    "uwu_embed_scatter_add": (C.c_int, [_P, _P, _I32, _I32, _I32, _P, _P]),
     "uwu_nchw_to_nhwc": (C.c_int, [_P, _I32, _I32, _I32, _I32, _I32, _P, _P]),
     "uwu_nhwc_to_nchw": (C.c_int, [_P, _I32, _I32, _I32, _I32, _I64, _P, _P]),
     "uwu_upsample2x": (C.c_int, [_P, _I32, _I32, _I32, _I32, _I32, _P, _P]),

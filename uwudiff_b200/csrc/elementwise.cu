@@ -82,18 +82,31 @@ __global__ void __launch_bounds__(256) geglu_bwd_kernel(const __nv_bfloat16* __r
     }
 }
 
-// mode 0: y = silu(x); mode 1: y = x * silu'(a) (x = dy, a = pre-activation); mode 2: y = x + a; mode 3: y = x
+UWU_DEVINL float gelu_tanh_f(float x) {
+    const float u = 0.7978845608028654f * fmaf(0.044715f * x * x, x, x);
+    return 0.5f * x * (1.0f + tanhf(u));
+}
+UWU_DEVINL float gelu_tanh_grad_f(float x) {
+    const float u = 0.7978845608028654f * fmaf(0.044715f * x * x, x, x);
+    const float t = tanhf(u);
+    return 0.5f * (1.0f + t) + 0.5f * x * (1.0f - t * t) * 0.7978845608028654f * fmaf(3.0f * 0.044715f * x, x, 1.0f);
+}
+
+// mode 0: y = silu(x); mode 1: y = x * silu'(a) (x = dy, a = pre-activation); mode 2: y = x + a; mode 3: y = x;
+// mode 4: y = gelu_tanh(x); mode 5: y = x * gelu_tanh'(a)   (DiT MLP activation)
 __global__ void ew_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ a, long long nvec,
                           int mode, __nv_bfloat16* __restrict__ y) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
         float f[8], b[8];
         ld8e(x + i * 8, f);
-        if (mode == 1 || mode == 2) ld8e(a + i * 8, b);
+        if (mode == 1 || mode == 2 || mode == 5) ld8e(a + i * 8, b);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             if (mode == 0) f[j] = silu_f(f[j]);
             else if (mode == 1) f[j] *= silu_grad_f(b[j]);
             else if (mode == 2) f[j] += b[j];
+            else if (mode == 4) f[j] = gelu_tanh_f(f[j]);
+            else if (mode == 5) f[j] *= gelu_tanh_grad_f(b[j]);
         }
         st8e(y + i * 8, f);
     }
@@ -296,9 +309,9 @@ extern "C" int uwu_geglu_bwd(const void* in, const void* dout, int64_t M, int32_
 extern "C" int uwu_elementwise(const void* x, const void* a, int64_t n, int32_t mode, void* y, void* stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     UWU_CHECK_ARG(n >= 0 && n % 8 == 0, "uwu_elementwise: n=%lld must be a multiple of 8", (long long)n);
-    UWU_CHECK_ARG(mode >= 0 && mode <= 3, "uwu_elementwise: bad mode %d", mode);
+    UWU_CHECK_ARG(mode >= 0 && mode <= 5, "uwu_elementwise: bad mode %d", mode);
     if (n == 0) return UWU_OK;
-    UWU_CHECK_ARG(x && y && (mode == 0 || mode == 3 || a), "uwu_elementwise: null pointer");
+    UWU_CHECK_ARG(x && y && (mode == 0 || mode == 3 || mode == 4 || a), "uwu_elementwise: null pointer");
     ew_kernel<<<ew_grid(n / 8, 256), 256, 0, stream>>>(reinterpret_cast<const bf16*>(x), reinterpret_cast<const bf16*>(a),
                                                        n / 8, mode, reinterpret_cast<bf16*>(y));
     UWU_CHECK_LAUNCH();

@@ -338,7 +338,7 @@ def geglu_bwd(x: torch.Tensor, dout: torch.Tensor) -> torch.Tensor:
     return din
 
 
-EW_SILU, EW_SILU_BWD, EW_ADD, EW_COPY = 0, 1, 2, 3
+EW_SILU, EW_SILU_BWD, EW_ADD, EW_COPY, EW_GELU_TANH, EW_GELU_TANH_BWD = 0, 1, 2, 3, 4, 5
 
 
 def elementwise(x: torch.Tensor, a: Optional[torch.Tensor], mode: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -347,6 +347,93 @@ def elementwise(x: torch.Tensor, a: Optional[torch.Tensor], mode: int, out: Opti
     y = torch.empty_like(x) if out is None else out
     check(lib().uwu_elementwise(_ptr(x), _ptr(a), x.numel(), mode, _ptr(y), _stream()), "uwu_elementwise")
     return y
+
+
+# --------------------------------------------------------------------------------------------------
+# adaLN-Zero glue (DiT): mod is the fp32 [B, ld] output of SiLU -> Linear(D, 6D); windows are addressed by column offset
+# --------------------------------------------------------------------------------------------------
+def adaln_fwd(x: torch.Tensor, mod: torch.Tensor, shift_off: int, scale_off: int, rows_per_mod: int, eps: float = 1e-6):
+    """y = LN(x) * (1 + mod[b, scale_off:]) + mod[b, shift_off:]  ->  (y, stats[M, 2])."""
+    _req_cuda(x, mod)
+    assert x.dtype == torch.bfloat16 and x.is_contiguous() and mod.dtype == torch.float32 and mod.stride(1) == 1
+    M, Cc = x.shape
+    y = torch.empty_like(x)
+    stats = torch.empty((M, 2), device=x.device, dtype=torch.float32)
+    check(lib().uwu_adaln_fwd(_ptr(x), M, Cc, eps, _ptr(mod), mod.stride(0), shift_off, scale_off, rows_per_mod, _ptr(y),
+                              _ptr(stats), _stream()), "uwu_adaln_fwd")
+    return y, stats
+
+
+def adaln_bwd(x, dy, mod, scale_off: int, stats, rows_per_mod: int, dmod: torch.Tensor, dshift_off: int, dscale_off: int,
+              dres=None):
+    """dx = LN'(dy * (1 + scale)) (+ dres); per-sample dshift / dscale are written into the bf16 dmod rows."""
+    _req_cuda(x, dy, mod, stats, dmod, dres)
+    assert dy.is_contiguous() and dmod.dtype == torch.bfloat16 and dmod.stride(1) == 1 and (dres is None or dres.is_contiguous())
+    M, Cc = x.shape
+    dx = torch.empty_like(x)
+    check(lib().uwu_adaln_bwd(_ptr(x), _ptr(dy), M, Cc, _ptr(mod), mod.stride(0), scale_off, _ptr(stats), rows_per_mod,
+                              _ptr(dres), _ptr(dx), _ptr(dmod), dmod.stride(0), dshift_off, dscale_off, _stream()),
+          "uwu_adaln_bwd")
+    return dx
+
+
+def gate_residual_fwd(x, y, mod, gate_off: int, rows_per_mod: int):
+    """x + mod[b, gate_off:] * y"""
+    _req_cuda(x, y, mod)
+    assert x.is_contiguous() and y.is_contiguous() and x.dtype == y.dtype == torch.bfloat16 and mod.dtype == torch.float32
+    M, Cc = x.shape
+    out = torch.empty_like(x)
+    check(lib().uwu_gate_residual_fwd(_ptr(x), _ptr(y), M, Cc, _ptr(mod), mod.stride(0), gate_off, rows_per_mod, _ptr(out),
+                                      _stream()), "uwu_gate_residual_fwd")
+    return out
+
+
+def gate_residual_bwd(dout, y, mod, gate_off: int, rows_per_mod: int, dmod: torch.Tensor, dgate_off: int):
+    """dy = gate * dout; per-sample dgate = sum_t dout * y written into the bf16 dmod rows."""
+    _req_cuda(dout, y, mod, dmod)
+    assert dout.is_contiguous() and y.is_contiguous() and dmod.dtype == torch.bfloat16
+    M, Cc = dout.shape
+    dy = torch.empty_like(dout)
+    check(lib().uwu_gate_residual_bwd(_ptr(dout), _ptr(y), M, Cc, _ptr(mod), mod.stride(0), gate_off, rows_per_mod, _ptr(dy),
+                                      _ptr(dmod), dmod.stride(0), dgate_off, _stream()), "uwu_gate_residual_bwd")
+    return dy
+
+
+def patchify(img: torch.Tensor, p: int, order: int, ctok: int, ld: int) -> torch.Tensor:
+    """[B, C, H, W] fp32 -> [B*T, ld] bf16 token rows (order 0: conv-weight flattening, 1: unpatchify layout)."""
+    _req_cuda(img)
+    img = img.contiguous().float()
+    B, Cc, H, W = img.shape
+    out = torch.empty((B * (H // p) * (W // p), ld), device=img.device, dtype=torch.bfloat16)
+    check(lib().uwu_patchify(_ptr(img), B, Cc, H, W, p, order, ctok, _ptr(out), ld, _stream()), "uwu_patchify")
+    return out
+
+
+def unpatchify(tok: torch.Tensor, B: int, cimg: int, H: int, W: int, p: int, order: int, ctok: int) -> torch.Tensor:
+    """[B*T, ld] bf16/fp32 token rows -> [B, cimg, H, W] fp32 (first cimg of ctok channels)."""
+    _req_cuda(tok)
+    assert tok.stride(1) == 1
+    out = torch.empty((B, cimg, H, W), device=tok.device, dtype=torch.float32)
+    check(lib().uwu_unpatchify(_ptr(tok), _DT[tok.dtype], tok.stride(0), B, cimg, H, W, p, order, ctok, _ptr(out), _stream()),
+          "uwu_unpatchify")
+    return out
+
+
+def embed_gather(table: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+    _req_cuda(table, idx)
+    assert table.dtype == torch.float32 and table.is_contiguous() and idx.dtype == torch.int64 and idx.is_contiguous()
+    V, D = table.shape
+    out = torch.empty((idx.numel(), D), device=table.device, dtype=torch.bfloat16)
+    check(lib().uwu_embed_gather(_ptr(table), _ptr(idx), idx.numel(), D, V, _ptr(out), _stream()), "uwu_embed_gather")
+    return out
+
+
+def embed_scatter_add(dout: torch.Tensor, idx: torch.Tensor, dtable: torch.Tensor) -> torch.Tensor:
+    _req_cuda(dout, idx, dtable)
+    assert dout.dtype == torch.bfloat16 and dout.is_contiguous() and dtable.dtype == torch.float32 and dtable.is_contiguous()
+    V, D = dtable.shape
+    check(lib().uwu_embed_scatter_add(_ptr(dout), _ptr(idx), idx.numel(), D, V, _ptr(dtable), _stream()), "uwu_embed_scatter_add")
+    return dtable
 
 
 def nchw_to_nhwc(x: torch.Tensor, cpad: int) -> torch.Tensor:

@@ -138,7 +138,8 @@ class DMTrainer(BaseTrainer):
             self.loss = instantiate_any(loss_config)
         self.n_diffusion_time_steps = self.loss.n_diffusion_time_steps
         # fused sinusoidal timestep embedding from the noising kernel (diffusers Timesteps(block_out_channels[0]))
-        self.loss.temb_dim = int(self.unet.config.block_out_channels[0])
+        cfg = self.unet.config
+        self.loss.temb_dim = int(cfg.block_out_channels[0] if hasattr(cfg, "block_out_channels") else cfg.frequency_embedding_size)
         self._fit = None
 
     # ---- reference API ---------------------------------------------------------------------------------------
@@ -166,6 +167,8 @@ class DMTrainer(BaseTrainer):
                 latent_dist = self.vae.encode(x).latent_dist
                 x = latent_dist.sample()
                 x = (x - self.vae_mean) / self.vae_std
+            if self.te is None:  # class-conditional denoisers (DiT): labels travel in added_cond["class_labels"]
+                return x, None, None, added_cond, cross_attn_kwargs
             if isinstance(self.te, BaseTextEncoder):
                 try:
                     embedding, normed_embedding, pooled_embedding, attn_mask = self.te(tokenizer_outputs, batch_size=x.shape[0])
