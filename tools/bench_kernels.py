@@ -217,6 +217,24 @@ def case_attn():
         tf(f"attn_bwd B{B} h{heads} L{L} Lk{Lk} (2.5x)", timeit(lambda: ops.attn_bwd(q, k, v, o, do, lse, B, heads, L, Lk)), 2.5 * fl)
 
 
+def case_attn_any():
+    """head dims other than 64: DiT-XL/2 (d 72), SD-1.5 (d 40 zero-padded on tcgen05; d 80 / 160 on mma.sync)."""
+    for (B, heads, L, Lk, d) in [(256, 16, 256, 256, 72), (32, 8, 4096, 4096, 40), (32, 8, 1024, 1024, 80), (32, 8, 256, 256, 160),
+                                 (32, 8, 1024, 77, 80)]:
+        C = heads * d
+        if Lk == L:
+            qkv = mk(B * L, 3 * C)
+            q, k, v = qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:]
+        else:
+            q, k, v = mk(B * L, C), mk(B * Lk, C), mk(B * Lk, C)
+        do = mk(B * L, C)
+        o, lse = ops.attn_fwd(q, k, v, B, heads, L, Lk, head_dim=d)
+        fl = 4.0 * B * heads * L * Lk * d
+        tf(f"attn_fwd B{B} h{heads} L{L} Lk{Lk} d{d}", timeit(lambda: ops.attn_fwd(q, k, v, B, heads, L, Lk, head_dim=d)), fl)
+        tf(f"attn_bwd B{B} h{heads} L{L} Lk{Lk} d{d} (2.5x)",
+           timeit(lambda: ops.attn_bwd(q, k, v, o, do, lse, B, heads, L, Lk, head_dim=d)), 2.5 * fl)
+
+
 if __name__ == "__main__":
     cases = sys.argv[1:] or ["ln", "geglu", "gn", "lokr", "wgrad", "lin", "attn"]
     for c in cases:

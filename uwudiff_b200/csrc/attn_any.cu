@@ -70,6 +70,28 @@ __device__ __forceinline__ void load_tile(__nv_bfloat16* s, const __nv_bfloat16*
     }
 }
 
+// same, through cp.async (16-byte chunks, zero-filled outside L x d); the caller commits / waits the group
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, int src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int DP>
+__device__ __forceinline__ void load_tile_async(__nv_bfloat16* s, const __nv_bfloat16* g, long long ld, int row0, int L, int d,
+                                                int rows) {
+    constexpr int LDS = DP + 8;
+    constexpr int CH = DP / 8;
+    const uint32_t sbase = smem_addr(s);
+    for (int i = threadIdx.x; i < rows * CH; i += NT) {
+        const int r = i / CH, c = i - r * CH;
+        const bool ok = row0 + r < L && c * 8 < d;
+        const __nv_bfloat16* src = ok ? g + (long long)(row0 + r) * ld + c * 8 : g;
+        cp_async16(sbase + (uint32_t)((r * LDS + c * 8) * 2), src, ok ? 16 : 0);
+    }
+}
+
 // acc[NTL][4] (16 rows x 8*NTL cols) += A[16 x DP] * B[8*NTL x DP]^T, both row-major in shared memory with stride DP + 8.
 // a_addr: this lane's ldmatrix address into the 16-row A slab; b_base: byte address of row 0 of B.
 template <int DP, int NTL>
@@ -137,27 +159,36 @@ __global__ void __launch_bounds__(NT) attn_any_fwd_kernel(const AnyArgs a) {
     constexpr int LDS = DP + 8;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __nv_bfloat16* Qs = reinterpret_cast<__nv_bfloat16*>(smem_raw);
-    __nv_bfloat16* Ks = Qs + TQ * LDS;
-    __nv_bfloat16* Vs = Ks + TK * LDS;
+    __nv_bfloat16* Ks = Qs + TQ * LDS;        // two stages
+    __nv_bfloat16* Vs = Ks + 2 * TK * LDS;    // two stages
     const int q0 = blockIdx.x * TQ, h = blockIdx.y, b = blockIdx.z;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
     const __nv_bfloat16* qg = a.q + (long long)b * a.Lq * a.ldq + (long long)h * a.d;
     const __nv_bfloat16* kg = a.k + (long long)b * a.Lk * a.ldk + (long long)h * a.d;
     const __nv_bfloat16* vg = a.v + (long long)b * a.Lk * a.ldv + (long long)h * a.d;
-    load_tile<DP>(Qs, qg, a.ldq, q0, a.Lq, a.d, TQ);
+    load_tile_async<DP>(Qs, qg, a.ldq, q0, a.Lq, a.d, TQ);
+    load_tile_async<DP>(Ks, kg, a.ldk, 0, a.Lk, a.d, TK);
+    load_tile_async<DP>(Vs, vg, a.ldv, 0, a.Lk, a.d, TK);
+    cp_async_commit();
     const uint32_t q_addr = smem_addr(Qs) + (uint32_t)(((warp * 16 + (lane & 15)) * LDS + ((lane >> 4) << 3)) * 2);
-    const uint32_t k_base = smem_addr(Ks), v_base = smem_addr(Vs);
 
     float o[DP / 8][4];
 #pragma unroll
     for (int i = 0; i < DP / 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
     float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
 
-    for (int k0 = 0; k0 < a.Lk; k0 += TK) {
+    int buf = 0;
+    for (int k0 = 0; k0 < a.Lk; k0 += TK, buf ^= 1) {
+        if (k0 + TK < a.Lk) {  // prefetch the next key tile into the other stage while this one is consumed
+            load_tile_async<DP>(Ks + (buf ^ 1) * TK * LDS, kg, a.ldk, k0 + TK, a.Lk, a.d, TK);
+            load_tile_async<DP>(Vs + (buf ^ 1) * TK * LDS, vg, a.ldv, k0 + TK, a.Lk, a.d, TK);
+            cp_async_commit();
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
         __syncthreads();
-        load_tile<DP>(Ks, kg, a.ldk, k0, a.Lk, a.d, TK);
-        load_tile<DP>(Vs, vg, a.ldv, k0, a.Lk, a.d, TK);
-        __syncthreads();
+        const uint32_t k_base = smem_addr(Ks + buf * TK * LDS), v_base = smem_addr(Vs + buf * TK * LDS);
         float s[TK / 8][4];
 #pragma unroll
         for (int i = 0; i < TK / 8; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
@@ -202,6 +233,7 @@ __global__ void __launch_bounds__(NT) attn_any_fwd_kernel(const AnyArgs a) {
             o[i][3] *= c1;
         }
         gemm_pn<DP, TK / 8>(o, s, v_base, lane);
+        __syncthreads();  // every warp is done with this stage before the prefetch after next overwrites it
     }
     l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
     l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
@@ -250,10 +282,10 @@ __global__ void __launch_bounds__(NT) attn_any_bwd_kv_kernel(const AnyArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __nv_bfloat16* Ks = reinterpret_cast<__nv_bfloat16*>(smem_raw);
     __nv_bfloat16* Vs = Ks + TK * LDS;
-    __nv_bfloat16* Qs = Vs + TK * LDS;
-    __nv_bfloat16* dOs = Qs + QT * LDS;
-    float* lses = reinterpret_cast<float*>(dOs + QT * LDS);
-    float* dls = lses + QT;
+    __nv_bfloat16* Qs = Vs + TK * LDS;        // two stages
+    __nv_bfloat16* dOs = Qs + 2 * QT * LDS;   // two stages
+    float* lses = reinterpret_cast<float*>(dOs + 2 * QT * LDS);  // [2][QT]
+    float* dls = lses + 2 * QT;                                  // [2][QT]
     const int k0 = blockIdx.x * TK, h = blockIdx.y, b = blockIdx.z;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
     const __nv_bfloat16* qg = a.q + (long long)b * a.Lq * a.ldq + (long long)h * a.d;
@@ -262,11 +294,21 @@ __global__ void __launch_bounds__(NT) attn_any_bwd_kv_kernel(const AnyArgs a) {
     const __nv_bfloat16* dog = a.dout + (long long)b * a.Lq * a.lddo + (long long)h * a.d;
     const float* lse2 = a.lse2 + ((size_t)b * a.heads + h) * a.Lq_pad;
     const float* delta = a.delta + ((size_t)b * a.heads + h) * a.Lq_pad;
-    load_tile<DP>(Ks, kg, a.ldk, k0, a.Lk, a.d, TK);
-    load_tile<DP>(Vs, vg, a.ldv, k0, a.Lk, a.d, TK);
+    auto stage_in = [&](int q0, int st) {
+        load_tile_async<DP>(Qs + st * QT * LDS, qg, a.ldq, q0, a.Lq, a.d, QT);
+        load_tile_async<DP>(dOs + st * QT * LDS, dog, a.lddo, q0, a.Lq, a.d, QT);
+        if (threadIdx.x < QT) {
+            const bool ok = q0 + threadIdx.x < a.Lq;
+            lses[st * QT + threadIdx.x] = ok ? lse2[q0 + threadIdx.x] : INFINITY;  // exp2(s - inf) = 0 masks padded queries
+            dls[st * QT + threadIdx.x] = ok ? delta[q0 + threadIdx.x] : 0.f;
+        }
+    };
+    load_tile_async<DP>(Ks, kg, a.ldk, k0, a.Lk, a.d, TK);
+    load_tile_async<DP>(Vs, vg, a.ldv, k0, a.Lk, a.d, TK);
+    stage_in(0, 0);
+    cp_async_commit();
     const uint32_t a_off = (uint32_t)(((warp * 16 + (lane & 15)) * LDS + ((lane >> 4) << 3)) * 2);
     const uint32_t k_addr = smem_addr(Ks) + a_off, v_addr = smem_addr(Vs) + a_off;
-    const uint32_t q_base = smem_addr(Qs), do_base = smem_addr(dOs);
     const int key = k0 + warp * 16 + g;
     const bool kv0 = key < a.Lk, kv1 = key + 8 < a.Lk;
 
@@ -276,16 +318,19 @@ __global__ void __launch_bounds__(NT) attn_any_bwd_kv_kernel(const AnyArgs a) {
         dk[i][0] = dk[i][1] = dk[i][2] = dk[i][3] = 0.f;
         dv[i][0] = dv[i][1] = dv[i][2] = dv[i][3] = 0.f;
     }
-    for (int q0 = 0; q0 < a.Lq; q0 += QT) {
-        __syncthreads();
-        load_tile<DP>(Qs, qg, a.ldq, q0, a.Lq, a.d, QT);
-        load_tile<DP>(dOs, dog, a.lddo, q0, a.Lq, a.d, QT);
-        if (threadIdx.x < QT) {
-            const bool ok = q0 + threadIdx.x < a.Lq;
-            lses[threadIdx.x] = ok ? lse2[q0 + threadIdx.x] : INFINITY;  // exp2(s - inf) = 0 masks padded queries
-            dls[threadIdx.x] = ok ? delta[q0 + threadIdx.x] : 0.f;
+    int buf = 0;
+    for (int q0 = 0; q0 < a.Lq; q0 += QT, buf ^= 1) {
+        if (q0 + QT < a.Lq) {
+            stage_in(q0 + QT, buf ^ 1);
+            cp_async_commit();
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
         }
         __syncthreads();
+        const uint32_t q_base = smem_addr(Qs + buf * QT * LDS), do_base = smem_addr(dOs + buf * QT * LDS);
+        const float* lsb = lses + buf * QT;
+        const float* dlb = dls + buf * QT;
         float st[QT / 8][4], dpt[QT / 8][4];
 #pragma unroll
         for (int i = 0; i < QT / 8; ++i) {
@@ -297,7 +342,7 @@ __global__ void __launch_bounds__(NT) attn_any_bwd_kv_kernel(const AnyArgs a) {
 #pragma unroll
         for (int nt = 0; nt < QT / 8; ++nt) {
             const int qi = nt * 8 + 2 * t;
-            const float ls0 = lses[qi], ls1 = lses[qi + 1], d0 = dls[qi], d1 = dls[qi + 1];
+            const float ls0 = lsb[qi], ls1 = lsb[qi + 1], d0 = dlb[qi], d1 = dlb[qi + 1];
             const float p0 = kv0 ? exp2f(st[nt][0] * a.scale_log2 - ls0) : 0.f;
             const float p1 = kv0 ? exp2f(st[nt][1] * a.scale_log2 - ls1) : 0.f;
             const float p2 = kv1 ? exp2f(st[nt][2] * a.scale_log2 - ls0) : 0.f;
@@ -313,6 +358,7 @@ __global__ void __launch_bounds__(NT) attn_any_bwd_kv_kernel(const AnyArgs a) {
         }
         gemm_pn<DP, QT / 8>(dv, st, do_base, lane);   // dV += P^T dO
         gemm_pn<DP, QT / 8>(dk, dpt, q_base, lane);   // dK += dS^T Q
+        __syncthreads();
     }
     __nv_bfloat16* dkg = a.dk + (long long)b * a.Lk * a.lddk + (long long)h * a.d;
     __nv_bfloat16* dvg = a.dv + (long long)b * a.Lk * a.lddv + (long long)h * a.d;
@@ -328,19 +374,21 @@ __global__ void __launch_bounds__(NT) attn_any_bwd_q_kernel(const AnyArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __nv_bfloat16* Qs = reinterpret_cast<__nv_bfloat16*>(smem_raw);
     __nv_bfloat16* dOs = Qs + TQ * LDS;
-    __nv_bfloat16* Ks = dOs + TQ * LDS;
-    __nv_bfloat16* Vs = Ks + TK * LDS;
+    __nv_bfloat16* Ks = dOs + TQ * LDS;       // two stages
+    __nv_bfloat16* Vs = Ks + 2 * TK * LDS;    // two stages
     const int q0 = blockIdx.x * TQ, h = blockIdx.y, b = blockIdx.z;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
     const __nv_bfloat16* qg = a.q + (long long)b * a.Lq * a.ldq + (long long)h * a.d;
     const __nv_bfloat16* kg = a.k + (long long)b * a.Lk * a.ldk + (long long)h * a.d;
     const __nv_bfloat16* vg = a.v + (long long)b * a.Lk * a.ldv + (long long)h * a.d;
     const __nv_bfloat16* dog = a.dout + (long long)b * a.Lq * a.lddo + (long long)h * a.d;
-    load_tile<DP>(Qs, qg, a.ldq, q0, a.Lq, a.d, TQ);
-    load_tile<DP>(dOs, dog, a.lddo, q0, a.Lq, a.d, TQ);
+    load_tile_async<DP>(Qs, qg, a.ldq, q0, a.Lq, a.d, TQ);
+    load_tile_async<DP>(dOs, dog, a.lddo, q0, a.Lq, a.d, TQ);
+    load_tile_async<DP>(Ks, kg, a.ldk, 0, a.Lk, a.d, TK);
+    load_tile_async<DP>(Vs, vg, a.ldv, 0, a.Lk, a.d, TK);
+    cp_async_commit();
     const uint32_t a_off = (uint32_t)(((warp * 16 + (lane & 15)) * LDS + ((lane >> 4) << 3)) * 2);
     const uint32_t q_addr = smem_addr(Qs) + a_off, do_addr = smem_addr(dOs) + a_off;
-    const uint32_t k_base = smem_addr(Ks), v_base = smem_addr(Vs);
     const int row = q0 + warp * 16 + g;
     const size_t sidx = ((size_t)b * a.heads + h) * a.Lq_pad;
     const float ls0 = row < a.Lq ? a.lse2[sidx + row] : INFINITY, ls1 = row + 8 < a.Lq ? a.lse2[sidx + row + 8] : INFINITY;
@@ -349,11 +397,18 @@ __global__ void __launch_bounds__(NT) attn_any_bwd_q_kernel(const AnyArgs a) {
     float dq[DP / 8][4];
 #pragma unroll
     for (int i = 0; i < DP / 8; ++i) dq[i][0] = dq[i][1] = dq[i][2] = dq[i][3] = 0.f;
-    for (int k0 = 0; k0 < a.Lk; k0 += TK) {
+    int buf = 0;
+    for (int k0 = 0; k0 < a.Lk; k0 += TK, buf ^= 1) {
+        if (k0 + TK < a.Lk) {
+            load_tile_async<DP>(Ks + (buf ^ 1) * TK * LDS, kg, a.ldk, k0 + TK, a.Lk, a.d, TK);
+            load_tile_async<DP>(Vs + (buf ^ 1) * TK * LDS, vg, a.ldv, k0 + TK, a.Lk, a.d, TK);
+            cp_async_commit();
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
         __syncthreads();
-        load_tile<DP>(Ks, kg, a.ldk, k0, a.Lk, a.d, TK);
-        load_tile<DP>(Vs, vg, a.ldv, k0, a.Lk, a.d, TK);
-        __syncthreads();
+        const uint32_t k_base = smem_addr(Ks + buf * TK * LDS), v_base = smem_addr(Vs + buf * TK * LDS);
         float s[TK / 8][4], dp[TK / 8][4];
 #pragma unroll
         for (int i = 0; i < TK / 8; ++i) {
@@ -376,6 +431,7 @@ __global__ void __launch_bounds__(NT) attn_any_bwd_q_kernel(const AnyArgs a) {
             dp[nt][3] = p3 * (dp[nt][3] - d1) * a.scale;
         }
         gemm_pn<DP, TK / 8>(dq, dp, k_base, lane);   // dQ += dS K
+        __syncthreads();
     }
     __nv_bfloat16* dqg = a.dq + (long long)b * a.Lq * a.lddq + (long long)h * a.d;
     store_slab<DP>(dq, 1.f, 1.f, dqg, a.lddq, row, a.Lq, a.d, lane);
@@ -383,7 +439,7 @@ __global__ void __launch_bounds__(NT) attn_any_bwd_q_kernel(const AnyArgs a) {
 
 template <int DP>
 int launch_fwd(const AnyArgs& a, cudaStream_t stream) {
-    constexpr int SMEM = (TQ + 2 * TK) * (DP + 8) * 2;
+    constexpr int SMEM = (TQ + 4 * TK) * (DP + 8) * 2;
     static bool attr = false;
     if (!attr) {
         UWU_CHECK_CUDA(cudaFuncSetAttribute(attn_any_fwd_kernel<DP>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
@@ -396,8 +452,8 @@ int launch_fwd(const AnyArgs& a, cudaStream_t stream) {
 
 template <int DP, int QT>
 int launch_bwd(const AnyArgs& a, cudaStream_t stream) {
-    constexpr int SMEM_KV = (2 * TK + 2 * QT) * (DP + 8) * 2 + 2 * QT * 4;
-    constexpr int SMEM_Q = (2 * TQ + 2 * TK) * (DP + 8) * 2;
+    constexpr int SMEM_KV = (2 * TK + 4 * QT) * (DP + 8) * 2 + 4 * QT * 4;
+    constexpr int SMEM_Q = (2 * TQ + 4 * TK) * (DP + 8) * 2;
     static bool attr = false;
     if (!attr) {
         UWU_CHECK_CUDA(cudaFuncSetAttribute(attn_any_bwd_kv_kernel<DP, QT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_KV));
