@@ -82,7 +82,9 @@ typedef struct uwu_gemm_desc {
     int32_t accumulate; /* fp32 output only: out += result */
     int32_t block_n;    /* 0 = choose */
     int32_t stream_k;   /* fp32 output, plain epilogue: 1 = split the (tile, k-block) space evenly over the SMs and
-                           reduce partial tiles with atomics, 0 = whole tiles per CTA, -1 = choose */
+                           reduce partial tiles with atomics; 2 = cut the reduction into slices (count chosen so that
+                           slices x tiles fills whole waves) dealt round-robin in slice-major order, so concurrent CTAs
+                           share one k-slice through L2; 0 = whole tiles per CTA; -1 = choose between 0 and 2 */
     /* segmented reduction (UWU_A_COL x UWU_B_KN): out = sum_{s < k_segs} A[:, s*a_seg_off + m]^T B[:, s*b_seg_off + n];
        K is the length of ONE segment. Used for the factored LoKr gradient dw2 = sum_l dY_l^T Z_l. 0/1 = off. */
     int32_t k_segs, a_seg_off, b_seg_off;

@@ -146,6 +146,19 @@ def case_wgrad():
                2.0 * Mtok * Co * Ci)
 
 
+def case_wgrad_dit():
+    """DiT-XL/2 full fine-tune weight gradients (tokens 65536) incl. accumulate=True as the trainer runs them."""
+    for (Mtok, Co, Ci) in [(65536, 1152, 4608), (65536, 4608, 1152), (65536, 3456, 1152), (65536, 1152, 1152)]:
+        dy, x = mk(Mtok, Co), mk(Mtok, Ci)
+        G = torch.zeros(Co, Ci, device=dev)
+        for sk in (0, 1, -1):
+            for bn in (0,):
+                tf(f"wgrad tokens{Mtok} {Co}x{Ci} stream_k={sk} bn={bn} accumulate",
+                   timeit(lambda: ops.gemm(dy, x, Co, Ci, Mtok, a_layout=A_COL, lda=Co, b_layout=B_KN, ldb=Ci, out=G, stream_k=sk,
+                                           block_n=bn, accumulate=True)), 2.0 * Mtok * Co * Ci)
+        tf(f"torch dY^T X {Co}x{Ci}", timeit(lambda: torch.matmul(dy.t(), x)), 2.0 * Mtok * Co * Ci)
+
+
 def case_lin():
     for (M, N, K) in [(16384, 1280, 1280), (16384, 3840, 1280), (16384, 10240, 1280), (16384, 1280, 5120), (65536, 640, 640),
                       (65536, 1920, 640), (65536, 5120, 640), (65536, 640, 2560)]:

@@ -74,6 +74,10 @@ struct GemmKernelArgs {
     int b_3d;  // MN-major B through a 3-D tensor map {64 n, K, N/64}: ONE TMA instruction per stage instead of block_n/64
     int stream_k;  // 1: the (tile, k-block) space is cut into equal contiguous ranges, one per CTA; partial tiles are
                    //    reduced with vector atomics into the fp32 output (which the host zeroed unless accumulating)
+                   // 2: the reduction is cut into sk_slices slices; units (slice, tile) are dealt round-robin in slice-major
+                   //    order, so the CTAs running at any moment share ONE k-slice of A and B through L2 (mode 1 spreads
+                   //    them over the whole reduction and re-reads every operand slab from HBM once per tile)
+    int sk_slices;
 };
 
 // One unit of work for the three warp roles: k-blocks [kb0, kb1) of output tile `tile`.
@@ -82,10 +86,17 @@ struct WorkIter {
     int step, num_kb, stream_k;
     int tile, kb0, kb1;
     int pair = 0, rank = 0, nnt = 1;
+    int slices = 1, ntiles = 1;
     __device__ __forceinline__ void init(const GemmKernelArgs& p, int num_tiles) {
         num_kb = p.num_kb;
         stream_k = p.stream_k;
-        if (stream_k) {
+        if (stream_k == 2) {
+            slices = p.sk_slices;
+            ntiles = num_tiles;
+            cur = blockIdx.x;
+            end = (long long)num_tiles * slices;
+            step = gridDim.x;
+        } else if (stream_k) {
             const long long units = (long long)num_tiles * num_kb;
             cur = units * blockIdx.x / gridDim.x;
             end = units * (blockIdx.x + 1) / gridDim.x;
@@ -106,7 +117,13 @@ struct WorkIter {
     }
     __device__ __forceinline__ bool next() {
         if (cur >= end) return false;
-        if (stream_k) {
+        if (stream_k == 2) {
+            const int sl = (int)(cur / ntiles);
+            tile = (int)(cur - (long long)sl * ntiles);
+            kb0 = (int)((long long)num_kb * sl / slices);
+            kb1 = (int)((long long)num_kb * (sl + 1) / slices);
+            cur += step;
+        } else if (stream_k) {
             tile = (int)(cur / num_kb);
             kb0 = (int)(cur - (long long)tile * num_kb);
             const long long left = end - cur;
@@ -822,11 +839,40 @@ extern "C" int uwu_gemm(const uwu_gemm_desc* d, void* stream_) {
     // stream-K: few output tiles but a long reduction (token-reduction weight gradients) would leave most SMs idle
     const int n_tiles_all = p.num_m_tiles * p.num_n_tiles;
     int sk = d->stream_k;
-    if (sk < 0) {
+    p.sk_slices = 1;
+    if (sk < 0 || sk == 2) {
         const int sms = sm_count();
+        const bool ok = p.out_fp32 && !d->bias && !d->bias_rows && !d->residual && p.num_kb >= 32;
         const int waves = (n_tiles_all + sms - 1) / sms;
-        sk = (p.out_fp32 && !d->bias && !d->bias_rows && !d->residual && p.num_kb >= 32 &&
-              (double)n_tiles_all < 0.85 * (double)waves * sms) ? 1 : 0;
+        const double operand_bytes = (double)p.num_kb * 64.0 * ((double)p.M + (double)p.N) * 2.0;
+        if (!ok) {
+            sk = 0;
+        } else if (sk < 0 && operand_bytes <= 96e6) {
+            // both operands stay L2-resident whatever the schedule: perfectly balanced contiguous ranges
+            sk = ((double)n_tiles_all < 0.85 * (double)waves * sms) ? 1 : 0;
+        } else {
+            // S slices so that S * tiles fills whole waves; a unit costs max(its k-blocks, ~24 k-blocks of atomic epilogue)
+            const double t1 = (double)waves * p.num_kb;
+            double best = t1;
+            int best_s = 1;
+            int max_s = p.num_kb / 8;
+            if (max_s > 64) max_s = 64;
+            for (int S = 2; S <= max_s; ++S) {
+                const long long units = (long long)n_tiles_all * S;
+                const double per = (double)p.num_kb / S;
+                const double t = (double)((units + sms - 1) / sms) * (per > 24.0 ? per : 24.0);
+                if (t < best * 0.98) {
+                    best = t;
+                    best_s = S;
+                }
+            }
+            if (best_s > 1 && best <= 0.8 * t1) {
+                sk = 2;
+                p.sk_slices = best_s;
+            } else {
+                sk = 0;
+            }
+        }
     }
     if (sk) {
         UWU_CHECK_ARG(p.out_fp32 && !d->bias && !d->bias_rows && !d->residual,
@@ -858,7 +904,8 @@ extern "C" int uwu_gemm(const uwu_gemm_desc* d, void* stream_) {
     const int num_tiles = p.num_m_tiles * p.num_n_tiles;
     int grid = sm_count();
     if (!p.stream_k && grid > num_tiles) grid = num_tiles;
-    if (p.stream_k && (long long)grid > (long long)num_tiles * p.num_kb) grid = (int)((long long)num_tiles * p.num_kb);
+    if (p.stream_k == 1 && (long long)grid > (long long)num_tiles * p.num_kb) grid = (int)((long long)num_tiles * p.num_kb);
+    if (p.stream_k == 2 && (long long)grid > (long long)num_tiles * p.sk_slices) grid = num_tiles * p.sk_slices;
     // 2-CTA clusters sharing each B tile through TMA multicast: a third less L2 -> shared-memory traffic per FLOP
     p.cluster2 = 0;
     p.b_half_bytes = 0;
