@@ -104,8 +104,10 @@ def test_enable_conv_and_unknown_algo_fail_loudly():
 
 
 def test_unsupported_architectures_fail_loudly():
-    with pytest.raises(NotImplementedError):  # SD-1.5: head_dim 40
-        P.UNet2DConditionModel(**U.tiny_config(block_out_channels=(320, 640), attention_head_dim=(8, 8)))
+    # SD-1.5 head dims (40 / 80 / 160) are supported; widths that are not multiples of 8 or exceed 160 are not
+    P.UNet2DConditionModel(**U.tiny_config(block_out_channels=(320, 640), attention_head_dim=(8, 8)))
+    with pytest.raises(NotImplementedError):
+        P.UNet2DConditionModel(**U.tiny_config(block_out_channels=(320, 640), attention_head_dim=(32, 2)))   # 10 and 320 wide
     with pytest.raises(NotImplementedError):
         P.UNet2DConditionModel(**U.tiny_config(block_out_channels=(48, 96)))
     with pytest.raises(OSError):
@@ -294,3 +296,28 @@ def test_sd15_known_config_builds_on_meta():
     n = sum(q.numel() for q in m.parameters())
     assert abs(n - 859_520_964) < 1000, n   # public parameter count of the SD-1.5 UNet
     assert m.mid_block.attentions[0].transformer_blocks[0].attn1.dim_head == 160
+
+
+def test_dit_parameter_names_config_and_flops():
+    """DiT host logic without a GPU: parameter names / shapes of the public DiT implementation, DiT-XL/2 size, FLOP model."""
+    from oracle import dit_oracle as DO
+    from uwudiff_b200 import dit as PD
+
+    cfg = DO.tiny_config()
+    o, p = DO.DiT(**cfg), PD.DiT(**cfg)
+    so, sp = o.state_dict(), p.state_dict()
+    assert set(so) == set(sp) and all(so[k].shape == sp[k].shape for k in so)
+    assert "blocks.0.adaLN_modulation.1.weight" in sp and sp["x_embedder.proj.weight"].shape == (144, 4, 2, 2)
+    assert torch.allclose(p.pos_embed, o.pos_embed)
+    with torch.device("meta"):
+        xl = PD.DiT(**PD.DiT.load_config("DiT-XL/2"))
+    assert abs(sum(q.numel() for q in xl.parameters()) - 675e6) < 1e6
+    assert abs(PD.dit_forward_flops(PD.DIT_XL_2_CONFIG)["total"] / 1e12 - 0.2372) < 1e-3   # SURVEY.md §8(d)
+    with pytest.raises(RuntimeError):  # no CPU fallback
+        p(torch.randn(1, 4, 16, 16), torch.tensor([1]), class_labels=torch.tensor([0]))
+    with pytest.raises(NotImplementedError):
+        PD.DiT(**DO.tiny_config(hidden_size=100, num_heads=2))
+    with pytest.raises(OSError):
+        PD.DiT.from_config("nobody/unknown-dit")
+    p.init_weight()
+    assert float(p.final_layer.linear.weight.abs().max()) == 0.0 and float(p.blocks[0].adaLN_modulation[1].weight.abs().max()) == 0.0
