@@ -269,6 +269,8 @@ int uwu_axpy_f32(const float* a, const float* b, float alpha, int32_t n, float* 
  * entry chunk_entry[c], elements [(c - chunk0) * chunk_elems, +chunk_elems) of its N*K weight (K % 4 == 0).
  *   kind 0: dst_bf16 = W                         kind 1: dst_bf16 = W + kron(a [N/p0, p2], b [p0, p1]) * scale   (LoKr)
  *   kind 2: dst_bf16 = W + (a [N, p0] @ b [p0, K]) * scale (LoRA)   kind 3: dst_f32 = W + a * scale  (norm deltas, N = 1)
+ *   kind 4: dst_bf16 = W + ((a [N, p0] @ b [p0, K]) o ((a + p1) [N, p0] @ (a + p2) [p0, K])) * scale (LoHa; the second factor
+ *           pair is addressed by element offsets from `a`: all adapter parameters live in one flat buffer)
  * Same arithmetic as uwu_fold_lokr / uwu_fold_lora / uwu_axpy_f32 (bit-identical results). */
 typedef struct uwu_fold_entry {
     const float* W;
@@ -293,6 +295,11 @@ int uwu_conv_wgrad_unpack(const float* G, int64_t ldg, int32_t Co, int32_t Ci, i
                           float* wgrad, void* stream);
 int uwu_colsum_groups_bf16(const void* x, int64_t ldx, int32_t groups, int32_t rows, int32_t C, int32_t accumulate, float* out,
                            void* stream);
+/* LoHa (lycoris `loha`): dW = ((w1a @ w1b) o (w2a @ w2b)) * scale, factors [N, r] / [r, K], r <= 16 */
+int uwu_fold_loha(const float* W, const float* w1a, const float* w1b, const float* w2a, const float* w2b, int32_t N, int32_t K,
+                  int32_t r, float scale, void* dst_bf16, void* stream);
+int uwu_loha_grad(const float* G, int64_t ldg, const float* w1a, const float* w1b, const float* w2a, const float* w2b, int32_t N,
+                  int32_t K, int32_t r, float scale, float* dw1a, float* dw1b, float* dw2a, float* dw2b, void* stream);
 /* adapter gradients from G = dY^T X (fp32 [N, ldg]); dw1/dw2 (dup/ddown) are ACCUMULATED into */
 int uwu_lokr_grad(const float* G, int64_t ldg, const float* w1, const float* w2, int32_t out_l, int32_t out_k, int32_t in_m,
                   int32_t in_n, float multiplier, float* dw1, float* dw2, void* stream);

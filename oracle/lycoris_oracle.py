@@ -63,6 +63,33 @@ class LoraLinear(nn.Module):
         return F.linear(x, org.weight + self.delta().to(org.weight.dtype) * self.multiplier, org.bias)
 
 
+class LohaLinear(nn.Module):
+    """LyCORIS `loha` (Hadamard product of two low-rank products) **[restated]**: dW = (w1a @ w1b) * (w2a @ w2b) * alpha/r;
+    init: w1_b ~ N(0, 1), w1_a ~ N(0, 0.1), w2_b ~ N(0, 1), w2_a = 0 (so dW starts at 0)."""
+
+    def __init__(self, name: str, org: nn.Linear, multiplier: float, dim: int, alpha: float):
+        super().__init__()
+        self.lora_name, self.multiplier, self.dim = name, multiplier, dim
+        self.hada_w1_a = nn.Parameter(torch.empty(org.out_features, dim))
+        self.hada_w1_b = nn.Parameter(torch.empty(dim, org.in_features))
+        self.hada_w2_a = nn.Parameter(torch.empty(org.out_features, dim))
+        self.hada_w2_b = nn.Parameter(torch.empty(dim, org.in_features))
+        self.register_buffer("alpha", torch.tensor(float(alpha)))
+        self.scale = alpha / dim
+        nn.init.normal_(self.hada_w1_b, std=1)
+        nn.init.normal_(self.hada_w1_a, std=0.1)
+        nn.init.normal_(self.hada_w2_b, std=1)
+        nn.init.constant_(self.hada_w2_a, 0)
+        self.org = [org]
+
+    def delta(self):
+        return (self.hada_w1_a @ self.hada_w1_b) * (self.hada_w2_a @ self.hada_w2_b) * self.scale
+
+    def forward(self, x):
+        org = self.org[0]
+        return F.linear(x, org.weight + self.delta().to(org.weight.dtype) * self.multiplier, org.bias)
+
+
 class LokrLinear(nn.Module):
     """full_matrix LoKr: both Kronecker factors dense (no low-rank split), scale forced to 1."""
 
@@ -139,6 +166,8 @@ class LycorisNetwork(nn.Module):
                     return LokrLinear(name, mod, multiplier, linear_dim, linear_alpha, int(cfg.get("factor", -1)))
                 if algo == "lora":
                     return LoraLinear(name, mod, multiplier, linear_dim, linear_alpha)
+                if algo == "loha":
+                    return LohaLinear(name, mod, multiplier, linear_dim, linear_alpha)
                 raise NotImplementedError(algo)
             if isinstance(mod, (nn.GroupNorm, nn.LayerNorm)) and train_norm:
                 return NormDelta(name, mod, multiplier)

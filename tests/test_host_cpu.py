@@ -97,7 +97,7 @@ def test_enable_conv_and_unknown_algo_fail_loudly():
     PL.LycorisNetwork.apply_preset(dict(LYCORIS_PRESET, enable_conv=True))
     with pytest.raises(NotImplementedError):
         PL.create_lycoris(p, **LYCORIS_CFG)
-    PL.LycorisNetwork.apply_preset(dict(LYCORIS_PRESET, module_algo_map={"Attention": dict(algo="loha")}))
+    PL.LycorisNetwork.apply_preset(dict(LYCORIS_PRESET, module_algo_map={"Attention": dict(algo="dylora")}))
     with pytest.raises(NotImplementedError):
         PL.create_lycoris(p, **LYCORIS_CFG)
     PL.LycorisNetwork.apply_preset(LYCORIS_PRESET)

@@ -436,6 +436,28 @@ def test_lora_fold_and_grads(ops):
     assert relerr(dup, G @ down.t() * scale) < 1e-4 and relerr(ddown, up.t() @ G * scale) < 1e-4
 
 
+@pytest.mark.parametrize("N,K,r", [(640, 320, 4), (128, 2048, 8), (1280, 1280, 16), (24, 36, 1)])
+def test_loha_fold_and_grads(ops, N, K, r):
+    """LoHa: dW = (w1a @ w1b) o (w2a @ w2b) * scale; factor gradients from G vs autograd (fp32)."""
+    scale = 1.0 / r
+    g = torch.Generator(device=DEV).manual_seed(N + K + r)
+    W = torch.randn(N, K, device=DEV, generator=g) * 0.1
+    f = [torch.randn(s, device=DEV, generator=g).requires_grad_(True) for s in ((N, r), (r, K), (N, r), (r, K))]
+    w1a, w1b, w2a, w2b = f
+    dst = torch.empty(N, K, device=DEV, dtype=torch.bfloat16)
+    ops.fold_loha(W, w1a.detach(), w1b.detach(), w2a.detach(), w2b.detach(), scale, dst)
+    ref = W + (w1a @ w1b) * (w2a @ w2b) * scale
+    assert relerr(dst, ref.detach()) < TOL_BF16
+    G = torch.randn(N, K, device=DEV, generator=g)
+    ref.backward(G)
+    grads = [torch.zeros_like(t) for t in f]
+    ops.loha_grad(G, w1a.detach(), w1b.detach(), w2a.detach(), w2b.detach(), scale, *[grads[i] for i in (0, 1, 2, 3)])
+    for got, t in zip(grads, f):
+        assert relerr(got, t.grad) < 1e-4
+    ops.loha_grad(G, w1a.detach(), w1b.detach(), w2a.detach(), w2b.detach(), scale, *grads)   # accumulates
+    assert relerr(grads[1], 2 * w1b.grad) < 1e-4
+
+
 def test_fused_adamw_and_clip_match_torch():
     from uwudiff_b200.optim import FusedAdamW
 

@@ -41,11 +41,11 @@ def build(seed=0, B=2, HW=16, zero_init=False):
     return cfg, o, p, x, t, ctx, ac
 
 
-def with_lycoris(o, p, scale=0.05):
+def with_lycoris(o, p, scale=0.05, preset=None):
     from uwudiff_b200 import lycoris as PL
 
-    LY.LycorisNetwork.apply_preset(LYCORIS_PRESET)
-    PL.LycorisNetwork.apply_preset(LYCORIS_PRESET)
+    LY.LycorisNetwork.apply_preset(preset or LYCORIS_PRESET)
+    PL.LycorisNetwork.apply_preset(preset or LYCORIS_PRESET)
     no = LY.create_lycoris(o, **LYCORIS_CFG)
     g = torch.Generator().manual_seed(1)
     for prm in no.parameters():  # non-trivial adapter state so every delta matters
@@ -120,6 +120,34 @@ def test_lycoris_forward_and_adapter_gradients_match_oracle():
     yp2.backward(gout.cuda())
     tot_p2 = torch.sqrt(sum((q.grad.float() ** 2).sum() for q in npd.parameters())).item()
     assert abs(tot_p2 - 2 * tot_o) / (2 * tot_o) < 1e-2
+
+
+def test_loha_adapters_forward_and_gradients_match_oracle():
+    """north_star (d): LoHa deltas folded into the base GEMM operand, their low-rank gradients from the same backward."""
+    cfg, o, p, x, t, ctx, ac = build(seed=4)
+    preset = dict(LYCORIS_PRESET, module_algo_map={"Attention": dict(algo="loha"), "FeedForward": dict(algo="loha")})
+    try:
+        no, npd = with_lycoris(o, p, scale=0.2, preset=preset)
+        assert any(n.endswith("hada_w1_a") for n, _ in npd.named_parameters())
+        gout = torch.randn(x.shape, generator=torch.Generator().manual_seed(2))
+        yo = o(x, t, encoder_hidden_states=ctx, added_cond_kwargs=ac)[0]
+        yo.backward(gout)
+        yp = p(x.cuda(), t.cuda(), **cuda_kwargs(ctx, ac))[0]
+        yp.backward(gout.cuda())
+        torch.cuda.synchronize()
+        assert rel(yp, yo) < 3e-2
+        po = dict(no.named_parameters())
+        assert [n for n, _ in npd.named_parameters()] == list(po.keys())
+        worst = max(rel(prm.grad, po[n].grad) for n, prm in npd.named_parameters())
+        assert worst < 1.5e-1, worst
+        tot_o = torch.sqrt(sum((q.grad.float() ** 2).sum() for q in no.parameters())).item()
+        tot_p = torch.sqrt(sum((q.grad.float() ** 2).sum() for q in npd.parameters())).item()
+        assert abs(tot_p - tot_o) / tot_o < 1e-2
+    finally:
+        from uwudiff_b200 import lycoris as PL
+
+        LY.LycorisNetwork.apply_preset(LYCORIS_PRESET)
+        PL.LycorisNetwork.apply_preset(LYCORIS_PRESET)
 
 
 @pytest.mark.parametrize("ttype,snr,deb", [("v_prediction", True, False), ("epsilon", True, True)])

@@ -104,6 +104,8 @@ SIGNATURES = {
     "uwu_phase_split2": (C.c_int, [_P, _I32, _I32, _I32, _I32, _I32, _P, _P]),
     "uwu_colsum_workspace_floats": (C.c_int64, [_I64, _I32]),
     "uwu_colsum_bf16": (C.c_int, [_P, _I64, _I32, _I64, _I32, _P, _P, _P]),
+    "uwu_fold_loha": (C.c_int, [_P, _P, _P, _P, _P, _I32, _I32, _I32, _F, _P, _P]),
+    "uwu_loha_grad": (C.c_int, [_P, _I64, _P, _P, _P, _P, _I32, _I32, _I32, _F, _P, _P, _P, _P, _P]),
     "uwu_fold_lokr": (C.c_int, [_P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _F, _P, _P]),
     "uwu_fold_lora": (C.c_int, [_P, _P, _P, _I32, _I32, _I32, _F, _P, _P]),
     "uwu_axpy_f32": (C.c_int, [_P, _P, _F, _I32, _P, _P]),

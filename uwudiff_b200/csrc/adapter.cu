@@ -63,6 +63,125 @@ __global__ void fold_lora_kernel(const float* __restrict__ W, const float* __res
     }
 }
 
+// LoHa delta for 4 consecutive columns of row n: (sum_q w1a[n,q] w1b[q,k]) * (sum_q w2a[n,q] w2b[q,k])
+__device__ __forceinline__ void loha_delta4(const float* __restrict__ w1a, const float* __restrict__ w1b,
+                                            const float* __restrict__ w2a, const float* __restrict__ w2b, int n, int k, int K, int r,
+                                            float (&d)[4]) {
+    float p1[4] = {0.f, 0.f, 0.f, 0.f}, p2[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int q = 0; q < r; ++q) {
+        const float u1 = w1a[n * r + q], u2 = w2a[n * r + q];
+        const float4 b1 = *reinterpret_cast<const float4*>(w1b + (size_t)q * K + k);
+        const float4 b2 = *reinterpret_cast<const float4*>(w2b + (size_t)q * K + k);
+        p1[0] = fmaf(u1, b1.x, p1[0]); p1[1] = fmaf(u1, b1.y, p1[1]); p1[2] = fmaf(u1, b1.z, p1[2]); p1[3] = fmaf(u1, b1.w, p1[3]);
+        p2[0] = fmaf(u2, b2.x, p2[0]); p2[1] = fmaf(u2, b2.y, p2[1]); p2[2] = fmaf(u2, b2.z, p2[2]); p2[3] = fmaf(u2, b2.w, p2[3]);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) d[j] = p1[j] * p2[j];
+}
+
+__global__ void fold_loha_kernel(const float* __restrict__ W, const float* __restrict__ w1a, const float* __restrict__ w1b,
+                                 const float* __restrict__ w2a, const float* __restrict__ w2b, int N, int K, int r, float s,
+                                 __nv_bfloat16* __restrict__ dst) {
+    const long long total = (long long)N * K / 4;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long e = i * 4;
+        const int n = (int)(e / K), k = (int)(e - (long long)n * K);
+        const float4 w = *reinterpret_cast<const float4*>(W + e);
+        float d[4];
+        loha_delta4(w1a, w1b, w2a, w2b, n, k, K, r, d);
+        uint2 o;
+        o.x = pack_bf16(w.x + d[0] * s, w.y + d[1] * s);
+        o.y = pack_bf16(w.z + d[2] * s, w.w + d[3] * s);
+        *reinterpret_cast<uint2*>(dst + e) = o;
+    }
+}
+
+// LoHa gradients from G = dL/dW_eff [N, K]: dP1 = s G o P2, dP2 = s G o P1 with P1 = w1a w1b, P2 = w2a w2b (rank r <= 16)
+//   rows kernel: one warp per row n      -> dw1a[n, :] += dP1[n, :] w1b^T,  dw2a[n, :] += dP2[n, :] w2b^T
+//   cols kernel: one thread per column k -> dw1b[:, k] += w1a^T dP1[:, k],  dw2b[:, k] += w2a^T dP2[:, k]  (rows split over
+//                blockIdx.y, partial sums added atomically)
+constexpr int LOHA_MAXR = 16;
+__global__ void __launch_bounds__(256) loha_grad_rows_kernel(const float* __restrict__ G, long long ldg,
+                                                             const float* __restrict__ w1a, const float* __restrict__ w1b,
+                                                             const float* __restrict__ w2a, const float* __restrict__ w2b, int N,
+                                                             int K, int r, float s, float* __restrict__ dw1a,
+                                                             float* __restrict__ dw2a) {
+    const int n = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (n >= N) return;
+    float u1[LOHA_MAXR], u2[LOHA_MAXR], a1[LOHA_MAXR], a2[LOHA_MAXR];
+#pragma unroll
+    for (int q = 0; q < LOHA_MAXR; ++q) {
+        u1[q] = q < r ? w1a[n * r + q] : 0.f;
+        u2[q] = q < r ? w2a[n * r + q] : 0.f;
+        a1[q] = a2[q] = 0.f;
+    }
+    for (int k = lane; k < K; k += 32) {
+        float p1 = 0.f, p2 = 0.f;
+#pragma unroll
+        for (int q = 0; q < LOHA_MAXR; ++q)
+            if (q < r) {
+                p1 = fmaf(u1[q], w1b[(size_t)q * K + k], p1);
+                p2 = fmaf(u2[q], w2b[(size_t)q * K + k], p2);
+            }
+        const float g = G[(size_t)n * ldg + k] * s;
+        const float d1 = g * p2, d2 = g * p1;
+#pragma unroll
+        for (int q = 0; q < LOHA_MAXR; ++q)
+            if (q < r) {
+                a1[q] = fmaf(d1, w1b[(size_t)q * K + k], a1[q]);
+                a2[q] = fmaf(d2, w2b[(size_t)q * K + k], a2[q]);
+            }
+    }
+#pragma unroll
+    for (int q = 0; q < LOHA_MAXR; ++q)
+        if (q < r) {
+            const float s1 = warp_sum(a1[q]), s2 = warp_sum(a2[q]);
+            if (lane == 0) {
+                dw1a[n * r + q] += s1;
+                dw2a[n * r + q] += s2;
+            }
+        }
+}
+__global__ void __launch_bounds__(128) loha_grad_cols_kernel(const float* __restrict__ G, long long ldg,
+                                                             const float* __restrict__ w1a, const float* __restrict__ w1b,
+                                                             const float* __restrict__ w2a, const float* __restrict__ w2b, int N,
+                                                             int K, int r, int rows_per, float s, float* __restrict__ dw1b,
+                                                             float* __restrict__ dw2b) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= K) return;
+    const int n0 = blockIdx.y * rows_per, n1 = min(N, n0 + rows_per);
+    float b1[LOHA_MAXR], b2[LOHA_MAXR], a1[LOHA_MAXR], a2[LOHA_MAXR];
+#pragma unroll
+    for (int q = 0; q < LOHA_MAXR; ++q) {
+        b1[q] = q < r ? w1b[(size_t)q * K + k] : 0.f;
+        b2[q] = q < r ? w2b[(size_t)q * K + k] : 0.f;
+        a1[q] = a2[q] = 0.f;
+    }
+    for (int n = n0; n < n1; ++n) {
+        float p1 = 0.f, p2 = 0.f;
+#pragma unroll
+        for (int q = 0; q < LOHA_MAXR; ++q)
+            if (q < r) {
+                p1 = fmaf(w1a[n * r + q], b1[q], p1);
+                p2 = fmaf(w2a[n * r + q], b2[q], p2);
+            }
+        const float g = G[(size_t)n * ldg + k] * s;
+        const float d1 = g * p2, d2 = g * p1;
+#pragma unroll
+        for (int q = 0; q < LOHA_MAXR; ++q)
+            if (q < r) {
+                a1[q] = fmaf(w1a[n * r + q], d1, a1[q]);
+                a2[q] = fmaf(w2a[n * r + q], d2, a2[q]);
+            }
+    }
+#pragma unroll
+    for (int q = 0; q < LOHA_MAXR; ++q)
+        if (q < r) {
+            atomicAdd(&dw1b[(size_t)q * K + k], a1[q]);
+            atomicAdd(&dw2b[(size_t)q * K + k], a2[q]);
+        }
+}
+
 // All adapter folds of one step in ONE launch: block -> (entry, chunk) through a table built once on the host.
 __global__ void __launch_bounds__(256) fold_batch_kernel(const uwu_fold_entry* __restrict__ entries,
                                                          const int32_t* __restrict__ chunk_entry, int chunk_elems) {
@@ -98,6 +217,11 @@ __global__ void __launch_bounds__(256) fold_batch_kernel(const uwu_fold_entry* _
                 const float4 dn = *reinterpret_cast<const float4*>(e.b + (size_t)q * K + k);
                 d[0] = fmaf(u, dn.x, d[0]); d[1] = fmaf(u, dn.y, d[1]); d[2] = fmaf(u, dn.z, d[2]); d[3] = fmaf(u, dn.w, d[3]);
             }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v[j] = v[j] + d[j] * e.scale;
+        } else if (e.kind == 4) {  // LoHa: + (w1a @ w1b) o (w2a @ w2b) * scale; w2a / w2b = a + p1 / a + p2 (one flat buffer)
+            float d[4];
+            loha_delta4(e.a, e.b, e.a + e.p1, e.a + e.p2, n, k, K, e.p0, d);
 #pragma unroll
             for (int j = 0; j < 4; ++j) v[j] = v[j] + d[j] * e.scale;
         }
@@ -528,6 +652,37 @@ extern "C" int uwu_lokr_grad(const float* G, int64_t ldg, const float* w1, const
     else
         lokr_grad_kernel<false><<<n1 + n2, 256, 0, stream>>>(G, ldg, w1, w2, out_l, out_k, in_m, in_n, rows_per, splits, l_per, lsplits,
                                                             blocks2, n1, multiplier, dw1, dw2);
+    UWU_CHECK_LAUNCH();
+    return UWU_OK;
+}
+
+extern "C" int uwu_fold_loha(const float* W, const float* w1a, const float* w1b, const float* w2a, const float* w2b, int32_t N,
+                             int32_t K, int32_t r, float scale, void* dst_bf16, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    UWU_CHECK_ARG(W && w1a && w1b && w2a && w2b && dst_bf16 && N > 0 && K > 0 && K % 4 == 0 && r > 0, "uwu_fold_loha: bad arguments");
+    UWU_CHECK_ARG(((reinterpret_cast<uintptr_t>(w1b) | reinterpret_cast<uintptr_t>(w2b) | reinterpret_cast<uintptr_t>(W)) & 15) == 0,
+                  "uwu_fold_loha: W / w1b / w2b must be 16-byte aligned");
+    fold_loha_kernel<<<grid_for((long long)N * K / 4, 256), 256, 0, stream>>>(W, w1a, w1b, w2a, w2b, N, K, r, scale,
+                                                                             reinterpret_cast<__nv_bfloat16*>(dst_bf16));
+    UWU_CHECK_LAUNCH();
+    return UWU_OK;
+}
+
+extern "C" int uwu_loha_grad(const float* G, int64_t ldg, const float* w1a, const float* w1b, const float* w2a, const float* w2b,
+                             int32_t N, int32_t K, int32_t r, float scale, float* dw1a, float* dw1b, float* dw2a, float* dw2b,
+                             void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    UWU_CHECK_ARG(G && w1a && w1b && w2a && w2b && dw1a && dw1b && dw2a && dw2b && N > 0 && K > 0 && ldg >= K,
+                  "uwu_loha_grad: bad arguments");
+    UWU_CHECK_ARG(r > 0 && r <= LOHA_MAXR, "uwu_loha_grad: rank %d unsupported (1..%d)", r, LOHA_MAXR);
+    loha_grad_rows_kernel<<<(N + 7) / 8, 256, 0, stream>>>(G, ldg, w1a, w1b, w2a, w2b, N, K, r, scale, dw1a, dw2a);
+    UWU_CHECK_LAUNCH();
+    int splits = (2 * sm_count() * 128 + K - 1) / K;
+    if (splits < 1) splits = 1;
+    if (splits > N) splits = N;
+    const int rows_per = (N + splits - 1) / splits;
+    loha_grad_cols_kernel<<<dim3((K + 127) / 128, (N + rows_per - 1) / rows_per), 128, 0, stream>>>(G, ldg, w1a, w1b, w2a, w2b, N, K, r,
+                                                                                                 rows_per, scale, dw1b, dw2b);
     UWU_CHECK_LAUNCH();
     return UWU_OK;
 }

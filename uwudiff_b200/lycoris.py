@@ -84,6 +84,39 @@ class LoraLinear(_Adapter):
         return (self.lora_up.weight @ self.lora_down.weight) * self.scale
 
 
+class LohaLinear(_Adapter):
+    """lycoris `loha`: dW = (hada_w1_a @ hada_w1_b) o (hada_w2_a @ hada_w2_b) * alpha / r, folded into the bf16 GEMM operand;
+    factor gradients from G = dY^T X (uwu_loha_grad)."""
+
+    def __init__(self, name: str, org: nn.Linear, multiplier: float, dim: int, alpha: float):
+        super().__init__()
+        if dim > 16:
+            raise NotImplementedError("uwudiff_b200.lycoris: LoHa rank > 16 is not built")
+        self.lora_name, self.multiplier, self.dim = name, multiplier, dim
+        self.hada_w1_a = nn.Parameter(torch.empty(org.out_features, dim))
+        self.hada_w1_b = nn.Parameter(torch.empty(dim, org.in_features))
+        self.hada_w2_a = nn.Parameter(torch.empty(org.out_features, dim))
+        self.hada_w2_b = nn.Parameter(torch.empty(dim, org.in_features))
+        self.register_buffer("alpha", torch.tensor(float(alpha)))
+        self.scale = alpha / dim
+        nn.init.normal_(self.hada_w1_b, std=1)
+        nn.init.normal_(self.hada_w1_a, std=0.1)
+        nn.init.normal_(self.hada_w2_b, std=1)
+        nn.init.constant_(self.hada_w2_a, 0)
+
+    def fold_into(self, W, dst):
+        ops.fold_loha(W, self.hada_w1_a, self.hada_w1_b, self.hada_w2_a, self.hada_w2_b, self.scale * self.multiplier, dst)
+
+    def grads_from(self, G):
+        from .unet import _grad_of
+
+        ops.loha_grad(G, self.hada_w1_a, self.hada_w1_b, self.hada_w2_a, self.hada_w2_b, self.scale * self.multiplier,
+                      _grad_of(self.hada_w1_a), _grad_of(self.hada_w1_b), _grad_of(self.hada_w2_a), _grad_of(self.hada_w2_b))
+
+    def delta(self):
+        return (self.hada_w1_a @ self.hada_w1_b) * (self.hada_w2_a @ self.hada_w2_b) * self.scale
+
+
 class LokrLinear(_Adapter):
     def __init__(self, name: str, org: nn.Linear, multiplier: float, dim: int, alpha: float, factor: int):
         super().__init__()
@@ -196,7 +229,9 @@ class LycorisNetwork(nn.Module):
                     return LokrLinear(name, mod, multiplier, linear_dim, linear_alpha, int(cfg.get("factor", -1)))
                 if algo == "lora":
                     return LoraLinear(name, mod, multiplier, linear_dim, linear_alpha)
-                raise NotImplementedError(f"uwudiff_b200.lycoris: algo '{algo}' is not built (lora, lokr)")
+                if algo == "loha":
+                    return LohaLinear(name, mod, multiplier, linear_dim, linear_alpha)
+                raise NotImplementedError(f"uwudiff_b200.lycoris: algo '{algo}' is not built (lora, lokr, loha)")
             if isinstance(mod, (nn.GroupNorm, nn.LayerNorm)) and train_norm:
                 return NormDelta(name, mod, multiplier)
             return None
@@ -286,6 +321,13 @@ class LycorisNetwork(nn.Module):
                     (ol, ok), (im, inn) = lora.shape
                     add(1, org.weight, lora.lokr_w1, lora.lokr_w2, org.fold_dst(), org.out_features, org.in_features, ok, inn, im,
                         lora.scale * lora.multiplier)
+                elif isinstance(lora, LohaLinear):
+                    base = lora.hada_w1_a.data_ptr()
+                    off_a, off_b = lora.hada_w2_a.data_ptr() - base, lora.hada_w2_b.data_ptr() - base
+                    assert off_a % 4 == 0 and off_b % 4 == 0 and abs(off_a) < 2 ** 33 and abs(off_b) < 2 ** 33
+                    add(4, org.weight, lora.hada_w1_a, lora.hada_w1_b, org.fold_dst(), org.out_features, org.in_features,
+                        lora.dim, off_a // 4, off_b // 4, lora.scale * lora.multiplier)
+                    keep.extend([lora.hada_w2_a, lora.hada_w2_b])
                 else:
                     add(2, org.weight, lora.lora_up.weight, lora.lora_down.weight, org.fold_dst(), org.out_features,
                         org.in_features, lora.dim, scale=lora.scale * lora.multiplier)

@@ -532,6 +532,27 @@ def fold_lokr(W: torch.Tensor, w1: Optional[torch.Tensor], w2: Optional[torch.Te
     return dst
 
 
+def fold_loha(W, w1a, w1b, w2a, w2b, scale: float, dst: torch.Tensor) -> torch.Tensor:
+    """dst (bf16 [N,K]) = W + ((w1a @ w1b) * (w2a @ w2b)) * scale"""
+    _req_cuda(W, w1a, w1b, w2a, w2b, dst)
+    assert all(t.is_contiguous() and t.dtype == torch.float32 for t in (W, w1a, w1b, w2a, w2b)) and dst.is_contiguous()
+    N, K = W.shape
+    r = w1b.shape[0]
+    assert w1a.shape == w2a.shape == (N, r) and w1b.shape == w2b.shape == (r, K)
+    check(lib().uwu_fold_loha(_ptr(W), _ptr(w1a), _ptr(w1b), _ptr(w2a), _ptr(w2b), N, K, r, scale, _ptr(dst), _stream()),
+          "uwu_fold_loha")
+    return dst
+
+
+def loha_grad(G, w1a, w1b, w2a, w2b, scale: float, dw1a, dw1b, dw2a, dw2b):
+    """LoHa factor gradients (accumulated) from G = dL/dW_eff [N, K] fp32."""
+    _req_cuda(G, w1a, w1b, w2a, w2b, dw1a, dw1b, dw2a, dw2b)
+    N, K = G.shape
+    r = w1b.shape[0]
+    check(lib().uwu_loha_grad(_ptr(G), G.stride(0), _ptr(w1a), _ptr(w1b), _ptr(w2a), _ptr(w2b), N, K, r, scale, _ptr(dw1a),
+                              _ptr(dw1b), _ptr(dw2a), _ptr(dw2b), _stream()), "uwu_loha_grad")
+
+
 def fold_lora(W: torch.Tensor, up: torch.Tensor, down: torch.Tensor, scale: float, dst: torch.Tensor) -> torch.Tensor:
     _req_cuda(W, up, down, dst)
     assert W.is_contiguous() and up.is_contiguous() and down.is_contiguous() and dst.is_contiguous()
