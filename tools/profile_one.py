@@ -73,6 +73,29 @@ def main(what):
                                                             temb_dim=320, want_eps=False)
             ops.wmse_fwd(x_t, target, w)
             ops.wmse_bwd(x_t, target, w)
+    elif what == "dit":
+        # DiT-XL/2 shapes: token-reduction weight gradient under the three split-K schedules, d = 72 attention, adaLN glue
+        from uwudiff_b200._lib import A_COL, B_KN
+
+        Mtok, Co, Ci = 65536, 1152, 4608
+        dy, x = mk(Mtok, Co), mk(Mtok, Ci)
+        G = torch.zeros(Co, Ci, device=dev)
+        for sk in (0, 1, -1):
+            ops.gemm(dy, x, Co, Ci, Mtok, a_layout=A_COL, lda=Co, b_layout=B_KN, ldb=Ci, out=G, stream_k=sk, accumulate=True)
+        B, heads, L, d = 256, 16, 256, 72
+        C = heads * d
+        qkv, do = mk(B * L, 3 * C), mk(B * L, C)
+        q, k, v = qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:]
+        o, lse = ops.attn_fwd(q, k, v, B, heads, L, L, head_dim=d)
+        ops.attn_bwd(q, k, v, o, do, lse, B, heads, L, L, head_dim=d)
+        xt, dyt = mk(B * L, C), mk(B * L, C)
+        mod = torch.randn(B, 6 * C, device=dev)
+        dmod = torch.zeros(B, 6 * C, device=dev, dtype=torch.bfloat16)
+        y, st = ops.adaln_fwd(xt, mod, 0, C, L)
+        ops.adaln_bwd(xt, dyt, mod, C, st, L, dmod, 0, C, dres=dyt)
+        ops.gate_residual_fwd(xt, y, mod, 2 * C, L)
+        ops.gate_residual_bwd(dyt, y, mod, 2 * C, L, dmod, 2 * C)
+        ops.elementwise(mk(B * L, 4 * C), None, ops.EW_GELU_TANH)
     torch.cuda.synchronize()
 
 
