@@ -179,7 +179,9 @@ def test_conv_stride2_through_phase_planes(ops):
 # flash attention forward / backward (d = 64)
 # ------------------------------------------------------------------------------------------------------------------
 ATTN_SHAPES = [(1, 1, 128, 128), (1, 1, 256, 128), (1, 1, 128, 256), (2, 3, 256, 256), (2, 2, 1024, 1024), (2, 2, 64, 64),
-               (2, 5, 256, 77), (1, 2, 320, 200)]
+               (2, 5, 256, 77), (1, 2, 320, 200),
+               # short-key (cross-attention) kernels: Lk <= 128 with Lq_pad >= 2 * padded Lk; > 1024 queries = atomic dK/dV path
+               (2, 3, 1024, 77), (1, 2, 1100, 77), (1, 2, 2500, 100), (1, 1, 300, 3), (1, 2, 333, 128)]
 
 
 def attn_ref(q, k, v, B, heads, Lq, Lk, dout=None, d=64):
@@ -229,7 +231,7 @@ def test_attention_backward(ops, B, heads, Lq, Lk):
 
 
 # head dims other than 64 (SD-1.5: 40 / 80 / 160, DiT-XL/2: 72) run on the mma.sync kernels of attn_any.cu
-ATTN_ANY_SHAPES = [(2, 8, 256, 256, 40), (1, 8, 1024, 1024, 40), (2, 8, 256, 77, 80), (2, 4, 64, 64, 160), (1, 2, 200, 77, 160),
+ATTN_ANY_SHAPES = [(2, 8, 256, 77, 40), (1, 3, 1300, 77, 40), (2, 8, 256, 256, 40), (1, 8, 1024, 1024, 40), (2, 8, 256, 77, 80), (2, 4, 64, 64, 160), (1, 2, 200, 77, 160),
                    (3, 16, 256, 256, 72), (1, 3, 130, 70, 72), (1, 2, 320, 200, 128), (2, 2, 96, 96, 32), (1, 1, 64, 64, 8)]
 
 
@@ -258,6 +260,25 @@ def test_attention_any_strided_qkv(ops):
     ro, _, rdq, rdk, rdv = attn_ref(q.contiguous(), k.contiguous(), v.contiguous(), B, heads, L, L, do, d=d)
     assert relerr(o, ro) < TOL_ATTN
     assert relerr(dqkv, torch.cat([rdq, rdk, rdv], dim=1)) < TOL_ATTN
+
+
+@pytest.mark.parametrize("short_fwd,short_bwd,Lq", [("1", "1", 512), ("0", "0", 512), ("1", "0", 512), ("1", "1", 200), ("0", "1", 1500)])
+def test_attention_short_key_paths(ops, monkeypatch, short_fwd, short_bwd, Lq):
+    """Cross-attention shapes: the short-key forward (default) and opt-in backward, the tcgen05 kernels, and their mixes
+    (both use the same natural-log lse) against the fp32 reference, with strided (fused KV) operands."""
+    monkeypatch.setenv("UWU_ATTN_SHORT", short_fwd)
+    monkeypatch.setenv("UWU_ATTN_SHORT_BWD", short_bwd)
+    B, heads, Lk = 2, 4, 77
+    C = heads * 64
+    q, kv, do = mk(B * Lq, C, s=1.0), mk(B * Lk, 2 * C, s=1.0), mk(B * Lq, C, s=1.0)
+    k, v = kv[:, :C], kv[:, C:]
+    o, lse = ops.attn_fwd(q, k, v, B, heads, Lq, Lk)
+    dkv = torch.empty_like(kv)
+    dq, _, _ = ops.attn_bwd(q, k, v, o, do, lse, B, heads, Lq, Lk, dk=dkv[:, :C], dv=dkv[:, C:])
+    ro, rlse, rdq, rdk, rdv = attn_ref(q, k.contiguous(), v.contiguous(), B, heads, Lq, Lk, do)
+    assert relerr(o, ro) < TOL_ATTN and relerr(dq, rdq) < TOL_ATTN
+    assert relerr(dkv, torch.cat([rdk, rdv], dim=1)) < TOL_ATTN
+    assert relerr(lse.view(B, heads, -1)[:, :, :Lq], rlse) < 1e-4
 
 
 def test_attention_rejects_bad_head_dim(ops):

@@ -193,6 +193,18 @@ def case_bn640():
             tf(f"M{M} N{N} K{K} bn{bn} B_KN", timeit(lambda: ops.gemm(a, bt, M, N, K, b_layout=B_KN, ldb=N, out=out, block_n=bn)), 2.0 * M * N * K)
 
 
+def case_bn1280():
+    """Tile-width sweep for the N = 1280 class (384 launches per SDXL step): wave quantisation vs per-tile efficiency."""
+    for (M, N, K) in [(16384, 1280, 1280), (16384, 1280, 5120), (16384, 3840, 1280), (16384, 1280, 3840)]:
+        a, b, bt = mk(M, K), mk(N, K), mk(K, N)
+        out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+        res = mk(M, N)
+        for bn in (128, 160, 192, 224, 256):
+            tf(f"M{M} N{N} K{K} bn{bn} K-major B", timeit(lambda: ops.gemm(a, b, M, N, K, out=out, block_n=bn)), 2.0 * M * N * K)
+            tf(f"M{M} N{N} K{K} bn{bn} K-major B +res", timeit(lambda: ops.gemm(a, b, M, N, K, out=out, block_n=bn, residual=res)), 2.0 * M * N * K)
+            tf(f"M{M} N{N} K{K} bn{bn} B_KN", timeit(lambda: ops.gemm(a, bt, M, N, K, b_layout=B_KN, ldb=N, out=out, block_n=bn)), 2.0 * M * N * K)
+
+
 def case_lin_cold():
     """Same GEMMs with L2 flushed (a 512 MB copy) before every timed launch: the in-step condition for weights."""
     big = torch.empty(256 << 20, device=dev, dtype=torch.uint8)
@@ -246,6 +258,16 @@ def case_attn_any():
         tf(f"attn_fwd B{B} h{heads} L{L} Lk{Lk} d{d}", timeit(lambda: ops.attn_fwd(q, k, v, B, heads, L, Lk, head_dim=d)), fl)
         tf(f"attn_bwd B{B} h{heads} L{L} Lk{Lk} d{d} (2.5x)",
            timeit(lambda: ops.attn_bwd(q, k, v, o, do, lse, B, heads, L, Lk, head_dim=d)), 2.5 * fl)
+
+
+def case_attn_cross():
+    for (B, heads, L, Lk) in [(16, 20, 1024, 77), (16, 10, 4096, 77)]:
+        C = heads * 64
+        q, k, v, do = mk(B * L, C), mk(B * Lk, C), mk(B * Lk, C), mk(B * L, C)
+        o, lse = ops.attn_fwd(q, k, v, B, heads, L, Lk)
+        fl = 4.0 * B * heads * L * Lk * 64
+        tf(f"attn_fwd B{B} h{heads} L{L} Lk{Lk}", timeit(lambda: ops.attn_fwd(q, k, v, B, heads, L, Lk)), fl)
+        tf(f"attn_bwd B{B} h{heads} L{L} Lk{Lk} (2.5x)", timeit(lambda: ops.attn_bwd(q, k, v, o, do, lse, B, heads, L, Lk)), 2.5 * fl)
 
 
 if __name__ == "__main__":

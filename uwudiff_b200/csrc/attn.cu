@@ -755,6 +755,14 @@ int attn_any_bwd(const void* q, const void* k, const void* v, const void* o, con
                  long long ldo, long long lddo, long long lddq, long long lddk, long long lddv, float scale, float* workspace,
                  cudaStream_t stream);
 
+// short-key (cross-attention) kernels, attn_any.cu
+bool attn_short_ok(int Lq, int Lk, int d, bool backward);
+int attn_short_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int B, int heads, int Lq, int Lk, int d,
+                   long long ldq, long long ldk, long long ldv, long long ldo, float scale, cudaStream_t stream);
+int attn_short_bwd(const void* q, const void* k, const void* v, const void* dout, const float* lse, void* dq, void* dk, void* dv,
+                   int B, int heads, int Lq, int Lk, int d, long long ldq, long long ldk, long long ldv, long long lddo,
+                   long long lddq, long long lddk, long long lddv, float scale, float* workspace, cudaStream_t stream);
+
 }  // namespace uwu
 
 using namespace uwu;
@@ -782,6 +790,8 @@ extern "C" int uwu_attn_fwd(const void* q, const void* k, const void* v, void* o
     UWU_CHECK_ARG(q && k && v && o && lse, "uwu_attn_fwd: null pointer");
     UWU_CHECK_ARG(ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(o) & 15) == 0, "uwu_attn_fwd: output must be 16-byte aligned");
     if (head_dim > 64) return attn_any_fwd(q, k, v, o, lse, B, heads, Lq, Lk, head_dim, ldq, ldk, ldv, ldo, scale, stream);
+    if (attn_short_ok(Lq, Lk, head_dim, false))
+        return attn_short_fwd(q, k, v, o, lse, B, heads, Lq, Lk, head_dim, ldq, ldk, ldv, ldo, scale, stream);
     static thread_local AttnFwdArgs a;
     if (int rc = make_head_map(&a.tmQ, q, heads, head_dim, Lq, B, ldq, "q")) return rc;
     if (int rc = make_head_map(&a.tmK, k, heads, head_dim, Lk, B, ldk, "k")) return rc;
@@ -832,6 +842,9 @@ extern "C" int uwu_attn_bwd(const void* q, const void* k, const void* v, const v
     if (head_dim > 64)
         return attn_any_bwd(q, k, v, o, dout, lse, dq, dk, dv, B, heads, Lq, Lk, head_dim, ldq, ldk, ldv, ldo, lddo, lddq, lddk,
                             lddv, scale, workspace, stream);
+    if (attn_short_ok(Lq, Lk, head_dim, true))
+        return attn_short_bwd(q, k, v, dout, lse, dq, dk, dv, B, heads, Lq, Lk, head_dim, ldq, ldk, ldv, lddo, lddq, lddk, lddv,
+                              scale, workspace, stream);
     const int Lq_pad = (Lq + 127) / 128 * 128;
     const int64_t rows = (int64_t)B * heads * Lq_pad;
     float* lse2 = workspace;
