@@ -251,6 +251,7 @@ __global__ void __launch_bounds__(256) lokr_grad_kernel(const float* __restrict_
                                                         const float* __restrict__ w2, int ol, int ok, int im, int in_n, int rows_per,
                                                         int splits, int l_per, int lsplits, int blocks2, int n1, float mult,
                                                         float* __restrict__ dw1, float* __restrict__ dw2) {
+    pdl_trigger();
     if ((int)blockIdx.x < n1) {
         const int tile = blockIdx.x / splits, sp = blockIdx.x - tile * splits;
         const int l = tile / im, i = tile - l * im;
@@ -335,6 +336,7 @@ __global__ void __launch_bounds__(256) lokr_grad_kernel(const float* __restrict_
 template <int LB>
 __global__ void __launch_bounds__(256) lokr_z_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, const float* __restrict__ w1,
                                                      long long M, int ol, int im, int in_n, __nv_bfloat16* __restrict__ z) {
+    pdl_trigger();
     extern __shared__ float sw1[];  // [ol][im]
     for (int i = threadIdx.x; i < ol * im; i += blockDim.x) sw1[i] = w1[i];
     __syncthreads();
@@ -392,6 +394,7 @@ template <int LT, int IT>
 __global__ void __launch_bounds__(256) lokr_dw1_mma_kernel(const __nv_bfloat16* __restrict__ v, const __nv_bfloat16* __restrict__ x,
                                                            long long ldx, long long M, int ol, int im, int in_n, float mult,
                                                            float* __restrict__ dw1) {
+    pdl_trigger();
     __shared__ float red[LT * 16 * IT * 8];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, t = lane & 3;
@@ -565,6 +568,7 @@ __global__ void copy2d_kernel(const T* __restrict__ src, long long lds, __nv_bfl
 template <typename T>
 __global__ void copy2d_vec_kernel(const T* __restrict__ src, long long lds, __nv_bfloat16* __restrict__ dst, long long ldd,
                                   long long rows, int cols8) {
+    pdl_trigger();
     const long long total = rows * cols8;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const long long r = i / cols8;

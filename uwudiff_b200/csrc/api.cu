@@ -1,5 +1,6 @@
 // C-ABI plumbing: error string, version, TMA descriptor encoding through the driver entry point
 // (no link-time dependency on libcuda), SM count cache.
+#include <cstdlib>
 #include "api_internal.h"
 
 #include <atomic>
@@ -73,6 +74,15 @@ int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_
         return UWU_ERR_INVALID;
     }
     return 0;
+}
+
+bool pdl_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("UWU_PDL");
+        v = e ? atoi(e) : 1;
+    }
+    return v != 0;
 }
 
 int sm_count() {

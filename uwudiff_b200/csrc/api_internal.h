@@ -20,8 +20,25 @@ int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_
                      const uint32_t* box, int swizzle128);
 
 int sm_count();
+bool pdl_enabled();  // programmatic dependent launch for the TMEM kernels (UWU_PDL=0 disables)
 
 extern std::atomic<long long> g_launches;
+
+// launch with the programmatic stream-serialization attribute (see pdl_trigger / pdl_wait in common.cuh)
+template <typename Arg>
+inline cudaError_t launch_pdl(void (*kernel)(Arg), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, const Arg& arg) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, arg);
+}
 
 }  // namespace uwu
 

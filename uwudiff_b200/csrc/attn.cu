@@ -59,6 +59,7 @@ static constexpr int FWD_SMEM = FWD_BAR + 256 + 1024;
 static constexpr int FWD_THREADS = 320;
 
 __global__ void __launch_bounds__(FWD_THREADS, 1) attn_fwd_kernel(const __grid_constant__ AttnFwdArgs p) {
+    pdl_trigger();
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = align1024(smem_raw);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + FWD_BAR);
@@ -105,6 +106,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) attn_fwd_kernel(const __grid_c
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();
     // TMEM columns: S tile t at [128 t, 128 t + 128), PV tile t at [256 + 64 t, +64)
 
     if (warp == 0) {
@@ -343,6 +345,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) attn_fwd_kernel(const __grid_c
 __global__ void attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ o, long long ldo, const __nv_bfloat16* __restrict__ dout,
                                      long long lddo, const float* __restrict__ lse, int B, int heads, int Lq, int Lq_pad, int hd,
                                      float* __restrict__ lse2, float* __restrict__ delta) {
+    pdl_trigger();
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long total = (long long)B * Lq * heads;
     if (idx >= total) return;
@@ -370,6 +373,7 @@ __global__ void attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ o, long l
 // dq[b*Lq+q, 64h+d] = scale * acc[b,h,q/128, d/4, q%128, d%4]   (single-pass backward: fp32 dQ scratch -> bf16)
 __global__ void attn_bwd_dq_convert_kernel(const float* __restrict__ acc, int B, int heads, int Lq, int nqt, float scale, int hd,
                                            __nv_bfloat16* __restrict__ dq, long long lddq) {
+    pdl_trigger();
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // one 8-wide d chunk per thread
     const long long total = (long long)B * Lq * heads * 8;
     if (idx >= total) return;
@@ -436,6 +440,7 @@ static constexpr int BWD_THREADS = 64 + 512;  // TMA warp, MMA warp, 16 compute 
 // iteration i+1 before the accumulating products of iteration i, so the exp / dS math overlaps the tensor pipe.
 template <int kMode>
 __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_kernel(const __grid_constant__ AttnBwdArgs p) {
+    pdl_trigger();
     using Cfg = BwdCfg<kMode>;
     constexpr bool kDQ = kMode == 1;
     constexpr bool kFused = kMode == 2;
@@ -489,6 +494,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_kernel(const __grid_c
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();
 
     if (warp == 0) {
         if (lane == 0) {
@@ -805,7 +811,7 @@ extern "C" int uwu_attn_fwd(const void* q, const void* k, const void* v, void* o
         attr_set = true;
     }
     dim3 grid((Lq + 255) / 256, heads, B);
-    attn_fwd_kernel<<<grid, FWD_THREADS, FWD_SMEM, stream>>>(a);
+    UWU_CHECK_CUDA(launch_pdl(attn_fwd_kernel, grid, dim3(FWD_THREADS), FWD_SMEM, stream, a));
     UWU_CHECK_LAUNCH();
     return UWU_OK;
 }
@@ -879,7 +885,8 @@ extern "C" int uwu_attn_bwd(const void* q, const void* k, const void* v, const v
     if (attn_bwd_mode() == 1) {
         a.dq_acc = workspace + 2 * rows;
         UWU_CHECK_CUDA(cudaMemsetAsync(a.dq_acc, 0, (size_t)(rows * 64) * sizeof(float), stream));
-        attn_bwd_kernel<2><<<dim3((Lk + 127) / 128, heads, B), BWD_THREADS, BwdCfg<2>::SMEM, stream>>>(a);  // dK, dV, dQ partials
+        UWU_CHECK_CUDA(launch_pdl(attn_bwd_kernel<2>, dim3((Lk + 127) / 128, heads, B), dim3(BWD_THREADS), BwdCfg<2>::SMEM, stream,
+                                  a));  // dK, dV, dQ partials
         UWU_CHECK_LAUNCH();
         const long long total = (long long)B * Lq * heads * 8;
         attn_bwd_dq_convert_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(

@@ -489,6 +489,7 @@ __device__ __forceinline__ void store_rows16(const float (&acc)[8][4], float m0,
 
 template <int NK8>
 __global__ void __launch_bounds__(128) attn_short_fwd_kernel(const AnyArgs a) {
+    pdl_trigger();
     constexpr int LKP = NK8 * 8;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __nv_bfloat16* Ks = reinterpret_cast<__nv_bfloat16*>(smem_raw);

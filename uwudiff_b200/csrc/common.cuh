@@ -20,6 +20,11 @@ UWU_DEVINL uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to
 UWU_DEVINL void st_shared_v4(uint32_t saddr, const uint4& v) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
+// Programmatic dependent launch: `pdl_trigger` lets the next kernel of the stream (if it was launched with the programmatic
+// stream-serialization attribute) start its prologue while this grid drains; `pdl_wait` blocks until the previous grid has
+// completed and its memory is visible.  Both are no-ops when the launch does not use the attribute.
+UWU_DEVINL void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+UWU_DEVINL void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 UWU_DEVINL uint32_t lane_id() { return threadIdx.x & 31; }
 
 UWU_DEVINL bool elect_one() {

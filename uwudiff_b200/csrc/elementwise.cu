@@ -28,6 +28,7 @@ UWU_DEVINL void st8e(__nv_bfloat16* p, const float (&v)[8]) {
 // (row, 8-wide column vector) pairs of that range with incremental 32-bit index updates (no 64-bit division).
 __global__ void __launch_bounds__(256) geglu_fwd_kernel(const __nv_bfloat16* __restrict__ in, long long M, int F,
                                                         __nv_bfloat16* __restrict__ out) {
+    pdl_trigger();
     const int fv = F >> 3;
     const long long rows_per = (M + gridDim.x - 1) / gridDim.x;
     const long long m0 = blockIdx.x * rows_per;
@@ -54,6 +55,7 @@ __global__ void __launch_bounds__(256) geglu_fwd_kernel(const __nv_bfloat16* __r
 // din[m, f] = dout * gelu(g);  din[m, F+f] = dout * h * gelu'(g),  gelu'(g) = Phi(g) + g phi(g)
 __global__ void __launch_bounds__(256) geglu_bwd_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16* __restrict__ dout,
                                                         long long M, int F, __nv_bfloat16* __restrict__ din) {
+    pdl_trigger();
     const int fv = F >> 3;
     const long long rows_per = (M + gridDim.x - 1) / gridDim.x;
     const long long m0 = blockIdx.x * rows_per;
@@ -106,6 +108,7 @@ UWU_DEVINL float gelu_tanh_grad_f(float x) {
 // mode 4: y = gelu_tanh(x); mode 5: y = x * gelu_tanh'(a)   (DiT MLP activation)
 __global__ void ew_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ a, long long nvec,
                           int mode, __nv_bfloat16* __restrict__ y) {
+    pdl_trigger();
     constexpr int U = 4;  // independent 16-byte loads in flight per thread
     const long long stride = (long long)gridDim.x * blockDim.x;
     const bool two = mode == 1 || mode == 2 || mode == 5;

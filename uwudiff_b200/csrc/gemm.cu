@@ -148,6 +148,7 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
 }
 
 __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __grid_constant__ GemmKernelArgs p) {
+    pdl_trigger();
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // 1024-byte alignment is required by the 128B swizzle atoms
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -192,6 +193,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
     if (p.cluster2) cluster_sync_all();  // the peer's barriers are initialised before anything is multicast to them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();  // everything above (barriers, TMEM, descriptor prefetch) overlaps the tail of the previous kernel
 
     const int num_tiles = p.num_m_tiles * p.num_n_tiles;
 
@@ -952,8 +954,18 @@ extern "C" int uwu_gemm(const uwu_gemm_desc* d, void* stream_) {
         UWU_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel, p));
         g_launches.fetch_add(1, std::memory_order_relaxed);
     } else {
-        gemm_tcgen05_kernel<<<grid, NUM_THREADS, smem_bytes, stream>>>(p);
-        UWU_CHECK_LAUNCH();
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid);
+        cfg.blockDim = dim3(NUM_THREADS);
+        cfg.dynamicSmemBytes = smem_bytes;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        UWU_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel, p));
+        g_launches.fetch_add(1, std::memory_order_relaxed);
     }
     return UWU_OK;
 }

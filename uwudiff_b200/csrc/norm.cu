@@ -33,6 +33,7 @@ struct GNGeom {
 
 // partial sums: ws[((n * chunks + chunk) * G + g) * 2 + {0,1}] = {sum, sumsq}
 __global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x, GNGeom g, float* __restrict__ ws) {
+    pdl_trigger();
     extern __shared__ float sh[];  // [2][C]
     const int n = blockIdx.y, chunk = blockIdx.x;
     const int v = threadIdx.x % g.cv, rr = threadIdx.x / g.cv;
@@ -83,6 +84,7 @@ __global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x, GNGeom g, f
 
 // finalise mean / rstd per (n, g) from the chunk partials; stats[n, g, {mean, rstd}]
 __global__ void gn_finalize_kernel(const float* __restrict__ ws, GNGeom g, float eps, float* __restrict__ stats) {
+    pdl_trigger();
     // one warp per (n, g): lanes stride over the chunk partials
     const int idx = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (idx >= g.N * g.G) return;
@@ -108,6 +110,7 @@ template <bool kSilu>
 __global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ stats,
                                 const float* __restrict__ gamma, const float* __restrict__ beta, GNGeom g,
                                 __nv_bfloat16* __restrict__ y) {
+    pdl_trigger();
     const int n = blockIdx.y, chunk = blockIdx.x;
     const int v = threadIdx.x % g.cv, rr = threadIdx.x / g.cv;
     const int cpg = g.C / g.G;
@@ -142,6 +145,7 @@ template <bool kSilu>
 __global__ void gn_bwd_stats_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
                                     const float* __restrict__ stats, const float* __restrict__ gamma,
                                     const float* __restrict__ beta, GNGeom g, float* __restrict__ wsb) {
+    pdl_trigger();
     extern __shared__ float sh[];  // [2][C]
     const int n = blockIdx.y, chunk = blockIdx.x;
     const int v = threadIdx.x % g.cv, rr = threadIdx.x / g.cv;
@@ -197,6 +201,7 @@ __global__ void gn_bwd_stats_kernel(const __nv_bfloat16* __restrict__ x, const _
 //   red[n, {0,1}, g] = {A/cnt, B/cnt}
 __global__ void gn_bwd_reduce_kernel(const float* __restrict__ wsb, const float* __restrict__ gamma, GNGeom g,
                                      float* __restrict__ red, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+    pdl_trigger();
     // one block per n; threads over channels
     extern __shared__ float sh[];  // [2][C] per-channel sums for this n
     const int n = blockIdx.x;
@@ -233,6 +238,7 @@ __global__ void gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x, const _
                                     const float* __restrict__ stats, const float* __restrict__ gamma,
                                     const float* __restrict__ beta, const float* __restrict__ red,
                                     const __nv_bfloat16* __restrict__ dres, GNGeom g, __nv_bfloat16* __restrict__ dx) {
+    pdl_trigger();
     const int n = blockIdx.y, chunk = blockIdx.x;
     const int v = threadIdx.x % g.cv, rr = threadIdx.x / g.cv;
     const int cpg = g.C / g.G;
@@ -312,6 +318,7 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const __nv_bfloat16* __rest
                                                      const float* __restrict__ mscale, const float* __restrict__ mshift,
                                                      int rows_per_mod, __nv_bfloat16* __restrict__ y,
                                                      float* __restrict__ stats) {
+    pdl_trigger();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int cv = C / 8;
     const float inv_c = 1.0f / (float)C;
@@ -498,6 +505,7 @@ __global__ void __launch_bounds__(192, 4) ln_bwd_cols_kernel(const __nv_bfloat16
                                                           int M, int C, const float* __restrict__ gamma,
                                                           const float* __restrict__ stats, const __nv_bfloat16* __restrict__ dres,
                                                           __nv_bfloat16* __restrict__ dx, float* __restrict__ pg) {
+    pdl_trigger();
     __shared__ float part[2][R][8][2];  // [parity][row][warp][s1, s2]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
     const int cv = C >> 3;
@@ -594,6 +602,7 @@ __global__ void __launch_bounds__(192, 4) ln_bwd_cols_kernel(const __nv_bfloat16
 // out[c] (+)= sum_p partial[p, c]
 __global__ void colsum_partials_kernel(const float* __restrict__ partial, int P, int stride, int n, int accumulate,
                                        float* __restrict__ out) {
+    pdl_trigger();
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n) return;
     float a = 0.f;
@@ -605,6 +614,7 @@ __global__ void colsum_partials_kernel(const float* __restrict__ partial, int P,
 // grid (ceil(2C/128), slices): each block sums its slice of p and adds atomically (outputs pre-zeroed unless accumulating).
 __global__ void __launch_bounds__(128) ln_param_reduce_kernel(const float* __restrict__ partial, int P, int C, int p_per,
                                                               float* __restrict__ dgamma, float* __restrict__ dbeta) {
+    pdl_trigger();
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= 2 * C) return;
     const int p0 = blockIdx.y * p_per, p1 = min(P, p0 + p_per);
