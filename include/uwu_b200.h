@@ -295,6 +295,22 @@ int uwu_conv_wgrad_unpack(const float* G, int64_t ldg, int32_t Co, int32_t Ci, i
                           float* wgrad, void* stream);
 int uwu_colsum_groups_bf16(const void* x, int64_t ldx, int32_t groups, int32_t rows, int32_t C, int32_t accumulate, float* out,
                            void* stream);
+/* The same contraction for many adapters in ONE launch (each adapter keeps its own G buffer until the flush).
+ * Table entry: vec = 1 when in_n % 4 == 0, ldg % 4 == 0 and G / w2 are 16-byte aligned; target = block budget of the entry;
+ * block0 = first block of the entry (prefix sum of uwu_lokr_grad_plan_blocks over the table). */
+typedef struct uwu_lokr_grad_entry {
+    const float* G;
+    const float* w1;
+    const float* w2;
+    float* dw1;
+    float* dw2;
+    int64_t ldg;
+    int32_t out_l, out_k, in_m, in_n;
+    float multiplier;
+    int32_t vec, target, block0;
+} uwu_lokr_grad_entry;
+int32_t uwu_lokr_grad_plan_blocks(int32_t out_l, int32_t out_k, int32_t in_m, int32_t in_n, int32_t vec, int32_t target);
+int uwu_lokr_grad_batch(const uwu_lokr_grad_entry* entries_dev, int32_t n_entries, int32_t total_blocks, void* stream);
 /* LoHa (lycoris `loha`): dW = ((w1a @ w1b) o (w2a @ w2b)) * scale, factors [N, r] / [r, K], r <= 16 */
 int uwu_fold_loha(const float* W, const float* w1a, const float* w1b, const float* w2a, const float* w2b, int32_t N, int32_t K,
                   int32_t r, float scale, void* dst_bf16, void* stream);

@@ -62,6 +62,12 @@ class FoldEntry(C.Structure):
                 ("scale", C.c_float), ("chunk0", C.c_int32)]
 
 
+class LokrGradEntry(C.Structure):
+    _fields_ = [("G", C.c_void_p), ("w1", C.c_void_p), ("w2", C.c_void_p), ("dw1", C.c_void_p), ("dw2", C.c_void_p),
+                ("ldg", C.c_int64), ("out_l", C.c_int32), ("out_k", C.c_int32), ("in_m", C.c_int32), ("in_n", C.c_int32),
+                ("multiplier", C.c_float), ("vec", C.c_int32), ("target", C.c_int32), ("block0", C.c_int32)]
+
+
 _lib = None
 
 # name -> (restype, argtypes); kept in one table so tests can check every header symbol is exported
@@ -104,6 +110,8 @@ SIGNATURES = {
     "uwu_phase_split2": (C.c_int, [_P, _I32, _I32, _I32, _I32, _I32, _P, _P]),
     "uwu_colsum_workspace_floats": (C.c_int64, [_I64, _I32]),
     "uwu_colsum_bf16": (C.c_int, [_P, _I64, _I32, _I64, _I32, _P, _P, _P]),
+    "uwu_lokr_grad_plan_blocks": (C.c_int32, [_I32, _I32, _I32, _I32, _I32, _I32]),
+    "uwu_lokr_grad_batch": (C.c_int, [_P, _I32, _I32, _P]),
     "uwu_fold_loha": (C.c_int, [_P, _P, _P, _P, _P, _I32, _I32, _I32, _F, _P, _P]),
     "uwu_loha_grad": (C.c_int, [_P, _I64, _P, _P, _P, _P, _I32, _I32, _I32, _F, _P, _P, _P, _P, _P]),
     "uwu_fold_lokr": (C.c_int, [_P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _F, _P, _P]),

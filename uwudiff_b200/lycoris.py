@@ -14,6 +14,7 @@ passes over contiguous memory.
 from __future__ import annotations
 
 import math
+import os
 from typing import Dict, List
 
 import torch
@@ -135,9 +136,26 @@ class LokrLinear(_Adapter):
     def fold_into(self, W, dst):
         ops.fold_lokr(W, self.lokr_w1, self.lokr_w2, dst, self.scale * self.multiplier)
 
-    def grads_from(self, G):
+    def g_buffer(self, N: int, K: int):
+        """Persistent fp32 [N, K] buffer for this adapter's G = dY^T X: the contraction into (dw1, dw2) is deferred and runs
+        batched with the other adapters of the same top-level block (LycorisNetwork.flush_grads).  None = not deferring."""
+        net = getattr(self, "_net", None)
+        if net is None or not net.defer_grads or not self.lokr_w1.is_cuda:
+            return None
+        g = getattr(self, "_g", None)
+        if g is None or g.shape != (N, K) or g.device != self.lokr_w1.device:
+            g = torch.empty((N, K), device=self.lokr_w1.device, dtype=torch.float32)
+            object.__setattr__(self, "_g", g)
+        return g
+
+    def grads_from(self, G, persistent: bool = False):
         from .unet import _grad_of
 
+        net = getattr(self, "_net", None)
+        if persistent and net is not None and net.defer_grads:
+            _grad_of(self.lokr_w1), _grad_of(self.lokr_w2)
+            net._pending.append((self, G))
+            return
         ops.lokr_grad(G, self.lokr_w1, self.lokr_w2, _grad_of(self.lokr_w1), _grad_of(self.lokr_w2),
                       self.scale * self.multiplier)
 
@@ -216,6 +234,10 @@ class LycorisNetwork(nn.Module):
         object.__setattr__(self, "_root", module)
         self.loras: List[_Adapter] = []
         self._orgs: List[nn.Module] = []
+        # deferred LoKr contractions: (adapter, G) pairs waiting for flush_grads(); UWU_LOKR_DEFER=0 restores per-layer launches
+        self.defer_grads = os.environ.get("UWU_LOKR_DEFER", "1") != "0"
+        object.__setattr__(self, "_pending", [])
+        object.__setattr__(self, "_grad_tables", {})
         names = set()
         if self.ENABLE_CONV:
             raise NotImplementedError("uwudiff_b200.lycoris: conv adapters (enable_conv = true) are not built; the "
@@ -346,6 +368,48 @@ class LycorisNetwork(nn.Module):
         for org in self._orgs:
             org._fold_epoch = FOLD.epoch
 
+    def flush_grads(self):
+        """Contract every pending G of the LoKr adapters into (dw1, dw2) in ONE launch (uwu_lokr_grad_batch).  Called by the
+        denoiser's backward whenever a top-level block is finished (before its gradients are handed to the DDP buckets)."""
+        import ctypes as C
+
+        from . import _lib
+
+        pend = self._pending
+        if not pend:
+            return
+        key = tuple((id(ad), G.data_ptr(), ad.lokr_w1.grad.data_ptr(), ad.lokr_w2.grad.data_ptr(), ad.lokr_w1.data_ptr())
+                    for ad, G in pend)
+        t = self._grad_tables.get(key)
+        if t is None:
+            n = len(pend)
+            sms = torch.cuda.get_device_properties(pend[0][1].device).multi_processor_count
+            target = max(8, (8 * sms) // n)
+            ents, block0 = [], 0
+            for ad, G in pend:
+                (ol, ok), (im, inn) = ad.shape
+                e = _lib.LokrGradEntry()
+                e.G, e.w1, e.w2 = G.data_ptr(), ad.lokr_w1.data_ptr(), ad.lokr_w2.data_ptr()
+                e.dw1, e.dw2 = ad.lokr_w1.grad.data_ptr(), ad.lokr_w2.grad.data_ptr()
+                e.ldg = G.stride(0)
+                e.out_l, e.out_k, e.in_m, e.in_n = ol, ok, im, inn
+                e.multiplier = ad.scale * ad.multiplier
+                e.vec = int(inn % 4 == 0 and G.stride(0) % 4 == 0 and G.data_ptr() % 16 == 0 and ad.lokr_w2.data_ptr() % 16 == 0)
+                e.target, e.block0 = target, block0
+                nb = int(_lib.lib().uwu_lokr_grad_plan_blocks(ol, ok, im, inn, e.vec, target))
+                assert nb > 0
+                block0 += nb
+                ents.append(e)
+            arr = (_lib.LokrGradEntry * n)(*ents)
+            table = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(pend[0][1].device)
+            t = (table, n, block0)
+            if len(self._grad_tables) > 64:
+                self._grad_tables.clear()
+            self._grad_tables[key] = t
+        _lib.check(_lib.lib().uwu_lokr_grad_batch(t[0].data_ptr(), t[1], t[2], torch.cuda.current_stream().cuda_stream),
+                   "uwu_lokr_grad_batch")
+        pend.clear()
+
     def refresh_bf16(self):
         """bf16 copy of all adapter parameters (operands of the factored-gradient GEMMs): one kernel per backward."""
         if self.flat_params_bf16 is not None:
@@ -365,6 +429,7 @@ class LycorisNetwork(nn.Module):
         object.__setattr__(self._root, "_uwu_lycoris", self)
         for lora, org in zip(self.loras, self._orgs):
             object.__setattr__(org, "_uwu_adapter", lora)
+            object.__setattr__(lora, "_net", self)
             if hasattr(org, "drop_cache"):
                 org.drop_cache()
 

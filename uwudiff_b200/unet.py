@@ -144,6 +144,11 @@ class Linear(nn.Linear, _Cached):
             if hasattr(ad, "factored_ok") and ad.factored_ok(M):
                 ad.grads_factored(dy, x, M)
                 return
+            G = ad.g_buffer(N, K) if hasattr(ad, "g_buffer") else None
+            if G is not None:  # LoKr: keep G, contract it later in one batched launch (LycorisNetwork.flush_grads)
+                ops.gemm(dy, x, N, K, M, a_layout=A_COL, lda=dy.stride(0), b_layout=B_KN, ldb=x.stride(0), out=G)
+                ad.grads_from(G, persistent=True)
+                return
             G = ops._workspace(N * K, dy.device, "wgrad")[: N * K].view(N, K)
             ops.gemm(dy, x, N, K, M, a_layout=A_COL, lda=dy.stride(0), b_layout=B_KN, ldb=x.stride(0), out=G)
             ad.grads_from(G)
@@ -170,11 +175,18 @@ def _fused_param_grads(mods, dy, x, M):
             off += m.out_features
         return
     N, K = sum(m.out_features for m in mods), mods[0].in_features
-    G = ops._workspace(N * K, dy.device, "wgrad")[: N * K].view(N, K)
+    ad0 = mods[0]._uwu_adapter
+    G = ad0.g_buffer(N, K) if all(hasattr(m._uwu_adapter, "g_buffer") for m in mods) else None  # fused buffer owned by the first
+    persistent = G is not None
+    if G is None:
+        G = ops._workspace(N * K, dy.device, "wgrad")[: N * K].view(N, K)
     ops.gemm(dy, x, N, K, M, a_layout=A_COL, lda=dy.stride(0), b_layout=B_KN, ldb=x.stride(0), out=G)
     off = 0
     for m in mods:
-        m._uwu_adapter.grads_from(G[off:off + m.out_features])
+        if persistent:
+            m._uwu_adapter.grads_from(G[off:off + m.out_features], persistent=True)
+        else:
+            m._uwu_adapter.grads_from(G[off:off + m.out_features])
         off += m.out_features
 
 
@@ -917,7 +929,13 @@ class UNet2DConditionModel(nn.Module):
         ly = getattr(self, "_uwu_lycoris", None)
         if ly is not None:
             ly.refresh_bf16()
-        done = self.after_backward or (lambda mods: None)
+        after = self.after_backward or (lambda mods: None)
+
+        def done(mods):  # pending LoKr contractions of the finished blocks run (batched) before their gradients are used
+            if ly is not None:
+                ly.flush_grads()
+            after(mods)
+
         st.H, st.W = H, W
         dy = ops.nchw_to_nhwc(gout, self.conv_out._cache.cod_p)
         if y_last is not None:
