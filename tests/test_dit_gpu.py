@@ -170,6 +170,33 @@ def test_dit_all_parameter_gradients_match_oracle():
     assert dot / (num ** 0.5 * den ** 0.5) > 0.995
 
 
+def test_dit_xl_width_gradients_match_oracle():
+    """Two DiT-XL/2-sized blocks (hidden 1152, 16 heads of 72, 256 tokens, patch 2 on 32x32 latents): the production tile shapes."""
+    cfg, o, p, x, t, y = build(seed=8, B=4, input_size=32, hidden_size=1152, num_heads=16, depth=2, num_classes=1000,
+                               frequency_embedding_size=256)
+    gout = torch.randn(x.shape, generator=torch.Generator().manual_seed(4))
+    yo = o(x, t, class_labels=y)[0]
+    yo.backward(gout)
+    yp = p(x.cuda(), t.cuda(), class_labels=y.cuda())[0]
+    yp.backward(gout.cuda())
+    torch.cuda.synchronize()
+    assert rel(yp, yo) < 3e-2
+    po = dict(o.named_parameters())
+    num = den = dot = 0.0
+    worst, worst_name = 0.0, ""
+    for n, q in p.named_parameters():
+        go, gp = po[n].grad.float(), q.grad.float().cpu()
+        r = rel(gp, go)
+        if r > worst:
+            worst, worst_name = r, n
+        num += (gp * gp).sum().item()
+        den += (go * go).sum().item()
+        dot += (gp * go).sum().item()
+    assert worst < 1.5e-1, (worst, worst_name)
+    assert abs(num ** 0.5 - den ** 0.5) / den ** 0.5 < 2e-2
+    assert dot / (num ** 0.5 * den ** 0.5) > 0.995
+
+
 def test_dit_training_step_through_diffusion_loss():
     """eps-prediction MSE through the fused noising / loss kernels with injected noise and timesteps vs the oracle loss."""
     from oracle import diffusers_shim, loss_oracle

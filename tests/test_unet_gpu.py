@@ -23,11 +23,11 @@ def rel(a, b):
     return ((a - b).abs().max() / (b.abs().max() + 1e-12)).item()
 
 
-def build(seed=0, B=2, HW=16, zero_init=False):
+def build(seed=0, B=2, HW=16, zero_init=False, **over):
     from uwudiff_b200 import unet as P
 
     torch.manual_seed(seed)
-    cfg = U.tiny_config()
+    cfg = U.tiny_config(**over)
     o = U.UNet2DConditionModel(**cfg)
     if zero_init:
         o.init_weight()
@@ -120,6 +120,34 @@ def test_lycoris_forward_and_adapter_gradients_match_oracle():
     yp2.backward(gout.cuda())
     tot_p2 = torch.sqrt(sum((q.grad.float() ** 2).sum() for q in npd.parameters())).item()
     assert abs(tot_p2 - 2 * tot_o) / (2 * tot_o) < 1e-2
+
+
+def test_lycoris_at_sdxl_like_widths_matches_oracle():
+    """Same check at widths / token counts that take the production code paths: 320- and 640-wide transformer levels with
+    5 / 10 heads of 64, 4096 and 1024 tokens (256-wide GEMM tiles, split-K weight gradients, the factored LoKr route for the
+    FeedForward adapters, which needs >= 4096 tokens, the short-key cross-attention kernel, deferred batched contractions)."""
+    cfg, o, p, x, t, ctx, ac = build(seed=9, B=4, HW=32, sample_size=32, block_out_channels=(320, 640),
+                                     down_block_types=("CrossAttnDownBlock2D", "CrossAttnDownBlock2D"),
+                                     up_block_types=("CrossAttnUpBlock2D", "CrossAttnUpBlock2D"), attention_head_dim=(5, 10),
+                                     transformer_layers_per_block=(1, 1), cross_attention_dim=256)
+    no, npd = with_lycoris(o, p)
+    from uwudiff_b200 import lycoris as PL
+
+    M0 = 4 * 32 * 32
+    assert any(isinstance(a, PL.LokrLinear) and a.factored_ok(M0) for a in npd.loras), "no adapter takes the factored route"
+    gout = torch.randn(x.shape, generator=torch.Generator().manual_seed(2))
+    yo = o(x, t, encoder_hidden_states=ctx, added_cond_kwargs=ac)[0]
+    yo.backward(gout)
+    yp = p(x.cuda(), t.cuda(), **cuda_kwargs(ctx, ac))[0]
+    yp.backward(gout.cuda())
+    torch.cuda.synchronize()
+    assert rel(yp, yo) < 3e-2
+    po = dict(no.named_parameters())
+    worst = max(rel(prm.grad, po[n].grad) for n, prm in npd.named_parameters())
+    assert worst < 1.5e-1, worst
+    tot_o = torch.sqrt(sum((q.grad.float() ** 2).sum() for q in no.parameters())).item()
+    tot_p = torch.sqrt(sum((q.grad.float() ** 2).sum() for q in npd.parameters())).item()
+    assert abs(tot_p - tot_o) / tot_o < 1e-2
 
 
 def test_loha_adapters_forward_and_gradients_match_oracle():
