@@ -25,9 +25,10 @@ def _strided(t, rows, cols, ld):
 
 def gemm(a, b, M, N, K, *, a_layout=0, b_layout=0, lda=None, ldb=None, out=None, out_dtype=BF16, bias=None,
          bias_rows=None, rows_per_bias=1, residual=None, alpha=1.0, accumulate=False, block_n=0, out2=None, n_split=0,
-         conv=None, a2=None, dbg=None):
+         conv=None, a2=None, dbg=None, stream_k=-1, k_segs=0, a_seg_off=0, b_seg_off=0, grp_n=0, a_grp_koff=0):
     _launches[0] += 1
     assert a.dtype == BF16 and b.dtype == BF16
+    assert k_segs <= 1 and grp_n == 0, "segmented-K / grouped-N GEMMs (factored LoKr route) are CUDA-only paths"
     if a_layout == _lib.A_ROW:
         A = _strided(a, M, K, lda if lda is not None else K).float()
     elif a_layout == _lib.A_COL:
@@ -257,6 +258,32 @@ def colsum(x, out=None, accumulate=False):
     return out
 
 
+def im2col3x3(x, N, H, W, C, stride=1):
+    """[N*H*W, C] bf16 NHWC -> [N*Ho*Wo, 9*C] bf16, column = tap * C + c, tap = ky * 3 + kx, zero padding 1."""
+    _launches[0] += 1
+    img = x.reshape(N, H, W, C).permute(0, 3, 1, 2).float()
+    cols = F.unfold(img, kernel_size=3, padding=1, stride=stride)            # [N, C*9, Ho*Wo], row = c * 9 + tap
+    L = cols.shape[-1]
+    cols = cols.view(N, C, 9, L).permute(0, 3, 2, 1).reshape(N * L, 9 * C)   # -> column = tap * C + c
+    return cols.to(BF16)
+
+
+def conv_wgrad_unpack(G, Co, Ci, Ci_pad, taps, wgrad, accumulate=True):
+    """wgrad[co, ci, tap] (+)= G[co, tap * Ci_pad + ci]"""
+    _launches[0] += 1
+    g = G[:Co].reshape(Co, taps, Ci_pad)[:, :, :Ci].permute(0, 2, 1).reshape(wgrad.shape)
+    wgrad.copy_(wgrad + g if accumulate else g)
+
+
+def colsum_groups(x, groups, rows, out=None, accumulate=False):
+    _launches[0] += 1
+    v = x[: groups * rows].float().reshape(groups, rows, -1).sum(1)
+    if out is None:
+        return v
+    out.copy_(out + v if accumulate else v)
+    return out
+
+
 def fold_lokr(W, w1, w2, dst, multiplier=1.0):
     _launches[0] += 1
     assert dst.is_contiguous() and dst.shape == W.shape
@@ -362,7 +389,7 @@ def launch_count():
 PATCHED = ["gemm", "conv3x3_nhwc", "attn_fwd", "attn_bwd", "groupnorm_fwd", "groupnorm_bwd", "layernorm_fwd", "layernorm_bwd",
            "geglu_fwd", "geglu_bwd", "elementwise", "nchw_to_nhwc", "nhwc_to_nchw", "upsample2x", "phase_split2", "colsum",
            "fold_lokr", "fold_lora", "axpy_f32", "lokr_grad", "lora_grad", "copy2d", "sincos_embed", "_workspace", "noise_fwd",
-           "wmse_fwd", "wmse_bwd", "launch_count", "_req_cuda"]
+           "wmse_fwd", "wmse_bwd", "launch_count", "_req_cuda", "im2col3x3", "conv_wgrad_unpack", "colsum_groups"]
 
 
 def install(monkeypatch):

@@ -242,6 +242,28 @@ def test_unet_lycoris_backward_matches_oracle(fake_ops):
     assert all(getattr(m, "_sv", None) is None for m in p.modules())  # activations released after backward
 
 
+def test_unet_full_finetune_backward_matches_oracle(fake_ops):
+    """Full fine-tuning host logic (lycoris_config = None): every parameter gets its gradient (conv weights through
+    im2col + token-reduction GEMM + unpack, biases, norms, time / add embeddings)."""
+    cfg, o, p, x, t, ctx, ac = _tiny_pair()
+    o.requires_grad_(True)
+    p.requires_grad_(True)
+    gout = torch.randn(x.shape)
+    yo = o(x, t, encoder_hidden_states=ctx, added_cond_kwargs=ac)[0]
+    yo.backward(gout)
+    yp = p(x, t, encoder_hidden_states=ctx, added_cond_kwargs=ac)[0]
+    yp.backward(gout)
+    po = dict(o.named_parameters())
+    assert not [n for n, q in p.named_parameters() if q.grad is None]
+    a = torch.cat([q.grad.flatten().float() for n, q in p.named_parameters()])
+    b = torch.cat([po[n].grad.flatten().float() for n, q in p.named_parameters()])
+    assert torch.nn.functional.cosine_similarity(a, b, dim=0).item() > 0.995
+    assert abs(a.norm() - b.norm()) / b.norm() < 2e-2
+    for n in ("conv_in.weight", "down_blocks.0.resnets.0.conv1.weight", "conv_out.bias", "time_embedding.linear_1.weight"):
+        q = dict(p.named_parameters())[n]
+        assert rel(q.grad, po[n].grad) < 1.5e-1, n
+
+
 def test_trainer_fit_step_loss_matches_oracle(fake_ops, monkeypatch):
     from uwudiff_b200.trainer import DMTrainer
 

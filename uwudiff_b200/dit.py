@@ -275,6 +275,10 @@ class DiT(nn.Module):
         nn.init.zeros_(self.final_layer.linear.bias)
         self.refresh_weights()
 
+    def ddp_blocks(self):
+        """Units reported through `after_backward` (uwudiff_b200/parallel.py), in parameter layout order."""
+        return [self.x_embedder, self.t_embedder, self.y_embedder] + list(self.blocks) + [self.final_layer]
+
     def enable_gradient_checkpointing(self):
         self.gradient_checkpointing = True  # recorded; 180 GB of HBM3e hold the saved activations of the named configs
 

@@ -38,9 +38,7 @@ class GradientBuckets:
         offs = {id(p): (p.grad.data_ptr() - base) // 4 for p in params}
         # first flat offset owned by each top-level block, in forward (= layout) order
         self._block_start = {}
-        tops = ([self.unet.conv_in, self.unet.time_embedding] + ([self.unet.add_embedding] if self.unet.add_embedding is not None else [])
-                + list(self.unet.down_blocks) + [self.unet.mid_block] + list(self.unet.up_blocks)
-                + [self.unet.conv_norm_out, self.unet.conv_out])
+        tops = self.unet.ddp_blocks()  # the units the hand-scheduled backward reports through `after_backward`
         for top in tops:
             mine = []
             for m in top.modules():

@@ -791,6 +791,11 @@ class UNet2DConditionModel(nn.Module):
             config = cls.load_config(config, **kwargs)
         return cls(**dict(config))
 
+    def ddp_blocks(self):
+        """Top-level blocks in forward (= parameter layout) order; backward reports them finished in reverse."""
+        return ([self.conv_in, self.time_embedding] + ([self.add_embedding] if self.add_embedding is not None else [])
+                + list(self.down_blocks) + [self.mid_block] + list(self.up_blocks) + [self.conv_norm_out, self.conv_out])
+
     def enable_gradient_checkpointing(self):
         # The reference recomputes each block in backward to fit 28 GB-class GPUs (test_scripts/test_train.py:38-39).
         # With 180 GB of HBM3e the saved activations of the named configs fit, so the flag is recorded and the
