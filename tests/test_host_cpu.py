@@ -343,3 +343,42 @@ def test_dit_parameter_names_config_and_flops():
         PD.DiT.from_config("nobody/unknown-dit")
     p.init_weight()
     assert float(p.final_layer.linear.weight.abs().max()) == 0.0 and float(p.blocks[0].adaLN_modulation[1].weight.abs().max()) == 0.0
+
+
+def test_lycoris_weight_file_roundtrip_and_merge(fake_ops, tmp_path):
+    """§8(f) rank 3: `lycoris_weight/epoch=N.pt` = lycoris state_dict ∪ trainable unet params (trainer.py:189-215); a fresh
+    trainer that loads it reproduces the adapted output, and merge_lycoris() (trainer.py:184-187) folds the deltas into the
+    base weights so that the bare UNet gives the same output."""
+    from uwudiff_b200.trainer import DMTrainer
+
+    def make():
+        torch.manual_seed(0)
+        return DMTrainer(
+            model_config={"unet": {"_target_": "duwu.modules.unet_patch.UNet2DFromScratch.from_config", "config": dict(U.tiny_config())},
+                          "te": {"_target_": "duwu.modules.text_encoders.ConcatTextEncoders", "hidden_dim": 128, "pooled_dim": 64},
+                          "vae": None},
+            lycoris_config={"preset": LYCORIS_PRESET, "config": LYCORIS_CFG}, use_warm_up=False, device="cpu")
+
+    tr = make()
+    g = torch.Generator().manual_seed(5)
+    tr.lycoris_model.flat_params.copy_(torch.randn(tr.lycoris_model.flat_params.shape, generator=g) * 0.05)
+    path = tr.save_lycoris_weight(str(tmp_path / "lycoris_weight"), epoch=3)
+    assert path.endswith("epoch=3.pt")
+    sd = torch.load(path)
+    assert set(sd) == set(tr.lycoris_model.state_dict())  # frozen base: no unet parameters in the file
+    assert any(k.endswith("lokr_w1") for k in sd) and all(k.startswith("lycoris_") for k in sd)
+    x, t = torch.randn(2, 4, 16, 16), torch.tensor([3, 700])
+    ctx, ac = torch.randn(2, 77, 128), dict(text_embeds=torch.randn(2, 64), time_ids=torch.tensor([[1024., 1024, 0, 0, 1024, 1024]] * 2))
+    with torch.no_grad():
+        y = tr.unet(x, t, encoder_hidden_states=ctx, added_cond_kwargs=ac)[0]
+    tr2 = make()
+    tr2.lycoris_model.load_state_dict(sd)
+    with torch.no_grad():
+        y2 = tr2.unet(x, t, encoder_hidden_states=ctx, added_cond_kwargs=ac)[0]
+    assert torch.equal(y, y2)
+    with torch.no_grad():
+        tr2.merge_lycoris()
+    assert all(getattr(m, "_uwu_adapter", None) is None for m in tr2.unet.modules())
+    with torch.no_grad():
+        y3 = tr2.unet(x, t, encoder_hidden_states=ctx, added_cond_kwargs=ac)[0]
+    assert rel(y3, y) < 2e-3   # same deltas, folded in fp32 into the master weights instead of into the bf16 operand
