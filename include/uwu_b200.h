@@ -290,6 +290,11 @@ int uwu_fold_batch(const uwu_fold_entry* entries_dev, const int32_t* chunk_entry
  *   uwu_conv_wgrad_unpack: wgrad[co, ci, t] (+)= G[co, t*Ci_pad + ci]   (torch Conv2d layout <- packed GEMM layout)
  *   uwu_colsum_groups_bf16: out[g, c] (+)= sum_r x[g*rows + r, c]        (per-image sums: gradient of the time-embedding bias rows)
  * Replaces autograd's conv2d weight gradient / sum reductions under loss.backward() in the reference's full fine-tuning mode. */
+/* Conv2d master weight [Co, Ci, kh, kw] fp32 -> bf16 implicit-GEMM operands (zero-padded): fwd [co_pad, taps*ci_pad] with
+ * fwd[co, t*ci_pad + ci] = W[co, ci, t], and (optional) dgrad [Ci, taps*cod_pad] with dgrad[ci, t*cod_pad + co] =
+ * W[co, ci, taps-1-t] (spatially flipped kernel, channels swapped).  One launch per convolution per step in full fine-tuning. */
+int uwu_conv_pack(const float* W, int32_t Co, int32_t Ci, int32_t taps, int32_t ci_pad, int32_t co_pad, int32_t cod_pad,
+                  void* fwd_bf16, void* dgrad_bf16, void* stream);
 int uwu_im2col3x3(const void* x, int32_t N, int32_t H, int32_t W, int32_t C, int32_t stride, void* cols, void* stream);
 int uwu_conv_wgrad_unpack(const float* G, int64_t ldg, int32_t Co, int32_t Ci, int32_t Ci_pad, int32_t taps, int32_t accumulate,
                           float* wgrad, void* stream);

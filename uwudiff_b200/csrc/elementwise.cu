@@ -231,15 +231,59 @@ __global__ void phase_split_kernel(const __nv_bfloat16* __restrict__ src, int N,
 }
 
 // column sums of a bf16 matrix (bias gradients): partial[blockIdx.y][c] over a row chunk
-__global__ void colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, long long M, int C, long long ld, int rows_per_block,
-                                   float* __restrict__ partial) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
+// partial[blockIdx.y][c] = sum of rows [blockIdx.y * rows_per_block, ...) of column c.  Thread = one 8-wide column vector
+// (16-byte loads, four rows in flight), 4 row lanes per block combined through shared memory.
+// kVec = false: generic fallback (C % 8 != 0 or unaligned rows), one column per thread.
+template <bool kVec>
+__global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, long long M, int C, long long ld,
+                                                          int rows_per_block, float* __restrict__ partial) {
     const long long r0 = (long long)blockIdx.y * rows_per_block;
     const long long r1 = min(M, r0 + rows_per_block);
-    float a = 0.f;
-    for (long long r = r0; r < r1; ++r) a += __bfloat162float(x[r * ld + c]);
-    partial[(size_t)blockIdx.y * C + c] = a;
+    if (!kVec) {
+        const int c = blockIdx.x * blockDim.x + threadIdx.x;
+        if (c >= C) return;
+        float a = 0.f;
+        for (long long r = r0; r < r1; ++r) a += __bfloat162float(x[r * ld + c]);
+        partial[(size_t)blockIdx.y * C + c] = a;
+        return;
+    }
+    __shared__ float sh[4][64][8];
+    const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+    const int v = blockIdx.x * 64 + tx;
+    const bool active = v * 8 < C;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    if (active) {
+        const __nv_bfloat16* col = x + v * 8;
+        long long r = r0 + ty;
+        for (; r + 12 < r1; r += 16) {
+            uint4 u[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) u[k] = *reinterpret_cast<const uint4*>(col + (r + 4 * k) * ld);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                float f[8];
+                up8e(u[k], f);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[j] += f[j];
+            }
+        }
+        for (; r < r1; r += 4) {
+            float f[8];
+            up8e(*reinterpret_cast<const uint4*>(col + r * ld), f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] += f[j];
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sh[ty][tx][j] = acc[j];
+    __syncthreads();
+    if (ty == 0 && active) {
+        float* o = partial + (size_t)blockIdx.y * C + v * 8;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = (sh[0][tx][j] + sh[1][tx][j]) + (sh[2][tx][j] + sh[3][tx][j]);
+    }
 }
 __global__ void colsum_final_kernel(const float* __restrict__ partial, int P, int C, int accumulate, float* __restrict__ out) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -271,6 +315,29 @@ __global__ void __launch_bounds__(256) im2col3x3_kernel(const __nv_bfloat16* __r
         if (hi >= 0 && hi < H && wi >= 0 && wi < W)
             u = *reinterpret_cast<const uint4*>(x + (((size_t)n * H + hi) * W + wi) * C + v * 8);
         *reinterpret_cast<uint4*>(cols + (((size_t)n * Ho + ho) * Wo + wo) * (size_t)(9 * C) + (size_t)t * C + v * 8) = u;
+    }
+}
+// Conv2d master weight W[Co, Ci, kk] (fp32, kk = kh*kw taps) -> the two bf16 GEMM operands of the implicit-GEMM convolution,
+// zero padding included (every element of both outputs is written):
+//   fwd  [co_p, kk * ci_p] : fwd[co, t * ci_p + ci]  = W[co, ci, t]
+//   dgrad[Ci,  kk * cod_p] : dgrad[ci, t * cod_p + co] = W[co, ci, kk - 1 - t]   (correlation with the flipped kernel)
+__global__ void conv_pack_kernel(const float* __restrict__ W, int Co, int Ci, int kk, int ci_p, int co_p, int cod_p,
+                                 __nv_bfloat16* __restrict__ fwd, __nv_bfloat16* __restrict__ dgrad) {
+    const long long n_fwd = (long long)co_p * kk * ci_p;
+    const long long n_dg = dgrad ? (long long)Ci * kk * cod_p : 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_fwd + n_dg; i += (long long)gridDim.x * blockDim.x) {
+        if (i < n_fwd) {
+            const int ci = (int)(i % ci_p);
+            long long r = i / ci_p;
+            const int t = (int)(r % kk), co = (int)(r / kk);
+            fwd[i] = __float2bfloat16((co < Co && ci < Ci) ? W[((size_t)co * Ci + ci) * kk + t] : 0.f);
+        } else {
+            const long long j = i - n_fwd;
+            const int co = (int)(j % cod_p);
+            long long r = j / cod_p;
+            const int t = (int)(r % kk), ci = (int)(r / kk);
+            dgrad[j] = __float2bfloat16(co < Co ? W[((size_t)co * Ci + ci) * kk + (kk - 1 - t)] : 0.f);
+        }
     }
 }
 // wgrad[co, ci, ky, kx] (+)= G[co, (3*ky + kx) * Cp + ci]   (torch Conv2d weight layout <- packed GEMM layout), kk = kh*kw
@@ -414,8 +481,11 @@ extern "C" int uwu_colsum_bf16(const void* x, int64_t M, int32_t C, int64_t ld, 
     UWU_CHECK_ARG(M > 0 && C > 0 && ld >= C, "uwu_colsum_bf16: bad shape");
     UWU_CHECK_ARG(x && out && workspace, "uwu_colsum_bf16: null pointer");
     const int P = (int)((M + 511) / 512);
-    dim3 grid((C + 127) / 128, P);
-    colsum_bf16_kernel<<<grid, 128, 0, stream>>>(reinterpret_cast<const bf16*>(x), M, C, ld, 512, workspace);
+    const bool vec = C % 8 == 0 && ld % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
+    if (vec)
+        colsum_bf16_kernel<true><<<dim3((C / 8 + 63) / 64, P), 256, 0, stream>>>(reinterpret_cast<const bf16*>(x), M, C, ld, 512, workspace);
+    else
+        colsum_bf16_kernel<false><<<dim3((C + 255) / 256, P), 256, 0, stream>>>(reinterpret_cast<const bf16*>(x), M, C, ld, 512, workspace);
     UWU_CHECK_LAUNCH();
     colsum_final_kernel<<<(C + 127) / 128, 128, 0, stream>>>(workspace, P, C, accumulate, out);
     UWU_CHECK_LAUNCH();
@@ -429,6 +499,17 @@ extern "C" int uwu_im2col3x3(const void* x, int32_t N, int32_t H, int32_t W, int
     const int Ho = (H + 2 - 3) / stride + 1, Wo = (W + 2 - 3) / stride + 1;
     im2col3x3_kernel<<<ew_grid((long long)N * Ho * Wo * 9 * (C / 8), 256), 256, 0, stream>>>(
         reinterpret_cast<const bf16*>(x), N, H, W, C, stride, Ho, Wo, reinterpret_cast<bf16*>(cols));
+    UWU_CHECK_LAUNCH();
+    return UWU_OK;
+}
+extern "C" int uwu_conv_pack(const float* W, int32_t Co, int32_t Ci, int32_t taps, int32_t ci_pad, int32_t co_pad, int32_t cod_pad,
+                             void* fwd_bf16, void* dgrad_bf16, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    UWU_CHECK_ARG(W && fwd_bf16 && Co > 0 && Ci > 0 && taps > 0 && ci_pad >= Ci && co_pad >= Co && (!dgrad_bf16 || cod_pad >= Co),
+                  "uwu_conv_pack: bad arguments");
+    const long long total = (long long)co_pad * taps * ci_pad + (dgrad_bf16 ? (long long)Ci * taps * cod_pad : 0);
+    conv_pack_kernel<<<ew_grid(total, 256), 256, 0, stream>>>(W, Co, Ci, taps, ci_pad, co_pad, cod_pad,
+                                                              reinterpret_cast<bf16*>(fwd_bf16), reinterpret_cast<bf16*>(dgrad_bf16));
     UWU_CHECK_LAUNCH();
     return UWU_OK;
 }

@@ -494,6 +494,15 @@ def im2col3x3(x: torch.Tensor, N: int, H: int, W: int, C: int, stride: int = 1) 
     return cols
 
 
+def conv_pack(W: torch.Tensor, ci_p: int, co_p: int, cod_p: int, fwd: torch.Tensor, dgrad: Optional[torch.Tensor]):
+    """Conv2d fp32 weight [Co, Ci, kh, kw] -> bf16 forward operand [co_p, taps*ci_p] and (optional) flipped data-gradient
+    operand [Ci, taps*cod_p], zero padding written by the kernel."""
+    _req_cuda(W, fwd, dgrad)
+    assert W.dtype == torch.float32 and W.is_contiguous() and fwd.is_contiguous() and (dgrad is None or dgrad.is_contiguous())
+    Co, Ci, kh, kw = W.shape
+    check(lib().uwu_conv_pack(_ptr(W), Co, Ci, kh * kw, ci_p, co_p, cod_p, _ptr(fwd), _ptr(dgrad), _stream()), "uwu_conv_pack")
+
+
 def conv_wgrad_unpack(G: torch.Tensor, Co: int, Ci: int, Ci_pad: int, taps: int, wgrad: torch.Tensor, accumulate: bool = True):
     _req_cuda(G, wgrad)
     assert G.dtype == torch.float32 and wgrad.dtype == torch.float32 and wgrad.is_contiguous() and G.stride(1) == 1

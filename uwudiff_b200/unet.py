@@ -199,22 +199,27 @@ class Conv2d(nn.Conv2d, _Cached):
         W = self.weight.detach()
         Co, Ci, kh, kw = W.shape
         ci_p, co_p = _pad_to(Ci, 64), (Co if Co % 16 == 0 else _pad_to(Co, 16))
-        Wp = torch.zeros((co_p, kh, kw, ci_p), device=W.device, dtype=torch.float32)
-        Wp[:Co, :, :, :Ci] = W.permute(0, 2, 3, 1)
-        c = types.SimpleNamespace()
-        c.fwd = Wp.reshape(co_p, kh * kw * ci_p).to(BF16).contiguous()
-        c.ci_p, c.co_p = ci_p, co_p
-        c.bias = None
-        if self.bias is not None:
-            c.bias = torch.zeros((co_p,), device=W.device, dtype=torch.float32)
-            c.bias[:Co] = self.bias.detach()
-        # data gradient: correlation with the spatially flipped kernel, channels swapped
         cod_p = _pad_to(Co, 64)
-        Wd = torch.zeros((Ci, kh, kw, cod_p), device=W.device, dtype=torch.float32)
-        if self.stride[0] == 1:
-            Wd[:, :, :, :Co] = W.flip(2, 3).permute(1, 2, 3, 0)
-            c.dgrad = Wd.reshape(Ci, kh * kw * cod_p).to(BF16).contiguous()
-        else:
+        c = getattr(self, "_cache", None)
+        if c is None:  # operand buffers are allocated once; a trainable weight only refreshes their contents
+            c = types.SimpleNamespace()
+            c.ci_p, c.co_p, c.cod_p = ci_p, co_p, cod_p
+            c.fwd = torch.empty((co_p, kh * kw * ci_p), device=W.device, dtype=BF16)
+            c.dgrad = torch.empty((Ci, kh * kw * cod_p), device=W.device, dtype=BF16) if self.stride[0] == 1 else None
+            c.bias = torch.zeros((co_p,), device=W.device, dtype=torch.float32) if self.bias is not None else None
+        if W.is_cuda:
+            ops.conv_pack(W.contiguous(), ci_p, co_p, cod_p, c.fwd, c.dgrad)   # one launch: both operands, padding included
+        else:  # host-logic tests (tests/fake_ops.py) run the same layout in torch
+            Wp = torch.zeros((co_p, kh, kw, ci_p), device=W.device, dtype=torch.float32)
+            Wp[:Co, :, :, :Ci] = W.permute(0, 2, 3, 1)
+            c.fwd.copy_(Wp.reshape(co_p, kh * kw * ci_p))
+            if c.dgrad is not None:
+                Wd = torch.zeros((Ci, kh, kw, cod_p), device=W.device, dtype=torch.float32)
+                Wd[:, :, :, :Co] = W.flip(2, 3).permute(1, 2, 3, 0)
+                c.dgrad.copy_(Wd.reshape(Ci, kh * kw * cod_p))
+        if self.bias is not None:
+            c.bias[:Co].copy_(self.bias.detach())
+        if self.stride[0] != 1:
             # stride 2: one tap set per input phase (py, px); see Downsample2D.bwd
             c.dgrad_phase = []
             for py in range(2):
@@ -229,7 +234,6 @@ class Conv2d(nn.Conv2d, _Cached):
                             wk[:, :Co] = W[:, :, ky, kx].t()
                             cols.append(wk)
                     c.dgrad_phase.append((taps, torch.cat(cols, dim=1).to(BF16).contiguous()))
-        c.cod_p = cod_p
         self._cache = c
         return c
 
