@@ -96,6 +96,21 @@ def main(what):
         ops.gate_residual_fwd(xt, y, mod, 2 * C, L)
         ops.gate_residual_bwd(dyt, y, mod, 2 * C, L, dmod, 2 * C)
         ops.elementwise(mk(B * L, 4 * C), None, ops.EW_GELU_TANH)
+    elif what == "cross":
+        # cross-attention forward at the step shape on both paths (UWU_ATTN_SHORT is read per call), column sums, conv pack
+        B, heads, L, Lk = 16, 20, 1024, 77
+        C = heads * 64
+        q, k, v, do = mk(B * L, C), mk(B * Lk, C), mk(B * Lk, C), mk(B * L, C)
+        for flag in ("1", "0"):
+            os.environ["UWU_ATTN_SHORT"] = flag
+            o, lse = ops.attn_fwd(q, k, v, B, heads, L, Lk)
+        ops.attn_bwd(q, k, v, o, do, lse, B, heads, L, Lk)
+        x = mk(65536, 4608)
+        ops.colsum(x)
+        W = torch.randn(1280, 1280, 3, 3, device=dev)
+        fwd = torch.empty(1280, 9 * 1280, device=dev, dtype=torch.bfloat16)
+        dg = torch.empty(1280, 9 * 1280, device=dev, dtype=torch.bfloat16)
+        ops.conv_pack(W, 1280, 1280, 1280, fwd, dg)
     torch.cuda.synchronize()
 
 

@@ -346,28 +346,33 @@ __global__ void attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ o, long l
                                      long long lddo, const float* __restrict__ lse, int B, int heads, int Lq, int Lq_pad, int hd,
                                      float* __restrict__ lse2, float* __restrict__ delta) {
     pdl_trigger();
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    // 8 lanes per (row, head): lane j reads the j-th 16-byte chunk of the head's O and dO rows, so a warp instruction covers
+    // four contiguous 128-byte head slices (one thread per slice made every load touch 32 half-used sectors)
+    const long long item = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+    const int c = threadIdx.x & 7;
     const long long total = (long long)B * Lq * heads;
-    if (idx >= total) return;
-    const int h = (int)(idx % heads);
-    const long long bq = idx / heads;
+    const bool ok = item < total;
+    const long long it = ok ? item : total - 1;
+    const int h = (int)(it % heads);
+    const long long bq = it / heads;
     const int q = (int)(bq % Lq);
     const int b = (int)(bq / Lq);
-    const __nv_bfloat16* op = o + bq * ldo + h * hd;
-    const __nv_bfloat16* dp = dout + bq * lddo + h * hd;
     float acc = 0.f;
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-        if (c * 8 >= hd) break;
-        const uint4 a = *reinterpret_cast<const uint4*>(op + c * 8);
-        const uint4 d = *reinterpret_cast<const uint4*>(dp + c * 8);
+    if (ok && c * 8 < hd) {
+        const uint4 a = *reinterpret_cast<const uint4*>(o + bq * ldo + h * hd + c * 8);
+        const uint4 d = *reinterpret_cast<const uint4*>(dout + bq * lddo + h * hd + c * 8);
         const float2 a0 = unpack_bf16(a.x), a1 = unpack_bf16(a.y), a2 = unpack_bf16(a.z), a3 = unpack_bf16(a.w);
         const float2 d0 = unpack_bf16(d.x), d1 = unpack_bf16(d.y), d2 = unpack_bf16(d.z), d3 = unpack_bf16(d.w);
-        acc += a0.x * d0.x + a0.y * d0.y + a1.x * d1.x + a1.y * d1.y + a2.x * d2.x + a2.y * d2.y + a3.x * d3.x + a3.y * d3.y;
+        acc = a0.x * d0.x + a0.y * d0.y + a1.x * d1.x + a1.y * d1.y + a2.x * d2.x + a2.y * d2.y + a3.x * d3.x + a3.y * d3.y;
     }
-    const size_t oi = ((size_t)b * heads + h) * Lq_pad + q;
-    delta[oi] = acc;
-    lse2[oi] = lse[oi] * LOG2E;
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+    if (ok && c == 0) {
+        const size_t oi = ((size_t)b * heads + h) * Lq_pad + q;
+        delta[oi] = acc;
+        lse2[oi] = lse[oi] * LOG2E;
+    }
 }
 
 // dq[b*Lq+q, 64h+d] = scale * acc[b,h,q/128, d/4, q%128, d%4]   (single-pass backward: fp32 dQ scratch -> bf16)
@@ -870,7 +875,7 @@ extern "C" int uwu_attn_bwd(const void* q, const void* k, const void* v, const v
         UWU_CHECK_CUDA(cudaMemsetAsync(workspace, 0, (size_t)(rows * 2) * sizeof(float), stream));
     {
         const long long total = (long long)B * Lq * heads;
-        attn_bwd_prep_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(
+        attn_bwd_prep_kernel<<<(unsigned)((total * 8 + 255) / 256), 256, 0, stream>>>(
             reinterpret_cast<const __nv_bfloat16*>(o), ldo, reinterpret_cast<const __nv_bfloat16*>(dout), lddo, lse, B, heads,
             Lq, Lq_pad, head_dim, lse2, delta);
         UWU_CHECK_LAUNCH();

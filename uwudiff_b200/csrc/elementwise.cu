@@ -321,22 +321,34 @@ __global__ void __launch_bounds__(256) im2col3x3_kernel(const __nv_bfloat16* __r
 // zero padding included (every element of both outputs is written):
 //   fwd  [co_p, kk * ci_p] : fwd[co, t * ci_p + ci]  = W[co, ci, t]
 //   dgrad[Ci,  kk * cod_p] : dgrad[ci, t * cod_p + co] = W[co, ci, kk - 1 - t]   (correlation with the flipped kernel)
-__global__ void conv_pack_kernel(const float* __restrict__ W, int Co, int Ci, int kk, int ci_p, int co_p, int cod_p,
-                                 __nv_bfloat16* __restrict__ fwd, __nv_bfloat16* __restrict__ dgrad) {
-    const long long n_fwd = (long long)co_p * kk * ci_p;
-    const long long n_dg = dgrad ? (long long)Ci * kk * cod_p : 0;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_fwd + n_dg; i += (long long)gridDim.x * blockDim.x) {
-        if (i < n_fwd) {
-            const int ci = (int)(i % ci_p);
-            long long r = i / ci_p;
-            const int t = (int)(r % kk), co = (int)(r / kk);
-            fwd[i] = __float2bfloat16((co < Co && ci < Ci) ? W[((size_t)co * Ci + ci) * kk + t] : 0.f);
-        } else {
-            const long long j = i - n_fwd;
-            const int co = (int)(j % cod_p);
-            long long r = j / cod_p;
-            const int t = (int)(r % kk), ci = (int)(r / kk);
-            dgrad[j] = __float2bfloat16(co < Co ? W[((size_t)co * Ci + ci) * kk + (kk - 1 - t)] : 0.f);
+__global__ void __launch_bounds__(256) conv_pack_kernel(const float* __restrict__ W, int Co, int Ci, int kk, int ci_p, int co_p, int cod_p,
+                                                        __nv_bfloat16* __restrict__ fwd, __nv_bfloat16* __restrict__ dgrad) {
+    // block = a (32 co x 32 ci) tile of the padded weight, staged through shared memory so that the reads (ci*kk contiguous
+    // floats per co) and both writes (32 contiguous ci per (co, t); 32 contiguous co per (ci, t)) are coalesced
+    extern __shared__ float tile[];  // [32 co][32 ci][kk] (+1 padding per co row)
+    const int co0 = blockIdx.y * 32, ci0 = blockIdx.x * 32;
+    const int row = 32 * kk + 1;
+    for (int i = threadIdx.x; i < 32 * 32 * kk; i += blockDim.x) {
+        const int co = i / (32 * kk), r = i - co * 32 * kk;  // r = ci_local * kk + t, contiguous in W for a fixed co
+        const int ci = ci0 + r / kk;
+        float v = 0.f;
+        if (co0 + co < Co && ci < Ci) v = W[((size_t)(co0 + co) * Ci + ci0) * kk + r];
+        tile[co * row + r] = v;
+    }
+    __syncthreads();
+    // forward operand: fwd[co, t * ci_p + ci]
+    for (int i = threadIdx.x; i < 32 * kk * 32; i += blockDim.x) {
+        const int ci = i & 31, t = (i >> 5) % kk, co = (i >> 5) / kk;
+        if (co0 + co < co_p && ci0 + ci < ci_p)
+            fwd[(size_t)(co0 + co) * kk * ci_p + (size_t)t * ci_p + ci0 + ci] = __float2bfloat16(tile[co * row + ci * kk + t]);
+    }
+    // data-gradient operand: dgrad[ci, t * cod_p + co] = W[co, ci, kk - 1 - t]
+    if (dgrad) {
+        for (int i = threadIdx.x; i < 32 * kk * 32; i += blockDim.x) {
+            const int co = i & 31, t = (i >> 5) % kk, ci = (i >> 5) / kk;
+            if (ci0 + ci < Ci && co0 + co < cod_p)
+                dgrad[(size_t)(ci0 + ci) * kk * cod_p + (size_t)t * cod_p + co0 + co] =
+                    __float2bfloat16(tile[co * row + ci * kk + (kk - 1 - t)]);
         }
     }
 }
@@ -507,9 +519,11 @@ extern "C" int uwu_conv_pack(const float* W, int32_t Co, int32_t Ci, int32_t tap
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     UWU_CHECK_ARG(W && fwd_bf16 && Co > 0 && Ci > 0 && taps > 0 && ci_pad >= Ci && co_pad >= Co && (!dgrad_bf16 || cod_pad >= Co),
                   "uwu_conv_pack: bad arguments");
-    const long long total = (long long)co_pad * taps * ci_pad + (dgrad_bf16 ? (long long)Ci * taps * cod_pad : 0);
-    conv_pack_kernel<<<ew_grid(total, 256), 256, 0, stream>>>(W, Co, Ci, taps, ci_pad, co_pad, cod_pad,
-                                                              reinterpret_cast<bf16*>(fwd_bf16), reinterpret_cast<bf16*>(dgrad_bf16));
+    UWU_CHECK_ARG(taps <= 16, "uwu_conv_pack: at most 16 taps");
+    const int cmax = co_pad > cod_pad ? co_pad : cod_pad;
+    dim3 grid((ci_pad + 31) / 32, (cmax + 31) / 32);
+    conv_pack_kernel<<<grid, 256, (size_t)32 * (32 * taps + 1) * sizeof(float), stream>>>(
+        W, Co, Ci, taps, ci_pad, co_pad, cod_pad, reinterpret_cast<bf16*>(fwd_bf16), reinterpret_cast<bf16*>(dgrad_bf16));
     UWU_CHECK_LAUNCH();
     return UWU_OK;
 }
