@@ -414,6 +414,8 @@ struct AttnBwdArgs {
     __nv_bfloat16* dv;
     long long lddv;
     int hd;  // head dim (multiple of 8, <= 64)
+    int direct_dq;  // single-pass mode with ONE key tile (cross-attention): each dQ tile is complete in its CTA -> bf16 store,
+                    // no fp32 scratch, no memset, no conversion pass
 };
 
 // Shared-memory plan: two resident operand tiles, kStages x two streamed operand tiles, P / dS tiles.
@@ -633,6 +635,23 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_kernel(const __grid_c
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(dq_empty);
+            if (p.direct_dq) {
+                const int qrow = tile * 128 + row;
+                if (qrow < p.Lq) {
+                    __nv_bfloat16* op = p.dq + ((size_t)b * p.Lq + qrow) * p.lddq + h * p.hd + quarter * 16;
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        if (quarter * 16 + c * 8 >= p.hd) break;
+                        uint4 u;
+                        u.x = pack_bf16(__uint_as_float(rq[c * 8 + 0]) * p.scale, __uint_as_float(rq[c * 8 + 1]) * p.scale);
+                        u.y = pack_bf16(__uint_as_float(rq[c * 8 + 2]) * p.scale, __uint_as_float(rq[c * 8 + 3]) * p.scale);
+                        u.z = pack_bf16(__uint_as_float(rq[c * 8 + 4]) * p.scale, __uint_as_float(rq[c * 8 + 5]) * p.scale);
+                        u.w = pack_bf16(__uint_as_float(rq[c * 8 + 6]) * p.scale, __uint_as_float(rq[c * 8 + 7]) * p.scale);
+                        *reinterpret_cast<uint4*>(op + c * 8) = u;
+                    }
+                }
+                return;
+            }
             float* dst = p.dq_acc + (bh * (size_t)(p.Lq_pad / 128) + tile) * (size_t)(16 * 128 * 4) + ((size_t)(quarter * 4) * 128 + row) * 4;
 #pragma unroll
             for (int c = 0; c < 4; ++c)
@@ -887,7 +906,13 @@ extern "C" int uwu_attn_bwd(const void* q, const void* k, const void* v, const v
         UWU_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdCfg<2>::SMEM));
         attr_set = true;
     }
-    if (attn_bwd_mode() == 1) {
+    a.direct_dq = 0;
+    if (attn_bwd_mode() == 1 && Lk <= 128) {
+        a.dq_acc = workspace + 2 * rows;
+        a.direct_dq = 1;
+        UWU_CHECK_CUDA(launch_pdl(attn_bwd_kernel<2>, dim3(1, heads, B), dim3(BWD_THREADS), BwdCfg<2>::SMEM, stream, a));
+        UWU_CHECK_LAUNCH();
+    } else if (attn_bwd_mode() == 1) {
         a.dq_acc = workspace + 2 * rows;
         UWU_CHECK_CUDA(cudaMemsetAsync(a.dq_acc, 0, (size_t)(rows * 64) * sizeof(float), stream));
         UWU_CHECK_CUDA(launch_pdl(attn_bwd_kernel<2>, dim3((Lk + 127) / 128, heads, B), dim3(BWD_THREADS), BwdCfg<2>::SMEM, stream,
