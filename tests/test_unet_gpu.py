@@ -150,6 +150,29 @@ def test_lycoris_at_sdxl_like_widths_matches_oracle():
     assert abs(tot_p - tot_o) / tot_o < 1e-2
 
 
+def test_batched_fold_is_bit_identical_to_per_adapter_folds():
+    """uwu_fold_batch (one launch for every adapter) writes exactly what the per-adapter fold kernels write."""
+    from uwudiff_b200 import lycoris as PL
+    from uwudiff_b200 import unet as P
+
+    cfg, o, p, x, t, ctx, ac = build(seed=12)
+    no, npd = with_lycoris(o, p, scale=0.1)
+    P.FOLD.epoch += 1
+    npd.fold_all()
+    torch.cuda.synchronize()
+    checked = 0
+    for ad, org in zip(npd.loras, npd._orgs):
+        if isinstance(ad, PL.NormDelta):
+            g, b = org.fold_dst()
+            assert torch.equal(g, org.weight + ad.w_norm * ad.multiplier) and torch.equal(b, org.bias + ad.b_norm * ad.multiplier)
+        else:
+            ref = torch.empty((org.out_features, org.in_features), device="cuda", dtype=torch.bfloat16)
+            ad.fold_into(org._w2d(), ref)
+            assert torch.equal(org.fold_dst(), ref), ad.lora_name
+        checked += 1
+    assert checked == len(npd.loras) and checked > 20
+
+
 def test_loha_adapters_forward_and_gradients_match_oracle():
     """north_star (d): LoHa deltas folded into the base GEMM operand, their low-rank gradients from the same backward."""
     cfg, o, p, x, t, ctx, ac = build(seed=4)

@@ -196,18 +196,36 @@ __global__ void __launch_bounds__(256) fold_batch_kernel(const uwu_fold_entry* _
         return;
     }
     __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(e.dst);
-    for (long long i4 = beg + threadIdx.x * 4; i4 < end; i4 += blockDim.x * 4) {
-        const int n = (int)(i4 / K), k = (int)(i4 - (long long)n * K);
+    // 32-bit index arithmetic (N * K < 2^31 for every layer), row / column advanced incrementally instead of divided
+    const int ibeg = (int)beg, iend = (int)end;
+    int i4 = ibeg + threadIdx.x * 4;
+    int n = i4 / K, k = i4 - n * K;
+    const int step = blockDim.x * 4, dn = step / K, dk = step - dn * K;
+    for (; i4 < iend; i4 += step, n += dn, k += dk) {
+        if (k >= K) {
+            k -= K;
+            ++n;
+        }
         const float4 w = *reinterpret_cast<const float4*>(e.W + i4);
         float v[4] = {w.x, w.y, w.z, w.w};
         if (e.kind == 1) {  // LoKr: + kron(w1, w2)[n, k] * scale, same rounding sequence as fold_lokr_kernel
             const int ok = e.p0, in_n = e.p1, im = e.p2;
             const int l = n / ok, kk = n - l * ok;
+            if ((in_n & 3) == 0) {  // the 4 columns share one w1 element and read 4 consecutive w2 elements
+                const int ii = k / in_n, nn = k - ii * in_n;
+                const float w1v = e.a[l * im + ii];
+                const float4 w2v = *reinterpret_cast<const float4*>(e.b + kk * in_n + nn);
+                v[0] = __fadd_rn(v[0], __fmul_rn(__fmul_rn(w1v, w2v.x), e.scale));
+                v[1] = __fadd_rn(v[1], __fmul_rn(__fmul_rn(w1v, w2v.y), e.scale));
+                v[2] = __fadd_rn(v[2], __fmul_rn(__fmul_rn(w1v, w2v.z), e.scale));
+                v[3] = __fadd_rn(v[3], __fmul_rn(__fmul_rn(w1v, w2v.w), e.scale));
+            } else {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int c = k + j;
-                const int ii = c / in_n, nn = c - ii * in_n;
-                v[j] = __fadd_rn(v[j], __fmul_rn(__fmul_rn(e.a[l * im + ii], e.b[kk * in_n + nn]), e.scale));
+                for (int j = 0; j < 4; ++j) {
+                    const int c = k + j;
+                    const int ii = c / in_n, nn = c - ii * in_n;
+                    v[j] = __fadd_rn(v[j], __fmul_rn(__fmul_rn(e.a[l * im + ii], e.b[kk * in_n + nn]), e.scale));
+                }
             }
         } else if (e.kind == 2) {  // LoRA: + (up @ down)[n, k] * scale
             const int r = e.p0;

@@ -326,7 +326,7 @@ class LycorisNetwork(nn.Module):
             chunk = 1 << 14
 
             def add(kind, W, a, b, dst, N, K, p0=0, p1=0, p2=0, scale=1.0):
-                assert W.is_contiguous() and dst.is_contiguous() and (kind == 3 or K % 4 == 0)
+                assert W.is_contiguous() and dst.is_contiguous() and (kind == 3 or K % 4 == 0) and N * K < 2 ** 31
                 e = _lib.FoldEntry()
                 e.W, e.a, e.b, e.dst = W.data_ptr(), a.data_ptr(), (b.data_ptr() if b is not None else None), dst.data_ptr()
                 e.kind, e.N, e.K, e.p0, e.p1, e.p2, e.scale = kind, N, K, p0, p1, p2, scale
