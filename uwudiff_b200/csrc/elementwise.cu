@@ -299,22 +299,24 @@ __global__ void colsum_final_kernel(const float* __restrict__ partial, int P, in
 // cols[m, t*C + c] = x[n, ho*stride + dy_t - 1, wo*stride + dx_t - 1, c]  (0 outside the image), m = (n, ho, wo), t = 3*ky + kx
 __global__ void __launch_bounds__(256) im2col3x3_kernel(const __nv_bfloat16* __restrict__ x, int N, int H, int W, int C, int stride,
                                                         int Ho, int Wo, __nv_bfloat16* __restrict__ cols) {
+    // thread = one 8-channel vector of one output pixel, all 9 taps (one index decomposition per 9 x 16 bytes written)
     const int cv = C >> 3;
-    const long long total = (long long)N * Ho * Wo * 9 * cv;
+    const long long total = (long long)N * Ho * Wo * cv;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int v = (int)(i % cv);
-        long long r = i / cv;
-        const int t = (int)(r % 9);
-        r /= 9;
-        const int wo = (int)(r % Wo);
-        r /= Wo;
-        const int ho = (int)(r % Ho);
-        const int n = (int)(r / Ho);
-        const int hi = ho * stride + t / 3 - 1, wi = wo * stride + t % 3 - 1;
-        uint4 u = make_uint4(0, 0, 0, 0);
-        if (hi >= 0 && hi < H && wi >= 0 && wi < W)
-            u = *reinterpret_cast<const uint4*>(x + (((size_t)n * H + hi) * W + wi) * C + v * 8);
-        *reinterpret_cast<uint4*>(cols + (((size_t)n * Ho + ho) * Wo + wo) * (size_t)(9 * C) + (size_t)t * C + v * 8) = u;
+        const long long m = i / cv;
+        const int v = (int)(i - m * cv);
+        const int wo = (int)(m % Wo);
+        const long long r = m / Wo;
+        const int ho = (int)(r % Ho), n = (int)(r / Ho);
+        __nv_bfloat16* dst = cols + (size_t)m * (size_t)(9 * C) + v * 8;
+        const __nv_bfloat16* src = x + ((size_t)n * H * W) * C + v * 8;
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+            const int hi = ho * stride + t / 3 - 1, wi = wo * stride + t % 3 - 1;
+            uint4 u = make_uint4(0, 0, 0, 0);
+            if (hi >= 0 && hi < H && wi >= 0 && wi < W) u = *reinterpret_cast<const uint4*>(src + ((size_t)hi * W + wi) * C);
+            *reinterpret_cast<uint4*>(dst + (size_t)t * C) = u;
+        }
     }
 }
 // Conv2d master weight W[Co, Ci, kk] (fp32, kk = kh*kw taps) -> the two bf16 GEMM operands of the implicit-GEMM convolution,
@@ -509,7 +511,7 @@ extern "C" int uwu_im2col3x3(const void* x, int32_t N, int32_t H, int32_t W, int
     UWU_CHECK_ARG(x && cols && N > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0 && (stride == 1 || stride == 2),
                   "uwu_im2col3x3: bad arguments (C %% 8 == 0, stride 1 or 2)");
     const int Ho = (H + 2 - 3) / stride + 1, Wo = (W + 2 - 3) / stride + 1;
-    im2col3x3_kernel<<<ew_grid((long long)N * Ho * Wo * 9 * (C / 8), 256), 256, 0, stream>>>(
+    im2col3x3_kernel<<<ew_grid((long long)N * Ho * Wo * (C / 8), 256), 256, 0, stream>>>(
         reinterpret_cast<const bf16*>(x), N, H, W, C, stride, Ho, Wo, reinterpret_cast<bf16*>(cols));
     UWU_CHECK_LAUNCH();
     return UWU_OK;
