@@ -285,12 +285,23 @@ __global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* _
         for (int j = 0; j < 8; ++j) o[j] = (sh[0][tx][j] + sh[1][tx][j]) + (sh[2][tx][j] + sh[3][tx][j]);
     }
 }
-__global__ void colsum_final_kernel(const float* __restrict__ partial, int P, int C, int accumulate, float* __restrict__ out) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
+// out[c] (+)= sum_p partial[p, c]: 32 columns x 8 partial lanes per block
+__global__ void __launch_bounds__(256) colsum_final_kernel(const float* __restrict__ partial, int P, int C, int accumulate,
+                                                           float* __restrict__ out) {
+    __shared__ float sh[8][32];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + tx;
     float a = 0.f;
-    for (int p = 0; p < P; ++p) a += partial[(size_t)p * C + c];
-    out[c] = accumulate ? out[c] + a : a;
+    if (c < C)
+        for (int p = ty; p < P; p += 8) a += partial[(size_t)p * C + c];
+    sh[ty][tx] = a;
+    __syncthreads();
+    if (ty == 0 && c < C) {
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s += sh[k][tx];
+        out[c] = accumulate ? out[c] + s : s;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -355,16 +366,24 @@ __global__ void __launch_bounds__(256) conv_pack_kernel(const float* __restrict_
     }
 }
 // wgrad[co, ci, ky, kx] (+)= G[co, (3*ky + kx) * Cp + ci]   (torch Conv2d weight layout <- packed GEMM layout), kk = kh*kw
-__global__ void conv_wgrad_unpack_kernel(const float* __restrict__ G, long long ldg, int Co, int Ci, int Cp, int kk, int accumulate,
-                                         float* __restrict__ wgrad) {
-    const long long total = (long long)Co * Ci * kk;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int t = (int)(i % kk);
-        long long r = i / kk;
-        const int ci = (int)(r % Ci);
-        const int co = (int)(r / Ci);
-        const float g = G[(size_t)co * ldg + (size_t)t * Cp + ci];
-        wgrad[i] = accumulate ? wgrad[i] + g : g;
+__global__ void __launch_bounds__(256) conv_wgrad_unpack_kernel(const float* __restrict__ G, long long ldg, int Co, int Ci, int Cp, int kk,
+                                                                int accumulate, float* __restrict__ wgrad) {
+    // warp = 32 consecutive ci of one co: per tap a contiguous 128-byte read of G; the 32 x kk results are transposed through
+    // shared memory (stride kk <= 9 is odd or 1: conflict-free) so that the kk*32 contiguous floats of wgrad are written coalesced
+    __shared__ float sh[8][32 * 9];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ci_tiles = (Ci + 31) / 32;
+    const int total = Co * ci_tiles;
+    for (int w = blockIdx.x * 8 + warp; w < total; w += gridDim.x * 8) {
+        const int co = w / ci_tiles, ci0 = (w - co * ci_tiles) * 32;
+        const int ci = ci0 + lane;
+        const float* g = G + (size_t)co * ldg + ci;
+        for (int t = 0; t < kk; ++t) sh[warp][lane * kk + t] = ci < Ci ? g[(size_t)t * Cp] : 0.f;
+        __syncwarp();
+        const int nvalid = min(32, Ci - ci0) * kk;
+        float* wout = wgrad + ((size_t)co * Ci + ci0) * kk;
+        for (int e = lane; e < nvalid; e += 32) wout[e] = accumulate ? wout[e] + sh[warp][e] : sh[warp][e];
+        __syncwarp();
     }
 }
 // out[n, c] (+)= sum_{r < rows} x[n * rows + r, c]   (per-image column sums: time-embedding gradients), one block per (n, 64 columns)
@@ -501,7 +520,7 @@ extern "C" int uwu_colsum_bf16(const void* x, int64_t M, int32_t C, int64_t ld, 
     else
         colsum_bf16_kernel<false><<<dim3((C + 255) / 256, P), 256, 0, stream>>>(reinterpret_cast<const bf16*>(x), M, C, ld, 512, workspace);
     UWU_CHECK_LAUNCH();
-    colsum_final_kernel<<<(C + 127) / 128, 128, 0, stream>>>(workspace, P, C, accumulate, out);
+    colsum_final_kernel<<<(C + 31) / 32, 256, 0, stream>>>(workspace, P, C, accumulate, out);
     UWU_CHECK_LAUNCH();
     return UWU_OK;
 }
@@ -534,7 +553,9 @@ extern "C" int uwu_conv_wgrad_unpack(const float* G, int64_t ldg, int32_t Co, in
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     UWU_CHECK_ARG(G && wgrad && Co > 0 && Ci > 0 && Ci_pad >= Ci && taps > 0 && ldg >= (int64_t)taps * Ci_pad,
                   "uwu_conv_wgrad_unpack: bad arguments");
-    conv_wgrad_unpack_kernel<<<ew_grid((long long)Co * Ci * taps, 256), 256, 0, stream>>>(G, ldg, Co, Ci, Ci_pad, taps, accumulate, wgrad);
+    UWU_CHECK_ARG(taps <= 9, "uwu_conv_wgrad_unpack: at most 9 taps");
+    conv_wgrad_unpack_kernel<<<ew_grid((long long)Co * ((Ci + 31) / 32) * 32, 256), 256, 0, stream>>>(G, ldg, Co, Ci, Ci_pad, taps, accumulate,
+                                                                                                 wgrad);
     UWU_CHECK_LAUNCH();
     return UWU_OK;
 }
