@@ -64,6 +64,8 @@ class _W(nn.Module):
 class LoraLinear(_Adapter):
     def __init__(self, name: str, org: nn.Linear, multiplier: float, dim: int, alpha: float):
         super().__init__()
+        if dim > 16:
+            raise NotImplementedError("uwudiff_b200.lycoris: LoRA rank > 16 is not built (the gradient kernels keep the rank in registers)")
         self.lora_name, self.multiplier, self.dim = name, multiplier, dim
         self.lora_down = _W(dim, org.in_features)
         self.lora_up = _W(org.out_features, dim)
