@@ -199,36 +199,50 @@ __global__ void gn_bwd_stats_kernel(const __nv_bfloat16* __restrict__ x, const _
 // backward pass 1b: reduce chunk partials -> per (n, c) sums; then per (n, g): A = sum_c gamma*S1, B = sum_c gamma*S2;
 // also accumulates dgamma/dbeta (sum over n) when requested.
 //   red[n, {0,1}, g] = {A/cnt, B/cnt}
-__global__ void gn_bwd_reduce_kernel(const float* __restrict__ wsb, const float* __restrict__ gamma, GNGeom g,
-                                     float* __restrict__ red, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+__global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(const float* __restrict__ wsb, const float* __restrict__ gamma, GNGeom g,
+                                                            int gpb, float* __restrict__ red, float* __restrict__ dgamma,
+                                                            float* __restrict__ dbeta) {
     pdl_trigger();
-    // one block per n; threads over channels
-    extern __shared__ float sh[];  // [2][C] per-channel sums for this n
-    const int n = blockIdx.x;
-    for (int c = threadIdx.x; c < g.C; c += blockDim.x) {
+    // block = (image n, gpb consecutive groups): its nc = gpb * cpg channels are summed over the chunk partials by
+    // 256 / nc lanes per channel (fixed summation order: deterministic), then folded per group
+    extern __shared__ float sh[];  // [lanes][2][nc] partial sums, then [2][nc] channel sums in place of lane 0
+    const int n = blockIdx.x, g0 = blockIdx.y * gpb;
+    const int cpg = g.C / g.G;
+    const int ng = min(gpb, g.G - g0), nc = ng * cpg, c0 = g0 * cpg;
+    const int lanes = max(1, (int)blockDim.x / nc);
+    const int cl = threadIdx.x % nc, kl = threadIdx.x / nc;
+    if (kl < lanes) {
         float a = 0.f, b = 0.f;
-#pragma unroll 8
-        for (int k = 0; k < g.chunks; ++k) {
-            const float* p = wsb + ((size_t)n * g.chunks + k) * 2 * g.C;
-            a += p[c];
-            b += p[g.C + c];
+        for (int k = kl; k < g.chunks; k += lanes) {
+            const float* p = wsb + ((size_t)n * g.chunks + k) * 2 * g.C + c0 + cl;
+            a += p[0];
+            b += p[g.C];
         }
-        sh[c] = a;
-        sh[g.C + c] = b;
-        if (dgamma) atomicAdd(&dgamma[c], b);
-        if (dbeta) atomicAdd(&dbeta[c], a);
+        sh[(kl * 2) * nc + cl] = a;
+        sh[(kl * 2 + 1) * nc + cl] = b;
     }
     __syncthreads();
-    const int cpg = g.C / g.G;
+    for (int c = threadIdx.x; c < nc; c += blockDim.x) {
+        float a = 0.f, b = 0.f;
+        for (int l = 0; l < lanes; ++l) {
+            a += sh[(l * 2) * nc + c];
+            b += sh[(l * 2 + 1) * nc + c];
+        }
+        sh[c] = a;        // lane 0 slots now hold the channel totals (each slot is read before it is overwritten: same thread)
+        sh[nc + c] = b;
+        if (dgamma) atomicAdd(&dgamma[c0 + c], b);
+        if (dbeta) atomicAdd(&dbeta[c0 + c], a);
+    }
+    __syncthreads();
     const float cnt = (float)g.HW * (float)cpg;
-    for (int gi = threadIdx.x; gi < g.G; gi += blockDim.x) {
+    for (int gi = threadIdx.x; gi < ng; gi += blockDim.x) {
         float A = 0.f, B = 0.f;
         for (int c = gi * cpg; c < (gi + 1) * cpg; ++c) {
-            A = fmaf(gamma[c], sh[c], A);
-            B = fmaf(gamma[c], sh[g.C + c], B);
+            A = fmaf(gamma[c0 + c], sh[c], A);
+            B = fmaf(gamma[c0 + c], sh[nc + c], B);
         }
-        red[((size_t)n * 2) * g.G + gi] = A / cnt;
-        red[((size_t)n * 2 + 1) * g.G + gi] = B / cnt;
+        red[((size_t)n * 2) * g.G + g0 + gi] = A / cnt;
+        red[((size_t)n * 2 + 1) * g.G + g0 + gi] = B / cnt;
     }
 }
 
@@ -694,7 +708,17 @@ extern "C" int uwu_groupnorm_bwd(const void* x, const void* dy, int32_t N, int32
     else
         gn_bwd_stats_kernel<false><<<grid, threads, (size_t)g.rpi * 2 * C * sizeof(float), stream>>>(xp, dyp, stats, gamma, beta, g, wsb);
     UWU_CHECK_LAUNCH();
-    gn_bwd_reduce_kernel<<<N, 256, 2 * C * sizeof(float), stream>>>(wsb, gamma, g, red, dgamma, dbeta);
+    {
+        const int cpg = C / G;
+        int gpb = 128 / cpg;  // ~128 channels per block
+        if (gpb < 1) gpb = 1;
+        if (gpb > G) gpb = G;
+        const int nc = gpb * cpg;
+        UWU_CHECK_ARG(nc <= 256, "uwu_groupnorm_bwd: more than 256 channels per group");
+        const int lanes = 256 / nc > 0 ? 256 / nc : 1;
+        gn_bwd_reduce_kernel<<<dim3(N, (G + gpb - 1) / gpb), 256, (size_t)lanes * 2 * nc * sizeof(float), stream>>>(wsb, gamma, g, gpb, red,
+                                                                                                            dgamma, dbeta);
+    }
     UWU_CHECK_LAUNCH();
     if (fuse_silu)
         gn_bwd_apply_kernel<true><<<grid, threads, 0, stream>>>(xp, dyp, stats, gamma, beta, red,
