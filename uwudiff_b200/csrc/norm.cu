@@ -777,7 +777,13 @@ extern "C" int uwu_layernorm_bwd(const void* x, const void* dy, int32_t M, int32
     UWU_CHECK_ARG(!want_pg || workspace, "uwu_layernorm_bwd: workspace required for parameter gradients");
     if (want_pg && C <= 192 * 8) {
         const int threads = ((C / 8 + 31) / 32) * 32;
-        const int grid2 = ln_bwd_grid(M);
+        // at most one resident wave (register-limited blocks per SM): the kernel strides over the rows, so for the 160-thread
+        // blocks of C = 1280 a grid of 6 per SM ran as one full wave plus a half-empty one (62 -> 52 us)
+        int per_sm = 65536 / (threads * 84);
+        if (per_sm > 8) per_sm = 8;
+        if (per_sm < 1) per_sm = 1;
+        int grid2 = ln_bwd_grid(M);
+        if (grid2 > per_sm * sm_count()) grid2 = per_sm * sm_count();
         ln_bwd_cols_kernel<2><<<grid2, threads, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x),
                                                              reinterpret_cast<const __nv_bfloat16*>(dy), M, C, gamma, stats,
                                                              reinterpret_cast<const __nv_bfloat16*>(dres),
