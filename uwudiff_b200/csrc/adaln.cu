@@ -401,7 +401,8 @@ extern "C" int uwu_adaln_fwd(const void* x, int64_t M, int32_t C, float eps, con
     if (int rc = check_mod("uwu_adaln_fwd", M, C, mod, ld_mod, rows_per_mod)) return rc;
     UWU_CHECK_ARG(x && y && stats && shift_off % 4 == 0 && scale_off % 4 == 0, "uwu_adaln_fwd: bad pointer / offset");
     int blocks = (int)((M + AD_WARPS - 1) / AD_WARPS);
-    if (blocks > sm_count() * 8) blocks = sm_count() * 8;
+    const int per_sm = C / 8 <= 32 ? 8 : C / 8 <= 96 ? 4 : C / 8 <= 160 ? 3 : 2;  // resident blocks per SM at the variant's registers
+    if (blocks > sm_count() * per_sm) blocks = sm_count() * per_sm;
 #define CALL(V) adaln_fwd_kernel<V><<<blocks, AD_WARPS * 32, 0, stream>>>(reinterpret_cast<const bf16*>(x), (int)M, C, eps, mod, ld_mod, shift_off, scale_off, rows_per_mod, reinterpret_cast<bf16*>(y), stats)
     UWU_AD_DISPATCH(C / 8, CALL);
 #undef CALL

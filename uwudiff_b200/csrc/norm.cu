@@ -649,9 +649,11 @@ __global__ void __launch_bounds__(128) ln_param_reduce_kernel(const float* __res
     }
 }
 
-static int ln_grid(int M) {
+// one resident wave of 256-thread blocks: `per_sm` = blocks that fit an SM at the kernel's register count (the kernels stride
+// over the rows, so a larger grid only adds a partially filled last wave)
+static int ln_grid(int M, int per_sm = 8) {
     int blocks = (M + 7) / 8;
-    const int cap = sm_count() * 8;
+    const int cap = sm_count() * per_sm;
     return blocks < cap ? blocks : cap;
 }
 
@@ -744,7 +746,8 @@ extern "C" int uwu_layernorm_fwd(const void* x, int32_t M, int32_t C, float eps,
     auto* yp = reinterpret_cast<__nv_bfloat16*>(y);
     const int rpm = rows_per_mod > 0 ? rows_per_mod : 1;
     const int cv = C / 8;
-#define UWU_LN_FWD(V) ln_fwd_kernel<V><<<ln_grid(M), 256, 0, stream>>>(xp, M, C, eps, gamma, beta, mod_scale, mod_shift, rpm, yp, stats)
+    // registers per thread: <1> 32, <2> 53, <3> 64, <5> 79, <8> 127  ->  resident 256-thread blocks per SM 8 / 4 / 4 / 3 / 2
+#define UWU_LN_FWD(V) ln_fwd_kernel<V><<<ln_grid(M, (V) == 1 ? 8 : (V) <= 3 ? 4 : (V) == 5 ? 3 : 2), 256, 0, stream>>>(xp, M, C, eps, gamma, beta, mod_scale, mod_shift, rpm, yp, stats)
     if (cv <= 32) UWU_LN_FWD(1);
     else if (cv <= 64) UWU_LN_FWD(2);
     else if (cv <= 96) UWU_LN_FWD(3);
