@@ -27,6 +27,7 @@ extern "C" {
 /* dtype codes */
 #define UWU_F32 0
 #define UWU_BF16 1
+#define UWU_I64 2
 
 /* target / prediction types (src/duwu/loss/diffusion.py:84-98) */
 #define UWU_TARGET_EPSILON 0
@@ -143,6 +144,11 @@ int64_t uwu_wmse_workspace_floats(int32_t B, int64_t n_per);
 int uwu_wmse_fwd(const void* pred, int32_t pred_dtype, const void* target, int32_t target_dtype, int32_t B,
                  int64_t n_per, const float* w, float* workspace, float* losses, float* loss, void* stream);
 /* dpred = grad_scale * (*grad_scale_dev or 1) * w0*w1 * 2 (pred - target) / (n_per * B) */
+/* Per-timestep validation statistics: counts[t] += 1, sums[t] += l, sqsums[t] += l*l for every sample (one scatter-add launch;
+ * replaces the N_t boolean-mask loop of PlotValLossPerTimestep.on_validation_batch_end, src/duwu/trainer/callbacks.py:75-92).
+ * timesteps: int64 (UWU_I64) or fp32 (UWU_F32, truncated like `.long()`); out-of-range values are ignored. */
+int uwu_timestep_hist(const float* losses, const void* timesteps, int32_t t_dtype, int32_t B, int32_t T, float* counts,
+                      float* sums, float* sqsums, void* stream);
 int uwu_wmse_bwd(const void* pred, int32_t pred_dtype, const void* target, int32_t target_dtype, int32_t B,
                  int64_t n_per, const float* w, const float* grad_scale_dev, float grad_scale, void* dpred,
                  int32_t dpred_dtype, void* stream);

@@ -307,3 +307,41 @@ def test_full_size_properties(dl):
     assert abs(l2.item() / l1.item() - 4.0) < 1e-5
     ref = (((x_t - v) ** 2).flatten(1).mean(1) * w[0] * w[1])
     np.testing.assert_allclose(ls1.cpu().numpy(), ref.cpu().numpy(), rtol=2e-5)
+
+
+def test_timestep_histogram_matches_reference_loop():
+    """PlotValLossPerTimestep accumulation (callbacks.py:75-92, restated as the reference's mask loop) vs the scatter-add kernel,
+    int64 and fractional (rectified-flow) timesteps, accumulation over two batches, epoch-end statistics."""
+    import types
+
+    from uwudiff_b200.callbacks import PlotValLossPerTimestep
+
+    T = 1000
+    g = torch.Generator().manual_seed(3)
+    cb = PlotValLossPerTimestep(n_diffusion_time_steps=T)
+    mod = types.SimpleNamespace(n_diffusion_time_steps=T, ema_loss=torch.zeros((), device="cuda"))
+    cb.on_validation_epoch_start(None, mod)
+    ref = torch.zeros(3, T, dtype=torch.float64)
+    for k, tdtype in enumerate((torch.int64, torch.float32)):
+        losses = torch.rand(4096, generator=g) * 2
+        t = torch.randint(0, T, (4096,), generator=g)
+        t[:7] = torch.tensor([0, 999, 5, 5, 5, 999, 0])
+        tt = t.to(tdtype) + (0.37 if tdtype == torch.float32 else 0)
+        aux = types.SimpleNamespace(losses=losses.cuda(), timesteps=tt.cuda())
+        cb.on_validation_batch_end(None, mod, (None, aux), None, k)
+        tl = tt.long()
+        for ts in range(T):  # the reference's loop
+            m = tl == ts
+            ref[0, ts] += m.sum()
+            ref[1, ts] += losses[m].double().sum()
+            ref[2, ts] += (losses[m].double() ** 2).sum()
+    assert torch.equal(cb.validation_timestep_counts.cpu().double(), ref[0])
+    assert torch.allclose(cb.validation_timestep_losses.cpu().double(), ref[1], rtol=1e-5, atol=1e-6)
+    assert torch.allclose(cb.validation_timestep_squared_losses.cpu().double(), ref[2], rtol=1e-5, atol=1e-6)
+    ts, mean, std = cb.on_validation_epoch_end(None, mod)
+    valid = ref[0] > 0
+    assert torch.equal(ts.cpu(), torch.nonzero(valid).flatten())
+    assert torch.allclose(mean.cpu().double(), ref[1][valid] / ref[0][valid], rtol=1e-5)
+    rstd = torch.sqrt(torch.clamp(ref[2][valid] / ref[0][valid] - (ref[1][valid] / ref[0][valid]) ** 2, min=0))
+    assert torch.allclose(std.cpu().double(), rstd, rtol=1e-3, atol=1e-4)
+

@@ -113,6 +113,7 @@ SIGNATURES = {
     "uwu_lokr_grad_plan_blocks": (C.c_int32, [_I32, _I32, _I32, _I32, _I32, _I32]),
     "uwu_lokr_grad_batch": (C.c_int, [_P, _I32, _I32, _P]),
     "uwu_conv_pack": (C.c_int, [_P, _I32, _I32, _I32, _I32, _I32, _I32, _P, _P, _P]),
+    "uwu_timestep_hist": (C.c_int, [_P, _P, _I32, _I32, _I32, _P, _P, _P, _P]),
     "uwu_fold_loha": (C.c_int, [_P, _P, _P, _P, _P, _I32, _I32, _I32, _F, _P, _P]),
     "uwu_loha_grad": (C.c_int, [_P, _I64, _P, _P, _P, _P, _I32, _I32, _I32, _F, _P, _P, _P, _P, _P]),
     "uwu_fold_lokr": (C.c_int, [_P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _F, _P, _P]),

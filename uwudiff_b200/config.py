@@ -26,6 +26,7 @@ TARGET_ALIASES = {
     "duwu.loss.DiffusionLoss": "uwudiff_b200.loss.DiffusionLoss",
     "duwu.loss.RectifiedFlowLoss": "uwudiff_b200.loss.RectifiedFlowLoss",
     "duwu.loss.NNWeightedRFLoss": "uwudiff_b200.loss.NNWeightedRFLoss",
+    "duwu.trainer.callbacks.PlotValLossPerTimestep": "uwudiff_b200.callbacks.PlotValLossPerTimestep",
     "duwu.data.TrainDataModule": "uwudiff_b200.data.TrainDataModule",
     "duwu.data.DummyDataset": "uwudiff_b200.data.DummyDataset",
     "duwu.modules.unet_patch.UNet2DFromScratch": "uwudiff_b200.unet.UNet2DFromScratch",

@@ -490,6 +490,33 @@ static int wmse_bwd_dispatch(const void* pred, const void* target, long long n_p
     return UWU_OK;
 }
 
+// Per-timestep validation statistics (PlotValLossPerTimestep.on_validation_batch_end, src/duwu/trainer/callbacks.py:75-92):
+// the reference loops over all N_t timesteps with boolean masks (3 N_t tiny kernels per batch); here one scatter-add.
+__global__ void timestep_hist_kernel(const float* __restrict__ losses, const long long* __restrict__ t_i64,
+                                     const float* __restrict__ t_f32, int B, int T, float* __restrict__ counts,
+                                     float* __restrict__ sums, float* __restrict__ sqsums) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    const long long t = t_i64 ? t_i64[i] : (long long)t_f32[i];  // `.long()` truncation of fractional (rectified-flow) timesteps
+    if (t < 0 || t >= T) return;                                  // the reference's masks never match out-of-range values
+    const float l = losses[i];
+    atomicAdd(&counts[t], 1.0f);
+    atomicAdd(&sums[t], l);
+    atomicAdd(&sqsums[t], l * l);
+}
+
+extern "C" int uwu_timestep_hist(const float* losses, const void* timesteps, int32_t t_dtype, int32_t B, int32_t T, float* counts,
+                                 float* sums, float* sqsums, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    UWU_CHECK_ARG(losses && timesteps && counts && sums && sqsums && B > 0 && T > 0, "uwu_timestep_hist: bad arguments");
+    UWU_CHECK_ARG(t_dtype == UWU_I64 || t_dtype == UWU_F32, "uwu_timestep_hist: timesteps must be int64 or fp32");
+    timestep_hist_kernel<<<(B + 127) / 128, 128, 0, stream>>>(losses, t_dtype == UWU_I64 ? reinterpret_cast<const long long*>(timesteps) : nullptr,
+                                                            t_dtype == UWU_F32 ? reinterpret_cast<const float*>(timesteps) : nullptr, B, T,
+                                                            counts, sums, sqsums);
+    UWU_CHECK_LAUNCH();
+    return UWU_OK;
+}
+
 extern "C" int uwu_wmse_bwd(const void* pred, int32_t pred_dtype, const void* target, int32_t target_dtype, int32_t B,
                             int64_t n_per, const float* w, const float* grad_scale_dev, float grad_scale, void* dpred,
                             int32_t dpred_dtype, void* stream_) {

@@ -196,6 +196,18 @@ def wmse_bwd(pred: torch.Tensor, target: torch.Tensor, w: Optional[torch.Tensor]
     return dpred
 
 
+def timestep_hist(losses: torch.Tensor, timesteps: torch.Tensor, counts: torch.Tensor, sums: torch.Tensor, sqsums: torch.Tensor):
+    """counts[t] += 1, sums[t] += loss, sqsums[t] += loss^2 per sample (accumulating into fp32 [N_t] buffers)."""
+    _req_cuda(losses, timesteps, counts, sums, sqsums)
+    losses = losses.detach().float().contiguous()
+    if timesteps.dtype != torch.int64:
+        timesteps = timesteps.float()
+    timesteps = timesteps.contiguous()
+    assert all(t.dtype == torch.float32 and t.is_contiguous() and t.numel() == counts.numel() for t in (counts, sums, sqsums))
+    check(lib().uwu_timestep_hist(_ptr(losses), _ptr(timesteps), 2 if timesteps.dtype == torch.int64 else 0, losses.numel(),
+                                  counts.numel(), _ptr(counts), _ptr(sums), _ptr(sqsums), _stream()), "uwu_timestep_hist")
+
+
 def pred_convert(out: torch.Tensor, x: Optional[torch.Tensor], sigma: torch.Tensor, t: torch.Tensor, acp: torch.Tensor,
                  pred_type: str, target_type: str, backward: bool = False) -> torch.Tensor:
     """Model output -> target space (get_prediction_for_training, src/duwu/loss/diffusion.py:133-139); backward=True maps
