@@ -268,6 +268,19 @@ def im2col3x3(x, N, H, W, C, stride=1):
     return cols.to(BF16)
 
 
+def conv_pack(W, ci_p, co_p, cod_p, fwd, dgrad):
+    """fwd[co, t*ci_p + ci] = W[co, ci, t]; dgrad[ci, t*cod_p + co] = W[co, ci, taps-1-t] (flipped kernel); zero padding."""
+    _launches[0] += 1
+    Co, Ci, kh, kw = W.shape
+    Wp = torch.zeros((co_p, kh, kw, ci_p), dtype=torch.float32)
+    Wp[:Co, :, :, :Ci] = W.permute(0, 2, 3, 1)
+    fwd.copy_(Wp.reshape(co_p, kh * kw * ci_p))
+    if dgrad is not None:
+        Wd = torch.zeros((Ci, kh, kw, cod_p), dtype=torch.float32)
+        Wd[:, :, :, :Co] = W.flip(2, 3).permute(1, 2, 3, 0)
+        dgrad.copy_(Wd.reshape(Ci, kh * kw * cod_p))
+
+
 def conv_wgrad_unpack(G, Co, Ci, Ci_pad, taps, wgrad, accumulate=True):
     """wgrad[co, ci, tap] (+)= G[co, tap * Ci_pad + ci]"""
     _launches[0] += 1
@@ -389,7 +402,7 @@ def launch_count():
 PATCHED = ["gemm", "conv3x3_nhwc", "attn_fwd", "attn_bwd", "groupnorm_fwd", "groupnorm_bwd", "layernorm_fwd", "layernorm_bwd",
            "geglu_fwd", "geglu_bwd", "elementwise", "nchw_to_nhwc", "nhwc_to_nchw", "upsample2x", "phase_split2", "colsum",
            "fold_lokr", "fold_lora", "axpy_f32", "lokr_grad", "lora_grad", "copy2d", "sincos_embed", "_workspace", "noise_fwd",
-           "wmse_fwd", "wmse_bwd", "launch_count", "_req_cuda", "im2col3x3", "conv_wgrad_unpack", "colsum_groups"]
+           "wmse_fwd", "wmse_bwd", "launch_count", "_req_cuda", "im2col3x3", "conv_wgrad_unpack", "colsum_groups", "conv_pack"]
 
 
 def install(monkeypatch):

@@ -207,16 +207,7 @@ class Conv2d(nn.Conv2d, _Cached):
             c.fwd = torch.empty((co_p, kh * kw * ci_p), device=W.device, dtype=BF16)
             c.dgrad = torch.empty((Ci, kh * kw * cod_p), device=W.device, dtype=BF16) if self.stride[0] == 1 else None
             c.bias = torch.zeros((co_p,), device=W.device, dtype=torch.float32) if self.bias is not None else None
-        if W.is_cuda:
-            ops.conv_pack(W.contiguous(), ci_p, co_p, cod_p, c.fwd, c.dgrad)   # one launch: both operands, padding included
-        else:  # host-logic tests (tests/fake_ops.py) run the same layout in torch
-            Wp = torch.zeros((co_p, kh, kw, ci_p), device=W.device, dtype=torch.float32)
-            Wp[:Co, :, :, :Ci] = W.permute(0, 2, 3, 1)
-            c.fwd.copy_(Wp.reshape(co_p, kh * kw * ci_p))
-            if c.dgrad is not None:
-                Wd = torch.zeros((Ci, kh, kw, cod_p), device=W.device, dtype=torch.float32)
-                Wd[:, :, :, :Co] = W.flip(2, 3).permute(1, 2, 3, 0)
-                c.dgrad.copy_(Wd.reshape(Ci, kh * kw * cod_p))
+        ops.conv_pack(W.contiguous(), ci_p, co_p, cod_p, c.fwd, c.dgrad)   # one launch: both operands, padding included
         if self.bias is not None:
             c.bias[:Co].copy_(self.bias.detach())
         if self.stride[0] != 1:
