@@ -382,3 +382,46 @@ def test_lycoris_weight_file_roundtrip_and_merge(fake_ops, tmp_path):
     with torch.no_grad():
         y3 = tr2.unet(x, t, encoder_hidden_states=ctx, added_cond_kwargs=ac)[0]
     assert rel(y3, y) < 2e-3   # same deltas, folded in fp32 into the master weights instead of into the bf16 operand
+
+
+def test_gradient_accumulation_equals_mean_of_micro_batch_gradients(fake_ops):
+    """accumulate_grad_batches = 2: the optimizer sees (g0 + g1) / 2 of the two micro-batches and steps once."""
+    from uwudiff_b200.data import DummyDataset
+    from uwudiff_b200.trainer import DMTrainer
+
+    def make(k):
+        torch.manual_seed(0)
+        tr = DMTrainer(
+            model_config={"unet": {"_target_": "duwu.modules.unet_patch.UNet2DFromScratch.from_config", "config": dict(U.tiny_config())},
+                          "te": {"_target_": "duwu.modules.text_encoders.ConcatTextEncoders", "hidden_dim": 128, "pooled_dim": 64},
+                          "vae": None},
+            lycoris_config={"preset": LYCORIS_PRESET, "config": LYCORIS_CFG}, lr=0.0, optimizer="torch.optim.SGD", opt_config={},
+            use_warm_up=False, lr_scheduler=None, device="cpu")
+        g = torch.Generator().manual_seed(1)
+        tr.lycoris_model.flat_params.copy_(torch.randn(tr.lycoris_model.flat_params.shape, generator=g) * 0.05)
+        fit = tr.setup_fit(seed=7, accumulate_grad_batches=k)
+        seen = []
+        orig = fit["opt"].step
+
+        def spy(*a, **kw):
+            seen.append(tr.lycoris_model.flat_grads.clone())
+            return orig(*a, **kw)
+
+        fit["opt"].step = spy
+        return tr, seen
+
+    torch.manual_seed(3)
+    ds = DummyDataset(sample_size=[4, 16, 16], n_samples=4)
+    b0, b1 = ds.collate([ds[0], ds[1]]), ds.collate([ds[2], ds[3]])
+    tr2, seen2 = make(2)
+    tr2.fit_step(b0, 0)
+    assert seen2 == [] and tr2.global_step == 0 and float(tr2.lycoris_model.flat_grads.abs().sum()) > 0   # no step yet
+    tr2.fit_step(b1, 1)
+    assert len(seen2) == 1 and tr2.global_step == 1 and float(tr2.lycoris_model.flat_grads.abs().sum()) == 0.0
+    tr1, seen1 = make(1)          # lr = 0: parameters do not move, the noise / timestep draws advance identically
+    tr1.fit_step(b0, 0)
+    tr1.fit_step(b1, 1)
+    assert len(seen1) == 2
+    ref = (seen1[0] + seen1[1]) / 2
+    assert torch.allclose(seen2[0], ref, rtol=1e-4, atol=1e-7 * float(ref.abs().max() + 1))
+    assert rel(seen2[0], ref) < 1e-4

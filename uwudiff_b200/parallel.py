@@ -60,6 +60,7 @@ class GradientBuckets:
         self._works = []
         self.unet.after_backward = self._on_blocks_done
         self.reduced_elems = 0
+        self.enabled = True  # False while a gradient-accumulation micro-batch other than the last is in backward
 
     def begin_step(self):
         self._ready = self.flat.numel()
@@ -68,6 +69,8 @@ class GradientBuckets:
         self.reduced_elems = 0
 
     def _on_blocks_done(self, mods):
+        if not self.enabled:
+            return
         for m in mods:
             s = self._block_start.get(id(m))
             if s is not None:

@@ -198,7 +198,11 @@ class DMTrainer(BaseTrainer):
 
     # ---- what Lightning's fit loop did around training_step -----------------------------------------------------
     def setup_fit(self, gradient_clip_val: Optional[float] = None, process_group=None, seed: Optional[int] = None,
-                  n_buckets: int = 4):
+                  n_buckets: int = 4, accumulate_grad_batches: int = 1):
+        """`accumulate_grad_batches` is Lightning's Trainer option of the same name (the `lightning_config` block of the YAMLs
+        is passed to pl.Trainer verbatim): k micro-batches share one optimizer step, each loss scaled by 1/k; the gradient
+        exchange runs once, during the last micro-batch's backward (BASELINE.json configs[4]: global batch 128 on fewer GPUs
+        = micro-batches of 16 per GPU)."""
         from .parallel import GradientBuckets
 
         opt = self.configure_optimizers(max_grad_norm=gradient_clip_val)
@@ -213,7 +217,7 @@ class DMTrainer(BaseTrainer):
         if seed is not None:
             rank = torch.distributed.get_rank() if (torch.distributed.is_available() and torch.distributed.is_initialized()) else 0
             self.loss.seed = int(seed) + rank  # pl.seed_everything(seed + global_rank), test_scripts/test_train.py:68-69
-        self._fit = dict(opt=opt, sched=sched, buckets=buckets)
+        self._fit = dict(opt=opt, sched=sched, buckets=buckets, accum=max(1, int(accumulate_grad_batches)), micro=0)
         return self._fit
 
     def fit_step(self, batch, idx: int = 0):
@@ -221,10 +225,17 @@ class DMTrainer(BaseTrainer):
         if self._fit is None:
             self.setup_fit()
         f = self._fit
+        k = f["accum"]
+        last = (f["micro"] + 1) % k == 0
         if f["buckets"] is not None:
-            f["buckets"].begin_step()
+            f["buckets"].enabled = last  # earlier micro-batches only accumulate locally
+            if last:
+                f["buckets"].begin_step()
         out = self.training_step(batch, idx)
-        out["loss"].backward()
+        (out["loss"] if k == 1 else out["loss"] / k).backward()
+        f["micro"] += 1
+        if not last:
+            return out
         if f["buckets"] is not None:
             f["buckets"].finish()
         f["opt"].step()
