@@ -15,7 +15,7 @@ import copy
 import functools
 import importlib
 from dataclasses import dataclass
-from typing import Any, Optional
+from typing import Optional
 
 import torch
 import torch.nn as nn

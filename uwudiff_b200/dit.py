@@ -19,7 +19,6 @@ sequences over token-major bf16 activations [B*T, D] with fp32 master weights.
 """
 from __future__ import annotations
 
-import math
 import types
 from typing import Optional
 

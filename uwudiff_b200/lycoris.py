@@ -373,8 +373,6 @@ class LycorisNetwork(nn.Module):
     def flush_grads(self):
         """Contract every pending G of the LoKr adapters into (dw1, dw2) in ONE launch (uwu_lokr_grad_batch).  Called by the
         denoiser's backward whenever a top-level block is finished (before its gradients are handed to the DDP buckets)."""
-        import ctypes as C
-
         from . import _lib
 
         pend = self._pending

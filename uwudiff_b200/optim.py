@@ -6,12 +6,10 @@ synchronisation.  State-dict layout (`state[p] = {step, exp_avg, exp_avg_sq}`) m
 """
 from __future__ import annotations
 
-import ctypes as C
 from typing import Iterable, Optional
 
 import torch
 
-from . import ops
 from ._lib import check, lib
 
 _CHUNK = 1 << 16

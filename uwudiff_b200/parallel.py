@@ -10,7 +10,7 @@ In LyCORIS mode only the ≈52.4 M adapter parameters are exchanged (≈210 MB f
 """
 from __future__ import annotations
 
-from typing import List, Optional
+from typing import List
 
 import torch
 import torch.distributed as dist

@@ -18,7 +18,6 @@ in the reference.  There is no CPU path: CPU tensors raise.
 from __future__ import annotations
 
 import json
-import math
 import os
 import types
 from typing import List, Optional
@@ -27,7 +26,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
-from ._lib import A_COL, B_KN, UwuError
+from ._lib import A_COL, B_KN
 
 BF16 = torch.bfloat16
 
