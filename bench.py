@@ -3,18 +3,20 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--batch B] [--latent S]
 
-Workload (config.workload): BASELINE.json configs[2]/[4] — SDXL UNet frozen + LyCORIS (LoKr on Attention/FeedForward,
-LoRA r4 on proj_in/out, norm deltas: configs/lycoris preset of the reference), 4x128x128 latents, batch 16 PER GPU,
-v-prediction + min-SNR loss, AdamW + grad-clip 1.0, data-parallel gradient all-reduce.  Weak scaling: 16 samples per GPU
-at every N (N=8 is the global-batch-128 configuration of configs[4]).  A "step" = noising -> UNet forward -> weighted
-MSE -> backward -> (all-reduce) -> clip + AdamW, through `DMTrainer.fit_step` (the public API).
+Workload (config.workload): BASELINE.json configs[4] (= configs[2] per micro-batch) — SDXL UNet frozen + LyCORIS (LoKr on
+Attention/FeedForward, LoRA r4 on proj_in/out, norm deltas: configs/lycoris preset of the reference), 4x128x128 latents,
+v-prediction + min-SNR loss, AdamW + grad-clip 1.0, data-parallel gradient all-reduce.  Default `--scaling strong`: the
+GLOBAL batch is fixed at 128 as configs[4] states; every GPU runs 128 / (16 N) micro-batches of 16 (configs[2]) with
+gradient accumulation and ONE gradient exchange + optimizer step per global batch.  `--scaling weak` keeps 16 samples per
+GPU per step at every N (round-1 behaviour).  A "step" = one optimizer step: (noising -> UNet forward -> weighted MSE ->
+backward) x micro-batches -> (all-reduce) -> clip + AdamW, through `DMTrainer.fit_step` (the public API).
 
   value : samples/s, inputs already resident in HBM, CUDA-event timed, max over ranks.
   e2e   : same step fed from pinned host memory every step (H2D inside the timed region) + a D2H read of the loss.
   roofline      : the dominant kernel (tcgen05 GEMM / implicit-GEMM conv): algorithmic FLOPs of every launch of one step
                   / their CUDA-event durations, against MEASURED_PEAKS.json bf16_tflops_sustained.
-  cpu_baseline  : the CPU oracle (PyTorch restatement of the diffusers/lycoris reference path) on the host cores, on a
-                  bounded sample (1 image at reduced latent size), scaled by the algorithmic-FLOP ratio.
+  cpu_baseline  : the CPU oracle (PyTorch restatement of the diffusers/lycoris reference path) on the host cores: ONE real
+                  training step of ONE image at the real 4x128x128 latent size (no extrapolation); samples/s = 1 / seconds.
 `--impl reference` times that CPU path alone (the reference's own stack — diffusers, lycoris, lightning — is not
 installable here), same metric/config/unit.
 """
@@ -115,21 +117,30 @@ class CpuOracleStep:
     """The reference path restated on CPU: oracle UNet (diffusers restatement) + oracle LyCORIS (kron forward patch) +
     the reference loss arithmetic + torch.optim.AdamW, under torch.autocast('cpu', bf16) to mirror `bf16-mixed`."""
 
-    def __init__(self):
+    def __init__(self, device: str = "cpu"):
+        """device="cuda" is used only by tools/bench_eager_cuda.py (the same oracle on the GPU's library kernels — cuDNN,
+        cuBLASLt, SDPA — as the same-box comparator); bench.py itself only ever builds it on the CPU."""
         import torch
 
         from oracle import diffusers_shim, loss_oracle, lycoris_oracle, unet_oracle
 
         self.torch = torch
+        self.device = device
         torch.set_num_threads(os.cpu_count() or 1)
         self.cores = torch.get_num_threads()
         with torch.device("meta"):
             unet = unet_oracle.UNet2DConditionModel()
-        unet = unet.to_empty(device="cpu")
+        unet = unet.to_empty(device=device)
+        # timing only: every weight is filled from one pseudo-random block (U(-0.02, 0.02)) tiled over the tensor, which
+        # takes seconds instead of the minute a 2.57 B-element generator pass takes; norm scales 1, biases 0
         g = torch.Generator().manual_seed(0)
+        block = torch.empty(1 << 22).uniform_(-0.02, 0.02, generator=g).to(device)
         for p in unet.parameters():
             if p.dim() > 1:
-                p.data.uniform_(-0.02, 0.02, generator=g)
+                flat = p.data.view(-1)
+                for o in range(0, flat.numel(), block.numel()):
+                    n = min(block.numel(), flat.numel() - o)
+                    flat[o:o + n] = block[:n]
             else:
                 p.data.zero_()
         for m in unet.modules():
@@ -140,8 +151,12 @@ class CpuOracleStep:
         self.net.apply_to()
         unet.requires_grad_(False)
         self.unet = unet
+        if device != "cpu":
+            self.net.to(device)
         sch = diffusers_shim.EulerDiscreteScheduler.from_pretrained("x", prediction_type="v_prediction")
         self.tab = loss_oracle.scheduler_tables(sch)
+        if device != "cpu":
+            self.tab = loss_oracle.Tables(*(t.to(device) for t in self.tab))
         self.loss_oracle = loss_oracle
         self.opt = torch.optim.AdamW(self.net.parameters(), lr=1e-6, weight_decay=0.01, betas=(0.9, 0.999))
         self.cfg = unet_oracle.SDXL_UNET_CONFIG
@@ -155,8 +170,11 @@ class CpuOracleStep:
         ctx = torch.randn((batch, 77, 2048), generator=g)
         ac = dict(text_embeds=torch.randn((batch, 1280), generator=g),
                   time_ids=torch.tensor([[1024., 1024, 0, 0, 1024, 1024]] * batch))
+        if self.device != "cpu":
+            x0, eps, t, ctx = (v.to(self.device) for v in (x0, eps, t, ctx))
+            ac = {k: v.to(self.device) for k, v in ac.items()}
         t0 = time.time()
-        with torch.autocast("cpu", dtype=torch.bfloat16):
+        with torch.autocast(self.device, dtype=torch.bfloat16):
             loss, _ = self.loss_oracle.diffusion_loss(x0, eps, t, self.unet, self.tab, target_type="v_prediction",
                                                       prediction_type="v_prediction", use_snr_weight=True,
                                                       encoder_hidden_states=ctx, added_cond_kwargs=ac)
@@ -166,57 +184,62 @@ class CpuOracleStep:
         self.opt.zero_grad()
         return time.time() - t0
 
-    def scaled_samples_per_s(self, seconds: float, batch: int, latent: int, target_latent: int) -> float:
-        from uwudiff_b200.flops import unet_forward_flops
 
-        f_s = unet_forward_flops(self.cfg, latent, latent)["total"]
-        f_t = unet_forward_flops(self.cfg, target_latent, target_latent)["total"]
-        return (batch / seconds) * (f_s / f_t)
-
-
-def cpu_sample_choice(oracle: CpuOracleStep, budget_s: float, n_steps: int):
-    """Warm up at 32x32 latents, then pick the largest latent size whose n_steps fit the budget."""
-    t32 = oracle.step(1, 32)
-    t32 = oracle.step(1, 32)
-    from uwudiff_b200.flops import unet_forward_flops
-
-    r = unet_forward_flops(oracle.cfg, 64, 64)["total"] / unet_forward_flops(oracle.cfg, 32, 32)["total"]
-    latent = 64 if t32 * r * n_steps <= budget_s else 32
-    return latent, t32
+CPU_SAMPLE = ("one real training step per timed step on ONE image of the workload (B=1 of the micro-batch of 16) at the real "
+              "4x{S}x{S} latent size: full SDXL UNet + LyCORIS oracle, noising + fwd + bwd + clip + AdamW under "
+              "torch.autocast(cpu, bf16); samples/s = 1 / seconds per step, no extrapolation")
 
 
 def run_reference(args):
+    """`--impl reference`: the reference's training step on the host cores (the CPU oracle port: diffusers / lycoris /
+    lightning are not installable), all host threads, at the real latent size.  One timed step = one image."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     oracle = CpuOracleStep()
-    latent, _ = cpu_sample_choice(oracle, 150.0, args.steps + args.warmup)
-    for _ in range(args.warmup):
-        oracle.step(1, latent)
-    ts = [oracle.step(1, latent) for _ in range(args.steps)]
+    executed_warmup = min(args.warmup, 1)  # a CPU step has no clocks / caches to warm beyond the first call (~30 s each)
+    for _ in range(executed_warmup):
+        oracle.step(1, args.latent)
+    ts = [oracle.step(1, args.latent) for _ in range(args.steps)]
     sec = sum(ts) / len(ts)
-    v = oracle.scaled_samples_per_s(sec, 1, latent, args.latent)
-    sample = (f"1 image at {latent}x{latent} latents per step (full SDXL UNet + LyCORIS, fwd+bwd+clip+AdamW, autocast bf16), "
-              f"scaled by algorithmic forward FLOPs {latent}^2 -> {args.latent}^2")
+    v = 1.0 / sec
+    cfg = workload_config(args, 1)
+    cfg["sample_per_step"] = "1 image (B=1) at the full latent size"
     line = {
         "impl": "reference", "metric": "train_samples_per_s", "value": v, "unit": "samples/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": workload_config(args, 1),
-        "cpu_baseline": {"value": v, "unit": "samples/s", "cores": oracle.cores, "kind": "port", "sample": sample},
+        "steps": args.steps, "warmup": args.warmup, "warmup_executed": executed_warmup, "ms_per_step": sec * 1e3,
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": cfg,
+        "cpu_baseline": {"value": v, "unit": "samples/s", "cores": oracle.cores, "kind": "port",
+                         "sample": CPU_SAMPLE.format(S=args.latent)},
         "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
 
 
+def micro_batches(args, world):
+    """configs[4]: global batch 128 = world x micro-batches x 16 (strong scaling); weak scaling: one micro-batch per step."""
+    if args.scaling == "weak":
+        return 1
+    per_step = args.batch * world
+    if args.global_batch % per_step != 0:
+        raise SystemExit(f"bench.py: global batch {args.global_batch} is not a multiple of {args.batch} x {world} GPUs")
+    return args.global_batch // per_step
+
+
 def workload_config(args, world):
+    k = micro_batches(args, world)
     return {"workload": "SDXL UNet (2.57 B params, frozen) + LyCORIS LoKr/LoRA/norm adapters (52.4 M trainable), "
-                        f"4x{args.latent}x{args.latent} latents, batch {args.batch} per GPU, v-pred min-SNR, AdamW + clip 1.0 "
-                        "[BASELINE.json configs[2]; at 8 GPUs = configs[4] global batch 128]",
-            "global_batch": args.batch * world, "per_gpu_batch": args.batch, "latent": [4, args.latent, args.latent],
-            "parallelism": f"dp{world}", "l2": "working set >> L2 (~100 GB of activations per step), no flush needed",
-            "gradient_checkpointing": False}
+                        f"4x{args.latent}x{args.latent} latents, v-pred min-SNR, AdamW + clip 1.0; global batch "
+                        f"{args.batch * world * k} = {world} GPU(s) x {k} micro-batch(es) of {args.batch} "
+                        "[BASELINE.json configs[4]; each micro-batch is configs[2]]",
+            "global_batch": args.batch * world * k, "per_gpu_batch": args.batch * k, "micro_batch": args.batch,
+            "accumulate_grad_batches": k, "gradient_exchanges_per_step": 1 if world > 1 else 0,
+            "latent": [4, args.latent, args.latent],
+            "parallelism": f"dp{world}", "l2": "working set >> L2 (~100 GB of activations per micro-batch), no flush needed",
+            "gradient_checkpointing": False,
+            "conditioning": "synthetic text-encoder outputs (explicit opt-in: no pretrained CLIP weights offline), vae: null"}
 
 
 # ======================================================================================================
@@ -244,8 +267,11 @@ def run_gpu(args):
     torch.manual_seed(1215 + rank)
 
     conf = trainer_config(args.latent, args.batch)
+    ucfg.use_synthetic_conditioning(True)  # text-encoder outputs are synthetic tensors of the real shape (no weights offline)
     trainer = ucfg.instantiate_any(conf["trainer"])
-    trainer.setup_fit(gradient_clip_val=conf["lightning_config"]["gradient_clip_val"], seed=conf["seed"])
+    K = micro_batches(args, world)
+    trainer.setup_fit(gradient_clip_val=conf["lightning_config"]["gradient_clip_val"], seed=conf["seed"],
+                      accumulate_grad_batches=K)
     B, S = args.batch, args.latent
     host_x = torch.randn((B, 4, S, S)).pin_memory()
     host_ids = torch.tensor([[1024., 1024, 0, 0, 1024, 1024]] * B).pin_memory()
@@ -267,7 +293,8 @@ def run_gpu(args):
         e0.record()
         last = None
         for i in range(n):
-            out = trainer.fit_step(batch_fn(), i)
+            for _ in range(K):  # K micro-batches -> one optimizer step (the last one carries the gradient exchange)
+                out = trainer.fit_step(batch_fn(), i)
             if read_loss:
                 last = out["loss"].item()
             else:
@@ -288,7 +315,8 @@ def run_gpu(args):
 
     note(f"trainer ready (world {world})")
     for i in range(max(args.warmup, 3)):
-        trainer.fit_step(dev_batch, i)
+        for _ in range(K):
+            trainer.fit_step(dev_batch, i)
     barrier()
     note("warm-up done")
     clocks = ClockSampler(local) if rank == 0 else None
@@ -314,7 +342,8 @@ def run_gpu(args):
 
         ops.gemm = timed_gemm
         try:
-            trainer.fit_step(dev_batch, 0)
+            for _ in range(K):
+                trainer.fit_step(dev_batch, 0)
             torch.cuda.synchronize()
         finally:
             ops.gemm = real_gemm
@@ -324,17 +353,22 @@ def run_gpu(args):
         pk, pk_src = peaks()
         achieved = fl / (t_ms * 1e-3) / 1e12
         peak = pk["bf16_tflops_sustained"]
-        fwd = unet_forward_flops(SDXL_UNET_CONFIG, S, S)["total"] * B
+        fwd = unet_forward_flops(SDXL_UNET_CONFIG, S, S)["total"] * B * K
+        # `traffic` is NOT measured by this run: it is the DRAM byte count of one representative launch from the committed
+        # `ncu --set full` capture of the build named in the file (a static property of the kernel, labelled as such)
         traffic, traffic_note = None, None
-        try:  # DRAM bytes of the representative launch (GEGLU projection, M16384 N10240 K1280) from the committed ncu capture
-            with open(os.path.join(ROOT, "profiles", "r01_ncu_full_summary.json")) as f:
-                g0 = json.load(f)["gemm"][0]
-            traffic = (g0["dram_read_mb"] + g0["dram_write_mb"]) * 1e6
-            traffic_note = ("ncu --set full, one launch of M16384 N10240 K1280 (the largest Linear class): "
-                            f"{g0['dram_read_mb']:.0f} MB read + {g0['dram_write_mb']:.0f} MB written vs 403 MB algorithmic "
-                            f"(A 42 + B 26 + out 335), tensor pipe {g0['tensor_pct']:.1f}% active, {g0['time_us']:.0f} us")
-        except Exception:
-            pass
+        for fn in ("r02_ncu_full_summary.json", "r01_ncu_full_summary.json"):
+            try:
+                with open(os.path.join(ROOT, "profiles", fn)) as f:
+                    g0 = json.load(f)["gemm"][0]
+                traffic = (g0["dram_read_mb"] + g0["dram_write_mb"]) * 1e6
+                traffic_note = (f"STATIC, from profiles/{fn} (ncu --set full of an earlier run, one launch of "
+                                f"{g0.get('shape', 'M16384 N10240 K1280')}): {g0['dram_read_mb']:.0f} MB read + "
+                                f"{g0['dram_write_mb']:.0f} MB written vs 403 MB algorithmic (A 42 + B 26 + out 335), "
+                                f"tensor pipe {g0['tensor_pct']:.1f}% active, {g0['time_us']:.0f} us")
+                break
+            except Exception:
+                continue
         roof = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (Linear + implicit-GEMM conv, fwd/dgrad/adapter-wgrad)",
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
                 "traffic_note": traffic_note,
@@ -349,23 +383,20 @@ def run_gpu(args):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
             oracle = CpuOracleStep()
-            latent, _ = cpu_sample_choice(oracle, 25.0, 1)
-            sec = oracle.step(1, latent)
-            cpu = {"value": oracle.scaled_samples_per_s(sec, 1, latent, S), "unit": "samples/s", "cores": oracle.cores,
-                   "kind": "port",
-                   "sample": f"1 image at {latent}x{latent} latents (full SDXL UNet + LyCORIS oracle, fwd+bwd+clip+AdamW, autocast "
-                             f"bf16; {sec:.1f} s), scaled by algorithmic forward FLOPs {latent}^2 -> {S}^2"}
+            sec = oracle.step(1, S)
+            cpu = {"value": 1.0 / sec, "unit": "samples/s", "cores": oracle.cores, "kind": "port",
+                   "sample": CPU_SAMPLE.format(S=S) + f"; one un-warmed step, {sec:.1f} s"}
         except Exception as e:  # the baseline is informational; never lose the GPU line to it
             cpu = {"value": None, "unit": "samples/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e!r}"}
 
     if rank == 0:
         h2d = host_x.numel() * 4 + host_ids.numel() * 4
         line = {
-            "metric": "train_samples_per_s", "value": B * world / (ms_dev * 1e-3), "unit": "samples/s", "n_gpus": world,
+            "metric": "train_samples_per_s", "value": B * K * world / (ms_dev * 1e-3), "unit": "samples/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_dev, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": workload_config(args, world), "per_gpu": B / (ms_dev * 1e-3), "clocks": clk,
-            "e2e": {"value": B * world / (ms_e2e * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": h2d,
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": workload_config(args, world), "per_gpu": B * K / (ms_dev * 1e-3), "clocks": clk,
+            "e2e": {"value": B * K * world / (ms_e2e * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": h2d * K,
                     "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e},
             "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu,
             "loss": float(loss_host) if loss_host is not None else None,
@@ -384,6 +415,9 @@ def main():
     ap.add_argument("--batch", type=int, default=16, help="samples per GPU")
     ap.add_argument("--latent", type=int, default=128)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="strong: global batch fixed (configs[4]), gradient accumulation on fewer GPUs; weak: --batch per GPU")
+    ap.add_argument("--global-batch", type=int, default=128)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -38,6 +38,8 @@ extern "C" {
 /* loss-weight flags (src/duwu/loss/diffusion.py:141-167) */
 #define UWU_WEIGHT_MIN_SNR 1
 #define UWU_WEIGHT_DEBIASED 2
+#define UWU_WEIGHT_EDM 4 /* lambda(sigma) = (sigma^2 + sigma_data^2) / (sigma * sigma_data)^2 in the first weight row (north_star a;
+                            Karras et al. 2022 — the reference ships no EDM weighting, this is an additive mode) */
 
 const char* uwu_last_error(void);
 int uwu_version(void);
@@ -131,6 +133,9 @@ typedef struct uwu_noise_desc {
     int32_t temb_dim;
     const float* sigma_in; /* optional fp32 [B]: per-sample sigma used instead of sigma_t[t] (RectifiedFlowLoss "uniform_time"
                               sampling, src/duwu/loss/rectified_flow.py:27-45,63-71) */
+    float sigma_data;      /* UWU_WEIGHT_EDM: sigma_data (0.5 in the EDM paper) */
+    const uint64_t* step_dev; /* optional device counter ADDED to `offset` when the kernel runs: a launch captured in a CUDA graph
+                                 keeps drawing fresh noise / timesteps on every replay */
 } uwu_noise_desc;
 
 int uwu_noise_fwd(const uwu_noise_desc* desc, void* stream);

@@ -135,6 +135,49 @@ def main():
         out[f"{name}/losses"] = aux.losses.numpy()
         out[f"{name}/loss"] = np.float32(loss.item())
         out[f"{name}/meta"] = np.array([sampling, ptype, str(int(paired)), str(int(rescale))])
+    # NNWeightedRFLoss (rectified_flow.py:144-203) run verbatim with a PARAMETRIC stand-in denoiser (out = a * x_t) and a
+    # one-parameter loss head: records the loss and the gradients the reference sends to BOTH (the rescaled rf loss must
+    # reach the denoiser, the log-loss regression the head)
+    class Den(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.a = torch.nn.Parameter(torch.tensor(0.5))
+
+        def forward(self, x, t, **kw):
+            return (self.a * x,)
+
+    class Head(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.w = torch.nn.Parameter(torch.tensor(0.3))
+
+        def forward(self, x_t, sigmas, **kw):
+            return self.w * torch.log1p(sigmas) - 0.5
+
+    for j, ptype in enumerate(["rectified_flow", "epsilon"]):
+        name = f"nnw_{ptype}"
+        sch = diffusers_shim.EulerDiscreteScheduler.from_pretrained("x", prediction_type=ptype)
+        den, head = Den(), Head()
+        L = rf.NNWeightedRFLoss(loss_pred_module=head, scheduler=sch, prediction_type=ptype)
+        g = torch.Generator().manual_seed(7000 + j)
+        x_in = torch.randn((4, 4, 8, 8), generator=g)
+        torch.manual_seed(8000 + j)
+        loss, aux = L(x_in, den)
+        loss.backward()
+        torch.manual_seed(8000 + j)
+        noises = torch.randn_like(x_in)
+        smax = sch.sigmas[0]
+        time = torch.rand(4) * (smax / (1 + smax))
+        out[f"{name}/x_in"] = x_in.numpy()
+        out[f"{name}/noise"] = noises.numpy()
+        out[f"{name}/time"] = time.numpy()
+        out[f"{name}/loss"] = np.float32(loss.item())
+        out[f"{name}/losses"] = aux.losses.detach().numpy()
+        out[f"{name}/rescaled_losses"] = aux.rescaled_losses.detach().numpy()
+        out[f"{name}/pred_losses"] = aux.pred_losses.detach().numpy()
+        out[f"{name}/loss_pred_losses"] = aux.loss_pred_losses.detach().numpy()
+        out[f"{name}/grad_denoiser"] = np.float32(den.a.grad.item())
+        out[f"{name}/grad_head"] = np.float32(head.w.grad.item())
     # unsupported target type -> ValueError in the reference (:98)
     np.savez_compressed(OUT, **out)
     print("wrote", OUT, os.path.getsize(OUT), "bytes;", len(CASES), "cases")

@@ -12,6 +12,18 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+@pytest.fixture(autouse=True)
+def _synthetic_conditioning():
+    """No pretrained CLIP / VAE weights exist offline: trainer configs in the tests resolve `ConcatTextEncoders` /
+    `AutoencoderKL` to the synthetic stand-ins (explicit opt-in, uwudiff_b200/config.py); the kernel-backed text towers and
+    VAE encoder are tested directly in tests/test_conditioning_gpu.py."""
+    from uwudiff_b200 import config
+
+    prev = config.use_synthetic_conditioning(True)
+    yield
+    config.use_synthetic_conditioning(prev)
+
+
 @pytest.fixture(scope="session")
 def golden():
     import numpy as np

@@ -33,9 +33,12 @@ def main():
     from conftest import LYCORIS_CFG, LYCORIS_PRESET
     from oracle import unet_oracle as U
     from uwudiff_b200.data import DummyDataset
+    from uwudiff_b200 import config as ucfg
     from uwudiff_b200.trainer import DMTrainer
 
-    torch.manual_seed(0)  # identical replicas on every rank
+    ucfg.use_synthetic_conditioning(True)  # no pretrained text-encoder weights offline (explicit opt-in)
+
+    torch.manual_seed(40 + rank)  # DIFFERENT initial weights per rank: GradientBuckets must broadcast rank 0's replica
     cfgd = U.tiny_config()
     tr = DMTrainer(
         model_config={"unet": {"_target_": "duwu.modules.unet_patch.UNet2DFromScratch.from_config", "config": dict(cfgd)},
@@ -48,8 +51,8 @@ def main():
                                    "pretrained_model_name_or_path": "stabilityai/stable-diffusion-xl-base-1.0",
                                    "subfolder": "scheduler"}},
         device="cpu")
-    if mode == "lycoris":  # non-trivial adapter state so every gradient is non-zero
-        g = torch.Generator().manual_seed(1)
+    if mode == "lycoris":  # non-trivial adapter state so every gradient is non-zero (per-rank, overwritten by the broadcast)
+        g = torch.Generator().manual_seed(1 + rank)
         tr.lycoris_model.flat_params.copy_(torch.randn(tr.lycoris_model.flat_params.shape, generator=g) * 0.05)
     fit = tr.setup_fit(gradient_clip_val=None, seed=1215, n_buckets=3)
     buckets = fit["buckets"]
@@ -57,6 +60,7 @@ def main():
     assert tr.loss.seed == 1215 + rank  # pl.seed_everything(seed + global_rank), test_scripts/test_train.py:68-69
     params = list(tr.lycoris_model.parameters()) if mode == "lycoris" else [p for p in tr.unet.parameters() if p.requires_grad]
     before = torch.cat([p.detach().reshape(-1).clone() for p in params])
+    frozen = torch.cat([p.detach().reshape(-1)[:64].clone() for p in tr.unet.parameters()])  # frozen base synced as well
     torch.manual_seed(100 + rank)  # different data per rank
     ds = DummyDataset(sample_size=[4, 16, 16], n_samples=2)
     batch = ds.collate([ds[0], ds[1]])
@@ -73,6 +77,11 @@ def main():
     buckets._reduce = spy
     out = tr.fit_step(batch, 0)
     after = torch.cat([p.detach().reshape(-1).clone() for p in params])
+    ds2 = DummyDataset(sample_size=[4, 16, 16], n_samples=2)
+    for i in range(2):  # two more steps on different data per rank: replicas must stay identical
+        buckets._reduce = orig_reduce
+        tr.fit_step(ds2.collate([ds2[0], ds2[1]]), i + 1)
+    after3 = torch.cat([p.detach().reshape(-1).clone() for p in params])
     flat0 = buckets.flat.data_ptr()
     local = torch.zeros_like(buckets.flat)
     reduced = torch.zeros_like(buckets.flat)
@@ -82,7 +91,7 @@ def main():
         reduced[off:off + red.numel()] = red
     torch.save({"loss": float(out["loss"]), "before": before, "after": after, "local": local, "reduced": reduced,
                 "n_calls": len(seen["local"]), "reduced_elems": buckets.reduced_elems, "n": buckets.flat.numel(),
-                "t": out["aux_output"].timesteps.clone()}, out_path)
+                "t": out["aux_output"].timesteps.clone(), "frozen": frozen, "after3": after3}, out_path)
     dist.barrier()
     dist.destroy_process_group()
 

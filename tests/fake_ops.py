@@ -352,7 +352,7 @@ def _workspace(nfloats, device, tag="ws"):
 
 
 def noise_fwd(x0, tables, *, target_type, pred_type, use_snr_weight, use_debiased, gamma, eps=None, timesteps=None, seed=0,
-              offset=0, temb_dim=0, want_eps=True):
+              offset=0, temb_dim=0, want_eps=True, sigmas=None, edm_sigma_data=0.0, step_dev=None):
     _launches[0] += 1
     from oracle import loss_oracle, philox
 
@@ -364,10 +364,17 @@ def noise_fwd(x0, tables, *, target_type, pred_type, use_snr_weight, use_debiase
     if eps is None:
         eps = torch.from_numpy(philox.normals(B, n_per, seed, offset)).reshape(x0.shape).to(x0.dtype)
     tab = loss_oracle.Tables(tables["acp"], tables["sigma_t"], tables["snr"])
+    if sigmas is not None:  # rectified-flow time sampling: sigmas given, timesteps are placeholders
+        sg = sigmas.to(x0).view(-1, *([1] * (x0.dim() - 1)))
+        x_t = (x0 + eps.to(x0.dtype) * sg) * (1 / (sg ** 2 + 1) ** 0.5)
+        tgt = loss_oracle.target(x0, eps.to(x0.dtype), timesteps, tab, target_type)
+        return x_t, tgt, (eps if want_eps else None), timesteps, sigmas.float(), torch.ones((2, B)), None
     x_t = loss_oracle.noisy_latents(x0, eps.to(x0.dtype), timesteps, tab)
     tgt = loss_oracle.target(x0, eps.to(x0.dtype), timesteps, tab, target_type)
     w = loss_oracle.loss_weights(timesteps, tab, use_snr_weight=use_snr_weight, use_debiased=use_debiased, gamma=gamma,
                                  prediction_type=pred_type)
+    if edm_sigma_data > 0:
+        w = loss_oracle.edm_weight(timesteps, tab, edm_sigma_data)
     temb = sincos_embed(timesteps, temb_dim) if temb_dim else None
     return x_t, tgt, (eps if want_eps else None), timesteps, tab.sigma_t[timesteps], w, temb
 
@@ -391,6 +398,27 @@ def wmse_bwd(pred, target, w, grad=None, grad_scale=1.0, out_dtype=torch.float32
     return ((pred.float() - target.float()) * coef.view(-1, *([1] * (pred.dim() - 1)))).to(out_dtype)
 
 
+def pred_convert(out, x, sigma, t, acp, pred_type, target_type, backward=False):
+    """uwu_pred_convert: pred = A_b * out + C_b * x (get_prediction_for_training); backward maps d(pred) -> d(out) = A_b * g.
+    The per-sample coefficients are read off the oracle's conversion by probing it with (1, 0) and (0, 1)."""
+    _launches[0] += 1
+    from oracle import loss_oracle
+
+    B = out.shape[0]
+    tab = loss_oracle.Tables(acp, None, None)
+    one, zero = torch.ones((B, 1)), torch.zeros((B, 1))
+
+    def conv(o, xx):
+        x0, eps = loss_oracle.x0_eps_from_pred(xx, o, sigma.float(), pred_type)
+        return loss_oracle.target(x0, eps, t, tab, target_type)
+
+    A, Cc = conv(one, zero), conv(zero, one)
+    shape = (B,) + (1,) * (out.dim() - 1)
+    if backward:
+        return out.float() * A.view(shape)
+    return out.float() * A.view(shape) + x.float() * Cc.view(shape)
+
+
 def _req_cuda(*ts):
     pass
 
@@ -402,7 +430,7 @@ def launch_count():
 PATCHED = ["gemm", "conv3x3_nhwc", "attn_fwd", "attn_bwd", "groupnorm_fwd", "groupnorm_bwd", "layernorm_fwd", "layernorm_bwd",
            "geglu_fwd", "geglu_bwd", "elementwise", "nchw_to_nhwc", "nhwc_to_nchw", "upsample2x", "phase_split2", "colsum",
            "fold_lokr", "fold_lora", "axpy_f32", "lokr_grad", "lora_grad", "copy2d", "sincos_embed", "_workspace", "noise_fwd",
-           "wmse_fwd", "wmse_bwd", "launch_count", "_req_cuda", "im2col3x3", "conv_wgrad_unpack", "colsum_groups", "conv_pack"]
+           "wmse_fwd", "wmse_bwd", "pred_convert", "launch_count", "_req_cuda", "im2col3x3", "conv_wgrad_unpack", "colsum_groups", "conv_pack"]
 
 
 def install(monkeypatch):

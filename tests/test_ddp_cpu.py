@@ -46,6 +46,8 @@ def test_two_rank_gloo_step(tmp_path, mode, port):
     mean = (r0["local"] + r1["local"]) / 2
     assert torch.allclose(r0["reduced"], mean, rtol=1e-6, atol=1e-9)
     assert torch.equal(r0["reduced"], r1["reduced"])
-    # replicas start identical, move, and stay identical
-    assert torch.equal(r0["before"], r1["before"])
+    # replicas start identical although every rank seeded its model differently (rank 0's state is broadcast: trainable,
+    # frozen and adapter tensors), move, and stay identical over several steps
+    assert torch.equal(r0["before"], r1["before"]) and torch.equal(r0["frozen"], r1["frozen"])
+    assert torch.equal(r0["after3"], r1["after3"]) and not torch.equal(r0["after3"], r0["after"])
     assert torch.equal(r0["after"], r1["after"]) and not torch.equal(r0["after"], r0["before"])

@@ -425,3 +425,83 @@ def test_gradient_accumulation_equals_mean_of_micro_batch_gradients(fake_ops):
     ref = (seen1[0] + seen1[1]) / 2
     assert torch.allclose(seen2[0], ref, rtol=1e-4, atol=1e-7 * float(ref.abs().max() + 1))
     assert rel(seen2[0], ref) < 1e-4
+
+
+@pytest.mark.parametrize("ptype", ["rectified_flow", "epsilon"])
+def test_nn_weighted_rf_loss_sends_gradient_to_the_denoiser(fake_ops, golden, ptype):
+    """Host logic of NNWeightedRFLoss against the reference run verbatim (oracle/make_golden.py): the rescaled loss
+    reaches the denoiser's parameters, the log-loss regression the head."""
+    import numpy as np
+
+    from uwudiff_b200.loss import NNWeightedRFLoss
+    from uwudiff_b200.scheduler import EulerDiscreteScheduler
+
+    name = f"nnw_{ptype}"
+    sch = EulerDiscreteScheduler.from_pretrained("stabilityai/stable-diffusion-xl-base-1.0", subfolder="scheduler",
+                                                 prediction_type=ptype)
+
+    class Den(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.a = torch.nn.Parameter(torch.tensor(0.5))
+
+        def forward(self, x, t, **kw):
+            return (self.a * x,)
+
+    class Head(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.w = torch.nn.Parameter(torch.tensor(0.3))
+
+        def forward(self, x_t, sigmas, **kw):
+            return self.w * torch.log1p(sigmas) - 0.5
+
+    den, head = Den(), Head()
+    L = NNWeightedRFLoss(loss_pred_module=head, scheduler=sch, prediction_type=ptype)
+    loss, aux = L(torch.from_numpy(golden[f"{name}/x_in"]), den, noise=torch.from_numpy(golden[f"{name}/noise"]),
+                  time=torch.from_numpy(golden[f"{name}/time"]))
+    loss.backward()
+    np.testing.assert_allclose(aux.losses.detach().numpy(), golden[f"{name}/losses"], rtol=1e-4)
+    np.testing.assert_allclose(aux.rescaled_losses.detach().numpy(), golden[f"{name}/rescaled_losses"], rtol=1e-4)
+    assert abs(loss.item() - float(golden[f"{name}/loss"])) <= 1e-4 * abs(float(golden[f"{name}/loss"]))
+    assert den.a.grad is not None
+    assert abs(den.a.grad.item() - float(golden[f"{name}/grad_denoiser"])) <= 1e-3 * abs(float(golden[f"{name}/grad_denoiser"]))
+    assert abs(head.w.grad.item() - float(golden[f"{name}/grad_head"])) <= 1e-3 * abs(float(golden[f"{name}/grad_head"]))
+
+
+def test_gradual_warmup_ramp_matches_the_reference_scheduler_step_for_step():
+    """`GradualWarmupScheduler(opt, 1, N, after)` (trainer.py:62-65; ildoonet/pytorch-gradual-warmup-lr): the first optimizer
+    step runs at lr 0, step k at base * k / N, step N at base, step N + 1 at the after-scheduler's initial lr, then the
+    after-scheduler advances one epoch per step.  Also: state_dict round trip resumes the ramp."""
+    from uwudiff_b200.trainer import GradualWarmup
+
+    def make():
+        p = torch.nn.Parameter(torch.zeros(1))
+        opt = torch.optim.SGD([p], lr=1.0)
+        after = torch.optim.lr_scheduler.CosineAnnealingLR(opt, T_max=10, eta_min=0.0)
+        return opt, after, GradualWarmup(opt, 4, after)
+
+    opt, after, sch = make()
+    used = []
+    for _ in range(9):
+        used.append(opt.param_groups[0]["lr"])
+        opt.step()
+        sch.step()
+    import math
+
+    cos = [0.5 * (1 + math.cos(math.pi * e / 10)) for e in range(4)]
+    expect = [0.0, 0.25, 0.5, 0.75, 1.0, cos[0], cos[1], cos[2], cos[3]]
+    assert all(abs(a - b) < 1e-7 for a, b in zip(used, expect)), (used, expect)
+    # resume in the middle of the ramp and after the hand-over
+    for n_before in (2, 7):
+        opt, after, sch = make()
+        for _ in range(n_before):
+            opt.step()
+            sch.step()
+        sd = sch.state_dict()
+        opt2, after2, sch2 = make()
+        sch2.load_state_dict(sd)
+        assert abs(opt2.param_groups[0]["lr"] - expect[n_before]) < 1e-7
+        opt2.step()
+        sch2.step()
+        assert abs(opt2.param_groups[0]["lr"] - expect[n_before + 1]) < 1e-7

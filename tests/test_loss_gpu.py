@@ -156,6 +156,48 @@ def test_nn_weighted_rf_loss_matches_reference_formula(golden):
     assert head.w.grad is not None and torch.isfinite(head.w.grad)
 
 
+@pytest.mark.parametrize("ptype", ["rectified_flow", "epsilon"])
+def test_nn_weighted_rf_loss_gradients_match_reference_golden(golden, ptype):
+    """The reference's NNWeightedRFLoss run verbatim (oracle/make_golden.py) with a parametric denoiser out = a * x_t: the
+    rescaled rectified-flow loss must send its gradient to the DENOISER (rf_losses / pred_loss.detach()), the log-loss
+    regression to the head — both against the reference's own autograd values."""
+    from uwudiff_b200.loss import NNWeightedRFLoss
+    from uwudiff_b200.scheduler import EulerDiscreteScheduler
+
+    name = f"nnw_{ptype}"
+    sch = EulerDiscreteScheduler.from_pretrained("stabilityai/stable-diffusion-xl-base-1.0", subfolder="scheduler",
+                                                 prediction_type=ptype)
+
+    class Den(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.a = torch.nn.Parameter(torch.tensor(0.5))
+
+        def forward(self, x, t, **kw):
+            return (self.a * x,)
+
+    class Head(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.w = torch.nn.Parameter(torch.tensor(0.3))
+
+        def forward(self, x_t, sigmas, **kw):
+            return self.w * torch.log1p(sigmas) - 0.5
+
+    den, head = Den().cuda(), Head().cuda()
+    L = NNWeightedRFLoss(loss_pred_module=head, scheduler=sch, prediction_type=ptype)
+    loss, aux = L(torch.from_numpy(golden[f"{name}/x_in"]).cuda(), den, noise=torch.from_numpy(golden[f"{name}/noise"]).cuda(),
+                  time=torch.from_numpy(golden[f"{name}/time"]).cuda())
+    loss.backward()
+    for key, got in (("losses", aux.losses), ("rescaled_losses", aux.rescaled_losses), ("pred_losses", aux.pred_losses),
+                     ("loss_pred_losses", aux.loss_pred_losses)):
+        np.testing.assert_allclose(got.detach().float().cpu().numpy(), golden[f"{name}/{key}"], rtol=1e-3, err_msg=key)
+    assert abs(loss.item() - float(golden[f"{name}/loss"])) <= 3e-4 * abs(float(golden[f"{name}/loss"]))
+    assert den.a.grad is not None, "the denoiser got no gradient"
+    assert abs(den.a.grad.item() - float(golden[f"{name}/grad_denoiser"])) <= 2e-3 * abs(float(golden[f"{name}/grad_denoiser"]))
+    assert abs(head.w.grad.item() - float(golden[f"{name}/grad_head"])) <= 2e-3 * abs(float(golden[f"{name}/grad_head"]))
+
+
 def test_rectified_flow_loss_through_the_unet():
     """Fractional timesteps reach the denoiser's sinusoidal embedding; loss is finite and gradients flow to the adapters."""
     from conftest import LYCORIS_CFG, LYCORIS_PRESET
@@ -345,3 +387,54 @@ def test_timestep_histogram_matches_reference_loop():
     rstd = torch.sqrt(torch.clamp(ref[2][valid] / ref[0][valid] - (ref[1][valid] / ref[0][valid]) ** 2, min=0))
     assert torch.allclose(std.cpu().double(), rstd, rtol=1e-3, atol=1e-4)
 
+
+
+def test_edm_loss_weight_matches_oracle_for_all_timesteps():
+    """north_star (a): the EDM loss weight from the noising kernel, all 1000 timesteps, bit-exact against the fp32 oracle
+    formula; and through DiffusionLoss(use_edm_weight=True) on x0-prediction."""
+    from oracle import diffusers_shim, loss_oracle
+    from uwudiff_b200 import ops
+    from uwudiff_b200.loss import DiffusionLoss
+    from uwudiff_b200.scheduler import EulerDiscreteScheduler
+
+    sch = EulerDiscreteScheduler.from_pretrained("stabilityai/stable-diffusion-xl-base-1.0", subfolder="scheduler",
+                                                 prediction_type="sample")
+    L = DiffusionLoss(sch, use_edm_weight=True, edm_sigma_data=0.5)
+    T = 1000
+    t = torch.arange(T)
+    x0 = torch.randn(T, 4, 4, 4, device="cuda")
+    tab = L._device_tables(x0.device)
+    *_, w, _temb = ops.noise_fwd(x0, tab, target_type="sample", pred_type="sample", use_snr_weight=False, use_debiased=False,
+                                 gamma=5.0, timesteps=t.cuda(), seed=3, edm_sigma_data=0.5)
+    tab_o = loss_oracle.scheduler_tables(diffusers_shim.EulerDiscreteScheduler.from_pretrained("x", prediction_type="sample"))
+    w_o = loss_oracle.edm_weight(t, tab_o, 0.5)
+    assert torch.equal(w.cpu(), w_o), (w.cpu() - w_o).abs().max()
+    # end to end: loss = mean_b(lambda_b * mse_b) with injected noise / timesteps
+    tt = torch.tensor([5, 300, 650, 990])
+    x, eps = torch.randn(4, 4, 8, 8), torch.randn(4, 4, 8, 8)
+    loss, aux = L(x.cuda(), lambda z, ts, **k: (0.25 * z,), noise=eps.cuda(), timesteps=tt.cuda())
+    xt = loss_oracle.noisy_latents(x, eps, tt, tab_o)
+    mse = ((0.25 * xt - x) ** 2).flatten(1).mean(1)
+    ref = (loss_oracle.edm_weight(tt, tab_o, 0.5)[0] * mse).mean()
+    assert abs(loss.item() - ref.item()) <= 1e-5 * abs(ref.item())
+    with pytest.raises(AssertionError):
+        DiffusionLoss(EulerDiscreteScheduler.from_pretrained("stabilityai/stable-diffusion-xl-base-1.0", subfolder="scheduler"),
+                      use_edm_weight=True)(x.cuda(), lambda z, ts, **k: (z,))
+
+
+def test_noise_kernel_device_step_counter_advances_the_stream():
+    """A launch with `step_dev` (CUDA-graph replay) draws exactly what an eager launch with offset + *step_dev draws."""
+    from uwudiff_b200 import ops
+    from uwudiff_b200.loss import DiffusionLoss
+    from uwudiff_b200.scheduler import EulerDiscreteScheduler
+
+    sch = EulerDiscreteScheduler.from_pretrained("stabilityai/stable-diffusion-xl-base-1.0", subfolder="scheduler")
+    tab = DiffusionLoss(sch)._device_tables(torch.device("cuda"))
+    x0 = torch.randn(3, 4, 8, 8, device="cuda")
+    kw = dict(target_type="epsilon", pred_type="epsilon", use_snr_weight=False, use_debiased=False, gamma=5.0, seed=11)
+    ctr = torch.tensor([7], device="cuda", dtype=torch.int64)
+    a = ops.noise_fwd(x0, tab, offset=2, step_dev=ctr, **kw)
+    b = ops.noise_fwd(x0, tab, offset=9, **kw)
+    c = ops.noise_fwd(x0, tab, offset=2, **kw)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[3], b[3]) and torch.equal(a[2], b[2])
+    assert not torch.equal(a[2], c[2])

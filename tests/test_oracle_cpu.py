@@ -164,3 +164,19 @@ def test_sinusoidal_embedding_shape_and_values():
     assert e.shape == (3, 320)
     assert torch.allclose(e[0, :160], torch.ones(160)) and torch.allclose(e[0, 160:], torch.zeros(160))
     assert abs(e[1, 0].item() - np.cos(10.0)) < 1e-6 and abs(e[1, 160].item() - np.sin(10.0)) < 1e-6
+
+
+def test_edm_weight_known_answers():
+    """lambda(sigma) = (sigma^2 + sd^2) / (sigma sd)^2: equals 2 / sd^2 at sigma = sd, -> 1 / sd^2 for sigma -> inf,
+    ~ 1 / sigma^2 for sigma -> 0 (Karras et al. 2022, Table 1)."""
+    import torch
+
+    from oracle import loss_oracle
+
+    sig = torch.tensor([0.5, 1e4, 1e-3], dtype=torch.float32)
+    tab = loss_oracle.Tables(None, sig, None)
+    w = loss_oracle.edm_weight(torch.arange(3), tab, 0.5)
+    assert w.shape == (2, 3) and torch.equal(w[1], torch.ones(3))
+    assert abs(w[0, 0].item() - 8.0) < 1e-5
+    assert abs(w[0, 1].item() - 4.0) < 1e-4
+    assert abs(w[0, 2].item() * 1e-6 - 1.0) < 1e-4

@@ -227,7 +227,7 @@ def test_training_step_loss_and_update_match_oracle(ttype, snr, deb):
     assert torch.equal(aux_p.timesteps.cpu(), t)
     assert torch.equal(aux_p.noisy_latent.cpu(), aux_o["noisy_latent"]), "x_t must be bit-exact in fp32"
     assert torch.equal(aux_p.target.cpu(), aux_o["target"]), "target must be bit-exact in fp32"
-    assert abs(loss_p.item() - loss_o.item()) / abs(loss_o.item()) < 1e-2
+    assert abs(loss_p.item() - loss_o.item()) / abs(loss_o.item()) < 1e-3  # north_star: step loss within 1e-3 relative
     # gradient direction before the optimizer touches anything
     po = dict(no.named_parameters())
     gp = torch.cat([q.grad.detach().flatten().cpu() for _, q in npd.named_parameters()])
@@ -360,7 +360,7 @@ def test_c1_pixel_unet_full_training_step_matches_oracle():
     loss_p, aux_p = L(x0.cuda(), p, noise=eps.cuda(), timesteps=t.cuda(), **cuda_kwargs(ctx, ac))
     loss_p.backward()
     assert torch.equal(aux_p.noisy_latent.cpu(), aux_o["noisy_latent"]) and torch.equal(aux_p.target.cpu(), aux_o["target"])
-    assert abs(loss_p.item() - loss_o.item()) / abs(loss_o.item()) < 1e-2
+    assert abs(loss_p.item() - loss_o.item()) / abs(loss_o.item()) < 1e-3  # north_star: step loss within 1e-3 relative
     po = dict(o.named_parameters())
     gp = torch.cat([q.grad.flatten().cpu() for _, q in p.named_parameters()])
     go = torch.cat([po[n].grad.flatten() for n, _ in p.named_parameters()])
@@ -423,3 +423,52 @@ def test_dmtrainer_fit_step_runs_and_learns():
     assert all(l == l and l > 0 for l in losses)
     assert (after - before).abs().max().item() > 0
     assert ops.launch_count() - n0 > 300
+
+
+def test_merge_lycoris_through_the_fold_kernels_and_weight_file_roundtrip(tmp_path):
+    """§8 f3 on the GPU: `merge_lycoris()` (restore + merge_to, trainer.py:184-187) bakes kron(w1, w2) / up·down / norm deltas
+    into the fp32 masters; the merged, adapter-free model must reproduce the adapted model's output (both go through the
+    bf16 operand kernels), and the `lycoris_weight/epoch=N.pt` file must reload into a fresh wrapper bit-exactly."""
+    from uwudiff_b200 import config as ucfg
+    from uwudiff_b200 import lycoris as PL
+
+    cfg = U.tiny_config()
+    conf = {
+        "_target_": "duwu.trainer.DMTrainer", "_recursive_": False, "lr": 1e-3, "optimizer": "torch.optim.AdamW",
+        "opt_config": {"weight_decay": 0.01, "betas": [0.9, 0.999]}, "use_warm_up": False,
+        "lycoris_config": {"config": LYCORIS_CFG, "preset": LYCORIS_PRESET},
+        "model_config": {"unet": {"_target_": "duwu.modules.unet_patch.UNet2DFromScratch.from_config", "config": cfg},
+                         "te": {"_target_": "duwu.modules.text_encoders.ConcatTextEncoders", "hidden_dim": 128,
+                                "pooled_dim": 64, "_load_config_": {"to_freeze": True}},
+                         "vae": None},
+    }
+    torch.manual_seed(3)
+    tr = ucfg.instantiate_any(conf)
+    g = torch.Generator(device="cuda").manual_seed(1)
+    tr.lycoris_model.flat_params.copy_(torch.randn(tr.lycoris_model.flat_params.shape, device="cuda", generator=g) * 0.05)
+    B = 2
+    x = torch.randn(B, 4, 16, 16, device="cuda")
+    t = torch.tensor([10, 900], device="cuda")
+    kw = dict(encoder_hidden_states=torch.randn(B, 77, cfg["cross_attention_dim"], device="cuda"),
+              added_cond_kwargs=dict(text_embeds=torch.randn(B, 64, device="cuda"),
+                                     time_ids=torch.tensor([[1024., 1024, 0, 0, 1024, 1024]] * B, device="cuda")))
+    path = tr.save_lycoris_weight(str(tmp_path), epoch=3)
+    with torch.no_grad():
+        y_adapted = tr.unet(x, t, **kw)[0].clone()
+    sd = torch.load(path)
+    assert set(sd) == set(tr.lycoris_model.state_dict()), "file = lycoris state dict (no trainable unet params under LyCORIS)"
+    w_before = tr.unet.mid_block.attentions[0].transformer_blocks[0].attn1.to_q.weight.detach().clone()
+    tr.merge_lycoris()
+    assert getattr(tr.unet, "_uwu_lycoris", None) is None
+    assert not torch.equal(w_before, tr.unet.mid_block.attentions[0].transformer_blocks[0].attn1.to_q.weight)
+    with torch.no_grad():
+        y_merged = tr.unet(x, t, **kw)[0]
+    # W + dW is summed in fp32 by both routes before the bf16 rounding of the operand: identical up to one bf16 ulp flip
+    assert rel(y_merged, y_adapted) < 2e-3, rel(y_merged, y_adapted)
+    # a fresh wrapper over a fresh copy of the ORIGINAL base + the saved file reproduces the adapted output bit-exactly
+    torch.manual_seed(3)
+    tr2 = ucfg.instantiate_any(conf)
+    tr2.lycoris_model.load_state_dict(sd)
+    with torch.no_grad():
+        y_reloaded = tr2.unet(x, t, **kw)[0]
+    assert torch.equal(y_reloaded, y_adapted)

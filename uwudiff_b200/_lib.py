@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libuwu_b200.so")
 
 UWU_F32, UWU_BF16 = 0, 1
 TARGET_CODES = {"epsilon": 0, "v_prediction": 1, "sample": 2, "rectified_flow": 3}
-WEIGHT_MIN_SNR, WEIGHT_DEBIASED = 1, 2
+WEIGHT_MIN_SNR, WEIGHT_DEBIASED, WEIGHT_EDM = 1, 2, 4
 A_ROW, A_COL, A_CONV = 0, 1, 2
 B_NK, B_KN = 0, 1
 
@@ -53,6 +53,7 @@ class NoiseDesc(C.Structure):
         ("x_t", C.c_void_p), ("target", C.c_void_p), ("eps_out", C.c_void_p),
         ("t_out", C.c_void_p), ("sigma_out", C.c_void_p), ("w_out", C.c_void_p),
         ("temb_out", C.c_void_p), ("temb_dim", C.c_int32), ("sigma_in", C.c_void_p),
+        ("sigma_data", C.c_float), ("step_dev", C.c_void_p),
     ]
 
 

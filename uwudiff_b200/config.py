@@ -14,6 +14,8 @@ from __future__ import annotations
 import copy
 import functools
 import importlib
+import os
+import warnings
 from dataclasses import dataclass
 from typing import Optional
 
@@ -30,17 +32,42 @@ TARGET_ALIASES = {
     "duwu.data.TrainDataModule": "uwudiff_b200.data.TrainDataModule",
     "duwu.data.DummyDataset": "uwudiff_b200.data.DummyDataset",
     "duwu.modules.unet_patch.UNet2DFromScratch": "uwudiff_b200.unet.UNet2DFromScratch",
-    "duwu.modules.text_encoders.ConcatTextEncoders": "uwudiff_b200.data.SyntheticTextEncoders",
+    "duwu.modules.text_encoders.ConcatTextEncoders": "uwudiff_b200.text_encoders.ConcatTextEncoders",
+    "duwu.trainer.nn_weighted_loss_trainer.NNWeightedLossTrainer": "uwudiff_b200.trainer.NNWeightedLossTrainer",
     "diffusers.EulerDiscreteScheduler": "uwudiff_b200.scheduler.EulerDiscreteScheduler",
-    "diffusers.AutoencoderKL": "uwudiff_b200.data.SyntheticVAE",
+    "diffusers.AutoencoderKL": "uwudiff_b200.vae.AutoencoderKL",
     "torch.optim.AdamW": "uwudiff_b200.optim.FusedAdamW",
     "lycoris.LycorisNetwork": "uwudiff_b200.lycoris.LycorisNetwork",
     "lycoris.create_lycoris": "uwudiff_b200.lycoris.create_lycoris",
 }
 
 
+# Frozen conditioning stack: the kernel-backed CLIP text towers / VAE encoder are the default.  Their synthetic stand-ins
+# (constant embeddings / pooled pixels, uwudiff_b200/data.py) replace them ONLY behind this explicit opt-in — bench.py and
+# the tests set it because no pretrained weights exist offline; a real YAML never trains on them silently.
+SYNTHETIC_ALIASES = {
+    "duwu.modules.text_encoders.ConcatTextEncoders": "uwudiff_b200.data.SyntheticTextEncoders",
+    "diffusers.AutoencoderKL": "uwudiff_b200.data.SyntheticVAE",
+}
+_synthetic = [os.environ.get("UWU_SYNTHETIC_CONDITIONING", "0") == "1"]
+
+
+def use_synthetic_conditioning(flag: bool = True) -> bool:
+    """Opt in to (or out of) the synthetic text-encoder / VAE stand-ins; returns the previous setting."""
+    prev = _synthetic[0]
+    _synthetic[0] = bool(flag)
+    return prev
+
+
 def get_obj_from_str(string: str):
     """Resolve `pkg.mod.Class[.method]`, longest importable module prefix first (Hydra's `_locate` behaviour)."""
+    if _synthetic[0]:
+        for ref, ours in SYNTHETIC_ALIASES.items():
+            if string == ref or string.startswith(ref + "."):
+                warnings.warn(f"uwudiff_b200: '{ref}' resolved to the SYNTHETIC stand-in {ours} (UWU_SYNTHETIC_CONDITIONING)",
+                              stacklevel=2)
+                string = ours + string[len(ref):]
+                break
     for ref, ours in TARGET_ALIASES.items():
         if string == ref or string.startswith(ref + "."):
             string = ours + string[len(ref):]

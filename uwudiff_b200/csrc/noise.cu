@@ -109,6 +109,8 @@ struct NoiseArgs {
     int pred_type;
     int weight_flags;
     float gamma;
+    float sigma_data;        // EDM weighting
+    const uint64_t* step_dev;  // optional device counter added to `offset` (CUDA-graph replay)
     void* x_t;
     void* target;
     void* eps_out;           // optional
@@ -126,7 +128,8 @@ struct NoiseArgs {
 template <typename T>
 __global__ void __launch_bounds__(256) noise_fwd_kernel(const NoiseArgs a) {
     const int b = blockIdx.y;
-    const int t = a.t_in ? (int)a.t_in[b] : sample_timestep(b, a.T, a.seed, a.offset);
+    const uint64_t offset = a.offset + (a.step_dev ? *a.step_dev : 0ull);
+    const int t = a.t_in ? (int)a.t_in[b] : sample_timestep(b, a.T, a.seed, offset);
     const float sigma = IO<T>::rnd(a.sigma_in ? a.sigma_in[b] : a.sigma_t[t]);        // sigmas.to(ref_params)
     const float sig2p1 = IO<T>::rnd(__fadd_rn(IO<T>::rnd(__fmul_rn(sigma, sigma)), 1.0f));
     const float scale = IO<T>::rnd(__fdiv_rn(1.0f, IO<T>::rnd(__fsqrt_rn(sig2p1))));  // 1 / (sigma**2 + 1) ** 0.5
@@ -146,6 +149,11 @@ __global__ void __launch_bounds__(256) noise_fwd_kernel(const NoiseArgs a) {
                 w1 = (a.pred_type == UWU_TARGET_V) ? __fdiv_rn(m, __fadd_rn(snr, 1.0f)) : __fdiv_rn(m, snr);
             }
             if (a.weight_flags & UWU_WEIGHT_DEBIASED) w2 = __fdiv_rn(1.0f, __fsqrt_rn(fminf(snr, 1000.0f)));
+            if (a.weight_flags & UWU_WEIGHT_EDM) {
+                // Karras et al. 2022 (EDM) lambda(sigma) = (sigma^2 + sigma_data^2) / (sigma * sigma_data)^2
+                const float sd = a.sigma_data, sp = __fmul_rn(sigma, sd);
+                w1 = __fdiv_rn(__fadd_rn(__fmul_rn(sigma, sigma), __fmul_rn(sd, sd)), __fmul_rn(sp, sp));
+            }
             a.w_out[b] = w1;
             a.w_out[a.B + b] = w2;
         }
@@ -186,7 +194,7 @@ __global__ void __launch_bounds__(256) noise_fwd_kernel(const NoiseArgs a) {
             }
         } else {
             // group index over the flattened batch so that every element has its own counter
-            normal4((uint64_t)b * (uint64_t)ngroups + (uint64_t)g, a.seed, a.offset, e);
+            normal4((uint64_t)b * (uint64_t)ngroups + (uint64_t)g, a.seed, offset, e);
 #pragma unroll
             for (int j = 0; j < 4; ++j) e[j] = IO<T>::rnd(e[j]);
         }
@@ -399,6 +407,9 @@ extern "C" int uwu_noise_fwd(const uwu_noise_desc* d, void* stream_) {
     a.x0 = d->x0; a.eps_in = d->eps_in; a.t_in = d->t_in; a.sigma_in = d->sigma_in; a.seed = d->seed; a.offset = d->offset;
     a.acp = d->acp; a.sigma_t = d->sigma_t; a.snr = d->snr; a.T = d->T; a.B = d->B; a.n_per = d->n_per;
     a.target_type = d->target_type; a.pred_type = d->pred_type; a.weight_flags = d->weight_flags; a.gamma = d->gamma;
+    a.sigma_data = d->sigma_data; a.step_dev = d->step_dev;
+    UWU_CHECK_ARG(!(d->weight_flags & UWU_WEIGHT_EDM) || (d->sigma_data > 0.f && !(d->weight_flags & UWU_WEIGHT_MIN_SNR)),
+                  "uwu_noise_fwd: EDM weighting needs sigma_data > 0 and excludes min-SNR weighting");
     a.x_t = d->x_t; a.target = d->target; a.eps_out = d->eps_out; a.t_out = d->t_out; a.sigma_out = d->sigma_out;
     a.w_out = d->w_out; a.temb_out = reinterpret_cast<__nv_bfloat16*>(d->temb_out); a.temb_dim = d->temb_dim;
     const size_t esz = d->dtype == UWU_F32 ? 4 : 2;

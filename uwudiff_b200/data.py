@@ -1,4 +1,7 @@
-"""Batch contract of the reference (src/duwu/data/base.py:12-95): `DummyDataset` (pre-generated `torch.randn(sample_size)`
+"""The reference's batch contract, kept AS IS: `UwUBaseDataset.collate`, `DummyDataset` and `TrainDataModule` below are a
+near-verbatim mirror of src/duwu/data/base.py:9-95 (about 45 lines: the 5-tuple layout, the caption / `add_time_ids`
+constants and the method names are the drop-in API itself and leave nothing to redesign; they are off the hot path).
+`DummyDataset` (pre-generated `torch.randn(sample_size)`
 samples, fixed caption, fixed `add_time_ids`), `collate` -> the 5-tuple `(samples, captions, tokenizer_outputs,
 {"time_ids": ...}, {})` that `DMTrainer.get_latent_and_conditioning` unpacks (src/duwu/trainer/trainer.py:233-261),
 and `TrainDataModule`.  Lightning is not installable here, so `TrainDataModule` is a plain object with the same methods.

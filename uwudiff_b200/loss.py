@@ -56,13 +56,18 @@ class _PredConvert(torch.autograd.Function):
 class DiffusionLoss(nn.Module):
     def __init__(self, scheduler, use_snr_weight: bool = False, min_snr_gamma: float = 5.0,
                  use_debiased_estimation: bool = False, prediction_type: Optional[str] = None,
-                 target_type: Optional[str] = None, loss: Optional[nn.Module] = None):
+                 target_type: Optional[str] = None, loss: Optional[nn.Module] = None, use_edm_weight: bool = False,
+                 edm_sigma_data: float = 0.5):
+        """`use_edm_weight` / `edm_sigma_data` are additive (the reference has no EDM weighting): per-sample weight
+        lambda(sigma) = (sigma^2 + sigma_data^2) / (sigma * sigma_data)^2 of Karras et al. 2022, emitted by the noising kernel
+        like the min-SNR factor; defined for x0 ("sample") prediction."""
         super().__init__()
         self.scheduler = scheduler
         self.prepare_scheduler_for_custom_training()
         self.use_snr_weight = use_snr_weight
         self.min_snr_gamma = min_snr_gamma
         self.use_debiased_estimation = use_debiased_estimation
+        self.use_edm_weight, self.edm_sigma_data = use_edm_weight, float(edm_sigma_data)
         self.prediction_type = prediction_type or self.scheduler.config.prediction_type
         self.target_type = target_type or self.scheduler.config.prediction_type
         if loss is not None and not (isinstance(loss, nn.MSELoss) and loss.reduction == "none"):
@@ -112,12 +117,15 @@ class DiffusionLoss(nn.Module):
             assert self.prediction_type in ["epsilon", "v_prediction"]
         if self.use_debiased_estimation:
             assert self.prediction_type == self.target_type == "epsilon"
+        if self.use_edm_weight:
+            assert self.prediction_type == self.target_type == "sample" and not self.use_snr_weight
         tab = self._device_tables(x.device)
         x_t, target, _eps, t, _sigma, w, temb = ops.noise_fwd(
             x, tab, target_type=self.target_type, pred_type=self.prediction_type,
             use_snr_weight=self.use_snr_weight, use_debiased=self.use_debiased_estimation, gamma=self.min_snr_gamma,
             eps=noise, timesteps=timesteps, seed=self.seed, offset=self._step, temb_dim=self.temb_dim,
-            want_eps=False)
+            want_eps=False, edm_sigma_data=self.edm_sigma_data if self.use_edm_weight else 0.0,
+            step_dev=getattr(self, "_step_dev", None))
         self._step += 1
         if temb is not None:
             unet_kwargs = dict(unet_kwargs, _fused_temb=temb)
@@ -127,7 +135,7 @@ class DiffusionLoss(nn.Module):
         else:
             # :138-139 (with the reference's argument quirk: the CLEAN latents are passed as `xt`, :177)
             pred = _PredConvert.apply(model_output, x, _sigma, t, tab["acp"], self.prediction_type, self.target_type)
-        weighted = self.use_snr_weight or self.use_debiased_estimation
+        weighted = self.use_snr_weight or self.use_debiased_estimation or self.use_edm_weight
         loss, losses = _WeightedMSE.apply(pred, target, w if weighted else None)
         aux = DiffusionLossAuxOutput(losses=losses, timesteps=t, pred=pred, target=target, noisy_latent=x_t)
         return loss, aux
@@ -191,8 +199,8 @@ class RectifiedFlowLoss(DiffusionLoss):
         t = (1 - w) * low_idx + w * high_idx
         return t.view(sigmas.shape)
 
-    def forward(self, x: torch.Tensor, unet: nn.Module, *, noise: Optional[torch.Tensor] = None,
-                time: Optional[torch.Tensor] = None, timesteps: Optional[torch.Tensor] = None, **unet_kwargs):
+    def _predict(self, x, unet, noise, time, timesteps, unet_kwargs):
+        """Noising + denoiser + conversion to the rectified-flow target space: (pred, target, x_t, timesteps, sigma)."""
         x, noise = self.get_x0_and_noises(x, noise)
         tab = self._device_tables(x.device)
         if timesteps is None:
@@ -216,6 +224,11 @@ class RectifiedFlowLoss(DiffusionLoss):
         model_output = unet(x_t, t_unet, **unet_kwargs)[0]
         # pred = pred_eps - pred_x0 with (x0, eps) recovered from the NOISY latents (rectified_flow.py:79-83)
         pred = _PredConvert.apply(model_output, x_t, sigma, t_idx, tab["acp"], self.prediction_type, "rectified_flow")
+        return pred, target, x_t, t_unet, sigma
+
+    def forward(self, x: torch.Tensor, unet: nn.Module, *, noise: Optional[torch.Tensor] = None,
+                time: Optional[torch.Tensor] = None, timesteps: Optional[torch.Tensor] = None, **unet_kwargs):
+        pred, target, x_t, t_unet, _sigma = self._predict(x, unet, noise, time, timesteps, unet_kwargs)
         loss, losses = _WeightedMSE.apply(pred, target, None)
         aux = DiffusionLossAuxOutput(losses=losses, timesteps=t_unet, pred=pred, target=target, noisy_latent=x_t)
         return loss, aux
@@ -236,7 +249,8 @@ class NNWeightedRFLoss(RectifiedFlowLoss):
     """Drop-in for `duwu.loss.NNWeightedRFLoss` (src/duwu/loss/rectified_flow.py:144-203): the rectified-flow loss of each
     sample is divided by a learned prediction of itself (`loss_pred_module(noisy_latent, sigmas, **unet_kwargs)` returns the
     log-loss), plus the squared log-error of that prediction.  The heavy part (noising, denoiser, conversion, per-sample MSE)
-    runs in the same kernels as RectifiedFlowLoss; the per-sample weighting is B-element host-side torch arithmetic."""
+    runs in the same kernels as RectifiedFlowLoss; the 1 / predicted-loss weighting goes through the fused weighted-MSE kernel
+    (its backward carries it to the denoiser), the log-loss regression is B-element torch arithmetic on the device."""
 
     def __init__(self, loss_pred_module: nn.Module, **kwargs):
         super().__init__(**kwargs)
@@ -244,16 +258,20 @@ class NNWeightedRFLoss(RectifiedFlowLoss):
 
     def forward(self, x: torch.Tensor, unet: nn.Module, *, noise: Optional[torch.Tensor] = None,
                 time: Optional[torch.Tensor] = None, timesteps: Optional[torch.Tensor] = None, **unet_kwargs):
-        _, aux = super().forward(x, unet, noise=noise, time=time, timesteps=timesteps, **unet_kwargs)
-        rf_losses = aux.losses
-        sigmas = self._last_sigmas
-        log_ls_pred = self.loss_pred_module(aux.noisy_latent, sigmas.flatten(), **unet_kwargs).flatten()
-        log_ls = rf_losses.detach().log()
+        pred, target, x_t, t_unet, sigmas = self._predict(x, unet, noise, time, timesteps, unet_kwargs)
+        # per-sample rectified-flow losses, detached: they only feed the log-loss regression target (:184)
+        with torch.no_grad():
+            _, rf_losses = ops.wmse_fwd(pred.detach(), target, None)
+        log_ls_pred = self.loss_pred_module(x_t, sigmas.flatten(), **unet_kwargs).flatten()
+        log_ls = rf_losses.log()
         ls_pred_loss = (log_ls - log_ls_pred).square()
         pred_loss = log_ls_pred.detach().exp().clamp(min=1e-4)
-        rescaled_losses = rf_losses / pred_loss
-        losses = rescaled_losses + ls_pred_loss
+        # mean_b(rf_losses_b / pred_loss_b) through the fused kernel, so that d/d(pred) reaches the denoiser (:190-191):
+        # the weight rows are (1 / pred_loss, 1)
+        w = torch.stack([1.0 / pred_loss.float(), torch.ones_like(pred_loss, dtype=torch.float32)]).contiguous()
+        rescaled_mean, rescaled_losses = _WeightedMSE.apply(pred, target, w)
+        loss = rescaled_mean + ls_pred_loss.mean()
         out = NNWeightedRFLossAuxOutput(losses=rf_losses, rescaled_losses=rescaled_losses, pred_losses=pred_loss,
-                                        loss_pred_losses=ls_pred_loss, timesteps=aux.timesteps, pred=aux.pred, target=aux.target,
-                                        noisy_latent=aux.noisy_latent)
-        return losses.mean(), out
+                                        loss_pred_losses=ls_pred_loss, timesteps=t_unet, pred=pred, target=target,
+                                        noisy_latent=x_t)
+        return loss, out

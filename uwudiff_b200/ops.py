@@ -115,7 +115,8 @@ def conv3x3_nhwc(x: torch.Tensor, w_packed: torch.Tensor, *, x2: Optional[torch.
 def noise_fwd(x0: torch.Tensor, tables: dict, *, target_type: str, pred_type: str, use_snr_weight: bool,
               use_debiased: bool, gamma: float, eps: Optional[torch.Tensor] = None,
               timesteps: Optional[torch.Tensor] = None, seed: int = 0, offset: int = 0, temb_dim: int = 0,
-              want_eps: bool = True, sigmas: Optional[torch.Tensor] = None):
+              want_eps: bool = True, sigmas: Optional[torch.Tensor] = None, edm_sigma_data: float = 0.0,
+              step_dev: Optional[torch.Tensor] = None):
     """One launch: (x_t, target, eps, t, sigma, w[2,B], temb). See uwu_noise_fwd."""
     _req_cuda(x0, eps, timesteps)
     if target_type not in _lib.TARGET_CODES:
@@ -150,7 +151,12 @@ def noise_fwd(x0: torch.Tensor, tables: dict, *, target_type: str, pred_type: st
     d.dtype = _DT[x0.dtype]
     d.target_type = _lib.TARGET_CODES[target_type]
     d.pred_type = _lib.TARGET_CODES.get(pred_type, 0)
-    d.weight_flags = (_lib.WEIGHT_MIN_SNR if use_snr_weight else 0) | (_lib.WEIGHT_DEBIASED if use_debiased else 0)
+    d.weight_flags = (_lib.WEIGHT_MIN_SNR if use_snr_weight else 0) | (_lib.WEIGHT_DEBIASED if use_debiased else 0) | \
+                     (_lib.WEIGHT_EDM if edm_sigma_data > 0 else 0)
+    d.sigma_data = float(edm_sigma_data)
+    if step_dev is not None:
+        assert step_dev.dtype == torch.int64 and step_dev.is_cuda and step_dev.numel() == 1
+        d.step_dev = _ptr(step_dev)
     d.gamma = gamma
     d.x_t, d.target, d.eps_out = _ptr(x_t), _ptr(target), _ptr(eps_out)
     d.t_out, d.sigma_out, d.w_out = _ptr(t_out), _ptr(sigma), _ptr(w)

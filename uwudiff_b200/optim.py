@@ -17,9 +17,13 @@ _CHUNK = 1 << 16
 
 class FusedAdamW(torch.optim.Optimizer):
     def __init__(self, params: Iterable, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 1e-2,
-                 amsgrad: bool = False, *, max_grad_norm: Optional[float] = None, **unused):
-        if amsgrad:
-            raise NotImplementedError("FusedAdamW: amsgrad is not built")
+                 amsgrad: bool = False, *, max_grad_norm: Optional[float] = None, maximize: bool = False,
+                 foreach: Optional[bool] = None, capturable: bool = False, differentiable: bool = False,
+                 fused: Optional[bool] = None):
+        # torch.optim.AdamW's keyword set; the ones that only select an ATen code path are accepted, the ones that change the
+        # update rule are refused instead of ignored
+        if amsgrad or maximize or differentiable:
+            raise NotImplementedError("FusedAdamW: amsgrad / maximize / differentiable are not built")
         defaults = dict(lr=lr, betas=tuple(betas), eps=eps, weight_decay=weight_decay)
         super().__init__(params, defaults)
         self.max_grad_norm = max_grad_norm
@@ -63,6 +67,22 @@ class FusedAdamW(torch.optim.Optimizer):
             ))
         self._tables = groups
         self._norm_out = torch.ones((2,), dtype=torch.float32, device=groups[0]["device"]) if groups else None
+        # the clip coefficient is global (Lightning clips the norm over ALL optimizer parameters): one norm table over
+        # every group
+        self._norm_table = groups[0] if len(groups) == 1 else None
+        if len(groups) > 1:
+            dev = groups[0]["device"]
+            ps = [p for g in groups for p in g["params"]]
+            chunk_t, chunk_i = [], []
+            for ti, p in enumerate(ps):
+                n = (p.numel() + _CHUNK - 1) // _CHUNK
+                chunk_t += [ti] * n
+                chunk_i += list(range(n))
+            self._norm_table = dict(
+                g=torch.tensor([p.grad.data_ptr() for p in ps], dtype=torch.int64, device=dev),
+                numel=torch.tensor([p.numel() for p in ps], dtype=torch.int64, device=dev),
+                ct=torch.tensor(chunk_t, dtype=torch.int32, device=dev), ci=torch.tensor(chunk_i, dtype=torch.int32, device=dev),
+                n_chunks=len(chunk_t), partial=torch.empty((len(chunk_t),), dtype=torch.float32, device=dev))
         # a rebuild (gradient storage replaced) must not restart the bias-correction counter
         self._step = max([getattr(self, "_step", 0)] + [int(self.state[p]["step"]) for g in groups for p in g["params"]])
 
@@ -93,9 +113,7 @@ class FusedAdamW(torch.optim.Optimizer):
         L = lib()
         clip = None
         if self.max_grad_norm is not None and self.max_grad_norm > 0:
-            if len(self._tables) != 1:
-                raise NotImplementedError("FusedAdamW: gradient clipping over several param groups is not built")
-            t = self._tables[0]
+            t = self._norm_table
             check(L.uwu_mt_gradnorm(t["g"].data_ptr(), t["numel"].data_ptr(), t["ct"].data_ptr(), t["ci"].data_ptr(),
                                     t["n_chunks"], _CHUNK, float(self.max_grad_norm), t["partial"].data_ptr(),
                                     self._norm_out.data_ptr(), stream), "uwu_mt_gradnorm")

@@ -23,6 +23,7 @@ class GradientBuckets:
         self.backend = dist.get_backend(process_group)
         self.unet = trainer.unet
         ly = trainer.lycoris_model
+        self._sync_replicas(trainer)
         if ly is not None:
             self.flat = ly.flat_grads
             params = list(ly.parameters())
@@ -61,6 +62,25 @@ class GradientBuckets:
         self.unet.after_backward = self._on_blocks_done
         self.reduced_elems = 0
         self.enabled = True  # False while a gradient-accumulation micro-batch other than the last is in backward
+
+    def _sync_replicas(self, trainer):
+        """What torch DDP does at construction and the reference relies on (per-rank `seed + rank`,
+        test_scripts/test_train.py:68-69): parameters AND buffers of rank 0 — frozen base, adapters, loss head — are broadcast
+        so every replica starts from the same state whatever its local seed was; the bf16 operand caches are dropped."""
+        src = dist.get_global_rank(self.group, 0) if self.group is not None else 0
+        ly = trainer.lycoris_model
+        with torch.no_grad():
+            if ly is not None:
+                dist.broadcast(ly.flat_params, src=src, group=self.group)  # every adapter tensor is a view into it
+                for b in ly.buffers():
+                    dist.broadcast(b, src=src, group=self.group)
+            mods = [self.unet] + ([trainer.loss] if isinstance(getattr(trainer, "loss", None), torch.nn.Module) else [])
+            for mod in mods:
+                for t in list(mod.parameters()) + list(mod.buffers()):
+                    if t.is_floating_point() or t.dtype in (torch.int64, torch.int32):
+                        dist.broadcast(t.data, src=src, group=self.group)
+        if hasattr(self.unet, "refresh_weights"):
+            self.unet.refresh_weights()
 
     def begin_step(self):
         self._ready = self.flat.numel()

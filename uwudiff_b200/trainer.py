@@ -64,21 +64,58 @@ class BaseTrainer(nn.Module):
 
 class GradualWarmup:
     """`warmup_scheduler.GradualWarmupScheduler(optimizer, multiplier=1, total_epoch, after_scheduler)` as the reference
-    uses it (trainer.py:62-65): lr ramps linearly 0 -> base over `total_epoch` steps, then hands over."""
+    uses it (trainer.py:62-65), step for step: construction leaves lr = base * 0 / N (the first optimizer step runs at 0),
+    the k-th scheduler step sets base * k / N up to k = N, step N + 1 hands over at the after-scheduler's current lr and
+    later steps advance the after-scheduler."""
 
     def __init__(self, optimizer, total_epoch: int, after_scheduler=None):
         self.optimizer, self.total_epoch, self.after_scheduler = optimizer, total_epoch, after_scheduler
         self.base_lrs = [g["lr"] for g in optimizer.param_groups]
-        self.last_epoch = 0
+        if after_scheduler is not None and hasattr(after_scheduler, "base_lrs"):
+            self.base_lrs = list(after_scheduler.base_lrs)  # constructing it may already have touched group["lr"]
+        self.last_epoch = -1
+        self.finished = False
         self.step()
 
     def step(self):
-        self.last_epoch += 1
-        if self.last_epoch <= self.total_epoch:
-            for g, b in zip(self.optimizer.param_groups, self.base_lrs):
-                g["lr"] = b * self.last_epoch / self.total_epoch
-        elif self.after_scheduler is not None:
+        if self.finished and self.after_scheduler is not None:
             self.after_scheduler.step()
+            return
+        self.last_epoch += 1
+        if self.last_epoch > self.total_epoch:
+            if self.after_scheduler is not None:
+                self.finished = True
+                lrs = self.after_scheduler.get_last_lr()
+            else:
+                lrs = self.base_lrs
+        else:
+            lrs = [b * self.last_epoch / self.total_epoch for b in self.base_lrs]
+        for g, lr in zip(self.optimizer.param_groups, lrs):
+            g["lr"] = lr
+
+    def get_last_lr(self):
+        return [g["lr"] for g in self.optimizer.param_groups]
+
+    def state_dict(self):
+        sd = {"last_epoch": self.last_epoch, "finished": self.finished, "base_lrs": list(self.base_lrs),
+              "total_epoch": self.total_epoch}
+        if self.after_scheduler is not None:
+            sd["after_scheduler"] = self.after_scheduler.state_dict()
+        return sd
+
+    def load_state_dict(self, sd):
+        self.last_epoch, self.finished = sd["last_epoch"], sd["finished"]
+        self.base_lrs, self.total_epoch = list(sd["base_lrs"]), sd["total_epoch"]
+        if self.after_scheduler is not None and "after_scheduler" in sd:
+            self.after_scheduler.load_state_dict(sd["after_scheduler"])
+        if self.finished and self.after_scheduler is not None:
+            lrs = self.after_scheduler.get_last_lr()
+        elif self.last_epoch > self.total_epoch:
+            lrs = self.base_lrs
+        else:
+            lrs = [b * self.last_epoch / self.total_epoch for b in self.base_lrs]
+        for g, lr in zip(self.optimizer.param_groups, lrs):
+            g["lr"] = lr
 
 
 class DMTrainer(BaseTrainer):
@@ -137,9 +174,14 @@ class DMTrainer(BaseTrainer):
         else:
             self.loss = instantiate_any(loss_config)
         self.n_diffusion_time_steps = self.loss.n_diffusion_time_steps
+        if type(self) is DMTrainer and any(p.requires_grad for p in self.loss.parameters()):
+            raise ValueError("the loss module has trainable parameters (e.g. NNWeightedRFLoss.loss_pred_module) that DMTrainer's "
+                             "optimizer would never see: use uwudiff_b200.trainer.NNWeightedLossTrainer")
         # fused sinusoidal timestep embedding from the noising kernel (diffusers Timesteps(block_out_channels[0]))
+        # (the kernel emits the flip_sin_to_cos = True, freq_shift = 0 form; any other config takes the unfused path)
         cfg = self.unet.config
-        self.loss.temb_dim = int(cfg.block_out_channels[0] if hasattr(cfg, "block_out_channels") else cfg.frequency_embedding_size)
+        if getattr(cfg, "flip_sin_to_cos", True) and getattr(cfg, "freq_shift", 0) == 0:
+            self.loss.temb_dim = int(cfg.block_out_channels[0] if hasattr(cfg, "block_out_channels") else cfg.frequency_embedding_size)
         self._fit = None
 
     # ---- reference API ---------------------------------------------------------------------------------------
@@ -247,3 +289,53 @@ class DMTrainer(BaseTrainer):
             f["opt"].zero_grad(set_to_none=False)  # gradients keep their (flat) storage
         self.global_step += 1
         return out
+
+    # ---- checkpoint / resume of what Lightning's .ckpt carries besides the weights ----------------------------------
+    def fit_state_dict(self) -> Dict[str, Any]:
+        """Optimizer moments + step counter, LR-scheduler state, global step and the noise-stream position."""
+        if self._fit is None:
+            self.setup_fit()
+        f = self._fit
+        return {"optimizer": f["opt"].state_dict(), "lr_scheduler": f["sched"].state_dict() if f["sched"] is not None else None,
+                "global_step": self.global_step, "loss_step": getattr(self.loss, "_step", 0), "ema_loss": float(self.ema_loss)}
+
+    def load_fit_state_dict(self, sd: Dict[str, Any]):
+        if self._fit is None:
+            self.setup_fit()
+        f = self._fit
+        f["opt"].load_state_dict(sd["optimizer"])
+        if f["sched"] is not None and sd.get("lr_scheduler") is not None:
+            f["sched"].load_state_dict(sd["lr_scheduler"])
+        self.global_step = int(sd["global_step"])
+        if hasattr(self.loss, "_step"):
+            self.loss._step = int(sd.get("loss_step", 0))
+        self.ema_loss.fill_(float(sd.get("ema_loss", 0.0)))
+
+
+class NNWeightedLossTrainer(DMTrainer):
+    """Drop-in for `duwu.trainer.nn_weighted_loss_trainer.NNWeightedLossTrainer` (nn_weighted_loss_trainer.py:12-95): the loss
+    module (an `NNWeightedRFLoss` with its `loss_pred_module`) is trained too, in its own parameter group with
+    `loss_opt_config`.  (The reference class passes `lycoris_model=` to a `DMTrainer` that takes `lycoris_config=` and is
+    un-constructible as shipped; here the keyword is `lycoris_config`.)"""
+
+    def __init__(self, *args, loss_opt_config: Dict[str, Any] = {"lr": 1e-3, "weight_decay": 0, "betas": (0.9, 0.999)}, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.loss = self.loss.to(self.ema_loss.device)
+        self.loss.requires_grad_(True).train()
+        self.loss_params = list(self.loss.parameters())
+        self.loss_opt_config = dict(loss_opt_config)
+        self.train_params = list(self.train_params)
+
+    def configure_optimizers(self, max_grad_norm: Optional[float] = None):
+        kw = {}
+        from .optim import FusedAdamW
+
+        if self.optimizer is FusedAdamW and max_grad_norm is not None:
+            kw["max_grad_norm"] = max_grad_norm
+        optimizer = self.optimizer([{"params": self.loss_params, **self.loss_opt_config},
+                                    {"params": self.train_params, "lr": self.lr, **self.opt_config}], **kw)
+        lr_sch = self.lr_sch(optimizer, **self.lr_sch_config) if self.lr_sch is not None else None
+        lr_scheduler = GradualWarmup(optimizer, self.warm_up_period, lr_sch) if self.use_warm_up else lr_sch
+        if lr_scheduler is None:
+            return optimizer
+        return {"optimizer": optimizer, "lr_scheduler": {"scheduler": lr_scheduler, "interval": "step"}}

@@ -59,6 +59,16 @@ KNOWN_UNET_CONFIGS = {"stabilityai/stable-diffusion-xl-base-1.0": SDXL_UNET_CONF
 # current forward, `gen` changes whenever an operand cache is dropped (the fold table holds raw destination pointers).
 FOLD = types.SimpleNamespace(epoch=0, gen=0)
 
+# Test hook (tests/test_sdxl_parity_gpu.py): callable(module, tag, tensor) that sees the output stream of every resnet /
+# transformer block in forward ("out") and the gradient each block returns in backward ("dx").  None in production.
+PROBE = None
+
+
+def _probe(mod, tag, t):
+    if PROBE is not None:
+        PROBE(mod, tag, t)
+    return t
+
 
 def _pad_to(n: int, m: int) -> int:
     return (n + m - 1) // m * m
@@ -384,7 +394,7 @@ class ResnetBlock2D(nn.Module):
         # full fine-tuning keeps the normalised activations: they are the inputs of the conv weight gradients
         keep = (a if self.conv1.trainable else None, b if self.conv2.trainable else None)
         self._sv = (x, s1, h1, s2, (N, H, W), keep)
-        return out
+        return _probe(self, "out", out)
 
     def bwd(self, dout, st):
         x, s1, h1, s2, (N, H, W), (a, b) = self._sv
@@ -405,7 +415,7 @@ class ResnetBlock2D(nn.Module):
             if self.conv_shortcut.trainable:
                 self.conv_shortcut.param_grads1x1(x, dout, N * H * W)
             dres = self.conv_shortcut.dgrad1x1(dout, N * H * W)
-        return self.norm1.bwd(x, da, s1, N, H * W, True, dres=dres)
+        return _probe(self, "dx", self.norm1.bwd(x, da, s1, N, H * W, True, dres=dres))
 
 
 class Attention(nn.Module):
@@ -538,7 +548,9 @@ class BasicTransformerBlock(nn.Module):
         n3, s3 = self.norm3.fwd(x2)
         x3 = self.ff.fwd(n3, x2, st)
         self._sv = (x0, s1, x1, s2, x2, s3)
-        return x3
+        _probe(self, "x1", x1)
+        _probe(self, "x2", x2)
+        return _probe(self, "out", x3)
 
     def bwd(self, dx3, st):
         x0, s1, x1, s2, x2, s3 = self._sv
@@ -548,7 +560,7 @@ class BasicTransformerBlock(nn.Module):
         dn2 = self.attn2.bwd(dx2, st)
         dx1 = self.norm2.bwd(x1, dn2, s2, dres=dx2)
         dn1 = self.attn1.bwd(dx1, st)
-        return self.norm1.bwd(x0, dn1, s1, dres=dx1)
+        return _probe(self, "dx", self.norm1.bwd(x0, dn1, s1, dres=dx1))
 
 
 class Transformer2DModel(nn.Module):
@@ -573,7 +585,7 @@ class Transformer2DModel(nn.Module):
             h = blk.fwd(h, st)
         out = self.proj_out.fwd(h, st.M, residual=x)
         self._sv = (x, s, n, h)
-        return out
+        return _probe(self, "out", out)
 
     def bwd(self, dout, st):
         x, s, n, h = self._sv
@@ -583,7 +595,7 @@ class Transformer2DModel(nn.Module):
         for blk in reversed(self.transformer_blocks):
             dh = blk.bwd(dh, st)
         dn = self.proj_in.bwd(dh, n, st.M)
-        return self.norm.bwd(x, dn, s, st.N, st.H * st.W, False, dres=dout)
+        return _probe(self, "dx", self.norm.bwd(x, dn, s, st.N, st.H * st.W, False, dres=dout))
 
 
 class Downsample2D(nn.Module):
@@ -710,11 +722,16 @@ class _UNetFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, hook, unet, sample, timestep, ehs, added, fused_temb):
         ctx.unet = unet
+        unet._fwd_gen = ctx.gen = getattr(unet, "_fwd_gen", 0) + 1
         out = unet._forward_impl(sample, timestep, ehs, added, fused_temb)
         return out
 
     @staticmethod
     def backward(ctx, gout):
+        # activations are stashed on the modules, not in the graph: only the LATEST grad-enabled forward can be differentiated
+        if ctx.gen != ctx.unet._fwd_gen or ctx.unet._fsv is None:
+            raise RuntimeError("uwudiff_b200: backward of a forward whose saved activations were overwritten by a later "
+                               "forward (or already consumed); run one forward -> one backward per step")
         ctx.unet._backward_impl(gout)
         return (torch.zeros((), device=gout.device),) + (None,) * 6
 
@@ -733,6 +750,8 @@ class UNet2DConditionModel(nn.Module):
         hd = (hd,) * n if isinstance(hd, int) else tuple(hd)  # diffusers quirk: attention_head_dim == number of heads
         groups, eps, cross = c["norm_num_groups"], c["norm_eps"], c["cross_attention_dim"]
         lin = c["use_linear_projection"]
+        if c.get("freq_shift", 0) != 0:
+            raise NotImplementedError("uwudiff_b200: freq_shift != 0 is not built (every reference config uses 0)")
         for ch in boc:
             if ch % 64 != 0:
                 raise NotImplementedError(f"uwudiff_b200: block_out_channels must be multiples of 64 (got {boc})")
@@ -919,6 +938,33 @@ class UNet2DConditionModel(nn.Module):
         self._fsv = (st, x, s_out, cat_shapes, (B, H, W), x_in0, y if self.conv_out.trainable else None)
         return out
 
+    def _down_units(self):
+        """Forward-order list of (block index, kind, layer index) for the down path."""
+        units = []
+        for bi, blk in enumerate(self.down_blocks):
+            for i in range(len(blk.resnets)):
+                units.append((bi, "res", i))
+                if blk.has_attn:
+                    units.append((bi, "attn", i))
+            if blk.downsamplers is not None:
+                units.append((bi, "down", 0))
+        return units
+
+    def _first_trainable_unit(self, units) -> int:
+        def trainable(mod):
+            for m in mod.modules():
+                ad = getattr(m, "_uwu_adapter", None)
+                if ad is not None and ad.trainable():
+                    return True
+            return any(p.requires_grad for p in mod.parameters())
+
+        for ui, (bi, kind, i) in enumerate(units):
+            blk = self.down_blocks[bi]
+            mod = blk.downsamplers[0] if kind == "down" else (blk.attentions[i] if kind == "attn" else blk.resnets[i])
+            if trainable(mod):
+                return ui
+        return len(units)
+
     # ---------------------------------------------------------------------------------------------
     # backward
     # ---------------------------------------------------------------------------------------------
@@ -964,17 +1010,29 @@ class UNet2DConditionModel(nn.Module):
         def take():
             return dskips.pop()
 
-        for blk in reversed(self.down_blocks):
-            if blk.downsamplers is not None:
+        # Down path in reverse.  Units upstream of the first trainable module get no backward at all (autograd in the
+        # reference prunes them the same way): under the LyCORIS preset that is down_blocks[0] and the first resnet of
+        # down_blocks[1].
+        units = self._down_units()
+        first = 0 if (x_in0 is not None or st.need_temb_grad) else self._first_trainable_unit(units)
+        for ui in reversed(range(first, len(units))):
+            bi, kind, i = units[ui]
+            blk = self.down_blocks[bi]
+            if kind == "down":
                 dx = ops.elementwise(_contig(dx), take(), ops.EW_ADD)
                 dx = blk.downsamplers[0].bwd(dx, st)
                 st.H, st.W = st.H * 2, st.W * 2
-            for i in reversed(range(len(blk.resnets))):
+            elif kind == "attn":
                 dx = ops.elementwise(_contig(dx), take(), ops.EW_ADD)
-                if blk.has_attn:
-                    dx = blk.attentions[i].bwd(dx, st)
+                dx = blk.attentions[i].bwd(dx, st)
+            else:
+                if not blk.has_attn:
+                    dx = ops.elementwise(_contig(dx), take(), ops.EW_ADD)
                 dx = blk.resnets[i].bwd(dx, st)
-            done([blk])
+            if ui == first or units[ui - 1][0] != bi:
+                done([self.down_blocks[b] for b in range(bi if ui > first else 0, bi + 1)])
+        if first >= len(units):
+            done(list(self.down_blocks))
         # conv_in / embeddings: frozen under LyCORIS (no gradient flows to x_t); trained in full fine-tuning
         if x_in0 is not None:
             dx = ops.elementwise(_contig(dx), take(), ops.EW_ADD)  # + gradient of the first skip connection
