@@ -352,11 +352,13 @@ int uwu_lokr_dw1(const void* v, const void* x, int64_t ldx, int64_t M, int32_t o
  * (pointers as uint64, numels, and a chunk table (tensor index, chunk index) of n_chunks entries) */
 int uwu_mt_gradnorm(const uint64_t* g_ptrs, const int64_t* numels, const int32_t* chunk_tensor, const int32_t* chunk_index,
                     int32_t n_chunks, int32_t chunk_elems, float max_norm, float* partial_ws, float* out2, void* stream);
-/* torch.optim.AdamW step (decoupled weight decay, bias correction by `step`), gradients scaled by norm_clip[1] if given */
+/* torch.optim.AdamW step (decoupled weight decay, bias correction by `step`), gradients scaled by norm_clip[1] if given.
+ * hyper_dev (optional, device fp32[3] = {lr, 1 - beta1^step, sqrt(1 - beta2^step)}) overrides lr / step when the kernel
+ * runs, so that a launch captured in a CUDA graph follows the LR schedule (src/duwu/trainer/trainer.py:52-74) on replay */
 int uwu_mt_adamw(const uint64_t* p_ptrs, const uint64_t* g_ptrs, const uint64_t* m_ptrs, const uint64_t* v_ptrs,
                  const int64_t* numels, const int32_t* chunk_tensor, const int32_t* chunk_index, int32_t n_chunks,
                  int32_t chunk_elems, float lr, float beta1, float beta2, float eps, float weight_decay, int64_t step,
-                 const float* norm_clip, void* stream);
+                 const float* norm_clip, const float* hyper_dev, void* stream);
 /* strided 2-D copy with cast to bf16 (skip-connection concat, conditioning staging) */
 int uwu_copy2d_bf16(const void* src, int32_t src_dtype, int64_t lds, void* dst_bf16, int64_t ldd, int64_t rows, int32_t cols,
                     void* stream);

@@ -472,3 +472,106 @@ def test_merge_lycoris_through_the_fold_kernels_and_weight_file_roundtrip(tmp_pa
     with torch.no_grad():
         y_reloaded = tr2.unet(x, t, **kw)[0]
     assert torch.equal(y_reloaded, y_adapted)
+
+
+def _tiny_trainer(lr=1e-3, seed=3):
+    from uwudiff_b200 import config as ucfg
+
+    cfg = U.tiny_config()
+    conf = {
+        "_target_": "duwu.trainer.DMTrainer", "_recursive_": False, "lr": lr, "optimizer": "torch.optim.AdamW",
+        "opt_config": {"weight_decay": 0.01, "betas": [0.9, 0.999]}, "use_warm_up": False,
+        "lycoris_config": {"config": LYCORIS_CFG, "preset": LYCORIS_PRESET},
+        "loss_config": {"_target_": "duwu.loss.DiffusionLoss",
+                        "scheduler": {"_target_": "diffusers.EulerDiscreteScheduler.from_pretrained",
+                                      "pretrained_model_name_or_path": "stabilityai/stable-diffusion-xl-base-1.0",
+                                      "subfolder": "scheduler", "prediction_type": "v_prediction"},
+                        "use_snr_weight": True},
+        "model_config": {"unet": {"_target_": "duwu.modules.unet_patch.UNet2DFromScratch.from_config", "config": cfg},
+                         "te": {"_target_": "duwu.modules.text_encoders.ConcatTextEncoders", "hidden_dim": 128,
+                                "pooled_dim": 64, "_load_config_": {"to_freeze": True}},
+                         "vae": None},
+    }
+    torch.manual_seed(seed)
+    tr = ucfg.instantiate_any(conf)
+    g = torch.Generator(device="cuda").manual_seed(1)
+    tr.lycoris_model.flat_params.copy_(torch.randn(tr.lycoris_model.flat_params.shape, device="cuda", generator=g) * 0.05)
+    return tr
+
+
+def _batches(n, B=2, seed=11):
+    g = torch.Generator().manual_seed(seed)
+    ids = torch.tensor([[1024., 1024, 0, 0, 1024, 1024]] * B)
+    return [(torch.randn(B, 4, 16, 16, generator=g).cuda(), ["DUMMY TEST"] * B, [], {"time_ids": ids.cuda()}, {}) for _ in range(n)]
+
+
+def test_cuda_graph_step_is_bit_identical_to_the_eager_step():
+    """`setup_fit(cuda_graph=True)`: after two eager optimizer steps the step is captured (forward + backward, clip + AdamW)
+    and replayed.  Same seeds, same batches: losses, timesteps and parameters after 6 steps equal the all-eager run BIT FOR
+    BIT (same kernels, same order; lr schedule, Adam bias correction, EMA decay and the noise stream advance on replay)."""
+    from uwudiff_b200 import ops
+
+    data = _batches(6)
+    runs = []
+    for graph in (False, True):
+        tr = _tiny_trainer()
+        tr.setup_fit(gradient_clip_val=1.0, seed=1215, cuda_graph=graph, graph_warmup_steps=2)
+        losses, ts = [], []
+        n0 = ops.launch_count()
+        for i, b in enumerate(data):
+            out = tr.fit_step(b, i)
+            losses.append(out["loss"].item())
+            ts.append(out["aux_output"].timesteps.clone())
+        runs.append(dict(losses=losses, ts=ts, params=tr.lycoris_model.flat_params.clone(), ema=float(tr.ema_loss),
+                         lr=tr._fit["opt"].param_groups[0]["lr"], launches=ops.launch_count() - n0, state=tr._fit["graph"]))
+    e, g = runs
+    assert g["state"]["state"] == "replay" and g["state"]["n_fwdbwd"] > 300
+    assert all(torch.equal(a, b) for a, b in zip(e["ts"], g["ts"])), "the noise / timestep stream must advance on replay"
+    assert len({tuple(t.tolist()) for t in g["ts"]}) > 1
+    assert e["losses"] == g["losses"], (e["losses"], g["losses"])
+    assert torch.equal(e["params"], g["params"])
+    assert abs(e["ema"] - g["ema"]) <= 1e-6 * abs(e["ema"]) and e["lr"] == g["lr"]
+    assert abs(e["launches"] - g["launches"]) <= 8, (e["launches"], g["launches"])  # replayed launches are counted
+
+
+def test_gradient_accumulation_on_the_gpu_matches_one_large_batch_of_gradients():
+    """configs[4] on fewer GPUs: k micro-batches with `accumulate_grad_batches = k` -> one optimizer step on the MEAN of the
+    micro-batch gradients (eager and CUDA-graph paths), parameters untouched before the last micro-batch."""
+    data = _batches(8)
+    # reference: gradients of each micro-batch alone (fresh trainers, identical init and noise stream)
+    tr = _tiny_trainer()
+    tr.setup_fit(gradient_clip_val=None, seed=1215, accumulate_grad_batches=1)
+    grads = []
+    for i in range(2):
+        tr.lycoris_model.zero_grad()
+        out = tr.training_step(data[i], i)
+        out["loss"].backward()
+        grads.append(tr.lycoris_model.flat_grads.clone())
+    mean = (grads[0] + grads[1]) / 2
+    for graph in (False, True):
+        tr = _tiny_trainer()
+        tr.setup_fit(gradient_clip_val=None, seed=1215, accumulate_grad_batches=2, cuda_graph=graph, graph_warmup_steps=1)
+        p0 = tr.lycoris_model.flat_params.clone()
+        tr.fit_step(data[0], 0)
+        assert torch.equal(tr.lycoris_model.flat_params, p0), "no optimizer step before the last micro-batch"
+        acc = tr.lycoris_model.flat_grads.clone()
+        assert torch.allclose(acc, grads[0] / 2, rtol=1e-5, atol=1e-9)
+        # second micro-batch: capture the accumulated gradient just before the optimizer consumes it
+        seen = {}
+        real_step = tr._fit["opt"].step
+
+        def spy(*a, **k):
+            seen["g"] = tr.lycoris_model.flat_grads.clone()
+            return real_step(*a, **k)
+
+        tr._fit["opt"].step = spy
+        tr.fit_step(data[1], 1)
+        assert torch.allclose(seen["g"], mean, rtol=1e-5, atol=1e-9)
+        assert not torch.equal(tr.lycoris_model.flat_params, p0) and float(tr.lycoris_model.flat_grads.abs().max()) == 0.0
+        tr._fit["opt"].step = real_step
+        # keep going (graph mode: warm-up is over after the first optimizer step -> capture + replay); stays finite
+        for i in range(2, 8):
+            out = tr.fit_step(data[i], i)
+        assert torch.isfinite(out["loss"]).item() and tr.global_step == 4
+        if graph:
+            assert tr._fit["graph"]["state"] == "replay"

@@ -14,6 +14,8 @@ Prints one JSON line.  `tensor_tflops` = 3 x algorithmic forward FLOPs (fwd + dg
 import argparse
 import json
 import os
+
+os.environ.setdefault("UWU_SYNTHETIC_CONDITIONING", "1")  # synthetic text-encoder outputs (no weights offline)
 import sys
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))

@@ -14,6 +14,8 @@ from __future__ import annotations
 import argparse
 import json
 import os
+
+os.environ.setdefault("UWU_SYNTHETIC_CONDITIONING", "1")  # synthetic text-encoder outputs (no weights offline)
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

@@ -3,6 +3,8 @@
     python tools/bench_kernels.py [ln] [geglu] [gn] [lokr] [wgrad] [lin] [attn]
 """
 import os
+
+os.environ.setdefault("UWU_SYNTHETIC_CONDITIONING", "1")  # synthetic text-encoder outputs (no weights offline)
 import sys
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))

@@ -8,6 +8,8 @@ exchanged exactly once.  Prints one JSON line on rank 0 (samples/s over all rank
 """
 import json
 import os
+
+os.environ.setdefault("UWU_SYNTHETIC_CONDITIONING", "1")  # synthetic text-encoder outputs (no weights offline)
 import sys
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))

@@ -6,6 +6,8 @@ Each case prints max-abs / relative error against a torch fp32 matmul/conv2d of 
 """
 import sys
 import os
+
+os.environ.setdefault("UWU_SYNTHETIC_CONDITIONING", "1")  # synthetic text-encoder outputs (no weights offline)
 import itertools
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -164,6 +166,95 @@ def case_perf():
         wp = mk(Co, 9 * C)
         out = torch.empty(Nimg * H * W, Co, device=dev, dtype=torch.bfloat16)
         bench(lambda: ops.conv3x3_nhwc(x, wp, out=out), 2 * Nimg * H * W * Co * 9 * C, f"conv {Nimg}x{H}x{W} C{C}->{Co}")
+
+
+def case_perf12():
+    """The most expensive GEMM / conv classes of the SDXL + LyCORIS step (profiles/r01_step_breakdown_441ms.log), isolated,
+    next to torch.matmul (cuBLASLt) / cuDNN on the same shapes.  Run with UWU_GEMM_PAIR=0 and =1 to compare the 1-CTA and
+    the CTA-pair kernels."""
+    import os
+
+    def bench(fn, flops, iters=20):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(iters):
+            fn()
+        e.record()
+        torch.cuda.synchronize()
+        ms = s.elapsed_time(e) / iters
+        return ms * 1e3, flops / ms / 1e9
+
+    print(f"UWU_GEMM_PAIR={os.environ.get('UWU_GEMM_PAIR', '1 (default)')}")
+    print(f"{'shape':44s} {'uwu us':>9s} {'TF/s':>8s} {'torch us':>9s} {'TF/s':>8s} {'ratio':>6s}")
+    lin = [(16384, 1280, 1280, "nk", True), (16384, 10240, 1280, "nk", False), (16384, 1280, 10240, "kn", False),
+           (16384, 1280, 5120, "nk", True), (16384, 5120, 1280, "kn", False), (16384, 3840, 1280, "nk", False),
+           (16384, 1280, 3840, "kn", False), (16384, 1280, 2048, "nk", False), (65536, 640, 640, "nk", True),
+           (65536, 5120, 640, "nk", False), (65536, 640, 5120, "kn", False), (65536, 640, 2560, "nk", True),
+           (8192, 8192, 8192, "nk", False)]
+    for (M, N, K, bl, with_res) in lin:
+        a = mk(M, K)
+        b = mk(N, K) if bl == "nk" else mk(K, N)
+        out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+        res = mk(M, N) if with_res else None
+        bias = torch.randn(N, device=dev) if with_res else None
+        fn = lambda: ops.gemm(a, b, M, N, K, out=out, b_layout=B_NK if bl == "nk" else B_KN, residual=res, bias=bias)
+        us, tf = bench(fn, 2 * M * N * K)
+        if bl == "nk":
+            ref = (lambda: torch.addmm(res, a, b.t())) if with_res else (lambda: torch.matmul(a, b.t()))
+        else:
+            ref = lambda: torch.matmul(a, b)
+        rus, rtf = bench(ref, 2 * M * N * K)
+        tag = f"lin M{M} N{N} K{K} {bl}{' +bias+res' if with_res else ''}"
+        print(f"{tag:44s} {us:9.1f} {tf:8.1f} {rus:9.1f} {rtf:8.1f} {tf / rtf:6.2f}", flush=True)
+    torch.backends.cudnn.benchmark = True
+    for (Nimg, H, W, C, Co) in [(16, 128, 128, 320, 320), (16, 64, 64, 640, 640), (16, 32, 32, 1280, 1280),
+                                (16, 32, 32, 2560, 1280), (16, 128, 128, 640, 320)]:
+        x = mk(Nimg, H, W, C)
+        wp = mk(Co, 9 * C)
+        out = torch.empty(Nimg * H * W, Co, device=dev, dtype=torch.bfloat16)
+        fl = 2 * Nimg * H * W * Co * 9 * C
+        us, tf = bench(lambda: ops.conv3x3_nhwc(x, wp, out=out), fl, iters=10)
+        xc = x.permute(0, 3, 1, 2)  # channels-last NCHW view for cuDNN
+        wc = wp.view(Co, 3, 3, C).permute(0, 3, 1, 2)
+        rus, rtf = bench(lambda: F.conv2d(xc, wc, padding=1), fl, iters=10)
+        tag = f"conv {Nimg}x{H}x{W} C{C}->{Co}"
+        print(f"{tag:44s} {us:9.1f} {tf:8.1f} {rus:9.1f} {rtf:8.1f} {tf / rtf:6.2f}", flush=True)
+
+
+def case_perfw():
+    """Token-reduction (adapter / weight gradient) GEMMs of the step: G[N_out, K_in] = dY^T X, fp32 output, split-K schedules."""
+    import os
+
+    print(f"UWU_GEMM_PAIR={os.environ.get('UWU_GEMM_PAIR', '2 (default)')}")
+    for (Co, Ci, Mtok) in [(1280, 5120, 16384), (1280, 1280, 16384), (3840, 1280, 16384), (5120, 1280, 16384),
+                           (640, 640, 65536), (640, 2560, 65536), (1920, 640, 65536), (2560, 2048, 1232)]:
+        dy, x = mk(Mtok, Co), mk(Mtok, Ci)
+        G = torch.empty(Co, Ci, device=dev, dtype=torch.float32)
+        fn = lambda: ops.gemm(dy, x, Co, Ci, Mtok, a_layout=A_COL, lda=Co, b_layout=B_KN, ldb=Ci, out=G)
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(20):
+            fn()
+        e.record()
+        torch.cuda.synchronize()
+        ms = s.elapsed_time(e) / 20
+        ref = dy.float().t() @ x.float()
+        err = ((G - ref).abs().max() / ref.abs().max()).item()
+        s.record()
+        for _ in range(20):
+            torch.matmul(dy.t(), x)
+        e.record()
+        torch.cuda.synchronize()
+        rms_ = s.elapsed_time(e) / 20
+        fl = 2.0 * Co * Ci * Mtok
+        print(f"wgrad G[{Co},{Ci}] K{Mtok}: {ms*1e3:8.1f} us {fl/ms/1e9:8.1f} TF/s   torch bf16-out {rms_*1e3:8.1f} us "
+              f"{fl/rms_/1e9:8.1f} TF/s   rel err {err:.2e}", flush=True)
 
 
 if __name__ == "__main__":

@@ -40,6 +40,19 @@ def main(what):
         bias = torch.zeros(N, device=dev)
         for _ in range(3):
             ops.gemm(a, b, M, N, K, out=out, bias=bias)
+    elif what == "conv320":
+        # the weakest GEMM class against cuDNN (profiles/r02_gemm_perf12*.log): 3x3 conv 320 -> 320 at 128 x 128, batch 16
+        x = mk(16, 128, 128, 320)
+        wp = mk(320, 9 * 320)
+        out = torch.empty(16 * 128 * 128, 320, device=dev, dtype=torch.bfloat16)
+        bias = torch.zeros(320, device=dev)
+        for _ in range(3):
+            ops.conv3x3_nhwc(x, wp, out=out, bias=bias)
+        x = mk(16, 64, 64, 640)
+        wp = mk(640, 9 * 640)
+        out = torch.empty(16 * 64 * 64, 640, device=dev, dtype=torch.bfloat16)
+        for _ in range(3):
+            ops.conv3x3_nhwc(x, wp, out=out)
     elif what == "bw":
         # one launch each of the bandwidth-bound kernels at step shapes
         from uwudiff_b200.loss import DiffusionLoss

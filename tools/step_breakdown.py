@@ -8,6 +8,8 @@ is recorded and aggregated by op (and by shape for the GEMM / conv / attention c
 import argparse
 import collections
 import os
+
+os.environ.setdefault("UWU_SYNTHETIC_CONDITIONING", "1")  # synthetic text-encoder outputs (no weights offline)
 import sys
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))

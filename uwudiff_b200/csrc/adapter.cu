@@ -617,7 +617,13 @@ __global__ void __launch_bounds__(256) mt_norm_final_kernel(const float* __restr
 }
 
 __global__ void __launch_bounds__(256) mt_adamw_kernel(MTTables t, float lr, float beta1, float beta2, float eps, float wd,
-                                                       float bc1, float bc2_sqrt, const float* __restrict__ clip) {
+                                                       float bc1, float bc2_sqrt, const float* __restrict__ clip,
+                                                       const float* __restrict__ hyper) {
+    if (hyper) {  // per-step scalars read from device memory: the launch can live in a CUDA graph while lr / step advance
+        lr = hyper[0];
+        bc1 = hyper[1];
+        bc2_sqrt = hyper[2];
+    }
     const int ti = t.chunk_tensor[blockIdx.x];
     const long long n = t.numel[ti];
     const long long beg = (long long)t.chunk_index[blockIdx.x] * t.chunk_elems;
@@ -813,15 +819,17 @@ extern "C" int uwu_mt_gradnorm(const uint64_t* g_ptrs, const int64_t* numels, co
 extern "C" int uwu_mt_adamw(const uint64_t* p_ptrs, const uint64_t* g_ptrs, const uint64_t* m_ptrs, const uint64_t* v_ptrs,
                             const int64_t* numels, const int32_t* chunk_tensor, const int32_t* chunk_index, int32_t n_chunks,
                             int32_t chunk_elems, float lr, float beta1, float beta2, float eps, float weight_decay,
-                            int64_t step, const float* norm_clip, void* stream_) {
+                            int64_t step, const float* norm_clip, const float* hyper_dev, void* stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-    UWU_CHECK_ARG(p_ptrs && g_ptrs && m_ptrs && v_ptrs && numels && chunk_tensor && chunk_index && n_chunks > 0 && step > 0,
+    UWU_CHECK_ARG(p_ptrs && g_ptrs && m_ptrs && v_ptrs && numels && chunk_tensor && chunk_index && n_chunks > 0 &&
+                      (step > 0 || hyper_dev),
                   "uwu_mt_adamw: bad arguments");
+    if (step <= 0) step = 1;
     MTTables t{p_ptrs, g_ptrs, m_ptrs, v_ptrs, numels, chunk_tensor, chunk_index, chunk_elems};
     const double bc1 = 1.0 - pow((double)beta1, (double)step);
     const double bc2 = 1.0 - pow((double)beta2, (double)step);
     mt_adamw_kernel<<<n_chunks, 256, 0, stream>>>(t, lr, beta1, beta2, eps, weight_decay, (float)bc1, (float)sqrt(bc2),
-                                                  norm_clip);
+                                                  norm_clip, hyper_dev);
     UWU_CHECK_LAUNCH();
     return UWU_OK;
 }

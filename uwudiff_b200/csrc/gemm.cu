@@ -72,6 +72,8 @@ struct GemmKernelArgs {
     int cluster2;      // 1: launched as 2-CTA clusters sharing every B tile (same n-tile, adjacent m-tiles)
     int b_half_bytes;  // shared-memory offset of the second half of a B stage
     int b_3d;  // MN-major B through a 3-D tensor map {64 n, K, N/64}: ONE TMA instruction per stage instead of block_n/64
+    int pair;      // 1: CTA-pair kernel (cta_group::2): one 256 x block_n tile per cluster of two CTAs; each CTA stages its
+                   //    own 128 rows of A and HALF of the B tile, the leader CTA issues M = 256 UMMAs for both
     int stream_k;  // 1: the (tile, k-block) space is cut into equal contiguous ranges, one per CTA; partial tiles are
                    //    reduced with vector atomics into the fp32 output (which the host zeroed unless accumulating)
                    // 2: the reduction is cut into sk_slices slices; units (slice, tile) are dealt round-robin in slice-major
@@ -90,29 +92,31 @@ struct WorkIter {
     __device__ __forceinline__ void init(const GemmKernelArgs& p, int num_tiles) {
         num_kb = p.num_kb;
         stream_k = p.stream_k;
-        if (stream_k == 2) {
-            slices = p.sk_slices;
-            ntiles = num_tiles;
-            cur = blockIdx.x;
-            end = (long long)num_tiles * slices;
-            step = gridDim.x;
-        } else if (stream_k) {
-            const long long units = (long long)num_tiles * num_kb;
-            cur = units * blockIdx.x / gridDim.x;
-            end = units * (blockIdx.x + 1) / gridDim.x;
-            step = 0;
-        } else if (p.cluster2) {
-            // units are (m-pair, n-tile); both CTAs of a cluster walk the same units
-            cur = blockIdx.x >> 1;
-            end = (long long)((p.num_m_tiles + 1) >> 1) * p.num_n_tiles;
-            step = gridDim.x >> 1;
+        // workers: CTAs, or clusters of two when the unit of work is a 256-row tile pair (both CTAs walk the same units)
+        int bid = blockIdx.x, nb = gridDim.x;
+        if (p.cluster2 || p.pair) {
             pair = 1;
             rank = (int)(blockIdx.x & 1);
             nnt = p.num_n_tiles;
+            bid >>= 1;
+            nb >>= 1;
+            num_tiles = ((p.num_m_tiles + 1) >> 1) * p.num_n_tiles;
+        }
+        if (stream_k == 2) {
+            slices = p.sk_slices;
+            ntiles = num_tiles;
+            cur = bid;
+            end = (long long)num_tiles * slices;
+            step = nb;
+        } else if (stream_k) {
+            const long long units = (long long)num_tiles * num_kb;
+            cur = units * bid / nb;
+            end = units * (bid + 1) / nb;
+            step = 0;
         } else {
-            cur = blockIdx.x;
+            cur = bid;
             end = num_tiles;
-            step = gridDim.x;
+            step = nb;
         }
     }
     __device__ __forceinline__ bool next() {
@@ -131,13 +135,13 @@ struct WorkIter {
             cur += kb1 - kb0;
         } else {
             tile = (int)cur;
-            if (pair) {  // unit -> this CTA's tile id (m-tile 2*m_pair + rank may lie past the last row tile: fully clipped)
-                const int n_blk = tile % nnt, m_pair = tile / nnt;
-                tile = (2 * m_pair + rank) * nnt + n_blk;
-            }
             kb0 = 0;
             kb1 = num_kb;
             cur += step;
+        }
+        if (pair) {  // unit -> this CTA's tile id (m-tile 2*m_pair + rank may lie past the last row tile: fully clipped)
+            const int n_blk = tile % nnt, m_pair = tile / nnt;
+            tile = (2 * m_pair + rank) * nnt + n_blk;
         }
         return true;
     }
@@ -147,6 +151,7 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
+template <bool PAIR>
 __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __grid_constant__ GemmKernelArgs p) {
     pdl_trigger();
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -176,26 +181,32 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < p.stages; ++s) {
             mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], p.cluster2 ? 2 : 1);  // cluster mode: both CTAs' MMA warps release a stage
+            mbar_init(&empty_bar[s], (!PAIR && p.cluster2) ? 2 : 1);  // multicast-cluster mode: both CTAs' MMA warps release a stage
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&tmem_full[s], 1);
-            mbar_init(&tmem_empty[s], 4);  // one arrive per epilogue warp
+            mbar_init(&tmem_empty[s], PAIR ? 8 : 4);  // one arrive per epilogue warp (pair: of both CTAs, on the leader's barrier)
         }
         fence_barrier_init();
     }
     if (warp == 2) {
-        tmem_alloc(tmem_slot, TMEM_COLS);
-        tmem_relinquish();
+        if (PAIR) {
+            tmem_alloc2(tmem_slot, TMEM_COLS);
+            tmem_relinquish2();
+        } else {
+            tmem_alloc(tmem_slot, TMEM_COLS);
+            tmem_relinquish();
+        }
     }
     tc_fence_before();
     __syncthreads();
-    if (p.cluster2) cluster_sync_all();  // the peer's barriers are initialised before anything is multicast to them
+    if (PAIR || p.cluster2) cluster_sync_all();  // the peer's barriers are initialised before anything is multicast to them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     pdl_wait();  // everything above (barriers, TMEM, descriptor prefetch) overlaps the tail of the previous kernel
 
     const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+    const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;
 
     if (warp == 0) {
         // ===================================== TMA producer =====================================
@@ -221,6 +232,39 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* sa = smem + (size_t)stage * stage_bytes;
                     uint8_t* sb = sa + A_STAGE_BYTES;
+                    if (PAIR) {
+                        // Both CTAs' boxes complete on the LEADER's full barrier (the leader expects the bytes of both).
+                        // The peer may run ahead of the leader's expect_tx: its stage was released by the leader's MMA
+                        // commit, i.e. the barrier is already in the phase these bytes belong to, and a phase cannot complete
+                        // before the leader's own arrive.
+                        const uint32_t fb = mapa_u32(smem_u32(&full_bar[stage]), 0);
+                        if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], tx_bytes);
+                        const int kseg = p.kb_per_seg > 0 ? kb / p.kb_per_seg : 0;
+                        const int kbs = kb - kseg * p.kb_per_seg;
+                        if (p.a_mode == 0) {
+                            tma_load_2d_cg2(sa, &p.tmA, fb, kb * BLOCK_K, m0);
+                        } else if (p.a_mode == 1) {
+                            tma_load_2d_cg2(sa, &p.tmA, fb, m0, kbs * BLOCK_K);
+                            tma_load_2d_cg2(sa + 8192, &p.tmA, fb, m0 + 64, kbs * BLOCK_K);
+                        } else {
+                            const int tap = kb / p.kb_per_tap;
+                            const int cb = kb - tap * p.kb_per_tap;
+                            if (cb < p.kb_src1)
+                                tma_load_4d_cg2(sa, &p.tmA, fb, cb * BLOCK_K, cw + p.tap_dw[tap], ch + p.tap_dh[tap], cn + p.tap_dn[tap]);
+                            else
+                                tma_load_4d_cg2(sa, &p.tmA2, fb, (cb - p.kb_src1) * BLOCK_K, cw + p.tap_dw[tap], ch + p.tap_dh[tap],
+                                                cn + p.tap_dn[tap]);
+                        }
+                        if (p.b_mode == 0)
+                            tma_load_2d_cg2(sb, &p.tmBh, fb, kb * BLOCK_K, n0 + (int)cta_rank * (p.block_n >> 1));
+                        else
+                            tma_load_3d_cg2(sb, &p.tmBh, fb, 0, kb * BLOCK_K, (n0 >> 6) + (int)cta_rank * (p.block_n >> 7));
+                        if (++stage == p.stages) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                        continue;
+                    }
                     mbar_expect_tx(&full_bar[stage], tx_bytes);
                     // ---- A ----
                     int kseg = 0, kbs = kb;  // segment and k-block within it
@@ -275,8 +319,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
         }
     } else if (warp == 1) {
         // ===================================== MMA issuer =====================================
-        if (lane == 0) {
-            const uint32_t idesc = make_idesc_bf16(BLOCK_M, (uint32_t)p.block_n, p.a_mode == 1, p.b_mode == 1);
+        if (lane == 0 && cta_rank == 0) {
+            const uint32_t idesc = make_idesc_bf16(PAIR ? 2 * BLOCK_M : BLOCK_M, (uint32_t)p.block_n, p.a_mode == 1, p.b_mode == 1);
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
@@ -296,10 +340,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
                     const uint64_t bdesc = make_smem_desc(sb, p.b_lbo, p.b_sbo);
 #pragma unroll
                     for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-                        umma_bf16(d_tmem, adesc + (uint64_t)((k * p.a_kadv) >> 4), bdesc + (uint64_t)((k * p.b_kadv) >> 4),
-                                  idesc, (uint32_t)(kb != wi.kb0 || k != 0));
+                        if (PAIR)
+                            umma_bf16_cg2(d_tmem, adesc + (uint64_t)((k * p.a_kadv) >> 4), bdesc + (uint64_t)((k * p.b_kadv) >> 4),
+                                          idesc, (uint32_t)(kb != wi.kb0 || k != 0));
+                        else
+                            umma_bf16(d_tmem, adesc + (uint64_t)((k * p.a_kadv) >> 4), bdesc + (uint64_t)((k * p.b_kadv) >> 4),
+                                      idesc, (uint32_t)(kb != wi.kb0 || k != 0));
                     }
-                    if (p.cluster2)
+                    if (PAIR)
+                        umma_commit_cg2(&empty_bar[stage], (uint16_t)3);  // frees this stage in BOTH CTAs once the MMAs retire
+                    else if (p.cluster2)
                         umma_commit_multicast(&empty_bar[stage], (uint16_t)3);  // both producers may refill once we are done
                     else
                         umma_commit(&empty_bar[stage]);  // frees this smem stage once the MMAs retire
@@ -308,7 +358,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
                         phase ^= 1;
                     }
                 }
-                umma_commit(&tmem_full[acc]);  // accumulator ready for the epilogue
+                if (PAIR)
+                    umma_commit_cg2(&tmem_full[acc], (uint16_t)3);  // both CTAs' epilogues own half of the rows
+                else
+                    umma_commit(&tmem_full[acc]);  // accumulator ready for the epilogue
                 if (++acc == 2) {
                     acc = 0;
                     acc_phase ^= 1;
@@ -364,7 +417,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
                     if (ch == nchunks - 1) {  // accumulator fully read: hand it back to the MMA warp before the stores
                         tc_fence_before();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+                        if (lane == 0) {
+                            if (PAIR)
+                                mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty[acc]), 0));
+                            else
+                                mbar_arrive(&tmem_empty[acc]);
+                        }
                     }
                     uint8_t* sbuf = stg + buf * 4096;
                     // the TMA store that last used this buffer (two chunks ago) must have finished reading it
@@ -604,7 +662,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
             // release the accumulator buffer back to the MMA warp
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            if (lane == 0) {
+                if (PAIR)
+                    mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty[acc]), 0));
+                else
+                    mbar_arrive(&tmem_empty[acc]);
+            }
             if (++acc == 2) {
                 acc = 0;
                 acc_phase ^= 1;
@@ -614,16 +677,21 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
 
     tc_fence_before();
     __syncthreads();
-    if (p.cluster2) cluster_sync_all();  // no CTA leaves while its peer may still multicast into it / arrive on its barriers
+    if (PAIR || p.cluster2) cluster_sync_all();  // no CTA leaves while its peer may still multicast into it / arrive on its barriers
     if (warp == 2) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, TMEM_COLS);
+        if (PAIR)
+            tmem_dealloc2(tmem_base, TMEM_COLS);
+        else
+            tmem_dealloc(tmem_base, TMEM_COLS);
     }
 }
 
 // ----------------------------------------------------------------------------------------------
 // host side
 // ----------------------------------------------------------------------------------------------
+static bool num_tiles_ge(const GemmKernelArgs& p, int n) { return p.num_m_tiles * p.num_n_tiles >= n; }
+
 static int pick_block_n(long long N) {
     if (N <= 16) return 16;
     if (N <= 32) return 32;
@@ -838,12 +906,25 @@ extern "C" int uwu_gemm(const uwu_gemm_desc* d, void* stream_) {
             p.epi_tma = 1;
         }
     }
+    // CTA-pair eligibility (decided before the stream-K schedule: the schedule's workers are then clusters, its tiles pairs)
+    static int want_pair = -1, want_mc = -1;
+    if (want_pair < 0) {
+        const char* e = getenv("UWU_GEMM_PAIR");
+        want_pair = e ? atoi(e) : 2;  // 2: everywhere it fits; 1: not for the split-K (weight-gradient) schedules; 0: never
+        const char* e2 = getenv("UWU_GEMM_CLUSTER");
+        want_mc = e2 ? atoi(e2) : 0;  // multicast-only clusters: measured neutral in round 1, kept for comparison
+    }
+    const bool half_ok = d->b_layout == UWU_B_NK ? (bn % 16 == 0) : (p.b_3d && bn % 128 == 0);
+    const bool pair_shape_ok = d->k_segs <= 1 && d->grp_n == 0 && p.num_m_tiles >= 2 && half_ok && sm_count() % 2 == 0;
+    const bool sk_candidate = d->stream_k != 0 && p.out_fp32 && !d->bias && !d->bias_rows && !d->residual && p.num_kb >= 32;
+    const bool use_pair = want_pair && pair_shape_ok && (want_pair >= 2 || !sk_candidate);
+
     // stream-K: few output tiles but a long reduction (token-reduction weight gradients) would leave most SMs idle
-    const int n_tiles_all = p.num_m_tiles * p.num_n_tiles;
+    const int n_tiles_all = use_pair ? ((p.num_m_tiles + 1) / 2) * p.num_n_tiles : p.num_m_tiles * p.num_n_tiles;
     int sk = d->stream_k;
     p.sk_slices = 1;
     if (sk < 0 || sk == 2) {
-        const int sms = sm_count();
+        const int sms = use_pair ? sm_count() / 2 : sm_count();
         const bool ok = p.out_fp32 && !d->bias && !d->bias_rows && !d->residual && p.num_kb >= 32;
         const int waves = (n_tiles_all + sms - 1) / sms;
         const double operand_bytes = (double)p.num_kb * 64.0 * ((double)p.M + (double)p.N) * 2.0;
@@ -889,6 +970,37 @@ extern "C" int uwu_gemm(const uwu_gemm_desc* d, void* stream_) {
     }
     p.stream_k = sk;
 
+    // ---------------- CTA pair (cta_group::2) ----------------
+    // One 256 x block_n tile per cluster of two CTAs: every CTA stages its own 128 rows of A and HALF of the B tile, the
+    // leader issues M = 256 UMMAs.  Per FLOP that is a third less shared-memory fill traffic and half the B operand reads of
+    // the 1-CTA kernel (128 x 256 tiles).  UWU_GEMM_PAIR=0 falls back to the 1-CTA kernel everywhere.
+    p.pair = 0;
+    p.cluster2 = 0;
+    p.b_half_bytes = 0;
+    p.tmBh = p.tmB;
+    if ((use_pair || (want_mc && pair_shape_ok && !p.stream_k)) ) {
+        if (d->b_layout == UWU_B_NK) {
+            uint64_t dims[2] = {(uint64_t)d->K, (uint64_t)d->N};
+            uint64_t str[1] = {(uint64_t)d->ldb * 2};
+            uint32_t box[2] = {BLOCK_K, (uint32_t)(bn / 2)};
+            if (encode_tmap_bf16(&p.tmBh, d->b, 2, dims, str, box, 1)) return UWU_ERR_INVALID;
+            p.b_half_bytes = (bn / 2) * BLOCK_K * 2;
+        } else {
+            uint64_t dims[3] = {64, (uint64_t)d->K, (uint64_t)(d->N / 64)};
+            uint64_t str[2] = {(uint64_t)d->ldb * 2, 128};
+            uint32_t box[3] = {64, BLOCK_K, (uint32_t)(bn / 128)};
+            if (encode_tmap_bf16(&p.tmBh, d->b, 3, dims, str, box, 1)) return UWU_ERR_INVALID;
+            p.b_half_bytes = (bn / 128) * 8192;
+        }
+        if (use_pair) {
+            p.pair = 1;
+            p.b_stage_bytes = p.b_half_bytes;                       // each CTA holds only its half
+            p.tx_bytes = 2 * (A_STAGE_BYTES + p.b_half_bytes);      // both CTAs' boxes complete on the leader's barrier
+        } else if (num_tiles_ge(p, 2 * sm_count())) {
+            p.cluster2 = 1;
+        }
+    }
+
     // ---------------- launch ----------------
     const int stage_bytes = A_STAGE_BYTES + p.b_stage_bytes;
     const int smem_budget = 227 * 1024 - 1024 /*align slack*/ - 256 /*barriers*/ - EPI_STAGE_BYTES;
@@ -900,72 +1012,49 @@ extern "C" int uwu_gemm(const uwu_gemm_desc* d, void* stream_) {
 
     static bool attr_set = false;
     if (!attr_set) {
-        UWU_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        UWU_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        UWU_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
     }
-    const int num_tiles = p.num_m_tiles * p.num_n_tiles;
-    int grid = sm_count();
-    if (!p.stream_k && grid > num_tiles) grid = num_tiles;
-    if (p.stream_k == 1 && (long long)grid > (long long)num_tiles * p.num_kb) grid = (int)((long long)num_tiles * p.num_kb);
-    if (p.stream_k == 2 && (long long)grid > (long long)num_tiles * p.sk_slices) grid = num_tiles * p.sk_slices;
-    // 2-CTA clusters sharing each B tile through TMA multicast: a third less L2 -> shared-memory traffic per FLOP
-    p.cluster2 = 0;
-    p.b_half_bytes = 0;
-    p.tmBh = p.tmB;
-    {
-        static int want = -1;
-        if (want < 0) {
-            const char* e = getenv("UWU_GEMM_CLUSTER");
-            want = e ? atoi(e) : 0;  // measured neutral on B200 (1290 vs 1263 TFLOP/s isolated, equal in the step): off by default
-        }
-        const bool shape_ok = !p.stream_k && d->k_segs <= 1 && d->grp_n == 0 && num_tiles >= 2 * sm_count() && p.num_m_tiles >= 2 &&
-                              (d->b_layout == UWU_B_NK ? (bn % 16 == 0) : (p.b_3d && bn % 128 == 0)) && sm_count() % 2 == 0;
-        if (want && shape_ok) {
-            if (d->b_layout == UWU_B_NK) {
-                uint64_t dims[2] = {(uint64_t)d->K, (uint64_t)d->N};
-                uint64_t str[1] = {(uint64_t)d->ldb * 2};
-                uint32_t box[2] = {BLOCK_K, (uint32_t)(bn / 2)};
-                if (encode_tmap_bf16(&p.tmBh, d->b, 2, dims, str, box, 1)) return UWU_ERR_INVALID;
-                p.b_half_bytes = (bn / 2) * BLOCK_K * 2;
-            } else {
-                uint64_t dims[3] = {64, (uint64_t)d->K, (uint64_t)(d->N / 64)};
-                uint64_t str[2] = {(uint64_t)d->ldb * 2, 128};
-                uint32_t box[3] = {64, BLOCK_K, (uint32_t)(bn / 128)};
-                if (encode_tmap_bf16(&p.tmBh, d->b, 3, dims, str, box, 1)) return UWU_ERR_INVALID;
-                p.b_half_bytes = (bn / 128) * 8192;
-            }
-            p.cluster2 = 1;
-            grid = sm_count();
-        }
+    // workers = CTAs, or clusters of two CTAs walking (m-pair, n-tile) units
+    const bool clustered = p.pair || p.cluster2;
+    const long long work_tiles = clustered ? (long long)((p.num_m_tiles + 1) / 2) * p.num_n_tiles
+                                           : (long long)p.num_m_tiles * p.num_n_tiles;
+    long long workers = clustered ? sm_count() / 2 : sm_count();
+    if (!p.stream_k && workers > work_tiles) workers = work_tiles;
+    if (p.stream_k == 1 && workers > work_tiles * p.num_kb) workers = work_tiles * p.num_kb;
+    if (p.stream_k == 2 && workers > work_tiles * p.sk_slices) workers = work_tiles * p.sk_slices;
+    const int grid = (int)(clustered ? 2 * workers : workers);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (p.pair || p.cluster2) {
+        attr[na].id = cudaLaunchAttributeClusterDimension;
+        attr[na].val.clusterDim.x = 2;
+        attr[na].val.clusterDim.y = 1;
+        attr[na].val.clusterDim.z = 1;
+        ++na;
     }
-    if (p.cluster2) {
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(grid);
-        cfg.blockDim = dim3(NUM_THREADS);
-        cfg.dynamicSmemBytes = smem_bytes;
-        cfg.stream = stream;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = 2;
-        attr[0].val.clusterDim.y = 1;
-        attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = 1;
-        UWU_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel, p));
-        g_launches.fetch_add(1, std::memory_order_relaxed);
-    } else {
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(grid);
-        cfg.blockDim = dim3(NUM_THREADS);
-        cfg.dynamicSmemBytes = smem_bytes;
-        cfg.stream = stream;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
-        cfg.attrs = attr;
-        cfg.numAttrs = 1;
-        UWU_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel, p));
-        g_launches.fetch_add(1, std::memory_order_relaxed);
+    static int pair_pdl = -1;
+    if (pair_pdl < 0) {
+        const char* e = getenv("UWU_GEMM_PAIR_PDL");
+        pair_pdl = e ? atoi(e) : 1;
     }
+    if (!(p.pair || p.cluster2) || pair_pdl) {
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+        ++na;
+    }
+    cfg.attrs = attr;
+    cfg.numAttrs = na;
+    if (p.pair)
+        UWU_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<true>, p));
+    else
+        UWU_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<false>, p));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
     return UWU_OK;
 }

@@ -210,14 +210,15 @@ class RectifiedFlowLoss(DiffusionLoss):
         if sigmas is None:  # uniform_timestep: integer timesteps, sigma gathered from the table inside the kernel
             x_t, target, _e, t, sigma, _w, _temb = ops.noise_fwd(
                 x, tab, target_type="rectified_flow", pred_type=self.prediction_type, use_snr_weight=False, use_debiased=False,
-                gamma=self.min_snr_gamma, eps=noise, timesteps=timesteps, seed=self.seed, offset=self._step, want_eps=False)
+                gamma=self.min_snr_gamma, eps=noise, timesteps=timesteps, seed=self.seed, offset=self._step, want_eps=False,
+                step_dev=getattr(self, "_step_dev", None))
             t_idx, t_unet = t, t
         else:
             t_idx = torch.zeros((x.shape[0],), device=x.device, dtype=torch.int64)
             x_t, target, _e, _t, sigma, _w, _temb = ops.noise_fwd(
                 x, tab, target_type="rectified_flow", pred_type=self.prediction_type, use_snr_weight=False, use_debiased=False,
                 gamma=self.min_snr_gamma, eps=noise, timesteps=t_idx, seed=self.seed, offset=self._step, want_eps=False,
-                sigmas=sigmas)
+                sigmas=sigmas, step_dev=getattr(self, "_step_dev", None))
             t_unet = timesteps
         self._step += 1
         self._last_sigmas = sigma

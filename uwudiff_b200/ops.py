@@ -31,8 +31,17 @@ def _req_cuda(*ts):
             raise _lib.UwuError("uwudiff_b200 kernels need CUDA tensors (no CPU fallback)")
 
 
+_graph_launches = [0]
+
+
 def launch_count() -> int:
-    return int(lib().uwu_launch_count())
+    """Kernels of libuwu_b200.so launched so far: direct launches counted by the library + launches replayed through
+    captured CUDA graphs (the library only sees those once, at capture; the trainer adds them per replay)."""
+    return int(lib().uwu_launch_count()) + _graph_launches[0]
+
+
+def add_graph_launches(n: int) -> None:
+    _graph_launches[0] += int(n)
 
 
 # --------------------------------------------------------------------------------------------------

@@ -100,8 +100,19 @@ class FusedAdamW(torch.optim.Optimizer):
                 if p.grad is not None:
                     p.grad.zero_()
 
+    def hyper_values(self, group: int = 0):
+        """{lr, 1 - beta1^t, sqrt(1 - beta2^t)} of the NEXT step for a param group (what a graph-captured step reads from
+        device memory instead of taking by value)."""
+        g = self.param_groups[group]
+        # the C ABI takes the betas as fp32 and forms the corrections in double from those (uwu_mt_adamw): same values here
+        b1, b2 = (torch.tensor(b, dtype=torch.float32).item() for b in g["betas"])
+        t = self._step + 1
+        return [float(g["lr"]), 1.0 - b1 ** t, (1.0 - b2 ** t) ** 0.5]
+
     @torch.no_grad()
-    def step(self, closure=None):
+    def step(self, closure=None, hyper_dev=None):
+        """`hyper_dev`: optional list (one per param group that owns tables) of device fp32[3] tensors holding
+        `hyper_values()`; the kernels then read lr / bias corrections from device memory (CUDA-graph capture)."""
         loss = closure() if closure is not None else None
         if self._tables is not None:
             self._check_storage()
@@ -120,13 +131,14 @@ class FusedAdamW(torch.optim.Optimizer):
             clip = self._norm_out
             self.last_norm = self._norm_out
         self._step += 1
-        for t in self._tables:
+        for ti, t in enumerate(self._tables):
             g = self.param_groups[t["gi"]]
             b1, b2 = g["betas"]
+            hd = hyper_dev[ti].data_ptr() if hyper_dev is not None else None
             check(L.uwu_mt_adamw(t["p"].data_ptr(), t["g"].data_ptr(), t["m"].data_ptr(), t["v"].data_ptr(),
                                  t["numel"].data_ptr(), t["ct"].data_ptr(), t["ci"].data_ptr(), t["n_chunks"], _CHUNK,
                                  float(g["lr"]), float(b1), float(b2), float(g["eps"]), float(g["weight_decay"]),
-                                 self._step, clip.data_ptr() if clip is not None else None, stream), "uwu_mt_adamw")
+                                 self._step, clip.data_ptr() if clip is not None else None, hd, stream), "uwu_mt_adamw")
         return loss
 
     def state_dict(self):

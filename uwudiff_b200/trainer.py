@@ -174,6 +174,7 @@ class DMTrainer(BaseTrainer):
         else:
             self.loss = instantiate_any(loss_config)
         self.n_diffusion_time_steps = self.loss.n_diffusion_time_steps
+        self._hyper = None
         if type(self) is DMTrainer and any(p.requires_grad for p in self.loss.parameters()):
             raise ValueError("the loss module has trainable parameters (e.g. NNWeightedRFLoss.loss_pred_module) that DMTrainer's "
                              "optimizer would never see: use uwudiff_b200.trainer.NNWeightedLossTrainer")
@@ -224,12 +225,17 @@ class DMTrainer(BaseTrainer):
         added_cond["text_embeds"] = pooled_embedding
         return x, ctx, attn_mask, added_cond, cross_attn_kwargs
 
-    def training_step(self, batch, idx):
-        x, ctx, attn_mask, added_cond, cross_attn_kwargs = self.get_latent_and_conditioning(batch)
+    def training_step(self, batch, idx, _prepared=None):
+        x, ctx, attn_mask, added_cond, cross_attn_kwargs = _prepared or self.get_latent_and_conditioning(batch)
         loss, aux_output = self.loss(x, self.unet, encoder_hidden_states=ctx, encoder_attention_mask=attn_mask,
                                      added_cond_kwargs=added_cond, cross_attention_kwargs=cross_attn_kwargs)
-        ema_decay = min(self.global_step / (10 + self.global_step), self.ema_decay)
-        self.ema_loss = ema_decay * self.ema_loss + (1 - ema_decay) * loss.detach()  # stays on the device, no .item()
+        hyper = getattr(self, "_hyper", None)
+        if hyper is not None:  # CUDA-graph capture: the decay is a device scalar refreshed before every replay
+            d = hyper[-1, 0]
+            self.ema_loss.mul_(d).add_(loss.detach() * (1 - d))
+        else:
+            ema_decay = min(self.global_step / (10 + self.global_step), self.ema_decay)
+            self.ema_loss = ema_decay * self.ema_loss + (1 - ema_decay) * loss.detach()  # stays on the device, no .item()
         return {"loss": loss, "aux_output": aux_output}
 
     @torch.no_grad()
@@ -240,7 +246,7 @@ class DMTrainer(BaseTrainer):
 
     # ---- what Lightning's fit loop did around training_step -----------------------------------------------------
     def setup_fit(self, gradient_clip_val: Optional[float] = None, process_group=None, seed: Optional[int] = None,
-                  n_buckets: int = 4, accumulate_grad_batches: int = 1):
+                  n_buckets: int = 4, accumulate_grad_batches: int = 1, cuda_graph: bool = False, graph_warmup_steps: int = 2):
         """`accumulate_grad_batches` is Lightning's Trainer option of the same name (the `lightning_config` block of the YAMLs
         is passed to pl.Trainer verbatim): k micro-batches share one optimizer step, each loss scaled by 1/k; the gradient
         exchange runs once, during the last micro-batch's backward (BASELINE.json configs[4]: global batch 128 on fewer GPUs
@@ -259,13 +265,33 @@ class DMTrainer(BaseTrainer):
         if seed is not None:
             rank = torch.distributed.get_rank() if (torch.distributed.is_available() and torch.distributed.is_initialized()) else 0
             self.loss.seed = int(seed) + rank  # pl.seed_everything(seed + global_rank), test_scripts/test_train.py:68-69
-        self._fit = dict(opt=opt, sched=sched, buckets=buckets, accum=max(1, int(accumulate_grad_batches)), micro=0)
+        self._fit = dict(opt=opt, sched=sched, buckets=buckets, accum=max(1, int(accumulate_grad_batches)), micro=0, graph=None)
+        if cuda_graph:
+            from .optim import FusedAdamW
+
+            if not isinstance(opt, FusedAdamW):
+                raise NotImplementedError("cuda_graph=True needs the fused AdamW (its lr / step are read from device memory)")
+            self._fit["graph"] = dict(state="warmup", seen=0, warm=max(1, int(graph_warmup_steps)))
         return self._fit
 
     def fit_step(self, batch, idx: int = 0):
-        """forward + backward + (DDP all-reduce) + clip + optimizer + lr schedule for one batch; returns the step dict."""
+        """forward + backward + (DDP all-reduce) + clip + optimizer + lr schedule for one batch; returns the step dict.
+        With `setup_fit(cuda_graph=True)` the first `graph_warmup_steps` optimizer steps run eagerly, then forward + backward
+        and clip + AdamW are captured once as two CUDA graphs and replayed (shapes are static)."""
         if self._fit is None:
             self.setup_fit()
+        f = self._fit
+        g = f["graph"]
+        if g is None or g["state"] == "warmup":
+            out, stepped = self._fit_step_eager(batch, idx)
+            if g is not None and stepped:
+                g["seen"] += 1
+                if g["seen"] >= g["warm"]:
+                    g["state"] = "capture"
+            return out
+        return self._fit_step_graph(batch, idx)
+
+    def _fit_step_eager(self, batch, idx: int = 0):
         f = self._fit
         k = f["accum"]
         last = (f["micro"] + 1) % k == 0
@@ -277,7 +303,7 @@ class DMTrainer(BaseTrainer):
         (out["loss"] if k == 1 else out["loss"] / k).backward()
         f["micro"] += 1
         if not last:
-            return out
+            return out, False
         if f["buckets"] is not None:
             f["buckets"].finish()
         f["opt"].step()
@@ -288,7 +314,93 @@ class DMTrainer(BaseTrainer):
         else:
             f["opt"].zero_grad(set_to_none=False)  # gradients keep their (flat) storage
         self.global_step += 1
-        return out
+        return out, True
+
+    # ---- CUDA-graph replay of the step ---------------------------------------------------------------------------
+    def _graph_capture(self, prepared):
+        """Capture (a) noising -> UNet forward -> loss -> backward -> EMA and (b) clip + AdamW + gradient reset.  Everything
+        that changes from step to step is read from device memory: the noise-stream position (`loss._step_dev`, advanced
+        inside graph (a)), lr / bias corrections / EMA decay (`self._hyper`, refreshed by a small H2D copy before each replay),
+        the inputs (static buffers the batch is copied into)."""
+        from . import ops
+
+        f = self._fit
+        g = f["graph"]
+        x, ctx, attn_mask, added_cond, cak = prepared
+        dev = x.device
+        g["x"] = x.clone()
+        g["ctx"] = None if ctx is None else ctx.clone()
+        g["added"] = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in added_cond.items()}
+        g["mask"], g["cak"] = attn_mask, cak
+        n_groups = len(f["opt"].param_groups)
+        self._hyper = torch.zeros((n_groups + 1, 4), device=dev, dtype=torch.float32)
+        self._write_hyper()
+        self.loss._step_dev = torch.zeros((1,), device=dev, dtype=torch.int64)
+        if f["buckets"] is not None:
+            f["buckets"].enabled = False  # the exchange runs between the two graphs, on the flat gradient buffer
+        k = f["accum"]
+        torch.cuda.synchronize()
+        torch.cuda.empty_cache()  # the graphs' private pool needs the room the eager steps' cached blocks occupy
+        n0 = ops.launch_count()
+        ga = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(ga):
+            out = self.training_step(None, 0, _prepared=(g["x"], g["ctx"], g["mask"], g["added"], g["cak"]))
+            (out["loss"] if k == 1 else out["loss"] / k).backward()
+            self.loss._step_dev += 1
+        n1 = ops.launch_count()
+        gb = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gb, pool=ga.pool()):
+            tables = f["opt"]._tables or []
+            f["opt"].step(hyper_dev=[self._hyper[t["gi"]] for t in tables] if tables else None)
+            f["opt"]._step -= 1  # capture does not execute: the counter advances once per replay (below)
+            if self.lycoris_model is not None:
+                self.lycoris_model.zero_grad()
+            else:
+                f["opt"].zero_grad(set_to_none=False)
+        n2 = ops.launch_count()
+        g.update(fwdbwd=ga, optstep=gb, n_fwdbwd=n1 - n0, n_opt=n2 - n1, out=out, state="replay")
+
+    def _write_hyper(self):
+        """[lr, 1 - b1^t, sqrt(1 - b2^t), 0] per param group + [ema decay, 0, 0, 0]: one pinned H2D copy per step."""
+        opt = self._fit["opt"]
+        rows = [opt.hyper_values(gi) + [0.0] for gi in range(len(opt.param_groups))]
+        rows.append([min(self.global_step / (10 + self.global_step), self.ema_decay), 0.0, 0.0, 0.0])
+        self._hyper.copy_(torch.tensor(rows, dtype=torch.float32).pin_memory(), non_blocking=True)
+
+    def _fit_step_graph(self, batch, idx: int = 0):
+        from . import ops
+
+        f = self._fit
+        g = f["graph"]
+        prepared = self.get_latent_and_conditioning(batch)
+        if g["state"] == "capture":
+            if f["opt"]._tables is None:
+                raise RuntimeError("cuda_graph: the optimizer has not stepped yet (graph_warmup_steps >= 1)")
+            self._graph_capture(prepared)
+        x, ctx, _mask, added_cond, _cak = prepared
+        g["x"].copy_(x, non_blocking=True)
+        if ctx is not None:
+            g["ctx"].copy_(ctx, non_blocking=True)
+        for kk, v in added_cond.items():
+            if torch.is_tensor(v):
+                g["added"][kk].copy_(v, non_blocking=True)
+        k = f["accum"]
+        last = (f["micro"] + 1) % k == 0
+        self._write_hyper()
+        g["fwdbwd"].replay()
+        ops.add_graph_launches(g["n_fwdbwd"])
+        f["micro"] += 1
+        if not last:
+            return g["out"]
+        if f["buckets"] is not None:
+            f["buckets"]._reduce(f["buckets"].flat)  # one exchange of the whole flat buffer, ordered on this stream
+        g["optstep"].replay()
+        ops.add_graph_launches(g["n_opt"])
+        f["opt"]._step += 1
+        if f["sched"] is not None:
+            f["sched"].step()
+        self.global_step += 1
+        return g["out"]
 
     # ---- checkpoint / resume of what Lightning's .ckpt carries besides the weights ----------------------------------
     def fit_state_dict(self) -> Dict[str, Any]:
