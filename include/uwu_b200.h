@@ -96,6 +96,15 @@ typedef struct uwu_gemm_desc {
     int32_t grp_n, a_grp_koff;
     /* diagnostics: override shared-memory descriptor fields (0 = default) */
     int32_t dbg_a_lbo, dbg_a_sbo, dbg_a_kadv, dbg_b_lbo, dbg_b_sbo, dbg_b_kadv;
+    /* fused GEGLU epilogues (diffusers GEGLU: hidden, gate = proj(x).chunk(2, -1); hidden * gelu(gate) — the FeedForward of
+       BasicTransformerBlock, src/duwu/modules/rope_unet.py:395-404), CTA-pair kernel only (M >= 256), bf16 output:
+       1 = forward  : N = 2F; `out` [M, 2F] receives the pre-activation (h | g), `out2` [M, F] receives h * gelu(g);
+       2 = backward : N = F, the GEMM result is d = dL/d(h * gelu(g)); `aux` = saved pre-activation [M, ld_aux >= 2F];
+                      `out` [M, 2F] receives (d * gelu(g) | d * h * gelu'(g)).
+       Results are bit-identical to uwu_gemm followed by uwu_geglu_fwd / uwu_geglu_bwd. */
+    int32_t epi_mode;
+    const void* aux;
+    int64_t ld_aux;
 } uwu_gemm_desc;
 
 int uwu_gemm(const uwu_gemm_desc* desc, void* stream);

@@ -423,6 +423,10 @@ def _req_cuda(*ts):
     pass
 
 
+def geglu_fusable(M, F):
+    return False  # the fused GEGLU epilogues exist only in the CUDA GEMM kernel
+
+
 def launch_count():
     return _launches[0]
 
@@ -430,7 +434,7 @@ def launch_count():
 PATCHED = ["gemm", "conv3x3_nhwc", "attn_fwd", "attn_bwd", "groupnorm_fwd", "groupnorm_bwd", "layernorm_fwd", "layernorm_bwd",
            "geglu_fwd", "geglu_bwd", "elementwise", "nchw_to_nhwc", "nhwc_to_nchw", "upsample2x", "phase_split2", "colsum",
            "fold_lokr", "fold_lora", "axpy_f32", "lokr_grad", "lora_grad", "copy2d", "sincos_embed", "_workspace", "noise_fwd",
-           "wmse_fwd", "wmse_bwd", "pred_convert", "launch_count", "_req_cuda", "im2col3x3", "conv_wgrad_unpack", "colsum_groups", "conv_pack"]
+           "wmse_fwd", "wmse_bwd", "pred_convert", "geglu_fusable", "launch_count", "_req_cuda", "im2col3x3", "conv_wgrad_unpack", "colsum_groups", "conv_pack"]
 
 
 def install(monkeypatch):

@@ -499,3 +499,33 @@ def test_fused_adamw_and_clip_match_torch():
         assert abs(float(opt.last_norm[0]) - norm_ref.item()) < 1e-4 * norm_ref.item()
         for p, r in zip(ps, rs):
             assert relerr(p.detach(), r.detach()) < 1e-5
+
+
+@pytest.mark.parametrize("M,C,F", [(16384, 1280, 5120), (4096, 640, 2560), (300, 64, 256), (256, 128, 512)])
+def test_fused_geglu_epilogues_are_bit_identical_to_the_unfused_kernels(M, C, F):
+    """GEGLU in the GEMM epilogues (CTA-pair kernel): up-projection + h * gelu(g), and the down-projection's data gradient
+    + GEGLU backward, against uwu_gemm followed by uwu_geglu_fwd / uwu_geglu_bwd — same MMA order, same roundings."""
+    from uwudiff_b200 import ops
+    from uwudiff_b200._lib import B_KN
+
+    if not ops.geglu_fusable(M, F):
+        pytest.skip("fused GEGLU disabled (UWU_GEGLU_FUSE=0 / UWU_GEMM_PAIR=0)")
+    g = torch.Generator(device="cuda").manual_seed(M + F)
+    x = (torch.randn(M, C, device="cuda", generator=g) * 0.5).to(torch.bfloat16)
+    w1 = (torch.randn(2 * F, C, device="cuda", generator=g) * C ** -0.5).to(torch.bfloat16)
+    b1 = torch.randn(2 * F, device="cuda", generator=g) * 0.1
+    p_ref = ops.gemm(x, w1, M, 2 * F, C, bias=b1)
+    act_ref = ops.geglu_fwd(p_ref)
+    p, act = ops.gemm_geglu_fwd(x, w1, M, F, C, b1)
+    assert torch.equal(p, p_ref) and torch.equal(act, act_ref)
+    # and against fp32 torch (erf GELU): the kernels use a 1.5e-7-accurate erf
+    ref32 = torch.nn.functional.linear(x.float(), w1.float(), b1)
+    h32, g32 = ref32.chunk(2, -1)
+    a32 = h32 * torch.nn.functional.gelu(g32)
+    assert ((act.float() - a32).abs().max() / a32.abs().max()).item() < 8e-3
+    dy = (torch.randn(M, C, device="cuda", generator=g) * 0.5).to(torch.bfloat16)
+    w2 = (torch.randn(C, F, device="cuda", generator=g) * F ** -0.5).to(torch.bfloat16)  # down projection [out = C, in = F]
+    d_ref = ops.gemm(dy, w2, M, F, C, b_layout=B_KN, ldb=F)
+    dp_ref = ops.geglu_bwd(p_ref, d_ref)
+    dp = ops.gemm_geglu_bwd(dy, w2, p, M, F, C)
+    assert torch.equal(dp, dp_ref)

@@ -8,6 +8,7 @@ echo "== sdxl parity"; timeout 1200 python -m pytest tests/test_sdxl_parity_gpu.
 echo "== perfw pair=1 / 2"
 UWU_GEMM_PAIR=1 timeout 300 python tools/diag_gemm.py perfw > $O/perfw_pair1.log 2>&1; cat $O/perfw_pair1.log
 UWU_GEMM_PAIR=2 timeout 300 python tools/diag_gemm.py perfw > $O/perfw_pair2.log 2>&1; cat $O/perfw_pair2.log
+echo "== bench weak graph off, unfused GEGLU"; UWU_GEGLU_FUSE=0 timeout 900 python bench.py --steps 5 --warmup 3 --scaling weak --no-cpu-baseline --graph off > $O/bench_weak_nograph_nofuse.json 2> $O/bench_weak_nograph_nofuse.err; cut -c1-200 $O/bench_weak_nograph_nofuse.json; tail -3 $O/bench_weak_nograph_nofuse.err
 echo "== bench weak graph off"; timeout 900 python bench.py --steps 5 --warmup 3 --scaling weak --no-cpu-baseline --graph off > $O/bench_weak_nograph.json 2> $O/bench_weak_nograph.err; cut -c1-300 $O/bench_weak_nograph.json; tail -3 $O/bench_weak_nograph.err
 echo "== bench weak graph on"; timeout 900 python bench.py --steps 5 --warmup 3 --scaling weak --no-cpu-baseline --graph on > $O/bench_weak_graph.json 2> $O/bench_weak_graph.err; cut -c1-300 $O/bench_weak_graph.json; tail -5 $O/bench_weak_graph.err
 echo "== breakdown"; timeout 600 python tools/step_breakdown.py > $O/breakdown.log 2>&1; head -24 $O/breakdown.log

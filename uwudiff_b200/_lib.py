@@ -39,6 +39,7 @@ class GemmDesc(C.Structure):
         ("k_segs", C.c_int32), ("a_seg_off", C.c_int32), ("b_seg_off", C.c_int32), ("grp_n", C.c_int32), ("a_grp_koff", C.c_int32),
         ("dbg_a_lbo", C.c_int32), ("dbg_a_sbo", C.c_int32), ("dbg_a_kadv", C.c_int32),
         ("dbg_b_lbo", C.c_int32), ("dbg_b_sbo", C.c_int32), ("dbg_b_kadv", C.c_int32),
+        ("epi_mode", C.c_int32), ("aux", C.c_void_p), ("ld_aux", C.c_int64),
     ]
 
 

@@ -72,6 +72,10 @@ struct GemmKernelArgs {
     int cluster2;      // 1: launched as 2-CTA clusters sharing every B tile (same n-tile, adjacent m-tiles)
     int b_half_bytes;  // shared-memory offset of the second half of a B stage
     int b_3d;  // MN-major B through a 3-D tensor map {64 n, K, N/64}: ONE TMA instruction per stage instead of block_n/64
+    // fused GEGLU epilogues (pair kernel): 1 forward (N = 2F: TMEM columns [0,128) = h, [128,256) = g of 128 hidden units),
+    // 2 backward (N = F: the tile's dg is combined with h, g read from the saved pre-activation `aux`)
+    int epi_mode, geglu_f, epi_warp_bytes;
+    CUtensorMap tmAux;  // mode 2: pre-activation [M, 2F], box {64 columns, 32 rows}, 128B swizzle
     int pair;      // 1: CTA-pair kernel (cta_group::2): one 256 x block_n tile per cluster of two CTAs; each CTA stages its
                    //    own 128 rows of A and HALF of the B tile, the leader CTA issues M = 256 UMMAs for both
     int stream_k;  // 1: the (tile, k-block) space is cut into equal contiguous ranges, one per CTA; partial tiles are
@@ -159,12 +163,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int stage_bytes = A_STAGE_BYTES + p.b_stage_bytes;
     uint8_t* epi_stage = smem + (size_t)p.stages * stage_bytes;  // 1024-byte aligned (stage sizes are multiples of 1024)
-    uint8_t* bar_base = epi_stage + EPI_STAGE_BYTES;
+    uint8_t* bar_base = epi_stage + 4 * p.epi_warp_bytes;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(bar_base);
     uint64_t* empty_bar = full_bar + MAX_STAGES;
     uint64_t* tmem_full = empty_bar + MAX_STAGES;  // [2]
     uint64_t* tmem_empty = tmem_full + 2;          // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    uint64_t* epi_bar = tmem_empty + 2;            // [4] one per epilogue warp (TMA loads of epilogue operands)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(epi_bar + 4);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -177,6 +182,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
             tma_prefetch_desc(&p.tmO);
             tma_prefetch_desc(&p.tmO2);
         }
+        if (p.epi_mode == 2) tma_prefetch_desc(&p.tmAux);
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < p.stages; ++s) {
@@ -187,6 +193,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
             mbar_init(&tmem_full[s], 1);
             mbar_init(&tmem_empty[s], PAIR ? 8 : 4);  // one arrive per epilogue warp (pair: of both CTAs, on the leader's barrier)
         }
+        for (int s = 0; s < 4; ++s) mbar_init(&epi_bar[s], 1);
         fence_barrier_init();
     }
     if (warp == 2) {
@@ -255,7 +262,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
                                 tma_load_4d_cg2(sa, &p.tmA2, fb, (cb - p.kb_src1) * BLOCK_K, cw + p.tap_dw[tap], ch + p.tap_dh[tap],
                                                 cn + p.tap_dn[tap]);
                         }
-                        if (p.b_mode == 0)
+                        if (p.epi_mode == 1)  // leader stages the 128 h rows of W, the peer the matching 128 g rows
+                            tma_load_2d_cg2(sb, &p.tmBh, fb, kb * BLOCK_K, (int)cta_rank * p.geglu_f + n_blk * 128);
+                        else if (p.b_mode == 0)
                             tma_load_2d_cg2(sb, &p.tmBh, fb, kb * BLOCK_K, n0 + (int)cta_rank * (p.block_n >> 1));
                         else
                             tma_load_3d_cg2(sb, &p.tmBh, fb, 0, kb * BLOCK_K, (n0 >> 6) + (int)cta_rank * (p.block_n >> 7));
@@ -381,9 +390,177 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
             // Each warp owns 32 rows and works in 64-column chunks through two private 4 KiB staging buffers; the store of
             // chunk c overlaps the math of chunk c+1.  Residual rows are read with fully coalesced 16-byte loads (4 rows
             // per warp instruction, one chunk ahead), transposed through the same staging buffer.
-            uint8_t* stg = epi_stage + sub * 8192;
+            uint8_t* stg = epi_stage + sub * p.epi_warp_bytes;
             const int lrow = lane >> 3, lchk = lane & 7;  // coalesced residual layout: 4 rows x 8 16-byte chunks per instruction
             int buf = 0;
+            if (PAIR && p.epi_mode == 1) {
+                // ---- GEGLU forward: pre-activation (h | g) -> `out`, h * gelu(g) -> `out2`; three staged TMA stores per
+                // 64 hidden units (diffusers GEGLU.forward: hidden, gate = proj(x).chunk(2); hidden * gelu(gate)) ----
+                uint8_t *sH = stg, *sG = stg + 4096, *sA = stg + 8192;
+                while (wi.next()) {
+                    const int tile = wi.tile;
+                    const int n_blk = tile % p.num_n_tiles;
+                    const int m_blk = tile / p.num_n_tiles;
+                    const int row0 = m_blk * BLOCK_M + sub * 32;
+                    const int hcol0 = n_blk * 128;
+                    mbar_wait(&tmem_full[acc], acc_phase);
+                    tc_fence_after();
+                    const uint32_t t_row = tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(acc * ACC_STRIDE);
+                    for (int c = 0; c < 2; ++c) {
+#pragma unroll 1
+                        for (int hh = 0; hh < 2; ++hh) {
+                            uint32_t rh[32], rg[32];
+                            tmem_ld32(t_row + (uint32_t)(c * 64 + hh * 32), rh);
+                            tmem_ld32(t_row + (uint32_t)(128 + c * 64 + hh * 32), rg);
+                            tmem_ld_wait();
+                            if (c == 1 && hh == 1) {  // accumulator fully read
+                                tc_fence_before();
+                                __syncwarp();
+                                if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty[acc]), 0));
+                            }
+                            if (hh == 0) {
+                                if (lane == 0) bulk_wait_group_read0();  // the previous chunk's three stores have read their buffers
+                                __syncwarp();
+                            }
+                            const int cc = hcol0 + c * 64 + hh * 32;
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                float h[8], g[8], a[8];
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) {
+                                    h[j] = __uint_as_float(rh[q * 8 + j]) * p.alpha;
+                                    g[j] = __uint_as_float(rg[q * 8 + j]) * p.alpha;
+                                }
+                                if (p.bias != nullptr) {
+                                    const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + cc + q * 8));
+                                    const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + cc + q * 8 + 4));
+                                    const float4 c0 = __ldg(reinterpret_cast<const float4*>(p.bias + p.geglu_f + cc + q * 8));
+                                    const float4 c1 = __ldg(reinterpret_cast<const float4*>(p.bias + p.geglu_f + cc + q * 8 + 4));
+                                    h[0] += b0.x; h[1] += b0.y; h[2] += b0.z; h[3] += b0.w; h[4] += b1.x; h[5] += b1.y; h[6] += b1.z; h[7] += b1.w;
+                                    g[0] += c0.x; g[1] += c0.y; g[2] += c0.z; g[3] += c0.w; g[4] += c1.x; g[5] += c1.y; g[6] += c1.z; g[7] += c1.w;
+                                }
+                                uint4 oh, og, oa;
+                                oh.x = pack_bf16(h[0], h[1]); oh.y = pack_bf16(h[2], h[3]); oh.z = pack_bf16(h[4], h[5]); oh.w = pack_bf16(h[6], h[7]);
+                                og.x = pack_bf16(g[0], g[1]); og.y = pack_bf16(g[2], g[3]); og.z = pack_bf16(g[4], g[5]); og.w = pack_bf16(g[6], g[7]);
+                                // the activation is formed from the bf16-rounded pre-activation, exactly what the unfused
+                                // kernel (and the backward pass, which re-reads it) sees
+                                float2 t;
+                                t = unpack_bf16(oh.x); h[0] = t.x; h[1] = t.y; t = unpack_bf16(oh.y); h[2] = t.x; h[3] = t.y;
+                                t = unpack_bf16(oh.z); h[4] = t.x; h[5] = t.y; t = unpack_bf16(oh.w); h[6] = t.x; h[7] = t.y;
+                                t = unpack_bf16(og.x); g[0] = t.x; g[1] = t.y; t = unpack_bf16(og.y); g[2] = t.x; g[3] = t.y;
+                                t = unpack_bf16(og.z); g[4] = t.x; g[5] = t.y; t = unpack_bf16(og.w); g[6] = t.x; g[7] = t.y;
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) a[j] = h[j] * gelu_fast_f(g[j]);
+                                oa.x = pack_bf16(a[0], a[1]); oa.y = pack_bf16(a[2], a[3]); oa.z = pack_bf16(a[4], a[5]); oa.w = pack_bf16(a[6], a[7]);
+                                const int off = lane * 128 + (((hh * 4 + q) ^ (lane & 7)) << 4);
+                                *reinterpret_cast<uint4*>(sH + off) = oh;
+                                *reinterpret_cast<uint4*>(sG + off) = og;
+                                *reinterpret_cast<uint4*>(sA + off) = oa;
+                            }
+                        }
+                        fence_proxy_async();
+                        __syncwarp();
+                        if (lane == 0) {
+                            tma_store_2d(&p.tmO, sH, hcol0 + c * 64, row0);
+                            tma_store_2d(&p.tmO, sG, p.geglu_f + hcol0 + c * 64, row0);
+                            tma_store_2d(&p.tmO2, sA, hcol0 + c * 64, row0);
+                            bulk_commit_group();
+                        }
+                    }
+                    if (++acc == 2) {
+                        acc = 0;
+                        acc_phase ^= 1;
+                    }
+                }
+                if (lane == 0) bulk_wait_group0();
+            } else if (PAIR && p.epi_mode == 2) {
+                // ---- GEGLU backward: the tile is d = dL/d(h * gelu(g)); with h, g from the saved pre-activation (TMA loads into
+                // the warp's staging buffers): dh = d * gelu(g) -> out[:, n], dg = d * h * gelu'(g) -> out[:, F + n] ----
+                uint8_t *iH = stg, *iG = stg + 4096, *oH = stg + 8192, *oG = stg + 12288;
+                uint32_t ephase = 0;
+                while (wi.next()) {
+                    const int tile = wi.tile;
+                    const int n_blk = tile % p.num_n_tiles;
+                    const int m_blk = tile / p.num_n_tiles;
+                    const int row0 = m_blk * BLOCK_M + sub * 32;
+                    const int n0 = n_blk * p.block_n;
+                    const int nchunks = p.block_n >> 6;
+                    if (lane == 0) {
+                        mbar_expect_tx(&epi_bar[sub], 8192);
+                        tma_load_2d(iH, &p.tmAux, &epi_bar[sub], n0, row0);
+                        tma_load_2d(iG, &p.tmAux, &epi_bar[sub], p.geglu_f + n0, row0);
+                    }
+                    mbar_wait(&tmem_full[acc], acc_phase);
+                    tc_fence_after();
+                    const uint32_t t_row = tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(acc * ACC_STRIDE);
+                    for (int ch = 0; ch < nchunks; ++ch) {
+                        const int col0 = n0 + ch * 64;
+                        uint32_t r[2][32];
+                        tmem_ld32(t_row + (uint32_t)(ch * 64), r[0]);
+                        tmem_ld32(t_row + (uint32_t)(ch * 64 + 32), r[1]);
+                        tmem_ld_wait();
+                        if (ch == nchunks - 1) {
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty[acc]), 0));
+                        }
+                        mbar_wait(&epi_bar[sub], ephase);
+                        ephase ^= 1;
+                        uint4 vh[8], vg[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const int off = lane * 128 + ((j ^ (lane & 7)) << 4);
+                            vh[j] = *reinterpret_cast<const uint4*>(iH + off);
+                            vg[j] = *reinterpret_cast<const uint4*>(iG + off);
+                        }
+                        __syncwarp();  // every lane has its h / g rows in registers: the input buffers may be refilled
+                        fence_proxy_async();
+                        if (lane == 0 && ch + 1 < nchunks) {
+                            mbar_expect_tx(&epi_bar[sub], 8192);
+                            tma_load_2d(iH, &p.tmAux, &epi_bar[sub], col0 + 64, row0);
+                            tma_load_2d(iG, &p.tmAux, &epi_bar[sub], p.geglu_f + col0 + 64, row0);
+                        }
+                        if (lane == 0) bulk_wait_group_read0();  // the previous chunk's stores have read the output buffers
+                        __syncwarp();
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            float h[8], g[8], dh[8], dg[8];
+                            float2 t;
+                            t = unpack_bf16(vh[j].x); h[0] = t.x; h[1] = t.y; t = unpack_bf16(vh[j].y); h[2] = t.x; h[3] = t.y;
+                            t = unpack_bf16(vh[j].z); h[4] = t.x; h[5] = t.y; t = unpack_bf16(vh[j].w); h[6] = t.x; h[7] = t.y;
+                            t = unpack_bf16(vg[j].x); g[0] = t.x; g[1] = t.y; t = unpack_bf16(vg[j].y); g[2] = t.x; g[3] = t.y;
+                            t = unpack_bf16(vg[j].z); g[4] = t.x; g[5] = t.y; t = unpack_bf16(vg[j].w); g[6] = t.x; g[7] = t.y;
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) {
+                                // the unfused path rounds d to bf16 between the GEMM and the GEGLU kernel: same here
+                                const float d = __bfloat162float(__float2bfloat16(__uint_as_float(r[j >> 2][(j & 3) * 8 + e]) * p.alpha));
+                                float cdf, pdf;
+                                gelu_cdf_pdf(g[e], cdf, pdf);
+                                dh[e] = d * g[e] * cdf;
+                                dg[e] = d * h[e] * fmaf(g[e], pdf, cdf);
+                            }
+                            uint4 uh, ug;
+                            uh.x = pack_bf16(dh[0], dh[1]); uh.y = pack_bf16(dh[2], dh[3]); uh.z = pack_bf16(dh[4], dh[5]); uh.w = pack_bf16(dh[6], dh[7]);
+                            ug.x = pack_bf16(dg[0], dg[1]); ug.y = pack_bf16(dg[2], dg[3]); ug.z = pack_bf16(dg[4], dg[5]); ug.w = pack_bf16(dg[6], dg[7]);
+                            const int off = lane * 128 + ((j ^ (lane & 7)) << 4);
+                            *reinterpret_cast<uint4*>(oH + off) = uh;
+                            *reinterpret_cast<uint4*>(oG + off) = ug;
+                        }
+                        fence_proxy_async();
+                        __syncwarp();
+                        if (lane == 0) {
+                            tma_store_2d(&p.tmO, oH, col0, row0);
+                            tma_store_2d(&p.tmO, oG, p.geglu_f + col0, row0);
+                            bulk_commit_group();
+                        }
+                    }
+                    if (++acc == 2) {
+                        acc = 0;
+                        acc_phase ^= 1;
+                    }
+                }
+                if (lane == 0) bulk_wait_group0();
+            } else {
             while (wi.next()) {
                 const int tile = wi.tile;
                 const int n_blk = tile % p.num_n_tiles;
@@ -529,6 +706,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
                 }
             }
             if (lane == 0) bulk_wait_group0();  // all stores have landed before the CTA releases its shared memory
+            }
         } else
         while (wi.next()) {
             const int tile = wi.tile;
@@ -729,10 +907,30 @@ extern "C" int uwu_gemm(const uwu_gemm_desc* d, void* stream_) {
     p.M = (int)d->M;
     p.N = (int)d->N;
     int bn = d->block_n > 0 ? d->block_n : pick_block_n(d->N);
+    p.epi_mode = d->epi_mode;
+    p.geglu_f = 0;
+    p.epi_warp_bytes = 8192;
+    if (d->epi_mode != 0) {
+        UWU_CHECK_ARG(d->epi_mode == 1 || d->epi_mode == 2, "uwu_gemm: bad epi_mode %d", d->epi_mode);
+        UWU_CHECK_ARG(d->out_dtype == UWU_BF16 && !d->residual && !d->bias_rows && !d->accumulate && d->k_segs <= 1 && d->grp_n == 0,
+                      "uwu_gemm: the fused GEGLU epilogues take a bf16 output and no residual / bias_rows / accumulate");
+        bn = 256;
+        if (d->epi_mode == 1) {
+            UWU_CHECK_ARG(d->N % 256 == 0 && d->b_layout == UWU_B_NK && d->out2 != nullptr,
+                          "uwu_gemm(GEGLU fwd): N = 2F with F a multiple of 128, K-major weights and out2 are required");
+            p.geglu_f = (int)(d->N / 2);
+            p.epi_warp_bytes = 12288;
+        } else {
+            UWU_CHECK_ARG(d->N % 256 == 0 && d->aux != nullptr && d->ld_aux % 8 == 0 && d->out2 == nullptr && !d->bias,
+                          "uwu_gemm(GEGLU bwd): N = F must be a multiple of 256; aux (the saved pre-activation) is required");
+            p.geglu_f = (int)d->N;
+            p.epi_warp_bytes = 16384;
+        }
+    }
     UWU_CHECK_ARG(bn % 16 == 0 && bn >= 16 && bn <= 256, "uwu_gemm: block_n %d must be a multiple of 16 in [16,256]", bn);
     p.block_n = bn;
     p.num_m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
-    p.num_n_tiles = (p.N + bn - 1) / bn;
+    p.num_n_tiles = d->epi_mode == 1 ? p.geglu_f / 128 : (p.N + bn - 1) / bn;
     p.a_mode = d->a_layout;
     p.b_mode = d->b_layout;
     p.kb_per_seg = 0; p.a_seg_off = 0; p.b_seg_off = 0; p.b_3d = 0;
@@ -875,8 +1073,8 @@ extern "C" int uwu_gemm(const uwu_gemm_desc* d, void* stream_) {
     p.ldo = d->ldo > 0 ? d->ldo : d->N;
     p.out2 = d->out2;
     p.ldo2 = d->ldo2;
-    p.n_split = d->out2 ? d->n_split : 0x7fffffff;
-    UWU_CHECK_ARG(d->out2 == nullptr || (d->n_split > 0 && d->n_split % 32 == 0 && d->n_split % bn == 0),
+    p.n_split = (d->out2 && d->epi_mode == 0) ? d->n_split : 0x7fffffff;
+    UWU_CHECK_ARG(d->out2 == nullptr || d->epi_mode != 0 || (d->n_split > 0 && d->n_split % 32 == 0 && d->n_split % bn == 0),
                   "uwu_gemm: n_split %d must be a positive multiple of block_n %d", d->n_split, bn);
     p.out_fp32 = d->out_dtype == UWU_F32;
     p.bias = d->bias;
@@ -906,6 +1104,33 @@ extern "C" int uwu_gemm(const uwu_gemm_desc* d, void* stream_) {
             p.epi_tma = 1;
         }
     }
+    if (d->epi_mode != 0) {
+        // fused GEGLU: `out` is [M, 2F] in both modes (pre-activation / its gradient), forward adds `out2` [M, F] = h * gelu(g),
+        // backward reads the saved pre-activation through tmAux
+        const long long F2 = 2ll * p.geglu_f;
+        UWU_CHECK_ARG(p.ldo % 8 == 0 && p.ldo >= F2 && (reinterpret_cast<uintptr_t>(d->out) & 15) == 0,
+                      "uwu_gemm(GEGLU): out must be a 16-byte aligned [M, 2F] bf16 matrix");
+        uint32_t box[2] = {64, 32};
+        {
+            uint64_t dims[2] = {(uint64_t)F2, (uint64_t)p.M};
+            uint64_t str[1] = {(uint64_t)p.ldo * 2};
+            if (encode_tmap_bf16(&p.tmO, d->out, 2, dims, str, box, 1)) return UWU_ERR_INVALID;
+            p.tmO2 = p.tmO;
+        }
+        if (d->epi_mode == 1) {
+            UWU_CHECK_ARG(p.ldo2 % 8 == 0 && p.ldo2 >= p.geglu_f && (reinterpret_cast<uintptr_t>(d->out2) & 15) == 0,
+                          "uwu_gemm(GEGLU fwd): out2 must be a 16-byte aligned [M, F] bf16 matrix");
+            uint64_t dims[2] = {(uint64_t)p.geglu_f, (uint64_t)p.M};
+            uint64_t str[1] = {(uint64_t)p.ldo2 * 2};
+            if (encode_tmap_bf16(&p.tmO2, d->out2, 2, dims, str, box, 1)) return UWU_ERR_INVALID;
+        } else {
+            UWU_CHECK_ARG(d->ld_aux >= F2 && (reinterpret_cast<uintptr_t>(d->aux) & 15) == 0, "uwu_gemm(GEGLU bwd): bad aux");
+            uint64_t dims[2] = {(uint64_t)F2, (uint64_t)p.M};
+            uint64_t str[1] = {(uint64_t)d->ld_aux * 2};
+            if (encode_tmap_bf16(&p.tmAux, d->aux, 2, dims, str, box, 1)) return UWU_ERR_INVALID;
+        }
+        p.epi_tma = 1;
+    }
     // CTA-pair eligibility (decided before the stream-K schedule: the schedule's workers are then clusters, its tiles pairs)
     static int want_pair = -1, want_mc = -1;
     if (want_pair < 0) {
@@ -919,6 +1144,8 @@ extern "C" int uwu_gemm(const uwu_gemm_desc* d, void* stream_) {
     const bool sk_candidate = d->stream_k != 0 && p.out_fp32 && !d->bias && !d->bias_rows && !d->residual && p.num_kb >= 32;
     const bool use_pair = want_pair && pair_shape_ok && (want_pair >= 2 || !sk_candidate);
 
+    UWU_CHECK_ARG(d->epi_mode == 0 || use_pair,
+                  "uwu_gemm(GEGLU): the fused epilogues need the CTA-pair kernel (M >= 256, UWU_GEMM_PAIR != 0)");
     // stream-K: few output tiles but a long reduction (token-reduction weight gradients) would leave most SMs idle
     const int n_tiles_all = use_pair ? ((p.num_m_tiles + 1) / 2) * p.num_n_tiles : p.num_m_tiles * p.num_n_tiles;
     int sk = d->stream_k;
@@ -1003,12 +1230,13 @@ extern "C" int uwu_gemm(const uwu_gemm_desc* d, void* stream_) {
 
     // ---------------- launch ----------------
     const int stage_bytes = A_STAGE_BYTES + p.b_stage_bytes;
-    const int smem_budget = 227 * 1024 - 1024 /*align slack*/ - 256 /*barriers*/ - EPI_STAGE_BYTES;
+    const int epi_bytes = 4 * p.epi_warp_bytes;
+    const int smem_budget = 227 * 1024 - 1024 /*align slack*/ - 256 /*barriers*/ - epi_bytes;
     int stages = smem_budget / stage_bytes;
     if (stages > MAX_STAGES) stages = MAX_STAGES;
     UWU_CHECK_ARG(stages >= 2, "uwu_gemm: tile too large for shared memory");
     p.stages = stages;
-    const size_t smem_bytes = (size_t)stages * stage_bytes + EPI_STAGE_BYTES + 1024 + 256;
+    const size_t smem_bytes = (size_t)stages * stage_bytes + epi_bytes + 1024 + 256;
 
     static bool attr_set = false;
     if (!attr_set) {

@@ -7,6 +7,7 @@ No function falls back to a PyTorch/CPU implementation.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional, Sequence
 
 import torch
@@ -54,9 +55,9 @@ def gemm(a: torch.Tensor, b: torch.Tensor, M: int, N: int, K: int, *, a_layout: 
          alpha: float = 1.0, accumulate: bool = False, block_n: int = 0, out2: Optional[torch.Tensor] = None,
          n_split: int = 0, conv: Optional[dict] = None, a2: Optional[torch.Tensor] = None,
          dbg: Optional[dict] = None, stream_k: int = -1, k_segs: int = 0, a_seg_off: int = 0, b_seg_off: int = 0,
-         grp_n: int = 0, a_grp_koff: int = 0) -> torch.Tensor:
+         grp_n: int = 0, a_grp_koff: int = 0, epi_mode: int = 0, aux: Optional[torch.Tensor] = None) -> torch.Tensor:
     """out[M,N] = alpha * A·Bᵀ + bias + bias_rows + residual (see uwu_gemm in include/uwu_b200.h)."""
-    _req_cuda(a, b, out, bias, bias_rows, residual, out2, a2)
+    _req_cuda(a, b, out, bias, bias_rows, residual, out2, a2, aux)
     assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16, "GEMM operands must be bf16"
     if out is None:
         out = torch.empty((M, N), device=a.device, dtype=out_dtype)
@@ -91,11 +92,39 @@ def gemm(a: torch.Tensor, b: torch.Tensor, M: int, N: int, K: int, *, a_layout: 
         d.residual, d.ldr = _ptr(residual), residual.stride(0) if residual.dim() == 2 else N
     d.alpha, d.accumulate, d.block_n, d.stream_k = alpha, int(accumulate), block_n, stream_k
     d.k_segs, d.a_seg_off, d.b_seg_off, d.grp_n, d.a_grp_koff = k_segs, a_seg_off, b_seg_off, grp_n, a_grp_koff
+    d.epi_mode = epi_mode
+    if aux is not None:
+        assert aux.dtype == torch.bfloat16 and aux.stride(1) == 1
+        d.aux, d.ld_aux = _ptr(aux), aux.stride(0)
     if dbg:
         for k, v in dbg.items():
             setattr(d, "dbg_" + k, v)
     check(lib().uwu_gemm(C.byref(d), _stream()), "uwu_gemm")
     return out
+
+
+_GEGLU_FUSE = os.environ.get("UWU_GEGLU_FUSE", "1") != "0"
+_PAIR_ON = os.environ.get("UWU_GEMM_PAIR", "2") != "0"
+
+
+def geglu_fusable(M: int, F: int) -> bool:
+    """The GEGLU epilogues live in the CTA-pair GEMM kernel: at least two 128-row tiles, F a multiple of 256."""
+    return _GEGLU_FUSE and _PAIR_ON and M >= 256 and F % 256 == 0
+
+
+def gemm_geglu_fwd(x: torch.Tensor, w: torch.Tensor, M: int, F: int, K: int, bias: Optional[torch.Tensor], lda: Optional[int] = None):
+    """(p, act): p[M, 2F] = x wᵀ + bias (pre-activation h | g, kept for backward), act[M, F] = h * gelu(g) — one launch."""
+    p = torch.empty((M, 2 * F), device=x.device, dtype=torch.bfloat16)
+    act = torch.empty((M, F), device=x.device, dtype=torch.bfloat16)
+    gemm(x, w, M, 2 * F, K, lda=lda, bias=bias, out=p, out2=act, epi_mode=1)
+    return p, act
+
+
+def gemm_geglu_bwd(dy: torch.Tensor, w_kn: torch.Tensor, p: torch.Tensor, M: int, F: int, K: int, lda: Optional[int] = None) -> torch.Tensor:
+    """dp[M, 2F] = geglu'(p) applied to d = dy · w_kn ([K, F], the down projection's data gradient) — one launch."""
+    dp = torch.empty((M, 2 * F), device=dy.device, dtype=torch.bfloat16)
+    gemm(dy, w_kn, M, F, K, lda=lda, b_layout=B_KN, ldb=F, out=dp, epi_mode=2, aux=p)
+    return dp
 
 
 TAPS_3X3 = [(0, dy - 1, dx - 1) for dy in range(3) for dx in range(3)]

@@ -517,16 +517,29 @@ class FeedForward(nn.Module):
         self.net = nn.ModuleList([GEGLU(dim, dim * mult), nn.Dropout(0.0), Linear(dim * mult, dim)])
 
     def fwd(self, n, x_res, st):
-        p = self.net[0].proj.fwd(n, st.M)
-        g = ops.geglu_fwd(p)
+        proj = self.net[0].proj
+        F = proj.out_features // 2
+        if ops.geglu_fusable(st.M, F):
+            # GEGLU in the up-projection's epilogue: pre-activation (kept for backward) and h * gelu(g) from one launch
+            p, g = ops.gemm_geglu_fwd(n, proj.w16(), st.M, F, proj.in_features, proj.bias, lda=n.stride(0))
+        else:
+            p = proj.fwd(n, st.M)
+            g = ops.geglu_fwd(p)
         self._sv = (n, p, g)
         return self.net[2].fwd(g, st.M, residual=x_res)
 
     def bwd(self, dx, st):
         n, p, g = self._sv
         self._sv = None
-        dg = self.net[2].bwd(dx, g, st.M)
-        dp = ops.geglu_bwd(p, dg)
+        lin2 = self.net[2]
+        F = lin2.in_features
+        if ops.geglu_fusable(st.M, F):
+            # GEGLU backward in the epilogue of the down-projection's data-gradient GEMM: d(h * gelu(g)) never reaches HBM
+            lin2.param_grads(dx, g, st.M)
+            dp = ops.gemm_geglu_bwd(dx, lin2._cache, p, st.M, F, lin2.out_features, lda=dx.stride(0))
+        else:
+            dg = lin2.bwd(dx, g, st.M)
+            dp = ops.geglu_bwd(p, dg)
         return self.net[0].proj.bwd(dp, n, st.M)
 
 
