@@ -187,6 +187,12 @@ int64_t uwu_attn_lse_floats(int32_t B, int32_t heads, int32_t Lq);
 int uwu_attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int32_t B, int32_t heads, int32_t Lq,
                  int32_t Lk, int32_t head_dim, int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo, float scale,
                  void* stream);
+/* forward-only attention with a causal mask and / or a per-(batch, key) padding mask, for the frozen CLIP text towers behind
+ * ConcatTextEncoders (src/duwu/modules/text_encoders.py:139-200 calls transformers.CLIPTextModel(input_ids, attention_mask=...),
+ * whose self-attention is causal + padding-masked).  Lk <= 128, head_dim <= 64.  key_mask: int32 [B, Lk], 0 = padding, or NULL. */
+int uwu_attn_fwd_masked(const void* q, const void* k, const void* v, void* o, float* lse, int32_t B, int32_t heads, int32_t Lq,
+                        int32_t Lk, int32_t head_dim, int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo, float scale,
+                        int32_t causal, const int32_t* key_mask, void* stream);
 int64_t uwu_attn_bwd_workspace_floats(int32_t B, int32_t heads, int32_t Lq);
 int uwu_attn_bwd(const void* q, const void* k, const void* v, const void* o, const void* dout, const float* lse, void* dq,
                  void* dk, void* dv, int32_t B, int32_t heads, int32_t Lq, int32_t Lk, int32_t head_dim, int64_t ldq,

@@ -505,3 +505,20 @@ def test_gradual_warmup_ramp_matches_the_reference_scheduler_step_for_step():
         opt2.step()
         sch2.step()
         assert abs(opt2.param_groups[0]["lr"] - expect[n_before + 1]) < 1e-7
+
+
+def test_clip_text_model_state_dict_matches_transformers():
+    """Parameter names / shapes of the kernel-backed CLIP text tower == `transformers.CLIPTextModel` (the class the reference
+    instantiates, configs/demo_training_lycoris.yaml:93,102), for both SDXL tower configs (meta device: no memory)."""
+    from transformers import CLIPTextConfig
+    from transformers import CLIPTextModel as HF
+
+    from uwudiff_b200.text_encoders import CLIP_BIGG_CONFIG, CLIP_L_CONFIG, CLIPTextModel
+
+    for cfg in (CLIP_L_CONFIG, CLIP_BIGG_CONFIG):
+        with torch.device("meta"):
+            hf = HF(CLIPTextConfig(**cfg))
+            ours = CLIPTextModel(cfg)
+        a = {k: tuple(v.shape) for k, v in hf.state_dict().items() if "position_ids" not in k}
+        b = {k: tuple(v.shape) for k, v in ours.state_dict().items()}
+        assert a == b

@@ -87,6 +87,7 @@ SIGNATURES = {
     "uwu_pred_convert": (C.c_int, [_P, _P, _I32, _P, _P, _P, _I32, _I64, _I32, _I32, _I32, _P, _P]),
     "uwu_attn_lse_floats": (C.c_int64, [_I32, _I32, _I32]),
     "uwu_attn_fwd": (C.c_int, [_P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I64, _I64, _I64, _I64, _F, _P]),
+    "uwu_attn_fwd_masked": (C.c_int, [_P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I64, _I64, _I64, _I64, _F, _I32, _P, _P]),
     "uwu_attn_bwd_workspace_floats": (C.c_int64, [_I32, _I32, _I32]),
     "uwu_attn_bwd": (C.c_int, [_P] * 9 + [_I32] * 5 + [_I64] * 8 + [_F, _P, _P]),
     "uwu_groupnorm_workspace_floats": (C.c_int64, [_I32, _I32, _I32, _I32]),

@@ -34,6 +34,7 @@ TARGET_ALIASES = {
     "duwu.modules.unet_patch.UNet2DFromScratch": "uwudiff_b200.unet.UNet2DFromScratch",
     "duwu.modules.text_encoders.ConcatTextEncoders": "uwudiff_b200.text_encoders.ConcatTextEncoders",
     "duwu.trainer.nn_weighted_loss_trainer.NNWeightedLossTrainer": "uwudiff_b200.trainer.NNWeightedLossTrainer",
+    "transformers.CLIPTextModel": "uwudiff_b200.text_encoders.CLIPTextModel",
     "diffusers.EulerDiscreteScheduler": "uwudiff_b200.scheduler.EulerDiscreteScheduler",
     "diffusers.AutoencoderKL": "uwudiff_b200.vae.AutoencoderKL",
     "torch.optim.AdamW": "uwudiff_b200.optim.FusedAdamW",

@@ -126,7 +126,8 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) attn_fwd_kernel(const __grid_c
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        // the whole warp walks the loop (warp-uniform waits and operands); one elected lane issues each group of UMMAs
+        {
             const uint32_t idesc_qk = make_idesc_bf16(128, 128, 0, 0);
             const uint32_t idesc_pv = make_idesc_bf16(128, 64, 0, 1);
             const uint32_t sq = smem_u32(smem + FWD_SQ), sk = smem_u32(smem + FWD_SK), sv = smem_u32(smem + FWD_SV),
@@ -141,11 +142,14 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) attn_fwd_kernel(const __grid_c
             mbar_wait(q_full, 0);
             mbar_wait(&k_full[0], 0);
             tc_fence_after();
-            for (int t = 0; t < ntiles; ++t) {
-                issue_qk(t, 0);
-                umma_commit(&s_full[t]);
+            if (elect_one()) {
+                for (int t = 0; t < ntiles; ++t) {
+                    issue_qk(t, 0);
+                    umma_commit(&s_full[t]);
+                }
+                umma_commit(&k_empty[0]);
             }
-            umma_commit(&k_empty[0]);
+            __syncwarp();
             for (int j = 0; j < nkv; ++j) {
                 const int s = j % FWD_ST;
                 const uint32_t ph = (uint32_t)((j / FWD_ST) & 1);
@@ -156,23 +160,30 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) attn_fwd_kernel(const __grid_c
                 for (int t = 0; t < ntiles; ++t) {
                     mbar_wait(&p_full[t], (uint32_t)(j & 1));
                     tc_fence_after();
-                    // S(t, j) has been consumed: the next scores go first, they are what the softmax warps wait for;
-                    // nobody waits for P V (O lives in TMEM) except the P-buffer reuse guard below
-                    if (has_next) {
-                        issue_qk(t, s1);
-                        umma_commit(&s_full[t]);
-                    }
-                    const uint64_t vd = desc_mnmajor(sv + s * AT_TILE, 8192);
+                    if (elect_one()) {
+                        // S(t, j) has been consumed: the next scores go first, they are what the softmax warps wait for;
+                        // nobody waits for P V (O lives in TMEM) except the P-buffer reuse guard below
+                        if (has_next) {
+                            issue_qk(t, s1);
+                            umma_commit(&s_full[t]);
+                        }
+                        const uint64_t vd = desc_mnmajor(sv + s * AT_TILE, 8192);
+                        const uint64_t pd = desc_kmajor(sp + t * 2 * AT_TILE);
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        const uint64_t ad = desc_kmajor(sp + t * 2 * AT_TILE + (k >> 2) * AT_TILE) + (uint64_t)((k & 3) * 2);
-                        umma_bf16(tmem_base + 256u + (uint32_t)(t * 64), ad, vd + (uint64_t)(k * 128), idesc_pv,
-                                  (uint32_t)((j | k) != 0));  // O accumulates in TMEM over the whole key loop
+                        for (int k = 0; k < 8; ++k) {
+                            const uint64_t ad = pd + (uint64_t)(((k >> 2) * AT_TILE) >> 4) + (uint64_t)((k & 3) * 2);
+                            umma_bf16(tmem_base + 256u + (uint32_t)(t * 64), ad, vd + (uint64_t)(k * 128), idesc_pv,
+                                      (uint32_t)((j | k) != 0));  // O accumulates in TMEM over the whole key loop
+                        }
+                        umma_commit(&pv_full[t]);
                     }
-                    umma_commit(&pv_full[t]);
+                    __syncwarp();
                 }
-                umma_commit(&v_empty[s]);
-                if (has_next) umma_commit(&k_empty[s1]);
+                if (elect_one()) {
+                    umma_commit(&v_empty[s]);
+                    if (has_next) umma_commit(&k_empty[s1]);
+                }
+                __syncwarp();
             }
         }
     } else {
@@ -526,7 +537,8 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_kernel(const __grid_c
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        // the whole warp walks the loop (warp-uniform waits and operands); one elected lane issues each group of UMMAs
+        {
             const uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);              // S, dP: both operands K-major
             const uint32_t idesc_acc = make_idesc_bf16(128, 64, kDQ ? 0 : 1, 1);  // dQ: A K-major; dV/dK: A MN-major; B MN-major
             const uint32_t sr0 = smem_u32(smem + BWD_SR0), sr1 = smem_u32(smem + BWD_SR1), ss0 = smem_u32(smem + Cfg::SS0),
@@ -545,8 +557,11 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_kernel(const __grid_c
             mbar_wait(res_full, 0);
             mbar_wait(&st_full[0], 0);
             tc_fence_after();
-            issue_sdp(0);
-            umma_commit(sdp_full);
+            if (elect_one()) {
+                issue_sdp(0);
+                umma_commit(sdp_full);
+            }
+            __syncwarp();
             int s = 0, s1 = (kStages > 1) ? 1 : 0;
             uint32_t ph1 = 0;  // phase of stage s1
             for (int i = 0; i < n_iter; ++i) {
@@ -554,12 +569,16 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_kernel(const __grid_c
                     mbar_wait(&st_full[s1], ph1);
                     mbar_wait(sdp_empty, (uint32_t)(i & 1));  // compute warps have pulled S / dP of iteration i out of TMEM
                     tc_fence_after();
-                    issue_sdp(s1);
-                    umma_commit(sdp_full);
+                    if (elect_one()) {
+                        issue_sdp(s1);
+                        umma_commit(sdp_full);
+                    }
+                    __syncwarp();
                 }
                 mbar_wait(pds_full, (uint32_t)(i & 1));
+                if (kFused) mbar_wait(dq_empty, (uint32_t)((i & 1) ^ 1));
                 tc_fence_after();
-                {
+                if (elect_one()) {
                     const uint64_t b0 = desc_mnmajor(ss0 + s * AT_TILE, 8192);  // Q (dK) or K (dQ), [rows = reduction, 64 d]
                     const uint64_t b1 = desc_mnmajor(ss1 + s * AT_TILE, 8192);  // dO (dV)
                     if (kDQ) {
@@ -584,8 +603,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_kernel(const __grid_c
                         if (kFused) {
                             // dQ_i[q, d] = sum_key dS[q, key] K[key, d]: A = dS K-major, B = the resident K tile MN-major;
                             // a fresh 64-column accumulator per query tile, drained by the compute warps one iteration later
-                            mbar_wait(dq_empty, (uint32_t)((i & 1) ^ 1));
-                            tc_fence_after();
+                            // (dq_empty was awaited by the whole warp above)
                             const uint32_t idesc_dq = make_idesc_bf16(128, 64, 0, 1);
                             const uint64_t kb = desc_mnmajor(sr0, 8192);
 #pragma unroll
@@ -595,17 +613,19 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_kernel(const __grid_c
                             }
                         }
                     }
+                    umma_commit(&st_empty[s]);
+                    umma_commit(pds_empty);
+                    if (kFused) umma_commit(dq_full);
                 }
-                umma_commit(&st_empty[s]);
-                umma_commit(pds_empty);
-                if (kFused) umma_commit(dq_full);
+                __syncwarp();
                 s = s1;
                 if (++s1 == kStages) {
                     s1 = 0;
                     ph1 ^= 1;
                 }
             }
-            umma_commit(acc_full);
+            if (elect_one()) umma_commit(acc_full);
+            __syncwarp();
         }
     } else {
         // 16 compute warps: warp (sub, quarter) owns TMEM lanes [32 sub, +32) (the query rows) and key columns [32 quarter, +32)
@@ -787,6 +807,9 @@ int attn_any_bwd(const void* q, const void* k, const void* v, const void* o, con
 
 // short-key (cross-attention) kernels, attn_any.cu
 bool attn_short_ok(int Lq, int Lk, int d, bool backward);
+int attn_short_fwd_masked(const void* q, const void* k, const void* v, void* o, float* lse, int B, int heads, int Lq, int Lk, int d,
+                          long long ldq, long long ldk, long long ldv, long long ldo, float scale, int causal, const int32_t* key_mask,
+                          cudaStream_t stream);
 int attn_short_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int B, int heads, int Lq, int Lk, int d,
                    long long ldq, long long ldk, long long ldv, long long ldo, float scale, cudaStream_t stream);
 int attn_short_bwd(const void* q, const void* k, const void* v, const void* dout, const float* lse, void* dq, void* dk, void* dv,
@@ -838,6 +861,19 @@ extern "C" int uwu_attn_fwd(const void* q, const void* k, const void* v, void* o
     UWU_CHECK_CUDA(launch_pdl(attn_fwd_kernel, grid, dim3(FWD_THREADS), FWD_SMEM, stream, a));
     UWU_CHECK_LAUNCH();
     return UWU_OK;
+}
+
+extern "C" int uwu_attn_fwd_masked(const void* q, const void* k, const void* v, void* o, float* lse, int32_t B, int32_t heads,
+                                   int32_t Lq, int32_t Lk, int32_t head_dim, int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo,
+                                   float scale, int32_t causal, const int32_t* key_mask, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    if (int rc = attn_check(B, heads, Lq, Lk, head_dim)) return rc;
+    UWU_CHECK_ARG(q && k && v && o && lse, "uwu_attn_fwd_masked: null pointer");
+    UWU_CHECK_ARG(Lk <= 128 && head_dim <= 64 && head_dim % 8 == 0,
+                  "uwu_attn_fwd_masked: built for text-encoder sequences (Lk <= 128, head_dim <= 64), got Lk=%d d=%d", Lk, head_dim);
+    UWU_CHECK_ARG(!causal || Lq == Lk, "uwu_attn_fwd_masked: the causal mask needs Lq == Lk");
+    UWU_CHECK_ARG(ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(o) & 15) == 0, "uwu_attn_fwd_masked: output must be 16-byte aligned");
+    return attn_short_fwd_masked(q, k, v, o, lse, B, heads, Lq, Lk, head_dim, ldq, ldk, ldv, ldo, scale, causal, key_mask, stream);
 }
 
 extern "C" int64_t uwu_attn_bwd_workspace_floats(int32_t B, int32_t heads, int32_t Lq) {

@@ -36,6 +36,8 @@ struct AnyArgs {
     long long ldq, ldk, ldv, ldo, lddo, lddq, lddk, lddv;
     int B, heads, Lq, Lk, Lq_pad, d;
     float scale, scale_log2;
+    int causal;               // masked short forward only: key j is visible to query i iff j <= i
+    const int32_t* key_mask;  // masked short forward only: optional [B, Lk], 0 = padding key (never attended)
 };
 
 __device__ __forceinline__ void ldsm4(uint32_t (&r)[4], uint32_t addr) {
@@ -487,7 +489,7 @@ __device__ __forceinline__ void store_rows16(const float (&acc)[8][4], float m0,
     __syncwarp();
 }
 
-template <int NK8>
+template <int NK8, bool MASKED>
 __global__ void __launch_bounds__(128) attn_short_fwd_kernel(const AnyArgs a) {
     pdl_trigger();
     constexpr int LKP = NK8 * 8;
@@ -526,7 +528,14 @@ __global__ void __launch_bounds__(128) attn_short_fwd_kernel(const AnyArgs a) {
         for (int nt = 0; nt < NK8; ++nt) {
             const int col = nt * 8 + 2 * t;
 #pragma unroll
-            for (int e = 0; e < 4; ++e) s[nt][e] = (col + (e & 1) < a.Lk) ? s[nt][e] * a.scale_log2 : -INFINITY;
+            for (int e = 0; e < 4; ++e) {
+                bool ok = col + (e & 1) < a.Lk;
+                if (MASKED) {  // CLIP text towers: causal mask + tokenizer padding mask (transformers create_causal_mask)
+                    const int cj = col + (e & 1), ri = row0 + g + ((e >> 1) << 3);
+                    ok = ok && (!a.causal || cj <= ri) && (a.key_mask == nullptr || a.key_mask[(size_t)b * a.Lk + cj] != 0);
+                }
+                s[nt][e] = ok ? s[nt][e] * a.scale_log2 : -INFINITY;
+            }
             mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
             mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
         }
@@ -787,15 +796,15 @@ __global__ void attn_short_kv_convert_kernel(const AnyArgs a, const float* __res
     *reinterpret_cast<uint4*>(a.dv + ((long long)b * a.Lk + key) * a.lddv + (long long)h * a.d + c8 * 8) = uv;
 }
 
-template <int NK8>
+template <int NK8, bool MASKED = false>
 int launch_short_fwd(const AnyArgs& a, cudaStream_t stream) {
     constexpr int SMEM = (2 * NK8 * 8 + 4 * 2 * 16) * SH_LDS * 2;
     static bool attr = false;
     if (!attr) {
-        UWU_CHECK_CUDA(cudaFuncSetAttribute(attn_short_fwd_kernel<NK8>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+        UWU_CHECK_CUDA(cudaFuncSetAttribute(attn_short_fwd_kernel<NK8, MASKED>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
         attr = true;
     }
-    attn_short_fwd_kernel<NK8><<<dim3((a.Lq + SH_ROWS - 1) / SH_ROWS, a.heads, a.B), 128, SMEM, stream>>>(a);
+    attn_short_fwd_kernel<NK8, MASKED><<<dim3((a.Lq + SH_ROWS - 1) / SH_ROWS, a.heads, a.B), 128, SMEM, stream>>>(a);
     UWU_CHECK_LAUNCH();
     return UWU_OK;
 }
@@ -922,6 +931,23 @@ int attn_short_fwd(const void* q, const void* k, const void* v, void* o, float* 
     a.scale = scale; a.scale_log2 = scale * LOG2E;
     if (int rc = check_any(a, "uwu_attn_fwd")) return rc;
     return Lk <= 80 ? launch_short_fwd<10>(a, stream) : launch_short_fwd<16>(a, stream);
+}
+
+int attn_short_fwd_masked(const void* q, const void* k, const void* v, void* o, float* lse, int B, int heads, int Lq, int Lk, int d,
+                          long long ldq, long long ldk, long long ldv, long long ldo, float scale, int causal, const int32_t* key_mask,
+                          cudaStream_t stream) {
+    AnyArgs a{};
+    a.q = reinterpret_cast<const __nv_bfloat16*>(q);
+    a.k = reinterpret_cast<const __nv_bfloat16*>(k);
+    a.v = reinterpret_cast<const __nv_bfloat16*>(v);
+    a.out = reinterpret_cast<__nv_bfloat16*>(o);
+    a.lse = lse;
+    a.ldq = ldq; a.ldk = ldk; a.ldv = ldv; a.ldo = ldo;
+    a.B = B; a.heads = heads; a.Lq = Lq; a.Lk = Lk; a.Lq_pad = (Lq + 127) / 128 * 128; a.d = d;
+    a.scale = scale; a.scale_log2 = scale * LOG2E;
+    a.causal = causal; a.key_mask = key_mask;
+    if (int rc = check_any(a, "uwu_attn_fwd_masked")) return rc;
+    return Lk <= 80 ? launch_short_fwd<10, true>(a, stream) : launch_short_fwd<16, true>(a, stream);
 }
 
 int attn_short_bwd(const void* q, const void* k, const void* v, const void* dout, const float* lse, void* dq, void* dk, void* dv,

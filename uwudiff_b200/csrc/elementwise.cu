@@ -106,6 +106,7 @@ UWU_DEVINL float gelu_tanh_grad_f(float x) {
 
 // mode 0: y = silu(x); mode 1: y = x * silu'(a) (x = dy, a = pre-activation); mode 2: y = x + a; mode 3: y = x;
 // mode 4: y = gelu_tanh(x); mode 5: y = x * gelu_tanh'(a)   (DiT MLP activation)
+// mode 6: y = x * sigmoid(1.702 x) ("quick_gelu", CLIP-L text tower); mode 7: y = gelu_erf(x) (CLIP-bigG text tower)
 __global__ void ew_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ a, long long nvec,
                           int mode, __nv_bfloat16* __restrict__ y) {
     pdl_trigger();
@@ -136,6 +137,8 @@ __global__ void ew_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat
                 else if (mode == 2) f[j] += b[j];
                 else if (mode == 4) f[j] = gelu_tanh_f(f[j]);
                 else if (mode == 5) f[j] *= gelu_tanh_grad_f(b[j]);
+                else if (mode == 6) f[j] = __fdividef(f[j], 1.0f + __expf(-1.702f * f[j]));
+                else if (mode == 7) f[j] = gelu_fast_f(f[j]);
             }
             st8e(y + i * 8, f);
         }
@@ -439,9 +442,9 @@ extern "C" int uwu_geglu_bwd(const void* in, const void* dout, int64_t M, int32_
 extern "C" int uwu_elementwise(const void* x, const void* a, int64_t n, int32_t mode, void* y, void* stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     UWU_CHECK_ARG(n >= 0 && n % 8 == 0, "uwu_elementwise: n=%lld must be a multiple of 8", (long long)n);
-    UWU_CHECK_ARG(mode >= 0 && mode <= 5, "uwu_elementwise: bad mode %d", mode);
+    UWU_CHECK_ARG(mode >= 0 && mode <= 7, "uwu_elementwise: bad mode %d", mode);
     if (n == 0) return UWU_OK;
-    UWU_CHECK_ARG(x && y && (mode == 0 || mode == 3 || mode == 4 || a), "uwu_elementwise: null pointer");
+    UWU_CHECK_ARG(x && y && (mode == 0 || mode == 3 || mode == 4 || mode == 6 || mode == 7 || a), "uwu_elementwise: null pointer");
     ew_kernel<<<ew_grid(n / 8, 256), 256, 0, stream>>>(reinterpret_cast<const bf16*>(x), reinterpret_cast<const bf16*>(a),
                                                        n / 8, mode, reinterpret_cast<bf16*>(y));
     UWU_CHECK_LAUNCH();

@@ -76,6 +76,9 @@ struct GemmKernelArgs {
     // 2 backward (N = F: the tile's dg is combined with h, g read from the saved pre-activation `aux`)
     int epi_mode, geglu_f, epi_warp_bytes;
     CUtensorMap tmAux;  // mode 2: pre-activation [M, 2F], box {64 columns, 32 rows}, 128B swizzle
+    // wide tiles (pair kernel, K-major B): block_n = n_inst * bn_inst (<= 512) is computed by n_inst UMMAs per k-step that share
+    // the A tile (fewer operand bytes per FLOP from L2, the limiter of this kernel); block_n > 256 leaves room for ONE accumulator
+    int n_inst, bn_inst, b_inst_bytes, n_acc;
     int pair;      // 1: CTA-pair kernel (cta_group::2): one 256 x block_n tile per cluster of two CTAs; each CTA stages its
                    //    own 128 rows of A and HALF of the B tile, the leader CTA issues M = 256 UMMAs for both
     int stream_k;  // 1: the (tile, k-block) space is cut into equal contiguous ranges, one per CTA; partial tiles are
@@ -217,7 +220,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
 
     if (warp == 0) {
         // ===================================== TMA producer =====================================
-        if (lane == 0) {
+        // the whole warp walks the loop (warp-uniform operands); one elected lane issues the copies of a k-block
+        {
             int stage = 0;
             uint32_t phase = 0;
             const uint32_t tx_bytes = (uint32_t)p.tx_bytes;
@@ -239,86 +243,87 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* sa = smem + (size_t)stage * stage_bytes;
                     uint8_t* sb = sa + A_STAGE_BYTES;
-                    if (PAIR) {
-                        // Both CTAs' boxes complete on the LEADER's full barrier (the leader expects the bytes of both).
-                        // The peer may run ahead of the leader's expect_tx: its stage was released by the leader's MMA
-                        // commit, i.e. the barrier is already in the phase these bytes belong to, and a phase cannot complete
-                        // before the leader's own arrive.
-                        const uint32_t fb = mapa_u32(smem_u32(&full_bar[stage]), 0);
-                        if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], tx_bytes);
-                        const int kseg = p.kb_per_seg > 0 ? kb / p.kb_per_seg : 0;
-                        const int kbs = kb - kseg * p.kb_per_seg;
-                        if (p.a_mode == 0) {
-                            tma_load_2d_cg2(sa, &p.tmA, fb, kb * BLOCK_K, m0);
-                        } else if (p.a_mode == 1) {
-                            tma_load_2d_cg2(sa, &p.tmA, fb, m0, kbs * BLOCK_K);
-                            tma_load_2d_cg2(sa + 8192, &p.tmA, fb, m0 + 64, kbs * BLOCK_K);
-                        } else {
-                            const int tap = kb / p.kb_per_tap;
-                            const int cb = kb - tap * p.kb_per_tap;
-                            if (cb < p.kb_src1)
-                                tma_load_4d_cg2(sa, &p.tmA, fb, cb * BLOCK_K, cw + p.tap_dw[tap], ch + p.tap_dh[tap], cn + p.tap_dn[tap]);
+                    if (elect_one()) {
+                        if (PAIR) {
+                            // Both CTAs' boxes complete on the LEADER's full barrier (the leader expects the bytes of both).
+                            // The peer may run ahead of the leader's expect_tx: its stage was released by the leader's MMA
+                            // commit, i.e. the barrier is already in the phase these bytes belong to, and a phase cannot complete
+                            // before the leader's own arrive.
+                            const uint32_t fb = mapa_u32(smem_u32(&full_bar[stage]), 0);
+                            if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], tx_bytes);
+                            const int kseg = p.kb_per_seg > 0 ? kb / p.kb_per_seg : 0;
+                            const int kbs = kb - kseg * p.kb_per_seg;
+                            if (p.a_mode == 0) {
+                                tma_load_2d_cg2(sa, &p.tmA, fb, kb * BLOCK_K, m0);
+                            } else if (p.a_mode == 1) {
+                                tma_load_2d_cg2(sa, &p.tmA, fb, m0, kbs * BLOCK_K);
+                                tma_load_2d_cg2(sa + 8192, &p.tmA, fb, m0 + 64, kbs * BLOCK_K);
+                            } else {
+                                const int tap = kb / p.kb_per_tap;
+                                const int cb = kb - tap * p.kb_per_tap;
+                                if (cb < p.kb_src1)
+                                    tma_load_4d_cg2(sa, &p.tmA, fb, cb * BLOCK_K, cw + p.tap_dw[tap], ch + p.tap_dh[tap], cn + p.tap_dn[tap]);
+                                else
+                                    tma_load_4d_cg2(sa, &p.tmA2, fb, (cb - p.kb_src1) * BLOCK_K, cw + p.tap_dw[tap], ch + p.tap_dh[tap],
+                                                    cn + p.tap_dn[tap]);
+                            }
+                            if (p.epi_mode == 1)  // leader stages the 128 h rows of W, the peer the matching 128 g rows
+                                tma_load_2d_cg2(sb, &p.tmBh, fb, kb * BLOCK_K, (int)cta_rank * p.geglu_f + n_blk * 128);
+                            else if (p.b_mode == 0)
+                                for (int i = 0; i < p.n_inst; ++i)  // instruction i covers columns [i * bn_inst, (i + 1) * bn_inst): half per CTA
+                                    tma_load_2d_cg2(sb + i * p.b_inst_bytes, &p.tmBh, fb, kb * BLOCK_K,
+                                                    n0 + i * p.bn_inst + (int)cta_rank * (p.bn_inst >> 1));
                             else
-                                tma_load_4d_cg2(sa, &p.tmA2, fb, (cb - p.kb_src1) * BLOCK_K, cw + p.tap_dw[tap], ch + p.tap_dh[tap],
-                                                cn + p.tap_dn[tap]);
-                        }
-                        if (p.epi_mode == 1)  // leader stages the 128 h rows of W, the peer the matching 128 g rows
-                            tma_load_2d_cg2(sb, &p.tmBh, fb, kb * BLOCK_K, (int)cta_rank * p.geglu_f + n_blk * 128);
-                        else if (p.b_mode == 0)
-                            tma_load_2d_cg2(sb, &p.tmBh, fb, kb * BLOCK_K, n0 + (int)cta_rank * (p.block_n >> 1));
-                        else
-                            tma_load_3d_cg2(sb, &p.tmBh, fb, 0, kb * BLOCK_K, (n0 >> 6) + (int)cta_rank * (p.block_n >> 7));
-                        if (++stage == p.stages) {
-                            stage = 0;
-                            phase ^= 1;
-                        }
-                        continue;
-                    }
-                    mbar_expect_tx(&full_bar[stage], tx_bytes);
-                    // ---- A ----
-                    int kseg = 0, kbs = kb;  // segment and k-block within it
-                    if (p.kb_per_seg > 0) {
-                        kseg = kb / p.kb_per_seg;
-                        kbs = kb - kseg * p.kb_per_seg;
-                    }
-                    const int grp = p.grp_n > 0 ? n0 / p.grp_n : 0;
-                    if (p.a_mode == 0) {
-                        tma_load_2d(sa, &p.tmA, &full_bar[stage], kb * BLOCK_K + grp * p.a_grp_koff, m0);
-                    } else if (p.a_mode == 1) {
-                        const int am = m0 + kseg * p.a_seg_off;
-                        tma_load_2d(sa, &p.tmA, &full_bar[stage], am, kbs * BLOCK_K);
-                        tma_load_2d(sa + 8192, &p.tmA, &full_bar[stage], am + 64, kbs * BLOCK_K);
-                    } else {
-                        const int tap = kb / p.kb_per_tap;
-                        const int cb = kb - tap * p.kb_per_tap;
-                        if (cb < p.kb_src1)
-                            tma_load_4d(sa, &p.tmA, &full_bar[stage], cb * BLOCK_K, cw + p.tap_dw[tap],
-                                        ch + p.tap_dh[tap], cn + p.tap_dn[tap]);
-                        else
-                            tma_load_4d(sa, &p.tmA2, &full_bar[stage], (cb - p.kb_src1) * BLOCK_K, cw + p.tap_dw[tap],
-                                        ch + p.tap_dh[tap], cn + p.tap_dn[tap]);
-                    }
-                    // ---- B ----
-                    if (p.cluster2) {
-                        // this CTA fetches its half of the shared B tile and multicasts it into both CTAs' stage
-                        const int rk = wi.rank;
-                        if (p.b_mode == 0)
-                            tma_load_2d_mc(sb + rk * p.b_half_bytes, &p.tmBh, &full_bar[stage], kb * BLOCK_K,
-                                           n0 + rk * (p.block_n >> 1), (uint16_t)3);
-                        else
-                            tma_load_3d_mc(sb + rk * p.b_half_bytes, &p.tmBh, &full_bar[stage], 0, kb * BLOCK_K,
-                                           (n0 >> 6) + rk * (p.block_n >> 7), (uint16_t)3);
-                    } else if (p.b_mode == 0) {
-                        tma_load_2d(sb, &p.tmB, &full_bar[stage], kb * BLOCK_K, n0);
-                    } else {
-                        const int bn0 = n0 - grp * p.grp_n + kseg * p.b_seg_off;
-                        if (p.b_3d) {
-                            tma_load_3d(sb, &p.tmB, &full_bar[stage], 0, kbs * BLOCK_K, bn0 >> 6);
+                                tma_load_3d_cg2(sb, &p.tmBh, fb, 0, kb * BLOCK_K, (n0 >> 6) + (int)cta_rank * (p.block_n >> 7));
                         } else {
-                            for (int j = 0; j * 64 < p.block_n; ++j)
-                                tma_load_2d(sb + j * 8192, &p.tmB, &full_bar[stage], bn0 + j * 64, kbs * BLOCK_K);
+                            mbar_expect_tx(&full_bar[stage], tx_bytes);
+                            // ---- A ----
+                            int kseg = 0, kbs = kb;  // segment and k-block within it
+                            if (p.kb_per_seg > 0) {
+                                kseg = kb / p.kb_per_seg;
+                                kbs = kb - kseg * p.kb_per_seg;
+                            }
+                            const int grp = p.grp_n > 0 ? n0 / p.grp_n : 0;
+                            if (p.a_mode == 0) {
+                                tma_load_2d(sa, &p.tmA, &full_bar[stage], kb * BLOCK_K + grp * p.a_grp_koff, m0);
+                            } else if (p.a_mode == 1) {
+                                const int am = m0 + kseg * p.a_seg_off;
+                                tma_load_2d(sa, &p.tmA, &full_bar[stage], am, kbs * BLOCK_K);
+                                tma_load_2d(sa + 8192, &p.tmA, &full_bar[stage], am + 64, kbs * BLOCK_K);
+                            } else {
+                                const int tap = kb / p.kb_per_tap;
+                                const int cb = kb - tap * p.kb_per_tap;
+                                if (cb < p.kb_src1)
+                                    tma_load_4d(sa, &p.tmA, &full_bar[stage], cb * BLOCK_K, cw + p.tap_dw[tap],
+                                                ch + p.tap_dh[tap], cn + p.tap_dn[tap]);
+                                else
+                                    tma_load_4d(sa, &p.tmA2, &full_bar[stage], (cb - p.kb_src1) * BLOCK_K, cw + p.tap_dw[tap],
+                                                ch + p.tap_dh[tap], cn + p.tap_dn[tap]);
+                            }
+                            // ---- B ----
+                            if (p.cluster2) {
+                                // this CTA fetches its half of the shared B tile and multicasts it into both CTAs' stage
+                                const int rk = wi.rank;
+                                if (p.b_mode == 0)
+                                    tma_load_2d_mc(sb + rk * p.b_half_bytes, &p.tmBh, &full_bar[stage], kb * BLOCK_K,
+                                                   n0 + rk * (p.block_n >> 1), (uint16_t)3);
+                                else
+                                    tma_load_3d_mc(sb + rk * p.b_half_bytes, &p.tmBh, &full_bar[stage], 0, kb * BLOCK_K,
+                                                   (n0 >> 6) + rk * (p.block_n >> 7), (uint16_t)3);
+                            } else if (p.b_mode == 0) {
+                                tma_load_2d(sb, &p.tmB, &full_bar[stage], kb * BLOCK_K, n0);
+                            } else {
+                                const int bn0 = n0 - grp * p.grp_n + kseg * p.b_seg_off;
+                                if (p.b_3d) {
+                                    tma_load_3d(sb, &p.tmB, &full_bar[stage], 0, kbs * BLOCK_K, bn0 >> 6);
+                                } else {
+                                    for (int j = 0; j * 64 < p.block_n; ++j)
+                                        tma_load_2d(sb + j * 8192, &p.tmB, &full_bar[stage], bn0 + j * 64, kbs * BLOCK_K);
+                                }
+                            }
                         }
                     }
+                    __syncwarp();
                     if (++stage == p.stages) {
                         stage = 0;
                         phase ^= 1;
@@ -328,9 +333,20 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
         }
     } else if (warp == 1) {
         // ===================================== MMA issuer =====================================
-        if (lane == 0 && cta_rank == 0) {
-            const uint32_t idesc = make_idesc_bf16(PAIR ? 2 * BLOCK_M : BLOCK_M, (uint32_t)p.block_n, p.a_mode == 1, p.b_mode == 1);
+        // The whole warp walks the loop (warp-uniform control flow and operands: the descriptors stay in uniform registers);
+        // lane 0 issues.  The per-k-block instruction count of this loop bounds the kernel when tiles are narrow: one thread has
+        // ~block_n * 2 cycles per k-block to wait, issue 4 (8) UMMAs and commit, so everything that can be hoisted is.
+        if (cta_rank == 0) {
+            const uint32_t idesc = make_idesc_bf16(PAIR ? 2 * BLOCK_M : BLOCK_M, (uint32_t)(PAIR ? p.bn_inst : p.block_n), p.a_mode == 1,
+                                                   p.b_mode == 1);
+            const uint32_t smem_base = smem_u32(smem);
+            const uint64_t adesc0 = make_smem_desc(smem_base, p.a_lbo, p.a_sbo);
+            const uint64_t bdesc0 = make_smem_desc(smem_base + A_STAGE_BYTES, p.b_lbo, p.b_sbo);
+            const uint32_t a_kinc = p.a_kadv >> 4, b_kinc = p.b_kadv >> 4, stage_inc = (uint32_t)stage_bytes >> 4;
+            const uint32_t b_iinc = (uint32_t)p.b_inst_bytes >> 4;
+            const int n_stages = p.stages;
             int stage = 0;
+            uint32_t stage_off = 0;  // (stage * stage_bytes) >> 4: added to the 14-bit start-address field of both descriptors
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
@@ -340,38 +356,58 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
                 mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * ACC_STRIDE);
+                // instructions whose columns lie entirely past N are skipped (ragged last tile)
+                int n_inst_tile = 1;
+                if (PAIR && p.n_inst > 1) {
+                    const int n0 = (wi.tile % p.num_n_tiles) * p.block_n;
+                    n_inst_tile = min(p.n_inst, (p.N - n0 + p.bn_inst - 1) / p.bn_inst);
+                }
+                uint32_t accf = 0;  // first UMMA of the tile overwrites the accumulator
                 for (int kb = wi.kb0; kb < wi.kb1; ++kb) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
-                    const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
-                    const uint32_t sb = sa + A_STAGE_BYTES;
-                    const uint64_t adesc = make_smem_desc(sa, p.a_lbo, p.a_sbo);
-                    const uint64_t bdesc = make_smem_desc(sb, p.b_lbo, p.b_sbo);
+                    const uint64_t adesc = adesc0 + stage_off, bdesc = bdesc0 + stage_off;
+                    if (elect_one()) {
+                        if (PAIR) {
+                            if (n_inst_tile == 1) {
 #pragma unroll
-                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-                        if (PAIR)
-                            umma_bf16_cg2(d_tmem, adesc + (uint64_t)((k * p.a_kadv) >> 4), bdesc + (uint64_t)((k * p.b_kadv) >> 4),
-                                          idesc, (uint32_t)(kb != wi.kb0 || k != 0));
-                        else
-                            umma_bf16(d_tmem, adesc + (uint64_t)((k * p.a_kadv) >> 4), bdesc + (uint64_t)((k * p.b_kadv) >> 4),
-                                      idesc, (uint32_t)(kb != wi.kb0 || k != 0));
+                                for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+                                    umma_bf16_cg2(d_tmem, adesc + k * a_kinc, bdesc + k * b_kinc, idesc, k == 0 ? accf : 1u);
+                            } else {
+#pragma unroll
+                                for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                                    umma_bf16_cg2(d_tmem, adesc + k * a_kinc, bdesc + k * b_kinc, idesc, k == 0 ? accf : 1u);
+                                    umma_bf16_cg2(d_tmem + (uint32_t)p.bn_inst, adesc + k * a_kinc, bdesc + k * b_kinc + b_iinc, idesc,
+                                                  k == 0 ? accf : 1u);
+                                }
+                            }
+                            umma_commit_cg2(&empty_bar[stage], (uint16_t)3);  // frees this stage in BOTH CTAs once the MMAs retire
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+                                umma_bf16(d_tmem, adesc + k * a_kinc, bdesc + k * b_kinc, idesc, k == 0 ? accf : 1u);
+                            if (p.cluster2)
+                                umma_commit_multicast(&empty_bar[stage], (uint16_t)3);  // both producers may refill once we are done
+                            else
+                                umma_commit(&empty_bar[stage]);  // frees this smem stage once the MMAs retire
+                        }
                     }
-                    if (PAIR)
-                        umma_commit_cg2(&empty_bar[stage], (uint16_t)3);  // frees this stage in BOTH CTAs once the MMAs retire
-                    else if (p.cluster2)
-                        umma_commit_multicast(&empty_bar[stage], (uint16_t)3);  // both producers may refill once we are done
-                    else
-                        umma_commit(&empty_bar[stage]);  // frees this smem stage once the MMAs retire
-                    if (++stage == p.stages) {
+                    accf = 1;
+                    stage_off += stage_inc;
+                    if (++stage == n_stages) {
                         stage = 0;
+                        stage_off = 0;
                         phase ^= 1;
                     }
                 }
-                if (PAIR)
-                    umma_commit_cg2(&tmem_full[acc], (uint16_t)3);  // both CTAs' epilogues own half of the rows
-                else
-                    umma_commit(&tmem_full[acc]);  // accumulator ready for the epilogue
-                if (++acc == 2) {
+                if (elect_one()) {
+                    if (PAIR)
+                        umma_commit_cg2(&tmem_full[acc], (uint16_t)3);  // both CTAs' epilogues own half of the rows
+                    else
+                        umma_commit(&tmem_full[acc]);  // accumulator ready for the epilogue
+                }
+                __syncwarp();
+                if (++acc == p.n_acc) {
                     acc = 0;
                     acc_phase ^= 1;
                 }
@@ -485,7 +521,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
                     const int row0 = m_blk * BLOCK_M + sub * 32;
                     const int n0 = n_blk * p.block_n;
                     const int nchunks = p.block_n >> 6;
-                    if (lane == 0) {
+                    if (elect_one()) {
                         mbar_expect_tx(&epi_bar[sub], 8192);
                         tma_load_2d(iH, &p.tmAux, &epi_bar[sub], n0, row0);
                         tma_load_2d(iG, &p.tmAux, &epi_bar[sub], p.geglu_f + n0, row0);
@@ -515,7 +551,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
                         }
                         __syncwarp();  // every lane has its h / g rows in registers: the input buffers may be refilled
                         fence_proxy_async();
-                        if (lane == 0 && ch + 1 < nchunks) {
+                        if (ch + 1 < nchunks && elect_one()) {
                             mbar_expect_tx(&epi_bar[sub], 8192);
                             tma_load_2d(iH, &p.tmAux, &epi_bar[sub], col0 + 64, row0);
                             tma_load_2d(iG, &p.tmAux, &epi_bar[sub], p.geglu_f + col0 + 64, row0);
@@ -700,7 +736,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
                                     *reinterpret_cast<const uint4*>(sbuf + lane * 128 + ((j ^ (lane & 7)) << 4));
                     }
                 }
-                if (++acc == 2) {
+                if (++acc == p.n_acc) {
                     acc = 0;
                     acc_phase ^= 1;
                 }
@@ -846,7 +882,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
                 else
                     mbar_arrive(&tmem_empty[acc]);
             }
-            if (++acc == 2) {
+            if (++acc == p.n_acc) {
                 acc = 0;
                 acc_phase ^= 1;
             }
@@ -927,7 +963,26 @@ extern "C" int uwu_gemm(const uwu_gemm_desc* d, void* stream_) {
             p.epi_warp_bytes = 16384;
         }
     }
-    UWU_CHECK_ARG(bn % 16 == 0 && bn >= 16 && bn <= 256, "uwu_gemm: block_n %d must be a multiple of 16 in [16,256]", bn);
+    // wide tiles: 320 columns as two 160-wide UMMAs per k-step sharing the A tile (CTA-pair kernel, K-major weights, long
+    // reductions: the 3x3 convolutions, whose N = 320 / 640 / 1280 otherwise run 160-wide or ragged 256-wide tiles)
+    int n_inst = 1;
+    {
+        static int want_wide = -1, pair_env = 1;
+        if (want_wide < 0) {
+            const char* e = getenv("UWU_GEMM_WIDE");
+            want_wide = e ? atoi(e) : 1;
+            const char* e2 = getenv("UWU_GEMM_PAIR");
+            pair_env = e2 ? atoi(e2) : 2;
+        }
+        const long long kblocks = (d->K + 63) / 64;
+        if (want_wide && pair_env && sm_count() % 2 == 0 && d->block_n == 0 && d->epi_mode == 0 && d->b_layout == UWU_B_NK &&
+            d->k_segs <= 1 && d->grp_n == 0 && d->M >= 256 && d->N % 320 == 0 && d->out_dtype == UWU_BF16 && d->out2 == nullptr &&
+            ((d->N <= 640 && kblocks >= 40) || kblocks >= 90)) {
+            bn = 320;
+            n_inst = 2;
+        }
+    }
+    UWU_CHECK_ARG(bn % 16 == 0 && bn >= 16 && (bn <= 256 || n_inst > 1), "uwu_gemm: block_n %d must be a multiple of 16 in [16,256]", bn);
     p.block_n = bn;
     p.num_m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
     p.num_n_tiles = d->epi_mode == 1 ? p.geglu_f / 128 : (p.N + bn - 1) / bn;
@@ -1030,7 +1085,7 @@ extern "C" int uwu_gemm(const uwu_gemm_desc* d, void* stream_) {
         UWU_CHECK_ARG(d->ldb % 8 == 0 && d->ldb >= d->K, "uwu_gemm: ldb %lld must be >= K and a multiple of 8", (long long)d->ldb);
         uint64_t dims[2] = {(uint64_t)d->K, (uint64_t)d->N};
         uint64_t str[1] = {(uint64_t)d->ldb * 2};
-        uint32_t box[2] = {BLOCK_K, (uint32_t)bn};
+        uint32_t box[2] = {BLOCK_K, (uint32_t)(bn > 256 ? 256 : bn)};  // (wide tiles never use this map: per-instruction half boxes)
         if (encode_tmap_bf16(&p.tmB, d->b, 2, dims, str, box, 1)) return UWU_ERR_INVALID;
         p.b_stage_bytes = bn * BLOCK_K * 2;
         p.b_lbo = 0; p.b_sbo = 1024; p.b_kadv = 32;
@@ -1089,7 +1144,8 @@ extern "C" int uwu_gemm(const uwu_gemm_desc* d, void* stream_) {
     {
         const bool res_ok = d->residual == nullptr || (p.ldr % 8 == 0 && (reinterpret_cast<uintptr_t>(d->residual) & 15) == 0);
         const bool o2_ok = d->out2 == nullptr || (p.ldo2 % 8 == 0 && (reinterpret_cast<uintptr_t>(d->out2) & 15) == 0 && d->n_split % 64 == 0);
-        if (!p.out_fp32 && p.ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(d->out) & 15) == 0 && p.N % 8 == 0 && res_ok && o2_ok) {
+        if (d->epi_mode == 0 && !p.out_fp32 && p.ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(d->out) & 15) == 0 && p.N % 8 == 0 && res_ok &&
+            o2_ok) {
             const long long n1 = d->out2 ? (long long)d->n_split : (long long)p.N;
             uint64_t dims[2] = {(uint64_t)n1, (uint64_t)p.M};
             uint64_t str[1] = {(uint64_t)p.ldo * 2};
@@ -1142,7 +1198,9 @@ extern "C" int uwu_gemm(const uwu_gemm_desc* d, void* stream_) {
     const bool half_ok = d->b_layout == UWU_B_NK ? (bn % 16 == 0) : (p.b_3d && bn % 128 == 0);
     const bool pair_shape_ok = d->k_segs <= 1 && d->grp_n == 0 && p.num_m_tiles >= 2 && half_ok && sm_count() % 2 == 0;
     const bool sk_candidate = d->stream_k != 0 && p.out_fp32 && !d->bias && !d->bias_rows && !d->residual && p.num_kb >= 32;
-    const bool use_pair = want_pair && pair_shape_ok && (want_pair >= 2 || !sk_candidate);
+    // split-K (weight-gradient) schedules: pairs only when the row tiles pair up evenly (measured: G[640,*] and G[1920,*], 5 / 15
+    // row tiles, lose 8 % to the half-empty last pair; G[1280,*] .. G[5120,*] gain 4 - 14 %)
+    const bool use_pair = want_pair && pair_shape_ok && (!sk_candidate || (want_pair >= 2 && p.num_m_tiles % 2 == 0));
 
     UWU_CHECK_ARG(d->epi_mode == 0 || use_pair,
                   "uwu_gemm(GEGLU): the fused epilogues need the CTA-pair kernel (M >= 256, UWU_GEMM_PAIR != 0)");
@@ -1205,13 +1263,22 @@ extern "C" int uwu_gemm(const uwu_gemm_desc* d, void* stream_) {
     p.cluster2 = 0;
     p.b_half_bytes = 0;
     p.tmBh = p.tmB;
+    p.n_inst = 1;
+    p.bn_inst = bn;
+    p.b_inst_bytes = 0;
+    p.n_acc = 2;
+    UWU_CHECK_ARG(n_inst == 1 || use_pair, "uwu_gemm: internal error (wide tile without the CTA-pair kernel)");
     if ((use_pair || (want_mc && pair_shape_ok && !p.stream_k)) ) {
         if (d->b_layout == UWU_B_NK) {
             uint64_t dims[2] = {(uint64_t)d->K, (uint64_t)d->N};
             uint64_t str[1] = {(uint64_t)d->ldb * 2};
-            uint32_t box[2] = {BLOCK_K, (uint32_t)(bn / 2)};
+            p.n_inst = n_inst;
+            p.bn_inst = bn / n_inst;
+            p.b_inst_bytes = (p.bn_inst / 2) * BLOCK_K * 2;
+            p.n_acc = bn > 256 ? 1 : 2;
+            uint32_t box[2] = {BLOCK_K, (uint32_t)(p.bn_inst / 2)};
             if (encode_tmap_bf16(&p.tmBh, d->b, 2, dims, str, box, 1)) return UWU_ERR_INVALID;
-            p.b_half_bytes = (bn / 2) * BLOCK_K * 2;
+            p.b_half_bytes = n_inst * p.b_inst_bytes;
         } else {
             uint64_t dims[3] = {64, (uint64_t)d->K, (uint64_t)(d->N / 64)};
             uint64_t str[2] = {(uint64_t)d->ldb * 2, 128};

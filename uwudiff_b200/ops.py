@@ -306,6 +306,23 @@ def attn_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, B: int, heads: i
     return out, lse
 
 
+def attn_fwd_masked(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, B: int, heads: int, L: int, *, causal: bool = True,
+                    key_mask: Optional[torch.Tensor] = None, scale: Optional[float] = None, head_dim: int = 64):
+    """Forward-only attention with a causal mask and / or a [B, L] key-padding mask (CLIP text towers); L <= 128, d <= 64."""
+    _req_cuda(q, k, v, key_mask)
+    assert q.dtype == k.dtype == v.dtype == torch.bfloat16 and q.stride(1) == 1 and k.stride(1) == 1 and v.stride(1) == 1
+    scale = head_dim ** -0.5 if scale is None else scale
+    out = torch.empty((B * L, heads * head_dim), device=q.device, dtype=torch.bfloat16)
+    lse = torch.empty((int(lib().uwu_attn_lse_floats(B, heads, L)),), device=q.device, dtype=torch.float32)
+    if key_mask is not None:
+        key_mask = key_mask.to(device=q.device, dtype=torch.int32).contiguous()
+        assert key_mask.shape == (B, L)
+    check(lib().uwu_attn_fwd_masked(_ptr(q), _ptr(k), _ptr(v), _ptr(out), _ptr(lse), B, heads, L, L, head_dim, q.stride(0),
+                                    k.stride(0), v.stride(0), out.stride(0), scale, int(causal), _ptr(key_mask), _stream()),
+          "uwu_attn_fwd_masked")
+    return out
+
+
 def attn_bwd(q, k, v, o, dout, lse, B: int, heads: int, Lq: int, Lk: int, scale: Optional[float] = None,
              head_dim: int = 64, dq=None, dk=None, dv=None):
     _req_cuda(q, k, v, o, dout, lse)
@@ -394,7 +411,7 @@ def geglu_bwd(x: torch.Tensor, dout: torch.Tensor) -> torch.Tensor:
     return din
 
 
-EW_SILU, EW_SILU_BWD, EW_ADD, EW_COPY, EW_GELU_TANH, EW_GELU_TANH_BWD = 0, 1, 2, 3, 4, 5
+EW_SILU, EW_SILU_BWD, EW_ADD, EW_COPY, EW_GELU_TANH, EW_GELU_TANH_BWD, EW_QUICK_GELU, EW_GELU_ERF = 0, 1, 2, 3, 4, 5, 6, 7
 
 
 def elementwise(x: torch.Tensor, a: Optional[torch.Tensor], mode: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
