@@ -222,6 +222,10 @@ int64_t uwu_layernorm_bwd_workspace_floats(int32_t M, int32_t C);
 int uwu_layernorm_bwd(const void* x, const void* dy, int32_t M, int32_t C, const float* gamma, const float* stats,
                       const void* dres, void* dx, float* dgamma, float* dbeta, int32_t accumulate, float* workspace,
                       void* stream);
+
+/* in-place row softmax of a bf16 [M, ld >= N] matrix: the single-head (head_dim 512) attention of the frozen VAE encoder
+ * (`AutoencoderKL.encode`, src/duwu/trainer/trainer.py:241-244), whose S = Q K^T and P V products run on uwu_gemm */
+int uwu_softmax_rows(void* x, int64_t M, int32_t N, int64_t ld, void* stream);
 /* GEGLU: out[m, f] = in[m, f] * gelu_erf(in[m, F + f])  (hidden, gate = proj.chunk(2)) */
 int uwu_geglu_fwd(const void* in, int64_t M, int32_t F, void* out, void* stream);
 int uwu_geglu_bwd(const void* in, const void* dout, int64_t M, int32_t F, void* din, void* stream);

@@ -423,7 +423,7 @@ def _req_cuda(*ts):
     pass
 
 
-def geglu_fusable(M, F):
+def geglu_fusable(M, F, backward=False):
     return False  # the fused GEGLU epilogues exist only in the CUDA GEMM kernel
 
 

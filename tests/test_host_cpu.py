@@ -7,7 +7,7 @@ import os
 import pytest
 import torch
 
-from conftest import LYCORIS_CFG, LYCORIS_PRESET
+from conftest import LYCORIS_CFG, LYCORIS_PRESET, ROOT
 from oracle import diffusers_shim, loss_oracle
 from oracle import lycoris_oracle as LY
 from oracle import unet_oracle as U
@@ -522,3 +522,57 @@ def test_clip_text_model_state_dict_matches_transformers():
         a = {k: tuple(v.shape) for k, v in hf.state_dict().items() if "position_ids" not in k}
         b = {k: tuple(v.shape) for k, v in ours.state_dict().items()}
         assert a == b
+
+
+def test_sampling_schedule_and_denoiser_match_the_reference_wrapper():
+    """`DiscreteSchedule` / `DiscreteEpsDDPMDenoiser` (src/duwu/sampling/k_diffusion_wrapper.py:23-103) against vectors produced
+    by the reference file run verbatim (oracle/make_sampling_golden.py): bit-exact, it is the same torch arithmetic."""
+    import numpy as np
+
+    from uwudiff_b200 import sampling as S
+    from uwudiff_b200.scheduler import EulerDiscreteScheduler
+
+    g = np.load(os.path.join(ROOT, "tests", "golden", "sampling_golden.npz"))
+    sch = EulerDiscreteScheduler.from_pretrained("stabilityai/stable-diffusion-xl-base-1.0", subfolder="scheduler")
+    den = S.DiscreteEpsDDPMDenoiser(lambda x, t, **k: 0.3 * x + 0.01 * t.view(-1, 1, 1, 1), sch.alphas_cumprod, False)
+    sig, tt = torch.from_numpy(g["sigma_in"]), torch.from_numpy(g["t_in"])
+    assert np.array_equal(den.sigma_to_t(sig).numpy(), g["sigma_to_t"])
+    assert np.array_equal(den.sigma_to_t(sig, quantize=True).numpy(), g["sigma_to_t_quant"])
+    assert np.array_equal(den.t_to_sigma(tt).numpy(), g["t_to_sigma"])
+    assert np.array_equal(den.get_sigmas(7).numpy(), g["get_sigmas_7"])
+    x, s4 = torch.from_numpy(g["x"]), torch.from_numpy(g["s4"])
+    assert np.array_equal(den(x, s4).numpy(), g["denoised"])
+    assert np.array_equal(den(x, s4, sigma_cond=s4 * 0.5).numpy(), g["denoised_cond"])
+
+
+def test_euler_ancestral_and_cfg_algebra():
+    """k-diffusion's `get_ancestral_step` / `to_d` identities and the CFG combination of cfg.py:113-125."""
+    from uwudiff_b200 import sampling as S
+
+    sd, su = S.get_ancestral_step(torch.tensor(3.0), torch.tensor(1.0), eta=1.0)
+    assert abs(float(sd) ** 2 + float(su) ** 2 - 1.0) < 1e-6 and float(su) <= 1.0      # sigma_down^2 + sigma_up^2 = sigma_to^2
+    assert S.get_ancestral_step(torch.tensor(3.0), torch.tensor(1.0), eta=0.0) == (torch.tensor(1.0), 0.0)
+    x = torch.randn(2, 4, 8, 8)
+    # an exact denoiser (x0 known): one deterministic Euler step to sigma = 0 lands on x0
+    x0 = torch.randn(2, 4, 8, 8)
+    noisy = x0 + 5.0 * torch.randn(2, 4, 8, 8)
+    out = S.sample_euler_ancestral(lambda z, s, sigma_cond=None: (x0, None), noisy, torch.tensor([5.0, 0.0]), eta=0.0)
+    assert torch.allclose(out, x0, atol=1e-5)
+    # CFG: batch-doubled call, cond rows first; guidance 1 returns the conditional branch, 0 the unconditional one
+    calls = []
+
+    class W(S.DiscreteSchedule):
+        def forward(self, inp, sigma, sigma_cond=None, encoder_hidden_states=None, encoder_attention_mask=None, added_cond_kwargs=None):
+            calls.append((inp.shape[0], encoder_hidden_states.shape, added_cond_kwargs["text_embeds"].shape))
+            return inp * encoder_hidden_states.mean(dim=(1, 2)).view(-1, 1, 1, 1)
+
+    w = W(torch.linspace(0.03, 14.6, 1000), False)
+    emb, nemb = torch.full((2, 77, 16), 2.0), torch.full((2, 60, 16), 77.0 / 60.0 * 3.0)  # shorter negative context is zero-padded
+    pool, npool = torch.randn(2, 8), torch.randn(2, 8)
+    for cfg, expect in ((1.0, 2.0), (0.0, 3.0), (3.0, 3.0 + (2.0 - 3.0) * 3.0)):
+        fn = S.cfg_wrapper_from_embeddings(emb, pool, None, nemb, npool, None, 1024, 1024, w, cfg=cfg)
+        y, unc = fn(x, torch.ones(2))
+        assert torch.allclose(y, x * expect, atol=1e-5) and torch.allclose(unc, x * 3.0, atol=1e-5)
+    assert calls[0] == (4, torch.Size([4, 77, 16]), torch.Size([4, 8]))
+    assert S.truncate_or_pad_to_length(["a", "b"], 5, "cycling") == ["a", "b", "a", "b", "a"]
+    assert S.truncate_or_pad_to_length(["a", "b"], 3, "repeat_last") == ["a", "b", "b"]

@@ -508,8 +508,8 @@ def test_fused_geglu_epilogues_are_bit_identical_to_the_unfused_kernels(M, C, F)
     from uwudiff_b200 import ops
     from uwudiff_b200._lib import B_KN
 
-    if not ops.geglu_fusable(M, F):
-        pytest.skip("fused GEGLU disabled (UWU_GEGLU_FUSE=0 / UWU_GEMM_PAIR=0)")
+    if not ops.geglu_kernels_available(M, F):
+        pytest.skip("fused GEGLU needs the CTA-pair kernel (UWU_GEMM_PAIR=0)")
     g = torch.Generator(device="cuda").manual_seed(M + F)
     x = (torch.randn(M, C, device="cuda", generator=g) * 0.5).to(torch.bfloat16)
     w1 = (torch.randn(2 * F, C, device="cuda", generator=g) * C ** -0.5).to(torch.bfloat16)

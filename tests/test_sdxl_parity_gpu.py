@@ -237,8 +237,8 @@ def test_full_sdxl_step_end_to_end_vs_oracle(world):
     gy = torch.cat([grads_y[n].flatten() for n in names_p])
     rep["adapter_params"] = int(go.numel())
     rep["adapter_tensors"] = len(errs)
-    rep["adapter_grad_cos"] = torch.nn.functional.cosine_similarity(gp, go, dim=0).item()
-    rep["adapter_grad_cos_yardstick"] = torch.nn.functional.cosine_similarity(gy, go, dim=0).item()
+    rep["adapter_grad_cos"] = torch.nn.functional.cosine_similarity(gp.double(), go.double(), dim=0).item()
+    rep["adapter_grad_cos_yardstick"] = torch.nn.functional.cosine_similarity(gy.double(), go.double(), dim=0).item()
     rep["adapter_grad_norm_rel"] = abs(gp.norm() - go.norm()).item() / go.norm().item()
     rep["adapter_grad_global_rms"], rep["adapter_grad_global_rms_yardstick"] = rms(gp, go), rms(gy, go)
     sv, sy = sorted(errs.values()), sorted(yerrs.values())
@@ -336,7 +336,7 @@ def test_full_sdxl_per_layer_teacher_forced(world):
             yy.backward(dout.cuda().to(yy.dtype))
         row = dict(block=name, kind="resnet" if is_res else "transformer")
         y_out = rel(yy, yref)
-        y_branch = rel(yy.float().cpu() - xin, yref - xin)
+        y_branch = rel(yy.float().cpu() - xin, yref - xin) if yy.shape == xin.shape else None
         y_dx = rel(xg.grad, dxref) if dxref is not None else None
         y_g = {n2: rel(og[n2].grad, po[n2]) for n2 in gnames}
         # ---- product ----

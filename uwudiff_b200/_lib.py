@@ -96,6 +96,7 @@ SIGNATURES = {
     "uwu_layernorm_fwd": (C.c_int, [_P, _I32, _I32, _F, _P, _P, _P, _P, _I32, _P, _P, _P]),
     "uwu_layernorm_bwd_workspace_floats": (C.c_int64, [_I32, _I32]),
     "uwu_layernorm_bwd": (C.c_int, [_P, _P, _I32, _I32, _P, _P, _P, _P, _P, _P, _I32, _P, _P]),
+    "uwu_softmax_rows": (C.c_int, [_P, _I64, _I32, _I64, _P]),
     "uwu_geglu_fwd": (C.c_int, [_P, _I64, _I32, _P, _P]),
     "uwu_geglu_bwd": (C.c_int, [_P, _P, _I64, _I32, _P, _P]),
     "uwu_elementwise": (C.c_int, [_P, _P, _I64, _I32, _P, _P]),

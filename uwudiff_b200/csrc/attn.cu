@@ -58,7 +58,7 @@ static constexpr int FWD_BAR = (6 + 2 * FWD_ST) * AT_TILE;
 static constexpr int FWD_SMEM = FWD_BAR + 256 + 1024;
 static constexpr int FWD_THREADS = 320;
 
-__global__ void __launch_bounds__(FWD_THREADS, 1) attn_fwd_kernel(const __grid_constant__ AttnFwdArgs p) {
+__global__ void __maxnreg__(200) attn_fwd_kernel(const __grid_constant__ AttnFwdArgs p) {
     pdl_trigger();
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = align1024(smem_raw);
@@ -206,101 +206,131 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) attn_fwd_kernel(const __grid_c
                 tc_fence_after();
                 const int kv_valid = min(128, p.Lk - j * 128);
                 const bool full = kv_valid == 128;
-                // pass 1: row maximum (3-input max: two scores per instruction); TMEM loads issued in pairs
-                float mx = -INFINITY;
-#pragma unroll
-                for (int cp = 0; cp < 2; ++cp) {
-                    uint32_t ra[32], rb[32];
-                    tmem_ld32(t_s + (uint32_t)(cp * 64), ra);
-                    tmem_ld32(t_s + (uint32_t)(cp * 64 + 32), rb);
+                float rs = 0.f;
+                if (full) {
+                    // ---- full key tile: S is read from TMEM ONCE (128 registers per thread).  TMEM reads are the scarcest
+                    // resource of this kernel: 128 lanes x 128 fp32 columns = 64 KiB per tile, and the tensor-memory load path
+                    // delivers on the order of 64 B / clock / SM, so every extra pass over S costs ~1000 cycles per tile ----
+                    uint32_t sr[4][32];
+                    tmem_ld32(t_s, sr[0]);
+                    tmem_ld32(t_s + 32u, sr[1]);
+                    tmem_ld32(t_s + 64u, sr[2]);
+                    tmem_ld32(t_s + 96u, sr[3]);
                     tmem_ld_wait();
-                    if (full) {
-                        // four independent max chains (a single chain is a 4-cycle-latency dependency per element pair)
-                        float m0 = mx, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+                    float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
 #pragma unroll
-                        for (int i = 0; i < 32; i += 4) {
-                            m0 = fmax3(m0, __uint_as_float(ra[i]), __uint_as_float(ra[i + 1]));
-                            m1 = fmax3(m1, __uint_as_float(ra[i + 2]), __uint_as_float(ra[i + 3]));
-                            m2 = fmax3(m2, __uint_as_float(rb[i]), __uint_as_float(rb[i + 1]));
-                            m3 = fmax3(m3, __uint_as_float(rb[i + 2]), __uint_as_float(rb[i + 3]));
+                    for (int i = 0; i < 32; i += 2) {
+                        m0 = fmax3(m0, __uint_as_float(sr[0][i]), __uint_as_float(sr[0][i + 1]));
+                        m1 = fmax3(m1, __uint_as_float(sr[1][i]), __uint_as_float(sr[1][i + 1]));
+                        m2 = fmax3(m2, __uint_as_float(sr[2][i]), __uint_as_float(sr[2][i + 1]));
+                        m3 = fmax3(m3, __uint_as_float(sr[3][i]), __uint_as_float(sr[3][i + 1]));
+                    }
+                    const float m_new = fmaxf(m, fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)));
+                    if (j == 0) {
+                        m = m_new;
+                    } else if (__any_sync(0xffffffffu, (m_new - m) * sl2 > 8.0f)) {
+                        // rare: bring O (complete up to the previous key tile) and l to the new reference maximum
+                        mbar_wait(&pv_full[t], (uint32_t)((j - 1) & 1));
+                        tc_fence_after();
+                        const float alpha = ex2_approx((m - m_new) * sl2);
+#pragma unroll
+                        for (int c = 0; c < 2; ++c) {
+                            uint32_t r[32];
+                            tmem_ld32(t_pv + (uint32_t)(c * 32), r);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
+                            tmem_st32(t_pv + (uint32_t)(c * 32), r);
                         }
-                        mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
-                    } else {
+                        tmem_st_wait();
+                        l *= alpha;
+                        m = m_new;
+                    }
+                    const float msl = m * sl2;
+                    // the P V product of the previous key tile must have finished reading the P buffer before it is overwritten
+                    if (j > 0) mbar_wait(&pv_full[t], (uint32_t)((j - 1) & 1));
+                    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;  // independent partial row sums (no serial FADD chain)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+#pragma unroll
+                        for (int q4 = 0; q4 < 4; ++q4) {
+                            float e[8];
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) e[i] = ex2_approx(fmaf(__uint_as_float(sr[c][q4 * 8 + i]), sl2, -msl));
+                            s0 += e[0] + e[4];
+                            s1 += e[1] + e[5];
+                            s2 += e[2] + e[6];
+                            s3 += e[3] + e[7];
+                            uint4 u;
+                            u.x = pack_bf16(e[0], e[1]);
+                            u.y = pack_bf16(e[2], e[3]);
+                            u.z = pack_bf16(e[4], e[5]);
+                            u.w = pack_bf16(e[6], e[7]);
+                            const int cc = (c & 1) * 4 + q4;
+                            st_shared_v4(prow_s + (uint32_t)((c >> 1) * AT_TILE + ((cc ^ sw) << 4)), u);
+                        }
+                    }
+                    rs = (s0 + s1) + (s2 + s3);
+                } else {
+                    // ---- ragged last key tile (Lk % 128 != 0): two masked passes over TMEM ----
+                    float mx = -INFINITY;
+#pragma unroll
+                    for (int cp = 0; cp < 2; ++cp) {
+                        uint32_t ra[32], rb[32];
+                        tmem_ld32(t_s + (uint32_t)(cp * 64), ra);
+                        tmem_ld32(t_s + (uint32_t)(cp * 64 + 32), rb);
+                        tmem_ld_wait();
 #pragma unroll
                         for (int i = 0; i < 32; ++i) {
                             if (cp * 64 + i < kv_valid) mx = fmaxf(mx, __uint_as_float(ra[i]));
                             if (cp * 64 + 32 + i < kv_valid) mx = fmaxf(mx, __uint_as_float(rb[i]));
                         }
                     }
-                }
-                const float m_new = fmaxf(m, mx);
-                if (j == 0) {
-                    m = m_new;
-                } else if (__any_sync(0xffffffffu, (m_new - m) * sl2 > 8.0f)) {
-                    // rare: bring O (complete up to the previous key tile) and l to the new reference maximum
-                    mbar_wait(&pv_full[t], (uint32_t)((j - 1) & 1));
-                    tc_fence_after();
-                    const float alpha = ex2_approx((m - m_new) * sl2);
+                    const float m_new = fmaxf(m, mx);
+                    if (j == 0) {
+                        m = m_new;
+                    } else if (__any_sync(0xffffffffu, (m_new - m) * sl2 > 8.0f)) {
+                        mbar_wait(&pv_full[t], (uint32_t)((j - 1) & 1));
+                        tc_fence_after();
+                        const float alpha = ex2_approx((m - m_new) * sl2);
 #pragma unroll
-                    for (int c = 0; c < 2; ++c) {
-                        uint32_t r[32];
-                        tmem_ld32(t_pv + (uint32_t)(c * 32), r);
-                        tmem_ld_wait();
+                        for (int c = 0; c < 2; ++c) {
+                            uint32_t r[32];
+                            tmem_ld32(t_pv + (uint32_t)(c * 32), r);
+                            tmem_ld_wait();
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
-                        tmem_st32(t_pv + (uint32_t)(c * 32), r);
-                    }
-                    tmem_st_wait();
-                    l *= alpha;
-                    m = m_new;
-                }
-                const float msl = m * sl2;
-                // the P V product of the previous key tile must have finished reading the P buffer before it is overwritten
-                if (j > 0) mbar_wait(&pv_full[t], (uint32_t)((j - 1) & 1));
-                // pass 2: probabilities -> bf16 -> swizzled smem, row sum; the TMEM load of chunk c+1 is in flight while
-                // chunk c is exponentiated
-                float rs = 0.f;
-                uint32_t rbuf[2][32];
-                tmem_ld32(t_s, rbuf[0]);
-                tmem_ld_wait();
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    if (c < 3) tmem_ld32(t_s + (uint32_t)((c + 1) * 32), rbuf[(c + 1) & 1]);
-                    const uint32_t(&r)[32] = rbuf[c & 1];
-                    float pe[32];
-                    if (full) {
-                        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;  // independent partial row sums (no serial FADD chain)
-#pragma unroll
-                        for (int i = 0; i < 32; i += 4) {
-                            pe[i] = ex2_approx(fmaf(__uint_as_float(r[i]), sl2, -msl));
-                            pe[i + 1] = ex2_approx(fmaf(__uint_as_float(r[i + 1]), sl2, -msl));
-                            pe[i + 2] = ex2_approx(fmaf(__uint_as_float(r[i + 2]), sl2, -msl));
-                            pe[i + 3] = ex2_approx(fmaf(__uint_as_float(r[i + 3]), sl2, -msl));
-                            s0 += pe[i];
-                            s1 += pe[i + 1];
-                            s2 += pe[i + 2];
-                            s3 += pe[i + 3];
+                            for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
+                            tmem_st32(t_pv + (uint32_t)(c * 32), r);
                         }
-                        rs += (s0 + s1) + (s2 + s3);
-                    } else {
+                        tmem_st_wait();
+                        l *= alpha;
+                        m = m_new;
+                    }
+                    const float msl = m * sl2;
+                    if (j > 0) mbar_wait(&pv_full[t], (uint32_t)((j - 1) & 1));
+#pragma unroll 1
+                    for (int c = 0; c < 4; ++c) {
+                        uint32_t r[32];
+                        tmem_ld32(t_s + (uint32_t)(c * 32), r);
+                        tmem_ld_wait();
+                        float pe[32];
 #pragma unroll
                         for (int i = 0; i < 32; ++i) {
                             const float e = ex2_approx(fmaf(__uint_as_float(r[i]), sl2, -msl));
                             pe[i] = (c * 32 + i < kv_valid) ? e : 0.f;
                             rs += pe[i];
                         }
-                    }
 #pragma unroll
-                    for (int q4 = 0; q4 < 4; ++q4) {
-                        uint4 u;
-                        u.x = pack_bf16(pe[q4 * 8 + 0], pe[q4 * 8 + 1]);
-                        u.y = pack_bf16(pe[q4 * 8 + 2], pe[q4 * 8 + 3]);
-                        u.z = pack_bf16(pe[q4 * 8 + 4], pe[q4 * 8 + 5]);
-                        u.w = pack_bf16(pe[q4 * 8 + 6], pe[q4 * 8 + 7]);
-                        const int cc = (c & 1) * 4 + q4;
-                        st_shared_v4(prow_s + (uint32_t)((c >> 1) * AT_TILE + ((cc ^ sw) << 4)), u);
+                        for (int q4 = 0; q4 < 4; ++q4) {
+                            uint4 u;
+                            u.x = pack_bf16(pe[q4 * 8 + 0], pe[q4 * 8 + 1]);
+                            u.y = pack_bf16(pe[q4 * 8 + 2], pe[q4 * 8 + 3]);
+                            u.z = pack_bf16(pe[q4 * 8 + 4], pe[q4 * 8 + 5]);
+                            u.w = pack_bf16(pe[q4 * 8 + 6], pe[q4 * 8 + 7]);
+                            const int cc = (c & 1) * 4 + q4;
+                            st_shared_v4(prow_s + (uint32_t)((c >> 1) * AT_TILE + ((cc ^ sw) << 4)), u);
+                        }
                     }
-                    if (c < 3) tmem_ld_wait();
                 }
                 l += rs;
                 tc_fence_before();

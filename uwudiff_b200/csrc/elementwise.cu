@@ -419,6 +419,69 @@ static int ew_grid(long long work, int threads) {
 using namespace uwu;
 typedef __nv_bfloat16 bf16;
 
+// Row softmax of a bf16 matrix, in place: x[r, :] = softmax(x[r, :]).  Used by the frozen VAE encoder's single-head attention
+// (head_dim 512 — outside the flash kernels' range; S = Q K^T and P V run on the GEMM kernel).  One block per row, the row is
+// read three times from L2 (max, sum, write).
+__global__ void __launch_bounds__(256) softmax_rows_kernel(__nv_bfloat16* __restrict__ x, long long ld, int N) {
+    __nv_bfloat16* row = x + (size_t)blockIdx.x * ld;
+    __shared__ float red[8];
+    __shared__ float bc;
+    const int nv = N >> 3;
+    float mx = -INFINITY;
+    for (int v = threadIdx.x; v < nv; v += blockDim.x) {
+        float f[8];
+        ld8e(row + v * 8, f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) mx = fmaxf(mx, f[j]);
+    }
+    mx = warp_max(mx);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float m = red[0];
+        for (int w = 1; w < 8; ++w) m = fmaxf(m, red[w]);
+        bc = m;
+    }
+    __syncthreads();
+    mx = bc;
+    float sum = 0.f;
+    for (int v = threadIdx.x; v < nv; v += blockDim.x) {
+        float f[8];
+        ld8e(row + v * 8, f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sum += __expf(f[j] - mx);
+    }
+    sum = warp_sum(sum);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int w = 0; w < 8; ++w) t += red[w];
+        bc = 1.0f / t;
+    }
+    __syncthreads();
+    const float inv = bc;
+    for (int v = threadIdx.x; v < nv; v += blockDim.x) {
+        float f[8];
+        ld8e(row + v * 8, f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = __expf(f[j] - mx) * inv;
+        st8e(row + v * 8, f);
+    }
+}
+
+extern "C" int uwu_softmax_rows(void* x, int64_t M, int32_t N, int64_t ld, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    UWU_CHECK_ARG(M >= 0 && N > 0 && N % 8 == 0 && ld >= N && ld % 8 == 0, "uwu_softmax_rows: bad shape M=%lld N=%d ld=%lld",
+                  (long long)M, N, (long long)ld);
+    if (M == 0) return UWU_OK;
+    UWU_CHECK_ARG(x && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && M < (1ll << 31), "uwu_softmax_rows: bad pointer / too many rows");
+    softmax_rows_kernel<<<(unsigned)M, 256, 0, stream>>>(reinterpret_cast<bf16*>(x), ld, N);
+    UWU_CHECK_LAUNCH();
+    return UWU_OK;
+}
+
 extern "C" int uwu_geglu_fwd(const void* in, int64_t M, int32_t F, void* out, void* stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     UWU_CHECK_ARG(M >= 0 && F > 0 && F % 8 == 0, "uwu_geglu_fwd: bad shape M=%lld F=%d", (long long)M, F);

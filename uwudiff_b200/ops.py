@@ -107,9 +107,21 @@ _GEGLU_FUSE = os.environ.get("UWU_GEGLU_FUSE", "1") != "0"
 _PAIR_ON = os.environ.get("UWU_GEMM_PAIR", "2") != "0"
 
 
-def geglu_fusable(M: int, F: int) -> bool:
+# measured in the step (profiles/r02_step_breakdown_*.log): the forward fusion saves ~80 us per 1280-wide block (375 vs 350 + 103
+# us); the backward fusion LOSES (385 vs 177 + 155 us): cdf / pdf / two products per element on the 128 epilogue threads of a
+# CTA take as long as the K = 1280 main loop, where the stand-alone kernel spreads the same math over 2048 threads per SM.
+# It stays available (UWU_GEGLU_FUSE_BWD=1) and bit-exact, but is off by default.
+_GEGLU_FUSE_BWD = os.environ.get("UWU_GEGLU_FUSE_BWD", "0") != "0"
+
+
+def geglu_fusable(M: int, F: int, backward: bool = False) -> bool:
     """The GEGLU epilogues live in the CTA-pair GEMM kernel: at least two 128-row tiles, F a multiple of 256."""
-    return _GEGLU_FUSE and _PAIR_ON and M >= 256 and F % 256 == 0
+    return _GEGLU_FUSE and (_GEGLU_FUSE_BWD or not backward) and _PAIR_ON and M >= 256 and F % 256 == 0
+
+
+def geglu_kernels_available(M: int, F: int) -> bool:
+    """Shapes the fused epilogues support at all (tests exercise both directions regardless of the default)."""
+    return _PAIR_ON and M >= 256 and F % 256 == 0
 
 
 def gemm_geglu_fwd(x: torch.Tensor, w: torch.Tensor, M: int, F: int, K: int, bias: Optional[torch.Tensor], lda: Optional[int] = None):
@@ -391,6 +403,14 @@ def layernorm_bwd(x, dy, gamma, stats, dres=None, dgamma=None, dbeta=None, accum
     check(lib().uwu_layernorm_bwd(_ptr(x), _ptr(dy), M, C, _ptr(gamma), _ptr(stats), _ptr(dres), _ptr(dx), _ptr(dgamma),
                                   _ptr(dbeta), int(accumulate), _ptr(ws), _stream()), "uwu_layernorm_bwd")
     return dx
+
+
+def softmax_rows_(x: torch.Tensor) -> torch.Tensor:
+    """In-place softmax over the last dim of a bf16 [M, N] matrix (row stride may exceed N)."""
+    _req_cuda(x)
+    assert x.dtype == torch.bfloat16 and x.dim() == 2 and x.stride(1) == 1
+    check(lib().uwu_softmax_rows(_ptr(x), x.shape[0], x.shape[1], x.stride(0), _stream()), "uwu_softmax_rows")
+    return x
 
 
 def geglu_fwd(x: torch.Tensor) -> torch.Tensor:

@@ -339,6 +339,11 @@ class DMTrainer(BaseTrainer):
         if f["buckets"] is not None:
             f["buckets"].enabled = False  # the exchange runs between the two graphs, on the flat gradient buffer
         k = f["accum"]
+        # autograd leaves created before the capture carry the (legacy) stream they were created on: their gradient
+        # accumulation would be scheduled there, which stream capture forbids -> the denoiser's graph hook is re-created
+        # inside the capture
+        if hasattr(self.unet, "_hook"):
+            self.unet._hook = None
         torch.cuda.synchronize()
         torch.cuda.empty_cache()  # the graphs' private pool needs the room the eager steps' cached blocks occupy
         n0 = ops.launch_count()

@@ -533,7 +533,7 @@ class FeedForward(nn.Module):
         self._sv = None
         lin2 = self.net[2]
         F = lin2.in_features
-        if ops.geglu_fusable(st.M, F):
+        if ops.geglu_fusable(st.M, F, backward=True):
             # GEGLU backward in the epilogue of the down-projection's data-gradient GEMM: d(h * gelu(g)) never reaches HBM
             lin2.param_grads(dx, g, st.M)
             dp = ops.gemm_geglu_bwd(dx, lin2._cache, p, st.M, F, lin2.out_features, lda=dx.stride(0))
