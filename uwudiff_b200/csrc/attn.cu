@@ -58,7 +58,7 @@ static constexpr int FWD_BAR = (6 + 2 * FWD_ST) * AT_TILE;
 static constexpr int FWD_SMEM = FWD_BAR + 256 + 1024;
 static constexpr int FWD_THREADS = 320;
 
-__global__ void __maxnreg__(200) attn_fwd_kernel(const __grid_constant__ AttnFwdArgs p) {
+__global__ void __maxnreg__(192) attn_fwd_kernel(const __grid_constant__ AttnFwdArgs p) {
     pdl_trigger();
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = align1024(smem_raw);

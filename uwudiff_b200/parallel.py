@@ -17,7 +17,7 @@ import torch.distributed as dist
 
 
 class GradientBuckets:
-    def __init__(self, trainer, process_group=None, n_buckets: int = 4):
+    def __init__(self, trainer, process_group=None, n_buckets: int = 0):
         self.group = process_group
         self.world = dist.get_world_size(process_group)
         self.backend = dist.get_backend(process_group)
@@ -50,6 +50,10 @@ class GradientBuckets:
             if mine:
                 self._block_start[id(top)] = min(mine)
         n = self.flat.numel()
+        if n_buckets <= 0:
+            # ~64 MiB per exchange: the LyCORIS buffer (210 MB) goes out in 4 pieces, the full fine-tuning buffers (DiT 2.7 GB,
+            # SD-1.5 3.4 GB) in 32, so that only a small last bucket is left to run after the backward pass has finished
+            n_buckets = max(4, min(32, (n * 4 + (64 << 20) - 1) // (64 << 20)))
         n_buckets = max(1, min(n_buckets, n // 1024 or 1))
         step = (n + n_buckets - 1) // n_buckets
         step = (step + 255) // 256 * 256

@@ -246,7 +246,7 @@ class DMTrainer(BaseTrainer):
 
     # ---- what Lightning's fit loop did around training_step -----------------------------------------------------
     def setup_fit(self, gradient_clip_val: Optional[float] = None, process_group=None, seed: Optional[int] = None,
-                  n_buckets: int = 4, accumulate_grad_batches: int = 1, cuda_graph: bool = False, graph_warmup_steps: int = 2):
+                  n_buckets: int = 0, accumulate_grad_batches: int = 1, cuda_graph: bool = False, graph_warmup_steps: int = 2):
         """`accumulate_grad_batches` is Lightning's Trainer option of the same name (the `lightning_config` block of the YAMLs
         is passed to pl.Trainer verbatim): k micro-batches share one optimizer step, each loss scaled by 1/k; the gradient
         exchange runs once, during the last micro-batch's backward (BASELINE.json configs[4]: global batch 128 on fewer GPUs
