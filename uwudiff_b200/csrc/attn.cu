@@ -58,7 +58,7 @@ static constexpr int FWD_BAR = (6 + 2 * FWD_ST) * AT_TILE;
 static constexpr int FWD_SMEM = FWD_BAR + 256 + 1024;
 static constexpr int FWD_THREADS = 320;
 
-__global__ void __maxnreg__(192) attn_fwd_kernel(const __grid_constant__ AttnFwdArgs p) {
+__global__ void __launch_bounds__(FWD_THREADS, 1) attn_fwd_kernel(const __grid_constant__ AttnFwdArgs p) {
     pdl_trigger();
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = align1024(smem_raw);
@@ -233,14 +233,16 @@ __global__ void __maxnreg__(192) attn_fwd_kernel(const __grid_constant__ AttnFwd
                         mbar_wait(&pv_full[t], (uint32_t)((j - 1) & 1));
                         tc_fence_after();
                         const float alpha = ex2_approx((m - m_new) * sl2);
-#pragma unroll
-                        for (int c = 0; c < 2; ++c) {
-                            uint32_t r[32];
-                            tmem_ld32(t_pv + (uint32_t)(c * 32), r);
+                        // 8 columns at a time: the 128 score registers stay live across this (rare) path, a 32-register
+                        // temporary here would push them onto the stack in the common path
+#pragma unroll 1
+                        for (int c = 0; c < 8; ++c) {
+                            uint32_t r[8];
+                            tmem_ld8(t_pv + (uint32_t)(c * 8), r);
                             tmem_ld_wait();
 #pragma unroll
-                            for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
-                            tmem_st32(t_pv + (uint32_t)(c * 32), r);
+                            for (int i = 0; i < 8; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
+                            tmem_st8(t_pv + (uint32_t)(c * 8), r);
                         }
                         tmem_st_wait();
                         l *= alpha;
