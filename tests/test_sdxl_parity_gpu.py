@@ -327,16 +327,18 @@ def test_full_sdxl_per_layer_teacher_forced(world):
         is_res = isinstance(om, U.ResnetBlock2D)
         gnames = [] if is_res else [n2 for n2 in po if n2.startswith("lycoris_" + name.replace(".", "_") + "_")]
         # ---- yardstick: the oracle block itself, stock PyTorch on the GPU under autocast(bf16), same inputs ----
-        xg = xin.cuda().requires_grad_(dxref is not None)
+        # (like the product, the yardstick gets the block input and the output gradient rounded to bf16: in the real bf16-mixed
+        # run both arrive from bf16 producers — proj_in / the previous block — so the residual stream of the block is bf16)
+        xg = xin.cuda().to(torch.bfloat16).requires_grad_(dxref is not None)
         for n2 in gnames:
             og[n2].grad = None
         with torch.autocast("cuda", dtype=torch.bfloat16):
             yy = om(xg, emb_gpu) if is_res else om(xg, ctx_gpu)
         if dout is not None and (dxref is not None or gnames):
-            yy.backward(dout.cuda().to(yy.dtype))
+            yy.backward(dout.cuda().to(torch.bfloat16).to(yy.dtype))
         row = dict(block=name, kind="resnet" if is_res else "transformer")
         y_out = rel(yy, yref)
-        y_branch = rel(yy.float().cpu() - xin, yref - xin) if yy.shape == xin.shape else None
+        y_branch = rel(yy.float().cpu() - xg.detach().float().cpu(), yref - xin) if yy.shape == xin.shape else None
         y_dx = rel(xg.grad, dxref) if dxref is not None else None
         y_g = {n2: rel(og[n2].grad, po[n2]) for n2 in gnames}
         # ---- product ----

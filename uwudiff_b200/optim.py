@@ -6,6 +6,7 @@ synchronisation.  State-dict layout (`state[p] = {step, exp_avg, exp_avg_sq}`) m
 """
 from __future__ import annotations
 
+import math
 from typing import Iterable, Optional
 
 import torch
@@ -107,7 +108,7 @@ class FusedAdamW(torch.optim.Optimizer):
         # the C ABI takes the betas as fp32 and forms the corrections in double from those (uwu_mt_adamw): same values here
         b1, b2 = (torch.tensor(b, dtype=torch.float32).item() for b in g["betas"])
         t = self._step + 1
-        return [float(g["lr"]), 1.0 - b1 ** t, (1.0 - b2 ** t) ** 0.5]
+        return [float(g["lr"]), 1.0 - math.pow(b1, t), math.sqrt(1.0 - math.pow(b2, t))]  # same libm calls as the C side
 
     @torch.no_grad()
     def step(self, closure=None, hyper_dev=None):
