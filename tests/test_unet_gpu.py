@@ -505,33 +505,42 @@ def _batches(n, B=2, seed=11):
     return [(torch.randn(B, 4, 16, 16, generator=g).cuda(), ["DUMMY TEST"] * B, [], {"time_ids": ids.cuda()}, {}) for _ in range(n)]
 
 
-def test_cuda_graph_step_is_bit_identical_to_the_eager_step():
+def test_cuda_graph_step_reproduces_the_eager_step():
     """`setup_fit(cuda_graph=True)`: after two eager optimizer steps the step is captured (forward + backward, clip + AdamW)
-    and replayed.  Same seeds, same batches: losses, timesteps and parameters after 6 steps equal the all-eager run BIT FOR
-    BIT (same kernels, same order; lr schedule, Adam bias correction, EMA decay and the noise stream advance on replay)."""
+    and replayed.  Same seeds, same batches, same kernels in the same order: timesteps are bit-equal, losses, gradient norms and
+    the parameters after 6 steps agree with the all-eager run to the noise floor of the fp32 atomic accumulations in the
+    split-K / dQ reductions (two EAGER runs differ by ~1.5e-8 in a few hundred parameters; a stale table or a missed
+    per-step scalar shows up at >= 3e-7 in the loss and 6e-5 in the gradient norm).  The lr schedule, Adam bias correction,
+    EMA decay and the noise stream must advance on replay.  Two graph runs in one process: host staging buffers of tables
+    uploaded during capture must outlive the capture."""
     from uwudiff_b200 import ops
 
     data = _batches(6)
     runs = []
-    for graph in (False, True):
+    for graph in (False, True, True):
         tr = _tiny_trainer()
         tr.setup_fit(gradient_clip_val=1.0, seed=1215, cuda_graph=graph, graph_warmup_steps=2)
-        losses, ts = [], []
+        losses, ts, norms = [], [], []
         n0 = ops.launch_count()
         for i, b in enumerate(data):
             out = tr.fit_step(b, i)
             losses.append(out["loss"].item())
+            norms.append(float(tr._fit["opt"].last_norm[0]))
             ts.append(out["aux_output"].timesteps.clone())
-        runs.append(dict(losses=losses, ts=ts, params=tr.lycoris_model.flat_params.clone(), ema=float(tr.ema_loss),
+        runs.append(dict(losses=losses, ts=ts, norms=norms, params=tr.lycoris_model.flat_params.clone(), ema=float(tr.ema_loss),
                          lr=tr._fit["opt"].param_groups[0]["lr"], launches=ops.launch_count() - n0, state=tr._fit["graph"]))
-    e, g = runs
-    assert g["state"]["state"] == "replay" and g["state"]["n_fwdbwd"] > 300
-    assert all(torch.equal(a, b) for a, b in zip(e["ts"], g["ts"])), "the noise / timestep stream must advance on replay"
-    assert len({tuple(t.tolist()) for t in g["ts"]}) > 1
-    assert e["losses"] == g["losses"], (e["losses"], g["losses"])
-    assert torch.equal(e["params"], g["params"])
-    assert abs(e["ema"] - g["ema"]) <= 1e-6 * abs(e["ema"]) and e["lr"] == g["lr"]
-    assert abs(e["launches"] - g["launches"]) <= 8, (e["launches"], g["launches"])  # replayed launches are counted
+    e = runs[0]
+    for g in runs[1:]:
+        assert g["state"]["state"] == "replay" and g["state"]["n_fwdbwd"] > 300
+        assert all(torch.equal(a, b) for a, b in zip(e["ts"], g["ts"])), "the noise / timestep stream must advance on replay"
+        assert len({tuple(t.tolist()) for t in g["ts"]}) > 1
+        for a, b in zip(e["losses"], g["losses"]):
+            assert abs(a - b) <= 1.5e-7 * abs(a), (e["losses"], g["losses"])
+        for a, b in zip(e["norms"], g["norms"]):
+            assert abs(a - b) <= 2e-6 * abs(a), (e["norms"], g["norms"])
+        assert (e["params"] - g["params"]).abs().max().item() <= 2e-7
+        assert abs(e["ema"] - g["ema"]) <= 1e-6 * abs(e["ema"]) and e["lr"] == g["lr"]
+        assert abs(e["launches"] - g["launches"]) <= 8, (e["launches"], g["launches"])  # replayed launches are counted
 
 
 def test_gradient_accumulation_on_the_gpu_matches_one_large_batch_of_gradients():

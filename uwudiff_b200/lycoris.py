@@ -401,9 +401,13 @@ class LycorisNetwork(nn.Module):
                 block0 += nb
                 ents.append(e)
             arr = (_lib.LokrGradEntry * n)(*ents)
-            table = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(pend[0][1].device)
-            t = (table, n, block0)
-            if len(self._grad_tables) > 64:
+            # staged through PINNED memory that lives as long as the table: under CUDA-graph capture the upload becomes a
+            # memcpy node that re-reads the host buffer on every replay (a pageable temporary would be freed by then)
+            host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).pin_memory()
+            table = torch.empty_like(host, device=pend[0][1].device)
+            table.copy_(host, non_blocking=True)
+            t = (table, n, block0, host)
+            if len(self._grad_tables) > 64 and not torch.cuda.is_current_stream_capturing():
                 self._grad_tables.clear()
             self._grad_tables[key] = t
         _lib.check(_lib.lib().uwu_lokr_grad_batch(t[0].data_ptr(), t[1], t[2], torch.cuda.current_stream().cuda_stream),

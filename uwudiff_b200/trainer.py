@@ -363,7 +363,9 @@ class DMTrainer(BaseTrainer):
             else:
                 f["opt"].zero_grad(set_to_none=False)
         n2 = ops.launch_count()
-        g.update(fwdbwd=ga, optstep=gb, n_fwdbwd=n1 - n0, n_opt=n2 - n1, out=out, state="replay")
+        # host staging buffers of tables uploaded inside the capture are re-read by every replay: keep them alive
+        keep = list(self.lycoris_model._grad_tables.values()) if self.lycoris_model is not None else []
+        g.update(fwdbwd=ga, optstep=gb, n_fwdbwd=n1 - n0, n_opt=n2 - n1, out=out, state="replay", keep=keep)
 
     def _write_hyper(self):
         """[lr, 1 - b1^t, sqrt(1 - b2^t), 0] per param group + [ema decay, 0, 0, 0]: one pinned H2D copy per step."""
