@@ -613,6 +613,149 @@ __global__ void __launch_bounds__(192, 4) ln_bwd_cols_kernel(const __nv_bfloat16
     }
 }
 
+// LayerNorm backward, streaming version: the rows are staged into shared memory by 1-D bulk copies (TMA) through an S-stage
+// mbarrier ring issued by one thread, so every block keeps (S - 1) stages of x / dy / dres in flight regardless of its
+// register count — the register-staged kernels above drain their loads at every per-row reduction and stop near 3.5 TB/s.
+// Thread = one 8-wide column vector (block = ceil(C/256) warps covers a row), R rows per stage; per-row sums through warp
+// shuffles + one __syncthreads per stage; dgamma / dbeta accumulate in registers (column ownership) and leave through
+// ONE 1-D bulk reduction per block (cp.reduce.async.bulk .add.f32) into the pre-zeroed / accumulating outputs.
+template <int R, bool kParamGrads>
+__global__ void __launch_bounds__(192) ln_bwd_stream_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
+                                                            int M, int C, const float* __restrict__ gamma,
+                                                            const float* __restrict__ stats, const __nv_bfloat16* __restrict__ dres,
+                                                            __nv_bfloat16* __restrict__ dx, float* __restrict__ dgamma,
+                                                            float* __restrict__ dbeta, int n_stages) {
+    pdl_trigger();
+    extern __shared__ __align__(128) uint8_t ln_smem[];
+    __shared__ __align__(8) uint64_t full[8];
+    __shared__ float part[2][R][8][2];  // [parity][row][warp][s1, s2]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    const int cv = C >> 3;
+    const int v = threadIdx.x;
+    const bool active = v < cv;
+    const float inv_c = 1.0f / (float)C;
+    const int n_arr = dres ? 3 : 2;
+    const uint32_t row_bytes = (uint32_t)C * 2u, arr_bytes = R * row_bytes, stage_bytes = n_arr * arr_bytes;
+    const int n_steps = (M - (int)blockIdx.x * R + (int)gridDim.x * R - 1) / ((int)gridDim.x * R);  // steps of this block
+
+    auto issue = [&](int it) {  // thread 0
+        const int r0 = ((int)blockIdx.x + it * (int)gridDim.x) * R;
+        const uint32_t bytes = (uint32_t)min(R, M - r0) * row_bytes;
+        const int sidx = it % n_stages;
+        uint8_t* dst = ln_smem + (size_t)sidx * stage_bytes;
+        mbar_expect_tx(&full[sidx], bytes * n_arr);
+        bulk_load_1d(dst, x + (size_t)r0 * C, bytes, &full[sidx]);
+        bulk_load_1d(dst + arr_bytes, dy + (size_t)r0 * C, bytes, &full[sidx]);
+        if (dres) bulk_load_1d(dst + 2 * arr_bytes, dres + (size_t)r0 * C, bytes, &full[sidx]);
+    };
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < n_stages; ++i) mbar_init(&full[i], 1);
+        fence_barrier_init();
+        for (int it = 0; it < n_stages - 1 && it < n_steps; ++it) issue(it);
+    }
+    float ga[8], ag[8], ab[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) ag[j] = ab[j] = 0.f, ga[j] = 1.0f;
+    if (active && gamma) ldf8(gamma + v * 8, ga);
+    __syncthreads();
+    for (int it = 0; it < n_steps; ++it) {
+        const int par = it & 1;
+        const int r0 = ((int)blockIdx.x + it * (int)gridDim.x) * R;
+        // the stage consumed in step it - 1 is free: every thread copied its vectors to registers before that step's barrier
+        if (threadIdx.x == 0 && it + n_stages - 1 < n_steps) issue(it + n_stages - 1);
+        const int sidx = it % n_stages;
+        const uint8_t* st = ln_smem + (size_t)sidx * stage_bytes + (size_t)v * 16;
+        float mean[R], rstd[R];
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+            const int row = r0 + k;
+            const float2 ms = row < M ? *reinterpret_cast<const float2*>(stats + (size_t)row * 2) : make_float2(0.f, 0.f);
+            mean[k] = ms.x;
+            rstd[k] = ms.y;
+        }
+        mbar_wait(&full[sidx], (uint32_t)(it / n_stages) & 1u);
+        uint4 rx[R], rd[R], rr[R];
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+            const bool ok = active && r0 + k < M;
+            rx[k] = ok ? *reinterpret_cast<const uint4*>(st + (size_t)k * row_bytes) : make_uint4(0, 0, 0, 0);
+            rd[k] = ok ? *reinterpret_cast<const uint4*>(st + arr_bytes + (size_t)k * row_bytes) : make_uint4(0, 0, 0, 0);
+            rr[k] = (ok && dres) ? *reinterpret_cast<const uint4*>(st + 2 * arr_bytes + (size_t)k * row_bytes) : make_uint4(0, 0, 0, 0);
+        }
+        float s1[R], s2[R];
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+            float f[8], d[8];
+            unpack8(rx[k], f);
+            unpack8(rd[k], d);
+            float a = 0.f, b = 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {  // inactive lanes / rows hold zeros
+                const float h = (f[j] - mean[k]) * rstd[k];
+                const float gv = d[j] * ga[j];
+                a += gv;
+                b = fmaf(gv, h, b);
+                if (kParamGrads) {
+                    ag[j] = fmaf(d[j], h, ag[j]);
+                    ab[j] += d[j];
+                }
+            }
+            s1[k] = warp_sum(a);
+            s2[k] = warp_sum(b);
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int k = 0; k < R; ++k) {
+                part[par][k][warp][0] = s1[k];
+                part[par][k][warp][1] = s2[k];
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+            float a = 0.f, b = 0.f;
+            for (int w = 0; w < nw; ++w) {
+                a += part[par][k][w][0];
+                b += part[par][k][w][1];
+            }
+            a *= inv_c;
+            b *= inv_c;
+            if (active && r0 + k < M) {
+                float f[8], d[8], e[8], o[8];
+                unpack8(rx[k], f);
+                unpack8(rd[k], d);
+                unpack8(rr[k], e);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float h = (f[j] - mean[k]) * rstd[k];
+                    o[j] = rstd[k] * (d[j] * ga[j] - a - h * b) + e[j];
+                }
+                st8(dx + (size_t)(r0 + k) * C + v * 8, o);
+            }
+        }
+    }
+    if (kParamGrads) {
+        // block partials -> shared -> one bulk reduction per output (stage 0 is free: all loads were consumed)
+        __syncthreads();
+        float* sh = reinterpret_cast<float*>(ln_smem);
+        if (active) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                sh[v * 8 + j] = ag[j];
+                sh[C + v * 8 + j] = ab[j];
+            }
+        }
+        fence_proxy_async();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            if (dgamma) bulk_reduce_add_f32(dgamma, sh, (uint32_t)C * 4u);
+            if (dbeta) bulk_reduce_add_f32(dbeta, sh + C, (uint32_t)C * 4u);
+            bulk_commit_group();
+            bulk_wait_group0();
+        }
+    }
+}
+
 // out[c] (+)= sum_p partial[p, c]
 __global__ void colsum_partials_kernel(const float* __restrict__ partial, int P, int stride, int n, int accumulate,
                                        float* __restrict__ out) {
@@ -778,6 +921,45 @@ extern "C" int uwu_layernorm_bwd(const void* x, const void* dy, int32_t M, int32
     UWU_CHECK_ARG(x && dy && dx && stats, "uwu_layernorm_bwd: null pointer");
     const bool want_pg = dgamma != nullptr || dbeta != nullptr;
     UWU_CHECK_ARG(!want_pg || workspace, "uwu_layernorm_bwd: workspace required for parameter gradients");
+    const bool aligned16 = (((uintptr_t)x | (uintptr_t)dy | (uintptr_t)dres | (uintptr_t)dx | (uintptr_t)dgamma | (uintptr_t)dbeta) & 15) == 0;
+    static const bool stream_off = getenv("UWU_LN_STREAM") && atoi(getenv("UWU_LN_STREAM")) == 0;
+    if (C <= 192 * 8 && aligned16 && !stream_off) {
+        // streaming kernel: R rows per stage so that a stage carries >= ~5 KB per array; stages sized to keep >= 3 blocks
+        // (or 160 KB) of loads in flight per SM
+        const int threads = ((C / 8 + 31) / 32) * 32;
+        const int R = C >= 1024 ? 2 : (C >= 512 ? 4 : 8);
+        const size_t stage = (size_t)(dres ? 3 : 2) * R * C * 2;
+        int n_stages = 4;
+        size_t smem = stage * n_stages;
+        if (smem < (size_t)2 * C * 4) smem = (size_t)2 * C * 4;
+        int per_sm = (int)((size_t)200 * 1024 / (smem + 1024));
+        if (per_sm > 4) per_sm = 4;
+        if (per_sm < 1) per_sm = 1;
+        int grid = (M + R - 1) / R;
+        if (grid > per_sm * sm_count()) grid = per_sm * sm_count();
+        if (want_pg && !accumulate) {
+            if (dgamma) UWU_CHECK_CUDA(cudaMemsetAsync(dgamma, 0, (size_t)C * 4, stream));
+            if (dbeta) UWU_CHECK_CUDA(cudaMemsetAsync(dbeta, 0, (size_t)C * 4, stream));
+        }
+#define UWU_LN_BWD_S(RR, PG)                                                                                                  \
+    do {                                                                                                                     \
+        static bool attr_done = false;                                                                                       \
+        if (!attr_done) {                                                                                                    \
+            UWU_CHECK_CUDA(cudaFuncSetAttribute(ln_bwd_stream_kernel<RR, PG>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+                                                200 * 1024));                                                                \
+            attr_done = true;                                                                                                \
+        }                                                                                                                    \
+        ln_bwd_stream_kernel<RR, PG><<<grid, threads, smem, stream>>>(                                                       \
+            reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<const __nv_bfloat16*>(dy), M, C, gamma, stats,       \
+            reinterpret_cast<const __nv_bfloat16*>(dres), reinterpret_cast<__nv_bfloat16*>(dx), dgamma, dbeta, n_stages);    \
+    } while (0)
+        if (R == 2) { if (want_pg) UWU_LN_BWD_S(2, true); else UWU_LN_BWD_S(2, false); }
+        else if (R == 4) { if (want_pg) UWU_LN_BWD_S(4, true); else UWU_LN_BWD_S(4, false); }
+        else { if (want_pg) UWU_LN_BWD_S(8, true); else UWU_LN_BWD_S(8, false); }
+#undef UWU_LN_BWD_S
+        UWU_CHECK_LAUNCH();
+        return UWU_OK;
+    }
     if (want_pg && C <= 192 * 8) {
         const int threads = ((C / 8 + 31) / 32) * 32;
         // at most one resident wave (register-limited blocks per SM): the kernel strides over the rows, so for the 160-thread

@@ -363,6 +363,7 @@ class DMTrainer(BaseTrainer):
             else:
                 f["opt"].zero_grad(set_to_none=False)
         n2 = ops.launch_count()
+        ops.add_graph_launches(-(n2 - n0))  # recorded, not executed: only replays count as launches
         # host staging buffers of tables uploaded inside the capture are re-read by every replay: keep them alive
         keep = list(self.lycoris_model._grad_tables.values()) if self.lycoris_model is not None else []
         g.update(fwdbwd=ga, optstep=gb, n_fwdbwd=n1 - n0, n_opt=n2 - n1, out=out, state="replay", keep=keep)
