@@ -367,6 +367,15 @@ int uwu_lokr_z(const void* x, int64_t ldx, const float* w1, int64_t M, int32_t o
                void* stream);
 int uwu_lokr_dw1(const void* v, const void* x, int64_t ldx, int64_t M, int32_t out_l, int32_t in_m, int32_t in_n,
                  float multiplier, float* dw1, void* stream);
+/* One-pass LoKr gradients for attention projections (w2 64x64, w1 <= 32x32): reads x [M, in_m*64] and dY [M, out_l*64] (bf16, row
+ * strides ldx / ldy) ONCE, forms Z = (w1 (x) I) X and V = X w2^T per 128-row tile on tcgen05, and accumulates
+ *   dw2 += multiplier * sum dY^T Z,   dw1[i, j] += multiplier * sum_t <dY[t, i, :], V[t, j, :]>
+ * in TMEM; results are added atomically into dw1 [out_l, in_m] / dw2 [64, 64] (fp32).  w1 / w2 are the fp32 masters (rounded
+ * to bf16 as MMA operands).  Replaces autograd through lycoris' `make_kron(w1, w2)` rebuild for the `Attention -> lokr,
+ * factor = 64` entries of configs/lycoris/sdxl-diffusers.toml (forward patch: src/duwu/trainer/trainer.py:152-154). */
+int uwu_lokr_fused_supported(int32_t out_l, int32_t out_k, int32_t in_m, int32_t in_n);
+int uwu_lokr_fused_grad(const void* x, int64_t ldx, const void* dy, int64_t ldy, int64_t M, int32_t out_l, int32_t in_m,
+                        const float* w1, const float* w2, float* dw1, float* dw2, float multiplier, void* stream);
 /* multi-tensor global grad norm: out2 = {||g||_2, min(1, max_norm/(norm+1e-6))}; tables are DEVICE arrays
  * (pointers as uint64, numels, and a chunk table (tensor index, chunk index) of n_chunks entries) */
 int uwu_mt_gradnorm(const uint64_t* g_ptrs, const int64_t* numels, const int32_t* chunk_tensor, const int32_t* chunk_index,

@@ -444,6 +444,29 @@ def test_lokr_factored_gradients(ops, M, ol, ok, im, inn):
     assert relerr(dw1, 1.5 * r1) < TOL_BF16 and relerr(dw2, 1.5 * r2) < TOL_BF16
 
 
+@pytest.mark.parametrize("M,ol,im", [(4096, 20, 20), (16384, 20, 20), (8192 + 5, 10, 10), (1232, 20, 32), (1000, 5, 5),
+                                      (70, 32, 20), (3, 20, 20), (65536, 10, 10)])
+def test_lokr_fused_one_pass_gradients(ops, M, ol, im):
+    """One-pass tcgen05 LoKr gradients (w2 64x64: the `Attention -> lokr, factor 64` adapters of the SDXL preset) == the
+    einsum over the full weight gradient G = dY^T X; dY is a column slice of a wider buffer (fused QKV), ragged last tile,
+    w1 wider / taller than square, accumulation with a multiplier."""
+    N, K = ol * 64, im * 64
+    wide = mk(M, N + 64, s=1.0)
+    dy = wide[:, 64:]
+    x = mk(M, K, s=1.0)
+    w1 = torch.randn(ol, im, device=DEV)
+    w2 = torch.randn(64, 64, device=DEV) * 0.5
+    dw1, dw2 = torch.zeros_like(w1), torch.zeros_like(w2)
+    assert ops.lokr_fused_supported(ol, 64, im, 64) and not ops.lokr_fused_supported(ol, 128, im, 64)
+    ops.lokr_fused_grad(dy, x, M, w1, w2, dw1, dw2, 1.0)
+    G4 = (dy.double().t() @ x.double()).view(ol, 64, im, 64)
+    r1 = torch.einsum("lkin,kn->li", G4, w2.to(torch.bfloat16).double()).float()
+    r2 = torch.einsum("lkin,li->kn", G4, w1.to(torch.bfloat16).double()).float()
+    assert relerr(dw1, r1) < TOL_BF16 and relerr(dw2, r2) < TOL_BF16, (relerr(dw1, r1), relerr(dw2, r2))
+    ops.lokr_fused_grad(dy, x, M, w1, w2, dw1, dw2, 0.5)  # accumulates, scaled
+    assert relerr(dw1, 1.5 * r1) < TOL_BF16 and relerr(dw2, 1.5 * r2) < TOL_BF16
+
+
 def test_lora_fold_and_grads(ops):
     N, K, r, scale = 640, 320, 4, 0.25
     W = torch.randn(N, K, device=DEV) * 0.1

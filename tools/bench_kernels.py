@@ -25,6 +25,21 @@ def timeit(fn, iters=20, warm=3):
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()
+    if os.environ.get("UWU_BENCH_GRAPH", "0") != "0":
+        # device time without the host's launch rate: `iters` calls captured into one CUDA graph, replayed
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for _ in range(iters):
+                fn()
+        g.replay()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / (3 * iters) * 1e3
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(iters):
@@ -132,6 +147,23 @@ def case_lokr_fact():
         bw(f"lokr_dw1 {tag}", timeit(lambda: ops.lokr_dw1(v, x, M, ol, im, inn, dw1)), M * (K + ol * inn) * 2)
         us = timeit(lambda: lokr_factored_grads(dy, x, M, w1, w2b, dw1, dw2))
         print(f"factored total {tag}: {us:.1f} us", flush=True)
+        G = torch.empty(N, K, device=dev)
+        us = timeit(lambda: (ops.gemm(dy, x, N, K, M, a_layout=A_COL, lda=N, b_layout=B_KN, ldb=K, out=G), ops.lokr_grad(G, w1, w2, dw1, dw2)))
+        print(f"G route total {tag}: {us:.1f} us", flush=True)
+
+
+def case_lokr_fused():
+    """One-pass LoKr gradients (attention adapters, w2 64x64) against the G = dY^T X route; bytes = one read of x and dY."""
+    for (M, ol, im) in [(16384, 20, 20), (65536, 10, 10), (4096, 20, 20)]:
+        N, K = ol * 64, im * 64
+        dy, x = mk(M, N), mk(M, K)
+        wide = mk(M, 3 * N)
+        w1, w2 = torch.randn(ol, im, device=dev), torch.randn(64, 64, device=dev)
+        dw1, dw2 = torch.zeros_like(w1), torch.zeros_like(w2)
+        tag = f"M{M} w1 {ol}x{im} w2 64x64"
+        bw(f"lokr_fused {tag}", timeit(lambda: ops.lokr_fused_grad(dy, x, M, w1, w2, dw1, dw2)), M * (N + K) * 2)
+        bw(f"lokr_fused x3 (QKV slices of one buffer) {tag}",
+           timeit(lambda: [ops.lokr_fused_grad(wide[:, i * N:(i + 1) * N], x, M, w1, w2, dw1, dw2) for i in range(3)]), 3 * M * (N + K) * 2)
         G = torch.empty(N, K, device=dev)
         us = timeit(lambda: (ops.gemm(dy, x, N, K, M, a_layout=A_COL, lda=N, b_layout=B_KN, ldb=K, out=G), ops.lokr_grad(G, w1, w2, dw1, dw2)))
         print(f"G route total {tag}: {us:.1f} us", flush=True)

@@ -109,6 +109,13 @@ def main(what):
         ops.gate_residual_fwd(xt, y, mod, 2 * C, L)
         ops.gate_residual_bwd(dyt, y, mod, 2 * C, L, dmod, 2 * C)
         ops.elementwise(mk(B * L, 4 * C), None, ops.EW_GELU_TANH)
+    elif what == "lokr_fused":
+        M, ol, im = 16384, 20, 20
+        dy, x = mk(M, ol * 64), mk(M, im * 64)
+        w1, w2 = torch.randn(ol, im, device=dev), torch.randn(64, 64, device=dev)
+        dw1, dw2 = torch.zeros_like(w1), torch.zeros_like(w2)
+        for _ in range(3):
+            ops.lokr_fused_grad(dy, x, M, w1, w2, dw1, dw2)
     elif what == "cross":
         # cross-attention forward at the step shape on both paths (UWU_ATTN_SHORT is read per call), column sums, conv pack
         B, heads, L, Lk = 16, 20, 1024, 77

@@ -48,6 +48,9 @@ def factorization(dimension: int, factor: int = -1):
     return m, n
 
 
+_LOKR_FUSED = os.environ.get("UWU_LOKR_FUSED", "1") != "0"
+
+
 class _Adapter(nn.Module):
     multiplier: float = 1.0
 
@@ -168,16 +171,28 @@ class LokrLinear(_Adapter):
         """Use the factored gradient (no G = dY^T X) when the factor shapes fit its kernels and it is cheaper than the
         full token-reduction GEMM: 2/in_m of the FLOPs, but four passes over [M, *]-sized data."""
         (ol, ok), (im, inn) = self.shape
+        if self.fused_ok(M):
+            return True
         # measured on B200 (profiles/r01_lokr_factored_stages.log): the factored route wins for the FeedForward adapters
         # (w2 2048x256: 263 vs 454 us, w2 1024x128: 404 vs 673 us) and loses for the 64x64 attention factors (135 vs 82 us),
         # whose four stages are latency / issue bound rather than FLOP bound
         return (self._w2_bf16 is not None and M >= 4096 and ol <= 32 and im <= 32 and im >= 4 and inn % 16 == 0 and ok % 8 == 0
                 and inn <= 256 and ok * inn >= 32768)
 
+    def fused_ok(self, M: int) -> bool:
+        """64x64 w2 (the attention adapters): ONE pass over x and dY on tcgen05 (uwu_lokr_fused_grad) instead of the
+        token-reduction GEMM G = dY^T X + contraction."""
+        (ol, ok), (im, inn) = self.shape
+        return _LOKR_FUSED and M >= 1024 and self.lokr_w1.is_cuda and ops.lokr_fused_supported(ol, ok, im, inn)
+
     def grads_factored(self, dy, x, M):
         """dy: bf16 [M, ol*ok] (row stride dy.stride(0)), x: bf16 [M, im*inn]; accumulates into lokr_w1.grad / lokr_w2.grad."""
         from .unet import _grad_of
 
+        if self.fused_ok(M):
+            ops.lokr_fused_grad(dy, x, M, self.lokr_w1.detach(), self.lokr_w2.detach(), _grad_of(self.lokr_w1), _grad_of(self.lokr_w2),
+                                self.scale * self.multiplier)
+            return
         lokr_factored_grads(dy, x, M, self.lokr_w1, self._w2_bf16, _grad_of(self.lokr_w1), _grad_of(self.lokr_w2),
                             self.scale * self.multiplier)
 

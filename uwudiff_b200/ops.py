@@ -696,6 +696,23 @@ def lokr_dw1(v: torch.Tensor, x: torch.Tensor, M: int, ol: int, im: int, in_n: i
     check(lib().uwu_lokr_dw1(_ptr(v), _ptr(x), x.stride(0), M, ol, im, in_n, multiplier, _ptr(dw1), _stream()), "uwu_lokr_dw1")
 
 
+def lokr_fused_supported(ol: int, ok: int, im: int, inn: int) -> bool:
+    return bool(lib().uwu_lokr_fused_supported(ol, ok, im, inn))
+
+
+def lokr_fused_grad(dy: torch.Tensor, x: torch.Tensor, M: int, w1: torch.Tensor, w2: torch.Tensor, dw1: torch.Tensor,
+                    dw2: torch.Tensor, multiplier: float = 1.0) -> None:
+    """One pass over x [M, im*64] and dy [M, ol*64] (bf16 views, unit column stride): dw1 / dw2 += LoKr adapter gradients."""
+    _req_cuda(dy, x, w1, w2, dw1, dw2)
+    ol, im = w1.shape
+    assert dy.dtype == x.dtype == torch.bfloat16 and dy.stride(1) == 1 and x.stride(1) == 1
+    assert w1.dtype == w2.dtype == dw1.dtype == dw2.dtype == torch.float32 and tuple(w2.shape) == (64, 64)
+    assert w1.is_contiguous() and w2.is_contiguous() and dw1.is_contiguous() and dw2.is_contiguous()
+    assert x.shape[1] == im * 64 and dy.shape[1] == ol * 64
+    check(lib().uwu_lokr_fused_grad(_ptr(x), x.stride(0), _ptr(dy), dy.stride(0), M, ol, im, _ptr(w1), _ptr(w2), _ptr(dw1),
+                                    _ptr(dw2), multiplier, _stream()), "uwu_lokr_fused_grad")
+
+
 def lora_grad(G: torch.Tensor, up: torch.Tensor, down: torch.Tensor, scale: float, dup: torch.Tensor, ddown: torch.Tensor) -> None:
     _req_cuda(G, up, down, dup, ddown)
     N, K = G.shape
