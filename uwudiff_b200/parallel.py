@@ -73,16 +73,28 @@ class GradientBuckets:
         so every replica starts from the same state whatever its local seed was; the bf16 operand caches are dropped."""
         src = dist.get_global_rank(self.group, 0) if self.group is not None else 0
         ly = trainer.lycoris_model
+        dev = (ly.flat_params if ly is not None else next(self.unet.parameters())).device
+
+        def bcast(t):
+            # host-resident buffers (the adapters' `alpha` scalars, scheduler tables) travel through the device the process
+            # group's backend serves (NCCL has no CPU tensors)
+            if t.device != dev and dev.type == "cuda":
+                tmp = t.to(dev)
+                dist.broadcast(tmp, src=src, group=self.group)
+                t.copy_(tmp)
+            else:
+                dist.broadcast(t, src=src, group=self.group)
+
         with torch.no_grad():
             if ly is not None:
-                dist.broadcast(ly.flat_params, src=src, group=self.group)  # every adapter tensor is a view into it
+                bcast(ly.flat_params)  # every adapter tensor is a view into it
                 for b in ly.buffers():
-                    dist.broadcast(b, src=src, group=self.group)
+                    bcast(b)
             mods = [self.unet] + ([trainer.loss] if isinstance(getattr(trainer, "loss", None), torch.nn.Module) else [])
             for mod in mods:
                 for t in list(mod.parameters()) + list(mod.buffers()):
                     if t.is_floating_point() or t.dtype in (torch.int64, torch.int32):
-                        dist.broadcast(t.data, src=src, group=self.group)
+                        bcast(t.data)
         if hasattr(self.unet, "refresh_weights"):
             self.unet.refresh_weights()
 
