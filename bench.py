@@ -433,7 +433,20 @@ def main():
     ap.add_argument("--global-batch", type=int, default=128)
     ap.add_argument("--graph", default="on", choices=["on", "off"],
                     help="replay forward+backward and clip+AdamW as two captured CUDA graphs (DMTrainer.setup_fit(cuda_graph=True))")
+    ap.add_argument("--config", default="c3", choices=["c3", "c1", "c2", "c4", "latent"],
+                    help="c3 (default): the headline, BASELINE.json configs[2] / configs[4]; c1 | c2 | c4 | latent: the other named "
+                         "configurations (pixel UNet, SD-1.5-size UNet, DiT-XL/2, SDXL full fine-tune at 32x32), one GPU, "
+                         "through tools/bench_configs.py")
     args = ap.parse_args()
+    if args.config != "c3":
+        if args.impl == "reference" or args.gpus > 1:
+            raise SystemExit("--config c1|c2|c4|latent runs this repo's arm on one GPU (multi-GPU check: tools/ddp_check.py)")
+        sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "tools"))
+        import bench_configs
+
+        sys.argv = [sys.argv[0], args.config, "--steps", str(args.steps), "--warmup", str(args.warmup)]
+        bench_configs.main()
+        return
     if args.impl == "reference":
         run_reference(args)
         return

@@ -213,6 +213,17 @@ int uwu_groupnorm_fwd(const void* x, int32_t N, int32_t HW, int32_t C, int32_t G
 int uwu_groupnorm_bwd(const void* x, const void* dy, int32_t N, int32_t HW, int32_t C, int32_t G, const float* gamma,
                       const float* beta, const float* stats, int32_t fuse_silu, const void* dres, void* dx,
                       float* dgamma, float* dbeta, float* workspace, void* stream);
+/* One-launch variants: statistics pass -> per-image barrier between the co-resident blocks of the grid -> apply pass that
+ * re-reads the block's own rows from L2 (one HBM pass less in forward, two less in backward).  `sync`: 2 * N uint32 in device
+ * memory, ZERO before the first call; every call leaves them ready for the next (persistent per-device buffer).  The
+ * backward variant is for a frozen affine (no dgamma / dbeta).  Return 1 = shape cannot run as one resident wave, nothing was
+ * launched: call the three-kernel entry point instead.  Same reference call sites as uwu_groupnorm_fwd / _bwd. */
+int uwu_groupnorm_fwd_fused(const void* x, int32_t N, int32_t HW, int32_t C, int32_t G, float eps, const float* gamma,
+                            const float* beta, int32_t fuse_silu, void* y, float* stats, float* workspace, uint32_t* sync,
+                            void* stream);
+int uwu_groupnorm_bwd_fused(const void* x, const void* dy, int32_t N, int32_t HW, int32_t C, int32_t G, const float* gamma,
+                            const float* beta, const float* stats, int32_t fuse_silu, const void* dres, void* dx,
+                            float* workspace, uint32_t* sync, void* stream);
 /* LayerNorm on x[M, C] with optional adaLN modulation y = LN(x) * (1 + mod_scale[m / rows_per_mod]) + mod_shift[..];
  * stats[M, 2] = {mean, rstd} (optional) */
 int uwu_layernorm_fwd(const void* x, int32_t M, int32_t C, float eps, const float* gamma, const float* beta,

@@ -310,6 +310,29 @@ def test_groupnorm_silu(ops, N, H, W, C, G, silu, eps):
     dx = ops.groupnorm_bwd(x, dy, N, HW, C, G, gamma, beta, stats, silu, dres=dres, dgamma=dgamma, dbeta=dbeta)
     assert relerr(dx, xr.grad.permute(0, 2, 1).reshape(N * HW, C) + dres.float()) < TOL_BF16
     assert relerr(dgamma, gr.grad) < 1e-3 and relerr(dbeta, br.grad) < 1e-3
+    # frozen affine (no parameter gradients): the one-launch backward; must agree with the three-kernel path bit for bit
+    # up to the summation order of the per-group sums, also when called repeatedly (self-resetting image barrier)
+    want = xr.grad.permute(0, 2, 1).reshape(N * HW, C) + dres.float()
+    for _ in range(3):
+        dx2 = ops.groupnorm_bwd(x, dy, N, HW, C, G, gamma, beta, stats, silu, dres=dres)
+        assert relerr(dx2, want) < TOL_BF16
+        y2, stats2 = ops.groupnorm_fwd(x, N, HW, C, G, eps, gamma, beta, silu)
+        assert torch.equal(y2, y) and torch.equal(stats2, stats)
+
+
+def test_groupnorm_one_launch_matches_three_kernel_path(ops, monkeypatch):
+    """Step shapes (16 images): one-launch forward / backward against the three-kernel path; the statistics may differ only by
+    the chunking of the fp32 sums."""
+    N, HW, C, G = 16, 1024, 1280, 32
+    x, dy = mk(N * HW, C, s=1.0), mk(N * HW, C, s=1.0)
+    gamma, beta = torch.randn(C, device=DEV) * 0.5 + 1, torch.randn(C, device=DEV) * 0.5
+    y1, st1 = ops.groupnorm_fwd(x, N, HW, C, G, 1e-5, gamma, beta, True)
+    dx1 = ops.groupnorm_bwd(x, dy, N, HW, C, G, gamma, beta, st1, True)
+    monkeypatch.setattr(ops, "_GN_FUSED", False)
+    y0, st0 = ops.groupnorm_fwd(x, N, HW, C, G, 1e-5, gamma, beta, True)
+    dx0 = ops.groupnorm_bwd(x, dy, N, HW, C, G, gamma, beta, st0, True)
+    assert relerr(st1, st0) < 1e-5 and relerr(y1, y0) < 1e-2 and relerr(dx1, dx0) < 1e-2
+    assert (y1 != y0).float().mean() < 1e-2  # only bf16 rounding flips from the last-bit differences of the statistics
 
 
 @pytest.mark.parametrize("M,C", [(256, 64), (1000, 640), (4096, 1280), (77, 128), (16384, 1280), (333, 320)])

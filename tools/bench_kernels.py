@@ -193,6 +193,25 @@ def case_wgrad_dit():
         tf(f"torch dY^T X {Co}x{Ci}", timeit(lambda: torch.matmul(dy.t(), x)), 2.0 * Mtok * Co * Ci)
 
 
+def case_lin_bn():
+    """Tile-width sweep on the short-K Linear shapes of the step (pair kernel): whole waves vs tile efficiency."""
+    for (M, N, K) in [(16384, 1280, 1280), (65536, 640, 640), (16384, 1280, 2048), (16384, 1280, 3840), (16384, 3840, 1280),
+                      (65536, 640, 2560)]:
+        a, b = mk(M, K), mk(N, K)
+        out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+        res = mk(M, N)
+        bias = torch.randn(N, device=dev)
+        for bn in (0, 128, 160, 192, 256, 320):
+            if bn and N % bn and bn != 256:
+                continue
+            try:
+                tf(f"lin+bias+res M{M} N{N} K{K} block_n={bn}",
+                   timeit(lambda: ops.gemm(a, b, M, N, K, out=out, residual=res, bias=bias, block_n=bn)), 2.0 * M * N * K)
+            except Exception as e:
+                print(f"block_n={bn}: {e}")
+        tf(f"torch addmm M{M} N{N} K{K}", timeit(lambda: torch.addmm(bias.to(torch.bfloat16), a, b.t())), 2.0 * M * N * K)
+
+
 def case_lin():
     for (M, N, K) in [(16384, 1280, 1280), (16384, 3840, 1280), (16384, 10240, 1280), (16384, 1280, 5120), (65536, 640, 640),
                       (65536, 1920, 640), (65536, 5120, 640), (65536, 640, 2560)]:

@@ -22,7 +22,7 @@ from uwudiff_b200 import ops
 
 WRAP = ["gemm", "noise_fwd", "sincos_embed", "wmse_fwd", "wmse_bwd", "attn_fwd", "attn_bwd", "groupnorm_fwd", "groupnorm_bwd",
         "layernorm_fwd", "layernorm_bwd", "geglu_fwd", "geglu_bwd", "elementwise", "nchw_to_nhwc", "nhwc_to_nchw", "upsample2x",
-        "phase_split2", "colsum", "fold_lokr", "fold_lora", "axpy_f32", "lokr_grad", "lora_grad", "copy2d", "lokr_z", "lokr_dw1",
+        "phase_split2", "colsum", "fold_lokr", "fold_lora", "axpy_f32", "lokr_grad", "lora_grad", "copy2d", "lokr_z", "lokr_dw1", "lokr_fused_grad",
         "im2col3x3", "conv_wgrad_unpack", "colsum_groups", "pred_convert", "adaln_fwd", "adaln_bwd", "gate_residual_fwd", "gate_residual_bwd", "patchify",
         "unpatchify", "embed_gather", "embed_scatter_add", "conv_pack", "fold_loha", "loha_grad", "timestep_hist"]
 

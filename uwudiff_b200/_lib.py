@@ -131,6 +131,8 @@ SIGNATURES = {
     "uwu_fold_batch": (C.c_int, [_P, _P, _I32, _I32, _P]),
     "uwu_lokr_z": (C.c_int, [_P, _I64, _P, _I64, _I32, _I32, _I32, _P, _P]),
     "uwu_lokr_dw1": (C.c_int, [_P, _P, _I64, _I64, _I32, _I32, _I32, _F, _P, _P]),
+    "uwu_groupnorm_fwd_fused": (C.c_int, [_P, _I32, _I32, _I32, _I32, _F, _P, _P, _I32, _P, _P, _P, _P, _P]),
+    "uwu_groupnorm_bwd_fused": (C.c_int, [_P, _P, _I32, _I32, _I32, _I32, _P, _P, _P, _I32, _P, _P, _P, _P, _P]),
     "uwu_lokr_fused_supported": (C.c_int, [_I32, _I32, _I32, _I32]),
     "uwu_lokr_fused_grad": (C.c_int, [_P, _I64, _P, _I64, _I64, _I32, _I32, _P, _P, _P, _P, _F, _P]),
     "uwu_mt_gradnorm": (C.c_int, [_P, _P, _P, _P, _I32, _I32, _F, _P, _P, _P]),

@@ -292,6 +292,242 @@ __global__ void gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x, const _
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// One-launch GroupNorm: statistics pass, per-image barrier, apply pass.  All blocks of the grid are co-resident (the host sizes
+// the grid from the occupancy query), so the blocks of one image can wait for each other on a self-resetting counter /
+// generation pair in global memory; the second pass then re-reads the block's own rows while they are still in L2 (a 10-40 MB
+// image easily fits the 126 MB L2), which removes one of the two (forward) / two of the five (backward) HBM passes of the
+// three-kernel path above.
+// ------------------------------------------------------------------------------------------------
+UWU_DEVINL unsigned ld_acquire_u32(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// sync[2 * n] = arrival counter, sync[2 * n + 1] = generation of image slot n (zero before the first use; both are left
+// consistent for the next launch: the last arriver resets the counter before it bumps the generation)
+UWU_DEVINL void gn_image_barrier(unsigned* sync, int n, unsigned blocks) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned* cnt = sync + 2 * n;
+        unsigned* gen = cnt + 1;
+        const unsigned g0 = ld_acquire_u32(gen);
+        __threadfence();
+        const unsigned old = atomicAdd(cnt, 1u);
+        if (old == blocks - 1) {
+            *cnt = 0u;
+            __threadfence();
+            atomicAdd(gen, 1u);
+        } else {
+            while (ld_acquire_u32(gen) == g0) __nanosleep(40);
+        }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+template <bool kSilu>
+__global__ void __launch_bounds__(256) gn_fwd_fused_kernel(const __nv_bfloat16* __restrict__ x, GNGeom g, float eps,
+                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                           __nv_bfloat16* __restrict__ y, float* __restrict__ stats,
+                                                           float* __restrict__ ws, unsigned* __restrict__ sync) {
+    pdl_trigger();
+    extern __shared__ float sh[];  // [rpi][2][C] partials, later [G][2] statistics
+    const int n = blockIdx.y, chunk = blockIdx.x;
+    const int v = threadIdx.x % g.cv, rr = threadIdx.x / g.cv;
+    const int cpg = g.C / g.G;
+    const int r0 = chunk * g.rows_per_chunk;
+    const int r1 = min(g.HW, r0 + g.rows_per_chunk);
+    const size_t off = ((size_t)n * g.HW) * g.C + v * 8;
+    {
+        float s[8], q[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
+#pragma unroll 4
+        for (int r = r0 + rr; r < r1; r += g.rpi) {
+            float f[8];
+            ld8(x + off + (size_t)r * g.C, f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                s[j] += f[j];
+                q[j] = fmaf(f[j], f[j], q[j]);
+            }
+        }
+        float* mine = sh + (size_t)rr * 2 * g.C;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            mine[v * 8 + j] = s[j];
+            mine[g.C + v * 8 + j] = q[j];
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * g.C; i += blockDim.x) {
+        float a = sh[i];
+        for (int k = 1; k < g.rpi; ++k) a += sh[(size_t)k * 2 * g.C + i];
+        sh[i] = a;
+    }
+    __syncthreads();
+    for (int gi = threadIdx.x; gi < g.G; gi += blockDim.x) {
+        float a = 0.f, b = 0.f;
+        for (int c = gi * cpg; c < (gi + 1) * cpg; ++c) {
+            a += sh[c];
+            b += sh[g.C + c];
+        }
+        float* o = ws + (((size_t)n * g.chunks + chunk) * g.G + gi) * 2;
+        o[0] = a;
+        o[1] = b;
+    }
+    gn_image_barrier(sync, n, (unsigned)g.chunks);
+    // every block finalises the statistics of its image (chunks * G * 2 floats from L2), block 0 publishes them
+    for (int gi = threadIdx.x; gi < g.G; gi += blockDim.x) {
+        float a = 0.f, b = 0.f;
+        for (int c = 0; c < g.chunks; ++c) {
+            const float2 pp = __ldcg(reinterpret_cast<const float2*>(ws + (((size_t)n * g.chunks + c) * g.G + gi) * 2));
+            a += pp.x;
+            b += pp.y;
+        }
+        const float cnt = (float)g.HW * (float)cpg;
+        const float mean = a / cnt;
+        const float var = fmaxf(b / cnt - mean * mean, 0.f);
+        const float rstd = rsqrtf(var + eps);
+        sh[gi * 2] = mean;
+        sh[gi * 2 + 1] = rstd;
+        if (chunk == 0) {
+            stats[((size_t)n * g.G + gi) * 2] = mean;
+            stats[((size_t)n * g.G + gi) * 2 + 1] = rstd;
+        }
+    }
+    __syncthreads();
+    float sc[8], sf[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int c = v * 8 + j, gi = c / cpg;
+        sc[j] = sh[gi * 2 + 1] * gamma[c];
+        sf[j] = beta[c] - sh[gi * 2] * sc[j];
+    }
+#pragma unroll 4
+    for (int r = r0 + rr; r < r1; r += g.rpi) {
+        float f[8];
+        ld8(x + off + (size_t)r * g.C, f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float z = fmaf(f[j], sc[j], sf[j]);
+            f[j] = kSilu ? silu_f(z) : z;
+        }
+        st8(y + off + (size_t)r * g.C, f);
+    }
+}
+
+// backward without parameter gradients (frozen affine): per-chunk, per-group sums A = sum gamma*dz, B = sum gamma*dz*xhat
+// -> image barrier -> dx
+template <bool kSilu>
+__global__ void __launch_bounds__(256, 3) gn_bwd_fused_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
+                                                           const float* __restrict__ stats, const float* __restrict__ gamma,
+                                                           const float* __restrict__ beta, const __nv_bfloat16* __restrict__ dres,
+                                                           GNGeom g, __nv_bfloat16* __restrict__ dx, float* __restrict__ ws,
+                                                           unsigned* __restrict__ sync) {
+    pdl_trigger();
+    extern __shared__ float sh[];  // [rpi][2][C] partials, later [G][2] = {A / cnt, B / cnt}
+    const int n = blockIdx.y, chunk = blockIdx.x;
+    const int v = threadIdx.x % g.cv, rr = threadIdx.x / g.cv;
+    const int cpg = g.C / g.G;
+    float mean[8], rstd[8], ga[8], be[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int c = v * 8 + j, gi = c / cpg;
+        mean[j] = stats[((size_t)n * g.G + gi) * 2];
+        rstd[j] = stats[((size_t)n * g.G + gi) * 2 + 1];
+        ga[j] = gamma[c];
+        be[j] = beta[c];
+    }
+    const int r0 = chunk * g.rows_per_chunk;
+    const int r1 = min(g.HW, r0 + g.rows_per_chunk);
+    const size_t off = ((size_t)n * g.HW) * g.C + v * 8;
+    {
+        float s1[8], s2[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
+#pragma unroll 4
+        for (int r = r0 + rr; r < r1; r += g.rpi) {
+            float f[8], d[8];
+            ld8(x + off + (size_t)r * g.C, f);
+            ld8(dy + off + (size_t)r * g.C, d);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float xh = (f[j] - mean[j]) * rstd[j];
+                float dz = d[j];
+                if (kSilu) dz *= silu_grad_f(fmaf(xh, ga[j], be[j]));
+                s1[j] += dz;
+                s2[j] = fmaf(dz, xh, s2[j]);
+            }
+        }
+        float* mine = sh + (size_t)rr * 2 * g.C;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {  // gamma-weighted: only the per-group sums are needed
+            mine[v * 8 + j] = s1[j] * ga[j];
+            mine[g.C + v * 8 + j] = s2[j] * ga[j];
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * g.C; i += blockDim.x) {
+        float a = sh[i];
+        for (int k = 1; k < g.rpi; ++k) a += sh[(size_t)k * 2 * g.C + i];
+        sh[i] = a;
+    }
+    __syncthreads();
+    for (int gi = threadIdx.x; gi < g.G; gi += blockDim.x) {
+        float a = 0.f, b = 0.f;
+        for (int c = gi * cpg; c < (gi + 1) * cpg; ++c) {
+            a += sh[c];
+            b += sh[g.C + c];
+        }
+        float* o = ws + (((size_t)n * g.chunks + chunk) * g.G + gi) * 2;
+        o[0] = a;
+        o[1] = b;
+    }
+    gn_image_barrier(sync, n, (unsigned)g.chunks);
+    for (int gi = threadIdx.x; gi < g.G; gi += blockDim.x) {
+        float a = 0.f, b = 0.f;
+        for (int c = 0; c < g.chunks; ++c) {
+            const float2 pp = __ldcg(reinterpret_cast<const float2*>(ws + (((size_t)n * g.chunks + c) * g.G + gi) * 2));
+            a += pp.x;
+            b += pp.y;
+        }
+        const float cnt = (float)g.HW * (float)cpg;
+        sh[gi * 2] = a / cnt;
+        sh[gi * 2 + 1] = b / cnt;
+    }
+    __syncthreads();
+    float A[8], Bc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int gi = (v * 8 + j) / cpg;
+        A[j] = sh[gi * 2];
+        Bc[j] = sh[gi * 2 + 1];
+    }
+#pragma unroll 4
+    for (int r = r0 + rr; r < r1; r += g.rpi) {
+        float f[8], d[8], o[8];
+        ld8(x + off + (size_t)r * g.C, f);
+        ld8(dy + off + (size_t)r * g.C, d);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float xh = (f[j] - mean[j]) * rstd[j];
+            float dz = d[j];
+            if (kSilu) dz *= silu_grad_f(fmaf(xh, ga[j], be[j]));
+            o[j] = rstd[j] * (ga[j] * dz - A[j] - xh * Bc[j]);
+        }
+        if (dres) {
+            float e[8];
+            ld8(dres + off + (size_t)r * g.C, e);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] += e[j];
+        }
+        st8(dx + off + (size_t)r * g.C, o);
+    }
+}
+
 static int gn_geom(int N, int HW, int C, int G, GNGeom* g) {
     UWU_CHECK_ARG(N > 0 && HW > 0 && C > 0 && G > 0, "groupnorm: bad shape N=%d HW=%d C=%d G=%d", N, HW, C, G);
     UWU_CHECK_ARG(C % 8 == 0 && C % G == 0, "groupnorm: C=%d must be a multiple of 8 and of G=%d", C, G);
@@ -808,7 +1044,10 @@ extern "C" int64_t uwu_groupnorm_workspace_floats(int32_t N, int32_t HW, int32_t
     GNGeom g;
     if (gn_geom(N, HW, C, G, &g)) return -1;
     // forward partials (N*chunks*G*2) or backward partials (N*chunks*2*C) + reduced (N*2*G)
-    return (int64_t)N * g.chunks * 2 * C + (int64_t)N * 2 * G + 64;
+    // (+ the per-group partials of the one-launch kernels, whose chunk count is bounded by 256)
+    const int64_t three = (int64_t)N * g.chunks * 2 * C + (int64_t)N * 2 * G + 64;
+    const int64_t one = (int64_t)N * 256 * 2 * G + 64;
+    return three > one ? three : one;
 }
 
 extern "C" int uwu_groupnorm_fwd(const void* x, int32_t N, int32_t HW, int32_t C, int32_t G, float eps,
@@ -830,6 +1069,75 @@ extern "C" int uwu_groupnorm_fwd(const void* x, int32_t N, int32_t HW, int32_t C
         gn_apply_kernel<true><<<grid, threads, 0, stream>>>(xp, stats, gamma, beta, g, yp);
     else
         gn_apply_kernel<false><<<grid, threads, 0, stream>>>(xp, stats, gamma, beta, g, yp);
+    UWU_CHECK_LAUNCH();
+    return UWU_OK;
+}
+
+// grid of the one-launch kernels: all N * chunks blocks must be resident at once
+template <typename K>
+static int gn_fused_geom(K kernel, int N, int HW, int C, int G, GNGeom* g) {
+    if (gn_geom(N, HW, C, G, g)) return -1;
+    const int threads = g->cv * g->rpi;
+    const size_t smem = (size_t)g->rpi * 2 * C * sizeof(float);
+    if (threads > 256 || smem > 48 * 1024 || (size_t)G * 2 * sizeof(float) > smem) return 1;
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem) != cudaSuccess || per_sm < 1) return 1;
+    const int cap = per_sm * sm_count();
+    int chunks = cap / N;
+    if (chunks < 1) return 1;  // more images than resident blocks
+    const int max_chunks = (HW + g->rpi * 4 - 1) / (g->rpi * 4);
+    if (chunks > max_chunks) chunks = max_chunks;
+    if (chunks > 256) chunks = 256;
+    g->rows_per_chunk = (HW + chunks - 1) / chunks;
+    g->chunks = (HW + g->rows_per_chunk - 1) / g->rows_per_chunk;
+    return 0;
+}
+
+/* One-launch forward; `sync` = 2 * N uint32 that are ZERO before the first call and are left zero-consistent by every call
+ * (a persistent per-device buffer).  Returns 1 (nothing launched) when the shape cannot run as one resident wave. */
+extern "C" int uwu_groupnorm_fwd_fused(const void* x, int32_t N, int32_t HW, int32_t C, int32_t G, float eps,
+                                       const float* gamma, const float* beta, int32_t fuse_silu, void* y, float* stats,
+                                       float* workspace, uint32_t* sync, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    UWU_CHECK_ARG(x && y && stats && workspace && gamma && beta && sync, "uwu_groupnorm_fwd_fused: null pointer");
+    GNGeom g;
+    const int rc = fuse_silu ? gn_fused_geom(gn_fwd_fused_kernel<true>, N, HW, C, G, &g) : gn_fused_geom(gn_fwd_fused_kernel<false>, N, HW, C, G, &g);
+    if (rc < 0) return UWU_ERR_INVALID;
+    if (rc > 0) return 1;
+    const auto* xp = reinterpret_cast<const __nv_bfloat16*>(x);
+    auto* yp = reinterpret_cast<__nv_bfloat16*>(y);
+    dim3 grid(g.chunks, N);
+    const int threads = g.cv * g.rpi;
+    const size_t smem = (size_t)g.rpi * 2 * C * sizeof(float);
+    if (fuse_silu)
+        gn_fwd_fused_kernel<true><<<grid, threads, smem, stream>>>(xp, g, eps, gamma, beta, yp, stats, workspace, sync);
+    else
+        gn_fwd_fused_kernel<false><<<grid, threads, smem, stream>>>(xp, g, eps, gamma, beta, yp, stats, workspace, sync);
+    UWU_CHECK_LAUNCH();
+    return UWU_OK;
+}
+
+/* One-launch backward for a frozen affine (no dgamma / dbeta). */
+extern "C" int uwu_groupnorm_bwd_fused(const void* x, const void* dy, int32_t N, int32_t HW, int32_t C, int32_t G,
+                                       const float* gamma, const float* beta, const float* stats, int32_t fuse_silu,
+                                       const void* dres, void* dx, float* workspace, uint32_t* sync, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    UWU_CHECK_ARG(x && dy && dx && stats && workspace && gamma && beta && sync, "uwu_groupnorm_bwd_fused: null pointer");
+    GNGeom g;
+    const int rc = fuse_silu ? gn_fused_geom(gn_bwd_fused_kernel<true>, N, HW, C, G, &g) : gn_fused_geom(gn_bwd_fused_kernel<false>, N, HW, C, G, &g);
+    if (rc < 0) return UWU_ERR_INVALID;
+    if (rc > 0) return 1;
+    const auto* xp = reinterpret_cast<const __nv_bfloat16*>(x);
+    const auto* dyp = reinterpret_cast<const __nv_bfloat16*>(dy);
+    const auto* rp = reinterpret_cast<const __nv_bfloat16*>(dres);
+    auto* dxp = reinterpret_cast<__nv_bfloat16*>(dx);
+    dim3 grid(g.chunks, N);
+    const int threads = g.cv * g.rpi;
+    const size_t smem = (size_t)g.rpi * 2 * C * sizeof(float);
+    if (fuse_silu)
+        gn_bwd_fused_kernel<true><<<grid, threads, smem, stream>>>(xp, dyp, stats, gamma, beta, rp, g, dxp, workspace, sync);
+    else
+        gn_bwd_fused_kernel<false><<<grid, threads, smem, stream>>>(xp, dyp, stats, gamma, beta, rp, g, dxp, workspace, sync);
     UWU_CHECK_LAUNCH();
     return UWU_OK;
 }
