@@ -36,6 +36,7 @@ struct GemmKernelArgs {
     CUtensorMap tmO;   // bf16 output, box {64 columns, 32 rows}, 128B swizzle (epilogue TMA stores)
     CUtensorMap tmO2;  // same for out2 (columns >= n_split)
     int epi_tma;       // 1: bf16 output through shared-memory staging + TMA stores (coalesced), else direct stores
+    int res_tma;       // 1: the residual tile is prefetched by TMA (tmAux), one tile ahead, into per-chunk slots of each warp
     int M, N;
     int num_kb;  // number of 64-wide K blocks (conv: ntaps * kb_per_tap)
     int block_n;
@@ -172,7 +173,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
     uint64_t* tmem_full = empty_bar + MAX_STAGES;  // [2]
     uint64_t* tmem_empty = tmem_full + 2;          // [2]
     uint64_t* epi_bar = tmem_empty + 2;            // [4] one per epilogue warp (TMA loads of epilogue operands)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(epi_bar + 4);
+    uint64_t* res_bar = epi_bar + 4;               // [4 warps][4 chunks] residual slots (res_tma)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 16);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -185,7 +187,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
             tma_prefetch_desc(&p.tmO);
             tma_prefetch_desc(&p.tmO2);
         }
-        if (p.epi_mode == 2) tma_prefetch_desc(&p.tmAux);
+        if (p.epi_mode == 2 || p.res_tma) tma_prefetch_desc(&p.tmAux);
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < p.stages; ++s) {
@@ -197,6 +199,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
             mbar_init(&tmem_empty[s], PAIR ? 8 : 4);  // one arrive per epilogue warp (pair: of both CTAs, on the leader's barrier)
         }
         for (int s = 0; s < 4; ++s) mbar_init(&epi_bar[s], 1);
+        for (int s = 0; s < 16; ++s) mbar_init(&res_bar[s], 1);
         fence_barrier_init();
     }
     if (warp == 2) {
@@ -597,6 +600,21 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
                 }
                 if (lane == 0) bulk_wait_group0();
             } else {
+            uint8_t* rstg = stg + 8192;          // [4 chunks][32 rows x 128 B] residual slots of this warp (res_tma)
+            uint64_t* rbar = res_bar + sub * 4;
+            uint32_t rph = 0;                    // phase bit of each chunk's barrier
+            auto issue_res = [&](int tile_n, int ch) {  // one lane
+                const int n0n = (tile_n % p.num_n_tiles) * p.block_n;
+                if (n0n + ch * 64 < min(p.N, n0n + p.block_n)) {
+                    mbar_expect_tx(&rbar[ch], 4096);
+                    tma_load_2d(rstg + ch * 4096, &p.tmAux, &rbar[ch], n0n + ch * 64, (tile_n / p.num_n_tiles) * BLOCK_M + sub * 32);
+                }
+            };
+            if (p.res_tma && lane == 0) {
+                WorkIter w0 = wi;
+                if (w0.next())
+                    for (int ch = 0; ch < 4; ++ch) issue_res(w0.tile, ch);
+            }
             while (wi.next()) {
                 const int tile = wi.tile;
                 const int n_blk = tile % p.num_n_tiles;
@@ -608,6 +626,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
                 const int nchunks = (n_end - n0 + 63) >> 6;
                 const bool row_ok = row < p.M;
                 const float* brow = (p.bias_rows != nullptr && row_ok) ? p.bias_rows + (size_t)(row / p.rows_per_bias) * p.N : nullptr;
+                // residual by TMA: every 64-column chunk of the NEXT tile is requested as soon as this tile has consumed the
+                // chunk's slot, so the load has a whole tile epilogue to land (the register path below prefetches one chunk)
+                WorkIter wl = wi;
+                const bool has_next = p.res_tma && wl.next();
+                const int tile_next = wl.tile;
                 uint4 rnext[8];
                 auto load_res = [&](int col0) {
 #pragma unroll
@@ -617,7 +640,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
                                                            : make_uint4(0, 0, 0, 0);
                     }
                 };
-                if (p.residual != nullptr) load_res(n0);
+                if (p.residual != nullptr && !p.res_tma) load_res(n0);
                 mbar_wait(&tmem_full[acc], acc_phase);
                 tc_fence_after();
                 const uint32_t t_row = tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(acc * ACC_STRIDE);
@@ -642,7 +665,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
                     if (lane == 0) bulk_wait_group_read1();
                     __syncwarp();
                     uint4 rc[8];
-                    if (p.residual != nullptr) {
+                    if (p.res_tma) {
+                        mbar_wait(&rbar[ch], (rph >> ch) & 1u);
+                        rph ^= 1u << ch;
+                        const uint8_t* rs = rstg + ch * 4096;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) rc[j] = *reinterpret_cast<const uint4*>(rs + lane * 128 + ((j ^ (lane & 7)) << 4));
+                        __syncwarp();
+                        if (has_next && lane == 0) {
+                            fence_proxy_async();
+                            issue_res(tile_next, ch);
+                        }
+                    } else if (p.residual != nullptr) {
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
                             const int rr = lrow + 4 * i;
@@ -736,6 +770,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
                                     *reinterpret_cast<const uint4*>(sbuf + lane * 128 + ((j ^ (lane & 7)) << 4));
                     }
                 }
+                if (has_next && lane == 0)  // chunks the next tile has and this (ragged) one did not
+                    for (int ch = nchunks; ch < 4; ++ch) issue_res(tile_next, ch);
                 if (++acc == p.n_acc) {
                     acc = 0;
                     acc_phase ^= 1;
@@ -1160,6 +1196,25 @@ extern "C" int uwu_gemm(const uwu_gemm_desc* d, void* stream_) {
             p.epi_tma = 1;
         }
     }
+    // short reductions are bound by the epilogue, and the epilogue by the latency of the residual rows: fetch them by TMA a
+    // tile ahead.  It costs 64 KB of the stage ring (6 -> 4 stages): measured (profiles/r02_gemm_res_tma.log) K = 1280: 60.6 -> 52.8
+    // us at N = 1280, K = 640: 100 -> 76 us, but K = 2560 loses 9 % and K = 3840 3 %, hence the bound on K
+    p.res_tma = 0;
+    {
+        static int want = -1;
+        if (want < 0) {
+            const char* e = getenv("UWU_GEMM_RES_TMA");
+            want = e ? atoi(e) : 1;
+        }
+        if (want && p.epi_tma && d->epi_mode == 0 && d->residual != nullptr && bn <= 256 && n_inst == 1 && d->K <= (want > 1 ? (1 << 30) : 1536)) {
+            uint64_t dims[2] = {(uint64_t)p.N, (uint64_t)p.M};
+            uint64_t str[1] = {(uint64_t)p.ldr * 2};
+            uint32_t box[2] = {64, 32};
+            if (encode_tmap_bf16(&p.tmAux, d->residual, 2, dims, str, box, 1)) return UWU_ERR_INVALID;
+            p.res_tma = 1;
+            p.epi_warp_bytes = 8192 + 4 * 4096;
+        }
+    }
     if (d->epi_mode != 0) {
         // fused GEGLU: `out` is [M, 2F] in both modes (pre-activation / its gradient), forward adds `out2` [M, F] = h * gelu(g),
         // backward reads the saved pre-activation through tmAux
@@ -1298,12 +1353,12 @@ extern "C" int uwu_gemm(const uwu_gemm_desc* d, void* stream_) {
     // ---------------- launch ----------------
     const int stage_bytes = A_STAGE_BYTES + p.b_stage_bytes;
     const int epi_bytes = 4 * p.epi_warp_bytes;
-    const int smem_budget = 227 * 1024 - 1024 /*align slack*/ - 256 /*barriers*/ - epi_bytes;
+    const int smem_budget = 227 * 1024 - 1024 /*align slack*/ - 512 /*barriers*/ - epi_bytes;
     int stages = smem_budget / stage_bytes;
     if (stages > MAX_STAGES) stages = MAX_STAGES;
     UWU_CHECK_ARG(stages >= 2, "uwu_gemm: tile too large for shared memory");
     p.stages = stages;
-    const size_t smem_bytes = (size_t)stages * stage_bytes + epi_bytes + 1024 + 256;
+    const size_t smem_bytes = (size_t)stages * stage_bytes + epi_bytes + 1024 + 512;
 
     static bool attr_set = false;
     if (!attr_set) {

@@ -183,7 +183,9 @@ class LokrLinear(_Adapter):
         """64x64 w2 (the attention adapters): ONE pass over x and dY on tcgen05 (uwu_lokr_fused_grad) instead of the
         token-reduction GEMM G = dY^T X + contraction."""
         (ol, ok), (im, inn) = self.shape
-        return _LOKR_FUSED and M >= 1024 and self.lokr_w1.is_cuda and ops.lokr_fused_supported(ol, ok, im, inn)
+        # (the ~12 us of per-launch set-up — operand build, pipeline fill, final reduction — only pay off from a few thousand
+        # tokens on: the cross-attention K / V adapters see 1232 text tokens and stay on the G route, 35 us for the pair)
+        return _LOKR_FUSED and M >= 4096 and self.lokr_w1.is_cuda and ops.lokr_fused_supported(ol, ok, im, inn)
 
     def grads_factored(self, dy, x, M):
         """dy: bf16 [M, ol*ok] (row stride dy.stride(0)), x: bf16 [M, im*inn]; accumulates into lokr_w1.grad / lokr_w2.grad."""
