@@ -335,12 +335,20 @@ def run_gpu(args):
 
     ops.gemm = timed_gemm
     es0, es1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # UWU_PROFILE_STEP=1: this (eager, warmed-up) optimizer step is the cudaProfilerStart/Stop range, so that
+    # `ncu --profile-from-start off` lists exactly the launches of one step (profiles/r02_launches_*.md)
+    prof = os.environ.get("UWU_PROFILE_STEP", "0") != "0"
     try:
+        if prof:
+            torch.cuda.synchronize()
+            torch.cuda.profiler.start()
         es0.record()
         for _ in range(K):
             trainer.fit_step(dev_batch, 0)
         es1.record()
         torch.cuda.synchronize()
+        if prof:
+            torch.cuda.profiler.stop()
     finally:
         ops.gemm = real_gemm
     eager_step_ms = es0.elapsed_time(es1)
