@@ -85,6 +85,22 @@ def test_gemm_epilogues(ops):
     assert relerr(o1, r[:, :160]) < TOL_BF16 and relerr(o2, r[:, 160:]) < TOL_BF16
 
 
+@pytest.mark.parametrize("M,N,K,ldr", [(65536, 640, 640, 640), (16384, 1280, 1280, 1280), (40000, 1000, 512, 1024), (300, 640, 1280, 640),
+                                          (33000, 200, 256, 208), (70000, 328, 1536, 328)])
+def test_gemm_residual_prefetched_by_tma_over_many_tiles(ops, M, N, K, ldr):
+    """Short reductions take the epilogue whose residual rows are requested by TMA one tile ahead (K <= 1536): several tiles
+    per CTA, a ragged last column tile that has FEWER 64-column chunks than the next tile of the same CTA (N = 640 -> 256 +
+    256 + 128: the slots the short tile never consumed must still be requested), rows past M, a padded residual pitch."""
+    a, b = mk(M, K), mk(N, K)
+    bias = torch.randn(N, device=DEV)
+    resbuf = mk(M, ldr)
+    res = resbuf[:, :N]
+    out = ops.gemm(a, b, M, N, K, bias=bias, residual=res)
+    ref = a.float() @ b.float().t() + bias + res.float()
+    assert relerr(out, ref) < TOL_BF16
+    torch.cuda.synchronize()
+
+
 @pytest.mark.parametrize("M,N,K", [(128, 128, 128), (256, 320, 512), (1280, 1280, 4096), (200, 136, 328)])
 def test_gemm_a_col_major(ops, M, N, K):
     from uwudiff_b200._lib import A_COL
