@@ -256,11 +256,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
                             if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], tx_bytes);
                             const int kseg = p.kb_per_seg > 0 ? kb / p.kb_per_seg : 0;
                             const int kbs = kb - kseg * p.kb_per_seg;
+                            const int grp = p.grp_n > 0 ? n0 / p.grp_n : 0;
                             if (p.a_mode == 0) {
-                                tma_load_2d_cg2(sa, &p.tmA, fb, kb * BLOCK_K, m0);
+                                tma_load_2d_cg2(sa, &p.tmA, fb, kb * BLOCK_K + grp * p.a_grp_koff, m0);
                             } else if (p.a_mode == 1) {
-                                tma_load_2d_cg2(sa, &p.tmA, fb, m0, kbs * BLOCK_K);
-                                tma_load_2d_cg2(sa + 8192, &p.tmA, fb, m0 + 64, kbs * BLOCK_K);
+                                const int am = m0 + kseg * p.a_seg_off;
+                                tma_load_2d_cg2(sa, &p.tmA, fb, am, kbs * BLOCK_K);
+                                tma_load_2d_cg2(sa + 8192, &p.tmA, fb, am + 64, kbs * BLOCK_K);
                             } else {
                                 const int tap = kb / p.kb_per_tap;
                                 const int cb = kb - tap * p.kb_per_tap;
@@ -277,7 +279,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
                                     tma_load_2d_cg2(sb + i * p.b_inst_bytes, &p.tmBh, fb, kb * BLOCK_K,
                                                     n0 + i * p.bn_inst + (int)cta_rank * (p.bn_inst >> 1));
                             else
-                                tma_load_3d_cg2(sb, &p.tmBh, fb, 0, kb * BLOCK_K, (n0 >> 6) + (int)cta_rank * (p.block_n >> 7));
+                                tma_load_3d_cg2(sb, &p.tmBh, fb, 0, kbs * BLOCK_K,
+                                                ((n0 - grp * p.grp_n + kseg * p.b_seg_off) >> 6) + (int)cta_rank * (p.block_n >> 7));
                         } else {
                             mbar_expect_tx(&full_bar[stage], tx_bytes);
                             // ---- A ----
@@ -1132,8 +1135,9 @@ extern "C" int uwu_gemm(const uwu_gemm_desc* d, void* stream_) {
         uint64_t bw = d->grp_n > 0 ? (uint64_t)d->grp_n : (uint64_t)d->N + (uint64_t)(segs - 1) * (uint64_t)d->b_seg_off;
         UWU_CHECK_ARG((int64_t)bw <= d->ldb, "uwu_gemm: segmented / grouped B columns exceed ldb");
         p.b_3d = 0;
-        if (segs == 1 && d->grp_n == 0 && d->N % 64 == 0 && bn % 64 == 0) {
-            uint64_t dims[3] = {64, (uint64_t)d->K, (uint64_t)(d->N / 64)};
+        if (bw % 64 == 0 && bn % 64 == 0 && (d->grp_n == 0 || d->grp_n % 64 == 0) && (segs == 1 || d->b_seg_off % 64 == 0)) {
+            // (grouped / segmented operands too: the group / segment only shifts the 64-column coordinate)
+            uint64_t dims[3] = {64, (uint64_t)d->K, (uint64_t)(bw / 64)};
             uint64_t str[2] = {(uint64_t)d->ldb * 2, 128};
             uint32_t box[3] = {64, BLOCK_K, (uint32_t)(bn / 64)};
             if (encode_tmap_bf16(&p.tmB, d->b, 3, dims, str, box, 1)) return UWU_ERR_INVALID;
@@ -1251,7 +1255,7 @@ extern "C" int uwu_gemm(const uwu_gemm_desc* d, void* stream_) {
         want_mc = e2 ? atoi(e2) : 0;  // multicast-only clusters: measured neutral in round 1, kept for comparison
     }
     const bool half_ok = d->b_layout == UWU_B_NK ? (bn % 16 == 0) : (p.b_3d && bn % 128 == 0);
-    const bool pair_shape_ok = d->k_segs <= 1 && d->grp_n == 0 && p.num_m_tiles >= 2 && half_ok && sm_count() % 2 == 0;
+    const bool pair_shape_ok = p.num_m_tiles >= 2 && half_ok && sm_count() % 2 == 0;  // (k_segs / grp_n: KN operands, need b_3d)
     const bool sk_candidate = d->stream_k != 0 && p.out_fp32 && !d->bias && !d->bias_rows && !d->residual && p.num_kb >= 32;
     // split-K (weight-gradient) schedules: pairs only when the row tiles pair up evenly (measured: G[640,*] and G[1920,*], 5 / 15
     // row tiles, lose 8 % to the half-empty last pair; G[1280,*] .. G[5120,*] gain 4 - 14 %)
@@ -1335,7 +1339,9 @@ extern "C" int uwu_gemm(const uwu_gemm_desc* d, void* stream_) {
             if (encode_tmap_bf16(&p.tmBh, d->b, 2, dims, str, box, 1)) return UWU_ERR_INVALID;
             p.b_half_bytes = n_inst * p.b_inst_bytes;
         } else {
-            uint64_t dims[3] = {64, (uint64_t)d->K, (uint64_t)(d->N / 64)};
+            const int segs2 = (d->a_layout == UWU_A_COL && d->k_segs > 1) ? d->k_segs : 1;
+            const uint64_t bw2 = d->grp_n > 0 ? (uint64_t)d->grp_n : (uint64_t)d->N + (uint64_t)(segs2 - 1) * (uint64_t)d->b_seg_off;
+            uint64_t dims[3] = {64, (uint64_t)d->K, (uint64_t)(bw2 / 64)};
             uint64_t str[2] = {(uint64_t)d->ldb * 2, 128};
             uint32_t box[3] = {64, BLOCK_K, (uint32_t)(bn / 128)};
             if (encode_tmap_bf16(&p.tmBh, d->b, 3, dims, str, box, 1)) return UWU_ERR_INVALID;
