@@ -457,37 +457,43 @@ struct AttnBwdArgs {
     __nv_bfloat16* dv;
     long long lddv;
     int hd;  // head dim (multiple of 8, <= 64)
+    int gx, n_items;  // work items: gx resident tiles per (batch, head), gx * heads * B in total (persistent CTAs)
     int direct_dq;  // single-pass mode with ONE key tile (cross-attention): each dQ tile is complete in its CTA -> bf16 store,
                     // no fp32 scratch, no memset, no conversion pass
 };
 
-// Shared-memory plan: two resident operand tiles, kStages x two streamed operand tiles, P / dS tiles.
-static constexpr int BWD_SR0 = 0;            // resident 0: K (dK/dV pass) or Q  (dQ pass)
-static constexpr int BWD_SR1 = AT_TILE;      // resident 1: V              or dO
-static constexpr int BWD_SDS = 2 * AT_TILE;  // dS [128 queries x 128 keys] bf16, two [128 x 64] K-major tiles
-static constexpr int BWD_SP = 4 * AT_TILE;   // P, same layout (dK/dV pass only)
+// Shared-memory plan: TWO buffers of two resident operand tiles (the next work item's K / V arrive while this one computes),
+// dS and P tiles, kStages x two streamed operand tiles.
+static constexpr int BWD_SR = 0;             // resident: buffer kvb, operand w at (2 kvb + w) tiles: K|V (dK/dV pass) or Q|dO (dQ pass)
+static constexpr int BWD_SDS = 4 * AT_TILE;  // dS [128 queries x 128 keys] bf16, two [128 x 64] K-major tiles
+static constexpr int BWD_SP = 6 * AT_TILE;   // P, same layout (dK/dV pass only)
 // kMode 0: dK/dV pass, 1: dQ pass, 2: single pass (dK, dV and dQ partials reduced into an fp32 scratch with vector atomics)
 template <int kMode>
 struct BwdCfg {
     static constexpr bool kDQ = kMode == 1;
     static constexpr int kStages = kDQ ? 4 : 3;
-    static constexpr int SS0 = (kDQ ? 4 : 6) * AT_TILE;  // streamed 0: Q (dK/dV pass) or K (dQ pass)
+    static constexpr int SS0 = (kDQ ? 6 : 8) * AT_TILE;  // streamed 0: Q (dK/dV pass) or K (dQ pass)
     static constexpr int SS1 = SS0 + kStages * AT_TILE;   // streamed 1: dO             or V
     static constexpr int BAR = SS1 + kStages * AT_TILE;
     static constexpr int SMEM = BAR + 256 + 1024;
 };
 static constexpr int BWD_THREADS = 64 + 512;  // TMA warp, MMA warp, 16 compute warps (4 per SM sub-partition)
-// TMEM columns: S [0,128) dP [128,256) acc0 [256,320) acc1 [320,384)
+// TMEM columns: S [0,128) dP [128,256) acc0 [256,320) acc1 [320,384) dQ partial [384,448)
 
-// Two passes over the (query tile, key tile) pairs, neither needs a cross-CTA reduction or an fp32 scratch:
-//   kDQ = false: CTA = 128 keys of one (batch, head), streams the query tiles (3 stages): dV += P^T dO, dK += dS^T Q
-//   kDQ = true : CTA = 128 queries, streams the key tiles (4 stages):                     dQ += dS K
-// In both, S = Q K^T and dP = dO V^T land in TMEM with one thread per QUERY row, so lse / delta are per-thread scalars;
+// PERSISTENT CTAs over the work items (resident tile x, head, batch): one CTA per SM walks items blockIdx.x, + gridDim.x, ...
+// All pipelines (operand ring, S/dP, P/dS, dQ) run through the item boundaries: the next item's resident tiles are loaded into
+// the other K|V buffer, its first S / dP products are issued before the last accumulating products of the current item, and
+// only the drain of the dK / dV accumulators (16 warps, ~1 us) separates two items.  With 8 query tiles per item (the
+// 1024-token levels) set-up + first loads + pipeline fill + drain + relaunch were a third of a CTA's life.
+//
+// Two kinds of pass, neither needs a cross-CTA reduction for dK / dV:
+//   kDQ = false: item = 128 keys of one (batch, head), streams the query tiles (3 stages): dV += P^T dO, dK += dS^T Q
+//                (kMode 2 also forms dQ_i = dS K per query tile and reduces it into an fp32 scratch with vector atomics)
+//   kDQ = true : item = 128 queries, streams the key tiles (4 stages):                     dQ += dS K
+// S = Q K^T and dP = dO V^T land in TMEM with one thread per QUERY row, so lse / delta are per-thread scalars;
 // P = exp2(S c - lse) and dS = P o (dP - delta) go to 128B-swizzled smem as [query][key] bf16, which the accumulating
-// products read K-major (dQ) or MN-major (dV, dK: the transposes, for free).  S / dP are recomputed in the second pass
-// (7 instead of 5 tile products per pair): the single-pass version was bound by the streamed-operand latency and the
-// per-iteration handshakes, not by the tensor pipe (profiles/r01_attn_bwd_ncu.md).  The MMA warp issues S / dP of
-// iteration i+1 before the accumulating products of iteration i, so the exp / dS math overlaps the tensor pipe.
+// products read K-major (dQ) or MN-major (dV, dK: the transposes, for free).  The MMA warp issues S / dP of step g+1 before
+// the accumulating products of step g, so the exp / dS math overlaps the tensor pipe.
 template <int kMode>
 __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_kernel(const __grid_constant__ AttnBwdArgs p) {
     pdl_trigger();
@@ -498,22 +504,34 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_kernel(const __grid_c
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = align1024(smem_raw);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::BAR);
-    uint64_t* res_full = bars;       // [1]
-    uint64_t* st_full = bars + 1;    // [4]
-    uint64_t* st_empty = bars + 5;   // [4]
-    uint64_t* sdp_full = bars + 9;
-    uint64_t* sdp_empty = bars + 10;
-    uint64_t* pds_full = bars + 11;
-    uint64_t* pds_empty = bars + 12;
-    uint64_t* acc_full = bars + 13;
-    uint64_t* dq_full = bars + 14;
-    uint64_t* dq_empty = bars + 15;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+    uint64_t* res_full = bars;        // [2] one per resident buffer
+    uint64_t* res_empty = bars + 2;   // [2]
+    uint64_t* st_full = bars + 4;     // [4]
+    uint64_t* st_empty = bars + 8;    // [4]
+    uint64_t* sdp_full = bars + 12;
+    uint64_t* sdp_empty = bars + 13;
+    uint64_t* pds_full = bars + 14;
+    uint64_t* pds_empty = bars + 15;
+    uint64_t* acc_full = bars + 16;
+    uint64_t* acc_empty = bars + 17;
+    uint64_t* dq_full = bars + 18;
+    uint64_t* dq_empty = bars + 19;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int r0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;  // first resident row (key or query)
     const int n_iter = kDQ ? (p.Lk + 127) / 128 : (p.Lq + 127) / 128;
-    const size_t bh = (size_t)b * p.heads + h;
+    // items of this CTA: first, stride, count; item -> (resident tile, head, batch)
+    const int item0 = (int)blockIdx.x, istep = (int)gridDim.x;
+    const int n_items = item0 < p.n_items ? (p.n_items - item0 + istep - 1) / istep : 0;
+    const int g_total = n_items * n_iter;  // pipeline steps of this CTA
+    auto decode = [&](int it, int& r0, int& h, int& b) {
+        const int item = item0 + it * istep;
+        const int x = item % p.gx;
+        const int hb = item / p.gx;
+        r0 = x * 128;
+        h = hb % p.heads;
+        b = hb / p.heads;
+    };
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&p.tmQ);
@@ -522,7 +540,10 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_kernel(const __grid_c
         tma_prefetch_desc(&p.tmdO);
     }
     if (warp == 1 && lane == 0) {
-        mbar_init(res_full, 1);
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&res_full[s], 1);
+            mbar_init(&res_empty[s], 1);
+        }
         for (int s = 0; s < kStages; ++s) {
             mbar_init(&st_full[s], 1);
             mbar_init(&st_empty[s], 1);
@@ -532,6 +553,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_kernel(const __grid_c
         mbar_init(pds_full, 16);
         mbar_init(pds_empty, 1);
         mbar_init(acc_full, 1);
+        mbar_init(acc_empty, 16);
         mbar_init(dq_full, 1);
         mbar_init(dq_empty, 16);
         fence_barrier_init();
@@ -552,31 +574,39 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_kernel(const __grid_c
             const CUtensorMap* tmR1 = kDQ ? &p.tmdO : &p.tmV;
             const CUtensorMap* tmS0 = kDQ ? &p.tmK : &p.tmQ;
             const CUtensorMap* tmS1 = kDQ ? &p.tmV : &p.tmdO;
-            mbar_expect_tx(res_full, 2 * AT_TILE);
-            tma_load_4d(smem + BWD_SR0, tmR0, res_full, 0, h, r0, b);
-            tma_load_4d(smem + BWD_SR1, tmR1, res_full, 0, h, r0, b);
             int s = 0;
             uint32_t ph = 0;
-            for (int i = 0; i < n_iter; ++i) {
-                mbar_wait(&st_empty[s], ph ^ 1);
-                mbar_expect_tx(&st_full[s], 2 * AT_TILE);
-                tma_load_4d(smem + Cfg::SS0 + s * AT_TILE, tmS0, &st_full[s], 0, h, i * 128, b);
-                tma_load_4d(smem + Cfg::SS1 + s * AT_TILE, tmS1, &st_full[s], 0, h, i * 128, b);
-                if (++s == kStages) {
-                    s = 0;
-                    ph ^= 1;
+            for (int it = 0; it < n_items; ++it) {
+                int r0, h, b;
+                decode(it, r0, h, b);
+                const int kvb = it & 1;
+                // the products of item it - 2 that read this resident buffer have retired
+                if (it >= 2) mbar_wait(&res_empty[kvb], (uint32_t)(((it >> 1) - 1) & 1));
+                mbar_expect_tx(&res_full[kvb], 2 * AT_TILE);
+                tma_load_4d(smem + BWD_SR + (2 * kvb) * AT_TILE, tmR0, &res_full[kvb], 0, h, r0, b);
+                tma_load_4d(smem + BWD_SR + (2 * kvb + 1) * AT_TILE, tmR1, &res_full[kvb], 0, h, r0, b);
+                for (int i = 0; i < n_iter; ++i) {
+                    mbar_wait(&st_empty[s], ph ^ 1);
+                    mbar_expect_tx(&st_full[s], 2 * AT_TILE);
+                    tma_load_4d(smem + Cfg::SS0 + s * AT_TILE, tmS0, &st_full[s], 0, h, i * 128, b);
+                    tma_load_4d(smem + Cfg::SS1 + s * AT_TILE, tmS1, &st_full[s], 0, h, i * 128, b);
+                    if (++s == kStages) {
+                        s = 0;
+                        ph ^= 1;
+                    }
                 }
             }
         }
     } else if (warp == 1) {
         // the whole warp walks the loop (warp-uniform waits and operands); one elected lane issues each group of UMMAs
-        {
+        if (g_total > 0) {
             const uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);              // S, dP: both operands K-major
             const uint32_t idesc_acc = make_idesc_bf16(128, 64, kDQ ? 0 : 1, 1);  // dQ: A K-major; dV/dK: A MN-major; B MN-major
-            const uint32_t sr0 = smem_u32(smem + BWD_SR0), sr1 = smem_u32(smem + BWD_SR1), ss0 = smem_u32(smem + Cfg::SS0),
-                           ss1 = smem_u32(smem + Cfg::SS1), sp = smem_u32(smem + BWD_SP), sds = smem_u32(smem + BWD_SDS);
+            const uint32_t sr = smem_u32(smem + BWD_SR), ss0 = smem_u32(smem + Cfg::SS0), ss1 = smem_u32(smem + Cfg::SS1),
+                           sp = smem_u32(smem + BWD_SP), sds = smem_u32(smem + BWD_SDS);
             // S = Q K^T, dP = dO V^T with the query tile as the M operand in both passes
-            auto issue_sdp = [&](int s) {
+            auto issue_sdp = [&](int s, int kvb) {
+                const uint32_t sr0 = sr + (2 * kvb) * AT_TILE, sr1 = sr0 + AT_TILE;
                 const uint64_t q_d = desc_kmajor(kDQ ? sr0 : ss0 + s * AT_TILE), k_d = desc_kmajor(kDQ ? ss0 + s * AT_TILE : sr0);
                 const uint64_t do_d = desc_kmajor(kDQ ? sr1 : ss1 + s * AT_TILE), v_d = desc_kmajor(kDQ ? ss1 + s * AT_TILE : sr1);
 #pragma unroll
@@ -586,31 +616,38 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_kernel(const __grid_c
                 for (int k = 0; k < 4; ++k)
                     umma_bf16(tmem_base + 128u, do_d + (uint64_t)(k * 2), v_d + (uint64_t)(k * 2), idesc_s, (uint32_t)(k != 0));
             };
-            mbar_wait(res_full, 0);
+            mbar_wait(&res_full[0], 0);
             mbar_wait(&st_full[0], 0);
             tc_fence_after();
             if (elect_one()) {
-                issue_sdp(0);
+                issue_sdp(0, 0);
                 umma_commit(sdp_full);
             }
             __syncwarp();
             int s = 0, s1 = (kStages > 1) ? 1 : 0;
-            uint32_t ph1 = 0;  // phase of stage s1
-            for (int i = 0; i < n_iter; ++i) {
-                if (i + 1 < n_iter) {
+            uint32_t ph1 = (kStages > 1) ? 0u : 1u;  // phase of stage s1's NEXT fill
+            int i = 0, it = 0;
+            for (int g = 0; g < g_total; ++g) {
+                const int kvb = it & 1;
+                const bool last = (i == n_iter - 1);
+                if (g + 1 < g_total) {
                     mbar_wait(&st_full[s1], ph1);
-                    mbar_wait(sdp_empty, (uint32_t)(i & 1));  // compute warps have pulled S / dP of iteration i out of TMEM
+                    const int it1 = last ? it + 1 : it;
+                    if (last) mbar_wait(&res_full[it1 & 1], (uint32_t)((it1 >> 1) & 1));  // the next item's resident tiles
+                    mbar_wait(sdp_empty, (uint32_t)(g & 1));  // compute warps have pulled S / dP of step g out of TMEM
                     tc_fence_after();
                     if (elect_one()) {
-                        issue_sdp(s1);
+                        issue_sdp(s1, it1 & 1);
                         umma_commit(sdp_full);
                     }
                     __syncwarp();
                 }
-                mbar_wait(pds_full, (uint32_t)(i & 1));
-                if (kFused) mbar_wait(dq_empty, (uint32_t)((i & 1) ^ 1));
+                mbar_wait(pds_full, (uint32_t)(g & 1));
+                if (kFused) mbar_wait(dq_empty, (uint32_t)((g & 1) ^ 1));
+                if (i == 0 && it > 0) mbar_wait(acc_empty, (uint32_t)((it - 1) & 1));  // previous item's accumulators drained
                 tc_fence_after();
                 if (elect_one()) {
+                    const uint32_t sr0 = sr + (2 * kvb) * AT_TILE;
                     const uint64_t b0 = desc_mnmajor(ss0 + s * AT_TILE, 8192);  // Q (dK) or K (dQ), [rows = reduction, 64 d]
                     const uint64_t b1 = desc_mnmajor(ss1 + s * AT_TILE, 8192);  // dO (dV)
                     if (kDQ) {
@@ -634,7 +671,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_kernel(const __grid_c
                                       (uint32_t)((i | k) != 0));
                         if (kFused) {
                             // dQ_i[q, d] = sum_key dS[q, key] K[key, d]: A = dS K-major, B = the resident K tile MN-major;
-                            // a fresh 64-column accumulator per query tile, drained by the compute warps one iteration later
+                            // a fresh 64-column accumulator per query tile, drained by the compute warps one step later
                             // (dq_empty was awaited by the whole warp above)
                             const uint32_t idesc_dq = make_idesc_bf16(128, 64, 0, 1);
                             const uint64_t kb = desc_mnmajor(sr0, 8192);
@@ -648,6 +685,10 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_kernel(const __grid_c
                     umma_commit(&st_empty[s]);
                     umma_commit(pds_empty);
                     if (kFused) umma_commit(dq_full);
+                    if (last) {
+                        umma_commit(acc_full);
+                        umma_commit(&res_empty[kvb]);
+                    }
                 }
                 __syncwarp();
                 s = s1;
@@ -655,9 +696,13 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_kernel(const __grid_c
                     s1 = 0;
                     ph1 ^= 1;
                 }
+                if (last) {
+                    i = 0;
+                    ++it;
+                } else {
+                    ++i;
+                }
             }
-            if (elect_one()) umma_commit(acc_full);
-            __syncwarp();
         }
     } else {
         // 16 compute warps: warp (sub, quarter) owns TMEM lanes [32 sub, +32) (the query rows) and key columns [32 quarter, +32)
@@ -672,15 +717,13 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_kernel(const __grid_c
         const uint64_t sl2_2 = pk2(sl2, sl2);
         const uint32_t prow_s = smem_u32(smem + BWD_SP + half * AT_TILE + row * 128);
         const uint32_t dsrow_s = smem_u32(smem + BWD_SDS + half * AT_TILE + row * 128);
-        // lse * log2(e) and delta of this thread's query row (padded rows of the scratch are zero and never written out)
-        const float* lse_p = p.lse2 + bh * p.Lq_pad + row;
-        const float* del_p = p.delta + bh * p.Lq_pad + row;
-        float my_lse = lse_p[kDQ ? r0 : 0], my_delta = del_p[kDQ ? r0 : 0];
-        // single-pass mode: drain the dQ partial of query tile `tile` (16 columns per warp) into the fp32 scratch with vector
-        // atomics straight from registers: lane-contiguous 16-byte chunks, 512 B per warp instruction
-        auto flush_dq = [&](int tile) __attribute__((always_inline)) {
+        int r0 = 0, h = 0, b = 0;
+        size_t bh = 0;
+        // single-pass mode: drain the dQ partial of query tile `tile` (pipeline step gq; 16 columns per warp) into the fp32
+        // scratch with vector atomics straight from registers: lane-contiguous 16-byte chunks, 512 B per warp instruction
+        auto flush_dq = [&](int tile, int gq, size_t bhq, int hq, int bq) __attribute__((always_inline)) {
             uint32_t rq[16];
-            mbar_wait(dq_full, (uint32_t)(tile & 1));
+            mbar_wait(dq_full, (uint32_t)(gq & 1));
             tc_fence_after();
             tmem_ld16(tmem_base + lane_addr + 384u + (uint32_t)(quarter * 16), rq);
             tmem_ld_wait();
@@ -690,7 +733,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_kernel(const __grid_c
             if (p.direct_dq) {
                 const int qrow = tile * 128 + row;
                 if (qrow < p.Lq) {
-                    __nv_bfloat16* op = p.dq + ((size_t)b * p.Lq + qrow) * p.lddq + h * p.hd + quarter * 16;
+                    __nv_bfloat16* op = p.dq + ((size_t)bq * p.Lq + qrow) * p.lddq + hq * p.hd + quarter * 16;
 #pragma unroll
                     for (int c = 0; c < 2; ++c) {
                         if (quarter * 16 + c * 8 >= p.hd) break;
@@ -704,7 +747,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_kernel(const __grid_c
                 }
                 return;
             }
-            float* dst = p.dq_acc + (bh * (size_t)(p.Lq_pad / 128) + tile) * (size_t)(16 * 128 * 4) + ((size_t)(quarter * 4) * 128 + row) * 4;
+            float* dst = p.dq_acc + (bhq * (size_t)(p.Lq_pad / 128) + tile) * (size_t)(16 * 128 * 4) + ((size_t)(quarter * 4) * 128 + row) * 4;
 #pragma unroll
             for (int c = 0; c < 4; ++c)
                 asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + (size_t)c * 512),
@@ -712,97 +755,113 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_kernel(const __grid_c
                              "f"(__uint_as_float(rq[c * 4 + 2])), "f"(__uint_as_float(rq[c * 4 + 3]))
                              : "memory");
         };
-        for (int i = 0; i < n_iter; ++i) {
-            float nx_lse = my_lse, nx_delta = my_delta;
-            if (!kDQ && i + 1 < n_iter) {  // next query tile's scalars, in flight during this tile's math
-                nx_lse = lse_p[(size_t)(i + 1) * 128];
-                nx_delta = del_p[(size_t)(i + 1) * 128];
-            }
-            mbar_wait(sdp_full, (uint32_t)(i & 1));
-            tc_fence_after();
-            // pull this thread's 32 S and 32 dP values out of TMEM and hand the accumulators back to the MMA warp
-            uint32_t rs1[32], rp1[32];
-            tmem_ld32(tmem_base + lane_addr + (uint32_t)(quarter * 32), rs1);
-            tmem_ld32(tmem_base + lane_addr + 128u + (uint32_t)(quarter * 32), rp1);
-            tmem_ld_wait();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(sdp_empty);
-            uint4 pu[kDQ ? 1 : 4], du[4];
-            const uint64_t nl2 = pk2(-my_lse, -my_lse), nd2 = pk2(-my_delta, -my_delta);
-#pragma unroll
-            for (int q4 = 0; q4 < 4; ++q4) {
-                uint32_t pw[4], dw[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {  // two elements per step: FFMA2 / FADD2 / FMUL2
-                    const int i2 = q4 * 8 + 2 * e;
-                    float a0, a1, d0, d1;
-                    unpk2(ffma2(pk2u(rs1[i2], rs1[i2 + 1]), sl2_2, nl2), a0, a1);
-                    const float p0 = ex2_approx(a0), p1 = ex2_approx(a1);
-                    unpk2(fmul2(pk2(p0, p1), fadd2(pk2u(rp1[i2], rp1[i2 + 1]), nd2)), d0, d1);
-                    pw[e] = pack_bf16(p0, p1);
-                    dw[e] = pack_bf16(d0, d1);
+        int g = 0;
+        for (int it = 0; it < n_items; ++it) {
+            decode(it, r0, h, b);
+            bh = (size_t)b * p.heads + h;
+            // lse * log2(e) and delta of this thread's query row (padded rows of the scratch are zero and never written out)
+            const float* lse_p = p.lse2 + bh * p.Lq_pad + row;
+            const float* del_p = p.delta + bh * p.Lq_pad + row;
+            float my_lse = lse_p[kDQ ? r0 : 0], my_delta = del_p[kDQ ? r0 : 0];
+            for (int i = 0; i < n_iter; ++i, ++g) {
+                float nx_lse = my_lse, nx_delta = my_delta;
+                if (!kDQ && i + 1 < n_iter) {  // next query tile's scalars, in flight during this tile's math
+                    nx_lse = lse_p[(size_t)(i + 1) * 128];
+                    nx_delta = del_p[(size_t)(i + 1) * 128];
                 }
-                du[q4] = make_uint4(dw[0], dw[1], dw[2], dw[3]);
-                if (!kDQ) pu[kDQ ? 0 : q4] = make_uint4(pw[0], pw[1], pw[2], pw[3]);
-            }
-            // the accumulating products of the previous iteration have retired: their smem operands may be overwritten
-            mbar_wait(pds_empty, (uint32_t)((i & 1) ^ 1));
-#pragma unroll
-            for (int q4 = 0; q4 < 4; ++q4) {
-                const uint32_t chunk = (uint32_t)(((((quarter & 1) << 2) + q4) ^ sw) << 4);
-                if (!kDQ) st_shared_v4(prow_s + chunk, pu[kDQ ? 0 : q4]);
-                st_shared_v4(dsrow_s + chunk, du[q4]);
-            }
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(pds_full);
-            if (kFused && i > 0) flush_dq(i - 1);  // previous tile's dQ, off the critical path
-            my_lse = nx_lse;
-            my_delta = nx_delta;
-        }
-        if (kFused) flush_dq(n_iter - 1);
-        // ---- write the accumulators (TMEM lane = key row in the dK/dV pass, query row in the dQ pass) ----
-        // warp (sub, quarter) writes columns [16 quarter, +16) of its 32 rows
-        mbar_wait(acc_full, 0);
-        tc_fence_after();
-        const int r = r0 + row;
-        if (kDQ) {
-            uint32_t v[16];
-            tmem_ld16(tmem_base + lane_addr + 320u + (uint32_t)(quarter * 16), v);
-            tmem_ld_wait();
-            if (r < p.Lq) {
-                __nv_bfloat16* op = p.dq + ((size_t)b * p.Lq + r) * p.lddq + h * p.hd + quarter * 16;
-#pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                    if (quarter * 16 + c * 8 >= p.hd) break;
-                    uint4 u;
-                    u.x = pack_bf16(__uint_as_float(v[c * 8 + 0]) * p.scale, __uint_as_float(v[c * 8 + 1]) * p.scale);
-                    u.y = pack_bf16(__uint_as_float(v[c * 8 + 2]) * p.scale, __uint_as_float(v[c * 8 + 3]) * p.scale);
-                    u.z = pack_bf16(__uint_as_float(v[c * 8 + 4]) * p.scale, __uint_as_float(v[c * 8 + 5]) * p.scale);
-                    u.w = pack_bf16(__uint_as_float(v[c * 8 + 6]) * p.scale, __uint_as_float(v[c * 8 + 7]) * p.scale);
-                    *reinterpret_cast<uint4*>(op + c * 8) = u;
-                }
-            }
-        } else {
-#pragma unroll
-            for (int which = 0; which < 2; ++which) {
-                uint32_t v[16];
-                tmem_ld16(tmem_base + lane_addr + 256u + (uint32_t)(which * 64 + quarter * 16), v);
+                mbar_wait(sdp_full, (uint32_t)(g & 1));
+                tc_fence_after();
+                // pull this thread's 32 S and 32 dP values out of TMEM and hand the accumulators back to the MMA warp
+                uint32_t rs1[32], rp1[32];
+                tmem_ld32(tmem_base + lane_addr + (uint32_t)(quarter * 32), rs1);
+                tmem_ld32(tmem_base + lane_addr + 128u + (uint32_t)(quarter * 32), rp1);
                 tmem_ld_wait();
-                if (r < p.Lk) {
-                    const float sc = which ? p.scale : 1.0f;
-                    __nv_bfloat16* base = which ? p.dk + ((size_t)b * p.Lk + r) * p.lddk : p.dv + ((size_t)b * p.Lk + r) * p.lddv;
-                    __nv_bfloat16* op = base + h * p.hd + quarter * 16;
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(sdp_empty);
+                uint4 pu[kDQ ? 1 : 4], du[4];
+                const uint64_t nl2 = pk2(-my_lse, -my_lse), nd2 = pk2(-my_delta, -my_delta);
+#pragma unroll
+                for (int q4 = 0; q4 < 4; ++q4) {
+                    uint32_t pw[4], dw[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {  // two elements per step: FFMA2 / FADD2 / FMUL2
+                        const int i2 = q4 * 8 + 2 * e;
+                        float a0, a1, d0, d1;
+                        unpk2(ffma2(pk2u(rs1[i2], rs1[i2 + 1]), sl2_2, nl2), a0, a1);
+                        const float p0 = ex2_approx(a0), p1 = ex2_approx(a1);
+                        unpk2(fmul2(pk2(p0, p1), fadd2(pk2u(rp1[i2], rp1[i2 + 1]), nd2)), d0, d1);
+                        pw[e] = pack_bf16(p0, p1);
+                        dw[e] = pack_bf16(d0, d1);
+                    }
+                    du[q4] = make_uint4(dw[0], dw[1], dw[2], dw[3]);
+                    if (!kDQ) pu[kDQ ? 0 : q4] = make_uint4(pw[0], pw[1], pw[2], pw[3]);
+                }
+                // the accumulating products of the previous step have retired: their smem operands may be overwritten
+                mbar_wait(pds_empty, (uint32_t)((g & 1) ^ 1));
+#pragma unroll
+                for (int q4 = 0; q4 < 4; ++q4) {
+                    const uint32_t chunk = (uint32_t)(((((quarter & 1) << 2) + q4) ^ sw) << 4);
+                    if (!kDQ) st_shared_v4(prow_s + chunk, pu[kDQ ? 0 : q4]);
+                    st_shared_v4(dsrow_s + chunk, du[q4]);
+                }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(pds_full);
+                if (kFused && i > 0) flush_dq(i - 1, g - 1, bh, h, b);  // previous tile's dQ, off the critical path
+                my_lse = nx_lse;
+                my_delta = nx_delta;
+            }
+            if (kFused) flush_dq(n_iter - 1, g - 1, bh, h, b);
+            // ---- write the accumulators (TMEM lane = key row in the dK/dV pass, query row in the dQ pass) ----
+            // warp (sub, quarter) writes columns [16 quarter, +16) of its 32 rows
+            mbar_wait(acc_full, (uint32_t)(it & 1));
+            tc_fence_after();
+            const int r = r0 + row;
+            if (kDQ) {
+                uint32_t v[16];
+                tmem_ld16(tmem_base + lane_addr + 320u + (uint32_t)(quarter * 16), v);
+                tmem_ld_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(acc_empty);
+                if (r < p.Lq) {
+                    __nv_bfloat16* op = p.dq + ((size_t)b * p.Lq + r) * p.lddq + h * p.hd + quarter * 16;
 #pragma unroll
                     for (int c = 0; c < 2; ++c) {
                         if (quarter * 16 + c * 8 >= p.hd) break;
                         uint4 u;
-                        u.x = pack_bf16(__uint_as_float(v[c * 8 + 0]) * sc, __uint_as_float(v[c * 8 + 1]) * sc);
-                        u.y = pack_bf16(__uint_as_float(v[c * 8 + 2]) * sc, __uint_as_float(v[c * 8 + 3]) * sc);
-                        u.z = pack_bf16(__uint_as_float(v[c * 8 + 4]) * sc, __uint_as_float(v[c * 8 + 5]) * sc);
-                        u.w = pack_bf16(__uint_as_float(v[c * 8 + 6]) * sc, __uint_as_float(v[c * 8 + 7]) * sc);
+                        u.x = pack_bf16(__uint_as_float(v[c * 8 + 0]) * p.scale, __uint_as_float(v[c * 8 + 1]) * p.scale);
+                        u.y = pack_bf16(__uint_as_float(v[c * 8 + 2]) * p.scale, __uint_as_float(v[c * 8 + 3]) * p.scale);
+                        u.z = pack_bf16(__uint_as_float(v[c * 8 + 4]) * p.scale, __uint_as_float(v[c * 8 + 5]) * p.scale);
+                        u.w = pack_bf16(__uint_as_float(v[c * 8 + 6]) * p.scale, __uint_as_float(v[c * 8 + 7]) * p.scale);
                         *reinterpret_cast<uint4*>(op + c * 8) = u;
+                    }
+                }
+            } else {
+                uint32_t v[2][16];
+                tmem_ld16(tmem_base + lane_addr + 256u + (uint32_t)(quarter * 16), v[0]);
+                tmem_ld16(tmem_base + lane_addr + 320u + (uint32_t)(quarter * 16), v[1]);
+                tmem_ld_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(acc_empty);  // both accumulators are in registers: the next item may overwrite them
+#pragma unroll
+                for (int which = 0; which < 2; ++which) {
+                    if (r < p.Lk) {
+                        const float sc = which ? p.scale : 1.0f;
+                        __nv_bfloat16* base = which ? p.dk + ((size_t)b * p.Lk + r) * p.lddk : p.dv + ((size_t)b * p.Lk + r) * p.lddv;
+                        __nv_bfloat16* op = base + h * p.hd + quarter * 16;
+#pragma unroll
+                        for (int c = 0; c < 2; ++c) {
+                            if (quarter * 16 + c * 8 >= p.hd) break;
+                            uint4 u;
+                            u.x = pack_bf16(__uint_as_float(v[which][c * 8 + 0]) * sc, __uint_as_float(v[which][c * 8 + 1]) * sc);
+                            u.y = pack_bf16(__uint_as_float(v[which][c * 8 + 2]) * sc, __uint_as_float(v[which][c * 8 + 3]) * sc);
+                            u.z = pack_bf16(__uint_as_float(v[which][c * 8 + 4]) * sc, __uint_as_float(v[which][c * 8 + 5]) * sc);
+                            u.w = pack_bf16(__uint_as_float(v[which][c * 8 + 6]) * sc, __uint_as_float(v[which][c * 8 + 7]) * sc);
+                            *reinterpret_cast<uint4*>(op + c * 8) = u;
+                        }
                     }
                 }
             }
@@ -814,6 +873,16 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_kernel(const __grid_c
         tc_fence_after();
         tmem_dealloc(tmem_base, 512);
     }
+}
+
+static int bwd_grid(int n_items) {  // persistent CTAs: one per SM (UWU_ATTN_BWD_PERSIST=0: one CTA per item, for A/B runs)
+    static int persist = -1;
+    if (persist < 0) {
+        const char* e = getenv("UWU_ATTN_BWD_PERSIST");
+        persist = e ? atoi(e) : 1;
+    }
+    const int sms = sm_count();
+    return (!persist || n_items < sms) ? n_items : sms;
 }
 
 // (head_dim, heads, L, B) view of a [B*L, ld] activation; the box is always 64 columns wide, so heads narrower than 64 are
@@ -978,12 +1047,16 @@ extern "C" int uwu_attn_bwd(const void* q, const void* k, const void* v, const v
     if (attn_bwd_mode() == 1 && Lk <= 128) {
         a.dq_acc = workspace + 2 * rows;
         a.direct_dq = 1;
-        UWU_CHECK_CUDA(launch_pdl(attn_bwd_kernel<2>, dim3(1, heads, B), dim3(BWD_THREADS), BwdCfg<2>::SMEM, stream, a));
+        a.gx = 1;
+        a.n_items = heads * B;
+        UWU_CHECK_CUDA(launch_pdl(attn_bwd_kernel<2>, dim3(bwd_grid(a.n_items)), dim3(BWD_THREADS), BwdCfg<2>::SMEM, stream, a));
         UWU_CHECK_LAUNCH();
     } else if (attn_bwd_mode() == 1) {
         a.dq_acc = workspace + 2 * rows;
         UWU_CHECK_CUDA(cudaMemsetAsync(a.dq_acc, 0, (size_t)(rows * 64) * sizeof(float), stream));
-        UWU_CHECK_CUDA(launch_pdl(attn_bwd_kernel<2>, dim3((Lk + 127) / 128, heads, B), dim3(BWD_THREADS), BwdCfg<2>::SMEM, stream,
+        a.gx = (Lk + 127) / 128;
+        a.n_items = a.gx * heads * B;
+        UWU_CHECK_CUDA(launch_pdl(attn_bwd_kernel<2>, dim3(bwd_grid(a.n_items)), dim3(BWD_THREADS), BwdCfg<2>::SMEM, stream,
                                   a));  // dK, dV, dQ partials
         UWU_CHECK_LAUNCH();
         const long long total = (long long)B * Lq * heads * 8;
@@ -991,9 +1064,13 @@ extern "C" int uwu_attn_bwd(const void* q, const void* k, const void* v, const v
             a.dq_acc, B, heads, Lq, Lq_pad / 128, scale, head_dim, reinterpret_cast<__nv_bfloat16*>(dq), lddq);
         UWU_CHECK_LAUNCH();
     } else {
-        attn_bwd_kernel<0><<<dim3((Lk + 127) / 128, heads, B), BWD_THREADS, BwdCfg<0>::SMEM, stream>>>(a);  // dK, dV
+        a.gx = (Lk + 127) / 128;
+        a.n_items = a.gx * heads * B;
+        attn_bwd_kernel<0><<<dim3(bwd_grid(a.n_items)), BWD_THREADS, BwdCfg<0>::SMEM, stream>>>(a);  // dK, dV
         UWU_CHECK_LAUNCH();
-        attn_bwd_kernel<1><<<dim3((Lq + 127) / 128, heads, B), BWD_THREADS, BwdCfg<1>::SMEM, stream>>>(a);  // dQ
+        a.gx = (Lq + 127) / 128;
+        a.n_items = a.gx * heads * B;
+        attn_bwd_kernel<1><<<dim3(bwd_grid(a.n_items)), BWD_THREADS, BwdCfg<1>::SMEM, stream>>>(a);  // dQ
         UWU_CHECK_LAUNCH();
     }
     return UWU_OK;
