@@ -246,6 +246,20 @@ def test_attention_backward(ops, B, heads, Lq, Lk):
     assert relerr(dq, rdq) < TOL_ATTN and relerr(dk, rdk) < TOL_ATTN and relerr(dv, rdv) < TOL_ATTN
 
 
+@pytest.mark.parametrize("B,heads,Lq,Lk", [(3, 10, 1024, 1024), (1, 40, 600, 600), (2, 20, 640, 640), (10, 20, 256, 77), (5, 31, 384, 384)])
+def test_attention_backward_persistent_ctas_walk_several_items(ops, B, heads, Lq, Lk):
+    """More (key tile, head, batch) items than SMs: every CTA of the persistent backward kernel walks two or more items — the
+    operand ring, the S/dP and P/dS hand-shakes and the dQ drain run through the item boundaries, the K|V buffers alternate,
+    the dK/dV accumulators are drained and re-armed (ragged last key / query tiles included)."""
+    C = heads * 64
+    q, k, v, do = mk(B * Lq, C, s=1.0), mk(B * Lk, C, s=1.0), mk(B * Lk, C, s=1.0), mk(B * Lq, C, s=1.0)
+    o, lse = ops.attn_fwd(q, k, v, B, heads, Lq, Lk)
+    _, _, rdq, rdk, rdv = attn_ref(q, k, v, B, heads, Lq, Lk, do)
+    for _ in range(2):  # twice: the second launch starts from whatever the first left in TMEM / shared memory
+        dq, dk, dv = ops.attn_bwd(q, k, v, o, do, lse, B, heads, Lq, Lk)
+        assert relerr(dq, rdq) < TOL_ATTN and relerr(dk, rdk) < TOL_ATTN and relerr(dv, rdv) < TOL_ATTN
+
+
 # head dims other than 64 (SD-1.5: 40 / 80 / 160, DiT-XL/2: 72) run on the mma.sync kernels of attn_any.cu
 ATTN_ANY_SHAPES = [(2, 8, 256, 77, 40), (1, 3, 1300, 77, 40), (2, 8, 256, 256, 40), (1, 8, 1024, 1024, 40), (2, 8, 256, 77, 80), (2, 4, 64, 64, 160), (1, 2, 200, 77, 160),
                    (3, 16, 256, 256, 72), (1, 3, 130, 70, 72), (1, 2, 320, 200, 128), (2, 2, 96, 96, 32), (1, 1, 64, 64, 8)]
