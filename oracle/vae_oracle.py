@@ -14,7 +14,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-SDXL_VAE_CONFIG = dict(in_channels=3, latent_channels=4, block_out_channels=(128, 256, 512, 512), layers_per_block=2,
+SDXL_VAE_CONFIG = dict(in_channels=3, out_channels=3, latent_channels=4, block_out_channels=(128, 256, 512, 512), layers_per_block=2,
                        norm_num_groups=32, scaling_factor=0.13025)
 
 
@@ -118,3 +118,69 @@ class AutoencoderKLEncoder(nn.Module):
     def encode_mean_logvar(self, x):
         mean, logvar = torch.chunk(self.moments(x), 2, dim=1)
         return mean, torch.clamp(logvar, -30.0, 20.0)
+
+
+class Upsample(nn.Module):
+    """diffusers Upsample2D(use_conv=True): nearest 2x, then a 3x3 conv."""
+
+    def __init__(self, ch):
+        super().__init__()
+        self.conv = nn.Conv2d(ch, ch, 3, padding=1)
+
+    def forward(self, x):
+        return self.conv(F.interpolate(x, scale_factor=2.0, mode="nearest"))
+
+
+class UpBlock(nn.Module):
+    """diffusers UpDecoderBlock2D: layers_per_block + 1 resnets (no time embedding), then the upsampler."""
+
+    def __init__(self, cin, cout, layers, groups, add_up):
+        super().__init__()
+        self.resnets = nn.ModuleList([Resnet(cin if i == 0 else cout, cout, groups) for i in range(layers)])
+        self.upsamplers = nn.ModuleList([Upsample(cout)]) if add_up else None
+
+    def forward(self, x):
+        for r in self.resnets:
+            x = r(x)
+        if self.upsamplers is not None:
+            x = self.upsamplers[0](x)
+        return x
+
+
+class Decoder(nn.Module):
+    """diffusers.models.autoencoders.vae.Decoder (restated): conv_in, UNetMidBlock2D, UpDecoderBlock2D x len(block_out_channels)
+    over the REVERSED channel list (layers_per_block + 1 resnets each, nearest-2x + conv except in the last), GroupNorm + SiLU,
+    conv_out."""
+
+    def __init__(self, out_channels, latent_channels, block_out_channels, layers_per_block, norm_num_groups):
+        super().__init__()
+        rev = tuple(reversed(tuple(block_out_channels)))
+        self.conv_in = nn.Conv2d(latent_channels, rev[0], 3, padding=1)
+        self.mid_block = MidBlock(rev[0], norm_num_groups)
+        blocks, cin = [], rev[0]
+        for i, ch in enumerate(rev):
+            blocks.append(UpBlock(cin, ch, layers_per_block + 1, norm_num_groups, i != len(rev) - 1))
+            cin = ch
+        self.up_blocks = nn.ModuleList(blocks)
+        self.conv_norm_out = nn.GroupNorm(norm_num_groups, rev[-1], eps=1e-6)
+        self.conv_out = nn.Conv2d(rev[-1], out_channels, 3, padding=1)
+
+    def forward(self, z):
+        x = self.mid_block(self.conv_in(z))
+        for b in self.up_blocks:
+            x = b(x)
+        return self.conv_out(F.silu(self.conv_norm_out(x)))
+
+
+class AutoencoderKLFull(AutoencoderKLEncoder):
+    """Encoder half + post_quant_conv + decoder: `decode(z)` = decoder(post_quant_conv(z)) (diffusers AutoencoderKL.decode)."""
+
+    def __init__(self, **cfg):
+        super().__init__(**cfg)
+        c = self.config
+        self.decoder = Decoder(c["out_channels"], c["latent_channels"], c["block_out_channels"], c["layers_per_block"],
+                               c["norm_num_groups"])
+        self.post_quant_conv = nn.Conv2d(c["latent_channels"], c["latent_channels"], 1)
+
+    def decode(self, z):
+        return self.decoder(self.post_quant_conv(z))

@@ -49,3 +49,28 @@ def test_cfg_euler_ancestral_sampling_matches_oracle():
     got = run(p, "cuda")
     assert got.shape == ref.shape == (n, 4, 16, 16)
     assert rel(got, ref) < 2e-2, rel(got, ref)
+
+
+def test_decode_tail_of_diffusion_sampling_matches_the_reference_postprocess():
+    """Latents -> `vae.decode` one at a time -> `vae_image_postprocess` (sampling.py:117-126, data/utils.py:10-19) through the
+    kernel-backed VAE decoder, against the oracle decoder + the same post-processing in fp32."""
+    from oracle import vae_oracle as VO
+    from uwudiff_b200 import sampling as S
+    from uwudiff_b200.vae import AutoencoderKL
+
+    torch.manual_seed(0)
+    cfg = dict(block_out_channels=(64, 128), layers_per_block=1)
+    o = VO.AutoencoderKLFull(**cfg).eval()
+    p = AutoencoderKL(**cfg)
+    p.load_state_dict(o.state_dict())
+    p = p.cuda().requires_grad_(False)
+    lat = torch.randn(3, 4, 8, 8, generator=torch.Generator().manual_seed(5))
+    imgs = S.decode_latents(p, lat.cuda())
+    with torch.no_grad():
+        ref = torch.cat([o.decode(z.unsqueeze(0)) for z in lat])
+    want = [((im * 0.5 + 0.5) * 255).clamp(0, 255).to(torch.uint8).permute(1, 2, 0) for im in ref]
+    assert len(imgs) == 3 and imgs[0].shape == (16, 16, 3) and imgs[0].dtype == torch.uint8
+    for a, b in zip(imgs, want):
+        assert (a.int() - b.int()).abs().max() <= 3  # bf16 decoder vs fp32, in 8-bit pixel steps
+    raw = S.decode_latents(p, lat.cuda(), to_uint8=False)
+    assert raw.shape == (3, 3, 16, 16)

@@ -1,6 +1,7 @@
-"""§8 f2 — `AutoencoderKL.encode` (the frozen VAE of src/duwu/trainer/trainer.py:241-244) on the sm_100a kernels against the fp32
-restatement oracle/vae_oracle.py (diffusers absent: parity unpinned; the parameter count 34 163 664 of the SDXL VAE encoder +
-quant_conv is checked as a known answer).  Same state dict on both sides; bf16 compute vs fp32: rel <= max(1e-2, 2 x the error of
+"""§8 f2 / f4 — `AutoencoderKL.encode` (the frozen VAE of src/duwu/trainer/trainer.py:241-244) and `.decode` (the sampling
+callback's latents -> pictures) on the sm_100a kernels against the fp32 restatement oracle/vae_oracle.py (diffusers absent:
+parity unpinned; the published parameter counts of the SD / SDXL VAE — 83 653 863 in total, 34 163 664 of them encoder +
+quant_conv — are checked as known answers).  Same state dict on both sides; bf16 compute vs fp32: rel <= max(1e-2, 2 x the error of
 the same oracle under torch.autocast(cuda, bf16)) on the moments."""
 import pytest
 import torch
@@ -20,7 +21,7 @@ def pair(**cfg):
     from uwudiff_b200.vae import AutoencoderKL
 
     torch.manual_seed(0)
-    o = VO.AutoencoderKLEncoder(**cfg).eval()
+    o = VO.AutoencoderKLFull(**cfg).eval()
     p = AutoencoderKL(**cfg)
     r = p.load_state_dict(o.state_dict())
     assert not r.missing_keys and not r.unexpected_keys
@@ -50,7 +51,9 @@ def test_vae_encoder_matches_oracle_tiny(px, B):
 def test_sdxl_vae_encoder_full_width_matches_oracle():
     """The real SDXL VAE config (128-256-512-512, 2 resnets per block, mid attention with one 512-wide head) at 256 x 256 px."""
     o, p = pair()
-    assert sum(q.numel() for q in p.parameters()) == 34_163_664 == sum(q.numel() for q in o.parameters())
+    assert sum(q.numel() for q in p.parameters()) == 83_653_863 == sum(q.numel() for q in o.parameters())
+    enc = lambda m: sum(q.numel() for n, q in m.named_parameters() if n.startswith(("encoder.", "quant_conv.")))  # noqa: E731
+    assert enc(p) == 34_163_664 == enc(o)
     x = torch.randn(2, 3, 256, 256, generator=torch.Generator().manual_seed(1))
     with torch.no_grad():
         ref = o.moments(x)
@@ -81,3 +84,37 @@ def test_trainer_latents_come_from_the_kernel_vae():
     vae = vae.cuda()
     lat = vae.encode(torch.randn(1, 3, 64, 64, device="cuda")).latent_dist.sample()
     assert lat.shape == (1, 4, 8, 8) and lat.dtype == torch.float16 and torch.isfinite(lat).all()
+
+
+@pytest.mark.parametrize("lat,B", [(8, 2), (16, 1)])
+def test_vae_decoder_matches_oracle_tiny(lat, B):
+    o, p = pair(block_out_channels=(64, 128, 128), layers_per_block=1)
+    z = torch.randn(B, 4, lat, lat, generator=torch.Generator().manual_seed(lat))
+    with torch.no_grad():
+        ref = o.decode(z)
+    img = p.decode(z.cuda()).sample
+    assert img.shape == ref.shape == (B, 3, lat * 4, lat * 4)
+    o2 = o.cuda()
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        yard = o2.decode(z.cuda())
+    assert rel(img, ref) <= max(1e-2, 2 * rel(yard, ref)), (rel(img, ref), rel(yard, ref))
+    assert torch.equal(p.decode(z.cuda(), return_dict=False)[0], img)
+
+
+def test_sdxl_vae_decoder_full_width_matches_oracle():
+    """The real SDXL VAE decoder (512-512-256-128, 3 resnets per block, mid attention) from 32 x 32 latents to 256 x 256 px, and
+    the encode -> decode round trip shape contract of the sampling callback."""
+    o, p = pair()
+    z = torch.randn(1, 4, 32, 32, generator=torch.Generator().manual_seed(2))
+    with torch.no_grad():
+        ref = o.decode(z)
+    img = p.decode(z.cuda()).sample
+    assert img.shape == ref.shape == (1, 3, 256, 256)
+    o = o.cuda()
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        yard = o.decode(z.cuda())
+    e, y = rel(img, ref), rel(yard, ref)
+    print(f"[vae] decoded image: kernels {e:.3e}  torch-autocast-bf16 {y:.3e}")
+    assert e <= max(1e-2, 2 * y), (e, y)
+    lat = p.encode(img).latent_dist.mode()
+    assert lat.shape == z.shape

@@ -236,3 +236,20 @@ def sample_latents(unet, train_scheduler, model_fn_factory: Callable, num_steps:
     if rescale:
         lat = lat / lat.std([1, 2, 3], keepdim=True)
     return lat * vae_std + vae_mean
+
+
+def decode_latents(vae, latents: torch.Tensor, to_uint8: bool = True):
+    """Tail of `diffusion_sampling` (src/duwu/sampling/sampling.py:117-126): each generated latent is decoded on its own
+    (`vae.decode(latent.unsqueeze(0)).sample`) and post-processed like `vae_image_postprocess` (src/duwu/data/utils.py:10-19):
+    (x * 0.5 + 0.5) * 255, clamped to [0, 255], uint8, HWC.  Returns a list of [H, W, 3] uint8 CPU tensors (PIL is the caller's
+    business), or the raw [N, 3, H, W] decoder output when `to_uint8` is False."""
+    outs = [vae.decode(lat.unsqueeze(0)).sample for lat in latents]
+    imgs = torch.cat(outs)
+    if not to_uint8:
+        return imgs
+    return [((im.float() * 0.5 + 0.5) * 255).cpu().clamp(0, 255).to(torch.uint8).permute(1, 2, 0).contiguous() for im in imgs]
+
+
+def diffusion_sampling(unet, vae, train_scheduler, model_fn_factory: Callable, **kw):
+    """`duwu.sampling.sampling.diffusion_sampling` (sampling.py:41-126) end to end: `sample_latents(...)` -> `decode_latents(...)`."""
+    return decode_latents(vae, sample_latents(unet, train_scheduler, model_fn_factory, **kw))

@@ -1,17 +1,21 @@
-"""Frozen VAE encoder of the reference step: `diffusers.AutoencoderKL.from_pretrained(...)` is called as
+"""Frozen VAE of the reference step (SURVEY.md §8 f2 encode, f4 decode): `diffusers.AutoencoderKL.from_pretrained(...)` is called as
 `latent_dist = self.vae.encode(x).latent_dist; x = latent_dist.sample(); x = (x - vae_mean) / vae_std`
 (src/duwu/trainer/trainer.py:241-244; configs/demo_training_lycoris.yaml:112-117, madebyollin/sdxl-vae-fp16-fix).
 
 `AutoencoderKL` here is the drop-in for that call path: `from_pretrained`, `.config.scaling_factor`, `.encode(x).latent_dist`
-with `.sample()` / `.mode()` / `.mean` / `.logvar`, diffusers parameter names for the encoder half (`encoder.*`,
-`quant_conv.*`; decoder weights in a checkpoint are ignored — the training step never decodes).  The arithmetic runs on the
+with `.sample()` / `.mode()` / `.mean` / `.logvar`, `.decode(z).sample` (what the reference's sampling callback turns latents
+into pictures with, src/duwu/trainer/callbacks.py), diffusers parameter names (`encoder.*`, `quant_conv.*`, `decoder.*`,
+`post_quant_conv.*`).  The arithmetic runs on the
 sm_100a kernels: implicit-GEMM 3x3 / stride-2 / 1x1 convolutions, fused GroupNorm(+SiLU), and the mid-block's single-head
 attention (head_dim 512) as Q K^T -> row softmax -> P V on the GEMM kernel.  Forward only (the VAE is frozen).  No CPU path.
 
 diffusers is not installable here, so the architecture is restated (PARITY UNPINNED, like oracle/unet_oracle.py): Encoder =
 conv_in, DownEncoderBlock2D x len(block_out_channels) (layers_per_block resnets without time embedding, eps 1e-6, then an
 asymmetric-padding stride-2 conv except in the last block), UNetMidBlock2D (resnet, attention, resnet), GroupNorm + SiLU,
-conv_out to 2 * latent_channels, quant_conv 1x1.
+conv_out to 2 * latent_channels, quant_conv 1x1.  Decoder = post_quant_conv 1x1, conv_in, UNetMidBlock2D, UpDecoderBlock2D x
+len(block_out_channels) over the reversed channel list (layers_per_block + 1 resnets, nearest-2x + conv except in the last),
+GroupNorm + SiLU, conv_out.  Known answer: 83 653 863 parameters for the SDXL / SD VAE config (34 163 664 of them encoder +
+quant_conv).
 """
 from __future__ import annotations
 
@@ -135,6 +139,40 @@ class Encoder(nn.Module):
         self.conv_out = Conv2d(boc[-1], 2 * c.latent_channels, 3, padding=1)
 
 
+class _Upsample(nn.Module):
+    """Upsample2D(use_conv=True): nearest 2x (uwu_upsample2x) then a 3x3 conv."""
+
+    def __init__(self, ch: int):
+        super().__init__()
+        self.conv = Conv2d(ch, ch, 3, padding=1)
+
+    def fwd(self, x, N, H, W):
+        up = ops.upsample2x(x, N, H, W, self.conv.in_channels)
+        return self.conv.fwd3x3(up, N, 2 * H, 2 * W)
+
+
+class _UpBlock(nn.Module):
+    def __init__(self, cin, cout, layers, groups, add_up):
+        super().__init__()
+        self.resnets = nn.ModuleList([_Resnet(cin if i == 0 else cout, cout, groups) for i in range(layers)])
+        self.upsamplers = nn.ModuleList([_Upsample(cout)]) if add_up else None
+
+
+class Decoder(nn.Module):
+    def __init__(self, c):
+        super().__init__()
+        rev = tuple(reversed(tuple(c.block_out_channels)))
+        self.conv_in = Conv2d(c.latent_channels, rev[0], 3, padding=1)
+        self.mid_block = _MidBlock(rev[0], c.norm_num_groups, c.mid_block_add_attention)
+        blocks, cin = [], rev[0]
+        for i, ch in enumerate(rev):
+            blocks.append(_UpBlock(cin, ch, c.layers_per_block + 1, c.norm_num_groups, i != len(rev) - 1))
+            cin = ch
+        self.up_blocks = nn.ModuleList(blocks)
+        self.conv_norm_out = GroupNorm(c.norm_num_groups, rev[-1], eps=1e-6)
+        self.conv_out = Conv2d(rev[-1], c.out_channels, 3, padding=1)
+
+
 class DiagonalGaussianDistribution:
     """diffusers.models.autoencoders.vae.DiagonalGaussianDistribution (restated): moments = [mean | logvar] on dim 1."""
 
@@ -162,6 +200,8 @@ class AutoencoderKL(_KernelModule):
         self.encoder = Encoder(self.config)
         lc = 2 * self.config.latent_channels
         self.quant_conv = nn.Conv2d(lc, lc, 1) if self.config.use_quant_conv else None
+        self.decoder = Decoder(self.config)
+        self.post_quant_conv = Conv2d(self.config.latent_channels, self.config.latent_channels, 1) if self.config.use_quant_conv else None
         self._out_op = None
 
     def drop_cache(self):
@@ -186,23 +226,21 @@ class AutoencoderKL(_KernelModule):
                         sd = torch.load(path, map_location="cpu")
                     model.load_state_dict(sd)
                     return model
-            warnings.warn(f"uwudiff_b200: no weight file under {root}: VAE encoder initialised RANDOMLY")
+            warnings.warn(f"uwudiff_b200: no weight file under {root}: VAE initialised RANDOMLY")
             return model
         for key in (pretrained_model_name_or_path, (pretrained_model_name_or_path, subfolder)):
             if key in KNOWN_VAE_CONFIGS:
                 warnings.warn(f"uwudiff_b200: '{pretrained_model_name_or_path}' is not a local directory and the HF hub is "
-                              "unreachable: VAE encoder built from the embedded config with RANDOM weights")
+                              "unreachable: VAE built from the embedded config with RANDOM weights")
                 return cls(**KNOWN_VAE_CONFIGS[key])
         raise OSError(f"VAE '{pretrained_model_name_or_path}': neither a local directory nor an embedded config")
 
     def load_state_dict(self, sd, *a, **k):
-        """Encoder half only: `decoder.*` / `post_quant_conv.*` entries of a full AutoencoderKL checkpoint are ignored (the
-        training step never decodes); old-style mid-block attention names (query / key / value / proj_attn) are accepted."""
+        """A full diffusers AutoencoderKL checkpoint (an encoder-only one leaves the decoder as initialised: pass strict=False);
+        old-style mid-block attention names (query / key / value / proj_attn) are accepted."""
         ren = {"query": "to_q", "key": "to_k", "value": "to_v", "proj_attn": "to_out.0"}
         out = {}
         for kk, v in sd.items():
-            if kk.startswith(("decoder.", "post_quant_conv.")):
-                continue
             parts = kk.split(".")
             if "attentions" in parts:
                 for old, new in ren.items():
@@ -263,3 +301,37 @@ class AutoencoderKL(_KernelModule):
         if not return_dict:
             return (dist,)
         return types.SimpleNamespace(latent_dist=dist)
+
+    @torch.no_grad()
+    def decode(self, z: torch.Tensor, return_dict: bool = True):
+        """diffusers `AutoencoderKL.decode(z).sample`: latents [N, latent_channels, h, w] (already divided by the scaling factor by
+        the caller, as in the reference's sampling callback) -> images [N, out_channels, 8h, 8w]."""
+        ops._req_cuda(z)
+        dec = self.decoder
+        N, Cz, H, W = z.shape
+        M = N * H * W
+        h = ops.nchw_to_nhwc(z, _pad_to(Cz, 64))
+        if self.post_quant_conv is not None:
+            # 1x1 conv straight into a zero-padded 64-channel buffer (the operand width of conv_in)
+            c = self.post_quant_conv._pack()
+            buf = torch.zeros((M, c.ci_p), device=z.device, dtype=BF16)
+            ops.gemm(h, c.fwd, M, c.co_p, c.ci_p, lda=h.stride(0), bias=c.bias, out=buf[:, :c.co_p])
+            h = buf
+        h = dec.conv_in.fwd3x3(h, N, H, W)
+        h = dec.mid_block.resnets[0].fwd(h, N, H, W)
+        if dec.mid_block.attentions is not None:
+            h = dec.mid_block.attentions[0].fwd(h, N, H, W)
+        h = dec.mid_block.resnets[1].fwd(h, N, H, W)
+        for blk in dec.up_blocks:
+            for r in blk.resnets:
+                h = r.fwd(h, N, H, W)
+            if blk.upsamplers is not None:
+                h = blk.upsamplers[0].fwd(h, N, H, W)
+                H, W = 2 * H, 2 * W
+        y, _ = dec.conv_norm_out.fwd(h, N, H * W, True)
+        c = dec.conv_out._pack()
+        img = ops.conv3x3_nhwc(y.view(N, H, W, c.ci_p), c.fwd, bias=c.bias, out_dtype=torch.float32)
+        sample = ops.nhwc_to_nchw(img, N, dec.conv_out.out_channels, H, W).to(self.out_dtype)
+        if not return_dict:
+            return (sample,)
+        return types.SimpleNamespace(sample=sample)
