@@ -370,12 +370,14 @@ int uwu_lora_grad(const float* G, int64_t ldg, const float* up, const float* dow
 
 /* Factored LoKr gradients: the adapter gradients of  y = x (W + kron(w1, w2))^T  without forming
  * G = dY^T X.  x: bf16 [M, in_m*in_n] (row stride ldx), w1: fp32 [out_l, in_m].
- *   uwu_lokr_z  : z[m, l*in_n + n] = sum_i w1[l, i] x[m, i*in_n + n]            (bf16 [M, out_l*in_n], contiguous)
+ *   uwu_lokr_z  : z[m, l*in_n + n] = sum_i w1[l, i] x[m, i*in_n + n]            (bf16 [M, out_l*in_n], contiguous;
+ *                 w1_transposed: w1 is stored [in_m, out_l] and mixes as its transpose — the dY-side transform
+ *                 U[m, j, p] = sum_i w1[i, j] dY[m, i, p] of the mirrored route, used when out_k < in_n)
  *   uwu_lokr_dw1: dw1[l, i] += multiplier * sum_{m, n} v[m, l*in_n + n] x[m, i*in_n + n]   (v: bf16 [M, out_l*in_n])
  * The two tensor-core steps in between (dw2 += sum_l dY_l^T Z_l and V_l = dY_l w2) are uwu_gemm calls with k_segs / grp_n.
  * Replaces autograd through lycoris' `make_kron` weight rebuild (forward patch installed at src/duwu/trainer/trainer.py:152-154). */
 int uwu_lokr_z(const void* x, int64_t ldx, const float* w1, int64_t M, int32_t out_l, int32_t in_m, int32_t in_n, void* z,
-               void* stream);
+               int32_t w1_transposed, void* stream);
 int uwu_lokr_dw1(const void* v, const void* x, int64_t ldx, int64_t M, int32_t out_l, int32_t in_m, int32_t in_n,
                  float multiplier, float* dw1, void* stream);
 /* One-pass LoKr gradients for attention projections (w2 64x64, w1 <= 32x32): reads x [M, in_m*64] and dY [M, out_l*64] (bf16, row

@@ -497,6 +497,27 @@ def test_lokr_factored_gradients(ops, M, ol, ok, im, inn):
     assert relerr(dw1, 1.5 * r1) < TOL_BF16 and relerr(dw2, 1.5 * r2) < TOL_BF16
 
 
+@pytest.mark.parametrize("M,ol,ok,im,inn", [(4096, 5, 256, 5, 1024), (8192, 5, 128, 5, 512), (5000, 4, 64, 6, 512), (4096, 8, 256, 5, 320)])
+def test_lokr_mirrored_factored_gradients(ops, M, ol, ok, im, inn):
+    """dY-side factored route (out_k < in_n: the FeedForward down projection, w2 256 x 1024): U = (w1^T (x) I) dY, segmented
+    token-reduction GEMM for dw2, T_j = X_j w2^T, mma.sync contraction for dw1 == the einsum over the full weight gradient."""
+    from uwudiff_b200.lycoris import lokr_factored_grads_mirror
+
+    N, K = ol * ok, im * inn
+    dy, x = mk(M, N, s=1.0), mk(M, K, s=1.0)
+    w1 = torch.randn(ol, im, device=DEV)
+    w2 = torch.randn(ok, inn, device=DEV) * 0.5
+    w2b = w2.to(torch.bfloat16)
+    dw1, dw2 = torch.zeros_like(w1), torch.zeros_like(w2)
+    lokr_factored_grads_mirror(dy, x, M, w1, w2b, dw1, dw2, 1.0)
+    G4 = (dy.float().t() @ x.float()).view(ol, ok, im, inn)
+    r1 = torch.einsum("lkin,kn->li", G4, w2b.float())
+    r2 = torch.einsum("lkin,li->kn", G4, w1)
+    assert relerr(dw1, r1) < TOL_BF16 and relerr(dw2, r2) < TOL_BF16, (relerr(dw1, r1), relerr(dw2, r2))
+    lokr_factored_grads_mirror(dy, x, M, w1, w2b, dw1, dw2, 0.5)
+    assert relerr(dw1, 1.5 * r1) < TOL_BF16 and relerr(dw2, 1.5 * r2) < TOL_BF16
+
+
 @pytest.mark.parametrize("M,ol,im", [(4096, 20, 20), (16384, 20, 20), (8192 + 5, 10, 10), (1232, 20, 32), (1000, 5, 5),
                                       (70, 32, 20), (3, 20, 20), (65536, 10, 10)])
 def test_lokr_fused_one_pass_gradients(ops, M, ol, im):

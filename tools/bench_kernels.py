@@ -152,6 +152,24 @@ def case_lokr_fact():
         print(f"G route total {tag}: {us:.1f} us", flush=True)
 
 
+def case_lokr_mirror():
+    """FeedForward down projection (w1 5x5, w2 256x1024 / 128x512): dY-side factored route vs the G = dY^T X route."""
+    from uwudiff_b200.lycoris import lokr_factored_grads_mirror
+
+    for (M, ol, ok, im, inn) in [(16384, 5, 256, 5, 1024), (65536, 5, 128, 5, 512)]:
+        N, K = ol * ok, im * inn
+        dy, x = mk(M, N), mk(M, K)
+        w1, w2 = torch.randn(ol, im, device=dev), torch.randn(ok, inn, device=dev)
+        w2b = w2.to(torch.bfloat16)
+        dw1, dw2 = torch.zeros_like(w1), torch.zeros_like(w2)
+        tag = f"M{M} w1 {ol}x{im} w2 {ok}x{inn}"
+        us = timeit(lambda: lokr_factored_grads_mirror(dy, x, M, w1, w2b, dw1, dw2))
+        print(f"mirrored factored total {tag}: {us:.1f} us", flush=True)
+        G = torch.empty(N, K, device=dev)
+        us = timeit(lambda: (ops.gemm(dy, x, N, K, M, a_layout=A_COL, lda=N, b_layout=B_KN, ldb=K, out=G), ops.lokr_grad(G, w1, w2, dw1, dw2)))
+        print(f"G route total {tag}: {us:.1f} us", flush=True)
+
+
 def case_lokr_fused():
     """One-pass LoKr gradients (attention adapters, w2 64x64) against the G = dY^T X route; bytes = one read of x and dY."""
     for (M, ol, im) in [(16384, 20, 20), (65536, 10, 10), (4096, 20, 20)]:

@@ -129,7 +129,7 @@ SIGNATURES = {
     "uwu_conv_wgrad_unpack": (C.c_int, [_P, _I64, _I32, _I32, _I32, _I32, _I32, _P, _P]),
     "uwu_colsum_groups_bf16": (C.c_int, [_P, _I64, _I32, _I32, _I32, _I32, _P, _P]),
     "uwu_fold_batch": (C.c_int, [_P, _P, _I32, _I32, _P]),
-    "uwu_lokr_z": (C.c_int, [_P, _I64, _P, _I64, _I32, _I32, _I32, _P, _P]),
+    "uwu_lokr_z": (C.c_int, [_P, _I64, _P, _I64, _I32, _I32, _I32, _P, _I32, _P]),
     "uwu_lokr_dw1": (C.c_int, [_P, _P, _I64, _I64, _I32, _I32, _I32, _F, _P, _P]),
     "uwu_groupnorm_fwd_fused": (C.c_int, [_P, _I32, _I32, _I32, _I32, _F, _P, _P, _I32, _P, _P, _P, _P, _P]),
     "uwu_groupnorm_bwd_fused": (C.c_int, [_P, _P, _I32, _I32, _I32, _I32, _P, _P, _P, _I32, _P, _P, _P, _P, _P]),

@@ -412,10 +412,10 @@ __global__ void __launch_bounds__(256) lokr_grad_batch_kernel(const uwu_lokr_gra
 // thread = (row m, 8 consecutive n); l processed in blocks of LB so the accumulators stay in registers
 template <int LB>
 __global__ void __launch_bounds__(256) lokr_z_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, const float* __restrict__ w1,
-                                                     long long M, int ol, int im, int in_n, __nv_bfloat16* __restrict__ z) {
+                                                     long long M, int ol, int im, int in_n, __nv_bfloat16* __restrict__ z, int w1_t) {
     pdl_trigger();
-    extern __shared__ float sw1[];  // [ol][im]
-    for (int i = threadIdx.x; i < ol * im; i += blockDim.x) sw1[i] = w1[i];
+    extern __shared__ float sw1[];  // [ol][im]  (w1_t: w1 is stored [im][ol], i.e. the mixing matrix is its transpose)
+    for (int i = threadIdx.x; i < ol * im; i += blockDim.x) sw1[i] = w1_t ? w1[(i % im) * ol + i / im] : w1[i];
     __syncthreads();
     const int nv = in_n >> 3;
     const long long total = M * nv;
@@ -858,7 +858,7 @@ extern "C" int uwu_copy2d_bf16(const void* src, int32_t src_dtype, int64_t lds, 
 }
 
 extern "C" int uwu_lokr_z(const void* x, int64_t ldx, const float* w1, int64_t M, int32_t out_l, int32_t in_m, int32_t in_n,
-                          void* z, void* stream_) {
+                          void* z, int32_t w1_transposed, void* stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     UWU_CHECK_ARG(x && w1 && z && M > 0, "uwu_lokr_z: bad arguments");
     UWU_CHECK_ARG(out_l > 0 && out_l <= 64 && in_m > 0 && in_m <= 64 && in_n > 0 && in_n % 8 == 0 && ldx % 8 == 0 &&
@@ -871,9 +871,9 @@ extern "C" int uwu_lokr_z(const void* x, int64_t ldx, const float* w1, int64_t M
     const auto* xp = reinterpret_cast<const __nv_bfloat16*>(x);
     auto* zp = reinterpret_cast<__nv_bfloat16*>(z);
     if (out_l % 5 == 0)
-        lokr_z_kernel<5><<<grid, 256, sm, stream>>>(xp, ldx, w1, M, out_l, in_m, in_n, zp);
+        lokr_z_kernel<5><<<grid, 256, sm, stream>>>(xp, ldx, w1, M, out_l, in_m, in_n, zp, w1_transposed);
     else
-        lokr_z_kernel<4><<<grid, 256, sm, stream>>>(xp, ldx, w1, M, out_l, in_m, in_n, zp);
+        lokr_z_kernel<4><<<grid, 256, sm, stream>>>(xp, ldx, w1, M, out_l, in_m, in_n, zp, w1_transposed);
     UWU_CHECK_LAUNCH();
     return UWU_OK;
 }

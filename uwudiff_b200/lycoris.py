@@ -49,6 +49,7 @@ def factorization(dimension: int, factor: int = -1):
 
 
 _LOKR_FUSED = os.environ.get("UWU_LOKR_FUSED", "1") != "0"
+_LOKR_MIRROR = os.environ.get("UWU_LOKR_MIRROR", "1") != "0"
 
 
 class _Adapter(nn.Module):
@@ -171,7 +172,7 @@ class LokrLinear(_Adapter):
         """Use the factored gradient (no G = dY^T X) when the factor shapes fit its kernels and it is cheaper than the
         full token-reduction GEMM: 2/in_m of the FLOPs, but four passes over [M, *]-sized data."""
         (ol, ok), (im, inn) = self.shape
-        if self.fused_ok(M):
+        if self.fused_ok(M) or self.mirror_ok(M):
             return True
         # measured on B200 (profiles/r01_lokr_factored_stages.log): the factored route wins for the FeedForward adapters
         # (w2 2048x256: 263 vs 454 us, w2 1024x128: 404 vs 673 us) and loses for the 64x64 attention factors (135 vs 82 us),
@@ -187,9 +188,25 @@ class LokrLinear(_Adapter):
         # tokens on: the cross-attention K / V adapters see 1232 text tokens and stay on the G route, 35 us for the pair)
         return _LOKR_FUSED and M >= 4096 and self.lokr_w1.is_cuda and ops.lokr_fused_supported(ol, ok, im, inn)
 
+    def mirror_ok(self, M: int) -> bool:
+        """out_k < in_n (the FeedForward down projection: w2 256 x 1024): the factored route with the w1-mixing applied to dY
+        instead of X, so that every intermediate is [M, im * ok] wide instead of [M, ol * in_n] (lokr_factored_grads_mirror)."""
+        (ol, ok), (im, inn) = self.shape
+        # measured (profiles/r02_lokr_mirror.log): w2 256 x 1024 at 16384 tokens 170 vs 184 us on the G route; w2 128 x 512 at
+        # 65536 tokens LOSES (299 vs 207 us: one row tile, no CTA pairs, five 128-wide GEMMs), hence ok == 256
+        return (_LOKR_MIRROR and self._w2_bf16 is not None and M >= 4096 and ol <= 32 and im <= 32 and ol >= 4 and ok == 256
+                and inn % 64 == 0 and ok < inn)
+
     def grads_factored(self, dy, x, M):
         """dy: bf16 [M, ol*ok] (row stride dy.stride(0)), x: bf16 [M, im*inn]; accumulates into lokr_w1.grad / lokr_w2.grad."""
         from .unet import _grad_of
+
+        if not self.fused_ok(M) and self.mirror_ok(M):
+            if not dy.is_contiguous():  # (a column slice of a fused projection: the dY-side kernels want whole rows)
+                dy = ops.copy2d(dy, torch.empty((M, dy.shape[1]), device=dy.device, dtype=dy.dtype))
+            lokr_factored_grads_mirror(dy, x, M, self.lokr_w1.detach(), self._w2_bf16, _grad_of(self.lokr_w1), _grad_of(self.lokr_w2),
+                                       self.scale * self.multiplier)
+            return
 
         if self.fused_ok(M):
             ops.lokr_fused_grad(dy, x, M, self.lokr_w1.detach(), self.lokr_w2.detach(), _grad_of(self.lokr_w1), _grad_of(self.lokr_w2),
@@ -217,6 +234,25 @@ def lokr_factored_grads(dy, x, M, w1, w2_bf16, dw1, dw2, mult: float = 1.0):
     ops.gemm(dy, w2_bf16, M, ol * inn, ok, a_layout=A_ROW, lda=dy.stride(0), b_layout=B_KN, ldb=inn, out=vw, grp_n=inn,
              a_grp_koff=ok, block_n=bn)
     ops.lokr_dw1(vw, x, M, ol, im, inn, dw1, mult)
+
+
+def lokr_factored_grads_mirror(dy, x, M, w1, w2_bf16, dw1, dw2, mult: float = 1.0):
+    """The same gradients with the w1-mixing applied on the OUTPUT side (cheaper when out_k < in_n, e.g. w2 256 x 1024):
+         U[m,j,:] = sum_i w1[i,j] dY[m,i,:];          dw2 += sum_{m,j} U[m,j,:]^T X[m,j,:];
+         T[m,j,:] = X[m,j,:] w2^T  ([M, im*ok]);      dw1[i,j] += sum_m <dY[m,i,:], T[m,j,:]>.
+    Every intermediate is [M, im * ok] (42 MB at 16384 x 1280) where the X-side route writes [M, ol * in_n] (168 MB) twice."""
+    from ._lib import A_COL, B_KN
+
+    (ol, im), (ok, inn) = w1.shape, w2_bf16.shape
+    uw = ops._workspace((M * im * ok + 1) // 2, dy.device, "lokr_z").view(torch.bfloat16)[: M * im * ok].view(M, im * ok)
+    ops.lokr_z(dy, w1, M, ok, uw, transposed=True)
+    # token-reduction GEMM whose reduction runs over (j, m): segment j reads U[:, j*ok:(j+1)*ok] and X[:, j*inn:(j+1)*inn]
+    ops.gemm(uw, x, ok, inn, M, a_layout=A_COL, lda=im * ok, b_layout=B_KN, ldb=x.stride(0), out=dw2, accumulate=True,
+             alpha=mult, stream_k=1, k_segs=im, a_seg_off=ok, b_seg_off=inn)
+    tw = ops._workspace((M * im * ok + 1) // 2, dy.device, "lokr_v").view(torch.bfloat16)[: M * im * ok].view(M, im * ok)
+    for j in range(im):  # T_j = X_j w2^T: w2 [ok, inn] is the K-major right operand as stored
+        ops.gemm(x[:, j * inn:(j + 1) * inn], w2_bf16, M, ok, inn, lda=x.stride(0), out=tw[:, j * ok:(j + 1) * ok])
+    ops.lokr_dw1(dy, tw, M, ol, im, ok, dw1, mult)
 
 
 class NormDelta(_Adapter):

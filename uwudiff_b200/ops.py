@@ -709,12 +709,14 @@ def lokr_grad(G: torch.Tensor, w1: torch.Tensor, w2: torch.Tensor, dw1: torch.Te
                               _stream()), "uwu_lokr_grad")
 
 
-def lokr_z(x: torch.Tensor, w1: torch.Tensor, M: int, in_n: int, out: torch.Tensor) -> torch.Tensor:
-    """out[m, l*in_n + n] = sum_i w1[l, i] x[m, i*in_n + n]  (bf16 [M, ol*in_n]); x may be a column-sliced view."""
+def lokr_z(x: torch.Tensor, w1: torch.Tensor, M: int, in_n: int, out: torch.Tensor, transposed: bool = False) -> torch.Tensor:
+    """out[m, l*in_n + n] = sum_i w[l, i] x[m, i*in_n + n]  (bf16 [M, ol*in_n]); x may be a column-sliced view.
+    w = w1, or w1^T when `transposed` (w1 is then read as stored, [in_m, out_l])."""
     _req_cuda(x, w1, out)
-    ol, im = w1.shape
+    ol, im = (w1.shape[1], w1.shape[0]) if transposed else w1.shape
     assert x.dtype == torch.bfloat16 and x.stride(1) == 1 and out.dtype == torch.bfloat16 and out.is_contiguous()
-    check(lib().uwu_lokr_z(_ptr(x), x.stride(0), _ptr(w1), M, ol, im, in_n, _ptr(out), _stream()), "uwu_lokr_z")
+    assert w1.is_contiguous() and w1.dtype == torch.float32
+    check(lib().uwu_lokr_z(_ptr(x), x.stride(0), _ptr(w1), M, ol, im, in_n, _ptr(out), int(transposed), _stream()), "uwu_lokr_z")
     return out
 
 
