@@ -423,6 +423,18 @@ class LycorisNetwork(nn.Module):
         for org in self._orgs:
             org._fold_epoch = FOLD.epoch
 
+    def mark_folded(self) -> bool:
+        """The operands still hold the fold of the previous forward (the adapters have not changed since: later micro-batches
+        of a gradient-accumulation window).  False if there is no previous fold to rely on."""
+        from .unet import FOLD
+
+        t = getattr(self, "_fold", None)
+        if t is None or t["gen"] != FOLD.gen:
+            return False
+        for org in self._orgs:
+            org._fold_epoch = FOLD.epoch
+        return True
+
     def flush_grads(self):
         """Contract every pending G of the LoKr adapters into (dw1, dw2) in ONE launch (uwu_lokr_grad_batch).  Called by the
         denoiser's backward whenever a top-level block is finished (before its gradients are handed to the DDP buckets)."""

@@ -299,6 +299,8 @@ class DMTrainer(BaseTrainer):
             f["buckets"].enabled = last  # earlier micro-batches only accumulate locally
             if last:
                 f["buckets"].begin_step()
+        if k > 1 and f["micro"] % k != 0 and self.lycoris_model is not None:
+            object.__setattr__(self.lycoris_model, "skip_next_fold", True)  # adapters untouched since the window's first forward
         out = self.training_step(batch, idx)
         (out["loss"] if k == 1 else out["loss"] / k).backward()
         f["micro"] += 1
@@ -353,6 +355,18 @@ class DMTrainer(BaseTrainer):
             (out["loss"] if k == 1 else out["loss"] / k).backward()
             self.loss._step_dev += 1
         n1 = ops.launch_count()
+        ga2, out2 = None, None
+        if k > 1 and self.lycoris_model is not None:
+            # micro-batches 2..k of an accumulation window: the same graph without the adapter fold (operands are still valid)
+            if hasattr(self.unet, "_hook"):
+                self.unet._hook = None
+            ga2 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(ga2, pool=ga.pool()):
+                object.__setattr__(self.lycoris_model, "skip_next_fold", True)
+                out2 = self.training_step(None, 0, _prepared=(g["x"], g["ctx"], g["mask"], g["added"], g["cak"]))
+                (out2["loss"] / k).backward()
+                self.loss._step_dev += 1
+        n1b = ops.launch_count()
         gb = torch.cuda.CUDAGraph()
         with torch.cuda.graph(gb, pool=ga.pool()):
             tables = f["opt"]._tables or []
@@ -364,9 +378,11 @@ class DMTrainer(BaseTrainer):
                 f["opt"].zero_grad(set_to_none=False)
         n2 = ops.launch_count()
         ops.add_graph_launches(-(n2 - n0))  # recorded, not executed: only replays count as launches
+        n2 -= n1b - n1  # (launch counts per graph: fwdbwd n1 - n0, its fold-free twin n1b - n1, optimizer step n2 - n1b)
         # host staging buffers of tables uploaded inside the capture are re-read by every replay: keep them alive
         keep = list(self.lycoris_model._grad_tables.values()) if self.lycoris_model is not None else []
-        g.update(fwdbwd=ga, optstep=gb, n_fwdbwd=n1 - n0, n_opt=n2 - n1, out=out, state="replay", keep=keep)
+        g.update(fwdbwd=ga, optstep=gb, n_fwdbwd=n1 - n0, n_opt=n2 - n1, out=out, state="replay", keep=keep, fwdbwd_nofold=ga2,
+                 out_nofold=out2, n_fwdbwd_nofold=n1b - n1)
 
     def _write_hyper(self):
         """[lr, 1 - b1^t, sqrt(1 - b2^t), 0] per param group + [ema decay, 0, 0, 0]: one pinned H2D copy per step."""
@@ -395,11 +411,18 @@ class DMTrainer(BaseTrainer):
         k = f["accum"]
         last = (f["micro"] + 1) % k == 0
         self._write_hyper()
-        g["fwdbwd"].replay()
-        ops.add_graph_launches(g["n_fwdbwd"])
+        first = f["micro"] % k == 0
+        if first or g.get("fwdbwd_nofold") is None:
+            g["fwdbwd"].replay()
+            ops.add_graph_launches(g["n_fwdbwd"])
+            out = g["out"]
+        else:
+            g["fwdbwd_nofold"].replay()
+            ops.add_graph_launches(g["n_fwdbwd_nofold"])
+            out = g["out_nofold"]
         f["micro"] += 1
         if not last:
-            return g["out"]
+            return out
         if f["buckets"] is not None:
             f["buckets"]._reduce(f["buckets"].flat)  # one exchange of the whole flat buffer, ordered on this stream
         g["optstep"].replay()
@@ -408,7 +431,7 @@ class DMTrainer(BaseTrainer):
         if f["sched"] is not None:
             f["sched"].step()
         self.global_step += 1
-        return g["out"]
+        return out
 
     # ---- checkpoint / resume of what Lightning's .ckpt carries besides the weights ----------------------------------
     def fit_state_dict(self) -> Dict[str, Any]:

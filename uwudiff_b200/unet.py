@@ -884,7 +884,14 @@ class UNet2DConditionModel(nn.Module):
         FOLD.epoch += 1
         ly = getattr(self, "_uwu_lycoris", None)
         if ly is not None:
-            ly.fold_all()  # every adapter delta folded into its bf16 operand (or norm affine) in one launch
+            # every adapter delta folded into its bf16 operand (or norm affine) in one launch — unless the owner of the
+            # optimizer step says the adapters are untouched since the last forward (DMTrainer: micro-batches 2..k of an
+            # accumulation window; 3.5 ms of fold per forward at SDXL size)
+            skip = getattr(ly, "skip_next_fold", False)
+            if skip:
+                object.__setattr__(ly, "skip_next_fold", False)
+            if not (skip and ly.mark_folded()):
+                ly.fold_all()
         st = _State()
         st.N, st.H, st.W = B, H, W
         st.need_temb_grad = any(p.requires_grad for p in self.time_embedding.parameters()) or any(
