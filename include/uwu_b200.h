@@ -91,8 +91,9 @@ typedef struct uwu_gemm_desc {
     /* segmented reduction (UWU_A_COL x UWU_B_KN): out = sum_{s < k_segs} A[:, s*a_seg_off + m]^T B[:, s*b_seg_off + n];
        K is the length of ONE segment. Used for the factored LoKr gradient dw2 = sum_l dY_l^T Z_l. 0/1 = off. */
     int32_t k_segs, a_seg_off, b_seg_off;
-    /* grouped N (UWU_A_ROW x UWU_B_KN): out[:, g*grp_n + n] = A[:, g*a_grp_koff : +K] B[:, n] with one B [K, grp_n]
-       shared by all N/grp_n groups (block-diagonal right operand). Used for V_l = dY_l w2. 0 = off. */
+    /* grouped N (UWU_A_ROW): out[:, g*grp_n + n] = A[:, g*a_grp_koff : +K] B[:, n] with ONE right operand — [K, grp_n] (UWU_B_KN)
+       or [grp_n, K] (UWU_B_NK) — shared by all N/grp_n groups (block-diagonal right operand). Used for V_l = dY_l w2 and
+       T_j = X_j w2^T of the factored LoKr gradients. 0 = off. */
     int32_t grp_n, a_grp_koff;
     /* diagnostics: override shared-memory descriptor fields (0 = default) */
     int32_t dbg_a_lbo, dbg_a_sbo, dbg_a_kadv, dbg_b_lbo, dbg_b_sbo, dbg_b_kadv;

@@ -277,7 +277,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
                             else if (p.b_mode == 0)
                                 for (int i = 0; i < p.n_inst; ++i)  // instruction i covers columns [i * bn_inst, (i + 1) * bn_inst): half per CTA
                                     tma_load_2d_cg2(sb + i * p.b_inst_bytes, &p.tmBh, fb, kb * BLOCK_K,
-                                                    n0 + i * p.bn_inst + (int)cta_rank * (p.bn_inst >> 1));
+                                                    n0 - grp * p.grp_n + i * p.bn_inst + (int)cta_rank * (p.bn_inst >> 1));
                             else
                                 tma_load_3d_cg2(sb, &p.tmBh, fb, 0, kbs * BLOCK_K,
                                                 ((n0 - grp * p.grp_n + kseg * p.b_seg_off) >> 6) + (int)cta_rank * (p.block_n >> 7));
@@ -312,12 +312,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
                                 const int rk = wi.rank;
                                 if (p.b_mode == 0)
                                     tma_load_2d_mc(sb + rk * p.b_half_bytes, &p.tmBh, &full_bar[stage], kb * BLOCK_K,
-                                                   n0 + rk * (p.block_n >> 1), (uint16_t)3);
+                                                   n0 - grp * p.grp_n + rk * (p.block_n >> 1), (uint16_t)3);
                                 else
                                     tma_load_3d_mc(sb + rk * p.b_half_bytes, &p.tmBh, &full_bar[stage], 0, kb * BLOCK_K,
                                                    (n0 >> 6) + rk * (p.block_n >> 7), (uint16_t)3);
                             } else if (p.b_mode == 0) {
-                                tma_load_2d(sb, &p.tmB, &full_bar[stage], kb * BLOCK_K, n0);
+                                tma_load_2d(sb, &p.tmB, &full_bar[stage], kb * BLOCK_K, n0 - grp * p.grp_n);
                             } else {
                                 const int bn0 = n0 - grp * p.grp_n + kseg * p.b_seg_off;
                                 if (p.b_3d) {
@@ -1030,7 +1030,7 @@ extern "C" int uwu_gemm(const uwu_gemm_desc* d, void* stream_) {
     p.kb_per_seg = 0; p.a_seg_off = 0; p.b_seg_off = 0; p.b_3d = 0;
     p.grp_n = 0; p.a_grp_koff = 0;
     if (d->grp_n > 0) {
-        UWU_CHECK_ARG(d->a_layout == UWU_A_ROW && d->b_layout == UWU_B_KN, "uwu_gemm: grp_n needs the A_ROW x B_KN form");
+        UWU_CHECK_ARG(d->a_layout == UWU_A_ROW, "uwu_gemm: grp_n needs a row-major A");  // B: [K, grp_n] (KN) or [grp_n, K] (NK)
         UWU_CHECK_ARG(d->grp_n % bn == 0, "uwu_gemm: block_n %d must divide grp_n %d", bn, d->grp_n);
         p.grp_n = d->grp_n;
         p.a_grp_koff = d->a_grp_koff;
@@ -1122,7 +1122,7 @@ extern "C" int uwu_gemm(const uwu_gemm_desc* d, void* stream_) {
     // ---------------- B tensor map ----------------
     if (d->b_layout == UWU_B_NK) {
         UWU_CHECK_ARG(d->ldb % 8 == 0 && d->ldb >= d->K, "uwu_gemm: ldb %lld must be >= K and a multiple of 8", (long long)d->ldb);
-        uint64_t dims[2] = {(uint64_t)d->K, (uint64_t)d->N};
+        uint64_t dims[2] = {(uint64_t)d->K, (uint64_t)(d->grp_n > 0 ? d->grp_n : d->N)};
         uint64_t str[1] = {(uint64_t)d->ldb * 2};
         uint32_t box[2] = {BLOCK_K, (uint32_t)(bn > 256 ? 256 : bn)};  // (wide tiles never use this map: per-instruction half boxes)
         if (encode_tmap_bf16(&p.tmB, d->b, 2, dims, str, box, 1)) return UWU_ERR_INVALID;
@@ -1329,7 +1329,7 @@ extern "C" int uwu_gemm(const uwu_gemm_desc* d, void* stream_) {
     UWU_CHECK_ARG(n_inst == 1 || use_pair, "uwu_gemm: internal error (wide tile without the CTA-pair kernel)");
     if ((use_pair || (want_mc && pair_shape_ok && !p.stream_k)) ) {
         if (d->b_layout == UWU_B_NK) {
-            uint64_t dims[2] = {(uint64_t)d->K, (uint64_t)d->N};
+            uint64_t dims[2] = {(uint64_t)d->K, (uint64_t)(d->grp_n > 0 ? d->grp_n : d->N)};
             uint64_t str[1] = {(uint64_t)d->ldb * 2};
             p.n_inst = n_inst;
             p.bn_inst = bn / n_inst;

@@ -49,9 +49,9 @@ def factorization(dimension: int, factor: int = -1):
 
 
 _LOKR_FUSED = os.environ.get("UWU_LOKR_FUSED", "1") != "0"
-# Mirrored factored route for the FeedForward down projections: 170 vs 184 us per adapter in isolation, i.e. -0.8 ms of a 340 ms
-# step (inside the run-to-run noise) for five more narrow GEMM launches per layer; opt-in (UWU_LOKR_MIRROR=1), tested either way.
-_LOKR_MIRROR = os.environ.get("UWU_LOKR_MIRROR", "0") != "0"
+# Mirrored factored route for the FeedForward down projections (UWU_LOKR_MIRROR=0 falls back to the G = dY^T X route): same-box
+# A/B -3 ms of a 347 ms step (profiles/r02_bench_g_*).
+_LOKR_MIRROR = os.environ.get("UWU_LOKR_MIRROR", "1") != "0"
 
 
 class _Adapter(nn.Module):
@@ -252,8 +252,10 @@ def lokr_factored_grads_mirror(dy, x, M, w1, w2_bf16, dw1, dw2, mult: float = 1.
     ops.gemm(uw, x, ok, inn, M, a_layout=A_COL, lda=im * ok, b_layout=B_KN, ldb=x.stride(0), out=dw2, accumulate=True,
              alpha=mult, stream_k=1, k_segs=im, a_seg_off=ok, b_seg_off=inn)
     tw = ops._workspace((M * im * ok + 1) // 2, dy.device, "lokr_v").view(torch.bfloat16)[: M * im * ok].view(M, im * ok)
-    for j in range(im):  # T_j = X_j w2^T: w2 [ok, inn] is the K-major right operand as stored
-        ops.gemm(x[:, j * inn:(j + 1) * inn], w2_bf16, M, ok, inn, lda=x.stride(0), out=tw[:, j * ok:(j + 1) * ok])
+    # T_j = X_j w2^T for all j in one grouped launch: group j reads A columns [j*inn, +inn) and the SAME right operand, w2
+    # [ok, inn] K-major as stored
+    bn = next(b for b in (256, 128, 64, 32, 16) if ok % b == 0)
+    ops.gemm(x, w2_bf16, M, im * ok, inn, lda=x.stride(0), out=tw, grp_n=ok, a_grp_koff=inn, block_n=bn)
     ops.lokr_dw1(dy, tw, M, ol, im, ok, dw1, mult)
 
 
