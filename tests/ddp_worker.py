@@ -44,21 +44,23 @@ def main():
         model_config={"unet": {"_target_": "duwu.modules.unet_patch.UNet2DFromScratch.from_config", "config": dict(cfgd)},
                       "te": {"_target_": "duwu.modules.text_encoders.ConcatTextEncoders", "hidden_dim": 128, "pooled_dim": 64},
                       "vae": None},
-        lycoris_config={"preset": LYCORIS_PRESET, "config": LYCORIS_CFG} if mode == "lycoris" else None,
+        lycoris_config={"preset": LYCORIS_PRESET, "config": LYCORIS_CFG} if mode in ("lycoris", "accum") else None,
         lr=1e-3, optimizer="torch.optim.SGD", opt_config={}, use_warm_up=False, lr_scheduler=None,
         loss_config={"_target_": "duwu.loss.DiffusionLoss",
                      "scheduler": {"_target_": "diffusers.EulerDiscreteScheduler.from_pretrained",
                                    "pretrained_model_name_or_path": "stabilityai/stable-diffusion-xl-base-1.0",
                                    "subfolder": "scheduler"}},
         device="cpu")
-    if mode == "lycoris":  # non-trivial adapter state so every gradient is non-zero (per-rank, overwritten by the broadcast)
+    if mode in ("lycoris", "accum"):  # non-trivial adapter state so every gradient is non-zero (per-rank, overwritten by the broadcast)
         g = torch.Generator().manual_seed(1 + rank)
         tr.lycoris_model.flat_params.copy_(torch.randn(tr.lycoris_model.flat_params.shape, generator=g) * 0.05)
+    if mode == "accum":
+        return accum_mode(tr, rank, world, out_path)
     fit = tr.setup_fit(gradient_clip_val=None, seed=1215, n_buckets=3)
     buckets = fit["buckets"]
     assert buckets is not None and buckets.world == world
     assert tr.loss.seed == 1215 + rank  # pl.seed_everything(seed + global_rank), test_scripts/test_train.py:68-69
-    params = list(tr.lycoris_model.parameters()) if mode == "lycoris" else [p for p in tr.unet.parameters() if p.requires_grad]
+    params = list(tr.lycoris_model.parameters()) if mode in ("lycoris", "accum") else [p for p in tr.unet.parameters() if p.requires_grad]
     before = torch.cat([p.detach().reshape(-1).clone() for p in params])
     frozen = torch.cat([p.detach().reshape(-1)[:64].clone() for p in tr.unet.parameters()])  # frozen base synced as well
     torch.manual_seed(100 + rank)  # different data per rank
@@ -92,6 +94,47 @@ def main():
     torch.save({"loss": float(out["loss"]), "before": before, "after": after, "local": local, "reduced": reduced,
                 "n_calls": len(seen["local"]), "reduced_elems": buckets.reduced_elems, "n": buckets.flat.numel(),
                 "t": out["aux_output"].timesteps.clone(), "frozen": frozen, "after3": after3}, out_path)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def accum_mode(tr, rank, world, out_path):
+    """configs[4] on fewer GPUs (bench.py --scaling strong): accumulate_grad_batches = 2 under data parallelism.  The first
+    micro-batch only accumulates locally (no exchange, parameters untouched, adapter fold skipped on the second forward); the
+    exchange runs once, during the last micro-batch's backward, on the MEAN of the micro-batch gradients."""
+    from uwudiff_b200.data import DummyDataset
+
+    fit = tr.setup_fit(gradient_clip_val=None, seed=1215, n_buckets=3, accumulate_grad_batches=2)
+    buckets = fit["buckets"]
+    params = list(tr.lycoris_model.parameters())
+    before = torch.cat([p.detach().reshape(-1).clone() for p in params])
+    torch.manual_seed(100 + rank)
+    ds = DummyDataset(sample_size=[4, 16, 16], n_samples=4)
+    mb = [ds.collate([ds[0], ds[1]]), ds.collate([ds[2], ds[3]])]
+    seen = {"local": [], "reduced": []}
+    orig_reduce = buckets._reduce
+
+    def spy(view):
+        seen["local"].append((view.data_ptr(), view.detach().clone()))
+        orig_reduce(view)
+        seen["reduced"].append(view.detach().clone())
+
+    buckets._reduce = spy
+    tr.fit_step(mb[0], 0)
+    calls_mb1 = len(seen["local"])
+    mid = torch.cat([p.detach().reshape(-1).clone() for p in params])
+    g_mb1 = tr.lycoris_model.flat_grads.detach().clone()  # (g0 / 2), local
+    tr.fit_step(mb[1], 1)
+    after = torch.cat([p.detach().reshape(-1).clone() for p in params])
+    flat0 = buckets.flat.data_ptr()
+    local, reduced = torch.zeros_like(buckets.flat), torch.zeros_like(buckets.flat)
+    for (ptr, loc), red in zip(seen["local"], seen["reduced"]):
+        off = (ptr - flat0) // 4
+        local[off:off + loc.numel()] = loc
+        reduced[off:off + red.numel()] = red
+    torch.save({"calls_mb1": calls_mb1, "n_calls": len(seen["local"]), "before": before, "mid": mid, "after": after, "local": local,
+                "reduced": reduced, "g_mb1": g_mb1, "reduced_elems": buckets.reduced_elems, "n": buckets.flat.numel(),
+                "global_step": tr.global_step}, out_path)
     dist.barrier()
     dist.destroy_process_group()
 

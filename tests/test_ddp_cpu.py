@@ -51,3 +51,17 @@ def test_two_rank_gloo_step(tmp_path, mode, port):
     assert torch.equal(r0["before"], r1["before"]) and torch.equal(r0["frozen"], r1["frozen"])
     assert torch.equal(r0["after3"], r1["after3"]) and not torch.equal(r0["after3"], r0["after"])
     assert torch.equal(r0["after"], r1["after"]) and not torch.equal(r0["after"], r0["before"])
+
+
+def test_two_rank_gloo_gradient_accumulation(tmp_path):
+    """Strong-scaling mode (global batch fixed, `accumulate_grad_batches` micro-batches per rank): one exchange per window."""
+    r0, r1 = run_world(tmp_path, "accum", 29633)
+    for r in (r0, r1):
+        assert r["calls_mb1"] == 0 and r["n_calls"] > 1               # nothing exchanged before the last micro-batch
+        assert torch.equal(r["mid"], r["before"])                     # parameters untouched inside the window
+        assert float(r["g_mb1"].abs().sum()) > 0                      # ... while the local gradient accumulates
+        assert r["reduced_elems"] == r["n"] and r["global_step"] == 1
+    assert not torch.equal(r0["local"], r1["local"])
+    mean = (r0["local"] + r1["local"]) / 2
+    assert torch.allclose(r0["reduced"], mean, rtol=1e-6, atol=1e-9) and torch.equal(r0["reduced"], r1["reduced"])
+    assert torch.equal(r0["after"], r1["after"]) and not torch.equal(r0["after"], r0["before"])
