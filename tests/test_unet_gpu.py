@@ -505,43 +505,57 @@ def _batches(n, B=2, seed=11):
     return [(torch.randn(B, 4, 16, 16, generator=g).cuda(), ["DUMMY TEST"] * B, [], {"time_ids": ids.cuda()}, {}) for _ in range(n)]
 
 
-def test_cuda_graph_step_reproduces_the_eager_step():
-    """`setup_fit(cuda_graph=True)`: after two eager optimizer steps the step is captured (forward + backward, clip + AdamW)
-    and replayed.  Same seeds, same batches, same kernels in the same order: timesteps are bit-equal, losses, gradient norms and
-    the parameters after 6 steps agree with the all-eager run to the noise floor of the fp32 atomic accumulations in the
-    split-K / dQ reductions (two EAGER runs differ by ~1.5e-8 in a few hundred parameters and, when such a difference flips a
-    bf16 rounding, by 2e-7 in a loss; a stale table or a missed per-step scalar shows up at 6e-5 in the gradient norm and
-    6e-6 in the parameters).  The lr schedule, Adam bias correction,
-    EMA decay and the noise stream must advance on replay.  Two graph runs in one process: host staging buffers of tables
-    uploaded during capture must outlive the capture."""
+def _run_six_steps(graph, data):
     from uwudiff_b200 import ops
 
+    tr = _tiny_trainer()
+    tr.setup_fit(gradient_clip_val=1.0, seed=1215, cuda_graph=graph, graph_warmup_steps=2)
+    losses, ts, norms = [], [], []
+    n0 = ops.launch_count()
+    for i, b in enumerate(data):
+        out = tr.fit_step(b, i)
+        losses.append(out["loss"].item())
+        norms.append(float(tr._fit["opt"].last_norm[0]))
+        ts.append(out["aux_output"].timesteps.clone())
+    return dict(losses=losses, ts=ts, norms=norms, params=tr.lycoris_model.flat_params.clone(), ema=float(tr.ema_loss),
+                lr=tr._fit["opt"].param_groups[0]["lr"], launches=ops.launch_count() - n0, state=tr._fit["graph"])
+
+
+def _worst(e, g):
+    rel = lambda xs, ys: max(abs(a - b) / abs(a) for a, b in zip(xs, ys))  # noqa: E731
+    return rel(e["losses"], g["losses"]), rel(e["norms"], g["norms"]), (e["params"] - g["params"]).abs().max().item()
+
+
+def test_cuda_graph_step_reproduces_the_eager_step():
+    """`setup_fit(cuda_graph=True)`: after two eager optimizer steps the step is captured (forward + backward, clip + AdamW)
+    and replayed.  Same seeds, same batches, same kernels in the same order: timesteps are bit-equal; the lr schedule, Adam bias
+    correction, EMA decay and the noise stream must advance on replay; two graph runs in one process (host staging buffers of
+    tables uploaded during capture must outlive the capture).
+
+    Losses, gradient norms and parameters: in 15 of 16 processes every run — eager or graph — is BIT-identical
+    (tools/dbg/graph_noise.py: 96 runs).  In the remaining processes the fp32 atomics of the split-K / dQ reductions land in
+    another order during the first steps, a 1e-8 parameter difference flips a bf16 rounding and the trajectories drift apart
+    by up to 3e-4 in a gradient norm (eager AND graph runs drift, in different directions, from the values every other
+    process reproduces).  A stale table or a missed per-step scalar (the bugs this test found) is deterministic: 6e-5 in the
+    gradient norm, 6e-6 in the parameters, every time.  Hence: tight bounds must hold in one of two attempts, loose bounds
+    (the drift of the noise) always."""
     data = _batches(6)
-    runs = []
-    for graph in (False, True, True):
-        tr = _tiny_trainer()
-        tr.setup_fit(gradient_clip_val=1.0, seed=1215, cuda_graph=graph, graph_warmup_steps=2)
-        losses, ts, norms = [], [], []
-        n0 = ops.launch_count()
-        for i, b in enumerate(data):
-            out = tr.fit_step(b, i)
-            losses.append(out["loss"].item())
-            norms.append(float(tr._fit["opt"].last_norm[0]))
-            ts.append(out["aux_output"].timesteps.clone())
-        runs.append(dict(losses=losses, ts=ts, norms=norms, params=tr.lycoris_model.flat_params.clone(), ema=float(tr.ema_loss),
-                         lr=tr._fit["opt"].param_groups[0]["lr"], launches=ops.launch_count() - n0, state=tr._fit["graph"]))
-    e = runs[0]
-    for g in runs[1:]:
-        assert g["state"]["state"] == "replay" and g["state"]["n_fwdbwd"] > 300
-        assert all(torch.equal(a, b) for a, b in zip(e["ts"], g["ts"])), "the noise / timestep stream must advance on replay"
-        assert len({tuple(t.tolist()) for t in g["ts"]}) > 1
-        for a, b in zip(e["losses"], g["losses"]):
-            assert abs(a - b) <= 2e-6 * abs(a), (e["losses"], g["losses"])  # 1 in 14 runs sees 2e-7: a bf16 rounding flip
-        for a, b in zip(e["norms"], g["norms"]):
-            assert abs(a - b) <= 2e-5 * abs(a), (e["norms"], g["norms"])
-        assert (e["params"] - g["params"]).abs().max().item() <= 1e-6
-        assert abs(e["ema"] - g["ema"]) <= 1e-6 * abs(e["ema"]) and e["lr"] == g["lr"]
-        assert abs(e["launches"] - g["launches"]) <= 8, (e["launches"], g["launches"])  # replayed launches are counted
+    tight = None
+    for attempt in range(2):
+        e = _run_six_steps(False, data)
+        gs = [_run_six_steps(True, data), _run_six_steps(True, data)]
+        for g in gs:
+            assert g["state"]["state"] == "replay" and g["state"]["n_fwdbwd"] > 300
+            assert all(torch.equal(a, b) for a, b in zip(e["ts"], g["ts"])), "the noise / timestep stream must advance on replay"
+            assert len({tuple(t.tolist()) for t in g["ts"]}) > 1
+            dl, dn, dp = _worst(e, g)
+            assert dl <= 5e-5 and dn <= 3e-3 and dp <= 1e-4, (dl, dn, dp)
+            assert abs(e["ema"] - g["ema"]) <= 1e-4 * abs(e["ema"]) and e["lr"] == g["lr"]
+            assert abs(e["launches"] - g["launches"]) <= 8, (e["launches"], g["launches"])  # replayed launches are counted
+        tight = all(dl <= 2e-6 and dn <= 2e-5 and dp <= 1e-6 for dl, dn, dp in (_worst(e, g) for g in gs))
+        if tight:
+            break
+    assert tight, "graph replay differs from the eager step beyond the atomic-order noise in two attempts out of two"
 
 
 def test_gradient_accumulation_on_the_gpu_matches_one_large_batch_of_gradients():

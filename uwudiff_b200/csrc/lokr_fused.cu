@@ -50,6 +50,7 @@ struct LokrFusedArgs {
 };
 
 __global__ void __launch_bounds__(LF_THREADS, 1) lokr_fused_kernel(const __grid_constant__ LokrFusedArgs p) {
+    pdl_trigger();  // dependents may be scheduled as this grid's CTAs retire; they wait for its completion before touching memory
     extern __shared__ uint8_t lf_raw[];
     // two rings with their own barriers: an Xs tile is released as soon as products (1) and (2) have read it, one tile-period
     // before its dYs tile
@@ -281,7 +282,6 @@ __global__ void __launch_bounds__(LF_THREADS, 1) lokr_fused_kernel(const __grid_
             }
         }
     }
-    pdl_trigger();
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {
